@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/sec of the streaming particle-filter step on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (this build)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU port of the reference path)
+
+A "step" is one pass of the hot path (resample + gather + propagate + weight + normalise,
+zparticles', haskell/src/Inference.hs:101-104) over all N_p particles.  Workload at 1 GPU:
+BASELINE.json configs[1], the 1-D Gaussian random-walk model at N_p = 10^8 on one B200.
+
+value : N_p * K / (device time of K back-to-back steps), observations resident in HBM.
+e2e   : the same through the public API with HOST observation buffers, one ZStream.step
+        per observation (pinned H2D of the observation + D2H of the posterior summary + sync
+        inside the timed region).
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+
+The CPU oracle (oracle/) is executed only by the cpu_baseline leg and by --impl reference.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MODELS = {"rw1d": (1, 1), "lg42": (4, 2), "lg63": (6, 3)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def model_desc(pz, name):
+    return {"rw1d": pz.rw1d, "lg42": pz.mtt_track, "lg63": pz.stt}[name]()
+
+
+def helper_desc(H, name):
+    return {"rw1d": H.model_rw1d, "lg42": H.model_mtt_track, "lg63": H.model_stt}[name]()
+
+
+def cpu_port_rate(H, name, n_sample, steps, threads, faithful=False):
+    """particle-updates/s of the CPU port.  faithful=False: the reference's algorithm (double,
+    log-domain normalise, multinomial draws) with the O(N) per-draw CDF walk replaced by a binary
+    search (identical ancestors) and OpenMP over particles; faithful=True: the literal O(N^2) walk,
+    one thread."""
+    lib = H.oracle()
+    d = helper_desc(H, name)
+    obs, _ = H.gen_obs(d, steps)
+    t0 = time.perf_counter()
+    rc = lib.pzo_refpf_run(C.byref(d), n_sample, 1, H.ptr(obs, C.c_double), steps, 0 if faithful else 1, None, None,
+                           1 if faithful else threads)
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return n_sample * steps / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import pzhelpers as H
+    threads = os.cpu_count() or 1
+    n_sample = min(args.particles, args.cpu_particles)
+    K, W = args.steps, args.warmup
+    cpu_port_rate(H, args.model, n_sample, max(1, min(W, 2)), threads)  # warm-up
+    rate, dt = cpu_port_rate(H, args.model, n_sample, K, threads)
+    nx, _ = MODELS[args.model]
+    line = {
+        "impl": "reference", "metric": "particle-updates/sec", "value": rate, "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.model} bootstrap particle filter, N={args.particles} per GPU (configs[1])",
+                   "model": args.model, "particles_per_gpu": args.particles, "state_dim": nx},
+        "cpu_baseline": {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": "port",
+                         "sample": f"N={n_sample} particles x {K} steps of the same model; reference algorithm "
+                                   "(Inference.hs:57-66,101-104: double, logaddexp normalise, multinomial resample2) "
+                                   "with the O(N) per-draw CDF walk replaced by a binary search and OpenMP over particles; "
+                                   "the literal O(N^2) reference cannot finish one step at this N"},
+        "e2e": {"value": rate, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    import pzhelpers as H
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pz = g.load_package()
+    name = args.model
+    nx, ny = MODELS[name]
+    n_p = args.particles
+    K, W = args.steps, args.warmup
+    d = model_desc(pz, name)
+    hd = helper_desc(H, name)
+    obs, _ = H.gen_obs(hd, W + K + 2 * K + 8)
+    if world > 1:
+        zs = pz.zparticles_sharded(n_p * world, d, seed=1, device=local_rank, rank=rank, world=world)
+    else:
+        zs = pz.zparticles(n_p, d, seed=1, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K back-to-back steps, observations staged in HBM
+    zs.run(obs[:W], want_summaries=False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    zs.run(obs[W:W + K], want_summaries=False)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms, launches = zs.last_timing()
+    clocks = sampler.summary() if sampler else None
+    if world > 1:
+        tt = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms = float(tt.item())
+    value = n_p * world * K / (dev_ms * 1e-3)
+
+    # ---- end to end: host observation -> ZStream.step -> posterior summary on the host
+    off = W + K
+    for i in range(min(W, 3)):
+        zs.step(obs[off + i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        post = zs.step(obs[off + 3 + i])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = n_p * world * K / e2e_s
+
+    # ---- roofline of the dominant kernel (fused resample+propagate+weight), CUDA events on its stream
+    prof = np.array([zs.step_profile(obs[off + 3 + K + i]) for i in range(min(K, 10))])
+    t_tile_ms = float(np.mean(prof[:, 0]))
+    alg_bytes = 2.0 * nx * 4 * n_p  # read the state once, write it once
+    achieved = alg_bytes / (t_tile_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    if rank != 0:
+        return
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    threads = os.cpu_count() or 1
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        n_sample = min(n_p, args.cpu_particles)
+        steps_cpu = 5
+        rate, dt = cpu_port_rate(H, name, n_sample, steps_cpu, threads)
+        frate, fdt = cpu_port_rate(H, name, 1000, 100, 1, faithful=True)
+        cpu = {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": "port",
+               "sample": f"N={n_sample} x {steps_cpu} steps, reference algorithm in double with binary-search multinomial + OpenMP ({dt:.1f} s)",
+               "faithful_o_n2": {"value": frate, "cores": 1,
+                                 "sample": f"configs[0]: N=1000 x 100 steps, literal O(N^2) resample2 ({fdt:.1f} s)"}}
+    line = {
+        "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name} bootstrap particle filter, N={n_p} particles per GPU (BASELINE.json configs[1])",
+                   "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp32",
+                   "weights": "u64 fixed point", "resampler": "systematic (canonical PZ-SYS-256)",
+                   "l2": "inputs exceed L2 (state %.0f MB per buffer)" % (nx * 4 * n_p / 1e6), "wall_s_timed": wall},
+        "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 136,
+                "ms_per_step": e2e_s / K * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "pf_step_tile", "peak_source": peak_src,
+                     "alg_bytes_per_launch": alg_bytes, "kernel_ms": t_tile_ms,
+                     "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
+                                         "pf_partition": float(np.mean(prof[:, 2]))}},
+        "cpu_baseline": cpu,
+        "posterior_check": {"step": int(post.step), "mean0": float(post.mean[0]), "ess": float(post.ess)},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="rw1d", choices=list(MODELS))
+    ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU")
+    ap.add_argument("--cpu-particles", type=int, default=2_000_000, help="bounded CPU sample size")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

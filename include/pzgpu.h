@@ -1,0 +1,176 @@
+/* pzgpu.h -- C ABI of the B200 streaming particle-filter step.
+ *
+ * This is the drop-in boundary for the one hot path of psg-mit/probzelus-haskell that
+ * this repository accelerates: the per-time-step particle filter behind
+ *
+ *     zparticles   :: Int -> ZStream (Weighted m) a b -> ZStream m a [b]    (haskell/src/Inference.hs:107-108)
+ *     zdsparticles :: Int -> ZStream (StateT Heap (Weighted m)) a b -> ...  (haskell/src/Inference.hs:113-114)
+ *
+ * The reference passes the model as a Haskell closure, which cannot cross to a GPU; here
+ * the model is a plain-old-data descriptor (pz_model_desc) for the supported state-space
+ * families.  A Haskell host binds these symbols with `foreign import ccall` (the stub is
+ * in INTEGRATION.md and haskell/PzGpu.hs); no torch / C++ types appear in any signature.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PZ_E* code; nothing throws;
+ *   - pz_last_error() returns a thread-local message for the last failing call;
+ *   - the caller owns all host buffers; the library owns device memory, streams, NCCL;
+ *   - a pz_filter handle is NOT thread-safe (the reference is single-threaded,
+ *     haskell/package.yaml:49-52); calls on one handle must be serialised.
+ */
+#ifndef PZGPU_H
+#define PZGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PZ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PZ_API __attribute__((visibility("default")))
+#else
+#define PZ_API
+#endif
+
+#define PZ_MAX_NX 6 /* state scalars per particle for the linear-Gaussian family */
+#define PZ_MAX_NY 3 /* observation scalars                                        */
+
+/* error codes */
+#define PZ_OK 0
+#define PZ_EINVAL (-1)      /* bad argument / unsupported descriptor           */
+#define PZ_ECUDA (-2)       /* CUDA runtime failure                            */
+#define PZ_ENCCL (-3)       /* NCCL failure / NCCL not loadable                */
+#define PZ_EDEGENERATE (-4) /* all weights zero or NaN: nothing to resample    */
+#define PZ_ECAPACITY (-5)   /* fixed capacity exceeded (tracks, observations, migration halo) */
+#define PZ_ENOMEM (-6)
+#define PZ_ESTATE (-7)      /* call not valid in the current filter state      */
+
+/* Model families (a17, a18, a19). */
+enum {
+  PZ_MODEL_RW1D = 1,     /* Examples/Demo.hs:184-201 (kalman1D*), Inference.hs:143-147 (rw)         */
+  PZ_MODEL_LINGAUSS = 2, /* Examples/SingleTargetTracking.hs:28-54; per-track model of MTT :56-73    */
+  PZ_MODEL_MTT = 3       /* Examples/MultiTargetTracking.hs:26-145                                   */
+};
+
+enum {
+  PZ_RESAMPLE_SYSTEMATIC = 0,     /* canonical fixed-point systematic resampler        */
+  PZ_RESAMPLE_MULTINOMIAL_REF = 1 /* N iid categorical draws: resample2, Inference.hs:57-61        */
+};
+
+/* Multi-target tracker constants, Examples/MultiTargetTracking.hs:36-73. */
+typedef struct pz_mtt_params {
+  double clutter_lambda;   /* clutterLambda = 3                                   */
+  double new_track_lambda; /* newTrackLambda = birthRate * tdiff = 0.1            */
+  double pd;               /* detection probability 0.8                           */
+  double survival_prob;    /* exp(-tdiff*deathRate)                               */
+  double clutter_var;      /* clutter ~ N(0, clutter_var * I2), 10                */
+  double birth_pos_var;    /* birth prior diag(5,5,0.1,0.1)                       */
+  double birth_vel_var;
+  double meas_var;         /* R = meas_var * I2, 1                                */
+  int32_t k_max;           /* fixed per-particle track capacity (<= 16)           */
+  int32_t m_max;           /* max observations per step (<= 32)                   */
+} pz_mtt_params;
+
+/* Kernel-side model descriptor.  Matrices are row-major, leading dimension = the
+ * logical column count (nx for F/Q/P0, nx for H, ny for R).                                 */
+typedef struct pz_model_desc {
+  int32_t kind;         /* PZ_MODEL_*                                                        */
+  int32_t nx;           /* state dim: 1 (RW1D), 4 (MTT track model), 6 (STT), <= PZ_MAX_NX   */
+  int32_t ny;           /* observation dim <= PZ_MAX_NY                                      */
+  int32_t scalar_ll_2x; /* 1 = reference's doubled scalar Gaussian score,
+                           Distributions.hs:160-161 (only honoured when ny == 1)             */
+  int32_t resampler;    /* PZ_RESAMPLE_*                                                     */
+  int32_t reserved[3];
+  double F[PZ_MAX_NX * PZ_MAX_NX];  /* x' ~ N(F x, Q)                                        */
+  double Q[PZ_MAX_NX * PZ_MAX_NX];
+  double H[PZ_MAX_NY * PZ_MAX_NX];  /* y  ~ N(H x', R)                                       */
+  double R[PZ_MAX_NY * PZ_MAX_NY];
+  double x0[PZ_MAX_NX];             /* initial state (the reference starts at a point mass)  */
+  pz_mtt_params mtt;
+} pz_model_desc;
+
+/* Posterior summary of one step: the weighted particle approximation of
+ * p(x_t | y_1..t).  The reference prints `average particles` after resampling
+ * (Examples/Demo.hs:207); `mean` is the Rao-Blackwellised version of that estimator
+ * (weighted, before resampling: same expectation, lower variance).                          */
+typedef struct pz_step_summary {
+  int64_t step;             /* 0-based index of the observation just assimilated             */
+  double log_evidence_inc;  /* log p^(y_t | y_1..t-1) = log( (1/N) sum_i w_i )                */
+  double ess;               /* (sum w)^2 / sum w^2                                           */
+  double mean[PZ_MAX_NX];
+  double var[PZ_MAX_NX];
+  int64_t n_migrated;       /* particles fetched from other ranks this step (sharded only)   */
+  int32_t e_max;            /* canonical resampler diagnostics: global block exponent        */
+  int32_t reserved;
+  uint64_t total_weight;    /* canonical fixed-point total T                                 */
+} pz_step_summary;
+
+typedef struct pz_filter pz_filter;
+
+/* Fill a descriptor with the reference's constants. */
+PZ_API int pz_model_rw1d(pz_model_desc* d, double q_var, double r_var);       /* Demo.hs:184-192: (1, 3)  */
+PZ_API int pz_model_stt(pz_model_desc* d);                                    /* SingleTargetTracking.hs:39-54 */
+PZ_API int pz_model_mtt_track(pz_model_desc* d);                              /* MultiTargetTracking.hs:56-73  */
+PZ_API int pz_model_mtt(pz_model_desc* d);                                    /* MultiTargetTracking.hs:36-145 */
+
+/* zparticles / zdsparticles: a filter over n_particles copies of the model on one device. */
+PZ_API int pz_filter_create(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int device,
+                     pz_filter** out);
+
+/* One rank of a filter whose n_global particles are sharded over `world` GPUs (one process
+ * per GPU).  nccl_unique_id is the 128-byte ncclUniqueId produced by pz_comm_unique_id() on
+ * rank 0 and distributed by the host.                                                        */
+PZ_API int pz_comm_unique_id(void* out128);
+PZ_API int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_global, uint64_t seed,
+                             int device, int rank, int world, const void* nccl_unique_id,
+                             pz_filter** out);
+
+/* ZStream.step (Util/ZStream.hs:16): assimilate one observation, return the posterior.
+ * obs is n_obs rows of obs_dim doubles (n_obs == 1 except for MTT).  Blocks until the
+ * summary is on the host.                                                                    */
+PZ_API int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim,
+                   pz_step_summary* out);
+
+/* ZS.runStream (Util/ZStream.hs:65-69) over a whole observation stream: n_steps rows of
+ * obs_dim doubles are staged on the device once, the steps run back to back, and the
+ * summaries (may be NULL) are copied back at the end.                                        */
+PZ_API int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_dim,
+                  pz_step_summary* out);
+
+/* Device time (ms, CUDA events on the filter's stream) of the kernels enqueued by the last
+ * pz_filter_step / pz_filter_run call, and the number of kernel launches it made.           */
+PZ_API int pz_filter_last_timing(pz_filter* f, double* ms, int64_t* launches);
+
+/* Diagnostics: run ONE step outside the CUDA graph with an event between its kernels;
+ * ms[0] = fused resample+propagate+weight kernel, ms[1] = block-sum scan, ms[2] = partition. */
+PZ_API int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim,
+                                  double ms[3]);
+
+/* The stream's output `[b]`: equally weighted particles AFTER resampling (what the Java
+ * visualiser draws).  Returns every `stride`-th output slot, all state dims, slot-major:
+ * out[(j/stride)*nx + d].                                                                    */
+PZ_API int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t out_len);
+
+/* Parity / debug taps. */
+PZ_API int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n);      /* ancestors of the pending resample */
+PZ_API int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len);       /* pre-resample population, SoA [nx][N] */
+PZ_API int pz_filter_read_logw(pz_filter* f, float* out, int64_t n);              /* log-weights of that population */
+PZ_API int64_t pz_filter_n_local(const pz_filter* f);
+
+/* Standalone canonical systematic resampler on stored log-weights (bit-exact tests):
+ * lw32_i = (float)logw[i], U = floor(u * 2^32).                                              */
+PZ_API int pz_resample_systematic(const double* logw, int64_t n, double u, int32_t* anc_out);
+PZ_API int pz_resample_multinomial(const double* logw, int64_t n, uint64_t seed, uint32_t step,
+                            int32_t* anc_out);
+
+PZ_API void pz_filter_destroy(pz_filter* f);
+PZ_API const char* pz_last_error(void);
+PZ_API int pz_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PZGPU_H */

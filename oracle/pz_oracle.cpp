@@ -1,0 +1,785 @@
+// pz_oracle.cpp -- CPU oracle for the streaming particle-filter step.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under probzelus-haskell_b200/ may include, link or
+// call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs use it, as the checker (never as the thing shipped).
+//
+// PARITY UNPINNED: the reference (psg-mit/probzelus-haskell) has no tests, golden vectors
+// or seeded outputs, and no GHC toolchain exists in this image, so
+// this restatement cannot be pinned against outputs of the Haskell binary.  It is pinned
+// instead against (i) the Random123 known-answer vectors for Philox4x32-10, (ii) the
+// exact Kalman filter written from the reference's own algebra (MVDistributions.hs:75-100,
+// DelayedSampling.hs:88-95), and (iii) libm for the math primitives.
+//
+// What is restated, with the reference lines each part follows:
+//   pzo_refpf_*      zparticles' + resample2 + normalize + labeledLogCategorical,
+//                    Inference.hs:57-66,101-108, in double, multinomial, O(N^2): the
+//                    reference-faithful filter (CPU-ref row of BASELINE.md section 4).
+//   pzo_filter_*     the SAME filter step with the build's canonical fixed-point
+//                    systematic resampler and fp32 state: the bit-exact twin of the CUDA
+//                    path (every rounding below is part of the spec in DESIGN.md).
+//   pzo_kalman_*     kalmanPredict / kalmanUpdate, MVDistributions.hs:75-100.
+//   model step       noisyIntegrateGen + observe (normal x 3), Demo.hs:184-198;
+//                    SingleTargetTracking.hs:33-36; MultiTargetTracking.hs:56-73.
+//   scores           gaussian_ll' (doubled!) Distributions.hs:160-161; mvNormal_ll0
+//                    MVDistributions.hs:45-46.
+//
+// Build: make -C oracle   (g++ -O2 -mfma -ffp-contract=off; FMAs appear only where the
+// spec says fmaf).
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "../include/pzgpu.h"
+
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11; Random123 philox.h).  Replaces the reference's
+// MWC256 SamplerIO.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+
+// counter word 3 selects the stream
+constexpr uint32_t kStreamProp = 0x50524F50u;      // "PROP": propagation noise, ctr=(group, call, step, .)
+constexpr uint32_t kStreamResample = 0x52455341u;  // "RESA": the one uniform of a systematic resample
+constexpr uint32_t kStreamMulti = 0x4D554C54u;     // "MULT": per-slot uniforms of a multinomial resample
+constexpr uint32_t kStreamObs = 0x4F425347u;       // "OBSG": synthetic observation generator
+
+inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)kPhiloxM0 * c[0];
+    uint64_t p1 = (uint64_t)kPhiloxM1 * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += kPhiloxW0; k1 += kPhiloxW1;
+  }
+}
+
+inline void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t out[4]) {
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  philox4x32_10(out, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// ---------------------------------------------------------------------------------------
+// Canonical fp32 math (DESIGN.md "Math").  Every operation is an individually rounded
+// IEEE fp32 op; fused multiply-adds appear exactly where fmaf is written.
+// ---------------------------------------------------------------------------------------
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+constexpr float kLog2e = 0x1.715476p+0f;
+constexpr float kNeg2Ln2 = -0x1.62e430p+0f;
+constexpr float kHalfPi = 0x1.921fb6p+0f;
+constexpr float kExp2C[7] = {0x1.62e430p-1f, 0x1.ebfbe0p-3f, 0x1.c6b08ep-5f, 0x1.3b2a1cp-7f,
+                             0x1.5d8776p-10f, 0x1.444004p-13f, 0x1.00c0e6p-16f};
+constexpr float kLogC[8] = {0x1.555552p-2f, -0x1.0000c8p-2f, 0x1.99a14cp-3f, -0x1.54d54ep-3f,
+                            0x1.22dc4cp-3f, -0x1.09abe4p-3f, 0x1.04591ap-3f, -0x1.4bd700p-4f};
+constexpr float kSinC[3] = {-0x1.555552p-3f, 0x1.110c2ap-7f, -0x1.9aca02p-13f};
+constexpr float kCosC[3] = {0x1.555554p-5f, -0x1.6c12d4p-10f, 0x1.9bd8d2p-16f};
+
+constexpr int32_t kNZero = INT32_MIN;  // exponent marker of a zero weight
+
+// log-weight -> (n, m): weight = m * 2^(n-23), m in [2^22.5, 2^23.5].  Zero weight: m = 0.
+inline void weight_split(float lw, int32_t* n, uint32_t* m) {
+  *n = kNZero; *m = 0;
+  if (!(lw > -INFINITY) || !(lw < INFINITY)) return;  // -inf, +inf, NaN -> zero weight
+  float e = lw * kLog2e;
+  if (!(e > -1.0e6f) || !(e < 1.0e6f)) return;
+  float r = rintf(e);
+  float f = e - r;
+  float p = kExp2C[6];
+  for (int i = 5; i >= 0; --i) p = fmaf(p, f, kExp2C[i]);
+  p = fmaf(p, f, 1.0f);
+  *n = (int32_t)r;
+  *m = (uint32_t)(int32_t)rintf(p * 8388608.0f);
+}
+
+// two 32-bit words -> two independent N(0,1) draws (Box-Muller on the canonical math)
+inline void normal_pair(uint32_t ra, uint32_t rb, float* z0, float* z1) {
+  float u = fmaf((float)ra, 0x1p-32f, 0x1p-33f);  // (0, 1]
+  uint32_t bits = f2u(u);
+  int32_t e = (int32_t)(bits - 0x3F3504F3u) >> 23;
+  float mant = u2f(bits - ((uint32_t)e << 23));  // [sqrt(.5), sqrt(2))
+  float t = mant - 1.0f;
+  float t2 = t * t;
+  float P = kLogC[7];
+  for (int i = 6; i >= 0; --i) P = fmaf(P, t, kLogC[i]);
+  float lnm = fmaf(t2 * t, P, fmaf(-0.5f, t2, t));
+  float rad2 = fmaf((float)e, kNeg2Ln2, -2.0f * lnm);
+  rad2 = fmaxf(rad2, 0.0f);
+  float R = sqrtf(rad2);
+  uint32_t q = rb >> 30;
+  float fr = fmaf((float)(rb & 0x3FFFFFFFu), 0x1p-30f, -0.5f);
+  float phi = fr * kHalfPi;
+  float z = phi * phi;
+  float S = fmaf(fmaf(kSinC[2], z, kSinC[1]), z, kSinC[0]);
+  float C = fmaf(fmaf(kCosC[2], z, kCosC[1]), z, kCosC[0]);
+  float s = fmaf(phi * z, S, phi);
+  float c = fmaf(z * z, C, fmaf(-0.5f, z, 1.0f));
+  float cq, sq;
+  switch (q) {
+    case 0: cq = c; sq = s; break;
+    case 1: cq = -s; sq = c; break;
+    case 2: cq = -c; sq = -s; break;
+    default: cq = s; sq = -c; break;
+  }
+  *z0 = R * cq;
+  *z1 = R * sq;
+}
+
+// ---------------------------------------------------------------------------------------
+// Linear-Gaussian model family: derived fp32 parameters.
+// ---------------------------------------------------------------------------------------
+struct LgParams {
+  int nx = 0, ny = 0;
+  float F[PZ_MAX_NX][PZ_MAX_NX];
+  float Lq[PZ_MAX_NX][PZ_MAX_NX];  // lower Cholesky factor of Q (sampleNormalDist uses hmatrix's
+                                   // UPPER factor, MVDistributions.hs:40; identical for the diagonal
+                                   // Q of every in-scope model)
+  float H[PZ_MAX_NY][PZ_MAX_NX];
+  float Rinv[PZ_MAX_NY][PZ_MAX_NY];
+  float x0[PZ_MAX_NX];
+  float wscale;     // -0.5 (mvNormal_ll0) or -1.0 (doubled scalar score, Distributions.hs:160-161)
+  double ll_const;  // additive constant of the score dropped from the per-particle weight
+};
+
+bool derive_lg(const pz_model_desc* d, LgParams* p) {
+  int nx = d->nx, ny = d->ny;
+  if (nx < 1 || nx > PZ_MAX_NX || ny < 1 || ny > PZ_MAX_NY) return false;
+  *p = LgParams();
+  p->nx = nx; p->ny = ny;
+  double L[PZ_MAX_NX][PZ_MAX_NX] = {};
+  for (int j = 0; j < nx; ++j) {
+    double s = d->Q[j * nx + j];
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    double ljj = s > 0 ? sqrt(s) : 0.0;
+    L[j][j] = ljj;
+    for (int i = j + 1; i < nx; ++i) {
+      double t = d->Q[i * nx + j];
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = ljj > 0 ? t / ljj : 0.0;
+    }
+  }
+  // R^-1 and log det R by Gauss-Jordan without pivoting (R is SPD)
+  double A[PZ_MAX_NY][2 * PZ_MAX_NY] = {};
+  for (int i = 0; i < ny; ++i) {
+    for (int j = 0; j < ny; ++j) A[i][j] = d->R[i * ny + j];
+    A[i][ny + i] = 1.0;
+  }
+  double logdet = 0;
+  for (int c = 0; c < ny; ++c) {
+    double piv = A[c][c];
+    if (!(piv > 0)) return false;
+    logdet += log(piv);
+    for (int j = 0; j < 2 * ny; ++j) A[c][j] /= piv;
+    for (int r = 0; r < ny; ++r) {
+      if (r == c) continue;
+      double f = A[r][c];
+      for (int j = 0; j < 2 * ny; ++j) A[r][j] -= f * A[c][j];
+    }
+  }
+  for (int i = 0; i < nx; ++i) {
+    for (int j = 0; j < nx; ++j) { p->F[i][j] = (float)d->F[i * nx + j]; p->Lq[i][j] = (float)L[i][j]; }
+    p->x0[i] = (float)d->x0[i];
+  }
+  for (int i = 0; i < ny; ++i) {
+    for (int j = 0; j < nx; ++j) p->H[i][j] = (float)d->H[i * nx + j];
+    for (int j = 0; j < ny; ++j) p->Rinv[i][j] = (float)A[i][ny + j];
+  }
+  bool dbl = (ny == 1 && d->scalar_ll_2x);
+  p->wscale = dbl ? -1.0f : -0.5f;
+  p->ll_const = (dbl ? -1.0 : -0.5) * (logdet + ny * log(2 * M_PI));
+  return true;
+}
+
+inline void lg_propagate(const LgParams& p, const float* x, const float* z, float* xn) {
+  for (int r = 0; r < p.nx; ++r) {
+    float acc = p.F[r][0] * x[0];
+    for (int c = 1; c < p.nx; ++c) acc = fmaf(p.F[r][c], x[c], acc);
+    for (int c = 0; c <= r; ++c) acc = fmaf(p.Lq[r][c], z[c], acc);
+    xn[r] = acc;
+  }
+}
+
+inline float lg_logweight(const LgParams& p, const float* xn, const float* y) {
+  float d[PZ_MAX_NY];
+  for (int k = 0; k < p.ny; ++k) {
+    float acc = p.H[k][0] * xn[0];
+    for (int c = 1; c < p.nx; ++c) acc = fmaf(p.H[k][c], xn[c], acc);
+    d[k] = y[k] - acc;
+  }
+  float quad = 0.0f;
+  for (int k = 0; k < p.ny; ++k) {
+    float t = p.Rinv[k][0] * d[0];
+    for (int l = 1; l < p.ny; ++l) t = fmaf(p.Rinv[k][l], d[l], t);
+    quad = (k == 0) ? d[0] * t : fmaf(d[k], t, quad);
+  }
+  return p.wscale * quad;
+}
+
+// normals for output slot j at step t (counter keyed on the GLOBAL slot, never on a thread id)
+inline void lg_noise(int nx, uint64_t j, uint32_t t, uint64_t seed, float* z) {
+  uint32_t r[4];
+  if (nx == 1) {
+    philox((uint32_t)(j >> 2), 0, t, kStreamProp, seed, r);
+    int l = (int)(j & 3);
+    float z0, z1;
+    normal_pair(r[2 * (l >> 1)], r[2 * (l >> 1) + 1], &z0, &z1);
+    z[0] = (l & 1) ? z1 : z0;
+    return;
+  }
+  for (int k = 0; 4 * k < nx; ++k) {
+    philox((uint32_t)j, (uint32_t)k, t, kStreamProp, seed, r);
+    float zz[4];
+    normal_pair(r[0], r[1], &zz[0], &zz[1]);
+    normal_pair(r[2], r[3], &zz[2], &zz[3]);
+    for (int i = 0; i < 4 && 4 * k + i < nx; ++i) z[4 * k + i] = zz[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Canonical fixed-point systematic resampler "PZ-SYS-256" (DESIGN.md "Resampler").
+// ---------------------------------------------------------------------------------------
+constexpr int kBlk = 256;
+
+struct ResamplePlan {
+  int64_t n = 0, nblk = 0;
+  std::vector<int32_t> nexp;   // per particle exponent
+  std::vector<uint32_t> mant;  // per particle mantissa
+  std::vector<int32_t> eb;     // per block exponent
+  std::vector<uint64_t> sb;    // per block sum at block scale
+  std::vector<uint64_t> pb;    // per block exclusive prefix at global scale (nblk+1 entries)
+  int32_t emax = kNZero;
+  uint64_t total = 0;
+  uint32_t rho = 0;
+  int shift = 0;
+};
+
+inline int bitlen64(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
+inline int bitlen128(u128 v) {
+  uint64_t hi = (uint64_t)(v >> 64);
+  return hi ? 64 + bitlen64(hi) : bitlen64((uint64_t)v);
+}
+
+inline uint32_t q_at(uint32_t m, int32_t n, int32_t eb) {
+  if (m == 0) return 0;
+  int64_t sh = (int64_t)eb - (int64_t)n;
+  return sh < 32 ? (uint32_t)((m << 8) >> sh) : 0u;
+}
+
+// returns false when every weight is zero (degenerate)
+bool build_plan(const float* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
+  pl->n = n;
+  pl->nblk = (n + kBlk - 1) / kBlk;
+  pl->nexp.resize(n); pl->mant.resize(n);
+  pl->eb.assign(pl->nblk, kNZero); pl->sb.assign(pl->nblk, 0); pl->pb.assign(pl->nblk + 1, 0);
+  for (int64_t i = 0; i < n; ++i) weight_split(lw[i], &pl->nexp[i], &pl->mant[i]);
+  pl->emax = kNZero;
+  for (int64_t b = 0; b < pl->nblk; ++b) {
+    int32_t e = kNZero;
+    int64_t hi = std::min(n, (b + 1) * kBlk);
+    for (int64_t i = b * kBlk; i < hi; ++i) if (pl->mant[i]) e = std::max(e, pl->nexp[i]);
+    uint64_t s = 0;
+    for (int64_t i = b * kBlk; i < hi; ++i) s += q_at(pl->mant[i], pl->nexp[i], e);
+    pl->eb[b] = e; pl->sb[b] = s;
+    pl->emax = std::max(pl->emax, e);
+  }
+  if (pl->emax == kNZero) return false;
+  uint64_t run = 0;
+  for (int64_t b = 0; b < pl->nblk; ++b) {
+    pl->pb[b] = run;
+    int64_t k = (int64_t)pl->emax - (int64_t)pl->eb[b];
+    run += (pl->eb[b] == kNZero || k >= 64) ? 0 : (pl->sb[b] >> k);
+  }
+  pl->pb[pl->nblk] = run;
+  pl->total = run;
+  if (run == 0) return false;
+  int L = bitlen64(run);
+  u128 rho = (((u128)(uint64_t)n_out) << (32 + L)) / run + 1;
+  int a = std::max(0, bitlen128(rho) - 31);
+  pl->rho = (uint32_t)(rho >> a) + 1;
+  pl->shift = L - a;
+  return true;
+}
+
+inline uint64_t pos_of(const ResamplePlan& pl, uint64_t C) {
+  u128 prod = (u128)C * pl.rho;
+  return (uint64_t)(pl.shift >= 0 ? (prod >> pl.shift) : (prod << (-pl.shift)));
+}
+
+inline int64_t slot_end(const ResamplePlan& pl, uint64_t C, uint32_t U, int64_t n_out) {
+  uint64_t pos = pos_of(pl, C);
+  if (pos <= U) return 0;
+  uint64_t o = (pos - U + 0xFFFFFFFFull) >> 32;
+  return (int64_t)std::min<uint64_t>(o, (uint64_t)n_out);
+}
+
+// ancestors of output slots [0, n_out); parent indices refer to [0, n)
+void systematic_ancestors(const ResamplePlan& pl, uint32_t U, int64_t n_out, int32_t* anc) {
+  int64_t prev = 0;
+  for (int64_t b = 0; b < pl.nblk; ++b) {
+    if (pl.eb[b] == kNZero) continue;
+    int64_t k = (int64_t)pl.emax - (int64_t)pl.eb[b];
+    uint64_t c = 0;
+    int64_t hi = std::min(pl.n, (b + 1) * kBlk);
+    for (int64_t i = b * kBlk; i < hi; ++i) {
+      c += q_at(pl.mant[i], pl.nexp[i], pl.eb[b]);
+      uint64_t C = pl.pb[b] + (k >= 64 ? 0 : (c >> k));
+      int64_t o = slot_end(pl, C, U, n_out);
+      for (int64_t j = prev; j < o; ++j) anc[j] = (int32_t)i;
+      if (o > prev) prev = o;
+    }
+  }
+  // by construction prev == n_out (coverage lemma)
+  for (int64_t j = prev; j < n_out; ++j) anc[j] = -1;
+}
+
+// multinomial on the same fixed-point CDF: N iid categorical draws (resample2,
+// Inference.hs:57-61), slot j uses the 64-bit uniform of Philox ctr=(j,0,t,"MULT").
+void multinomial_ancestors(const ResamplePlan& pl, uint64_t seed, uint32_t t, int64_t n_out, int32_t* anc) {
+  // full CDF (oracle can afford it)
+  std::vector<uint64_t> cdf(pl.n);
+  for (int64_t b = 0; b < pl.nblk; ++b) {
+    int64_t k = (int64_t)pl.emax - (int64_t)pl.eb[b];
+    uint64_t c = 0;
+    int64_t hi = std::min(pl.n, (b + 1) * kBlk);
+    for (int64_t i = b * kBlk; i < hi; ++i) {
+      if (pl.eb[b] != kNZero) c += q_at(pl.mant[i], pl.nexp[i], pl.eb[b]);
+      cdf[i] = pl.pb[b] + ((pl.eb[b] == kNZero || k >= 64) ? 0 : (c >> k));
+    }
+  }
+  for (int64_t j = 0; j < n_out; ++j) {
+    uint32_t r[4];
+    philox((uint32_t)j, 0, t, kStreamMulti, seed, r);
+    uint64_t u = ((uint64_t)r[0] << 32) | r[1];
+    uint64_t tau = (uint64_t)(((u128)u * pl.total) >> 64);  // [0, T)
+    int64_t i = std::upper_bound(cdf.begin(), cdf.end(), tau) - cdf.begin();  // min{i: C_i > tau}
+    anc[j] = (int32_t)i;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The canonical filter (bit-exact twin of the CUDA path).
+// ---------------------------------------------------------------------------------------
+struct OFilter {
+  pz_model_desc desc;
+  LgParams p;
+  int64_t n = 0;
+  uint64_t seed = 0;
+  uint32_t t = 0;
+  std::vector<float> x;    // SoA [nx][n], population the pending weights refer to
+  std::vector<float> lw;   // its log-weights
+  std::vector<int32_t> anc;  // ancestors used by the last step
+  double center[PZ_MAX_NX];  // centring constants of the moment sums (previous posterior mean)
+};
+
+void summarise(const OFilter& f, const ResamplePlan& pl, pz_step_summary* s, const double* center) {
+  // the same truncated fixed-point weights the resampler uses, at scale 2^(emax-31), in double
+  double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
+  for (int64_t i = 0; i < f.n; ++i) {
+    const int32_t eb = pl.eb[i / kBlk];
+    const uint32_t q = q_at(pl.mant[i], pl.nexp[i], eb);
+    if (!q) continue;
+    double w = ldexp((double)q, eb - pl.emax);
+    sw += w; sw2 += w * w;
+    for (int d = 0; d < f.p.nx; ++d) {
+      double dx = (double)(f.x[(size_t)d * f.n + i] - (float)center[d]);
+      sx[d] += w * dx; sxx[d] += w * dx * dx;
+    }
+  }
+  s->ess = sw * sw / sw2;
+  for (int d = 0; d < f.p.nx; ++d) {
+    double m = sx[d] / sw;
+    s->mean[d] = (double)(float)center[d] + m;
+    s->var[d] = sxx[d] / sw - m * m;
+  }
+  s->log_evidence_inc = log(sw) + (pl.emax - 31) * M_LN2 - log((double)f.n) + f.p.ll_const;
+  s->e_max = pl.emax;
+  s->total_weight = pl.total;
+  s->n_migrated = 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// extern "C" surface for ctypes
+// =========================================================================================
+extern "C" {
+
+void pzo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  philox4x32_10(c, key[0], key[1]);
+  memcpy(out, c, sizeof(c));
+}
+
+void pzo_weight_split(const float* lw, int64_t n, int32_t* nexp, uint32_t* mant) {
+  for (int64_t i = 0; i < n; ++i) weight_split(lw[i], &nexp[i], &mant[i]);
+}
+
+void pzo_normal_pairs(const uint32_t* ra, const uint32_t* rb, int64_t n, float* z0, float* z1) {
+  for (int64_t i = 0; i < n; ++i) normal_pair(ra[i], rb[i], &z0[i], &z1[i]);
+}
+
+uint32_t pzo_resample_uniform(uint64_t seed, uint32_t t) {
+  uint32_t r[4];
+  philox(0, 0, t, kStreamResample, seed, r);
+  return r[0];
+}
+
+// canonical systematic ancestors from fp32 log-weights; optional diagnostics
+int pzo_resample_systematic(const float* lw, int64_t n, uint32_t U, int32_t* anc, int32_t* eb_out,
+                            uint64_t* sb_out, uint64_t* pb_out, int32_t* emax, uint64_t* total) {
+  ResamplePlan pl;
+  if (!build_plan(lw, n, n, &pl)) return PZ_EDEGENERATE;
+  systematic_ancestors(pl, U, n, anc);
+  if (eb_out) memcpy(eb_out, pl.eb.data(), pl.nblk * sizeof(int32_t));
+  if (sb_out) memcpy(sb_out, pl.sb.data(), pl.nblk * sizeof(uint64_t));
+  if (pb_out) memcpy(pb_out, pl.pb.data(), (pl.nblk + 1) * sizeof(uint64_t));
+  if (emax) *emax = pl.emax;
+  if (total) *total = pl.total;
+  return 0;
+}
+
+int pzo_resample_multinomial(const float* lw, int64_t n, uint64_t seed, uint32_t t, int32_t* anc) {
+  ResamplePlan pl;
+  if (!build_plan(lw, n, n, &pl)) return PZ_EDEGENERATE;
+  multinomial_ancestors(pl, seed, t, n, anc);
+  return 0;
+}
+
+// Reference semantics of systematic resampling in double (monad-bayes
+// Control.Monad.Bayes.Population.systematic lineage: thresholds (u+j)/N, sequential CDF
+// walk).  Used to check the fixed-point resampler statistically, not bitwise.
+void pzo_resample_systematic_f64(const double* logw, int64_t n, double u, int32_t* anc) {
+  double mx = -INFINITY;
+  for (int64_t i = 0; i < n; ++i) if (logw[i] > mx) mx = logw[i];
+  double tot = 0;
+  for (int64_t i = 0; i < n; ++i) tot += exp(logw[i] - mx);
+  double c = 0; int64_t j = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    c += exp(logw[i] - mx) / tot;
+    while (j < n && (j + u) / n < c) anc[j++] = (int32_t)i;
+  }
+  while (j < n) anc[j++] = (int32_t)(n - 1);
+}
+
+void* pzo_filter_create(const pz_model_desc* d, int64_t n, uint64_t seed) {
+  OFilter* f = new OFilter();
+  f->desc = *d;
+  if (!derive_lg(d, &f->p) || n < 1) { delete f; return nullptr; }
+  f->n = n; f->seed = seed; f->t = 0;
+  f->x.assign((size_t)f->p.nx * n, 0.0f);
+  for (int k = 0; k < f->p.nx; ++k) {
+    for (int64_t i = 0; i < n; ++i) f->x[(size_t)k * n + i] = f->p.x0[k];
+    f->center[k] = d->x0[k];
+  }
+  f->lw.assign(n, 0.0f);  // equal weights before the first observation
+  f->anc.assign(n, 0);
+  return f;
+}
+
+void pzo_filter_destroy(void* h) { delete (OFilter*)h; }
+
+void pzo_filter_derived(void* h, float* F, float* Lq, float* H, float* Rinv, float* wscale, double* ll_const) {
+  OFilter* f = (OFilter*)h;
+  memcpy(F, f->p.F, sizeof(f->p.F)); memcpy(Lq, f->p.Lq, sizeof(f->p.Lq));
+  memcpy(H, f->p.H, sizeof(f->p.H)); memcpy(Rinv, f->p.Rinv, sizeof(f->p.Rinv));
+  *wscale = f->p.wscale; *ll_const = f->p.ll_const;
+}
+
+// One step of zparticles' (Inference.hs:101-104) in the cross-step order of the CUDA path:
+// resample the pending population by its weights, propagate every child, weight it by the
+// new observation.  (The reference weights first and resamples at the end of the same step;
+// the populations and weights visited are identical, only the step boundary moves.)
+int pzo_filter_step(void* h, const double* obs, pz_step_summary* out) {
+  OFilter* f = (OFilter*)h;
+  const LgParams& p = f->p;
+  int64_t n = f->n;
+  ResamplePlan pl;
+  if (!build_plan(f->lw.data(), n, n, &pl)) return PZ_EDEGENERATE;
+  if (f->desc.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
+    multinomial_ancestors(pl, f->seed, f->t, n, f->anc.data());
+  } else {
+    uint32_t U = pzo_resample_uniform(f->seed, f->t);
+    systematic_ancestors(pl, U, n, f->anc.data());
+  }
+  float y[PZ_MAX_NY];
+  for (int k = 0; k < p.ny; ++k) y[k] = (float)obs[k];
+  std::vector<float> xn((size_t)p.nx * n);
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < n; ++j) {
+    float xp[PZ_MAX_NX], z[PZ_MAX_NX + 2], xo[PZ_MAX_NX];
+    int64_t a = f->anc[j];
+    for (int d = 0; d < p.nx; ++d) xp[d] = f->x[(size_t)d * n + a];
+    lg_noise(p.nx, (uint64_t)j, f->t, f->seed, z);
+    lg_propagate(p, xp, z, xo);
+    for (int d = 0; d < p.nx; ++d) xn[(size_t)d * n + j] = xo[d];
+    f->lw[j] = lg_logweight(p, xo, y);
+  }
+  f->x.swap(xn);
+  ResamplePlan pl2;
+  bool ok = build_plan(f->lw.data(), n, n, &pl2);
+  if (out) {
+    memset(out, 0, sizeof(*out));
+    out->step = f->t;
+    if (ok) {
+      summarise(*f, pl2, out, f->center);
+      for (int d = 0; d < p.nx; ++d) f->center[d] = out->mean[d];
+    }
+  }
+  f->t += 1;
+  return ok ? 0 : PZ_EDEGENERATE;
+}
+
+void pzo_filter_state(void* h, float* x, float* lw, int32_t* anc) {
+  OFilter* f = (OFilter*)h;
+  if (x) memcpy(x, f->x.data(), f->x.size() * sizeof(float));
+  if (lw) memcpy(lw, f->lw.data(), f->lw.size() * sizeof(float));
+  if (anc) memcpy(anc, f->anc.data(), f->anc.size() * sizeof(int32_t));
+}
+
+// block statistics of the pending population (parity tap for the fused kernel's metadata)
+int pzo_filter_block_stats(void* h, int32_t* eb, uint64_t* sb, int32_t* emax, uint64_t* total) {
+  OFilter* f = (OFilter*)h;
+  ResamplePlan pl;
+  bool ok = build_plan(f->lw.data(), f->n, f->n, &pl);
+  if (eb) memcpy(eb, pl.eb.data(), pl.nblk * sizeof(int32_t));
+  if (sb) memcpy(sb, pl.sb.data(), pl.nblk * sizeof(uint64_t));
+  if (emax) *emax = pl.emax;
+  if (total) *total = pl.total;
+  return ok ? 0 : PZ_EDEGENERATE;
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact Kalman filter, kalmanPredict / kalmanUpdate (MVDistributions.hs:75-100), double.
+// mean[nx], cov[nx*nx] row-major, updated in place.  For ny == 1 with scalar_ll_2x the
+// exact target of the reference's doubled score is R_eff = R/2.
+// ---------------------------------------------------------------------------------------
+int pzo_kalman_step(const pz_model_desc* d, const double* y, double* mean, double* cov, double* loglik) {
+  int nx = d->nx, ny = d->ny;
+  double Rm[PZ_MAX_NY * PZ_MAX_NY];
+  bool dbl = (ny == 1 && d->scalar_ll_2x);
+  for (int i = 0; i < ny * ny; ++i) Rm[i] = d->R[i] * (dbl ? 0.5 : 1.0);
+  // predict: (F x, F P F^T + Q)
+  double xm[PZ_MAX_NX], FP[PZ_MAX_NX * PZ_MAX_NX], Pm[PZ_MAX_NX * PZ_MAX_NX];
+  for (int i = 0; i < nx; ++i) { xm[i] = 0; for (int k = 0; k < nx; ++k) xm[i] += d->F[i * nx + k] * mean[k]; }
+  for (int i = 0; i < nx; ++i) for (int j = 0; j < nx; ++j) {
+    double s = 0; for (int k = 0; k < nx; ++k) s += d->F[i * nx + k] * cov[k * nx + j]; FP[i * nx + j] = s; }
+  for (int i = 0; i < nx; ++i) for (int j = 0; j < nx; ++j) {
+    double s = 0; for (int k = 0; k < nx; ++k) s += FP[i * nx + k] * d->F[j * nx + k]; Pm[i * nx + j] = s + d->Q[i * nx + j]; }
+  // update: S = R + H P H^T, K = P H^T S^-1
+  double PHt[PZ_MAX_NX * PZ_MAX_NY], S[PZ_MAX_NY][2 * PZ_MAX_NY] = {}, yt[PZ_MAX_NY];
+  for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) {
+    double s = 0; for (int k = 0; k < nx; ++k) s += Pm[i * nx + k] * d->H[j * nx + k]; PHt[i * ny + j] = s; }
+  for (int i = 0; i < ny; ++i) {
+    for (int j = 0; j < ny; ++j) {
+      double s = 0; for (int k = 0; k < nx; ++k) s += d->H[i * nx + k] * PHt[k * ny + j]; S[i][j] = s + Rm[i * ny + j]; }
+    S[i][ny + i] = 1.0;
+    double s = 0; for (int k = 0; k < nx; ++k) s += d->H[i * nx + k] * xm[k]; yt[i] = y[i] - s;
+  }
+  double logdet = 0;
+  for (int c = 0; c < ny; ++c) {
+    double piv = S[c][c]; if (!(piv > 0)) return PZ_EINVAL; logdet += log(piv);
+    for (int j = 0; j < 2 * ny; ++j) S[c][j] /= piv;
+    for (int r = 0; r < ny; ++r) { if (r == c) continue; double f = S[r][c]; for (int j = 0; j < 2 * ny; ++j) S[r][j] -= f * S[c][j]; }
+  }
+  double Siy[PZ_MAX_NY], quad = 0;
+  for (int i = 0; i < ny; ++i) { double s = 0; for (int j = 0; j < ny; ++j) s += S[i][ny + j] * yt[j]; Siy[i] = s; quad += yt[i] * s; }
+  if (loglik) *loglik = -0.5 * (quad + logdet + ny * log(2 * M_PI));  // correct m-dim constant
+  double K[PZ_MAX_NX * PZ_MAX_NY];
+  for (int i = 0; i < nx; ++i) for (int j = 0; j < ny; ++j) {
+    double s = 0; for (int k = 0; k < ny; ++k) s += PHt[i * ny + k] * S[k][ny + j]; K[i * ny + j] = s; }
+  for (int i = 0; i < nx; ++i) { double s = 0; for (int j = 0; j < ny; ++j) s += K[i * ny + j] * yt[j]; mean[i] = xm[i] + s; }
+  for (int i = 0; i < nx; ++i) for (int j = 0; j < nx; ++j) {
+    double s = 0; for (int k = 0; k < ny; ++k) s += K[i * ny + k] * PHt[j * ny + k]; cov[i * nx + j] = Pm[i * nx + j] - s; }
+  (void)Siy;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Synthetic observation stream from the generative model (Demo.hs:203-207,
+// SingleTargetTracking.hs:61-65): x_t ~ N(F x_{t-1}, Q), y_t ~ N(H x_t, R), in double with
+// libm Box-Muller on Philox stream "OBSG".  truth may be NULL.
+// ---------------------------------------------------------------------------------------
+static void std_normals(uint64_t seed, uint32_t t, uint32_t call, double z[4]) {
+  uint32_t r[4];
+  philox(call, 0, t, kStreamObs, seed, r);
+  for (int k = 0; k < 2; ++k) {
+    double u1 = ((double)r[2 * k] + 0.5) * 0x1p-32, u2 = ((double)r[2 * k + 1] + 0.5) * 0x1p-32;
+    double R = sqrt(-2.0 * log(u1));
+    z[2 * k] = R * cos(2 * M_PI * u2); z[2 * k + 1] = R * sin(2 * M_PI * u2);
+  }
+}
+
+int pzo_generate_observations(const pz_model_desc* d, uint64_t seed, int64_t T, double* obs, double* truth) {
+  int nx = d->nx, ny = d->ny;
+  double Lq[PZ_MAX_NX][PZ_MAX_NX] = {}, Lr[PZ_MAX_NY][PZ_MAX_NY] = {};
+  for (int j = 0; j < nx; ++j) {
+    double s = d->Q[j * nx + j]; for (int k = 0; k < j; ++k) s -= Lq[j][k] * Lq[j][k];
+    double l = s > 0 ? sqrt(s) : 0; Lq[j][j] = l;
+    for (int i = j + 1; i < nx; ++i) { double t = d->Q[i * nx + j]; for (int k = 0; k < j; ++k) t -= Lq[i][k] * Lq[j][k]; Lq[i][j] = l > 0 ? t / l : 0; }
+  }
+  for (int j = 0; j < ny; ++j) {
+    double s = d->R[j * ny + j]; for (int k = 0; k < j; ++k) s -= Lr[j][k] * Lr[j][k];
+    double l = s > 0 ? sqrt(s) : 0; Lr[j][j] = l;
+    for (int i = j + 1; i < ny; ++i) { double t = d->R[i * ny + j]; for (int k = 0; k < j; ++k) t -= Lr[i][k] * Lr[j][k]; Lr[i][j] = l > 0 ? t / l : 0; }
+  }
+  double x[PZ_MAX_NX];
+  for (int i = 0; i < nx; ++i) x[i] = d->x0[i];
+  for (int64_t t = 0; t < T; ++t) {
+    double z[12];
+    std_normals(seed, (uint32_t)t, 0, z); std_normals(seed, (uint32_t)t, 1, z + 4); std_normals(seed, (uint32_t)t, 2, z + 8);
+    double xn[PZ_MAX_NX];
+    for (int i = 0; i < nx; ++i) {
+      double s = 0; for (int k = 0; k < nx; ++k) s += d->F[i * nx + k] * x[k];
+      for (int k = 0; k <= i; ++k) s += Lq[i][k] * z[k];
+      xn[i] = s;
+    }
+    for (int i = 0; i < nx; ++i) x[i] = xn[i];
+    for (int i = 0; i < ny; ++i) {
+      double s = 0; for (int k = 0; k < nx; ++k) s += d->H[i * nx + k] * x[k];
+      for (int k = 0; k <= i; ++k) s += Lr[i][k] * z[8 + k];
+      obs[t * ny + i] = s;
+    }
+    if (truth) for (int i = 0; i < nx; ++i) truth[t * nx + i] = x[i];
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Reference-faithful particle filter in double (CPU-ref row of BASELINE.md section 4):
+//   zparticles' (Inference.hs:101-104): N weighted model steps, then resample2;
+//   normalize (Inference.hs:63-66): total mass by a left fold of log-domain (+);
+//   labeledLogCategorical (Inference.hs:57-58): per draw, exponentiate all N normalised
+//   weights and walk the CDF -- O(N) per draw, O(N^2) per step, exactly the reference's
+//   cost profile.  Output per step: `average particles` after resampling (Demo.hs:207).
+// mode 0 = faithful O(N^2) walk; mode 1 = same draws by binary search on one CDF
+// (identical ancestors, O(N log N)), used where the faithful walk would not finish.
+// ---------------------------------------------------------------------------------------
+static inline double logaddexp(double a, double b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  double m = a > b ? a : b;
+  return m + log1p(exp(-fabs(a - b)));
+}
+
+int pzo_refpf_run(const pz_model_desc* d, int64_t n, uint64_t seed, const double* obs, int64_t T, int mode,
+                  double* mean_out, double* var_out, int threads) {
+  int nx = d->nx, ny = d->ny;
+  LgParams lp;
+  if (!derive_lg(d, &lp)) return PZ_EINVAL;
+  // double-precision model constants
+  double Lq[PZ_MAX_NX][PZ_MAX_NX] = {}, Rinv[PZ_MAX_NY][PZ_MAX_NY];
+  for (int i = 0; i < nx; ++i) for (int j = 0; j < nx; ++j) Lq[i][j] = lp.Lq[i][j];  // diagonal in all in-scope models
+  {
+    // recompute in double for fidelity
+    for (int j = 0; j < nx; ++j) {
+      double s = d->Q[j * nx + j]; for (int k = 0; k < j; ++k) s -= Lq[j][k] * Lq[j][k];
+      double l = s > 0 ? sqrt(s) : 0; Lq[j][j] = l;
+      for (int i = j + 1; i < nx; ++i) { double t = d->Q[i * nx + j]; for (int k = 0; k < j; ++k) t -= Lq[i][k] * Lq[j][k]; Lq[i][j] = l > 0 ? t / l : 0; }
+    }
+    double A[PZ_MAX_NY][2 * PZ_MAX_NY] = {};
+    for (int i = 0; i < ny; ++i) { for (int j = 0; j < ny; ++j) A[i][j] = d->R[i * ny + j]; A[i][ny + i] = 1; }
+    for (int c = 0; c < ny; ++c) {
+      double piv = A[c][c]; for (int j = 0; j < 2 * ny; ++j) A[c][j] /= piv;
+      for (int r = 0; r < ny; ++r) { if (r == c) continue; double f = A[r][c]; for (int j = 0; j < 2 * ny; ++j) A[r][j] -= f * A[c][j]; }
+    }
+    for (int i = 0; i < ny; ++i) for (int j = 0; j < ny; ++j) Rinv[i][j] = A[i][ny + j];
+  }
+  double wscale = lp.wscale, llc = lp.ll_const;
+#if defined(_OPENMP)
+  if (threads > 0) omp_set_num_threads(threads);
+#else
+  (void)threads;
+#endif
+  std::vector<double> x((size_t)nx * n), xn((size_t)nx * n), lw(n), w(n), cdf(n);
+  std::vector<int64_t> anc(n);
+  for (int k = 0; k < nx; ++k) for (int64_t i = 0; i < n; ++i) x[(size_t)k * n + i] = d->x0[k];
+  for (int64_t t = 0; t < T; ++t) {
+    const double* y = obs + t * ny;
+    // res <- sequence [ runWeighted (f a) | f <- fs ]
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      uint32_t r[4]; double z[8];
+      for (int c = 0; 4 * c < nx; ++c) {
+        philox((uint32_t)i, (uint32_t)c, (uint32_t)t, kStreamProp, seed ^ 0x5EEDull, r);
+        for (int k = 0; k < 2; ++k) {
+          double u1 = ((double)r[2 * k] + 0.5) * 0x1p-32, u2 = ((double)r[2 * k + 1] + 0.5) * 0x1p-32;
+          double R = sqrt(-2.0 * log(u1));
+          z[4 * c + 2 * k] = R * cos(2 * M_PI * u2); z[4 * c + 2 * k + 1] = R * sin(2 * M_PI * u2);
+        }
+      }
+      double xo[PZ_MAX_NX];
+      for (int a = 0; a < nx; ++a) {
+        double s = 0; for (int k = 0; k < nx; ++k) s += d->F[a * nx + k] * x[(size_t)k * n + i];
+        for (int k = 0; k <= a; ++k) s += Lq[a][k] * z[k];
+        xo[a] = s; xn[(size_t)a * n + i] = s;
+      }
+      double dd[PZ_MAX_NY], quad = 0;
+      for (int a = 0; a < ny; ++a) { double s = 0; for (int k = 0; k < nx; ++k) s += d->H[a * nx + k] * xo[k]; dd[a] = y[a] - s; }
+      for (int a = 0; a < ny; ++a) { double s = 0; for (int k = 0; k < ny; ++k) s += Rinv[a][k] * dd[k]; quad += dd[a] * s; }
+      lw[i] = wscale * quad + llc;  // score accumulated by `observe`
+    }
+    // normalize: totalMass = sum (map snd xs)  -- left fold of Log's (+)
+    double tot = -INFINITY;
+    for (int64_t i = 0; i < n; ++i) tot = logaddexp(tot, lw[i]);
+    if (!(tot > -INFINITY)) return PZ_EDEGENERATE;
+    // replicateM N (labeledLogCategorical normalized)
+    if (mode == 0) {
+#pragma omp parallel for schedule(static)
+      for (int64_t j = 0; j < n; ++j) {
+        uint32_t r[4];
+        philox((uint32_t)j, 0, (uint32_t)t, kStreamMulti, seed ^ 0x5EEDull, r);
+        double u = ((double)(((uint64_t)r[0] << 21) ^ (r[1] >> 11)) + 0.5) * 0x1p-53;
+        double c = 0; int64_t k = n - 1;
+        for (int64_t i = 0; i < n; ++i) { c += exp(lw[i] - tot); if (u < c) { k = i; break; } }
+        anc[j] = k;
+      }
+    } else {
+      double c = 0;
+      for (int64_t i = 0; i < n; ++i) { c += exp(lw[i] - tot); cdf[i] = c; }
+#pragma omp parallel for schedule(static)
+      for (int64_t j = 0; j < n; ++j) {
+        uint32_t r[4];
+        philox((uint32_t)j, 0, (uint32_t)t, kStreamMulti, seed ^ 0x5EEDull, r);
+        double u = ((double)(((uint64_t)r[0] << 21) ^ (r[1] >> 11)) + 0.5) * 0x1p-53;
+        int64_t k = std::upper_bound(cdf.begin(), cdf.end(), u) - cdf.begin();
+        anc[j] = k < n ? k : n - 1;
+      }
+    }
+    // unzip <$> resample2 res ; output = average particles (Util/Numeric.hs:7-10)
+    for (int a = 0; a < nx; ++a) {
+      double s = 0, s2 = 0;
+      double* dst = &x[(size_t)a * n]; const double* src = &xn[(size_t)a * n];
+      for (int64_t j = 0; j < n; ++j) { double v = src[anc[j]]; dst[j] = v; s += v; s2 += v * v; }
+      if (mean_out) mean_out[t * nx + a] = s / n;
+      if (var_out) var_out[t * nx + a] = s2 / n - (s / n) * (s / n);
+    }
+  }
+  return 0;
+}
+
+int pzo_num_threads(void) {
+#if defined(_OPENMP)
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,604 @@
+// pz_api.cu -- the C ABI of include/pzgpu.h: filter handle, device memory, stream, CUDA
+// graph and the launch sequence of one particle-filter step.
+//
+// Reference interface replaced (per call):
+//   pz_filter_create   zparticles n model   (Inference.hs:107-108) / zdsparticles (113-114)
+//   pz_filter_step     ZStream.step         (Util/ZStream.hs:16) applied to zparticles'
+//   pz_filter_run      ZS.runStream         (Util/ZStream.hs:65-69)
+//   pz_filter_read_particles   the `[b]` output list of zparticles' (Inference.hs:104)
+//
+// There is no CPU fallback: every entry point that computes returns PZ_ECUDA when no CUDA
+// device is usable.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "pz_kernels.cuh"
+
+using namespace pz;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PZ_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) return fail(PZ_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// Derived fp32 model parameters: Cholesky of Q, inverse and log-determinant of R in double,
+// rounded once to fp32 (DESIGN.md "Model descriptor").
+int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
+  const int nx = d->nx, ny = d->ny;
+  if (nx < 1 || nx > PZ_MAX_NX || ny < 1 || ny > PZ_MAX_NY) return fail(PZ_EINVAL, "unsupported dims nx=%d ny=%d", nx, ny);
+  memset(p, 0, sizeof(*p));
+  p->nx = nx; p->ny = ny;
+  double L[PZ_MAX_NX][PZ_MAX_NX] = {};
+  for (int j = 0; j < nx; ++j) {
+    double s = d->Q[j * nx + j];
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    if (s < 0) return fail(PZ_EINVAL, "Q is not positive semi-definite");
+    const double ljj = s > 0 ? sqrt(s) : 0.0;
+    L[j][j] = ljj;
+    for (int i = j + 1; i < nx; ++i) {
+      double t = d->Q[i * nx + j];
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = ljj > 0 ? t / ljj : 0.0;
+    }
+  }
+  double A[PZ_MAX_NY][2 * PZ_MAX_NY] = {};
+  for (int i = 0; i < ny; ++i) {
+    for (int j = 0; j < ny; ++j) A[i][j] = d->R[i * ny + j];
+    A[i][ny + i] = 1.0;
+  }
+  double logdet = 0;
+  for (int c = 0; c < ny; ++c) {
+    const double piv = A[c][c];
+    if (!(piv > 0)) return fail(PZ_EINVAL, "R is not positive definite");
+    logdet += log(piv);
+    for (int j = 0; j < 2 * ny; ++j) A[c][j] /= piv;
+    for (int r = 0; r < ny; ++r) {
+      if (r == c) continue;
+      const double f = A[r][c];
+      for (int j = 0; j < 2 * ny; ++j) A[r][j] -= f * A[c][j];
+    }
+  }
+  for (int i = 0; i < nx; ++i) {
+    for (int j = 0; j < nx; ++j) { p->F[i][j] = (float)d->F[i * nx + j]; p->Lq[i][j] = (float)L[i][j]; }
+    p->x0[i] = (float)d->x0[i];
+  }
+  for (int i = 0; i < ny; ++i) {
+    for (int j = 0; j < nx; ++j) p->H[i][j] = (float)d->H[i * nx + j];
+    for (int j = 0; j < ny; ++j) p->Rinv[i][j] = (float)A[i][ny + j];
+  }
+  const bool dbl = (ny == 1 && d->scalar_ll_2x);
+  p->wscale = dbl ? -1.0f : -0.5f;
+  *ll_const = (dbl ? -1.0 : -0.5) * (logdet + ny * log(2 * M_PI));
+  return PZ_OK;
+}
+
+// scratch of the generic (stored log-weight) path
+struct GenericScratch {
+  float* lw = nullptr;
+  int32_t* anc = nullptr;
+  int32_t* eb = nullptr;
+  uint64_t* sb = nullptr;
+  uint64_t* pb = nullptr;
+  int32_t* tile_start = nullptr;
+  uint64_t* scan_status = nullptr;
+  double* scan_part = nullptr;
+  PlanDev* plan = nullptr;
+  CtlDev* ctl = nullptr;
+  int64_t cap = 0;  // particles
+  void release() {
+    cudaFree(lw); cudaFree(anc); cudaFree(eb); cudaFree(sb); cudaFree(pb); cudaFree(tile_start);
+    cudaFree(scan_status); cudaFree(scan_part); cudaFree(plan); cudaFree(ctl);
+    *this = GenericScratch();
+  }
+};
+
+int generic_alloc(GenericScratch* g, int64_t n, bool full) {
+  if (g->cap >= n && (!full || g->eb)) return PZ_OK;
+  g->release();
+  const int64_t ld = round_up(n, kPad), nblk = (n + kBlk - 1) / kBlk;
+  const int64_t nscan = (nblk + kScanTile - 1) / kScanTile, ntiles = (n + kGenericTileOut - 1) / kGenericTileOut;
+  PZ_CUDA(cudaMalloc(&g->lw, ld * sizeof(float)));
+  PZ_CUDA(cudaMemset(g->lw, 0, ld * sizeof(float)));
+  PZ_CUDA(cudaMalloc(&g->anc, ld * sizeof(int32_t)));
+  PZ_CUDA(cudaMalloc(&g->tile_start, (ntiles + 1) * sizeof(int32_t)));
+  if (full) {
+    PZ_CUDA(cudaMalloc(&g->eb, (nblk + 1) * sizeof(int32_t)));
+    PZ_CUDA(cudaMalloc(&g->sb, (nblk + 1) * sizeof(uint64_t)));
+    PZ_CUDA(cudaMalloc(&g->pb, (nblk + 2) * sizeof(uint64_t)));
+    PZ_CUDA(cudaMalloc(&g->scan_status, (nscan + 1) * sizeof(uint64_t)));
+    PZ_CUDA(cudaMemset(g->scan_status, 0, (nscan + 1) * sizeof(uint64_t)));
+    PZ_CUDA(cudaMalloc(&g->scan_part, (nscan + 1) * kMaxRec * sizeof(double)));
+    PZ_CUDA(cudaMalloc(&g->plan, sizeof(PlanDev)));
+    PZ_CUDA(cudaMemset(g->plan, 0, sizeof(PlanDev)));
+    PZ_CUDA(cudaMalloc(&g->ctl, sizeof(CtlDev)));
+  }
+  g->cap = n;
+  return PZ_OK;
+}
+
+}  // namespace
+
+struct pz_filter {
+  pz_model_desc desc;
+  StepArgs a;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  float* h_obs = nullptr;            // pinned [kObsRing][PZ_MAX_NY]
+  pz_step_summary* h_summ = nullptr; // pinned [kObsRing]
+  float* d_obs = nullptr;
+  uint32_t t = 0;                    // host mirror of ctl->t
+  double last_ms = 0;
+  int64_t last_launches = 0;
+  GenericScratch g;                  // taps / multinomial path
+  int launches_per_step = 0;
+};
+
+namespace {
+
+void free_filter(pz_filter* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->graph) cudaGraphExecDestroy(f->graph);
+  StepArgs& a = f->a;
+  cudaFree(a.X[0]); cudaFree(a.X[1]); cudaFree(a.eb[0]); cudaFree(a.eb[1]); cudaFree(a.sb); cudaFree(a.pb);
+  cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part); cudaFree(a.plan);
+  cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ);
+  f->g.release();
+  if (f->h_obs) cudaFreeHost(f->h_obs);
+  if (f->h_summ) cudaFreeHost(f->h_summ);
+  if (f->ev0) cudaEventDestroy(f->ev0);
+  if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+int stage_obs(pz_filter* f, const double* obs, int64_t k, int32_t obs_dim) {
+  // rows for steps [t, t+k) -> ring rows (t+i) % kObsRing
+  for (int64_t i = 0; i < k; ++i) {
+    float* row = f->h_obs + ((f->t + i) % kObsRing) * PZ_MAX_NY;
+    for (int c = 0; c < PZ_MAX_NY; ++c) row[c] = c < obs_dim ? (float)obs[i * obs_dim + c] : 0.0f;
+  }
+  const int64_t r0 = f->t % kObsRing;
+  const int64_t first = (r0 + k <= kObsRing) ? k : kObsRing - r0;
+  const size_t rowb = PZ_MAX_NY * sizeof(float);
+  PZ_CUDA(cudaMemcpyAsync(f->d_obs + r0 * PZ_MAX_NY, f->h_obs + r0 * PZ_MAX_NY, first * rowb, cudaMemcpyHostToDevice, f->stream));
+  if (first < k)
+    PZ_CUDA(cudaMemcpyAsync(f->d_obs, f->h_obs, (k - first) * rowb, cudaMemcpyHostToDevice, f->stream));
+  return PZ_OK;
+}
+
+int fetch_summaries(pz_filter* f, uint32_t t0, int64_t k) {
+  const int64_t r0 = t0 % kObsRing;
+  const int64_t first = (r0 + k <= kObsRing) ? k : kObsRing - r0;
+  PZ_CUDA(cudaMemcpyAsync(f->h_summ + r0, f->a.summ + r0, first * sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  if (first < k)
+    PZ_CUDA(cudaMemcpyAsync(f->h_summ, f->a.summ, (k - first) * sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  return PZ_OK;
+}
+
+// ancestors of the pending resample into f->g.anc (systematic: canonical; multinomial: step t)
+int pending_ancestors(pz_filter* f, int* launches) {
+  StepArgs& a = f->a;
+  int rc = generic_alloc(&f->g, a.n_local, false);
+  if (rc) return rc;
+  int n = 0;
+  n += launch_logw(a, f->g.lw, f->stream);
+  GenericArgs g{};
+  g.lw = f->g.lw; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[1]; g.parity_ctl = a.ctl;
+  g.sb = a.sb; g.pb = a.pb; g.tile_start = f->g.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
+  g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk;
+  g.ntiles_out = (int32_t)((a.n_local + kGenericTileOut - 1) / kGenericTileOut);
+  g.nscan = a.nscan; g.U = 0; g.seed = a.seed; g.step = f->t;
+  if (a.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
+    n += launch_generic_multinomial(g, f->stream);
+  } else {
+    // partition for the generic tile size, then the ancestor kernel
+    StepArgs b = a;
+    b.tile_start = f->g.tile_start;
+    b.ntiles_out = g.ntiles_out;
+    n += launch_partition_only(b, kGenericTileOut, f->stream);
+    n += launch_generic_ancestors(g, f->stream);
+  }
+  if (launches) *launches += n;
+  PZ_CUDA(cudaGetLastError());
+  return PZ_OK;
+}
+
+int enqueue_step(pz_filter* f) {
+  StepArgs& a = f->a;
+  if (a.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
+    int n = 0;
+    int rc = pending_ancestors(f, &n);
+    if (rc) return rc;
+    n += launch_step(a, f->g.anc, f->stream);
+    f->last_launches += n;
+  } else if (f->graph) {
+    PZ_CUDA(cudaGraphLaunch(f->graph, f->stream));
+    f->last_launches += f->launches_per_step;
+  } else {
+    int n = launch_step(a, nullptr, f->stream);
+    if (n < 0) return fail(PZ_EINVAL, "no kernel instantiated for nx=%d ny=%d", a.model.nx, a.model.ny);
+    f->last_launches += n;
+  }
+  f->t += 1;
+  return PZ_OK;
+}
+
+int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank, int world,
+                  pz_filter** out) {
+  if (!model || !out) return fail(PZ_EINVAL, "null argument");
+  *out = nullptr;
+  if (model->kind == PZ_MODEL_MTT) return fail(PZ_EINVAL, "MTT descriptor: not available in this build");
+  if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS) return fail(PZ_EINVAL, "unknown model kind %d", model->kind);
+  if (!((model->nx == 1 && model->ny == 1) || (model->nx == 4 && model->ny == 2) || (model->nx == 6 && model->ny == 3)))
+    return fail(PZ_EINVAL, "no kernel instantiated for nx=%d ny=%d (supported: (1,1), (4,2), (6,3))", model->nx, model->ny);
+  if (n_global < 1 || n_global > (1ull << 30)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^30]");
+  if (world != 1) return fail(PZ_EINVAL, "sharded filters: use pz_filter_create_sharded");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PZ_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  PZ_CUDA(cudaSetDevice(device));
+  pz_filter* f = new (std::nothrow) pz_filter();
+  if (!f) return fail(PZ_ENOMEM, "out of host memory");
+  f->desc = *model;
+  f->device = device;
+  StepArgs& a = f->a;
+  memset(&a, 0, sizeof(a));
+  int rc = derive_lg(model, &a.model, &a.ll_const);
+  if (rc) { delete f; return rc; }
+  a.n_global = (int64_t)n_global;
+  a.n_local = (int64_t)n_global;
+  a.slot_base = 0;
+  (void)rank;
+  a.world = world;
+  a.seed = seed;
+  a.resampler = model->resampler;
+  a.ld = round_up(a.n_local, kPad);
+  a.nblk = (a.n_local + kBlk - 1) / kBlk;
+  a.nscan = (int32_t)((a.nblk + kScanTile - 1) / kScanTile);
+  const int to = fused_tile_out(model->nx);
+  a.ntiles_out = (int32_t)((a.n_local + to - 1) / to);
+  const size_t xbytes = (size_t)model->nx * a.ld * sizeof(float);
+#define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
+  PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  PZ_TRY(cudaEventCreate(&f->ev0));
+  PZ_TRY(cudaEventCreate(&f->ev1));
+  PZ_TRY(cudaMalloc(&a.X[0], xbytes));
+  PZ_TRY(cudaMalloc(&a.X[1], xbytes));
+  PZ_TRY(cudaMalloc(&a.eb[0], (a.nblk + 8) * sizeof(int32_t)));
+  PZ_TRY(cudaMalloc(&a.eb[1], (a.nblk + 8) * sizeof(int32_t)));
+  PZ_TRY(cudaMalloc(&a.sb, (a.nblk + 8) * sizeof(uint64_t)));
+  PZ_TRY(cudaMalloc(&a.pb, (a.nblk + 8) * sizeof(uint64_t)));
+  PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
+  PZ_TRY(cudaMalloc(&a.rec, (size_t)(a.ntiles_out + 1) * kMaxRec * sizeof(double)));
+  PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
+  PZ_TRY(cudaMalloc(&a.scan_part, (size_t)(a.nscan + 1) * kMaxRec * sizeof(double)));
+  PZ_TRY(cudaMalloc(&a.plan, sizeof(PlanDev)));
+  PZ_TRY(cudaMemset(a.plan, 0, sizeof(PlanDev)));
+  PZ_TRY(cudaMalloc(&a.ctl, sizeof(CtlDev)));
+  PZ_TRY(cudaMalloc(&f->d_obs, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
+  PZ_TRY(cudaMemset(f->d_obs, 0, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
+  a.obs = f->d_obs;
+  PZ_TRY(cudaMalloc(&a.summ, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMemset(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMallocHost(&f->h_obs, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
+  PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
+  launch_init(a, f->stream);
+  launch_scan_partition(a, to, f->stream);
+  PZ_TRY(cudaGetLastError());
+  PZ_TRY(cudaStreamSynchronize(f->stream));
+  // one captured graph serves every systematic step (the step index lives in ctl->t)
+  if (a.resampler == PZ_RESAMPLE_SYSTEMATIC) {
+    cudaGraph_t graph = nullptr;
+    PZ_TRY(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+    f->launches_per_step = launch_step(a, nullptr, f->stream);
+    PZ_TRY(cudaStreamEndCapture(f->stream, &graph));
+    PZ_TRY(cudaGraphInstantiate(&f->graph, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+#undef PZ_TRY
+  *out = f;
+  return PZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pz_abi_version(void) { return PZ_ABI_VERSION; }
+const char* pz_last_error(void) { return g_err; }
+
+static void fill_common(pz_model_desc* d, int kind, int nx, int ny) {
+  memset(d, 0, sizeof(*d));
+  d->kind = kind; d->nx = nx; d->ny = ny;
+  d->scalar_ll_2x = 1;  // reference behaviour (Distributions.hs:160-161)
+  d->resampler = PZ_RESAMPLE_SYSTEMATIC;
+}
+
+int pz_model_rw1d(pz_model_desc* d, double q_var, double r_var) {
+  if (!d || !(q_var >= 0) || !(r_var > 0)) return fail(PZ_EINVAL, "bad rw1d arguments");
+  fill_common(d, PZ_MODEL_RW1D, 1, 1);
+  d->F[0] = 1.0; d->Q[0] = q_var; d->H[0] = 1.0; d->R[0] = r_var;
+  return PZ_OK;
+}
+
+int pz_model_stt(pz_model_desc* d) {
+  if (!d) return fail(PZ_EINVAL, "null descriptor");
+  fill_common(d, PZ_MODEL_LINGAUSS, 6, 3);
+  const double tdiff = 1.0;  // SingleTargetTracking.hs:42
+  for (int i = 0; i < 6; ++i) d->F[i * 6 + i] = 1.0;
+  for (int i = 0; i < 3; ++i) {
+    d->F[i * 6 + 3 + i] = tdiff;             // motionMatrix :48-52
+    d->Q[i * 6 + i] = tdiff * 0.01;          // posCov :40
+    d->Q[(3 + i) * 6 + 3 + i] = tdiff * 0.1; // velCov :41
+    d->H[i * 6 + i] = 1.0;                   // posFromPosVel :53-54
+    d->R[i * 3 + i] = 10.0;                  // :35
+  }
+  return PZ_OK;
+}
+
+int pz_model_mtt_track(pz_model_desc* d) {
+  if (!d) return fail(PZ_EINVAL, "null descriptor");
+  fill_common(d, PZ_MODEL_LINGAUSS, 4, 2);
+  const double tdiff = 1.0;  // MultiTargetTracking.hs:37
+  for (int i = 0; i < 4; ++i) d->F[i * 4 + i] = 1.0;
+  for (int i = 0; i < 2; ++i) {
+    d->F[i * 4 + 2 + i] += tdiff * 1.0;            // motionMatrix :59-63
+    d->F[(2 + i) * 4 + i] += tdiff * (-1.0 / 100);
+    d->F[(2 + i) * 4 + 2 + i] += tdiff * (-0.1);
+    d->Q[i * 4 + i] = tdiff * 0.01;                // motionCov :64-67
+    d->Q[(2 + i) * 4 + 2 + i] = tdiff * 0.1;
+    d->H[i * 4 + i] = 1.0;                         // posFromPosVel :72-73
+    d->R[i * 2 + i] = 1.0;                         // :70
+  }
+  return PZ_OK;
+}
+
+int pz_model_mtt(pz_model_desc* d) {
+  int rc = pz_model_mtt_track(d);
+  if (rc) return rc;
+  d->kind = PZ_MODEL_MTT;
+  d->mtt.clutter_lambda = 3.0;       // MultiTargetTracking.hs:40
+  d->mtt.new_track_lambda = 0.1;     // :41
+  d->mtt.pd = 0.8;                   // :42
+  d->mtt.survival_prob = exp(-0.02); // :43
+  d->mtt.clutter_var = 10.0;         // :46
+  d->mtt.birth_pos_var = 5.0;        // :52-54
+  d->mtt.birth_vel_var = 0.1;
+  d->mtt.meas_var = 1.0;
+  d->mtt.k_max = 16;
+  d->mtt.m_max = 32;
+  return PZ_OK;
+}
+
+int pz_filter_create(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int device, pz_filter** out) {
+  return create_common(model, n_particles, seed, device, 0, 1, out);
+}
+
+int pz_comm_unique_id(void* out128) {
+  (void)out128;
+  return fail(PZ_ENCCL, "sharded filters are not available in this build");
+}
+
+int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank,
+                             int world, const void* nccl_unique_id, pz_filter** out) {
+  (void)nccl_unique_id;
+  if (world == 1) return create_common(model, n_global, seed, device, rank, 1, out);
+  return fail(PZ_ENCCL, "sharded filters are not available in this build");
+}
+
+int64_t pz_filter_n_local(const pz_filter* f) { return f ? f->a.n_local : 0; }
+
+int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, pz_step_summary* out) {
+  if (!f || !obs) return fail(PZ_EINVAL, "null argument");
+  if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d, got %d x %d", f->a.model.ny, n_obs, obs_dim);
+  PZ_CUDA(cudaSetDevice(f->device));
+  const uint32_t t0 = f->t;
+  f->last_launches = 0;
+  int rc = stage_obs(f, obs, 1, obs_dim);
+  if (rc) return rc;
+  PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+  rc = enqueue_step(f);
+  if (rc) return rc;
+  PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+  rc = fetch_summaries(f, t0, 1);
+  if (rc) return rc;
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+  f->last_ms = ms;
+  const pz_step_summary& s = f->h_summ[t0 % kObsRing];
+  if (out) *out = s;
+  if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t0);
+  return PZ_OK;
+}
+
+int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, double ms[3]) {
+  if (!f || !obs || !ms) return fail(PZ_EINVAL, "null argument");
+  if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d", f->a.model.ny);
+  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC) return fail(PZ_ESTATE, "profiled step: systematic resampler only");
+  PZ_CUDA(cudaSetDevice(f->device));
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) PZ_CUDA(cudaEventCreate(&ev[i]));
+  int rc = stage_obs(f, obs, 1, obs_dim);
+  if (rc) return rc;
+  f->last_launches = launch_step_profiled(f->a, f->stream, ev);
+  f->t += 1;
+  PZ_CUDA(cudaGetLastError());
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  for (int i = 0; i < 3; ++i) {
+    float x = 0;
+    cudaEventElapsedTime(&x, ev[i], ev[i + 1]);
+    ms[i] = x;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  return PZ_OK;
+}
+
+int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_dim, pz_step_summary* out) {
+  if (!f || !obs || n_steps < 0) return fail(PZ_EINVAL, "bad argument");
+  if (obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected observations of dim %d", f->a.model.ny);
+  PZ_CUDA(cudaSetDevice(f->device));
+  f->last_launches = 0;
+  f->last_ms = 0;
+  int64_t done = 0;
+  int status = PZ_OK;
+  while (done < n_steps) {
+    const int64_t k = (n_steps - done) < (kObsRing - 1) ? (n_steps - done) : (kObsRing - 1);
+    const uint32_t t0 = f->t;
+    int rc = stage_obs(f, obs + done * obs_dim, k, obs_dim);
+    if (rc) return rc;
+    PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+    for (int64_t i = 0; i < k; ++i) {
+      rc = enqueue_step(f);
+      if (rc) return rc;
+    }
+    PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+    rc = fetch_summaries(f, t0, k);
+    if (rc) return rc;
+    PZ_CUDA(cudaStreamSynchronize(f->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+    f->last_ms += ms;
+    for (int64_t i = 0; i < k; ++i) {
+      const pz_step_summary& s = f->h_summ[(t0 + i) % kObsRing];
+      if (out) out[done + i] = s;
+      if (s.total_weight == 0 && status == PZ_OK)
+        status = fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", (unsigned)(t0 + i));
+    }
+    done += k;
+  }
+  return status;
+}
+
+int pz_filter_last_timing(pz_filter* f, double* ms, int64_t* launches) {
+  if (!f) return fail(PZ_EINVAL, "null filter");
+  if (ms) *ms = f->last_ms;
+  if (launches) *launches = f->last_launches;
+  return PZ_OK;
+}
+
+int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len) {
+  if (!f || !out) return fail(PZ_EINVAL, "null argument");
+  const StepArgs& a = f->a;
+  if (out_len < a.model.nx * a.n_local) return fail(PZ_EINVAL, "buffer too small: need %lld floats", (long long)(a.model.nx * a.n_local));
+  PZ_CUDA(cudaSetDevice(f->device));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  const float* x = a.X[f->t & 1];
+  for (int d = 0; d < a.model.nx; ++d)
+    PZ_CUDA(cudaMemcpy(out + (size_t)d * a.n_local, x + (size_t)d * a.ld, a.n_local * sizeof(float), cudaMemcpyDeviceToHost));
+  return PZ_OK;
+}
+
+int pz_filter_read_logw(pz_filter* f, float* out, int64_t n) {
+  if (!f || !out) return fail(PZ_EINVAL, "null argument");
+  if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
+  PZ_CUDA(cudaSetDevice(f->device));
+  int rc = generic_alloc(&f->g, f->a.n_local, false);
+  if (rc) return rc;
+  launch_logw(f->a, f->g.lw, f->stream);
+  PZ_CUDA(cudaMemcpyAsync(out, f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  return PZ_OK;
+}
+
+int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n) {
+  if (!f || !out) return fail(PZ_EINVAL, "null argument");
+  if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
+  PZ_CUDA(cudaSetDevice(f->device));
+  int rc = pending_ancestors(f, nullptr);
+  if (rc) return rc;
+  PZ_CUDA(cudaMemcpyAsync(out, f->g.anc, f->a.n_local * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  return PZ_OK;
+}
+
+int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t out_len) {
+  if (!f || !out || stride < 1) return fail(PZ_EINVAL, "bad argument");
+  const StepArgs& a = f->a;
+  const int64_t n_sel = (a.n_local + stride - 1) / stride;
+  if (out_len < n_sel * a.model.nx) return fail(PZ_EINVAL, "buffer too small: need %lld doubles", (long long)(n_sel * a.model.nx));
+  PZ_CUDA(cudaSetDevice(f->device));
+  int rc = pending_ancestors(f, nullptr);
+  if (rc) return rc;
+  float* d_out = nullptr;
+  PZ_CUDA(cudaMalloc(&d_out, n_sel * a.model.nx * sizeof(float)));
+  launch_gather_thin(a, f->g.anc, stride, n_sel, d_out, f->stream);
+  std::vector<float> h((size_t)n_sel * a.model.nx);
+  cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(float), cudaMemcpyDeviceToHost, f->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(PZ_ECUDA, "read_particles: %s", cudaGetErrorString(e));
+  for (size_t i = 0; i < h.size(); ++i) out[i] = (double)h[i];
+  return PZ_OK;
+}
+
+void pz_filter_destroy(pz_filter* f) { free_filter(f); }
+
+// ---- standalone resamplers on stored log-weights --------------------------------------------
+static int standalone(const double* logw, int64_t n, bool multinomial, uint32_t U, uint64_t seed, uint32_t step,
+                      int32_t* anc_out) {
+  if (!logw || !anc_out || n < 1 || n > (1ll << 30)) return fail(PZ_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  GenericScratch gs;
+  int rc = generic_alloc(&gs, n, true);
+  if (rc) { gs.release(); return rc; }
+  std::vector<float> lw32((size_t)n);
+  for (int64_t i = 0; i < n; ++i) lw32[i] = (float)logw[i];
+  cudaStream_t s = nullptr;
+  GenericArgs g{};
+  g.lw = gs.lw; g.anc = gs.anc; g.eb = gs.eb; g.eb_alt = gs.eb; g.parity_ctl = nullptr; g.sb = gs.sb; g.pb = gs.pb;
+  g.tile_start = gs.tile_start; g.scan_status = gs.scan_status; g.scan_part = gs.scan_part; g.plan = gs.plan; g.ctl = gs.ctl;
+  g.n = n; g.nblk = (n + kBlk - 1) / kBlk;
+  g.ntiles_out = (int32_t)((n + kGenericTileOut - 1) / kGenericTileOut);
+  g.nscan = (int32_t)((g.nblk + kScanTile - 1) / kScanTile);
+  g.U = U; g.seed = seed; g.step = step;
+  PlanDev plan;
+  cudaError_t e = cudaMemcpy(gs.lw, lw32.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_ctl_reset(gs.ctl, s);
+    launch_generic_plan(g, true, s);
+    if (multinomial) launch_generic_multinomial(g, s);
+    else launch_generic_ancestors(g, s);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&plan, gs.plan, sizeof(plan), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && !plan.degenerate) e = cudaMemcpy(anc_out, gs.anc, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  gs.release();
+  if (e != cudaSuccess) return fail(PZ_ECUDA, "resample: %s", cudaGetErrorString(e));
+  if (plan.degenerate) return fail(PZ_EDEGENERATE, "every log-weight is -inf or NaN");
+  return PZ_OK;
+}
+
+int pz_resample_systematic(const double* logw, int64_t n, double u, int32_t* anc_out) {
+  if (!(u >= 0.0 && u < 1.0)) return fail(PZ_EINVAL, "u must be in [0, 1)");
+  return standalone(logw, n, false, (uint32_t)(u * 4294967296.0), 0, 0, anc_out);
+}
+
+int pz_resample_multinomial(const double* logw, int64_t n, uint64_t seed, uint32_t step, int32_t* anc_out) {
+  return standalone(logw, n, true, 0, seed, step, anc_out);
+}
+
+}  // extern "C"

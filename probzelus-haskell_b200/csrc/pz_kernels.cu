@@ -1,0 +1,966 @@
+// pz_kernels.cu -- hand-written sm_100a kernels of the streaming particle-filter step.
+//
+// One time step of zparticles' (haskell/src/Inference.hs:101-104) is three launches:
+//
+//   pf_step_tile<NX,NY,TO,FUSED>   per output tile of TO slots: merge-path locate the input
+//       blocks whose cumulative weight covers the tile, recompute their weights from state +
+//       previous observation (score/factor/observe, Distributions.hs:29-36,160-161;
+//       MVDistributions.hs:45-46), warp-scan them in 64-bit fixed point, scatter each
+//       parent into the shared-memory slots of its children (resample2 + `fst . (xs !!)`,
+//       Inference.hs:57-61, as a systematic resampler), then per child: Philox normals,
+//       x' = F x + L z (noisyIntegrateGen Demo.hs:184-187; SingleTargetTracking.hs:34;
+//       MultiTargetTracking.hs:56-67), the new log-weight, 128-bit coalesced stores of the
+//       state, and the block statistics (max exponent, fixed-point sum) + centred moment
+//       sums (average / weightedAverage, Util/Numeric.hs:7-22) of the new population.
+//   pf_scan_blocks     decoupled look-back exclusive scan of the block sums rescaled to the
+//       global exponent (normalize / shiftByMax, Inference.hs:63-66, Util/Numeric.hs:12-17),
+//       and, in the last CTA, the resampling plan and the posterior summary.
+//   pf_partition       merge-path split: first input block of every output tile.
+//
+// No tensor cores: the path is a streaming scan / gather with ~100 integer+fp32
+// instructions per particle; see DESIGN.md for the roofline discussion.
+#include "pz_kernels.cuh"
+#include "pz_math.cuh"
+
+namespace pz {
+
+typedef uint64_t u64;
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_up_u64(u64 v, int d) {
+  uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+  uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+  return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  return __longlong_as_double((long long)shfl_xor_u64((u64)__double_as_longlong(v), m));
+}
+__device__ __forceinline__ u64 warp_inclusive_scan(u64 v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u64 o = shfl_up_u64(v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+// 2^k as a double (0 when it would underflow; callers never pass k > 0 that overflows)
+__device__ __forceinline__ double pow2d(int k) {
+  if (k < -1022) return 0.0;
+  return __hiloint2double((1023 + k) << 20, 0);
+}
+
+struct SlotMap {  // output-slot position of a CDF value (DESIGN.md "Resampler")
+  uint32_t rho;
+  int32_t shift;
+  uint32_t U;
+  int64_t n_out;  // global number of output slots
+  __device__ __forceinline__ int64_t slot_end(u64 C) const {
+    u64 lo = (C & 0xffffffffull) * rho;
+    u64 hi = (C >> 32) * rho + (lo >> 32);  // bits 32.. of the 96-bit product
+    uint32_t lo32 = (uint32_t)lo;
+    u64 pos;
+    if (shift >= 32) pos = hi >> (shift - 32);
+    else if (shift > 0) pos = (hi << (32 - shift)) | (u64)(lo32 >> shift);
+    else pos = ((hi << 32) | lo32) << (-shift);
+    if (pos <= (u64)U) return 0;
+    u64 o = (pos - U + 0xFFFFFFFFull) >> 32;
+    return (int64_t)(o < (u64)n_out ? o : (u64)n_out);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// linear-Gaussian model step (same operation order as the oracle's lg_propagate / lg_logweight)
+// ------------------------------------------------------------------------------------------
+template <int NX>
+__device__ __forceinline__ void lg_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+#pragma unroll
+  for (int r = 0; r < NX; ++r) {
+    float acc = __fmul_rn(p.F[r][0], x[0]);
+#pragma unroll
+    for (int c = 1; c < NX; ++c) acc = __fmaf_rn(p.F[r][c], x[c], acc);
+#pragma unroll
+    for (int c = 0; c <= r; ++c) acc = __fmaf_rn(p.Lq[r][c], z[c], acc);
+    xn[r] = acc;
+  }
+}
+
+template <int NX, int NY>
+__device__ __forceinline__ float lg_logweight(const LgDev& p, const float* xn, const float* y) {
+  float d[NY];
+#pragma unroll
+  for (int k = 0; k < NY; ++k) {
+    float acc = __fmul_rn(p.H[k][0], xn[0]);
+#pragma unroll
+    for (int c = 1; c < NX; ++c) acc = __fmaf_rn(p.H[k][c], xn[c], acc);
+    d[k] = __fsub_rn(y[k], acc);
+  }
+  float quad = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NY; ++k) {
+    float t = __fmul_rn(p.Rinv[k][0], d[0]);
+#pragma unroll
+    for (int l = 1; l < NY; ++l) t = __fmaf_rn(p.Rinv[k][l], d[l], t);
+    quad = (k == 0) ? __fmul_rn(d[0], t) : __fmaf_rn(d[k], t, quad);
+  }
+  return __fmul_rn(p.wscale, quad);
+}
+
+// normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]
+template <int NX>
+__device__ __forceinline__ void lg_noise4(int64_t j, uint32_t t, uint64_t seed, float (&z)[NX][4]) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  if constexpr (NX == 1) {
+    U4 r = philox4x32_10((uint32_t)(j >> 2), 0u, t, kStreamProp, k0, k1);
+    normal_pair(r.x, r.y, z[0][0], z[0][1]);
+    normal_pair(r.z, r.w, z[0][2], z[0][3]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+#pragma unroll
+      for (int c = 0; 4 * c < NX; ++c) {
+        U4 r = philox4x32_10((uint32_t)(j + s), (uint32_t)c, t, kStreamProp, k0, k1);
+        float zz[4];
+        normal_pair(r.x, r.y, zz[0], zz[1]);
+        normal_pair(r.z, r.w, zz[2], zz[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (4 * c + i < NX) z[4 * c + i][s] = zz[i];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pf_init: the point-mass population before the first observation, with equal weights
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i < a.ld) {
+    for (int d = 0; d < a.model.nx; ++d) {
+      a.X[0][(size_t)d * a.ld + i] = a.model.x0[d];
+      a.X[1][(size_t)d * a.ld + i] = a.model.x0[d];
+    }
+  }
+  if (i < a.nblk) {
+    int64_t cnt = a.n_local - i * kBlk;
+    cnt = cnt > kBlk ? kBlk : cnt;
+    a.eb[0][i] = 0;
+    a.eb[1][i] = kNZero;
+    a.sb[i] = (u64)cnt << 31;  // q of lw = 0 is 2^23 << 8
+  }
+  if (i < a.nscan) a.scan_status[i] = 0ull;
+  if (i == 0) {
+    a.ctl->t = 0;
+    a.ctl->emax_acc = 0;
+    a.ctl->scan_counter = 0;
+    a.ctl->scan_done = 0;
+    a.ctl->uniform_in = 1;
+    for (int d = 0; d < 8; ++d) a.plan->center[d] = d < a.model.nx ? a.model.x0[d] : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pf_scan_blocks: single-pass decoupled look-back scan over the block sums
+// ------------------------------------------------------------------------------------------
+constexpr u64 kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
+
+struct ScanArgs {
+  const int32_t* eb0;  // block exponents of buffer 0 / 1; the population scanned is (ctl->t + delta) & 1
+  const int32_t* eb1;
+  const u64* sb;
+  u64* pb;
+  u64* status;
+  double* part;      // [nscan][kMaxRec]
+  const double* rec; // [nrec][kMaxRec] or nullptr
+  PlanDev* plan;
+  CtlDev* ctl;
+  pz_step_summary* summ;  // ring or nullptr
+  int64_t nblk;
+  int64_t n_out_global;
+  int64_t n_local;
+  int32_t nscan;
+  int32_t nrec;
+  int32_t nx;
+  int32_t delta;      // 0: population already current (init / generic); 1: produced by the fused step
+  int32_t explicit_U; // standalone API: use U_value instead of Philox
+  uint32_t U_value;
+  uint64_t seed;
+  double ll_const;
+  int32_t world;
+};
+
+__device__ void finalize_plan(const ScanArgs& s, u64 total) {
+  PlanDev* pl = s.plan;
+  pl->total = total;
+  pl->base = 0;
+  pl->degenerate = (total == 0);
+  if (total != 0) {
+    int L = 64 - __clzll((long long)total);
+    unsigned __int128 rho = (((unsigned __int128)(u64)s.n_out_global) << (32 + L)) / total + 1;
+    u64 rhi = (u64)(rho >> 64), rlo = (u64)rho;
+    int bl = rhi ? 128 - __clzll((long long)rhi) : 64 - __clzll((long long)rlo);
+    int a = bl > 31 ? bl - 31 : 0;
+    pl->rho = (uint32_t)(rho >> a) + 1u;
+    pl->shift = L - a;
+  } else {
+    pl->rho = 0; pl->shift = 0;
+  }
+  const uint32_t t_next = s.ctl->t + (uint32_t)s.delta;
+  if (s.explicit_U) pl->U = s.U_value;
+  else pl->U = philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)s.seed, (uint32_t)(s.seed >> 32)).x;
+}
+
+__global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
+  __shared__ u64 s_warp[kWarps];
+  __shared__ u64 s_prefix;
+  __shared__ uint32_t s_tile, s_last;
+  __shared__ double s_red[kWarps][kMaxRec];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&s.ctl->scan_counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int32_t emax = s.ctl->emax_acc;
+  const int32_t* __restrict__ ebp = ((s.ctl->t + (uint32_t)s.delta) & 1u) ? s.eb1 : s.eb0;
+
+  // ---- local scan of kScanItems block sums per thread
+  u64 v[kScanItems];
+  u64 tsum = 0;
+  const int64_t b0 = (int64_t)tile * kScanTile + (int64_t)tid * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t b = b0 + k;
+    u64 S = 0;
+    if (b < s.nblk) {
+      int32_t e = ebp[b];
+      if (e != kNZero) {
+        uint32_t sh = (uint32_t)(emax - e);
+        S = sh < 64u ? (s.sb[b] >> sh) : 0ull;
+      }
+    }
+    v[k] = S;
+    tsum += S;
+  }
+  u64 incl = warp_inclusive_scan(tsum, lane);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  u64 wbase = 0, agg = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    u64 x = s_warp[w];
+    if (w < warp) wbase += x;
+    agg += x;
+  }
+  u64 excl = wbase + incl - tsum;
+
+  // ---- decoupled look-back (warp 0)
+  if (warp == 0) {
+    volatile u64* st = s.status;
+    u64 prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) st[0] = kFlagIncl | agg;
+    } else {
+      if (lane == 0) st[tile] = kFlagAgg | agg;
+      int64_t look = (int64_t)tile - 1;
+      while (true) {
+        int64_t idx = look - lane;
+        u64 w = kFlagIncl;  // virtual inclusive zero before tile 0
+        if (idx >= 0) {
+          do { w = st[idx]; } while ((w >> 62) == 0);
+        }
+        uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        // lanes at or before the first inclusive entry contribute
+        int first = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        u64 c = (lane <= first) ? (w & kValMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += shfl_xor_u64(c, d);
+        prefix += c;
+        if (incl_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) st[tile] = kFlagIncl | (prefix + agg);
+    }
+    if (lane == 0) s_prefix = prefix;
+  }
+  __syncthreads();
+  const u64 prefix = s_prefix;
+  u64 run = prefix + excl;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t b = b0 + k;
+    if (b < s.nblk) s.pb[b] = run;
+    run += v[k];
+  }
+  if (tile == (uint32_t)(s.nscan - 1) && tid == kThreads - 1) {
+    s.pb[s.nblk] = prefix + agg;
+    s.plan->local_total = prefix + agg;
+  }
+
+  // ---- moment records -> per-CTA partial at the global exponent
+  const int R = 3 + 2 * s.nx;
+  const bool have_rec = (s.rec != nullptr) && (s.nrec > 0) && !(s.delta == 0);
+  if (have_rec) {
+    double acc[kMaxRec];
+#pragma unroll
+    for (int r = 0; r < kMaxRec; ++r) acc[r] = 0.0;
+    const int rpc = (s.nrec + s.nscan - 1) / s.nscan;
+    for (int q = tid; q < rpc; q += kThreads) {
+      int64_t J = (int64_t)tile * rpc + q;
+      if (J < s.nrec) {
+        const double* rc = s.rec + (size_t)J * kMaxRec;
+        double et = rc[0];
+        if (et > -2.0e9) {
+          double f = pow2d((int)et - emax);
+          for (int r = 1; r < R; ++r) acc[r] += rc[r] * (r == 2 ? f * f : f);
+        }
+      }
+    }
+    for (int r = 1; r < R; ++r) {
+      double x = acc[r];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
+      if (lane == 0) s_red[warp][r] = x;
+    }
+    __syncthreads();
+    if (tid >= 1 && tid < R) {
+      double x = 0;
+      for (int w = 0; w < kWarps; ++w) x += s_red[w][tid];
+      s.part[(size_t)tile * kMaxRec + tid] = x;
+    }
+  }
+
+  // ---- last CTA: plan + posterior summary
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&s.ctl->scan_done, 1u) == (uint32_t)(s.nscan - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_tot[kMaxRec];
+  if (have_rec && tid >= 1 && tid < R) {
+    double x = 0;
+    for (int c = 0; c < s.nscan; ++c) x += ((volatile double*)s.part)[(size_t)c * kMaxRec + tid];
+    s_tot[tid] = x;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    PlanDev* pl = s.plan;
+    const u64 total = ((volatile PlanDev*)pl)->local_total;
+    pl->emax = emax;
+    if (s.world <= 1) finalize_plan(s, total);
+    if (have_rec) {
+      const double sw = s_tot[1], sw2 = s_tot[2];
+      pl->sw = sw; pl->sw2 = sw2;
+      pl->log_sw = log(sw) + (double)(emax - 31) * 0.6931471805599453;
+      float cen[PZ_MAX_NX];
+      for (int d = 0; d < s.nx; ++d) {
+        cen[d] = pl->center[d];
+        double m = s_tot[3 + d] / sw;
+        pl->mean[d] = (double)cen[d] + m;
+        pl->var[d] = s_tot[3 + s.nx + d] / sw - m * m;
+      }
+      if (s.world <= 1) {
+        for (int d = 0; d < s.nx; ++d) pl->center[d] = (float)pl->mean[d];
+        if (s.summ) {
+          pz_step_summary* o = s.summ + (s.ctl->t % kObsRing);
+          o->step = s.ctl->t;
+          o->log_evidence_inc = pl->log_sw - log((double)s.n_out_global) + s.ll_const;
+          o->ess = sw * sw / sw2;
+          for (int d = 0; d < PZ_MAX_NX; ++d) { o->mean[d] = d < s.nx ? pl->mean[d] : 0.0; o->var[d] = d < s.nx ? pl->var[d] : 0.0; }
+          o->n_migrated = 0;
+          o->e_max = emax;
+          o->reserved = 0;
+          o->total_weight = total;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pf_partition: first input block of every output tile + per-step counter maintenance
+// ------------------------------------------------------------------------------------------
+struct PartArgs {
+  const u64* pb;
+  int32_t* tile_start;
+  u64* status;
+  const PlanDev* plan;
+  CtlDev* ctl;
+  int64_t nblk;
+  int64_t slot_base;
+  int64_t n_out_global;
+  int32_t ntiles_out;
+  int32_t tile_out;
+  int32_t nscan;
+  int32_t delta;
+};
+
+__global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
+  const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const PlanDev* pl = p.plan;
+  if (J < p.ntiles_out) {
+    SlotMap sm{pl->rho, pl->shift, pl->U, p.n_out_global};
+    const u64 base = pl->base;
+    const int64_t j0 = p.slot_base + J * p.tile_out;
+    // min b in [0, nblk) with slot_end(base + pb[b+1]) > j0
+    int64_t lo = 0, hi = p.nblk;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (sm.slot_end(base + p.pb[mid + 1]) > j0) hi = mid; else lo = mid + 1;
+    }
+    p.tile_start[J] = (int32_t)lo;
+  }
+  if (J < p.nscan) p.status[J] = 0ull;
+  if (J == 0) {
+    p.ctl->t += (uint32_t)p.delta;
+    p.ctl->emax_acc = kNZero;
+    p.ctl->scan_counter = 0;
+    p.ctl->scan_done = 0;
+    if (p.delta) p.ctl->uniform_in = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pf_step_tile: the fused resample + gather + propagate + weight kernel
+// ------------------------------------------------------------------------------------------
+// Input side: one warp owns one canonical input block at a time (two half-blocks of 128
+// particles, one float4 per lane per state dimension => 512-byte coalesced requests).
+template <int NX, int NY>
+struct StateSource {
+  const float* x;      // X[cur]
+  int64_t ld, n_local;
+  const LgDev* m;
+  float y[NY];
+  bool uniform;
+  float v[NX][4];
+  __device__ __forceinline__ void load(int64_t i0, int32_t (&n)[4], uint32_t (&mm)[4]) {
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      float4 q = *reinterpret_cast<const float4*>(x + (size_t)d * ld + i0);
+      v[d][0] = q.x; v[d][1] = q.y; v[d][2] = q.z; v[d][3] = q.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n_local) {
+        if (uniform) { n[k] = 0; mm[k] = 1u << 23; }
+        else {
+          float xs[NX];
+#pragma unroll
+          for (int d = 0; d < NX; ++d) xs[d] = v[d][k];
+          weight_split(lg_logweight<NX, NY>(*m, xs, y), n[k], mm[k]);
+        }
+      } else { n[k] = kNZero; mm[k] = 0; }
+    }
+  }
+  __device__ __forceinline__ void put(float* s_par, int stride, int slot, int k, int64_t) const {
+#pragma unroll
+    for (int d = 0; d < NX; ++d) s_par[d * stride + slot] = v[d][k];
+  }
+};
+
+struct LogwSource {  // generic path: stored log-weights, payload = particle index
+  const float* lw;
+  int64_t n_local;
+  __device__ __forceinline__ void load(int64_t i0, int32_t (&n)[4], uint32_t (&mm)[4]) {
+    float4 q = *reinterpret_cast<const float4*>(lw + i0);
+    float w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n_local) weight_split(w[k], n[k], mm[k]);
+      else { n[k] = kNZero; mm[k] = 0; }
+    }
+  }
+  __device__ __forceinline__ void put(float* s_par, int, int slot, int k, int64_t i0) const {
+    reinterpret_cast<int32_t*>(s_par)[slot] = (int32_t)(i0 + k);
+  }
+};
+
+// Resample phase shared by the fused and the ancestor kernels: fills the shared-memory parent
+// slots of output tile [j0, jend).
+template <class Source>
+__device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const int32_t* eb_in,
+                                              const u64* pb, int64_t nblk, int64_t b_first, const SlotMap& sm,
+                                              u64 base, int32_t emax, int64_t j0, int64_t jend, int lane, int warp) {
+  for (int64_t b = b_first + warp; b < nblk; b += kWarps) {
+    const u64 Pb = base + pb[b];
+    int64_t o_blk = sm.slot_end(Pb);
+    if (o_blk >= jend) break;  // this and every later block start past the tile
+    const int32_t eb = eb_in[b];
+    if (eb == kNZero) continue;
+    const uint32_t ksh = (uint32_t)(emax - eb);
+    if (ksh >= 64u) continue;
+    u64 carry = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int64_t i0 = b * kBlk + half * 128 + lane * 4;
+      int32_t n[4]; uint32_t m[4];
+      src.load(i0, n, m);
+      u64 c[4];
+      u64 run = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { run += q_at(m[k], n[k], eb); c[k] = run; }
+      const u64 incl = warp_inclusive_scan(run, lane);
+      const u64 excl = carry + incl - run;
+      carry += shfl_u64(incl, 31);
+      int64_t o_lo = sm.slot_end(Pb + (excl >> ksh));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool has = (k == 0) ? (c[0] != 0) : (c[k] != c[k - 1]);
+        if (has) {
+          const int64_t o_hi = sm.slot_end(Pb + ((excl + c[k]) >> ksh));
+          const int64_t lo = o_lo > j0 ? o_lo : j0;
+          const int64_t hi = o_hi < jend ? o_hi : jend;
+          for (int64_t sl = lo; sl < hi; ++sl) src.put(s_par, stride, (int)(sl - j0), k, i0);
+          o_lo = o_hi;
+        }
+      }
+    }
+  }
+}
+
+struct TileArgs {
+  StepArgs a;
+  const int32_t* anc;  // MODE 1: parents by stored ancestor index
+};
+
+// MODE 0: fused systematic resample (parents staged by resample_tile)
+// MODE 1: parents gathered through a stored ancestor array (multinomial / debug path)
+template <int NX, int NY, int TO, int MODE>
+__global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__ TileArgs ta) {
+  extern __shared__ __align__(16) float s_par[];  // [NX][TO]
+  __shared__ int32_t s_eref[kWarps];
+  __shared__ double s_red[kWarps][kMaxRec];
+  const StepArgs& a = ta.a;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t t = a.ctl->t;
+  const int cur = t & 1, nxt = cur ^ 1;
+  const float* __restrict__ xin = a.X[cur];
+  float* __restrict__ xout = a.X[nxt];
+  const PlanDev* pl = a.plan;
+  const int64_t j0l = (int64_t)blockIdx.x * TO;  // local slot
+  const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
+  const int64_t j0 = a.slot_base + j0l, jend = a.slot_base + jendl;
+  const int nslots = (int)(jendl - j0l);
+
+  float y_new[NY];
+#pragma unroll
+  for (int k = 0; k < NY; ++k) y_new[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
+
+  if constexpr (MODE == 0) {
+    SlotMap sm{pl->rho, pl->shift, pl->U, a.n_global};
+    StateSource<NX, NY> src;
+    src.x = xin; src.ld = a.ld; src.n_local = a.n_local; src.m = &a.model;
+    src.uniform = a.ctl->uniform_in != 0;
+    const uint32_t tp = (t + kObsRing - 1) % kObsRing;
+#pragma unroll
+    for (int k = 0; k < NY; ++k) src.y[k] = a.obs[(size_t)tp * PZ_MAX_NY + k];
+    resample_tile(src, s_par, TO, a.eb[cur], a.pb, a.nblk, (int64_t)a.tile_start[blockIdx.x], sm, pl->base,
+                  pl->emax, j0, jend, lane, warp);
+  } else {
+    for (int sidx = tid; sidx < nslots; sidx += kThreads) {
+      const int64_t p = ta.anc[j0l + sidx];
+#pragma unroll
+      for (int d = 0; d < NX; ++d) s_par[d * TO + sidx] = xin[(size_t)d * a.ld + p];
+    }
+  }
+  __syncthreads();
+
+  // ---- output side: one warp owns one canonical output block (two halves of 128 slots)
+  double acc_sw = 0, acc_sw2 = 0, acc_sx[NX], acc_sxx[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) { acc_sx[d] = 0; acc_sxx[d] = 0; }
+  int32_t aref = kNZero;
+  float cen[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) cen[d] = pl->center[d];
+
+  for (int ob = warp; ob * kBlk < nslots; ob += kWarps) {
+    int32_t nn[8]; uint32_t mm[8];
+    int32_t emx = kNZero;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
+      float xp[NX][4], z[NX][4];
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        float4 q = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
+        xp[d][0] = q.x; xp[d][1] = q.y; xp[d][2] = q.z; xp[d][3] = q.w;
+      }
+      lg_noise4<NX>(j0 + sl, t, a.seed, z);
+      float xo[NX][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float xs[NX], zs[NX], xn[NX];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
+        lg_propagate<NX>(a.model, xs, zs, xn);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
+        if (sl + k < nslots) {
+          weight_split(lg_logweight<NX, NY>(a.model, xn, y_new), nn[half * 4 + k], mm[half * 4 + k]);
+          if (mm[half * 4 + k] && nn[half * 4 + k] > emx) emx = nn[half * 4 + k];
+        } else { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
+      }
+      if (sl < nslots) {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          float4 q = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
+          *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = q;
+          *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = q;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      int32_t o = __shfl_xor_sync(0xffffffffu, emx, d);
+      emx = o > emx ? o : emx;
+    }
+    // block sum at the block exponent + centred moments at the warp's running exponent
+    u64 ssum = 0;
+    if (emx != kNZero) {
+      double f = 1.0;
+      if (aref == kNZero) aref = emx;
+      else if (emx > aref) {
+        double g = pow2d(aref - emx);
+        acc_sw *= g; acc_sw2 *= g * g;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) { acc_sx[d] *= g; acc_sxx[d] *= g; }
+        aref = emx;
+      } else f = pow2d(emx - aref);
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int sl = ob * kBlk + half * 128 + lane * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t q = q_at(mm[half * 4 + k], nn[half * 4 + k], emx);
+          ssum += q;
+          if (q) {
+            const double w = (double)q * f;
+            acc_sw += w; acc_sw2 += w * w;
+#pragma unroll
+            for (int d = 0; d < NX; ++d) {
+              const double dx = (double)__fsub_rn(s_par[d * TO + sl + k], cen[d]);
+              const double wd = w * dx;
+              acc_sx[d] += wd; acc_sxx[d] += wd * dx;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ssum += shfl_xor_u64(ssum, d);
+    if (lane == 0) {
+      const int64_t bo = (j0l / kBlk) + ob;
+      a.eb[nxt][bo] = emx;
+      a.sb[bo] = ssum;
+    }
+  }
+
+  // ---- CTA-level reduction of the moment sums -> one record per tile
+  if (lane == 0) s_eref[warp] = aref;
+  __syncthreads();
+  int32_t etile = kNZero;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) etile = s_eref[w] > etile ? s_eref[w] : etile;
+  {
+    const double g = (aref == kNZero) ? 0.0 : pow2d(aref - etile);
+    double vals[kMaxRec];
+    vals[0] = 0; vals[1] = acc_sw * g; vals[2] = acc_sw2 * g * g;
+#pragma unroll
+    for (int d = 0; d < NX; ++d) { vals[3 + d] = acc_sx[d] * g; vals[3 + NX + d] = acc_sxx[d] * g; }
+#pragma unroll
+    for (int r = 1; r < 3 + 2 * NX; ++r) {
+      double x = vals[r];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
+      if (lane == 0) s_red[warp][r] = x;
+    }
+  }
+  __syncthreads();
+  if (tid < 3 + 2 * NX) {
+    double x = 0;
+    if (tid == 0) x = (double)etile;
+    else for (int w = 0; w < kWarps; ++w) x += s_red[w][tid];
+    a.rec[(size_t)blockIdx.x * kMaxRec + tid] = x;
+  }
+  if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
+}
+
+// ------------------------------------------------------------------------------------------
+// generic path kernels (stored log-weights)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) pf_stats_from_lw(const float* __restrict__ lw, int64_t n, int64_t nblk,
+                                                             int32_t* eb, u64* sb, CtlDev* ctl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * kWarps + warp;
+  if (b >= nblk) return;
+  int32_t nn[8]; uint32_t mm[8];
+  int32_t emx = kNZero;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int64_t i0 = b * kBlk + half * 128 + lane * 4;
+    float4 q = *reinterpret_cast<const float4*>(lw + i0);
+    float w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) weight_split(w[k], nn[half * 4 + k], mm[half * 4 + k]);
+      else { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
+      if (mm[half * 4 + k] && nn[half * 4 + k] > emx) emx = nn[half * 4 + k];
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    int32_t o = __shfl_xor_sync(0xffffffffu, emx, d);
+    emx = o > emx ? o : emx;
+  }
+  u64 ssum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ssum += q_at(mm[k], nn[k], emx);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ssum += shfl_xor_u64(ssum, d);
+  if (lane == 0) {
+    eb[b] = emx;
+    sb[b] = ssum;
+    if (emx != kNZero) atomicMax(&ctl->emax_acc, emx);
+  }
+}
+
+__device__ __forceinline__ const int32_t* generic_eb(const GenericArgs& g) {
+  return (g.parity_ctl && (g.parity_ctl->t & 1u)) ? g.eb_alt : g.eb;
+}
+
+__global__ void pf_ctl_reset(CtlDev* ctl) {
+  ctl->t = 0; ctl->emax_acc = kNZero; ctl->scan_counter = 0; ctl->scan_done = 0; ctl->uniform_in = 0;
+}
+
+template <int TO>
+__global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
+  __shared__ __align__(16) int32_t s_anc[TO];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const PlanDev* pl = g.plan;
+  const int64_t j0 = (int64_t)blockIdx.x * TO;
+  const int64_t jend = (j0 + TO < g.n) ? j0 + TO : g.n;
+  SlotMap sm{pl->rho, pl->shift, pl->U, g.n};
+  LogwSource src{g.lw, g.n};
+  for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = -1;
+  __syncthreads();
+  resample_tile(src, reinterpret_cast<float*>(s_anc), TO, generic_eb(g), g.pb, g.nblk, (int64_t)g.tile_start[blockIdx.x], sm,
+                pl->base, pl->emax, j0, jend, lane, warp);
+  __syncthreads();
+  for (int sidx = tid; j0 + sidx < jend; sidx += kThreads) g.anc[j0 + sidx] = s_anc[sidx];
+}
+
+// N iid categorical draws on the canonical fixed-point CDF (resample2, Inference.hs:57-61)
+__global__ void __launch_bounds__(kThreads) pf_multinomial(const GenericArgs g) {
+  const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= g.n) return;
+  const PlanDev* pl = g.plan;
+  const u64 total = pl->total;
+  U4 r = philox4x32_10((uint32_t)j, 0u, g.step, kStreamMulti, (uint32_t)g.seed, (uint32_t)(g.seed >> 32));
+  const u64 u = ((u64)r.x << 32) | r.y;
+  const u64 tau = __umul64hi(u, total);
+  // largest b with pb[b] <= tau
+  int64_t lo = 0, hi = g.nblk;  // invariant: pb[lo] <= tau < pb[hi]
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (g.pb[mid] <= tau) lo = mid; else hi = mid;
+  }
+  const int64_t b = lo;
+  const int32_t eb = generic_eb(g)[b];
+  const uint32_t ksh = (uint32_t)(pl->emax - eb);
+  const u64 Pb = g.pb[b];
+  u64 c = 0;
+  int64_t i = b * kBlk, iend = (b + 1) * kBlk < g.n ? (b + 1) * kBlk : g.n;
+  int32_t res = (int32_t)(iend - 1);
+  for (; i < iend; ++i) {
+    int32_t n; uint32_t m;
+    weight_split(g.lw[i], n, m);
+    c += q_at(m, n, eb);
+    if (Pb + (c >> ksh) > tau) { res = (int32_t)i; break; }
+  }
+  g.anc[j] = res;
+}
+
+template <int NX, int NY>
+__global__ void __launch_bounds__(kThreads) pf_logw(StepArgs a, float* lw_out) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.n_local) return;
+  const uint32_t t = a.ctl->t;
+  if (a.ctl->uniform_in) { lw_out[i] = 0.0f; return; }
+  const float* x = a.X[t & 1];
+  const uint32_t tp = (t + kObsRing - 1) % kObsRing;
+  float xs[NX], y[NY];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) xs[d] = x[(size_t)d * a.ld + i];
+#pragma unroll
+  for (int k = 0; k < NY; ++k) y[k] = a.obs[(size_t)tp * PZ_MAX_NY + k];
+  lw_out[i] = lg_logweight<NX, NY>(a.model, xs, y);
+}
+
+__global__ void __launch_bounds__(kThreads) pf_gather_thin(StepArgs a, const int32_t* anc, int32_t stride, int64_t n_sel,
+                                                           float* out) {
+  const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (s >= n_sel) return;
+  const float* x = a.X[a.ctl->t & 1];
+  const int64_t p = anc[s * stride];
+  for (int d = 0; d < a.model.nx; ++d) out[s * a.model.nx + d] = x[(size_t)d * a.ld + p];
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+int fused_tile_out(int nx) { return nx == 1 ? 4096 : 2048; }
+
+int launch_init(const StepArgs& a, cudaStream_t s) {
+  int64_t m = a.ld > a.nblk ? a.ld : a.nblk;
+  pf_init<<<cdiv(m, kThreads), kThreads, 0, s>>>(a);
+  return 1;
+}
+
+static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s);
+
+static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
+  ScanArgs sc{};
+  sc.eb0 = a.eb[0]; sc.eb1 = a.eb[1];
+  sc.sb = a.sb; sc.pb = a.pb; sc.status = a.scan_status; sc.part = a.scan_part;
+  sc.rec = with_rec ? a.rec : nullptr;
+  sc.plan = a.plan; sc.ctl = a.ctl; sc.summ = a.summ;
+  sc.nblk = a.nblk; sc.n_out_global = a.n_global; sc.n_local = a.n_local;
+  sc.nscan = a.nscan; sc.nrec = a.ntiles_out; sc.nx = a.model.nx; sc.delta = delta;
+  sc.explicit_U = 0; sc.U_value = 0; sc.seed = a.seed; sc.ll_const = a.ll_const; sc.world = a.world;
+  return sc;
+}
+
+// Scan + partition of the population in buffer (ctl->t + delta) & 1.  delta = 1 after a step.
+static int scan_partition(const StepArgs& a, int delta, int tile_out, cudaStream_t s) {
+  ScanArgs sc = make_scan(a, delta, delta == 1);
+  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  partition(a, tile_out, delta, s);
+  return 2;
+}
+
+static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
+  PartArgs pa{a.pb, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
+              a.ntiles_out, tile_out, a.nscan, delta};
+  int nthreads = a.ntiles_out > a.nscan ? a.ntiles_out : a.nscan;
+  pf_partition<<<cdiv(nthreads, kThreads), kThreads, 0, s>>>(pa);
+  return 1;
+}
+
+int launch_partition_only(const StepArgs& a, int tile_out, cudaStream_t s) { return partition(a, tile_out, 0, s); }
+
+int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
+  return scan_partition(a, 0, tile_out, s);
+}
+
+template <int NX, int NY, int TO, int MODE>
+static void launch_tile(const TileArgs& ta, cudaStream_t s) {
+  auto kern = pf_step_tile<NX, NY, TO, MODE>;
+  size_t smem = (size_t)NX * TO * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  kern<<<ta.a.ntiles_out, kThreads, smem, s>>>(ta);
+}
+
+// anc == nullptr: fused systematic step; else parents come from the stored ancestor array.
+int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s) {
+  TileArgs ta{a, anc};
+  const int nx = a.model.nx, ny = a.model.ny;
+  const bool fused = (anc == nullptr);
+#define PZ_DISPATCH(NXv, NYv, TOv)                                   \
+  if (nx == NXv && ny == NYv) {                                      \
+    if (fused) launch_tile<NXv, NYv, TOv, 0>(ta, s);                 \
+    else launch_tile<NXv, NYv, TOv, 1>(ta, s);                       \
+  } else
+  PZ_DISPATCH(1, 1, 4096)
+  PZ_DISPATCH(4, 2, 2048)
+  PZ_DISPATCH(6, 3, 2048)
+  { return -1; }
+#undef PZ_DISPATCH
+  return 1 + scan_partition(a, 1, fused_tile_out(nx), s);
+}
+
+int launch_ctl_reset(CtlDev* ctl, cudaStream_t s) {
+  pf_ctl_reset<<<1, 1, 0, s>>>(ctl);
+  return 1;
+}
+
+int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
+  TileArgs ta{a, nullptr};
+  const int nx = a.model.nx, ny = a.model.ny;
+  cudaEventRecord(ev[0], s);
+  if (nx == 1 && ny == 1) launch_tile<1, 1, 4096, 0>(ta, s);
+  else if (nx == 4 && ny == 2) launch_tile<4, 2, 2048, 0>(ta, s);
+  else if (nx == 6 && ny == 3) launch_tile<6, 3, 2048, 0>(ta, s);
+  else return -1;
+  cudaEventRecord(ev[1], s);
+  ScanArgs sc = make_scan(a, 1, true);
+  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  cudaEventRecord(ev[2], s);
+  partition(a, fused_tile_out(nx), 1, s);
+  cudaEventRecord(ev[3], s);
+  return 3;
+}
+
+int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s) {
+  int n = 0;
+  if (stats_from_lw) {
+    pf_stats_from_lw<<<cdiv(g.nblk, kWarps), kThreads, 0, s>>>(g.lw, g.n, g.nblk, g.eb, g.sb, g.ctl);
+    ++n;
+  }
+  ScanArgs sc{};
+  sc.eb0 = g.eb; sc.eb1 = g.eb; sc.sb = g.sb; sc.pb = g.pb; sc.status = g.scan_status; sc.part = g.scan_part; sc.rec = nullptr;
+  sc.plan = g.plan; sc.ctl = g.ctl; sc.summ = nullptr; sc.nblk = g.nblk; sc.n_out_global = g.n; sc.n_local = g.n;
+  sc.nscan = g.nscan; sc.nrec = 0; sc.nx = 0; sc.delta = 0; sc.explicit_U = 1; sc.U_value = g.U; sc.seed = g.seed;
+  sc.ll_const = 0; sc.world = 1;
+  pf_scan_blocks<<<g.nscan, kThreads, 0, s>>>(sc);
+  PartArgs pa{g.pb, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
+  int nthreads = g.ntiles_out > g.nscan ? g.ntiles_out : g.nscan;
+  pf_partition<<<cdiv(nthreads, kThreads), kThreads, 0, s>>>(pa);
+  return n + 2;
+}
+
+int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s) {
+  pf_ancestors<kGenericTileOut><<<g.ntiles_out, kThreads, 0, s>>>(g);
+  return 1;
+}
+
+int launch_generic_multinomial(const GenericArgs& g, cudaStream_t s) {
+  pf_multinomial<<<cdiv(g.n, kThreads), kThreads, 0, s>>>(g);
+  return 1;
+}
+
+int launch_logw(const StepArgs& a, float* lw_out, cudaStream_t s) {
+  const int nx = a.model.nx, ny = a.model.ny;
+  int grid = cdiv(a.n_local, kThreads);
+  if (nx == 1 && ny == 1) pf_logw<1, 1><<<grid, kThreads, 0, s>>>(a, lw_out);
+  else if (nx == 4 && ny == 2) pf_logw<4, 2><<<grid, kThreads, 0, s>>>(a, lw_out);
+  else if (nx == 6 && ny == 3) pf_logw<6, 3><<<grid, kThreads, 0, s>>>(a, lw_out);
+  else return -1;
+  return 1;
+}
+
+int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, float* out,
+                       cudaStream_t s) {
+  pf_gather_thin<<<cdiv(n_sel, kThreads), kThreads, 0, s>>>(a, anc, stride, n_sel, out);
+  return 1;
+}
+
+}  // namespace pz

@@ -1,0 +1,137 @@
+// pz_kernels.cuh -- device data structures and kernel entry points of the particle-filter
+// step (one time step of zparticles', haskell/src/Inference.hs:101-104).
+//
+// HBM layout (per device, fp32 structure-of-arrays, all arrays padded to kPad particles):
+//   X[2][NX][ld]    particle state, double-buffered: step t reads X[t&1], writes X[(t+1)&1]
+//   eb[2][nblk]     per canonical block (256 particles): block exponent E_b
+//   sb[nblk]        per block: sum of the fixed-point weights at the block's own scale
+//   pb[nblk+1]      exclusive prefix of the block sums rescaled to the global exponent
+//   tile_start[]    first input block of every output tile (merge-path partition)
+//   rec[]           per output tile: centred moment partial sums for the posterior summary
+// Log-weights and ancestors are never stored on the fused path: the weight of a particle is
+// recomputed from its state and the observation it was weighted against, and the ancestor
+// gather is staged through shared memory inside the same kernel that propagates the child.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/pzgpu.h"
+
+namespace pz {
+
+constexpr int kBlk = 256;        // canonical resampling block (particles)
+constexpr int kThreads = 256;    // CTA size of every kernel
+constexpr int kWarps = kThreads / 32;
+constexpr int kScanItems = 8;    // block sums per thread in pf_scan_blocks
+constexpr int kScanTile = kThreads * kScanItems;
+constexpr int kPad = 2048;       // allocation granularity in particles
+constexpr int kObsRing = 4096;   // rows of the device observation / summary rings
+constexpr int kMaxRec = 3 + 2 * PZ_MAX_NX;  // doubles per moment record
+
+// Derived fp32 parameters of the linear-Gaussian family (RW1D = LG(1,1)).
+struct LgDev {
+  float F[PZ_MAX_NX][PZ_MAX_NX];
+  float Lq[PZ_MAX_NX][PZ_MAX_NX];
+  float H[PZ_MAX_NY][PZ_MAX_NX];
+  float Rinv[PZ_MAX_NY][PZ_MAX_NY];
+  float x0[PZ_MAX_NX];
+  float wscale;
+  int32_t nx, ny;
+};
+
+// Resampling plan + posterior summary of one weighted population (device resident).
+struct PlanDev {
+  uint64_t total;       // T: global fixed-point total
+  uint64_t base;        // CDF offset of this rank's first particle (0 on one GPU)
+  uint64_t local_total; // this rank's share of T
+  uint32_t rho;         // slot-position multiplier (31 significant bits)
+  int32_t shift;        // pos = (C * rho) >> shift   (<< when negative)
+  int32_t emax;         // global block exponent
+  int32_t degenerate;   // 1 when T == 0
+  uint32_t U;           // the uniform of the resample that will consume this plan
+  uint32_t pad0;
+  float center[8];      // fp32 posterior mean: centring constants of the next moment sums
+  double sw, sw2;       // sum w, sum w^2 at scale 2^(emax-31)
+  double mean[PZ_MAX_NX], var[PZ_MAX_NX];
+  double log_sw;        // log(sum w) + (emax-31) ln 2
+};
+
+// Step counter and accumulators living in device memory so that one captured CUDA graph
+// serves every step.
+struct CtlDev {
+  uint32_t t;             // index of the observation the NEXT fused step assimilates
+  int32_t emax_acc;       // atomicMax target of the kernel producing block statistics
+  uint32_t scan_counter;  // dynamic tile ids of pf_scan_blocks
+  uint32_t scan_done;     // "last CTA" counter of pf_scan_blocks
+  uint32_t uniform_in;    // 1 while the pending population is the initial point mass
+  uint32_t pad[3];
+};
+
+struct StepArgs {
+  float* X[2];
+  int32_t* eb[2];
+  uint64_t* sb;
+  uint64_t* pb;
+  int32_t* tile_start;
+  double* rec;             // [ntiles_out][kMaxRec]
+  uint64_t* scan_status;   // [nscan]
+  double* scan_part;       // [nscan][kMaxRec]
+  PlanDev* plan;
+  CtlDev* ctl;
+  const float* obs;        // ring [kObsRing][PZ_MAX_NY]
+  pz_step_summary* summ;   // ring [kObsRing]
+  int64_t ld;              // leading dimension of X (particles)
+  int64_t n_local;         // particles on this rank (input and output)
+  int64_t n_global;
+  int64_t slot_base;       // global index of this rank's first slot / particle
+  int64_t nblk;            // local canonical blocks
+  int32_t ntiles_out;      // output tiles of the fused kernel
+  int32_t nscan;           // CTAs of pf_scan_blocks
+  uint64_t seed;
+  double ll_const;
+  int32_t resampler;
+  int32_t world;           // > 1: the plan is finalised by pf_plan_sharded after the all-gather
+  LgDev model;
+};
+
+// Host-callable launchers (pz_kernels.cu).  Each returns the number of kernels it enqueued.
+int launch_init(const StepArgs& a, cudaStream_t s);
+int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s);
+int launch_partition_only(const StepArgs& a, int tile_out, cudaStream_t s);  // a.tile_start / a.ntiles_out for another tile size
+int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s);  // step tile kernel + scan + partition
+int fused_tile_out(int nx);
+// same as launch_step(a, nullptr, s) with an event recorded after each of the three kernels
+int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]);
+
+// Generic (stored log-weight) path: standalone resampler, ancestor taps, visualiser read.
+struct GenericArgs {
+  const float* lw;       // [n]
+  int32_t* anc;          // [n_out]
+  int32_t* eb;           // block exponents (standalone) ...
+  int32_t* eb_alt;       // ... or, with parity_ctl set, eb / eb_alt = the filter's buffers 0 / 1
+  const CtlDev* parity_ctl;
+  uint64_t* sb;
+  uint64_t* pb;
+  int32_t* tile_start;
+  uint64_t* scan_status;
+  double* scan_part;
+  PlanDev* plan;
+  CtlDev* ctl;
+  int64_t n;
+  int64_t nblk;
+  int32_t ntiles_out;
+  int32_t nscan;
+  uint32_t U;            // explicit uniform (standalone API)
+  uint64_t seed;         // multinomial
+  uint32_t step;
+};
+int launch_ctl_reset(CtlDev* ctl, cudaStream_t s);
+int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s);
+int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s);
+int launch_generic_multinomial(const GenericArgs& g, cudaStream_t s);
+int launch_logw(const StepArgs& a, float* lw_out, cudaStream_t s);  // log-weights of the pending population
+int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, float* out,
+                       cudaStream_t s);
+constexpr int kGenericTileOut = 2048;
+
+}  // namespace pz

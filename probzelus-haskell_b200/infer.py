@@ -1,0 +1,276 @@
+"""ctypes binding of libpzgpu.so and the `infer`-style stream API.
+
+Reference interface mirrored here (names and argument meaning kept):
+
+    zparticles   :: Int -> ZStream (Weighted m) a b -> ZStream m a [b]   Inference.hs:107-108
+    zdsparticles :: Int -> ZStream (StateT Heap (Weighted m)) a b -> ..  Inference.hs:113-114
+    ZStream { step :: a -> f (ZStream f a b, b) }                        Util/ZStream.hs:16
+    runStream    :: (a -> m ()) -> ZStream m () a -> m ()                Util/ZStream.hs:65-69
+
+The model argument is a kernel-side descriptor instead of a Haskell closure.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PZ_MAX_NX, PZ_MAX_NY = 6, 3
+PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF = 0, 1
+_ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENCCL", -4: "EDEGENERATE", -5: "ECAPACITY", -6: "ENOMEM", -7: "ESTATE"}
+
+
+class PzError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"PZ_{_ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class MttParams(C.Structure):
+    _fields_ = [("clutter_lambda", C.c_double), ("new_track_lambda", C.c_double), ("pd", C.c_double),
+                ("survival_prob", C.c_double), ("clutter_var", C.c_double), ("birth_pos_var", C.c_double),
+                ("birth_vel_var", C.c_double), ("meas_var", C.c_double), ("k_max", C.c_int32),
+                ("m_max", C.c_int32)]
+
+
+class ModelDesc(C.Structure):
+    """pz_model_desc (include/pzgpu.h)."""
+    _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
+                ("resampler", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
+                ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
+                ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]
+
+
+class StepSummary(C.Structure):
+    """pz_step_summary (include/pzgpu.h)."""
+    _fields_ = [("step", C.c_int64), ("log_evidence_inc", C.c_double), ("ess", C.c_double),
+                ("mean", C.c_double * PZ_MAX_NX), ("var", C.c_double * PZ_MAX_NX), ("n_migrated", C.c_int64),
+                ("e_max", C.c_int32), ("reserved", C.c_int32), ("total_weight", C.c_uint64)]
+
+
+_SYMBOLS = [
+    "pz_abi_version", "pz_last_error", "pz_model_rw1d", "pz_model_stt", "pz_model_mtt_track", "pz_model_mtt",
+    "pz_filter_create", "pz_comm_unique_id", "pz_filter_create_sharded", "pz_filter_step", "pz_filter_run",
+    "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_ancestors", "pz_filter_read_state",
+    "pz_filter_read_logw", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
+    "pz_filter_destroy",
+]
+
+
+def exported_symbols():
+    """Every entry point include/pzgpu.h declares."""
+    return list(_SYMBOLS)
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpzgpu.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libpzgpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PzError(-2, f"{path} is missing: run __graft_entry__.build() (make -C probzelus-haskell_b200/csrc)")
+    L = C.CDLL(path)
+    f64p, i32p, f32p = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    L.pz_last_error.restype = C.c_char_p
+    L.pz_model_rw1d.argtypes = [C.POINTER(ModelDesc), C.c_double, C.c_double]
+    for nm in ("pz_model_stt", "pz_model_mtt_track", "pz_model_mtt"):
+        getattr(L, nm).argtypes = [C.POINTER(ModelDesc)]
+    L.pz_filter_create.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+    L.pz_comm_unique_id.argtypes = [C.c_void_p]
+    L.pz_filter_create_sharded.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pz_filter_step.argtypes = [C.c_void_p, f64p, C.c_int32, C.c_int32, C.POINTER(StepSummary)]
+    L.pz_filter_run.argtypes = [C.c_void_p, f64p, C.c_int64, C.c_int32, C.POINTER(StepSummary)]
+    L.pz_filter_last_timing.argtypes = [C.c_void_p, f64p, C.POINTER(C.c_int64)]
+    L.pz_filter_step_profile.argtypes = [C.c_void_p, f64p, C.c_int32, C.c_int32, f64p]
+    L.pz_filter_read_particles.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
+    L.pz_filter_read_ancestors.argtypes = [C.c_void_p, i32p, C.c_int64]
+    L.pz_filter_read_state.argtypes = [C.c_void_p, f32p, C.c_int64]
+    L.pz_filter_read_logw.argtypes = [C.c_void_p, f32p, C.c_int64]
+    L.pz_filter_n_local.argtypes = [C.c_void_p]
+    L.pz_filter_n_local.restype = C.c_int64
+    L.pz_resample_systematic.argtypes = [f64p, C.c_int64, C.c_double, i32p]
+    L.pz_resample_multinomial.argtypes = [f64p, C.c_int64, C.c_uint64, C.c_uint32, i32p]
+    L.pz_filter_destroy.argtypes = [C.c_void_p]
+    L.pz_filter_destroy.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise PzError(rc, lib().pz_last_error().decode())
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+# ---- model descriptors (kernel-side plugin surface) -------------------------------------------
+def rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=True, resampler=PZ_RESAMPLE_SYSTEMATIC):
+    """1-D Gaussian random walk + noisy observation: kalman1DObserved, Examples/Demo.hs:184-198."""
+    d = ModelDesc()
+    _check(lib().pz_model_rw1d(C.byref(d), q_var, r_var))
+    d.scalar_ll_2x, d.resampler = int(scalar_ll_2x), resampler
+    return d
+
+
+def stt(resampler=PZ_RESAMPLE_SYSTEMATIC):
+    """Single-target tracker, bootstrap (delay=False): Examples/SingleTargetTracking.hs:28-54."""
+    d = ModelDesc()
+    _check(lib().pz_model_stt(C.byref(d)))
+    d.resampler = resampler
+    return d
+
+
+def mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC):
+    """2-D position/velocity track model of the multi-target tracker: MultiTargetTracking.hs:56-73."""
+    d = ModelDesc()
+    _check(lib().pz_model_mtt_track(C.byref(d)))
+    d.resampler = resampler
+    return d
+
+
+def mtt():
+    """Multi-target tracker constants: Examples/MultiTargetTracking.hs:36-145."""
+    d = ModelDesc()
+    _check(lib().pz_model_mtt(C.byref(d)))
+    return d
+
+
+# ---- the stream ----------------------------------------------------------------------------------
+class Posterior:
+    """One element of the output stream: the particle approximation of p(x_t | y_1..t)."""
+
+    def __init__(self, stream, summary):
+        self._stream = stream
+        nx = stream.nx
+        self.step = summary.step
+        self.mean = np.array(summary.mean[:nx])
+        self.var = np.array(summary.var[:nx])
+        self.ess = summary.ess
+        self.log_evidence_inc = summary.log_evidence_inc
+        self.e_max = summary.e_max
+        self.total_weight = summary.total_weight
+        self.n_migrated = summary.n_migrated
+
+    def particles(self, stride=1):
+        """The reference's `[b]`: equally weighted particles after resampling (every stride-th)."""
+        if self._stream.t != self.step + 1:
+            raise PzError(-7, "the stream has advanced past this posterior")
+        return self._stream.read_particles(stride)
+
+
+class ZStream:
+    """ZStream IO Obs Posterior built around pz_filter_step (Util/ZStream.hs:16-21)."""
+
+    def __init__(self, model, n_particles, seed=0, device=0):
+        self.model, self.n, self.nx, self.ny = model, int(n_particles), model.nx, model.ny
+        self.t = 0
+        self._h = C.c_void_p()
+        _check(lib().pz_filter_create(C.byref(model), self.n, seed, device, C.byref(self._h)))
+
+    def step(self, obs):
+        y = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
+        s = StepSummary()
+        _check(lib().pz_filter_step(self._h, _ptr(y, C.c_double), 1, y.size, C.byref(s)))
+        self.t += 1
+        return Posterior(self, s)
+
+    def run(self, observations, want_summaries=True):
+        """runStream over a whole observation array [T, ny]; returns the T summaries."""
+        obs = np.ascontiguousarray(observations, dtype=np.float64).reshape(-1, self.ny)
+        T = obs.shape[0]
+        out = (StepSummary * T)() if want_summaries else None
+        rc = lib().pz_filter_run(self._h, _ptr(obs, C.c_double), T, self.ny, out)
+        self.t += T
+        _check(rc)
+        return [Posterior(self, s) for s in out] if want_summaries else None
+
+    def step_profile(self, obs):
+        """One step outside the CUDA graph; returns ms of (fused kernel, scan, partition)."""
+        y = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
+        ms = np.zeros(3)
+        _check(lib().pz_filter_step_profile(self._h, _ptr(y, C.c_double), 1, y.size, _ptr(ms, C.c_double)))
+        self.t += 1
+        return ms
+
+    def last_timing(self):
+        ms, n = C.c_double(), C.c_int64()
+        _check(lib().pz_filter_last_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def read_particles(self, stride=1):
+        n_sel = (self.n + stride - 1) // stride
+        out = np.zeros((n_sel, self.nx))
+        _check(lib().pz_filter_read_particles(self._h, stride, _ptr(out, C.c_double), out.size))
+        return out
+
+    def read_ancestors(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        _check(lib().pz_filter_read_ancestors(self._h, _ptr(out, C.c_int32), out.size))
+        return out
+
+    def read_state(self):
+        out = np.zeros((self.nx, self.n), dtype=np.float32)
+        _check(lib().pz_filter_read_state(self._h, _ptr(out, C.c_float), out.size))
+        return out
+
+    def read_logw(self):
+        out = np.zeros(self.n, dtype=np.float32)
+        _check(lib().pz_filter_read_logw(self._h, _ptr(out, C.c_float), out.size))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().pz_filter_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def zparticles(num_particles, model, seed=0, device=0):
+    """zparticles numParticles model (Inference.hs:107-108)."""
+    return ZStream(model, num_particles, seed, device)
+
+
+def zdsparticles(num_particles, model, seed=0, device=0):
+    """zdsparticles (Inference.hs:113-114): the per-particle heap is the fixed-capacity state."""
+    return ZStream(model, num_particles, seed, device)
+
+
+def infer(model, num_particles, seed=0, device=0):
+    """ProbZelus `infer`: model x particle count -> stream of posteriors."""
+    return ZStream(model, num_particles, seed, device)
+
+
+def run_stream(act, stream, observations):
+    """ZS.runStream act stream (Util/ZStream.hs:65-69), driven by a finite observation list."""
+    for y in observations:
+        act(stream.step(y))
+
+
+def resample_systematic(logw, u):
+    lw = np.ascontiguousarray(logw, dtype=np.float64)
+    anc = np.zeros(lw.size, dtype=np.int32)
+    _check(lib().pz_resample_systematic(_ptr(lw, C.c_double), lw.size, float(u), _ptr(anc, C.c_int32)))
+    return anc
+
+
+def resample_multinomial(logw, seed, step):
+    lw = np.ascontiguousarray(logw, dtype=np.float64)
+    anc = np.zeros(lw.size, dtype=np.int32)
+    _check(lib().pz_resample_multinomial(_ptr(lw, C.c_double), lw.size, seed, step, _ptr(anc, C.c_int32)))
+    return anc

@@ -1,0 +1,219 @@
+"""ctypes bindings shared by the tests: the CPU oracle (oracle/libpzoracle.so) and the
+reference's model constants restated as pz_model_desc builders.
+
+The oracle is test infrastructure: it is imported here, by __graft_entry__.smoke() and by
+bench.py's cpu_baseline leg only.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+PZ_MAX_NX, PZ_MAX_NY = 6, 3
+PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT = 1, 2, 3
+PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF = 0, 1
+PZ_EDEGENERATE = -4
+
+
+class MttParams(C.Structure):
+    _fields_ = [("clutter_lambda", C.c_double), ("new_track_lambda", C.c_double), ("pd", C.c_double),
+                ("survival_prob", C.c_double), ("clutter_var", C.c_double), ("birth_pos_var", C.c_double),
+                ("birth_vel_var", C.c_double), ("meas_var", C.c_double), ("k_max", C.c_int32),
+                ("m_max", C.c_int32)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
+                ("resampler", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
+                ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
+                ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]
+
+
+class StepSummary(C.Structure):
+    _fields_ = [("step", C.c_int64), ("log_evidence_inc", C.c_double), ("ess", C.c_double),
+                ("mean", C.c_double * PZ_MAX_NX), ("var", C.c_double * PZ_MAX_NX), ("n_migrated", C.c_int64),
+                ("e_max", C.c_int32), ("reserved", C.c_int32), ("total_weight", C.c_uint64)]
+
+
+def _fill(desc, kind, F, Q, H, R, x0=None, scalar_ll_2x=1, resampler=PZ_RESAMPLE_SYSTEMATIC):
+    F, Q, H, R = (np.atleast_2d(np.asarray(a, dtype=np.float64)) for a in (F, Q, H, R))
+    nx, ny = F.shape[0], H.shape[0]
+    desc.kind, desc.nx, desc.ny = kind, nx, ny
+    desc.scalar_ll_2x, desc.resampler = scalar_ll_2x, resampler
+    for name, a in (("F", F), ("Q", Q), ("H", H), ("R", R)):
+        flat = a.reshape(-1)
+        arr = getattr(desc, name)
+        for i, v in enumerate(flat):
+            arr[i] = float(v)
+    if x0 is not None:
+        for i, v in enumerate(x0):
+            desc.x0[i] = float(v)
+    return desc
+
+
+def model_rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=1, resampler=PZ_RESAMPLE_SYSTEMATIC):
+    """noisyIntegrateGen + observe (normal x 3): Examples/Demo.hs:184-198 (x0 = 0, var 1, obs var 3)."""
+    return _fill(ModelDesc(), PZ_MODEL_RW1D, [[1.0]], [[q_var]], [[1.0]], [[r_var]],
+                 scalar_ll_2x=scalar_ll_2x, resampler=resampler)
+
+
+def model_stt(resampler=PZ_RESAMPLE_SYSTEMATIC):
+    """Examples/SingleTargetTracking.hs:39-54: R^6 constant-velocity, tdiff=1, obs cov 10 I3."""
+    I3, Z3 = np.eye(3), np.zeros((3, 3))
+    F = np.block([[I3, I3], [Z3, I3]])
+    Q = np.block([[0.01 * I3, Z3], [Z3, 0.1 * I3]])
+    H = np.block([I3, Z3])
+    return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, 10.0 * I3, resampler=resampler)
+
+
+def model_mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC):
+    """Examples/MultiTargetTracking.hs:56-73: R^4 damped position/velocity track, obs cov I2."""
+    I2, Z2 = np.eye(2), np.zeros((2, 2))
+    F = np.eye(4) + np.block([[Z2, I2], [-0.01 * I2, -0.1 * I2]])
+    Q = np.block([[0.01 * I2, Z2], [Z2, 0.1 * I2]])
+    H = np.block([I2, Z2])
+    return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, I2, resampler=resampler)
+
+
+def desc_arrays(desc):
+    nx, ny = desc.nx, desc.ny
+    F = np.array(desc.F[: nx * nx]).reshape(nx, nx)
+    Q = np.array(desc.Q[: nx * nx]).reshape(nx, nx)
+    H = np.array(desc.H[: ny * nx]).reshape(ny, nx)
+    R = np.array(desc.R[: ny * ny]).reshape(ny, ny)
+    return F, Q, H, R
+
+
+_oracle = None
+
+
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "libpzoracle.so")
+    src = os.path.join(ORACLE_DIR, "pz_oracle.cpp")
+    hdr = os.path.join(ROOT, "include", "pzgpu.h")
+    if not os.path.exists(so) or (os.path.exists(src) and max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+    return so
+
+
+def oracle():
+    """Load (building if stale) the CPU oracle."""
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    lib = C.CDLL(build_oracle())
+    u32p, i32p, u64p, f32p, f64p = (C.POINTER(t) for t in (C.c_uint32, C.c_int32, C.c_uint64, C.c_float, C.c_double))
+    lib.pzo_philox4x32_10.argtypes = [u32p, u32p, u32p]
+    lib.pzo_weight_split.argtypes = [f32p, C.c_int64, i32p, u32p]
+    lib.pzo_normal_pairs.argtypes = [u32p, u32p, C.c_int64, f32p, f32p]
+    lib.pzo_resample_uniform.argtypes = [C.c_uint64, C.c_uint32]
+    lib.pzo_resample_uniform.restype = C.c_uint32
+    lib.pzo_resample_systematic.argtypes = [f32p, C.c_int64, C.c_uint32, i32p, i32p, u64p, u64p, i32p, u64p]
+    lib.pzo_resample_multinomial.argtypes = [f32p, C.c_int64, C.c_uint64, C.c_uint32, i32p]
+    lib.pzo_resample_systematic_f64.argtypes = [f64p, C.c_int64, C.c_double, i32p]
+    lib.pzo_resample_systematic_f64.restype = None
+    lib.pzo_filter_create.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64]
+    lib.pzo_filter_create.restype = C.c_void_p
+    lib.pzo_filter_destroy.argtypes = [C.c_void_p]
+    lib.pzo_filter_step.argtypes = [C.c_void_p, f64p, C.POINTER(StepSummary)]
+    lib.pzo_filter_state.argtypes = [C.c_void_p, f32p, f32p, i32p]
+    lib.pzo_filter_block_stats.argtypes = [C.c_void_p, i32p, u64p, i32p, u64p]
+    lib.pzo_filter_derived.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, f32p, f64p]
+    lib.pzo_kalman_step.argtypes = [C.POINTER(ModelDesc), f64p, f64p, f64p, f64p]
+    lib.pzo_generate_observations.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_int64, f64p, f64p]
+    lib.pzo_refpf_run.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64, f64p, C.c_int64, C.c_int, f64p, f64p, C.c_int]
+    lib.pzo_num_threads.restype = C.c_int
+    _oracle = lib
+    return lib
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+OBS_SEED = 0x0B5E2026  # observation stream key
+
+
+def gen_obs(desc, T, seed=OBS_SEED):
+    lib = oracle()
+    obs = np.zeros((T, desc.ny))
+    truth = np.zeros((T, desc.nx))
+    lib.pzo_generate_observations(C.byref(desc), seed, T, ptr(obs, C.c_double), ptr(truth, C.c_double))
+    return obs, truth
+
+
+def kalman(desc, obs):
+    """Exact posterior means / covariances for an observation stream (double)."""
+    lib = oracle()
+    nx = desc.nx
+    mean = np.array(desc.x0[:nx], dtype=np.float64)
+    cov = np.zeros((nx, nx))
+    means, covs, lls = [], [], []
+    ll = C.c_double()
+    for y in np.ascontiguousarray(obs, dtype=np.float64):
+        rc = lib.pzo_kalman_step(C.byref(desc), ptr(y, C.c_double), ptr(mean, C.c_double), ptr(cov, C.c_double), C.byref(ll))
+        assert rc == 0
+        means.append(mean.copy()); covs.append(cov.copy()); lls.append(ll.value)
+    return np.array(means), np.array(covs), np.array(lls)
+
+
+class OracleFilter:
+    """The canonical filter on the CPU (bit-exact twin of the CUDA path)."""
+
+    def __init__(self, desc, n, seed):
+        self.lib = oracle()
+        self.desc, self.n, self.nx = desc, n, desc.nx
+        self.h = self.lib.pzo_filter_create(C.byref(desc), n, seed)
+        assert self.h, "oracle rejected the descriptor"
+
+    def step(self, y):
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        s = StepSummary()
+        rc = self.lib.pzo_filter_step(self.h, ptr(y, C.c_double), C.byref(s))
+        return rc, s
+
+    def state(self):
+        x = np.zeros((self.nx, self.n), dtype=np.float32)
+        lw = np.zeros(self.n, dtype=np.float32)
+        anc = np.zeros(self.n, dtype=np.int32)
+        self.lib.pzo_filter_state(self.h, ptr(x, C.c_float), ptr(lw, C.c_float), ptr(anc, C.c_int32))
+        return x, lw, anc
+
+    def block_stats(self):
+        nblk = (self.n + 255) // 256
+        eb = np.zeros(nblk, dtype=np.int32)
+        sb = np.zeros(nblk, dtype=np.uint64)
+        em, tot = C.c_int32(), C.c_uint64()
+        rc = self.lib.pzo_filter_block_stats(self.h, ptr(eb, C.c_int32), ptr(sb, C.c_uint64), C.byref(em), C.byref(tot))
+        return rc, eb, sb, em.value, tot.value
+
+    def close(self):
+        if self.h:
+            self.lib.pzo_filter_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def oracle_systematic(lw32, U):
+    lib = oracle()
+    lw32 = np.ascontiguousarray(lw32, dtype=np.float32)
+    n = lw32.size
+    anc = np.zeros(n, dtype=np.int32)
+    rc = lib.pzo_resample_systematic(ptr(lw32, C.c_float), n, int(U), ptr(anc, C.c_int32), None, None, None, None, None)
+    return rc, anc
+
+
+def oracle_multinomial(lw32, seed, step):
+    lib = oracle()
+    lw32 = np.ascontiguousarray(lw32, dtype=np.float32)
+    n = lw32.size
+    anc = np.zeros(n, dtype=np.int32)
+    rc = lib.pzo_resample_multinomial(ptr(lw32, C.c_float), n, seed, step, ptr(anc, C.c_int32))
+    return rc, anc

@@ -1,0 +1,236 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI
+(libpzgpu.so via ctypes); the CPU oracle is the checker.
+
+Bars: bit-exact for ancestors, fixed-point block statistics and the fp32 particle state
+(integer / index work and the canonical fp32 spec); 1e-9 relative for the fp64 summaries
+(their reduction order differs between the kernels and the oracle); 3 standard errors for
+posterior moments against the exact Kalman filter."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import pzhelpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def weight_vectors(n, rng):
+    yield "uniform", np.zeros(n)
+    yield "gaussian", rng.standard_normal(n) * 3
+    hot = np.full(n, -np.inf); hot[(n * 7) // 11] = -2.5
+    yield "one_hot", hot
+    yield "geometric", -0.01 * np.arange(n, dtype=np.float64)
+    mix = rng.standard_normal(n) * 2
+    mix[rng.random(n) < 0.3] = -np.inf
+    if n > 3:
+        mix[1] = np.nan
+    yield "with_inf_nan", mix
+    yield "wide_range", -np.abs(rng.standard_normal(n)) * 200
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1000, 2048, 2049, 4097, 100003, 1 << 20])
+def test_resample_systematic_bit_exact(pz, n):
+    rng = np.random.default_rng(n)
+    for name, lw in weight_vectors(n, rng):
+        for u in (0.0, 0.37, 1 - 2.0 ** -32):
+            U = int(u * 2 ** 32)
+            rc, ref = H.oracle_systematic(lw.astype(np.float32), U)
+            if rc == H.PZ_EDEGENERATE:
+                with pytest.raises(pz.PzError) as e:
+                    pz.resample_systematic(lw, u)
+                assert e.value.code == H.PZ_EDEGENERATE
+                continue
+            got = pz.resample_systematic(lw, u)
+            assert np.array_equal(got, ref), (name, n, u, np.flatnonzero(got != ref)[:5])
+
+
+def test_resample_golden_fixture(pz):
+    g = np.load(H.ROOT + "/tests/golden/philox_normal_kat.npz")
+    got = pz.resample_systematic(g["lw_r"].astype(np.float64), int(g["U_r"]) / 2.0 ** 32)
+    assert np.array_equal(got, g["anc_r"])
+
+
+def test_resample_degenerate_reports_error(pz):
+    for lw in (np.full(1000, -np.inf), np.full(1000, np.nan)):
+        with pytest.raises(pz.PzError) as e:
+            pz.resample_systematic(lw, 0.5)
+        assert e.value.code == H.PZ_EDEGENERATE
+
+
+@pytest.mark.parametrize("n", [1000, 100003])
+def test_resample_multinomial_bit_exact(pz, n):
+    rng = np.random.default_rng(n + 1)
+    lw = rng.standard_normal(n) * 2
+    for step in (0, 5):
+        rc, ref = H.oracle_multinomial(lw.astype(np.float32), 1234, step)
+        assert rc == 0
+        assert np.array_equal(pz.resample_multinomial(lw, 1234, step), ref)
+
+
+MODELS = {"rw1d": (H.model_rw1d, "rw1d"), "lg42": (H.model_mtt_track, "mtt_track"), "lg63": (H.model_stt, "stt")}
+
+
+@pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
+@pytest.mark.parametrize("n", [1, 300, 4096, 10007, 200000])
+def test_filter_trajectory_bit_exact(pz, model, n):
+    """Whole-filter parity: after every step the fp32 population, the fixed-point total and
+    the global exponent equal the oracle's bit for bit; summaries agree to 1e-9."""
+    hd = MODELS[model][0]()
+    d = getattr(pz, MODELS[model][1])()
+    T = 8
+    obs, _ = H.gen_obs(hd, T)
+    zs = pz.zparticles(n, d, seed=4242)
+    orc = H.OracleFilter(hd, n, 4242)
+    for t in range(T):
+        # ancestors of the resample this step performs
+        if t in (0, 3):
+            anc_gpu = zs.read_ancestors()
+        post = zs.step(obs[t])
+        rc, s = orc.step(obs[t])
+        assert rc == 0
+        x_ref, lw_ref, anc_ref = orc.state()
+        if t in (0, 3):
+            assert np.array_equal(anc_gpu, anc_ref), (model, n, t)
+        x = zs.read_state()
+        assert np.array_equal(x.view(np.uint32), x_ref.view(np.uint32)), (model, n, t)
+        assert np.array_equal(zs.read_logw().view(np.uint32), lw_ref.view(np.uint32))
+        assert post.total_weight == s.total_weight and post.e_max == s.e_max and post.step == t
+        nx = hd.nx
+        assert np.allclose(post.mean, s.mean[:nx], rtol=1e-9, atol=1e-9)
+        assert np.allclose(post.var, s.var[:nx], rtol=1e-7, atol=1e-9)
+        assert abs(post.ess - s.ess) < 1e-7 * s.ess
+        assert abs(post.log_evidence_inc - s.log_evidence_inc) < 1e-9
+    zs.close(); orc.close()
+
+
+def test_filter_golden_fixture(pz):
+    """The committed fixture (made by tools/make_golden.py) without re-running the oracle."""
+    g = np.load(H.ROOT + "/tests/golden/philox_normal_kat.npz")
+    for name, mk in (("rw1d", pz.rw1d), ("lg42", pz.mtt_track), ("lg63", pz.stt)):
+        zs = pz.zparticles(3000, mk(), seed=42)
+        for y in g[name + "_obs"]:
+            post = zs.step(y)
+        assert np.array_equal(zs.read_state().view(np.uint32), g[name + "_x"].view(np.uint32))
+        assert post.total_weight == int(g[name + "_total"])
+        assert np.allclose(post.mean, g[name + "_mean"], rtol=1e-9, atol=1e-9)
+        zs.close()
+
+
+def test_run_equals_step(pz):
+    """runStream over a staged observation array == repeated ZStream.step (bitwise)."""
+    d = pz.rw1d()
+    obs, _ = H.gen_obs(H.model_rw1d(), 40)
+    a = pz.zparticles(50000, d, seed=9)
+    b = pz.zparticles(50000, d, seed=9)
+    pa = [a.step(y) for y in obs]
+    pb = b.run(obs)
+    assert np.array_equal(a.read_state().view(np.uint32), b.read_state().view(np.uint32))
+    for x, y in zip(pa, pb):
+        assert x.total_weight == y.total_weight and x.mean[0] == y.mean[0] and x.step == y.step
+    ms, launches = b.last_timing()
+    assert launches == 3 * 40 and ms > 0
+
+
+def test_reproducible_and_seed_sensitive(pz):
+    d = pz.mtt_track()
+    obs, _ = H.gen_obs(H.model_mtt_track(), 5)
+    outs = []
+    for seed in (1, 1, 2):
+        zs = pz.zparticles(20000, d, seed=seed)
+        zs.run(obs)
+        outs.append(zs.read_state().copy())
+        zs.close()
+    assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
+def test_posterior_matches_kalman(pz, model):
+    """Posterior mean / variance within 3 SE of the exact Kalman filter over 20 seeds at
+    N = 10^5 (BASELINE.md section 5 gate 2); also the log-evidence for the properly normalised scores."""
+    hd = MODELS[model][0]()
+    d = getattr(pz, MODELS[model][1])()
+    T, n, seeds = 30, 100000, 20
+    obs, _ = H.gen_obs(hd, T)
+    km, kc, kl = H.kalman(hd, obs)
+    nx = hd.nx
+    means = np.zeros((seeds, T, nx)); vars_ = np.zeros((seeds, T, nx)); ll = np.zeros(seeds)
+    for s in range(seeds):
+        zs = pz.zparticles(n, d, seed=1000 + s)
+        posts = zs.run(obs)
+        means[s] = [p.mean for p in posts]; vars_[s] = [p.var for p in posts]
+        ll[s] = sum(p.log_evidence_inc for p in posts)
+        zs.close()
+    se_m = means.std(axis=0, ddof=1) / np.sqrt(seeds)
+    zm = (means.mean(axis=0) - km) / np.maximum(se_m, 1e-12)
+    kvar = np.array([np.diag(c) for c in kc])
+    se_v = vars_.std(axis=0, ddof=1) / np.sqrt(seeds)
+    zv = (vars_.mean(axis=0) - kvar) / np.maximum(se_v, 1e-12)
+    assert np.mean(np.abs(zm) > 3) < 0.03 and np.max(np.abs(zm)) < 5, zm
+    assert np.mean(np.abs(zv) > 3) < 0.05 and np.max(np.abs(zv)) < 6, zv
+    if model != "rw1d":
+        assert abs(ll.mean() - kl.sum()) < 4 * ll.std(ddof=1) / np.sqrt(seeds) + 0.02
+
+
+def test_multinomial_reference_mode(pz):
+    """resampler = MULTINOMIAL_REF (resample2, Inference.hs:57-61): bit-exact vs the oracle and
+    statistically equal to the systematic filter."""
+    hd = H.model_rw1d(resampler=H.PZ_RESAMPLE_MULTINOMIAL_REF)
+    d = pz.rw1d(resampler=pz.PZ_RESAMPLE_MULTINOMIAL_REF)
+    n, T = 20000, 6
+    obs, _ = H.gen_obs(hd, T)
+    zs = pz.zparticles(n, d, seed=77)
+    orc = H.OracleFilter(hd, n, 77)
+    for t in range(T):
+        post = zs.step(obs[t])
+        rc, s = orc.step(obs[t])
+        x_ref, _, _ = orc.state()
+        assert np.array_equal(zs.read_state().view(np.uint32), x_ref.view(np.uint32)), t
+        assert post.total_weight == s.total_weight
+
+
+def test_read_particles_is_resampled_population(pz):
+    d = pz.stt()
+    hd = H.model_stt()
+    n = 30000
+    obs, _ = H.gen_obs(hd, 4)
+    zs = pz.zparticles(n, d, seed=3)
+    for y in obs:
+        post = zs.step(y)
+    x = zs.read_state()
+    anc = zs.read_ancestors()
+    p = post.particles(stride=7)
+    assert p.shape == ((n + 6) // 7, 6)
+    assert np.array_equal(p.astype(np.float32), x[:, anc[::7]].T)
+    # equally weighted resampled particles reproduce the weighted posterior mean
+    full = zs.read_particles(1)
+    assert np.allclose(full.mean(axis=0), post.mean, atol=5 * np.sqrt(post.var / n) + 1e-3)
+
+
+def test_degenerate_weights_are_reported(pz):
+    d = pz.rw1d()
+    zs = pz.zparticles(5000, d, seed=1)
+    zs.step([0.3])
+    with pytest.raises(pz.PzError) as e:
+        zs.step([float("nan")])
+    assert e.value.code == H.PZ_EDEGENERATE
+
+
+def test_large_n_properties(pz):
+    """BASELINE size (N = 10^8 would need the oracle for minutes): size-independent
+    properties at N = 2^24 -- sorted ancestors, offspring counts within 1 of N w_i, total
+    mass conservation, and equality of two independent runs."""
+    n = 1 << 24
+    d = pz.rw1d()
+    obs, _ = H.gen_obs(H.model_rw1d(), 3)
+    zs = pz.zparticles(n, d, seed=5)
+    zs.run(obs)
+    lw = zs.read_logw().astype(np.float64)
+    anc = zs.read_ancestors()
+    assert anc.min() >= 0 and anc.max() < n and np.all(np.diff(anc) >= 0)
+    w = np.exp(lw - lw.max()); w /= w.sum()
+    cnt = np.bincount(anc, minlength=n)
+    assert np.all(np.abs(cnt - n * w) < 1 + 1e-3 * n * w + 1e-4)
+    zs2 = pz.zparticles(n, d, seed=5)
+    zs2.run(obs)
+    assert np.array_equal(zs2.read_ancestors(), anc)
