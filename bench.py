@@ -222,7 +222,7 @@ def run_b200(args):
                    "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp32",
                    "weights": "u64 fixed point", "resampler": "systematic (canonical PZ-SYS-256)",
                    "l2": "inputs exceed L2 (state %.0f MB per buffer)" % (nx * 4 * n_p / 1e6), "wall_s_timed": wall},
-        "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 136,
+        "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 144,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,

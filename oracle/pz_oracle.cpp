@@ -92,14 +92,13 @@ constexpr float kLogC[8] = {0x1.555552p-2f, -0x1.0000c8p-2f, 0x1.99a14cp-3f, -0x
 constexpr float kSinC[3] = {-0x1.555552p-3f, 0x1.110c2ap-7f, -0x1.9aca02p-13f};
 constexpr float kCosC[3] = {0x1.555554p-5f, -0x1.6c12d4p-10f, 0x1.9bd8d2p-16f};
 
-constexpr int32_t kNZero = INT32_MIN;  // exponent marker of a zero weight
+constexpr int32_t kNZero = -(1 << 30);  // exponent marker of a zero weight
 
 // log-weight -> (n, m): weight = m * 2^(n-23), m in [2^22.5, 2^23.5].  Zero weight: m = 0.
 inline void weight_split(float lw, int32_t* n, uint32_t* m) {
   *n = kNZero; *m = 0;
-  if (!(lw > -INFINITY) || !(lw < INFINITY)) return;  // -inf, +inf, NaN -> zero weight
   float e = lw * kLog2e;
-  if (!(e > -1.0e6f) || !(e < 1.0e6f)) return;
+  if (!(fabsf(e) < 1.0e6f)) return;  // -inf, +inf, NaN, out of range -> zero weight
   float r = rintf(e);
   float f = e - r;
   float p = kExp2C[6];
@@ -266,20 +265,16 @@ struct ResamplePlan {
   std::vector<uint64_t> pb;    // per block exclusive prefix at global scale (nblk+1 entries)
   int32_t emax = kNZero;
   uint64_t total = 0;
-  uint32_t rho = 0;
-  int shift = 0;
+  uint64_t rho = 0;  // floor(N_out * 2^(32+L) / T) + 1
+  int L = 0;         // bit length of T
 };
 
 inline int bitlen64(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
-inline int bitlen128(u128 v) {
-  uint64_t hi = (uint64_t)(v >> 64);
-  return hi ? 64 + bitlen64(hi) : bitlen64((uint64_t)v);
-}
 
 inline uint32_t q_at(uint32_t m, int32_t n, int32_t eb) {
   if (m == 0) return 0;
   int64_t sh = (int64_t)eb - (int64_t)n;
-  return sh < 32 ? (uint32_t)((m << 8) >> sh) : 0u;
+  return sh < 32 ? (m >> sh) : 0u;
 }
 
 // returns false when every weight is zero (degenerate)
@@ -310,22 +305,19 @@ bool build_plan(const float* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
   pl->total = run;
   if (run == 0) return false;
   int L = bitlen64(run);
-  u128 rho = (((u128)(uint64_t)n_out) << (32 + L)) / run + 1;
-  int a = std::max(0, bitlen128(rho) - 31);
-  pl->rho = (uint32_t)(rho >> a) + 1;
-  pl->shift = L - a;
+  pl->L = L;
+  pl->rho = (uint64_t)((((u128)(uint64_t)n_out) << (32 + L)) / run) + 1;
   return true;
 }
 
+// position of CDF value C in units of 2^-32 output slots: floor(C * rho / 2^L) <= N * 2^32
 inline uint64_t pos_of(const ResamplePlan& pl, uint64_t C) {
-  u128 prod = (u128)C * pl.rho;
-  return (uint64_t)(pl.shift >= 0 ? (prod >> pl.shift) : (prod << (-pl.shift)));
+  return (uint64_t)(((u128)(C << (64 - pl.L)) * pl.rho) >> 64);
 }
 
+// number of output slots whose threshold j * 2^32 + U lies below pos(C)
 inline int64_t slot_end(const ResamplePlan& pl, uint64_t C, uint32_t U, int64_t n_out) {
-  uint64_t pos = pos_of(pl, C);
-  if (pos <= U) return 0;
-  uint64_t o = (pos - U + 0xFFFFFFFFull) >> 32;
+  uint64_t o = (pos_of(pl, C) + (0xFFFFFFFFull - U)) >> 32;
   return (int64_t)std::min<uint64_t>(o, (uint64_t)n_out);
 }
 
@@ -389,7 +381,7 @@ struct OFilter {
 };
 
 void summarise(const OFilter& f, const ResamplePlan& pl, pz_step_summary* s, const double* center) {
-  // the same truncated fixed-point weights the resampler uses, at scale 2^(emax-31), in double
+  // the same truncated fixed-point weights the resampler uses, at scale 2^(emax-23), in double
   double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
   for (int64_t i = 0; i < f.n; ++i) {
     const int32_t eb = pl.eb[i / kBlk];
@@ -408,7 +400,7 @@ void summarise(const OFilter& f, const ResamplePlan& pl, pz_step_summary* s, con
     s->mean[d] = (double)(float)center[d] + m;
     s->var[d] = sxx[d] / sw - m * m;
   }
-  s->log_evidence_inc = log(sw) + (pl.emax - 31) * M_LN2 - log((double)f.n) + f.p.ll_const;
+  s->log_evidence_inc = log(sw) + (pl.emax - 23) * M_LN2 - log((double)f.n) + f.p.ll_const;
   s->e_max = pl.emax;
   s->total_weight = pl.total;
   s->n_migrated = 0;

@@ -2,23 +2,26 @@
 //
 // One time step of zparticles' (haskell/src/Inference.hs:101-104) is three launches:
 //
-//   pf_step_tile<NX,NY,TO,FUSED>   per output tile of TO slots: merge-path locate the input
-//       blocks whose cumulative weight covers the tile, recompute their weights from state +
-//       previous observation (score/factor/observe, Distributions.hs:29-36,160-161;
-//       MVDistributions.hs:45-46), warp-scan them in 64-bit fixed point, scatter each
-//       parent into the shared-memory slots of its children (resample2 + `fst . (xs !!)`,
-//       Inference.hs:57-61, as a systematic resampler), then per child: Philox normals,
-//       x' = F x + L z (noisyIntegrateGen Demo.hs:184-187; SingleTargetTracking.hs:34;
-//       MultiTargetTracking.hs:56-67), the new log-weight, 128-bit coalesced stores of the
-//       state, and the block statistics (max exponent, fixed-point sum) + centred moment
-//       sums (average / weightedAverage, Util/Numeric.hs:7-22) of the new population.
+//   pf_step_tile<NX,NY,TO,MODE>   per output tile of TO slots:
+//       input side  -- merge-path locate the input blocks whose cumulative weight covers the
+//                      tile, recompute their weights from state + previous observation
+//                      (score/factor/observe, Distributions.hs:29-36,160-161;
+//                      MVDistributions.hs:45-46), warp-scan them in fixed point, and stage
+//                      every parent at the shared-memory slot of its FIRST child (head mark);
+//       output side -- a warp max-scan of the head marks gives every slot its parent
+//                      (resample2 + `fst . (xs !!)`, Inference.hs:57-61, as a systematic
+//                      resampler), then per child: Philox normals, x' = F x + L z
+//                      (noisyIntegrateGen Demo.hs:184-187; SingleTargetTracking.hs:34;
+//                      MultiTargetTracking.hs:56-67), the new log-weight, 128-bit coalesced
+//                      stores of the state, the block statistics (max exponent, fixed-point
+//                      sum) and the centred moment sums of the new population (average /
+//                      weightedAverage, Util/Numeric.hs:7-22).
 //   pf_scan_blocks     decoupled look-back exclusive scan of the block sums rescaled to the
 //       global exponent (normalize / shiftByMax, Inference.hs:63-66, Util/Numeric.hs:12-17),
 //       and, in the last CTA, the resampling plan and the posterior summary.
 //   pf_partition       merge-path split: first input block of every output tile.
 //
-// No tensor cores: the path is a streaming scan / gather with ~100 integer+fp32
-// instructions per particle; see DESIGN.md for the roofline discussion.
+// No tensor cores: the path is a streaming scan / gather; see DESIGN.md for the roofline.
 #include "pz_kernels.cuh"
 #include "pz_math.cuh"
 
@@ -29,9 +32,9 @@ typedef uint64_t u64;
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
-  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
-  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
   return ((u64)hi << 32) | lo;
 }
 __device__ __forceinline__ u64 shfl_up_u64(u64 v, int d) {
@@ -39,15 +42,10 @@ __device__ __forceinline__ u64 shfl_up_u64(u64 v, int d) {
   uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
   return ((u64)hi << 32) | lo;
 }
-__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) {
-  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
-  uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
-  return ((u64)hi << 32) | lo;
-}
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) {
   return __longlong_as_double((long long)shfl_xor_u64((u64)__double_as_longlong(v), m));
 }
-__device__ __forceinline__ u64 warp_inclusive_scan(u64 v, int lane) {
+__device__ __forceinline__ u64 warp_inclusive_scan_u64(u64 v, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     u64 o = shfl_up_u64(v, d);
@@ -55,28 +53,41 @@ __device__ __forceinline__ u64 warp_inclusive_scan(u64 v, int lane) {
   }
   return v;
 }
-// 2^k as a double (0 when it would underflow; callers never pass k > 0 that overflows)
+__device__ __forceinline__ uint32_t warp_inclusive_scan_u32(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_inclusive_max_u32(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v = max(v, o);
+  }
+  return v;
+}
+// 2^k as a double (0 when it would underflow)
 __device__ __forceinline__ double pow2d(int k) {
   if (k < -1022) return 0.0;
   return __hiloint2double((1023 + k) << 20, 0);
 }
 
-struct SlotMap {  // output-slot position of a CDF value (DESIGN.md "Resampler")
-  uint32_t rho;
-  int32_t shift;
-  uint32_t U;
-  int64_t n_out;  // global number of output slots
-  __device__ __forceinline__ int64_t slot_end(u64 C) const {
-    u64 lo = (C & 0xffffffffull) * rho;
-    u64 hi = (C >> 32) * rho + (lo >> 32);  // bits 32.. of the 96-bit product
-    uint32_t lo32 = (uint32_t)lo;
-    u64 pos;
-    if (shift >= 32) pos = hi >> (shift - 32);
-    else if (shift > 0) pos = (hi << (32 - shift)) | (u64)(lo32 >> shift);
-    else pos = ((hi << 32) | lo32) << (-shift);
-    if (pos <= (u64)U) return 0;
-    u64 o = (pos - U + 0xFFFFFFFFull) >> 32;
-    return (int64_t)(o < (u64)n_out ? o : (u64)n_out);
+// Output-slot position of a CDF value (DESIGN.md "Resampler"):
+//   pos(C) = floor(C * rho / 2^L)                 in units of 2^-32 slots, pos(T) = N * 2^32
+//   slot_end(C) = #{ j : j * 2^32 + U < pos(C) }  = hi32(pos + 2^32 - 1 - U)
+struct SlotMap {
+  u64 rho;
+  u64 kadd;      // 0xFFFFFFFF - U
+  int lsh;       // 64 - L
+  uint32_t n_out;
+  __device__ __forceinline__ SlotMap(const PlanDev* pl, int64_t n_global)
+      : rho(pl->rho), kadd(0xFFFFFFFFull - pl->U), lsh(64 - pl->L), n_out((uint32_t)n_global) {}
+  __device__ __forceinline__ uint32_t slot_end(u64 C) const {
+    const u64 pos = __umul64hi(C << lsh, rho);
+    return min((uint32_t)((pos + kadd) >> 32), n_out);
   }
 };
 
@@ -119,10 +130,10 @@ __device__ __forceinline__ float lg_logweight(const LgDev& p, const float* xn, c
 
 // normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]
 template <int NX>
-__device__ __forceinline__ void lg_noise4(int64_t j, uint32_t t, uint64_t seed, float (&z)[NX][4]) {
+__device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed, float (&z)[NX][4]) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   if constexpr (NX == 1) {
-    U4 r = philox4x32_10((uint32_t)(j >> 2), 0u, t, kStreamProp, k0, k1);
+    U4 r = philox4x32_10(j >> 2, 0u, t, kStreamProp, k0, k1);
     normal_pair(r.x, r.y, z[0][0], z[0][1]);
     normal_pair(r.z, r.w, z[0][2], z[0][3]);
   } else {
@@ -130,7 +141,7 @@ __device__ __forceinline__ void lg_noise4(int64_t j, uint32_t t, uint64_t seed, 
     for (int s = 0; s < 4; ++s) {
 #pragma unroll
       for (int c = 0; 4 * c < NX; ++c) {
-        U4 r = philox4x32_10((uint32_t)(j + s), (uint32_t)c, t, kStreamProp, k0, k1);
+        U4 r = philox4x32_10(j + s, (uint32_t)c, t, kStreamProp, k0, k1);
         float zz[4];
         normal_pair(r.x, r.y, zz[0], zz[1]);
         normal_pair(r.z, r.w, zz[2], zz[3]);
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
     cnt = cnt > kBlk ? kBlk : cnt;
     a.eb[0][i] = 0;
     a.eb[1][i] = kNZero;
-    a.sb[i] = (u64)cnt << 31;  // q of lw = 0 is 2^23 << 8
+    a.sb[i] = (u64)cnt << 23;  // q of lw = 0 is 2^23
   }
   if (i < a.nscan) a.scan_status[i] = 0ull;
   if (i == 0) {
@@ -193,7 +204,7 @@ struct ScanArgs {
   int32_t nscan;
   int32_t nrec;
   int32_t nx;
-  int32_t delta;      // 0: population already current (init / generic); 1: produced by the fused step
+  int32_t delta;      // 0: population already current (init / generic); 1: produced by the step kernel
   int32_t explicit_U; // standalone API: use U_value instead of Philox
   uint32_t U_value;
   uint64_t seed;
@@ -201,25 +212,18 @@ struct ScanArgs {
   int32_t world;
 };
 
-__device__ void finalize_plan(const ScanArgs& s, u64 total) {
-  PlanDev* pl = s.plan;
+__device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint32_t U) {
   pl->total = total;
-  pl->base = 0;
   pl->degenerate = (total == 0);
+  pl->U = U;
   if (total != 0) {
-    int L = 64 - __clzll((long long)total);
-    unsigned __int128 rho = (((unsigned __int128)(u64)s.n_out_global) << (32 + L)) / total + 1;
-    u64 rhi = (u64)(rho >> 64), rlo = (u64)rho;
-    int bl = rhi ? 128 - __clzll((long long)rhi) : 64 - __clzll((long long)rlo);
-    int a = bl > 31 ? bl - 31 : 0;
-    pl->rho = (uint32_t)(rho >> a) + 1u;
-    pl->shift = L - a;
+    const int L = 64 - __clzll((long long)total);
+    pl->L = L;
+    pl->rho = (u64)((((unsigned __int128)(u64)n_out_global) << (32 + L)) / total) + 1ull;
   } else {
-    pl->rho = 0; pl->shift = 0;
+    pl->L = 1;
+    pl->rho = 0;
   }
-  const uint32_t t_next = s.ctl->t + (uint32_t)s.delta;
-  if (s.explicit_U) pl->U = s.U_value;
-  else pl->U = philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)s.seed, (uint32_t)(s.seed >> 32)).x;
 }
 
 __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   __shared__ u64 s_prefix;
   __shared__ uint32_t s_tile, s_last;
   __shared__ double s_red[kWarps][kMaxRec];
+  __shared__ double s_tot[kMaxRec];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&s.ctl->scan_counter, 1u);
   __syncthreads();
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
     v[k] = S;
     tsum += S;
   }
-  u64 incl = warp_inclusive_scan(tsum, lane);
+  u64 incl = warp_inclusive_scan_u64(tsum, lane);
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   u64 wbase = 0, agg = 0;
@@ -280,8 +285,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
           do { w = st[idx]; } while ((w >> 62) == 0);
         }
         uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        // lanes at or before the first inclusive entry contribute
-        int first = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        int first = incl_mask ? __ffs(incl_mask) - 1 : 32;  // lanes up to the first inclusive entry contribute
         u64 c = (lane <= first) ? (w & kValMask) : 0ull;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) c += shfl_xor_u64(c, d);
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
 
   // ---- moment records -> per-CTA partial at the global exponent
   const int R = 3 + 2 * s.nx;
-  const bool have_rec = (s.rec != nullptr) && (s.nrec > 0) && !(s.delta == 0);
+  const bool have_rec = (s.rec != nullptr) && (s.nrec > 0) && (s.delta != 0);
   if (have_rec) {
     double acc[kMaxRec];
 #pragma unroll
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       if (J < s.nrec) {
         const double* rc = s.rec + (size_t)J * kMaxRec;
         double et = rc[0];
-        if (et > -2.0e9) {
+        if (et > -1.0e9) {
           double f = pow2d((int)et - emax);
           for (int r = 1; r < R; ++r) acc[r] += rc[r] * (r == 2 ? f * f : f);
         }
@@ -347,7 +351,6 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  __shared__ double s_tot[kMaxRec];
   if (have_rec && tid >= 1 && tid < R) {
     double x = 0;
     for (int c = 0; c < s.nscan; ++c) x += ((volatile double*)s.part)[(size_t)c * kMaxRec + tid];
@@ -358,26 +361,31 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
     PlanDev* pl = s.plan;
     const u64 total = ((volatile PlanDev*)pl)->local_total;
     pl->emax = emax;
-    if (s.world <= 1) finalize_plan(s, total);
+    if (s.world <= 1) {
+      const uint32_t t_next = s.ctl->t + (uint32_t)s.delta;
+      const uint32_t U = s.explicit_U ? s.U_value
+                                      : philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)s.seed, (uint32_t)(s.seed >> 32)).x;
+      pl->base = 0;
+      finalize_plan(pl, total, s.n_out_global, U);
+    }
     if (have_rec) {
       const double sw = s_tot[1], sw2 = s_tot[2];
       pl->sw = sw; pl->sw2 = sw2;
-      pl->log_sw = log(sw) + (double)(emax - 31) * 0.6931471805599453;
-      float cen[PZ_MAX_NX];
-      for (int d = 0; d < s.nx; ++d) {
-        cen[d] = pl->center[d];
-        double m = s_tot[3 + d] / sw;
-        pl->mean[d] = (double)cen[d] + m;
-        pl->var[d] = s_tot[3 + s.nx + d] / sw - m * m;
-      }
+      for (int d = 0; d < s.nx; ++d) { pl->sx[d] = s_tot[3 + d]; pl->sxx[d] = s_tot[3 + s.nx + d]; }
       if (s.world <= 1) {
-        for (int d = 0; d < s.nx; ++d) pl->center[d] = (float)pl->mean[d];
-        if (s.summ) {
-          pz_step_summary* o = s.summ + (s.ctl->t % kObsRing);
+        pz_step_summary* o = s.summ ? s.summ + (s.ctl->t % kObsRing) : nullptr;
+        for (int d = 0; d < s.nx; ++d) {
+          const float cen = pl->center[d];
+          const double m = pl->sx[d] / sw;
+          const double mean = (double)cen + m, var = pl->sxx[d] / sw - m * m;
+          pl->center[d] = (float)mean;
+          if (o) { o->mean[d] = mean; o->var[d] = var; }
+        }
+        if (o) {
+          for (int d = s.nx; d < PZ_MAX_NX; ++d) { o->mean[d] = 0.0; o->var[d] = 0.0; }
           o->step = s.ctl->t;
-          o->log_evidence_inc = pl->log_sw - log((double)s.n_out_global) + s.ll_const;
+          o->log_evidence_inc = log(sw) + (double)(emax - 23) * 0.6931471805599453 - log((double)s.n_out_global) + s.ll_const;
           o->ess = sw * sw / sw2;
-          for (int d = 0; d < PZ_MAX_NX; ++d) { o->mean[d] = d < s.nx ? pl->mean[d] : 0.0; o->var[d] = d < s.nx ? pl->var[d] : 0.0; }
           o->n_migrated = 0;
           o->e_max = emax;
           o->reserved = 0;
@@ -410,9 +418,9 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
   const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const PlanDev* pl = p.plan;
   if (J < p.ntiles_out) {
-    SlotMap sm{pl->rho, pl->shift, pl->U, p.n_out_global};
+    SlotMap sm(pl, p.n_out_global);
     const u64 base = pl->base;
-    const int64_t j0 = p.slot_base + J * p.tile_out;
+    const uint32_t j0 = (uint32_t)(p.slot_base + J * p.tile_out);
     // min b in [0, nblk) with slot_end(base + pb[b+1]) > j0
     int64_t lo = 0, hi = p.nblk;
     while (lo < hi) {
@@ -432,10 +440,9 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// pf_step_tile: the fused resample + gather + propagate + weight kernel
+// resample phase shared by the step and the ancestor kernels
 // ------------------------------------------------------------------------------------------
-// Input side: one warp owns one canonical input block at a time (two half-blocks of 128
-// particles, one float4 per lane per state dimension => 512-byte coalesced requests).
+// Sources: what one particle contributes (its weight) and what is staged for its children.
 template <int NX, int NY>
 struct StateSource {
   const float* x;      // X[cur]
@@ -444,26 +451,28 @@ struct StateSource {
   float y[NY];
   bool uniform;
   float v[NX][4];
-  __device__ __forceinline__ void load(int64_t i0, int32_t (&n)[4], uint32_t (&mm)[4]) {
+  template <bool FULL>
+  __device__ __forceinline__ void load(int64_t i0, int32_t eb, uint32_t (&q)[4]) {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
-      float4 q = *reinterpret_cast<const float4*>(x + (size_t)d * ld + i0);
-      v[d][0] = q.x; v[d][1] = q.y; v[d][2] = q.z; v[d][3] = q.w;
+      const float4 f = *reinterpret_cast<const float4*>(x + (size_t)d * ld + i0);
+      v[d][0] = f.x; v[d][1] = f.y; v[d][2] = f.z; v[d][3] = f.w;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (i0 + k < n_local) {
-        if (uniform) { n[k] = 0; mm[k] = 1u << 23; }
-        else {
-          float xs[NX];
+      int32_t n; uint32_t mm;
+      if (uniform) { n = 0; mm = 1u << 23; }
+      else {
+        float xs[NX];
 #pragma unroll
-          for (int d = 0; d < NX; ++d) xs[d] = v[d][k];
-          weight_split(lg_logweight<NX, NY>(*m, xs, y), n[k], mm[k]);
-        }
-      } else { n[k] = kNZero; mm[k] = 0; }
+        for (int d = 0; d < NX; ++d) xs[d] = v[d][k];
+        weight_split(lg_logweight<NX, NY>(*m, xs, y), n, mm);
+      }
+      q[k] = q_at(mm, n, eb);
+      if (!FULL && i0 + k >= n_local) q[k] = 0;
     }
   }
-  __device__ __forceinline__ void put(float* s_par, int stride, int slot, int k, int64_t) const {
+  __device__ __forceinline__ void put(float* s_par, int stride, uint32_t slot, int k, int64_t) const {
 #pragma unroll
     for (int d = 0; d < NX; ++d) s_par[d * stride + slot] = v[d][k];
   }
@@ -472,61 +481,97 @@ struct StateSource {
 struct LogwSource {  // generic path: stored log-weights, payload = particle index
   const float* lw;
   int64_t n_local;
-  __device__ __forceinline__ void load(int64_t i0, int32_t (&n)[4], uint32_t (&mm)[4]) {
-    float4 q = *reinterpret_cast<const float4*>(lw + i0);
-    float w[4] = {q.x, q.y, q.z, q.w};
+  template <bool FULL>
+  __device__ __forceinline__ void load(int64_t i0, int32_t eb, uint32_t (&q)[4]) {
+    const float4 f = *reinterpret_cast<const float4*>(lw + i0);
+    const float w[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (i0 + k < n_local) weight_split(w[k], n[k], mm[k]);
-      else { n[k] = kNZero; mm[k] = 0; }
+      int32_t n; uint32_t mm;
+      weight_split(w[k], n, mm);
+      q[k] = q_at(mm, n, eb);
+      if (!FULL && i0 + k >= n_local) q[k] = 0;
     }
   }
-  __device__ __forceinline__ void put(float* s_par, int, int slot, int k, int64_t i0) const {
+  __device__ __forceinline__ void put(float* s_par, int, uint32_t slot, int k, int64_t i0) const {
     reinterpret_cast<int32_t*>(s_par)[slot] = (int32_t)(i0 + k);
   }
 };
 
-// Resample phase shared by the fused and the ancestor kernels: fills the shared-memory parent
-// slots of output tile [j0, jend).
+// One half-block (128 particles, 4 per lane): fixed-point weights, warp scan, slot ranges, and
+// a head mark at the first child slot of every particle that has children in [j0, jend) -- plus
+// one at every 128-slot segment boundary its children span, so that each output segment can
+// resolve its parents with a warp-local max-scan.
+template <class Source, bool FULL>
+__device__ __forceinline__ void resample_half(Source& src, float* s_par, uint16_t* s_head, int stride, int64_t i0,
+                                              int32_t eb, uint32_t ksh, u64 Pb, const SlotMap& sm, uint32_t j0,
+                                              uint32_t jend, int lane, uint32_t& carry, uint32_t& o_prev) {
+  uint32_t q[4];
+  src.template load<FULL>(i0, eb, q);
+  const uint32_t c0 = q[0], c1 = c0 + q[1], c2 = c1 + q[2], c3 = c2 + q[3];
+  const uint32_t incl = warp_inclusive_scan_u32(c3, lane);
+  const uint32_t excl = carry + incl - c3;
+  carry += __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t o[4];
+  o[0] = sm.slot_end(Pb + (u64)((excl + c0) >> ksh));
+  o[1] = sm.slot_end(Pb + (u64)((excl + c1) >> ksh));
+  o[2] = sm.slot_end(Pb + (u64)((excl + c2) >> ksh));
+  o[3] = sm.slot_end(Pb + (u64)((excl + c3) >> ksh));
+  uint32_t o_lo = __shfl_up_sync(0xffffffffu, o[3], 1);
+  if (lane == 0) o_lo = o_prev;
+  o_prev = __shfl_sync(0xffffffffu, o[3], 31);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t lo = max(o_lo, j0), hi = min(o[k], jend);
+    if (lo < hi) {
+      uint32_t slot = lo - j0;
+      const uint32_t slot_hi = hi - j0;
+      do {
+        s_head[slot] = (uint16_t)(slot + 1);
+        src.put(s_par, stride, slot, k, i0);
+        slot = (slot + 128u) & ~127u;
+      } while (slot < slot_hi);
+    }
+    o_lo = o[k];
+  }
+}
+
 template <class Source>
-__device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const int32_t* eb_in,
-                                              const u64* pb, int64_t nblk, int64_t b_first, const SlotMap& sm,
-                                              u64 base, int32_t emax, int64_t j0, int64_t jend, int lane, int warp) {
-  for (int64_t b = b_first + warp; b < nblk; b += kWarps) {
-    const u64 Pb = base + pb[b];
-    int64_t o_blk = sm.slot_end(Pb);
-    if (o_blk >= jend) break;  // this and every later block start past the tile
-    const int32_t eb = eb_in[b];
-    if (eb == kNZero) continue;
+__device__ __forceinline__ void resample_tile(Source& src, float* s_par, uint16_t* s_head, int stride,
+                                              const int32_t* __restrict__ ebx, const u64* __restrict__ pbx, u64 base,
+                                              int64_t b_first, int64_t b_end, int64_t n_items, const SlotMap& sm,
+                                              int32_t emax, uint32_t j0, uint32_t jend, int lane, int warp) {
+  for (int64_t b = b_first + warp; b < b_end; b += kWarps) {
+    const u64 Pb = base + pbx[b];
+    uint32_t o_prev = sm.slot_end(Pb);
+    if (o_prev >= jend) break;  // this and every later block start past the tile
+    const int32_t eb = ebx[b];
     const uint32_t ksh = (uint32_t)(emax - eb);
-    if (ksh >= 64u) continue;
-    u64 carry = 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int64_t i0 = b * kBlk + half * 128 + lane * 4;
-      int32_t n[4]; uint32_t m[4];
-      src.load(i0, n, m);
-      u64 c[4];
-      u64 run = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { run += q_at(m[k], n[k], eb); c[k] = run; }
-      const u64 incl = warp_inclusive_scan(run, lane);
-      const u64 excl = carry + incl - run;
-      carry += shfl_u64(incl, 31);
-      int64_t o_lo = sm.slot_end(Pb + (excl >> ksh));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool has = (k == 0) ? (c[0] != 0) : (c[k] != c[k - 1]);
-        if (has) {
-          const int64_t o_hi = sm.slot_end(Pb + ((excl + c[k]) >> ksh));
-          const int64_t lo = o_lo > j0 ? o_lo : j0;
-          const int64_t hi = o_hi < jend ? o_hi : jend;
-          for (int64_t sl = lo; sl < hi; ++sl) src.put(s_par, stride, (int)(sl - j0), k, i0);
-          o_lo = o_hi;
-        }
-      }
+    if (eb == kNZero || ksh >= 32u) continue;  // no mass at the global scale
+    uint32_t carry = 0;
+    const int64_t i0 = b * kBlk + lane * 4;
+    if ((b + 1) * kBlk <= n_items) {
+      resample_half<Source, true>(src, s_par, s_head, stride, i0, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
+      resample_half<Source, true>(src, s_par, s_head, stride, i0 + 128, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
+    } else {
+      resample_half<Source, false>(src, s_par, s_head, stride, i0, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
+      resample_half<Source, false>(src, s_par, s_head, stride, i0 + 128, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
     }
   }
+}
+
+// Parent slot (+1) of the lane's 4 slots of one 128-slot segment.
+__device__ __forceinline__ void segment_parents(const uint16_t* s_head, int sl, int lane, uint32_t (&h)[4]) {
+  const uint2 hv = *reinterpret_cast<const uint2*>(&s_head[sl]);
+  h[0] = hv.x & 0xffffu;
+  h[1] = max(h[0], hv.x >> 16);
+  h[2] = max(h[1], hv.y & 0xffffu);
+  h[3] = max(h[2], hv.y >> 16);
+  const uint32_t incl = warp_inclusive_max_u32(h[3], lane);
+  uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = max(h[k], excl);
 }
 
 struct TileArgs {
@@ -536,11 +581,15 @@ struct TileArgs {
 
 // MODE 0: fused systematic resample (parents staged by resample_tile)
 // MODE 1: parents gathered through a stored ancestor array (multinomial / debug path)
+// resident CTAs per SM the register allocation is held to (NX = 1 / 4 / 6)
+constexpr int min_ctas(int nx) { return nx == 1 ? 4 : (nx <= 4 ? 3 : 2); }
+
 template <int NX, int NY, int TO, int MODE>
-__global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__ TileArgs ta) {
-  extern __shared__ __align__(16) float s_par[];  // [NX][TO]
+__global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __grid_constant__ TileArgs ta) {
+  extern __shared__ __align__(16) float s_par[];  // [NX][TO] parents, then [TO] head marks (u16)
   __shared__ int32_t s_eref[kWarps];
   __shared__ double s_red[kWarps][kMaxRec];
+  uint16_t* s_head = reinterpret_cast<uint16_t*>(s_par + NX * TO);
   const StepArgs& a = ta.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t t = a.ctl->t;
@@ -550,7 +599,7 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
   const PlanDev* pl = a.plan;
   const int64_t j0l = (int64_t)blockIdx.x * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
-  const int64_t j0 = a.slot_base + j0l, jend = a.slot_base + jendl;
+  const uint32_t j0 = (uint32_t)(a.slot_base + j0l), jend = (uint32_t)(a.slot_base + jendl);
   const int nslots = (int)(jendl - j0l);
 
   float y_new[NY];
@@ -558,15 +607,20 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
   for (int k = 0; k < NY; ++k) y_new[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
 
   if constexpr (MODE == 0) {
-    SlotMap sm{pl->rho, pl->shift, pl->U, a.n_global};
+    {  // clear the head marks: TO u16 = TO/8 uint4
+      uint4* hz = reinterpret_cast<uint4*>(s_head);
+      for (int i = tid; i < TO / 8; i += kThreads) hz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    SlotMap sm(pl, a.n_global);
     StateSource<NX, NY> src;
     src.x = xin; src.ld = a.ld; src.n_local = a.n_local; src.m = &a.model;
     src.uniform = a.ctl->uniform_in != 0;
     const uint32_t tp = (t + kObsRing - 1) % kObsRing;
 #pragma unroll
     for (int k = 0; k < NY; ++k) src.y[k] = a.obs[(size_t)tp * PZ_MAX_NY + k];
-    resample_tile(src, s_par, TO, a.eb[cur], a.pb, a.nblk, (int64_t)a.tile_start[blockIdx.x], sm, pl->base,
-                  pl->emax, j0, jend, lane, warp);
+    resample_tile(src, s_par, s_head, TO, a.eb[cur], a.pb, pl->base, (int64_t)a.tile_start[blockIdx.x], a.nblk,
+                  a.n_local, sm, pl->emax, j0, jend, lane, warp);
   } else {
     for (int sidx = tid; sidx < nslots; sidx += kThreads) {
       const int64_t p = ta.anc[j0l + sidx];
@@ -576,7 +630,7 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
   }
   __syncthreads();
 
-  // ---- output side: one warp owns one canonical output block (two halves of 128 slots)
+  // ---- output side: one warp owns one canonical output block (two segments of 128 slots)
   double acc_sw = 0, acc_sw2 = 0, acc_sx[NX], acc_sxx[NX];
 #pragma unroll
   for (int d = 0; d < NX; ++d) { acc_sx[d] = 0; acc_sxx[d] = 0; }
@@ -584,6 +638,7 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
   float cen[NX];
 #pragma unroll
   for (int d = 0; d < NX; ++d) cen[d] = pl->center[d];
+  const bool full_tile = (nslots == TO);
 
   for (int ob = warp; ob * kBlk < nslots; ob += kWarps) {
     int32_t nn[8]; uint32_t mm[8];
@@ -591,13 +646,26 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
-      float xp[NX][4], z[NX][4];
+      float xp[NX][4];
 #pragma unroll
       for (int d = 0; d < NX; ++d) {
-        float4 q = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
-        xp[d][0] = q.x; xp[d][1] = q.y; xp[d][2] = q.z; xp[d][3] = q.w;
+        const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
+        xp[d][0] = f.x; xp[d][1] = f.y; xp[d][2] = f.z; xp[d][3] = f.w;
       }
-      lg_noise4<NX>(j0 + sl, t, a.seed, z);
+      if constexpr (MODE == 0) {
+        uint32_t h[4];
+        segment_parents(s_head, sl, lane, h);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (h[k] != (uint32_t)(sl + k + 1) && h[k] != 0u) {
+#pragma unroll
+            for (int d = 0; d < NX; ++d) xp[d][k] = s_par[d * TO + h[k] - 1];
+          }
+        }
+        __syncwarp();  // every parent read of this segment precedes the write-back below
+      }
+      float z[NX][4];
+      lg_noise4<NX>(j0 + (uint32_t)sl, t, a.seed, z);
       float xo[NX][4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -607,64 +675,72 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
         lg_propagate<NX>(a.model, xs, zs, xn);
 #pragma unroll
         for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-        if (sl + k < nslots) {
-          weight_split(lg_logweight<NX, NY>(a.model, xn, y_new), nn[half * 4 + k], mm[half * 4 + k]);
-          if (mm[half * 4 + k] && nn[half * 4 + k] > emx) emx = nn[half * 4 + k];
-        } else { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
+        weight_split(lg_logweight<NX, NY>(a.model, xn, y_new), nn[half * 4 + k], mm[half * 4 + k]);
+        if (!full_tile && sl + k >= nslots) { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
+        emx = max(emx, nn[half * 4 + k]);
       }
-      if (sl < nslots) {
+      if (full_tile || sl < nslots) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          float4 q = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
-          *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = q;
-          *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = q;
+          const float4 f = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
+          *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = f;
+          *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = f;
         }
       }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      int32_t o = __shfl_xor_sync(0xffffffffu, emx, d);
-      emx = o > emx ? o : emx;
-    }
-    // block sum at the block exponent + centred moments at the warp's running exponent
-    u64 ssum = 0;
+    for (int d = 16; d > 0; d >>= 1) emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, d));
+    // block sum at the block exponent + centred moments (fp32 per lane, fp64 across blocks)
+    uint32_t ssum = 0;
     if (emx != kNZero) {
+      float p_sw = 0.f, p_sw2 = 0.f, p_sx[NX], p_sxx[NX];
+#pragma unroll
+      for (int d = 0; d < NX; ++d) { p_sx[d] = 0.f; p_sxx[d] = 0.f; }
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int sl = ob * kBlk + half * 128 + lane * 4;
+        float xv[NX][4];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
+          xv[d][0] = f.x; xv[d][1] = f.y; xv[d][2] = f.z; xv[d][3] = f.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t q = q_at(mm[half * 4 + k], nn[half * 4 + k], emx);
+          ssum += q;
+          const float w = __uint2float_rn(q);  // exact: q < 2^24
+          p_sw = __fadd_rn(p_sw, w);
+          p_sw2 = __fmaf_rn(w, w, p_sw2);
+#pragma unroll
+          for (int d = 0; d < NX; ++d) {
+            const float dx = q ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
+            const float wd = __fmul_rn(w, dx);
+            p_sx[d] = __fadd_rn(p_sx[d], wd);
+            p_sxx[d] = __fmaf_rn(wd, dx, p_sxx[d]);
+          }
+        }
+      }
       double f = 1.0;
       if (aref == kNZero) aref = emx;
       else if (emx > aref) {
-        double g = pow2d(aref - emx);
+        const double g = pow2d(aref - emx);
         acc_sw *= g; acc_sw2 *= g * g;
 #pragma unroll
         for (int d = 0; d < NX; ++d) { acc_sx[d] *= g; acc_sxx[d] *= g; }
         aref = emx;
       } else f = pow2d(emx - aref);
-      __syncwarp();
+      acc_sw += f * (double)p_sw; acc_sw2 += (f * f) * (double)p_sw2;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int sl = ob * kBlk + half * 128 + lane * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t q = q_at(mm[half * 4 + k], nn[half * 4 + k], emx);
-          ssum += q;
-          if (q) {
-            const double w = (double)q * f;
-            acc_sw += w; acc_sw2 += w * w;
-#pragma unroll
-            for (int d = 0; d < NX; ++d) {
-              const double dx = (double)__fsub_rn(s_par[d * TO + sl + k], cen[d]);
-              const double wd = w * dx;
-              acc_sx[d] += wd; acc_sxx[d] += wd * dx;
-            }
-          }
-        }
-      }
+      for (int d = 0; d < NX; ++d) { acc_sx[d] += f * (double)p_sx[d]; acc_sxx[d] += f * (double)p_sxx[d]; }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ssum += shfl_xor_u64(ssum, d);
+    for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
     if (lane == 0) {
       const int64_t bo = (j0l / kBlk) + ob;
       a.eb[nxt][bo] = emx;
-      a.sb[bo] = ssum;
+      a.sb[bo] = (u64)ssum;
     }
   }
 
@@ -673,7 +749,7 @@ __global__ void __launch_bounds__(kThreads) pf_step_tile(const __grid_constant__
   __syncthreads();
   int32_t etile = kNZero;
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) etile = s_eref[w] > etile ? s_eref[w] : etile;
+  for (int w = 0; w < kWarps; ++w) etile = max(etile, s_eref[w]);
   {
     const double g = (aref == kNZero) ? 0.0 : pow2d(aref - etile);
     double vals[kMaxRec];
@@ -711,28 +787,25 @@ __global__ void __launch_bounds__(kThreads) pf_stats_from_lw(const float* __rest
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int64_t i0 = b * kBlk + half * 128 + lane * 4;
-    float4 q = *reinterpret_cast<const float4*>(lw + i0);
-    float w[4] = {q.x, q.y, q.z, q.w};
+    const float4 f = *reinterpret_cast<const float4*>(lw + i0);
+    const float w[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (i0 + k < n) weight_split(w[k], nn[half * 4 + k], mm[half * 4 + k]);
-      else { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
-      if (mm[half * 4 + k] && nn[half * 4 + k] > emx) emx = nn[half * 4 + k];
+      weight_split(w[k], nn[half * 4 + k], mm[half * 4 + k]);
+      if (i0 + k >= n) { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
+      emx = max(emx, nn[half * 4 + k]);
     }
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    int32_t o = __shfl_xor_sync(0xffffffffu, emx, d);
-    emx = o > emx ? o : emx;
-  }
-  u64 ssum = 0;
+  for (int d = 16; d > 0; d >>= 1) emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, d));
+  uint32_t ssum = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) ssum += q_at(mm[k], nn[k], emx);
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) ssum += shfl_xor_u64(ssum, d);
+  for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
   if (lane == 0) {
     eb[b] = emx;
-    sb[b] = ssum;
+    sb[b] = (emx == kNZero) ? 0ull : (u64)ssum;
     if (emx != kNZero) atomicMax(&ctl->emax_acc, emx);
   }
 }
@@ -748,18 +821,26 @@ __global__ void pf_ctl_reset(CtlDev* ctl) {
 template <int TO>
 __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   __shared__ __align__(16) int32_t s_anc[TO];
+  __shared__ __align__(16) uint16_t s_head[TO];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PlanDev* pl = g.plan;
   const int64_t j0 = (int64_t)blockIdx.x * TO;
   const int64_t jend = (j0 + TO < g.n) ? j0 + TO : g.n;
-  SlotMap sm{pl->rho, pl->shift, pl->U, g.n};
+  SlotMap sm(pl, g.n);
   LogwSource src{g.lw, g.n};
-  for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = -1;
+  for (int sidx = tid; sidx < TO; sidx += kThreads) { s_anc[sidx] = -1; s_head[sidx] = 0; }
   __syncthreads();
-  resample_tile(src, reinterpret_cast<float*>(s_anc), TO, generic_eb(g), g.pb, g.nblk, (int64_t)g.tile_start[blockIdx.x], sm,
-                pl->base, pl->emax, j0, jend, lane, warp);
+  resample_tile(src, reinterpret_cast<float*>(s_anc), s_head, TO, generic_eb(g), g.pb, pl->base,
+                (int64_t)g.tile_start[blockIdx.x], g.nblk, g.n, sm, pl->emax, (uint32_t)j0, (uint32_t)jend, lane, warp);
   __syncthreads();
-  for (int sidx = tid; j0 + sidx < jend; sidx += kThreads) g.anc[j0 + sidx] = s_anc[sidx];
+  for (int seg = warp; seg * 128 < (int)(jend - j0); seg += kWarps) {
+    const int sl = seg * 128 + lane * 4;
+    uint32_t h[4];
+    segment_parents(s_head, sl, lane, h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (j0 + sl + k < jend) g.anc[j0 + sl + k] = h[k] ? s_anc[h[k] - 1] : -1;
+  }
 }
 
 // N iid categorical draws on the canonical fixed-point CDF (resample2, Inference.hs:57-61)
@@ -831,8 +912,6 @@ int launch_init(const StepArgs& a, cudaStream_t s) {
   return 1;
 }
 
-static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s);
-
 static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   ScanArgs sc{};
   sc.eb0 = a.eb[0]; sc.eb1 = a.eb[1];
@@ -845,14 +924,6 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   return sc;
 }
 
-// Scan + partition of the population in buffer (ctl->t + delta) & 1.  delta = 1 after a step.
-static int scan_partition(const StepArgs& a, int delta, int tile_out, cudaStream_t s) {
-  ScanArgs sc = make_scan(a, delta, delta == 1);
-  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
-  partition(a, tile_out, delta, s);
-  return 2;
-}
-
 static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
   PartArgs pa{a.pb, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
               a.ntiles_out, tile_out, a.nscan, delta};
@@ -863,6 +934,14 @@ static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s)
 
 int launch_partition_only(const StepArgs& a, int tile_out, cudaStream_t s) { return partition(a, tile_out, 0, s); }
 
+// Scan + partition of the population in buffer (ctl->t + delta) & 1.  delta = 1 after a step.
+static int scan_partition(const StepArgs& a, int delta, int tile_out, cudaStream_t s) {
+  ScanArgs sc = make_scan(a, delta, delta == 1);
+  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  partition(a, tile_out, delta, s);
+  return 2;
+}
+
 int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
   return scan_partition(a, 0, tile_out, s);
 }
@@ -870,7 +949,7 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
 template <int NX, int NY, int TO, int MODE>
 static void launch_tile(const TileArgs& ta, cudaStream_t s) {
   auto kern = pf_step_tile<NX, NY, TO, MODE>;
-  size_t smem = (size_t)NX * TO * sizeof(float);
+  size_t smem = (size_t)NX * TO * sizeof(float) + (size_t)TO * sizeof(uint16_t);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -879,44 +958,45 @@ static void launch_tile(const TileArgs& ta, cudaStream_t s) {
   kern<<<ta.a.ntiles_out, kThreads, smem, s>>>(ta);
 }
 
-// anc == nullptr: fused systematic step; else parents come from the stored ancestor array.
-int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s) {
-  TileArgs ta{a, anc};
-  const int nx = a.model.nx, ny = a.model.ny;
-  const bool fused = (anc == nullptr);
+static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
+  const int nx = ta.a.model.nx, ny = ta.a.model.ny;
+  const bool fused = (ta.anc == nullptr);
 #define PZ_DISPATCH(NXv, NYv, TOv)                                   \
   if (nx == NXv && ny == NYv) {                                      \
     if (fused) launch_tile<NXv, NYv, TOv, 0>(ta, s);                 \
     else launch_tile<NXv, NYv, TOv, 1>(ta, s);                       \
-  } else
+    return 1;                                                        \
+  }
   PZ_DISPATCH(1, 1, 4096)
   PZ_DISPATCH(4, 2, 2048)
   PZ_DISPATCH(6, 3, 2048)
-  { return -1; }
 #undef PZ_DISPATCH
-  return 1 + scan_partition(a, 1, fused_tile_out(nx), s);
+  return -1;
+}
+
+// anc == nullptr: fused systematic step; else parents come from the stored ancestor array.
+int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s) {
+  TileArgs ta{a, anc};
+  if (dispatch_tile(ta, s) < 0) return -1;
+  return 1 + scan_partition(a, 1, fused_tile_out(a.model.nx), s);
+}
+
+int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
+  TileArgs ta{a, nullptr};
+  cudaEventRecord(ev[0], s);
+  if (dispatch_tile(ta, s) < 0) return -1;
+  cudaEventRecord(ev[1], s);
+  ScanArgs sc = make_scan(a, 1, true);
+  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  cudaEventRecord(ev[2], s);
+  partition(a, fused_tile_out(a.model.nx), 1, s);
+  cudaEventRecord(ev[3], s);
+  return 3;
 }
 
 int launch_ctl_reset(CtlDev* ctl, cudaStream_t s) {
   pf_ctl_reset<<<1, 1, 0, s>>>(ctl);
   return 1;
-}
-
-int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
-  TileArgs ta{a, nullptr};
-  const int nx = a.model.nx, ny = a.model.ny;
-  cudaEventRecord(ev[0], s);
-  if (nx == 1 && ny == 1) launch_tile<1, 1, 4096, 0>(ta, s);
-  else if (nx == 4 && ny == 2) launch_tile<4, 2, 2048, 0>(ta, s);
-  else if (nx == 6 && ny == 3) launch_tile<6, 3, 2048, 0>(ta, s);
-  else return -1;
-  cudaEventRecord(ev[1], s);
-  ScanArgs sc = make_scan(a, 1, true);
-  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
-  cudaEventRecord(ev[2], s);
-  partition(a, fused_tile_out(nx), 1, s);
-  cudaEventRecord(ev[3], s);
-  return 3;
 }
 
 int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s) {

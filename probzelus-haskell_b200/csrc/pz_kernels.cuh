@@ -39,21 +39,19 @@ struct LgDev {
   int32_t nx, ny;
 };
 
-// Resampling plan + posterior summary of one weighted population (device resident).
+// Resampling plan + posterior moment sums of one weighted population (device resident).
 struct PlanDev {
   uint64_t total;       // T: global fixed-point total
   uint64_t base;        // CDF offset of this rank's first particle (0 on one GPU)
   uint64_t local_total; // this rank's share of T
-  uint32_t rho;         // slot-position multiplier (31 significant bits)
-  int32_t shift;        // pos = (C * rho) >> shift   (<< when negative)
+  uint64_t rho;         // floor(N * 2^(32+L) / T) + 1: slot position of C is floor(C * rho / 2^L) * 2^-32
+  int32_t L;            // bit length of T
   int32_t emax;         // global block exponent
   int32_t degenerate;   // 1 when T == 0
   uint32_t U;           // the uniform of the resample that will consume this plan
-  uint32_t pad0;
   float center[8];      // fp32 posterior mean: centring constants of the next moment sums
-  double sw, sw2;       // sum w, sum w^2 at scale 2^(emax-31)
-  double mean[PZ_MAX_NX], var[PZ_MAX_NX];
-  double log_sw;        // log(sum w) + (emax-31) ln 2
+  double sw, sw2;       // sum w, sum w^2 at scale 2^(emax-23)
+  double sx[PZ_MAX_NX], sxx[PZ_MAX_NX];  // centred first / second moment sums
 };
 
 // Step counter and accumulators living in device memory so that one captured CUDA graph

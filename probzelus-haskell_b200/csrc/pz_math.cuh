@@ -46,15 +46,14 @@ constexpr float kLog2e = 0x1.715476p+0f;
 constexpr float kNeg2Ln2 = -0x1.62e430p+0f;
 constexpr float kHalfPi = 0x1.921fb6p+0f;
 
-constexpr int32_t kNZero = INT32_MIN;  // exponent marker of a zero weight
+constexpr int32_t kNZero = -(1 << 30);  // exponent marker of a zero weight
 
-// log-weight -> (n, m): weight = m * 2^(n-23).  -inf / +inf / NaN / out-of-range -> m = 0.
+// log-weight -> (n, m): weight = m * 2^(n-23), m in [2^22.5, 2^23.5].
+// -inf / +inf / NaN / out-of-range -> (kNZero, 0).
 __device__ __forceinline__ void weight_split(float lw, int32_t& n, uint32_t& m) {
-  n = kNZero; m = 0;
-  float e = __fmul_rn(lw, kLog2e);
-  if (!(lw > -INFINITY) || !(lw < INFINITY) || !(e > -1.0e6f) || !(e < 1.0e6f)) return;
-  float r = rintf(e);
-  float f = __fsub_rn(e, r);
+  const float e = __fmul_rn(lw, kLog2e);
+  const float r = rintf(e);
+  const float f = __fsub_rn(e, r);
   float p = 0x1.00c0e6p-16f;
   p = __fmaf_rn(p, f, 0x1.444004p-13f);
   p = __fmaf_rn(p, f, 0x1.5d8776p-10f);
@@ -63,15 +62,17 @@ __device__ __forceinline__ void weight_split(float lw, int32_t& n, uint32_t& m) 
   p = __fmaf_rn(p, f, 0x1.ebfbe0p-3f);
   p = __fmaf_rn(p, f, 0x1.62e430p-1f);
   p = __fmaf_rn(p, f, 1.0f);
-  n = __float2int_rn(r);
-  m = (uint32_t)__float2int_rn(__fmul_rn(p, 8388608.0f));
+  const bool ok = fabsf(e) < 1.0e6f;  // false for NaN and +-inf
+  n = ok ? __float2int_rn(r) : kNZero;
+  m = ok ? (uint32_t)__float2int_rn(__fmul_rn(p, 8388608.0f)) : 0u;
 }
 
-// fixed-point weight of (n, m) at block exponent eb
+// fixed-point weight of (n, m) at block exponent eb >= n: m >> (eb - n), 0 once the shift
+// reaches 32 (PTX shr clamps the shift amount, so no compare is needed)
 __device__ __forceinline__ uint32_t q_at(uint32_t m, int32_t n, int32_t eb) {
-  if (m == 0) return 0u;
-  uint32_t sh = (uint32_t)(eb - n);  // eb >= n for every non-zero member of the block
-  return sh < 32u ? ((m << 8) >> sh) : 0u;
+  uint32_t q;
+  asm("shr.u32 %0, %1, %2;" : "=r"(q) : "r"(m), "r"((uint32_t)(eb - n)));
+  return q;
 }
 
 // two 32-bit words -> two independent N(0,1) draws

@@ -217,3 +217,25 @@ def oracle_multinomial(lw32, seed, step):
     anc = np.zeros(n, dtype=np.int32)
     rc = lib.pzo_resample_multinomial(ptr(lw32, C.c_float), n, seed, step, ptr(anc, C.c_int32))
     return rc, anc
+
+
+def assert_within_mc_tolerance(est, exact, what):
+    """Monte Carlo parity gate: est[seed, step, dim] against exact[step, dim].
+
+    (i)  the stated tolerance: every single run lies within 3 standard errors of the exact value,
+         SE = the run-to-run standard deviation at this N (estimated over the seeds): at most 2 %
+         of the (seed, step, dim) cells may exceed 3 SE and none 5 SE;
+    (ii) bias: the time-averaged error of each seed is an independent sample; its mean over the
+         seeds must lie within 4.5 standard errors of zero per dimension.  (Particle filters carry
+         an O(1/N) bias, so this S-fold tighter gate uses a wider multiple than (i); per-step
+         z-scores of the seed average are autocorrelated in time and are therefore not gated
+         one by one.)"""
+    S = est.shape[0]
+    err = est - exact[None]
+    sd = est.std(axis=0, ddof=1)
+    z1 = err / np.maximum(sd, 1e-300)[None]
+    assert np.mean(np.abs(z1) > 3) <= 0.02 and np.max(np.abs(z1)) < 5.5, (what, "single runs beyond 3 SE", np.mean(np.abs(z1) > 3), np.max(np.abs(z1)))
+    per_seed_bias = err.mean(axis=1)                       # [seed, dim]
+    se_bias = per_seed_bias.std(axis=0, ddof=1) / np.sqrt(S)
+    zb = per_seed_bias.mean(axis=0) / np.maximum(se_bias, 1e-300)
+    assert np.all(np.abs(zb) < 4.5), (what, "time-averaged bias beyond 4.5 SE of the seed average", zb)
