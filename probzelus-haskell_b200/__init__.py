@@ -12,6 +12,6 @@ every call that computes raises PzError when libpzgpu.so or a CUDA device is mis
 from .infer import (  # noqa: F401
     PzError, ModelDesc, StepSummary, Posterior, ZStream, lib, lib_path, exported_symbols,
     rw1d, stt, mtt_track, mtt, zparticles, zdsparticles, infer, run_stream,
-    resample_systematic, resample_multinomial,
+    resample_systematic, resample_multinomial, comm_unique_id, zparticles_sharded, shard_halo_range,
     PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF,
 )

@@ -16,6 +16,9 @@
 #include <new>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is loaded with dlopen when a sharded filter is created
+
 #include "pz_kernels.cuh"
 
 using namespace pz;
@@ -152,21 +155,77 @@ struct pz_filter {
   int64_t last_launches = 0;
   GenericScratch g;                  // taps / multinomial path
   int launches_per_step = 0;
+  // sharded filter (one process per GPU)
+  ncclComm_t comm = nullptr;
+  int64_t hb = 0;                    // halo capacity in blocks on each side
+  float* xbuf[2] = {nullptr, nullptr};
+  int32_t* ebbuf[2] = {nullptr, nullptr};
+  uint64_t* pbxbuf = nullptr;
+  int32_t* h_table = nullptr;        // pinned [2*world]
+  int64_t last_migrated = 0;
 };
 
 namespace {
 
+// ---- NCCL, loaded on demand (a single-GPU host never needs libnccl) ----------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return PZ_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(PZ_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define PZ_SYM(field, name)                                                      \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                     \
+  if (!g_nccl.field) return fail(PZ_ENCCL, "libnccl lacks %s", name)
+  PZ_SYM(GetUniqueId, "ncclGetUniqueId");
+  PZ_SYM(CommInitRank, "ncclCommInitRank");
+  PZ_SYM(CommDestroy, "ncclCommDestroy");
+  PZ_SYM(AllReduce, "ncclAllReduce");
+  PZ_SYM(AllGather, "ncclAllGather");
+  PZ_SYM(Send, "ncclSend");
+  PZ_SYM(Recv, "ncclRecv");
+  PZ_SYM(GroupStart, "ncclGroupStart");
+  PZ_SYM(GroupEnd, "ncclGroupEnd");
+  PZ_SYM(GetErrorString, "ncclGetErrorString");
+#undef PZ_SYM
+  g_nccl.handle = h;
+  return PZ_OK;
+}
+
+#define PZ_NCCL(call)                                                                         \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess) return fail(PZ_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
 void free_filter(pz_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
   if (f->graph) cudaGraphExecDestroy(f->graph);
+  if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
   StepArgs& a = f->a;
-  cudaFree(a.X[0]); cudaFree(a.X[1]); cudaFree(a.eb[0]); cudaFree(a.eb[1]); cudaFree(a.sb); cudaFree(a.pb);
-  cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part); cudaFree(a.plan);
-  cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ);
+  cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
+  cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
+  cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec); cudaFree(a.shard_table);
   f->g.release();
   if (f->h_obs) cudaFreeHost(f->h_obs);
   if (f->h_summ) cudaFreeHost(f->h_summ);
+  if (f->h_table) cudaFreeHost(f->h_table);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
   if (f->stream) cudaStreamDestroy(f->stream);
@@ -200,6 +259,7 @@ int fetch_summaries(pz_filter* f, uint32_t t0, int64_t k) {
 // ancestors of the pending resample into f->g.anc (systematic: canonical; multinomial: step t)
 int pending_ancestors(pz_filter* f, int* launches) {
   StepArgs& a = f->a;
+  if (a.world > 1) return fail(PZ_ESTATE, "ancestor / particle taps are not available on a sharded filter");
   int rc = generic_alloc(&f->g, a.n_local, false);
   if (rc) return rc;
   int n = 0;
@@ -225,9 +285,87 @@ int pending_ancestors(pz_filter* f, int* launches) {
   return PZ_OK;
 }
 
+// ---- sharded filter: everything between two step kernels ---------------------------------------
+// Host-side halo plan (pure function, also exported for the CPU tests): which of `src`'s blocks
+// does `dst` need, given the global block holding the ancestor of dst's first / last slot.
+inline void halo_range(int64_t need_lo, int64_t need_hi, int64_t nb, int src, int64_t* lo, int64_t* hi) {
+  const int64_t s0 = (int64_t)src * nb, s1 = s0 + nb;
+  *lo = need_lo > s0 ? need_lo : s0;
+  *hi = (need_hi + 1) < s1 ? (need_hi + 1) : s1;
+  if (*hi < *lo) *hi = *lo;
+}
+
+// emax all-reduce -> scan -> all-gather -> plan -> boundary table -> halo exchange -> partition.
+// `delta` = 1 after a step kernel, 0 for the initial population.
+int sharded_advance(pz_filter* f, int delta, int* launches) {
+  StepArgs& a = f->a;
+  const int R = a.world, me = a.rank;
+  const int64_t nb = a.nblk;
+  cudaStream_t s = f->stream;
+  const int which = (int)((f->t + (uint32_t)delta) & 1u);  // buffer of the population just produced
+  PZ_NCCL(g_nccl.AllReduce(&a.ctl->emax_acc, &a.ctl->emax_acc, 1, ncclInt32, ncclMax, f->comm, s));
+  *launches += launch_scan_only(a, delta, s);
+  PZ_NCCL(g_nccl.AllGather(a.shard_rec + (size_t)me * kShardRec, a.shard_rec, kShardRec, ncclUint64, f->comm, s));
+  *launches += launch_plan_sharded(a, delta, s);
+  PZ_NCCL(g_nccl.AllReduce(a.shard_table, a.shard_table, 2 * R, ncclInt32, ncclMax, f->comm, s));
+  PZ_CUDA(cudaMemcpyAsync(f->h_table, a.shard_table, 2 * R * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PZ_CUDA(cudaStreamSynchronize(s));
+  for (int q = 0; q < 2 * R; ++q)
+    if (f->h_table[q] < 0) {
+      f->t += (uint32_t)delta;  // keep the host mirror in step with nothing: the filter is dead
+      return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight on every rank", f->t);
+    }
+  const int64_t need_lo = f->h_table[me], need_hi = f->h_table[R + me];
+  const int64_t own0 = (int64_t)me * nb;
+  const int64_t ext_lo = need_lo - own0 < 0 ? need_lo - own0 : 0;             // <= 0
+  const int64_t ext_hi = need_hi + 1 - own0 > nb ? need_hi + 1 - own0 : nb;   // >= nb
+  if (-ext_lo > f->hb || ext_hi - nb > f->hb)
+    return fail(PZ_ECAPACITY, "rank %d needs %lld + %lld halo blocks but the capacity is %lld (set PZ_HALO_BLOCKS)", me,
+                (long long)-ext_lo, (long long)(ext_hi - nb), (long long)f->hb);
+  float* x = a.X[which];
+  int32_t* eb = a.eb[which];
+  uint64_t* pbx = const_cast<uint64_t*>(a.pbx);
+  int64_t migrated = 0;
+  PZ_NCCL(g_nccl.GroupStart());
+  for (int peer = 0; peer < R; ++peer) {
+    if (peer == me) continue;
+    int64_t lo, hi;
+    halo_range(f->h_table[peer], f->h_table[R + peer], nb, me, &lo, &hi);  // my blocks that `peer` needs
+    if (hi > lo) {
+      const int64_t b0 = lo - own0, cnt = hi - lo;
+      for (int d = 0; d < a.model.nx; ++d)
+        PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld + b0 * kBlk, cnt * kBlk, ncclFloat32, peer, f->comm, s));
+      PZ_NCCL(g_nccl.Send(eb + b0, cnt, ncclInt32, peer, f->comm, s));
+      PZ_NCCL(g_nccl.Send(pbx + b0, cnt + 1, ncclUint64, peer, f->comm, s));
+    }
+    halo_range(need_lo, need_hi, nb, peer, &lo, &hi);  // `peer`'s blocks that I need
+    if (hi > lo) {
+      const int64_t b0 = lo - own0, cnt = hi - lo;  // b0 < 0 (left halo) or >= nb (right halo)
+      for (int d = 0; d < a.model.nx; ++d)
+        PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld + b0 * kBlk, cnt * kBlk, ncclFloat32, peer, f->comm, s));
+      PZ_NCCL(g_nccl.Recv(eb + b0, cnt, ncclInt32, peer, f->comm, s));
+      // a left-halo range ends where my own prefix starts (same value), a right-halo range starts there
+      PZ_NCCL(g_nccl.Recv(pbx + b0, cnt + 1, ncclUint64, peer, f->comm, s));
+      migrated += cnt * kBlk;
+    }
+  }
+  PZ_NCCL(g_nccl.GroupEnd());
+  f->last_migrated = migrated;
+  a.b_lo = ext_lo;
+  a.b_hi = ext_hi;
+  *launches += launch_partition_ext(a, fused_tile_out(a.model.nx), delta, s);
+  PZ_CUDA(cudaGetLastError());
+  return PZ_OK;
+}
+
 int enqueue_step(pz_filter* f) {
   StepArgs& a = f->a;
-  if (a.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
+  if (a.world > 1) {
+    int n = launch_tile_only(a, f->stream);
+    int rc = sharded_advance(f, 1, &n);
+    f->last_launches += n;
+    if (rc) return rc;
+  } else if (a.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
     int n = 0;
     int rc = pending_ancestors(f, &n);
     if (rc) return rc;
@@ -246,7 +384,7 @@ int enqueue_step(pz_filter* f) {
 }
 
 int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank, int world,
-                  pz_filter** out) {
+                  const void* nccl_id, pz_filter** out) {
   if (!model || !out) return fail(PZ_EINVAL, "null argument");
   *out = nullptr;
   if (model->kind == PZ_MODEL_MTT) return fail(PZ_EINVAL, "MTT descriptor: not available in this build");
@@ -254,7 +392,16 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   if (!((model->nx == 1 && model->ny == 1) || (model->nx == 4 && model->ny == 2) || (model->nx == 6 && model->ny == 3)))
     return fail(PZ_EINVAL, "no kernel instantiated for nx=%d ny=%d (supported: (1,1), (4,2), (6,3))", model->nx, model->ny);
   if (n_global < 1 || n_global > (1ull << 30)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^30]");
-  if (world != 1) return fail(PZ_EINVAL, "sharded filters: use pz_filter_create_sharded");
+  if (world < 1 || rank < 0 || rank >= world) return fail(PZ_EINVAL, "bad rank %d / world %d", rank, world);
+  if (world > 1) {
+    if (world > 32) return fail(PZ_EINVAL, "at most 32 ranks");
+    if (n_global % ((uint64_t)world * kBlk) != 0)
+      return fail(PZ_EINVAL, "a sharded filter needs n_particles divisible by world * 256 (whole resampling blocks per rank)");
+    if (model->resampler != PZ_RESAMPLE_SYSTEMATIC) return fail(PZ_EINVAL, "sharded filters use the systematic resampler");
+    if (!nccl_id) return fail(PZ_EINVAL, "null nccl_unique_id");
+    int rc = load_nccl();
+    if (rc) return rc;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail(PZ_EINVAL, "device %d out of range (%d devices)", device, ndev);
@@ -268,28 +415,48 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   int rc = derive_lg(model, &a.model, &a.ll_const);
   if (rc) { delete f; return rc; }
   a.n_global = (int64_t)n_global;
-  a.n_local = (int64_t)n_global;
-  a.slot_base = 0;
-  (void)rank;
+  a.n_local = (int64_t)(n_global / (uint64_t)world);
+  a.slot_base = (int64_t)rank * a.n_local;
   a.world = world;
+  a.rank = rank;
   a.seed = seed;
   a.resampler = model->resampler;
-  a.ld = round_up(a.n_local, kPad);
   a.nblk = (a.n_local + kBlk - 1) / kBlk;
   a.nscan = (int32_t)((a.nblk + kScanTile - 1) / kScanTile);
   const int to = fused_tile_out(model->nx);
   a.ntiles_out = (int32_t)((a.n_local + to - 1) / to);
+  if (world > 1) {
+    int64_t hb = a.nblk / 8 > 64 ? a.nblk / 8 : 64;
+    if (const char* e = getenv("PZ_HALO_BLOCKS")) hb = atoll(e) > 0 ? atoll(e) : hb;
+    f->hb = hb < a.nblk ? hb : a.nblk;
+  }
+  const int64_t H = f->hb * kBlk;
+  a.ld = round_up(a.n_local, kPad) + 2 * H;
   const size_t xbytes = (size_t)model->nx * a.ld * sizeof(float);
 #define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
   PZ_TRY(cudaEventCreate(&f->ev1));
-  PZ_TRY(cudaMalloc(&a.X[0], xbytes));
-  PZ_TRY(cudaMalloc(&a.X[1], xbytes));
-  PZ_TRY(cudaMalloc(&a.eb[0], (a.nblk + 8) * sizeof(int32_t)));
-  PZ_TRY(cudaMalloc(&a.eb[1], (a.nblk + 8) * sizeof(int32_t)));
+  for (int i = 0; i < 2; ++i) {
+    PZ_TRY(cudaMalloc(&f->xbuf[i], xbytes));
+    PZ_TRY(cudaMemset(f->xbuf[i], 0, xbytes));
+    a.X[i] = f->xbuf[i] + H;
+    PZ_TRY(cudaMalloc(&f->ebbuf[i], (a.nblk + 2 * f->hb + 8) * sizeof(int32_t)));
+    a.eb[i] = f->ebbuf[i] + f->hb;
+  }
   PZ_TRY(cudaMalloc(&a.sb, (a.nblk + 8) * sizeof(uint64_t)));
   PZ_TRY(cudaMalloc(&a.pb, (a.nblk + 8) * sizeof(uint64_t)));
+  if (world > 1) {
+    PZ_TRY(cudaMalloc(&f->pbxbuf, (a.nblk + 2 * f->hb + 8) * sizeof(uint64_t)));
+    a.pbx = f->pbxbuf + f->hb;
+    PZ_TRY(cudaMalloc(&a.shard_rec, (size_t)world * kShardRec * sizeof(uint64_t)));
+    PZ_TRY(cudaMalloc(&a.shard_table, 2 * world * sizeof(int32_t)));
+    PZ_TRY(cudaMallocHost(&f->h_table, 2 * world * sizeof(int32_t)));
+  } else {
+    a.pbx = a.pb;
+  }
+  a.b_lo = 0;
+  a.b_hi = a.nblk;
   PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
   PZ_TRY(cudaMalloc(&a.rec, (size_t)(a.ntiles_out + 1) * kMaxRec * sizeof(double)));
   PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
@@ -305,11 +472,21 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   PZ_TRY(cudaMallocHost(&f->h_obs, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
   PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
   launch_init(a, f->stream);
-  launch_scan_partition(a, to, f->stream);
+  if (world > 1) {
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&f->comm, world, id, rank);
+    if (r != ncclSuccess) { int c = fail(PZ_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); free_filter(f); return c; }
+    int n = 0;
+    rc = sharded_advance(f, 0, &n);
+    if (rc) { free_filter(f); return rc; }
+  } else {
+    launch_scan_partition(a, to, f->stream);
+  }
   PZ_TRY(cudaGetLastError());
   PZ_TRY(cudaStreamSynchronize(f->stream));
   // one captured graph serves every systematic step (the step index lives in ctl->t)
-  if (a.resampler == PZ_RESAMPLE_SYSTEMATIC) {
+  if (world == 1 && a.resampler == PZ_RESAMPLE_SYSTEMATIC) {
     cudaGraph_t graph = nullptr;
     PZ_TRY(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
     f->launches_per_step = launch_step(a, nullptr, f->stream);
@@ -393,19 +570,32 @@ int pz_model_mtt(pz_model_desc* d) {
 }
 
 int pz_filter_create(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int device, pz_filter** out) {
-  return create_common(model, n_particles, seed, device, 0, 1, out);
+  return create_common(model, n_particles, seed, device, 0, 1, nullptr, out);
 }
 
 int pz_comm_unique_id(void* out128) {
-  (void)out128;
-  return fail(PZ_ENCCL, "sharded filters are not available in this build");
+  if (!out128) return fail(PZ_EINVAL, "null argument");
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  PZ_NCCL(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, sizeof(id));
+  return PZ_OK;
 }
 
 int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank,
                              int world, const void* nccl_unique_id, pz_filter** out) {
-  (void)nccl_unique_id;
-  if (world == 1) return create_common(model, n_global, seed, device, rank, 1, out);
-  return fail(PZ_ENCCL, "sharded filters are not available in this build");
+  return create_common(model, n_global, seed, device, rank, world, nccl_unique_id, out);
+}
+
+/* Host-side halo plan of the sharded filter (pure function; CPU tests drive it over gloo).
+ * need_lo[q] / need_hi[q]: global block holding the ancestor of rank q's first / last slot.
+ * out[2*p], out[2*p+1]: global block range [lo, hi) of rank `src` that rank `dst` must receive. */
+int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_rank, int32_t src, int64_t* lo, int64_t* hi) {
+  if (!lo || !hi || blocks_per_rank < 1 || src < 0) return fail(PZ_EINVAL, "bad argument");
+  halo_range(need_lo, need_hi, blocks_per_rank, src, lo, hi);
+  return PZ_OK;
 }
 
 int64_t pz_filter_n_local(const pz_filter* f) { return f ? f->a.n_local : 0; }
@@ -428,7 +618,8 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
   float ms = 0;
   cudaEventElapsedTime(&ms, f->ev0, f->ev1);
   f->last_ms = ms;
-  const pz_step_summary& s = f->h_summ[t0 % kObsRing];
+  pz_step_summary& s = f->h_summ[t0 % kObsRing];
+  s.n_migrated = f->last_migrated;
   if (out) *out = s;
   if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t0);
   return PZ_OK;
@@ -437,7 +628,8 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
 int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, double ms[3]) {
   if (!f || !obs || !ms) return fail(PZ_EINVAL, "null argument");
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d", f->a.model.ny);
-  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC) return fail(PZ_ESTATE, "profiled step: systematic resampler only");
+  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1)
+    return fail(PZ_ESTATE, "profiled step: single-GPU systematic filters only");
   PZ_CUDA(cudaSetDevice(f->device));
   cudaEvent_t ev[4];
   for (int i = 0; i < 4; ++i) PZ_CUDA(cudaEventCreate(&ev[i]));

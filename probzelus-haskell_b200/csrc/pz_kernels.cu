@@ -158,7 +158,7 @@ __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i < a.ld) {
+  if (i < a.nblk * kBlk) {
     for (int d = 0; d < a.model.nx; ++d) {
       a.X[0][(size_t)d * a.ld + i] = a.model.x0[d];
       a.X[1][(size_t)d * a.ld + i] = a.model.x0[d];
@@ -210,6 +210,8 @@ struct ScanArgs {
   uint64_t seed;
   double ll_const;
   int32_t world;
+  int32_t rank;
+  u64* shard_rec;  // sharded: this rank's slot of the all-gathered record
 };
 
 __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint32_t U) {
@@ -223,6 +225,28 @@ __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint
   } else {
     pl->L = 1;
     pl->rho = 0;
+  }
+}
+
+// posterior summary from the centred moment sums in the plan (also re-centres for the next step)
+__device__ void write_summary(PlanDev* pl, pz_step_summary* o, uint32_t t, int nx, int64_t n_out_global, double ll_const) {
+  const double sw = pl->sw, sw2 = pl->sw2;
+  for (int d = 0; d < nx; ++d) {
+    const float cen = pl->center[d];
+    const double m = pl->sx[d] / sw;
+    const double mean = (double)cen + m, var = pl->sxx[d] / sw - m * m;
+    pl->center[d] = (float)mean;
+    if (o) { o->mean[d] = mean; o->var[d] = var; }
+  }
+  if (o) {
+    for (int d = nx; d < PZ_MAX_NX; ++d) { o->mean[d] = 0.0; o->var[d] = 0.0; }
+    o->step = t;
+    o->log_evidence_inc = log(sw) + (double)(pl->emax - 23) * 0.6931471805599453 - log((double)n_out_global) + ll_const;
+    o->ess = sw * sw / sw2;
+    o->n_migrated = 0;
+    o->e_max = pl->emax;
+    o->reserved = 0;
+    o->total_weight = pl->total;
   }
 }
 
@@ -369,28 +393,19 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       finalize_plan(pl, total, s.n_out_global, U);
     }
     if (have_rec) {
-      const double sw = s_tot[1], sw2 = s_tot[2];
-      pl->sw = sw; pl->sw2 = sw2;
+      pl->sw = s_tot[1]; pl->sw2 = s_tot[2];
       for (int d = 0; d < s.nx; ++d) { pl->sx[d] = s_tot[3 + d]; pl->sxx[d] = s_tot[3 + s.nx + d]; }
-      if (s.world <= 1) {
-        pz_step_summary* o = s.summ ? s.summ + (s.ctl->t % kObsRing) : nullptr;
-        for (int d = 0; d < s.nx; ++d) {
-          const float cen = pl->center[d];
-          const double m = pl->sx[d] / sw;
-          const double mean = (double)cen + m, var = pl->sxx[d] / sw - m * m;
-          pl->center[d] = (float)mean;
-          if (o) { o->mean[d] = mean; o->var[d] = var; }
-        }
-        if (o) {
-          for (int d = s.nx; d < PZ_MAX_NX; ++d) { o->mean[d] = 0.0; o->var[d] = 0.0; }
-          o->step = s.ctl->t;
-          o->log_evidence_inc = log(sw) + (double)(emax - 23) * 0.6931471805599453 - log((double)s.n_out_global) + s.ll_const;
-          o->ess = sw * sw / sw2;
-          o->n_migrated = 0;
-          o->e_max = emax;
-          o->reserved = 0;
-          o->total_weight = total;
-        }
+      if (s.world <= 1)
+        write_summary(pl, s.summ ? s.summ + (s.ctl->t % kObsRing) : nullptr, s.ctl->t, s.nx, s.n_out_global, s.ll_const);
+    }
+    if (s.world > 1) {  // this rank's record for the all-gather
+      u64* r = s.shard_rec + (size_t)s.rank * kShardRec;
+      r[0] = total;
+      r[1] = (u64)__double_as_longlong(have_rec ? pl->sw : 0.0);
+      r[2] = (u64)__double_as_longlong(have_rec ? pl->sw2 : 0.0);
+      for (int d = 0; d < PZ_MAX_NX; ++d) {
+        r[3 + d] = (u64)__double_as_longlong((have_rec && d < s.nx) ? pl->sx[d] : 0.0);
+        r[3 + PZ_MAX_NX + d] = (u64)__double_as_longlong((have_rec && d < s.nx) ? pl->sxx[d] : 0.0);
       }
     }
   }
@@ -400,7 +415,8 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
 // pf_partition: first input block of every output tile + per-step counter maintenance
 // ------------------------------------------------------------------------------------------
 struct PartArgs {
-  const u64* pb;
+  const u64* pb;      // prefix array searched (absolute on a sharded filter)
+  int64_t b_lo, b_hi; // block range searched
   int32_t* tile_start;
   u64* status;
   const PlanDev* plan;
@@ -419,13 +435,12 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
   const PlanDev* pl = p.plan;
   if (J < p.ntiles_out) {
     SlotMap sm(pl, p.n_out_global);
-    const u64 base = pl->base;
     const uint32_t j0 = (uint32_t)(p.slot_base + J * p.tile_out);
-    // min b in [0, nblk) with slot_end(base + pb[b+1]) > j0
-    int64_t lo = 0, hi = p.nblk;
+    // min b in [b_lo, b_hi) with slot_end(pb[b+1]) > j0
+    int64_t lo = p.b_lo, hi = p.b_hi;
     while (lo < hi) {
       int64_t mid = (lo + hi) >> 1;
-      if (sm.slot_end(base + p.pb[mid + 1]) > j0) hi = mid; else lo = mid + 1;
+      if (sm.slot_end(p.pb[mid + 1]) > j0) hi = mid; else lo = mid + 1;
     }
     p.tile_start[J] = (int32_t)lo;
   }
@@ -619,8 +634,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
     const uint32_t tp = (t + kObsRing - 1) % kObsRing;
 #pragma unroll
     for (int k = 0; k < NY; ++k) src.y[k] = a.obs[(size_t)tp * PZ_MAX_NY + k];
-    resample_tile(src, s_par, s_head, TO, a.eb[cur], a.pb, pl->base, (int64_t)a.tile_start[blockIdx.x], a.nblk,
-                  a.n_local, sm, pl->emax, j0, jend, lane, warp);
+    resample_tile(src, s_par, s_head, TO, a.eb[cur], a.pbx, 0ull, (int64_t)a.tile_start[blockIdx.x], a.b_hi,
+                  a.world > 1 ? INT64_MAX : a.n_local, sm, pl->emax, j0, jend, lane, warp);
   } else {
     for (int sidx = tid; sidx < nslots; sidx += kThreads) {
       const int64_t p = ta.anc[j0l + sidx];
@@ -830,7 +845,7 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   LogwSource src{g.lw, g.n};
   for (int sidx = tid; sidx < TO; sidx += kThreads) { s_anc[sidx] = -1; s_head[sidx] = 0; }
   __syncthreads();
-  resample_tile(src, reinterpret_cast<float*>(s_anc), s_head, TO, generic_eb(g), g.pb, pl->base,
+  resample_tile(src, reinterpret_cast<float*>(s_anc), s_head, TO, generic_eb(g), g.pb, 0ull,
                 (int64_t)g.tile_start[blockIdx.x], g.nblk, g.n, sm, pl->emax, (uint32_t)j0, (uint32_t)jend, lane, warp);
   __syncthreads();
   for (int seg = warp; seg * 128 < (int)(jend - j0); seg += kWarps) {
@@ -900,6 +915,75 @@ __global__ void __launch_bounds__(kThreads) pf_gather_thin(StepArgs a, const int
 }
 
 // ------------------------------------------------------------------------------------------
+// sharded filter: plan from the all-gathered rank records, absolute prefixes, boundary table
+// ------------------------------------------------------------------------------------------
+struct ShardPlanArgs {
+  PlanDev* plan;
+  CtlDev* ctl;
+  const u64* rec;      // [world][kShardRec]
+  const u64* pb;       // local prefix [nblk+1]
+  u64* pbx;            // absolute prefix, own entries [0, nblk]
+  pz_step_summary* summ;
+  int64_t nblk, n_global;
+  int32_t rank, world, nx, delta;
+  uint64_t seed;
+  double ll_const;
+};
+
+__global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs p) {
+  u64 base = 0, total = 0;
+  for (int q = 0; q < p.world; ++q) {
+    const u64 tq = p.rec[(size_t)q * kShardRec];
+    if (q < p.rank) base += tq;
+    total += tq;
+  }
+  const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (int64_t b = gid; b <= p.nblk; b += (int64_t)gridDim.x * kThreads) p.pbx[b] = base + p.pb[b];
+  if (gid == 0) {
+    PlanDev* pl = p.plan;
+    const uint32_t t_next = p.ctl->t + (uint32_t)p.delta;
+    const uint32_t U = philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)p.seed, (uint32_t)(p.seed >> 32)).x;
+    pl->base = base;
+    finalize_plan(pl, total, p.n_global, U);
+    if (p.delta) {  // moment sums of all ranks, in rank order (every rank computes the same value)
+      double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
+      for (int q = 0; q < p.world; ++q) {
+        const u64* r = p.rec + (size_t)q * kShardRec;
+        sw += __longlong_as_double((long long)r[1]);
+        sw2 += __longlong_as_double((long long)r[2]);
+        for (int d = 0; d < p.nx; ++d) {
+          sx[d] += __longlong_as_double((long long)r[3 + d]);
+          sxx[d] += __longlong_as_double((long long)r[3 + PZ_MAX_NX + d]);
+        }
+      }
+      pl->sw = sw; pl->sw2 = sw2;
+      for (int d = 0; d < p.nx; ++d) { pl->sx[d] = sx[d]; pl->sxx[d] = sxx[d]; }
+      write_summary(pl, p.summ ? p.summ + (p.ctl->t % kObsRing) : nullptr, p.ctl->t, p.nx, p.n_global, p.ll_const);
+    }
+  }
+}
+
+// For every rank q: the global block holding the ancestor of its first slot (entry q) and of
+// its last slot (entry world + q), or -1 when that ancestor is not one of this rank's particles.
+__global__ void pf_boundary_table(const PlanDev* plan, const u64* pbx, int64_t nblk, int64_t n_local, int64_t n_global,
+                                  int32_t rank, int32_t world, int32_t* table) {
+  const int q = threadIdx.x;
+  if (q >= 2 * world) return;
+  SlotMap sm(plan, n_global);
+  const uint32_t j = (q < world) ? (uint32_t)(q * n_local) : (uint32_t)((q - world + 1) * n_local - 1);
+  int32_t res = -1;
+  if (!plan->degenerate && sm.slot_end(pbx[0]) <= j && j < sm.slot_end(pbx[nblk])) {
+    int64_t lo = 0, hi = nblk;  // min b with slot_end(pbx[b+1]) > j
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (sm.slot_end(pbx[mid + 1]) > j) hi = mid; else lo = mid + 1;
+    }
+    res = (int32_t)((int64_t)rank * nblk + lo);
+  }
+  table[q] = res;
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -907,7 +991,7 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int fused_tile_out(int nx) { return nx == 1 ? 4096 : 2048; }
 
 int launch_init(const StepArgs& a, cudaStream_t s) {
-  int64_t m = a.ld > a.nblk ? a.ld : a.nblk;
+  int64_t m = a.nblk * kBlk;
   pf_init<<<cdiv(m, kThreads), kThreads, 0, s>>>(a);
   return 1;
 }
@@ -921,11 +1005,12 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   sc.nblk = a.nblk; sc.n_out_global = a.n_global; sc.n_local = a.n_local;
   sc.nscan = a.nscan; sc.nrec = a.ntiles_out; sc.nx = a.model.nx; sc.delta = delta;
   sc.explicit_U = 0; sc.U_value = 0; sc.seed = a.seed; sc.ll_const = a.ll_const; sc.world = a.world;
+  sc.rank = a.rank; sc.shard_rec = a.shard_rec;
   return sc;
 }
 
 static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
-  PartArgs pa{a.pb, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
+  PartArgs pa{a.pbx, a.b_lo, a.b_hi, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
               a.ntiles_out, tile_out, a.nscan, delta};
   int nthreads = a.ntiles_out > a.nscan ? a.ntiles_out : a.nscan;
   pf_partition<<<cdiv(nthreads, kThreads), kThreads, 0, s>>>(pa);
@@ -994,6 +1079,28 @@ int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
   return 3;
 }
 
+int launch_tile_only(const StepArgs& a, cudaStream_t s) {
+  TileArgs ta{a, nullptr};
+  return dispatch_tile(ta, s);
+}
+
+int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s) {
+  ScanArgs sc = make_scan(a, delta, delta == 1);
+  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  return 1;
+}
+
+int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s) {
+  ShardPlanArgs p{a.plan, a.ctl, a.shard_rec, a.pb, const_cast<u64*>(a.pbx), a.summ, a.nblk, a.n_global,
+                  a.rank, a.world, a.model.nx, delta, a.seed, a.ll_const};
+  int grid = cdiv(a.nblk + 1, kThreads);
+  pf_plan_sharded<<<grid > 1024 ? 1024 : grid, kThreads, 0, s>>>(p);
+  pf_boundary_table<<<1, 64, 0, s>>>(a.plan, a.pbx, a.nblk, a.n_local, a.n_global, a.rank, a.world, a.shard_table);
+  return 2;
+}
+
+int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s) { return partition(a, tile_out, delta, s); }
+
 int launch_ctl_reset(CtlDev* ctl, cudaStream_t s) {
   pf_ctl_reset<<<1, 1, 0, s>>>(ctl);
   return 1;
@@ -1009,9 +1116,9 @@ int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s
   sc.eb0 = g.eb; sc.eb1 = g.eb; sc.sb = g.sb; sc.pb = g.pb; sc.status = g.scan_status; sc.part = g.scan_part; sc.rec = nullptr;
   sc.plan = g.plan; sc.ctl = g.ctl; sc.summ = nullptr; sc.nblk = g.nblk; sc.n_out_global = g.n; sc.n_local = g.n;
   sc.nscan = g.nscan; sc.nrec = 0; sc.nx = 0; sc.delta = 0; sc.explicit_U = 1; sc.U_value = g.U; sc.seed = g.seed;
-  sc.ll_const = 0; sc.world = 1;
+  sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr;
   pf_scan_blocks<<<g.nscan, kThreads, 0, s>>>(sc);
-  PartArgs pa{g.pb, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
+  PartArgs pa{g.pb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
   int nthreads = g.ntiles_out > g.nscan ? g.ntiles_out : g.nscan;
   pf_partition<<<cdiv(nthreads, kThreads), kThreads, 0, s>>>(pa);
   return n + 2;

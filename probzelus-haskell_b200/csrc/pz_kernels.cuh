@@ -69,7 +69,10 @@ struct StepArgs {
   float* X[2];
   int32_t* eb[2];
   uint64_t* sb;
-  uint64_t* pb;
+  uint64_t* pb;            // local exclusive prefix of the rescaled block sums [nblk+1]
+  const uint64_t* pbx;     // CDF prefix the step kernel reads: == pb on one GPU; on a sharded filter the
+                           // ABSOLUTE prefix (rank base added), with halo entries at [-hb, 0) and (nblk, nblk+hb]
+  int64_t b_lo, b_hi;      // valid (halo-extended) block range of pbx / eb / X for the pending resample
   int32_t* tile_start;
   double* rec;             // [ntiles_out][kMaxRec]
   uint64_t* scan_status;   // [nscan]
@@ -89,8 +92,12 @@ struct StepArgs {
   double ll_const;
   int32_t resampler;
   int32_t world;           // > 1: the plan is finalised by pf_plan_sharded after the all-gather
+  int32_t rank;
+  uint64_t* shard_rec;     // sharded: [world][kShardRec] gathered {local_total, sw, sw2, sx[], sxx[]}
+  int32_t* shard_table;    // sharded: [2*world] global block of the ancestor of every rank's first / last slot
   LgDev model;
 };
+constexpr int kShardRec = 16;  // 64-bit words per rank in the all-gathered record
 
 // Host-callable launchers (pz_kernels.cu).  Each returns the number of kernels it enqueued.
 int launch_init(const StepArgs& a, cudaStream_t s);
@@ -100,6 +107,11 @@ int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s);  // step
 int fused_tile_out(int nx);
 // same as launch_step(a, nullptr, s) with an event recorded after each of the three kernels
 int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]);
+// sharded filter (one process per GPU): the step is split around the NCCL collectives
+int launch_tile_only(const StepArgs& a, cudaStream_t s);                 // fused step kernel
+int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s);      // after the emax all-reduce
+int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s);   // after the all-gather: plan, absolute prefix, summary, boundary table
+int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s);  // after the halo exchange
 
 // Generic (stored log-weight) path: standalone resampler, ancestor taps, visualiser read.
 struct GenericArgs {

@@ -53,7 +53,7 @@ _SYMBOLS = [
     "pz_filter_create", "pz_comm_unique_id", "pz_filter_create_sharded", "pz_filter_step", "pz_filter_run",
     "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_ancestors", "pz_filter_read_state",
     "pz_filter_read_logw", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
-    "pz_filter_destroy",
+    "pz_filter_destroy", "pz_shard_halo_range",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
     L.pz_filter_n_local.restype = C.c_int64
     L.pz_resample_systematic.argtypes = [f64p, C.c_int64, C.c_double, i32p]
     L.pz_resample_multinomial.argtypes = [f64p, C.c_int64, C.c_uint64, C.c_uint32, i32p]
+    L.pz_shard_halo_range.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pz_filter_destroy.argtypes = [C.c_void_p]
     L.pz_filter_destroy.restype = None
     _lib = L
@@ -172,11 +173,19 @@ class Posterior:
 class ZStream:
     """ZStream IO Obs Posterior built around pz_filter_step (Util/ZStream.hs:16-21)."""
 
-    def __init__(self, model, n_particles, seed=0, device=0):
-        self.model, self.n, self.nx, self.ny = model, int(n_particles), model.nx, model.ny
+    def __init__(self, model, n_particles, seed=0, device=0, rank=0, world=1, nccl_id=None):
+        self.model, self.nx, self.ny = model, model.nx, model.ny
         self.t = 0
+        self.rank, self.world = rank, world
         self._h = C.c_void_p()
-        _check(lib().pz_filter_create(C.byref(model), self.n, seed, device, C.byref(self._h)))
+        if world > 1:
+            buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+            _check(lib().pz_filter_create_sharded(C.byref(model), int(n_particles), seed, device, rank, world, buf,
+                                                  C.byref(self._h)))
+        else:
+            _check(lib().pz_filter_create(C.byref(model), int(n_particles), seed, device, C.byref(self._h)))
+        self.n = int(lib().pz_filter_n_local(self._h))  # particles held by this process
+        self.n_global = int(n_particles)
 
     def step(self, obs):
         y = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
@@ -244,6 +253,25 @@ class ZStream:
 def zparticles(num_particles, model, seed=0, device=0):
     """zparticles numParticles model (Inference.hs:107-108)."""
     return ZStream(model, num_particles, seed, device)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host distributes it to every rank)."""
+    buf = (C.c_char * 128)()
+    _check(lib().pz_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def zparticles_sharded(num_particles, model, nccl_id, rank, world, seed=0, device=0):
+    """zparticles over `world` GPUs, one process per GPU: this rank holds global slots
+    [rank * N / world, (rank + 1) * N / world); resampling is global."""
+    return ZStream(model, num_particles, seed, device, rank, world, nccl_id)
+
+
+def shard_halo_range(need_lo, need_hi, blocks_per_rank, src):
+    lo, hi = C.c_int64(), C.c_int64()
+    _check(lib().pz_shard_halo_range(need_lo, need_hi, blocks_per_rank, src, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
 
 
 def zdsparticles(num_particles, model, seed=0, device=0):

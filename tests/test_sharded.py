@@ -1,0 +1,192 @@
+"""The N > 1 path: particles sharded over ranks with a GLOBAL systematic resample.
+
+CPU (gloo, world_size 2): the sharding protocol -- block statistics per rank, all-reduce of the
+block exponent, all-gather of rank totals, boundary table, halo plan (pz_shard_halo_range from
+libpzgpu.so) and halo exchange -- restated with exact Python integers over torch.distributed,
+must reproduce the single-process oracle's ancestors bit for bit.
+
+GPU (-m gpu, needs >= 2 devices): the CUDA/NCCL implementation on 2 ranks equals the
+single-GPU run at the same seed bit for bit (counter-based RNG keyed on the global slot)."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import pzhelpers as H
+
+BLK = 256
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _split(lw32):
+    lib = H.oracle()
+    n = np.zeros(lw32.size, np.int32); m = np.zeros(lw32.size, np.uint32)
+    lib.pzo_weight_split(H.ptr(lw32, C.c_float), lw32.size, H.ptr(n, C.c_int32), H.ptr(m, C.c_uint32))
+    return n.astype(np.int64), m.astype(np.int64)
+
+
+def _slot_end(Cv, rho, L, U, n_out):
+    pos = ((int(Cv) << (64 - L)) * rho) >> 64
+    return min((pos + (0xFFFFFFFF - U)) >> 32, n_out)
+
+
+def _gloo_worker(rank, world, port, n_global, seed, ret):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pz = g.load_package()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    lw = (rng.standard_normal(n_global) * 3).astype(np.float32)
+    lw[rng.random(n_global) < 0.05] = -np.inf
+    lw[: n_global // 3] -= 6.0   # unbalanced rank totals => real migration
+    U = 0x12345678
+    n_local = n_global // world
+    nb = n_local // BLK
+    mine = lw[rank * n_local:(rank + 1) * n_local]
+    nn, mm = _split(mine)
+    NZ = -(1 << 30)
+    # per-block statistics (what the step kernel writes)
+    eb = np.array([max([nn[i] for i in range(b * BLK, (b + 1) * BLK) if mm[i]] or [NZ]) for b in range(nb)], dtype=np.int64)
+    q_loc = np.array([(int(mm[i]) >> min(int(eb[i // BLK] - nn[i]), 63)) if mm[i] else 0 for i in range(n_local)], dtype=object)
+    sb = [int(sum(q_loc[b * BLK:(b + 1) * BLK])) for b in range(nb)]
+    # (1) all-reduce max of the block exponent
+    e = torch.tensor([int(eb.max())]); dist.all_reduce(e, op=dist.ReduceOp.MAX); emax = int(e.item())
+    # (2) local scan at the global exponent, all-gather of rank totals
+    S = [(sb[b] >> int(emax - eb[b])) if (eb[b] != NZ and emax - eb[b] < 64) else 0 for b in range(nb)]
+    pb = [0]
+    for v in S:
+        pb.append(pb[-1] + v)
+    tot = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(tot, torch.tensor([pb[-1]], dtype=torch.int64))
+    totals = [int(t.item()) for t in tot]
+    base, T = sum(totals[:rank]), sum(totals)
+    L = T.bit_length(); rho = ((n_global << (32 + L)) // T) + 1
+    pbx = [base + v for v in pb]
+    # (3) boundary table: global block of the ancestor of every rank's first / last slot
+    table = torch.full((2 * world,), -1, dtype=torch.int64)
+    for qi in range(2 * world):
+        j = qi * n_local if qi < world else (qi - world + 1) * n_local - 1
+        if _slot_end(pbx[0], rho, L, U, n_global) <= j < _slot_end(pbx[nb], rho, L, U, n_global):
+            b = next(b for b in range(nb) if _slot_end(pbx[b + 1], rho, L, U, n_global) > j)
+            table[qi] = rank * nb + b
+    dist.all_reduce(table, op=dist.ReduceOp.MAX)
+    need_lo, need_hi = int(table[rank]), int(table[world + rank])
+    # (4) halo plan from the C library + exchange (weights, block exponents, absolute prefixes)
+    ext = {}  # global block -> (lw[256], eb, pbx_start, pbx_end)
+    for b in range(nb):
+        ext[rank * nb + b] = (mine[b * BLK:(b + 1) * BLK], int(eb[b]), pbx[b], pbx[b + 1])
+    reqs = []
+    recv_bufs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        lo, hi = pz.shard_halo_range(int(table[peer]), int(table[world + peer]), nb, rank)  # my blocks for peer
+        if hi > lo:
+            pay = torch.tensor(np.concatenate([np.concatenate([ext[gb][0].astype(np.float64), [ext[gb][1], ext[gb][2], ext[gb][3]]])
+                                               for gb in range(lo, hi)]))
+            reqs.append(dist.isend(pay, peer))
+        lo, hi = pz.shard_halo_range(need_lo, need_hi, nb, peer)  # peer's blocks for me
+        if hi > lo:
+            buf = torch.zeros((hi - lo) * (BLK + 3), dtype=torch.float64)
+            reqs.append(dist.irecv(buf, peer)); recv_bufs.append((lo, hi, buf))
+    for r in reqs:
+        r.wait()
+    migrated = 0
+    for lo, hi, buf in recv_bufs:
+        a = buf.numpy().reshape(hi - lo, BLK + 3)
+        for k, gb in enumerate(range(lo, hi)):
+            ext[gb] = (a[k, :BLK].astype(np.float32), int(a[k, BLK]), int(a[k, BLK + 1]), int(a[k, BLK + 2]))
+            migrated += BLK
+    # (5) resample my output slots from the (halo-extended) blocks
+    anc = np.full(n_local, -1, dtype=np.int64)
+    j_lo, j_hi = rank * n_local, (rank + 1) * n_local
+    for gb in range(need_lo, need_hi + 1):
+        blw, ebb, P0, _ = ext[gb]
+        if ebb == NZ or emax - ebb >= 32:
+            continue
+        bn, bm = _split(np.ascontiguousarray(blw))
+        c = 0
+        prev = _slot_end(P0, rho, L, U, n_global)
+        for i in range(BLK):
+            c += (int(bm[i]) >> min(int(ebb - bn[i]), 63)) if bm[i] else 0
+            o = _slot_end(P0 + (c >> (emax - ebb)), rho, L, U, n_global)
+            for j in range(max(prev, j_lo), min(o, j_hi)):
+                anc[j - j_lo] = gb * BLK + i
+            prev = max(prev, o)
+    out = [torch.zeros(n_local, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(out, torch.from_numpy(anc))
+    if rank == 0:
+        full = np.concatenate([t.numpy() for t in out])
+        rc, ref = H.oracle_systematic(lw, U)
+        ret["ok"] = bool(rc == 0 and np.array_equal(full, ref))
+        ret["migrated"] = migrated
+        ret["mismatch"] = int(np.sum(full != ref))
+    dist.destroy_process_group()
+
+
+def test_sharding_protocol_gloo_world2():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(2, port, 8192, 17, ret), nprocs=2, join=True)
+    assert ret.get("ok"), dict(ret)
+    assert ret["migrated"] > 0  # the skewed weights force rank 0 to fetch blocks from rank 1
+
+
+def test_halo_range_function(pz):
+    # rank 1 of 4 (100 blocks each) needs global blocks 95..210: 5 from rank 0, its own, 11 from rank 2
+    assert pz.shard_halo_range(95, 210, 100, 0) == (95, 100)
+    assert pz.shard_halo_range(95, 210, 100, 1) == (100, 200)
+    assert pz.shard_halo_range(95, 210, 100, 2) == (200, 211)
+    lo, hi = pz.shard_halo_range(95, 210, 100, 3)
+    assert hi == lo  # nothing from rank 3
+
+
+def _gpu_worker(rank, world, port, model, n_global, seed, T, idfile, outdir):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pz = g.load_package()
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ids = [pz.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, 0)
+    d = getattr(pz, model)()
+    hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
+    obs, _ = H.gen_obs(hd, T)
+    zs = pz.zparticles_sharded(n_global, d, ids[0], rank, world, seed=seed, device=rank)
+    posts = [zs.step(y) for y in obs]
+    np.save(os.path.join(outdir, f"x_{rank}.npy"), zs.read_state())
+    np.save(os.path.join(outdir, f"s_{rank}.npy"), np.array([[p.total_weight, p.e_max, p.n_migrated] + list(p.mean) for p in posts], dtype=np.float64))
+    zs.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
+def test_sharded_equals_single_gpu(pz, model, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n_global, seed, T = 2, 2 * 256 * 101, 99, 6  # partial last tile on every rank
+    mp.spawn(_gpu_worker, args=(world, _free_port(), model, n_global, seed, T, None, str(tmp_path)), nprocs=world, join=True)
+    d = getattr(pz, model)()
+    hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
+    obs, _ = H.gen_obs(hd, T)
+    zs = pz.zparticles(n_global, d, seed=seed)
+    posts = [zs.step(y) for y in obs]
+    x = zs.read_state()
+    xs = np.concatenate([np.load(tmp_path / f"x_{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(xs.view(np.uint32), x.view(np.uint32))
+    s0 = np.load(tmp_path / "s_0.npy")
+    for t, p in enumerate(posts):
+        assert int(s0[t, 0]) == p.total_weight and int(s0[t, 1]) == p.e_max
+        assert np.allclose(s0[t, 3:3 + d.nx], p.mean, rtol=1e-6, atol=2e-6)
