@@ -144,6 +144,8 @@ def run_b200(args):
     name = args.model
     nx, ny = MODELS[name]
     n_p = args.particles
+    if world > 1:
+        n_p -= n_p % 256  # a sharded filter holds whole resampling blocks (256 particles) per rank
     K, W = args.steps, args.warmup
     d = model_desc(pz, name)
     hd = helper_desc(H, name)
@@ -209,6 +211,13 @@ def run_b200(args):
     achieved = alg_bytes / (t_tile_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
+    # every rank tears its shard down together (NCCL communicator), then rank 0 reports
+    n_migrated = int(post.n_migrated)
+    post_step, post_mean0, post_ess = int(post.step), float(post.mean[0]), float(post.ess)
+    zs.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- CPU baseline on this box's host cores (bounded sample)
@@ -241,12 +250,9 @@ def run_b200(args):
                      "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
                                          "pf_partition": float(np.mean(prof[:, 2]))}},
         "cpu_baseline": cpu,
-        "posterior_check": {"step": int(post.step), "mean0": float(post.mean[0]), "ess": float(post.ess),
-                            "n_migrated_last_step": int(post.n_migrated)},
+        "posterior_check": {"step": post_step, "mean0": post_mean0, "ess": post_ess, "n_migrated_last_step_rank0": n_migrated},
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -12,5 +12,5 @@ for l in open('$1'):
 echo "== 2-GPU bench"
 for m in rw1d lg42; do
   P=10000000; [ $m = rw1d ] && P=100000000
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --model $m --particles $P --steps 20 --warmup 3 > gpurun_out/bench2_$m.json 2> gpurun_out/bench2_$m.err; echo "rc=$?"; show gpurun_out/bench2_$m.json; tail -5 gpurun_out/bench2_$m.err
+  timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --model $m --particles $P --steps 20 --warmup 3 > gpurun_out/bench2_$m.json 2> gpurun_out/bench2_$m.err; echo "rc=$?"; show gpurun_out/bench2_$m.json; tail -5 gpurun_out/bench2_$m.err
 done
