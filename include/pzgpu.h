@@ -160,6 +160,12 @@ PZ_API int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs
  * out[(j/stride)*nx + d].                                                                    */
 PZ_API int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t out_len);
 
+/* Tracker (PZ_MODEL_MTT) output: for every `stride`-th resampled particle the track map
+ * `Map id (mean, cov)` that processObservations returns (MultiTargetTracking.hs:133-139):
+ * count_out[i], id_out[i*16+k] (-1 past the count), mean_out[(i*16+k)*4..], cov_out[(i*16+k)*16..]. */
+PZ_API int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, double* mean_out,
+                                 double* cov_out, int64_t n_sel_cap);
+
 /* Parity / debug taps. */
 PZ_API int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n);      /* ancestors of the pending resample */
 PZ_API int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len);       /* pre-resample population, SoA [nx][N] */

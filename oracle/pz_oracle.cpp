@@ -775,3 +775,288 @@ int pzo_num_threads(void) {
 }
 
 }  // extern "C"
+
+// =========================================================================================
+// Multi-target tracker (Examples/MultiTargetTracking.hs:26-145), restated in double.
+//
+// Per particle: a map id -> Rao-Blackwellised track (Gaussian marginal over R^4), the heap of
+// zdsparticles reduced to its closed-form Kalman recursions:
+//   trackMotion     (:56-67)  x' ~ N(F x, Q)            -> Kalman predict (makeMarginal, DelayedSampling.hs:135-139)
+//   trackMeasurement(:69-73)  z  ~ N(H x', R)           -> score' (:124-128) / kalmanUpdate (MVDistributions.hs:83-100)
+//   proposeAssocs   (:111-124) sequential categorical over {Clutter < NewTrack < Track id asc}
+//   observingWithProposal (Metaprob.hs:157-162): w *= p(assocs, obs | state) / q(assocs)
+//   sampleStep      (:89-99)  count prior shuffleWithRepeats' (Distributions.hs:224-233)
+//   updateWithAssocs(:75-87)  births, coasting Bernoulli((1-pd)/(1-ps*pd)) as written
+// The weight is accumulated term by term as the reference does; the algebraic simplification
+// used by the CUDA kernel (sum_j log L_j + n_undetected log(1 - ps pd) + const) is checked
+// against it on every call (pzo_mtt_max_simplification_error).
+// =========================================================================================
+namespace {
+
+constexpr uint32_t kStreamMtt = 0x4D545453u;     // "MTTS": association / coasting uniforms
+constexpr uint32_t kStreamMttGen = 0x4D545447u;  // "MTTG": ground-truth generator
+
+struct MttTrack { int id; double m[4]; double P[4][4]; };
+
+struct MttConst {
+  double F[4][4], Q[4][4];
+  double lc, lb, pd, ps, cv, bp, bv, r;
+  int kmax;
+};
+
+MttConst mtt_const(const pz_model_desc* d) {
+  MttConst c;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { c.F[i][j] = d->F[i * 4 + j]; c.Q[i][j] = d->Q[i * 4 + j]; }
+  c.lc = d->mtt.clutter_lambda; c.lb = d->mtt.new_track_lambda; c.pd = d->mtt.pd; c.ps = d->mtt.survival_prob;
+  c.cv = d->mtt.clutter_var; c.bp = d->mtt.birth_pos_var; c.bv = d->mtt.birth_vel_var; c.r = d->mtt.meas_var;
+  c.kmax = d->mtt.k_max;
+  return c;
+}
+
+struct U01 {  // sequential uniforms from one Philox counter family
+  uint64_t seed; uint32_t a, t, stream; uint32_t call = 0; int have = 0; uint32_t r[4];
+  U01(uint64_t s, uint32_t a_, uint32_t t_, uint32_t st) : seed(s), a(a_), t(t_), stream(st) {}
+  double next() {
+    if (!have) { philox(a, call++, t, stream, seed, r); have = 4; }
+    return ((double)r[4 - have--] + 0.5) * 0x1p-32;
+  }
+  double normal() { double u1 = next(), u2 = next(); return sqrt(-2.0 * log(u1)) * cos(2 * M_PI * u2); }
+};
+
+void mtt_predict(const MttConst& c, MttTrack& t) {
+  double m[4], FP[4][4], P[4][4];
+  for (int i = 0; i < 4; ++i) { m[i] = 0; for (int k = 0; k < 4; ++k) m[i] += c.F[i][k] * t.m[k]; }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += c.F[i][k] * t.P[k][j]; FP[i][j] = s; }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += FP[i][k] * c.F[j][k]; P[i][j] = s + c.Q[i][j]; }
+  memcpy(t.m, m, sizeof(m)); memcpy(t.P, P, sizeof(P));
+}
+
+// log N(z; mu2, S) for a 2x2 S = [[a, b], [b, d]]  (mvNormal_ll0, MVDistributions.hs:45-46)
+double ll2(const double* z, double mu0, double mu1, double a, double b, double d) {
+  double det = a * d - b * b, d0 = z[0] - mu0, d1 = z[1] - mu1;
+  double quad = (d * d0 * d0 - 2 * b * d0 * d1 + a * d1 * d1) / det;
+  return -0.5 * (quad + log(det) + 2 * log(2 * M_PI));
+}
+
+// kalmanUpdate with H = [I2 0], R = r I2  (MVDistributions.hs:83-100)
+void mtt_update(MttTrack& t, const double* z, double r) {
+  double a = t.P[0][0] + r, b = t.P[0][1], d = t.P[1][1] + r, det = a * d - b * b;
+  double Si[2][2] = {{d / det, -b / det}, {-b / det, a / det}};
+  double y0 = z[0] - t.m[0], y1 = z[1] - t.m[1];
+  double K[4][2];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 2; ++j) K[i][j] = t.P[i][0] * Si[0][j] + t.P[i][1] * Si[1][j];
+  double P[4][4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) P[i][j] = t.P[i][j] - (K[i][0] * t.P[0][j] + K[i][1] * t.P[1][j]);
+  for (int i = 0; i < 4; ++i) t.m[i] += K[i][0] * y0 + K[i][1] * y1;
+  memcpy(t.P, P, sizeof(P));
+}
+
+double poisson_ll(double lambda, int k) { return k * log(lambda) - lambda - lgamma(k + 1.0); }
+double log_fact(int n) { return lgamma(n + 1.0); }
+
+struct OMtt {
+  pz_model_desc desc; MttConst c;
+  int64_t n; uint64_t seed; uint32_t t = 0;
+  std::vector<std::vector<MttTrack>> tr;  // per particle, sorted by id
+  std::vector<int> next_id;
+  std::vector<float> lw;
+  std::vector<int32_t> anc;
+  double max_simpl_err = 0;
+  int64_t overflow = 0;
+};
+
+MttTrack mtt_birth(const MttConst& c, int id) {
+  MttTrack t; t.id = id;
+  for (int i = 0; i < 4; ++i) { t.m[i] = 0; for (int j = 0; j < 4; ++j) t.P[i][j] = 0; }
+  t.P[0][0] = t.P[1][1] = c.bp; t.P[2][2] = t.P[3][3] = c.bv;
+  return t;
+}
+
+// one particle, one step; returns the log-weight increment
+double mtt_particle_step(OMtt& f, std::vector<MttTrack>& tracks, int& next_id, const double* obs, int M, U01& rng) {
+  const MttConst& c = f.c;
+  const double pspd = c.ps * c.pd;
+  std::vector<MttTrack> pred = tracks;
+  for (auto& t : pred) mtt_predict(c, t);
+  const int K = (int)pred.size();
+  std::vector<int> assoc_of_track(K, -1);   // obs index or -1
+  std::vector<int> assoc(M);                // -1 clutter, -2 new, k >= 0 track slot
+  double q_log = 0, obs_ll = 0, sum_logL = 0;
+  int n_c = 0, n_n = 0;
+  std::vector<double> like(K + 2), llv(K + 2);
+  for (int j = 0; j < M; ++j) {
+    const double* z = obs + 2 * j;
+    llv[0] = ll2(z, 0, 0, c.cv, 0, c.cv); like[0] = c.lc * exp(llv[0]);
+    llv[1] = ll2(z, 0, 0, c.bp + c.r, 0, c.bp + c.r); like[1] = c.lb * exp(llv[1]);
+    double tot = like[0] + like[1];
+    for (int k = 0; k < K; ++k) {
+      if (assoc_of_track[k] >= 0) { like[2 + k] = 0; continue; }
+      llv[2 + k] = ll2(z, pred[k].m[0], pred[k].m[1], pred[k].P[0][0] + c.r, pred[k].P[0][1], pred[k].P[1][1] + c.r);
+      like[2 + k] = pspd * exp(llv[2 + k]);
+      tot += like[2 + k];
+    }
+    double u = rng.next() * tot, cacc = 0; int pick = -1;
+    for (int a = 0; a < K + 2; ++a) {
+      if (a >= 2 && assoc_of_track[a - 2] >= 0) continue;
+      cacc += like[a]; pick = a;
+      if (u < cacc) break;
+    }
+    q_log += log(like[pick] / tot); obs_ll += llv[pick]; sum_logL += log(tot);
+    if (pick == 0) { assoc[j] = -1; ++n_c; }
+    else if (pick == 1) { assoc[j] = -2; ++n_n; }
+    else { assoc[j] = pick - 2; assoc_of_track[pick - 2] = j; }
+  }
+  // count prior: shuffleWithRepeats' score (Distributions.hs:230-233)
+  double prior = poisson_ll(c.lc, n_c) + poisson_ll(c.lb, n_n);
+  int n_undet = 0;
+  for (int k = 0; k < K; ++k) { if (assoc_of_track[k] >= 0) prior += log(pspd); else { prior += log(1 - pspd); ++n_undet; } }
+  prior -= (log_fact(M) - log_fact(n_c) - log_fact(n_n));
+  const double lw_inc = -q_log + prior + obs_ll;
+  const double simpl = sum_logL + n_undet * log(1 - pspd) - (c.lc + c.lb) - log_fact(M);
+  f.max_simpl_err = std::max(f.max_simpl_err, fabs(simpl - lw_inc));
+  // update: observed tracks conditioned, unobserved coast with Bernoulli((1-pd)/(1-ps pd)), births appended
+  std::vector<MttTrack> out;
+  const double p_coast = (1 - c.pd) / (1 - pspd);
+  for (int k = 0; k < K; ++k) {
+    if (assoc_of_track[k] >= 0) { mtt_update(pred[k], obs + 2 * assoc_of_track[k], c.r); out.push_back(pred[k]); }
+    else if (rng.next() < p_coast) out.push_back(pred[k]);
+  }
+  for (int j = 0; j < M; ++j)
+    if (assoc[j] == -2) {
+      MttTrack t = mtt_birth(c, next_id++);
+      mtt_update(t, obs + 2 * j, c.r);
+      if ((int)out.size() < c.kmax) out.push_back(t); else ++f.overflow;
+    }
+  tracks.swap(out);
+  return lw_inc;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* pzo_mtt_create(const pz_model_desc* d, int64_t n, uint64_t seed) {
+  OMtt* f = new OMtt();
+  f->desc = *d; f->c = mtt_const(d); f->n = n; f->seed = seed;
+  f->tr.resize(n); f->next_id.assign(n, 0); f->lw.assign(n, 0.0f); f->anc.assign(n, 0);
+  return f;
+}
+void pzo_mtt_destroy(void* h) { delete (OMtt*)h; }
+
+// one filter step: canonical systematic resample of the pending weights, then every child
+// runs observeStep on the observations (n_obs rows of 2).  Outputs the weighted mean / variance
+// of the track count and the log-evidence increment.
+int pzo_mtt_step(void* h, const double* obs, int32_t n_obs, double* mean_cnt, double* var_cnt, double* logz) {
+  OMtt* f = (OMtt*)h;
+  ResamplePlan pl;
+  if (!build_plan(f->lw.data(), f->n, f->n, &pl)) return PZ_EDEGENERATE;
+  systematic_ancestors(pl, pzo_resample_uniform(f->seed, f->t), f->n, f->anc.data());
+  std::vector<std::vector<MttTrack>> ntr(f->n);
+  std::vector<int> nid(f->n);
+  std::vector<double> lwd(f->n);
+  for (int64_t j = 0; j < f->n; ++j) {
+    ntr[j] = f->tr[f->anc[j]]; nid[j] = f->next_id[f->anc[j]];
+    U01 rng(f->seed, (uint32_t)j, f->t, kStreamMtt);
+    lwd[j] = mtt_particle_step(*f, ntr[j], nid[j], obs, n_obs, rng);
+    f->lw[j] = (float)lwd[j];
+  }
+  f->tr.swap(ntr); f->next_id.swap(nid);
+  double mx = -INFINITY; for (double v : lwd) mx = std::max(mx, v);
+  double sw = 0, sc = 0, scc = 0;
+  for (int64_t j = 0; j < f->n; ++j) { double w = exp(lwd[j] - mx), c = (double)f->tr[j].size(); sw += w; sc += w * c; scc += w * c * c; }
+  if (mean_cnt) *mean_cnt = sc / sw;
+  if (var_cnt) *var_cnt = scc / sw - (sc / sw) * (sc / sw);
+  if (logz) *logz = mx + log(sw / f->n);
+  f->t += 1;
+  return 0;
+}
+
+double pzo_mtt_max_simplification_error(void* h) { return ((OMtt*)h)->max_simpl_err; }
+void pzo_mtt_logw(void* h, float* out) { OMtt* f = (OMtt*)h; memcpy(out, f->lw.data(), f->n * sizeof(float)); }
+
+// tracks of particle i: returns the count; ids[k], mean[k*4..], cov[k*16..]
+int pzo_mtt_particle(void* h, int64_t i, int32_t* ids, double* mean, double* cov) {
+  OMtt* f = (OMtt*)h;
+  const auto& v = f->tr[i];
+  for (size_t k = 0; k < v.size(); ++k) {
+    ids[k] = v[k].id;
+    for (int a = 0; a < 4; ++a) { mean[k * 4 + a] = v[k].m[a]; for (int b = 0; b < 4; ++b) cov[k * 16 + a * 4 + b] = v[k].P[a][b]; }
+  }
+  return (int)v.size();
+}
+
+// weighted posterior mean of the state of track `id` over the particles that carry it, and the
+// weighted fraction of particles carrying it
+int pzo_mtt_track_posterior(void* h, int32_t id, double* mean4, double* frac) {
+  OMtt* f = (OMtt*)h;
+  double mx = -INFINITY; for (float v : f->lw) mx = std::max(mx, (double)v);
+  double sw = 0, swt = 0, m[4] = {0, 0, 0, 0};
+  for (int64_t j = 0; j < f->n; ++j) {
+    double w = exp((double)f->lw[j] - mx); sw += w;
+    for (const auto& t : f->tr[j]) if (t.id == id) { swt += w; for (int a = 0; a < 4; ++a) m[a] += w * t.m[a]; }
+  }
+  for (int a = 0; a < 4; ++a) mean4[a] = swt > 0 ? m[a] / swt : 0;
+  *frac = swt / sw;
+  return 0;
+}
+
+// Ground truth + observations: sampleStep under MP.sim (MultiTargetTracking.hs:126-131).
+// obs_out: up to m_max rows of 2 per step (row-major [T][m_max][2]); n_obs_out[T];
+// truth_out: [T][k_max][5] = (id, x0..x3), n_truth_out[T].
+int pzo_mtt_generate(const pz_model_desc* d, uint64_t seed, int64_t T, int32_t m_max, double* obs_out, int32_t* n_obs_out,
+                     double* truth_out, int32_t* n_truth_out) {
+  MttConst c = mtt_const(d);
+  struct Tr { int id; double x[4]; };
+  std::vector<Tr> tracks; int next_id = 0;
+  const double pspd = c.ps * c.pd, p_coast = (1 - c.pd) / (1 - pspd);
+  double Lq[4][4] = {};
+  for (int j = 0; j < 4; ++j) {
+    double s = c.Q[j][j]; for (int k = 0; k < j; ++k) s -= Lq[j][k] * Lq[j][k];
+    double l = s > 0 ? sqrt(s) : 0; Lq[j][j] = l;
+    for (int i = j + 1; i < 4; ++i) { double t = c.Q[i][j]; for (int k = 0; k < j; ++k) t -= Lq[i][k] * Lq[j][k]; Lq[i][j] = l > 0 ? t / l : 0; }
+  }
+  auto poisson = [](double lambda, U01& r) { double L = exp(-lambda), p = 1; int k = 0; do { ++k; p *= r.next(); } while (p > L); return k - 1; };
+  for (int64_t t = 0; t < T; ++t) {
+    U01 rng(seed, 0, (uint32_t)t, kStreamMttGen);
+    for (auto& tr : tracks) {  // trackMotion
+      double z[4], xn[4];
+      for (int i = 0; i < 4; ++i) z[i] = rng.normal();
+      for (int i = 0; i < 4; ++i) { double s = 0; for (int k = 0; k < 4; ++k) s += c.F[i][k] * tr.x[k]; for (int k = 0; k <= i; ++k) s += Lq[i][k] * z[k]; xn[i] = s; }
+      memcpy(tr.x, xn, sizeof(xn));
+    }
+    int n_c = poisson(c.lc, rng), n_n = poisson(c.lb, rng);
+    std::vector<int> keys;  // -1 clutter, -2 new, k track slot
+    for (int i = 0; i < n_c; ++i) keys.push_back(-1);
+    for (int i = 0; i < n_n; ++i) keys.push_back(-2);
+    std::vector<char> det(tracks.size(), 0);
+    for (size_t k = 0; k < tracks.size(); ++k) if (rng.next() < pspd) { det[k] = 1; keys.push_back((int)k); }
+    for (size_t i = keys.size(); i > 1; --i) { size_t j = (size_t)(rng.next() * i); std::swap(keys[i - 1], keys[j < i ? j : i - 1]); }  // uniform interleave
+    std::vector<Tr> born;
+    int M = 0;
+    for (int key : keys) {
+      if (M >= m_max) break;
+      double z0, z1;
+      if (key == -1) { z0 = sqrt(c.cv) * rng.normal(); z1 = sqrt(c.cv) * rng.normal(); }
+      else if (key == -2) {
+        Tr nt; nt.id = next_id++;
+        nt.x[0] = sqrt(c.bp) * rng.normal(); nt.x[1] = sqrt(c.bp) * rng.normal(); nt.x[2] = sqrt(c.bv) * rng.normal(); nt.x[3] = sqrt(c.bv) * rng.normal();
+        born.push_back(nt);
+        z0 = nt.x[0] + sqrt(c.r) * rng.normal(); z1 = nt.x[1] + sqrt(c.r) * rng.normal();
+      } else { z0 = tracks[key].x[0] + sqrt(c.r) * rng.normal(); z1 = tracks[key].x[1] + sqrt(c.r) * rng.normal(); }
+      obs_out[(t * m_max + M) * 2] = z0; obs_out[(t * m_max + M) * 2 + 1] = z1; ++M;
+    }
+    n_obs_out[t] = M;
+    std::vector<Tr> next;
+    for (size_t k = 0; k < tracks.size(); ++k) if (det[k] || rng.next() < p_coast) next.push_back(tracks[k]);
+    for (auto& b : born) if ((int)next.size() < c.kmax) next.push_back(b);
+    tracks.swap(next);
+    n_truth_out[t] = (int)tracks.size();
+    for (size_t k = 0; k < tracks.size(); ++k) {
+      truth_out[(t * c.kmax + k) * 5] = tracks[k].id;
+      for (int a = 0; a < 4; ++a) truth_out[(t * c.kmax + k) * 5 + 1 + a] = tracks[k].x[a];
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

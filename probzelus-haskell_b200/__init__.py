@@ -13,5 +13,5 @@ from .infer import (  # noqa: F401
     PzError, ModelDesc, StepSummary, Posterior, ZStream, lib, lib_path, exported_symbols,
     rw1d, stt, mtt_track, mtt, zparticles, zdsparticles, infer, run_stream,
     resample_systematic, resample_multinomial, comm_unique_id, zparticles_sharded, shard_halo_range,
-    PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF,
+    PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF, json_line_tracks, json_line_generic1d,
 )

@@ -163,6 +163,14 @@ struct pz_filter {
   uint64_t* pbxbuf = nullptr;
   int32_t* h_table = nullptr;        // pinned [2*world]
   int64_t last_migrated = 0;
+  // multi-target tracker
+  bool is_mtt = false;
+  uint32_t* mtt_s[2] = {nullptr, nullptr};   // particle records, double-buffered
+  float* mtt_obs = nullptr;                  // device [m_max][2]
+  float* h_mtt_obs = nullptr;                // pinned
+  unsigned long long* mtt_overflow = nullptr;
+  std::vector<char> mtt_params;
+  int32_t mtt_mmax = 0;
 };
 
 namespace {
@@ -222,6 +230,8 @@ void free_filter(pz_filter* f) {
   cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
   cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
   cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec); cudaFree(a.shard_table);
+  cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow);
+  if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
   f->g.release();
   if (f->h_obs) cudaFreeHost(f->h_obs);
   if (f->h_summ) cudaFreeHost(f->h_summ);
@@ -263,7 +273,7 @@ int pending_ancestors(pz_filter* f, int* launches) {
   int rc = generic_alloc(&f->g, a.n_local, false);
   if (rc) return rc;
   int n = 0;
-  n += launch_logw(a, f->g.lw, f->stream);
+  if (!f->is_mtt) n += launch_logw(a, f->g.lw, f->stream);  // the tracker stores its log-weights
   GenericArgs g{};
   g.lw = f->g.lw; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[1]; g.parity_ctl = a.ctl;
   g.sb = a.sb; g.pb = a.pb; g.tile_start = f->g.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
@@ -383,11 +393,125 @@ int enqueue_step(pz_filter* f) {
   return PZ_OK;
 }
 
+GenericArgs mtt_generic(pz_filter* f) {
+  StepArgs& a = f->a;
+  GenericArgs g{};
+  g.lw = f->g.lw; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[0]; g.parity_ctl = nullptr;
+  g.sb = a.sb; g.pb = a.pb; g.tile_start = a.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
+  g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk; g.ntiles_out = a.ntiles_out; g.nscan = a.nscan;
+  g.U = 0; g.seed = a.seed; g.step = f->t;
+  return g;
+}
+
+// stats of the stored log-weights -> scan -> (summary) -> partition
+int mtt_plan(pz_filter* f, int delta, double ll_const) {
+  StepArgs& a = f->a;
+  GenericArgs g = mtt_generic(f);
+  int n = launch_stats_from_lw(g, f->stream);
+  n += launch_scan_only(a, delta, f->stream);
+  if (delta)
+    n += launch_mtt_summary(f->g.lw, f->mtt_s[(f->t + 1) & 1], a.n_local, a.plan, a.ctl, a.summ, ll_const, f->mtt_overflow, f->stream);
+  n += launch_partition_ext(a, kGenericTileOut, delta, f->stream);
+  return n;
+}
+
+int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device, pz_filter** out) {
+  if (model->nx != 4 || model->ny != 2) return fail(PZ_EINVAL, "the MTT descriptor needs the (4,2) track model");
+  if (model->mtt.k_max != 16) return fail(PZ_EINVAL, "k_max must be 16 (one lane per track slot)");
+  if (model->mtt.m_max < 1 || model->mtt.m_max > 32) return fail(PZ_EINVAL, "m_max must be in [1, 32]");
+  if (n < 1 || n > (1ull << 28)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^28] for the tracker");
+  if (model->resampler != PZ_RESAMPLE_SYSTEMATIC) return fail(PZ_EINVAL, "the tracker uses the systematic resampler");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PZ_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  PZ_CUDA(cudaSetDevice(device));
+  pz_filter* f = new (std::nothrow) pz_filter();
+  if (!f) return fail(PZ_ENOMEM, "out of host memory");
+  f->desc = *model; f->device = device; f->is_mtt = true; f->mtt_mmax = model->mtt.m_max;
+  StepArgs& a = f->a;
+  memset(&a, 0, sizeof(a));
+  a.model.nx = 4; a.model.ny = 2;
+  a.n_global = a.n_local = (int64_t)n; a.world = 1; a.seed = seed; a.resampler = model->resampler;
+  a.nblk = (a.n_local + kBlk - 1) / kBlk;
+  a.nscan = (int32_t)((a.nblk + kScanTile - 1) / kScanTile);
+  a.ntiles_out = (int32_t)((a.n_local + kGenericTileOut - 1) / kGenericTileOut);
+  a.ld = round_up(a.n_local, kPad);
+  f->mtt_params.resize(mtt_params_size());
+  mtt_fill_params(model, f->mtt_params.data());
+  const size_t sbytes = (size_t)a.n_local * mtt_words_per_particle() * sizeof(uint32_t);
+#define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
+  PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  PZ_TRY(cudaEventCreate(&f->ev0));
+  PZ_TRY(cudaEventCreate(&f->ev1));
+  for (int i = 0; i < 2; ++i) { PZ_TRY(cudaMalloc(&f->mtt_s[i], sbytes)); PZ_TRY(cudaMemset(f->mtt_s[i], 0, sbytes)); }
+  PZ_TRY(cudaMalloc(&f->ebbuf[0], (a.nblk + 8) * sizeof(int32_t)));
+  a.eb[0] = a.eb[1] = f->ebbuf[0];
+  PZ_TRY(cudaMalloc(&a.sb, (a.nblk + 8) * sizeof(uint64_t)));
+  PZ_TRY(cudaMalloc(&a.pb, (a.nblk + 8) * sizeof(uint64_t)));
+  a.pbx = a.pb; a.b_lo = 0; a.b_hi = a.nblk;
+  PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
+  PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
+  PZ_TRY(cudaMemset(a.scan_status, 0, (a.nscan + 1) * sizeof(uint64_t)));
+  PZ_TRY(cudaMalloc(&a.scan_part, (size_t)(a.nscan + 1) * kMaxRec * sizeof(double)));
+  PZ_TRY(cudaMalloc(&a.plan, sizeof(PlanDev)));
+  PZ_TRY(cudaMemset(a.plan, 0, sizeof(PlanDev)));
+  PZ_TRY(cudaMalloc(&a.ctl, sizeof(CtlDev)));
+  PZ_TRY(cudaMalloc(&a.summ, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMemset(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMalloc(&f->mtt_obs, 64 * sizeof(float)));
+  PZ_TRY(cudaMallocHost(&f->h_mtt_obs, 64 * sizeof(float)));
+  PZ_TRY(cudaMalloc(&f->mtt_overflow, sizeof(unsigned long long)));
+  PZ_TRY(cudaMemset(f->mtt_overflow, 0, sizeof(unsigned long long)));
+  {
+    int rc = generic_alloc(&f->g, a.n_local, false);  // stored log-weights (all 0: equal weights) + ancestors
+    if (rc) { free_filter(f); return rc; }
+  }
+  launch_ctl_reset(a.ctl, f->stream);
+  mtt_plan(f, 0, 0.0);
+  PZ_TRY(cudaGetLastError());
+  PZ_TRY(cudaStreamSynchronize(f->stream));
+#undef PZ_TRY
+  *out = f;
+  return PZ_OK;
+}
+
+int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summary* out) {
+  StepArgs& a = f->a;
+  if (n_obs < 0 || n_obs > f->mtt_mmax) return fail(PZ_ECAPACITY, "%d observations exceed m_max = %d", n_obs, f->mtt_mmax);
+  const uint32_t t0 = f->t;
+  for (int i = 0; i < 2 * n_obs; ++i) f->h_mtt_obs[i] = (float)obs[i];
+  if (n_obs) PZ_CUDA(cudaMemcpyAsync(f->mtt_obs, f->h_mtt_obs, 2 * n_obs * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+  GenericArgs g = mtt_generic(f);
+  int n = launch_generic_ancestors(g, f->stream);
+  n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
+                       f->mtt_overflow, a.n_local, n_obs, a.seed, f->stream);
+  // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
+  const double ll_const = -(f->desc.mtt.clutter_lambda + f->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
+  n += mtt_plan(f, 1, ll_const);
+  f->t += 1;
+  PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+  PZ_CUDA(cudaMemcpyAsync(f->h_summ + (t0 % kObsRing), a.summ + (t0 % kObsRing), sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  PZ_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+  f->last_ms = ms; f->last_launches = n;
+  const pz_step_summary& s = f->h_summ[t0 % kObsRing];
+  if (out) *out = s;
+  if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", t0);
+  return PZ_OK;
+}
+
 int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank, int world,
                   const void* nccl_id, pz_filter** out) {
   if (!model || !out) return fail(PZ_EINVAL, "null argument");
   *out = nullptr;
-  if (model->kind == PZ_MODEL_MTT) return fail(PZ_EINVAL, "MTT descriptor: not available in this build");
+  if (model->kind == PZ_MODEL_MTT) {
+    if (world != 1) return fail(PZ_EINVAL, "the tracker runs on one GPU");
+    return create_mtt(model, n_global, seed, device, out);
+  }
   if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS) return fail(PZ_EINVAL, "unknown model kind %d", model->kind);
   if (!((model->nx == 1 && model->ny == 1) || (model->nx == 4 && model->ny == 2) || (model->nx == 6 && model->ny == 3)))
     return fail(PZ_EINVAL, "no kernel instantiated for nx=%d ny=%d (supported: (1,1), (4,2), (6,3))", model->nx, model->ny);
@@ -601,7 +725,12 @@ int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_ran
 int64_t pz_filter_n_local(const pz_filter* f) { return f ? f->a.n_local : 0; }
 
 int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, pz_step_summary* out) {
-  if (!f || !obs) return fail(PZ_EINVAL, "null argument");
+  if (!f || (!obs && n_obs > 0)) return fail(PZ_EINVAL, "null argument");
+  if (f->is_mtt) {
+    if (obs_dim != 2) return fail(PZ_EINVAL, "tracker observations are rows of 2 doubles");
+    PZ_CUDA(cudaSetDevice(f->device));
+    return mtt_step_host(f, obs, n_obs, out);
+  }
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d, got %d x %d", f->a.model.ny, n_obs, obs_dim);
   PZ_CUDA(cudaSetDevice(f->device));
   const uint32_t t0 = f->t;
@@ -628,7 +757,7 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
 int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, double ms[3]) {
   if (!f || !obs || !ms) return fail(PZ_EINVAL, "null argument");
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d", f->a.model.ny);
-  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1)
+  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1 || f->is_mtt)
     return fail(PZ_ESTATE, "profiled step: single-GPU systematic filters only");
   PZ_CUDA(cudaSetDevice(f->device));
   cudaEvent_t ev[4];
@@ -650,6 +779,7 @@ int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32
 
 int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_dim, pz_step_summary* out) {
   if (!f || !obs || n_steps < 0) return fail(PZ_EINVAL, "bad argument");
+  if (f->is_mtt) return fail(PZ_ESTATE, "pz_filter_run: the tracker takes a variable number of observations per step; use pz_filter_step");
   if (obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected observations of dim %d", f->a.model.ny);
   PZ_CUDA(cudaSetDevice(f->device));
   f->last_launches = 0;
@@ -694,6 +824,7 @@ int pz_filter_last_timing(pz_filter* f, double* ms, int64_t* launches) {
 int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len) {
   if (!f || !out) return fail(PZ_EINVAL, "null argument");
   const StepArgs& a = f->a;
+  if (f->is_mtt) return fail(PZ_ESTATE, "tracker state is read with pz_filter_read_tracks");
   if (out_len < a.model.nx * a.n_local) return fail(PZ_EINVAL, "buffer too small: need %lld floats", (long long)(a.model.nx * a.n_local));
   PZ_CUDA(cudaSetDevice(f->device));
   PZ_CUDA(cudaStreamSynchronize(f->stream));
@@ -709,7 +840,7 @@ int pz_filter_read_logw(pz_filter* f, float* out, int64_t n) {
   PZ_CUDA(cudaSetDevice(f->device));
   int rc = generic_alloc(&f->g, f->a.n_local, false);
   if (rc) return rc;
-  launch_logw(f->a, f->g.lw, f->stream);
+  if (!f->is_mtt) launch_logw(f->a, f->g.lw, f->stream);
   PZ_CUDA(cudaMemcpyAsync(out, f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
   PZ_CUDA(cudaStreamSynchronize(f->stream));
   return PZ_OK;
@@ -728,6 +859,7 @@ int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n) {
 
 int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t out_len) {
   if (!f || !out || stride < 1) return fail(PZ_EINVAL, "bad argument");
+  if (f->is_mtt) return fail(PZ_ESTATE, "tracker particles are read with pz_filter_read_tracks");
   const StepArgs& a = f->a;
   const int64_t n_sel = (a.n_local + stride - 1) / stride;
   if (out_len < n_sel * a.model.nx) return fail(PZ_EINVAL, "buffer too small: need %lld doubles", (long long)(n_sel * a.model.nx));
@@ -743,6 +875,42 @@ int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t 
   cudaFree(d_out);
   if (e != cudaSuccess) return fail(PZ_ECUDA, "read_particles: %s", cudaGetErrorString(e));
   for (size_t i = 0; i < h.size(); ++i) out[i] = (double)h[i];
+  return PZ_OK;
+}
+
+int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, double* mean_out, double* cov_out,
+                          int64_t n_sel_cap) {
+  if (!f || !count_out || !id_out || !mean_out || !cov_out || stride < 1) return fail(PZ_EINVAL, "bad argument");
+  if (!f->is_mtt) return fail(PZ_ESTATE, "not a tracker filter");
+  const StepArgs& a = f->a;
+  const int64_t n_sel = (a.n_local + stride - 1) / stride;
+  if (n_sel_cap < n_sel) return fail(PZ_EINVAL, "buffers too small: need %lld particles", (long long)n_sel);
+  PZ_CUDA(cudaSetDevice(f->device));
+  int rc = pending_ancestors(f, nullptr);
+  if (rc) return rc;
+  const int W = mtt_words_per_particle();
+  uint32_t* d_out = nullptr;
+  PZ_CUDA(cudaMalloc(&d_out, (size_t)n_sel * W * sizeof(uint32_t)));
+  launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream);
+  std::vector<uint32_t> h((size_t)n_sel * W);
+  cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(PZ_ECUDA, "read_tracks: %s", cudaGetErrorString(e));
+  static const int tri[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const uint32_t* p = h.data() + (size_t)i * W;
+    const int cnt = (int)p[0];
+    count_out[i] = cnt;
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t* r = p + 4 + 16 * k;
+      float fl[16];
+      memcpy(fl, r, sizeof(fl));
+      id_out[i * 16 + k] = k < cnt ? (int32_t)r[0] : -1;
+      for (int c = 0; c < 4; ++c) mean_out[(i * 16 + k) * 4 + c] = k < cnt ? (double)fl[1 + c] : 0.0;
+      for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) cov_out[(i * 16 + k) * 16 + x * 4 + y] = k < cnt ? (double)fl[5 + tri[x][y]] : 0.0;
+    }
+  }
   return PZ_OK;
 }
 

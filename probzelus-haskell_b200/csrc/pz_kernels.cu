@@ -1124,6 +1124,11 @@ int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s
   return n + 2;
 }
 
+int launch_stats_from_lw(const GenericArgs& g, cudaStream_t s) {
+  pf_stats_from_lw<<<cdiv(g.nblk, kWarps), kThreads, 0, s>>>(g.lw, g.n, g.nblk, g.eb, g.sb, g.ctl);
+  return 1;
+}
+
 int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s) {
   pf_ancestors<kGenericTileOut><<<g.ntiles_out, kThreads, 0, s>>>(g);
   return 1;

@@ -16,6 +16,7 @@ import numpy as np
 
 PZ_MAX_NX, PZ_MAX_NY = 6, 3
 PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF = 0, 1
+PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT = 1, 2, 3
 _ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENCCL", -4: "EDEGENERATE", -5: "ECAPACITY", -6: "ENOMEM", -7: "ESTATE"}
 
 
@@ -51,7 +52,7 @@ class StepSummary(C.Structure):
 _SYMBOLS = [
     "pz_abi_version", "pz_last_error", "pz_model_rw1d", "pz_model_stt", "pz_model_mtt_track", "pz_model_mtt",
     "pz_filter_create", "pz_comm_unique_id", "pz_filter_create_sharded", "pz_filter_step", "pz_filter_run",
-    "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_ancestors", "pz_filter_read_state",
+    "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_tracks", "pz_filter_read_ancestors", "pz_filter_read_state",
     "pz_filter_read_logw", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
     "pz_filter_destroy", "pz_shard_halo_range",
 ]
@@ -92,6 +93,7 @@ def lib():
     L.pz_filter_last_timing.argtypes = [C.c_void_p, f64p, C.POINTER(C.c_int64)]
     L.pz_filter_step_profile.argtypes = [C.c_void_p, f64p, C.c_int32, C.c_int32, f64p]
     L.pz_filter_read_particles.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
+    L.pz_filter_read_tracks.argtypes = [C.c_void_p, C.c_int32, i32p, i32p, f64p, f64p, C.c_int64]
     L.pz_filter_read_ancestors.argtypes = [C.c_void_p, i32p, C.c_int64]
     L.pz_filter_read_state.argtypes = [C.c_void_p, f32p, C.c_int64]
     L.pz_filter_read_logw.argtypes = [C.c_void_p, f32p, C.c_int64]
@@ -190,9 +192,23 @@ class ZStream:
     def step(self, obs):
         y = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
         s = StepSummary()
-        _check(lib().pz_filter_step(self._h, _ptr(y, C.c_double), 1, y.size, C.byref(s)))
-        self.t += 1
+        if self.model.kind == PZ_MODEL_MTT:   # a (possibly empty) list of 2-D detections
+            rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double) if y.size else None, y.size // 2, 2, C.byref(s))
+        else:
+            rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double), 1, y.size, C.byref(s))
+        if rc == 0 or rc == -4:
+            self.t += 1
+        _check(rc)
         return Posterior(self, s)
+
+    def read_tracks(self, stride=1):
+        """Tracker output: list (one per selected resampled particle) of lists of (id, mean[4], cov[4,4])."""
+        n_sel = (self.n + stride - 1) // stride
+        cnt = np.zeros(n_sel, dtype=np.int32); ids = np.zeros((n_sel, 16), dtype=np.int32)
+        mean = np.zeros((n_sel, 16, 4)); cov = np.zeros((n_sel, 16, 4, 4))
+        _check(lib().pz_filter_read_tracks(self._h, stride, _ptr(cnt, C.c_int32), _ptr(ids, C.c_int32), _ptr(mean, C.c_double),
+                                           _ptr(cov, C.c_double), n_sel))
+        return [[(int(ids[i, k]), mean[i, k].copy(), cov[i, k].copy()) for k in range(cnt[i])] for i in range(n_sel)]
 
     def run(self, observations, want_summaries=True):
         """runStream over a whole observation array [T, ny]; returns the T summaries."""
@@ -302,3 +318,33 @@ def resample_multinomial(logw, seed, step):
     anc = np.zeros(lw.size, dtype=np.int32)
     _check(lib().pz_resample_multinomial(_ptr(lw, C.c_double), lw.size, seed, step, _ptr(anc, C.c_int32)))
     return anc
+
+
+# ---- output encoding (the JSON lines the Java glimpsetracks visualiser reads) -------------------
+def _num(x):
+    return repr(float(x))
+
+
+def json_line_tracks(ground_truth, particles, observations):
+    """One line of `examples mtt N` / `examples stt delay N` (test/Examples.hs:23-24,
+    SingleTargetTracking.hs:67-69): [[ [id,[x..]].. ], [ [ [id,{"mean":[..],"cov":[[..]..]}].. ] per particle ], [[ox,oy(,oz)]..]].
+    ground_truth: [(id, state)], particles: [[(id, mean, cov-or-None)]], observations: [[..]].
+    A track with cov None is an RConst and serialises as a bare array (DSProg.hs:52-54)."""
+    def vec(v):
+        return "[" + ",".join(_num(a) for a in v) + "]"
+
+    def track(t):
+        tid, mean, cov = t
+        if cov is None:
+            return "[%d,%s]" % (tid, vec(mean))
+        return '[%d,{"mean":%s,"cov":[%s]}]' % (tid, vec(mean), ",".join(vec(r) for r in cov))
+
+    gt = "[" + ",".join("[%d,%s]" % (i, vec(x)) for i, x in ground_truth) + "]"
+    ps = "[" + ",".join("[" + ",".join(track(t) for t in p) + "]" for p in particles) + "]"
+    ob = "[" + ",".join(vec(o) for o in observations) + "]"
+    return "[" + gt + "," + ps + "," + ob + "]"
+
+
+def json_line_generic1d(values):
+    """One line for Generic1D.java (:333-348): a flat array, one double per plotted series."""
+    return "[" + ",".join(_num(v) for v in values) + "]"

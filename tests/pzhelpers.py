@@ -80,6 +80,17 @@ def model_mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC):
     return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, I2, resampler=resampler)
 
 
+def model_mtt():
+    """Examples/MultiTargetTracking.hs:36-73: tracker constants over the (4,2) track model."""
+    d = model_mtt_track()
+    d.kind = PZ_MODEL_MTT
+    d.mtt.clutter_lambda, d.mtt.new_track_lambda, d.mtt.pd = 3.0, 0.1, 0.8
+    d.mtt.survival_prob = float(np.exp(-0.02))
+    d.mtt.clutter_var, d.mtt.birth_pos_var, d.mtt.birth_vel_var, d.mtt.meas_var = 10.0, 5.0, 0.1, 1.0
+    d.mtt.k_max, d.mtt.m_max = 16, 32
+    return d
+
+
 def desc_arrays(desc):
     nx, ny = desc.nx, desc.ny
     F = np.array(desc.F[: nx * nx]).reshape(nx, nx)
@@ -128,6 +139,16 @@ def oracle():
     lib.pzo_generate_observations.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_int64, f64p, f64p]
     lib.pzo_refpf_run.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64, f64p, C.c_int64, C.c_int, f64p, f64p, C.c_int]
     lib.pzo_num_threads.restype = C.c_int
+    lib.pzo_mtt_generate.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_int64, C.c_int32, f64p, i32p, f64p, i32p]
+    lib.pzo_mtt_create.restype = C.c_void_p
+    lib.pzo_mtt_create.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64]
+    lib.pzo_mtt_destroy.argtypes = [C.c_void_p]
+    lib.pzo_mtt_step.argtypes = [C.c_void_p, f64p, C.c_int32, f64p, f64p, f64p]
+    lib.pzo_mtt_max_simplification_error.restype = C.c_double
+    lib.pzo_mtt_max_simplification_error.argtypes = [C.c_void_p]
+    lib.pzo_mtt_logw.argtypes = [C.c_void_p, f32p]
+    lib.pzo_mtt_particle.argtypes = [C.c_void_p, C.c_int64, i32p, f64p, f64p]
+    lib.pzo_mtt_track_posterior.argtypes = [C.c_void_p, C.c_int32, f64p, f64p]
     _oracle = lib
     return lib
 
@@ -239,3 +260,42 @@ def assert_within_mc_tolerance(est, exact, what):
     se_bias = per_seed_bias.std(axis=0, ddof=1) / np.sqrt(S)
     zb = per_seed_bias.mean(axis=0) / np.maximum(se_bias, 1e-300)
     assert np.all(np.abs(zb) < 4.5), (what, "time-averaged bias beyond 4.5 SE of the seed average", zb)
+
+
+def mtt_scenario(T, seed=5):
+    """Ground truth + detections from the generative model (generateGroundTruth, MTT.hs:126-131).
+    Returns (desc, [obs_t as (M_t, 2) arrays], [truth_t as list of (id, x[4])])."""
+    lib = oracle()
+    d = model_mtt()
+    obs = np.zeros((T, 32, 2)); nobs = np.zeros(T, np.int32)
+    truth = np.zeros((T, 16, 5)); ntr = np.zeros(T, np.int32)
+    lib.pzo_mtt_generate(C.byref(d), seed, T, 32, ptr(obs, C.c_double), ptr(nobs, C.c_int32), ptr(truth, C.c_double), ptr(ntr, C.c_int32))
+    return d, [np.ascontiguousarray(obs[t, :nobs[t]]) for t in range(T)], \
+        [[(int(truth[t, k, 0]), truth[t, k, 1:].copy()) for k in range(ntr[t])] for t in range(T)]
+
+
+class OracleMtt:
+    def __init__(self, desc, n, seed):
+        self.lib = oracle(); self.n = n
+        self.h = self.lib.pzo_mtt_create(C.byref(desc), n, seed)
+
+    def step(self, obs):
+        o = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 2)
+        m, v, lz = C.c_double(), C.c_double(), C.c_double()
+        rc = self.lib.pzo_mtt_step(self.h, ptr(o, C.c_double) if o.size else None, o.shape[0], C.byref(m), C.byref(v), C.byref(lz))
+        return rc, m.value, v.value, lz.value
+
+    def logw(self):
+        out = np.zeros(self.n, np.float32); self.lib.pzo_mtt_logw(self.h, ptr(out, C.c_float)); return out
+
+    def track_posterior(self, tid):
+        m = np.zeros(4); fr = C.c_double()
+        self.lib.pzo_mtt_track_posterior(self.h, tid, ptr(m, C.c_double), C.byref(fr))
+        return m, fr.value
+
+    def simplification_error(self):
+        return self.lib.pzo_mtt_max_simplification_error(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.pzo_mtt_destroy(self.h); self.h = None

@@ -1,0 +1,152 @@
+"""Multi-target tracker (Examples/MultiTargetTracking.hs:26-145).
+
+CPU: the oracle's term-by-term weight equals the reduced form the kernel computes; a
+single-target / no-clutter scenario collapses to the exact Kalman filter of the (4,2) track
+model; the JSON line has the shape App.java:347-399 reads.
+GPU (-m gpu): the CUDA tracker against the CPU restatement on the same detection stream
+(statistical: different RNG streams and fp32 vs fp64), its resampling against the oracle's
+canonical resampler on the device's own log-weights (bit-exact), and the track read-out."""
+import json
+
+import numpy as np
+import pytest
+
+import pzhelpers as H
+
+
+def test_oracle_weight_reduction_and_tracking():
+    d, obs, truth = H.mtt_scenario(60)
+    f = H.OracleMtt(d, 2000, 3)
+    cnt = []
+    for o in obs:
+        rc, m, v, lz = f.step(o)
+        assert rc == 0 and np.isfinite(lz)
+        cnt.append(m)
+    # -log q + log prior + log likelihood == sum_j log L_j + n_undet log(1 - ps pd) - (lc + lb) - log M!
+    assert f.simplification_error() < 1e-9
+    true_cnt = np.array([len(t) for t in truth])
+    # over the last 20 steps the filter's expected track count follows the truth
+    assert abs(np.mean(cnt[-20:]) - np.mean(true_cnt[-20:])) < 1.0
+    f.close()
+
+
+def test_oracle_single_target_reduces_to_kalman():
+    """pd = 1, (almost) no clutter or births after the first detection: the surviving track's
+    Rao-Blackwellised posterior is the exact Kalman posterior of the track model started from the
+    birth prior conditioned on the first detection."""
+    d = H.model_mtt()
+    d.mtt.pd, d.mtt.survival_prob = 0.999999, 0.999999
+    d.mtt.clutter_lambda, d.mtt.new_track_lambda = 1e-9, 1e-3
+    lg = H.model_mtt_track()
+    T = 12
+    yobs, _ = H.gen_obs(lg, T, seed=77)
+    f = H.OracleMtt(d, 64, 1)
+    F, Q, Hm, R = H.desc_arrays(lg)
+    mean = np.zeros(4); P = np.diag([5.0, 5.0, 0.1, 0.1])
+    for t in range(T):
+        rc, m, v, lz = f.step(yobs[t][None, :])
+        assert rc == 0
+        if t > 0:
+            mean = F @ mean; P = F @ P @ F.T + Q
+        S = Hm @ P @ Hm.T + R; K = P @ Hm.T @ np.linalg.inv(S)
+        mean = mean + K @ (yobs[t] - Hm @ mean); P = P - K @ Hm @ P
+        post, frac = f.track_posterior(0)
+        assert frac > 0.99 and abs(m - 1.0) < 0.02
+        assert np.allclose(post, mean, atol=1e-9)
+    f.close()
+
+
+def test_json_line_matches_java_parser(pz):
+    """App.java:347-399: arr[0] = [[id,[x,y,..]]..]; arr[1][i][j] = [id, {"mean":[..],"cov":[[..],[..],..]}] or
+    [id,[..]] (RConst); arr[2] = [[ox,oy]..]; only elements 0 and 1 of mean / cov rows are read."""
+    gt = [(0, [1.0, 2.0, 0.1, 0.2]), (3, [-1.5, 0.25, 0.0, 0.0])]
+    cov = np.arange(16.0).reshape(4, 4)
+    parts = [[(0, [1.1, 2.1, 0.0, 0.0], cov), (3, [0.0, 0.0, 0.0, 0.0], None)], []]
+    line = pz.json_line_tracks(gt, parts, [[0.5, -0.5], [3.0, 4.0]])
+    assert "\n" not in line
+    arr = json.loads(line)
+    assert len(arr) == 3
+    for node in arr[0]:
+        assert isinstance(node[0], int) and float(node[1][0]) == float(node[1][0]) and len(node[1]) >= 2
+    p0 = arr[1][0]
+    assert p0[0][0] == 0 and p0[0][1]["mean"][:2] == [1.1, 2.1]
+    assert p0[0][1]["cov"][0][0] == 0.0 and p0[0][1]["cov"][0][1] == 1.0 and p0[0][1]["cov"][1][1] == 5.0
+    assert isinstance(p0[1][1], list) and len(p0[1][1]) == 4      # RConst: bare array
+    assert arr[1][1] == [] and arr[2] == [[0.5, -0.5], [3.0, 4.0]]
+    flat = json.loads(pz.json_line_generic1d([1.0, 2.5, -3.0]))     # Generic1D.java:333-348
+    assert flat == [1.0, 2.5, -3.0]
+
+
+@pytest.mark.gpu
+def test_gpu_tracker_matches_cpu_restatement(pz):
+    d, obs, truth = H.mtt_scenario(50)
+    n, seeds = 20000, 6
+    gpu = np.zeros((seeds, len(obs))); cpu = np.zeros((seeds, len(obs)))
+    glz = np.zeros((seeds, len(obs))); clz = np.zeros((seeds, len(obs)))
+    for s in range(seeds):
+        zs = pz.zparticles(n, pz.mtt(), seed=10 + s)
+        orc = H.OracleMtt(d, n // 4, 100 + s)
+        for t, o in enumerate(obs):
+            post = zs.step(o)
+            rc, m, v, lz = orc.step(o)
+            assert rc == 0
+            gpu[s, t], cpu[s, t] = post.mean[0], m
+            glz[s, t], clz[s, t] = post.log_evidence_inc, lz
+        zs.close(); orc.close()
+    # expected track count: seed-averaged curves agree within Monte Carlo error
+    se = np.sqrt(gpu.var(axis=0, ddof=1) / seeds + cpu.var(axis=0, ddof=1) / seeds) + 0.02
+    z = (gpu.mean(axis=0) - cpu.mean(axis=0)) / se
+    assert np.mean(np.abs(z) > 3) < 0.1 and np.max(np.abs(z)) < 6, z
+    # log-evidence of the whole stream
+    a, b = glz.sum(axis=1), clz.sum(axis=1)
+    assert abs(a.mean() - b.mean()) < 4 * np.sqrt(a.var(ddof=1) / seeds + b.var(ddof=1) / seeds) + 0.5
+    true_cnt = np.array([len(t) for t in truth])
+    assert abs(gpu.mean(axis=0)[-15:].mean() - true_cnt[-15:].mean()) < 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_tracker_resampling_bit_exact_and_readout(pz):
+    d, obs, truth = H.mtt_scenario(30)
+    n = 30000
+    zs = pz.zparticles(n, pz.mtt(), seed=2)
+    lib = H.oracle()
+    for t, o in enumerate(obs):
+        post = zs.step(o)
+        if t in (3, 17, 29):
+            lw = zs.read_logw()
+            anc = zs.read_ancestors()
+            U = lib.pzo_resample_uniform(2, t + 1)   # the uniform of the NEXT step's resample
+            rc, ref = H.oracle_systematic(lw, U)
+            assert rc == 0 and np.array_equal(anc, ref), t
+    tracks = zs.read_tracks(stride=100)
+    assert len(tracks) == n // 100
+    cnts = np.array([len(p) for p in tracks])
+    assert abs(cnts.mean() - post.mean[0]) < 0.5
+    for p in tracks:
+        ids = [tid for tid, _, _ in p]
+        assert ids == sorted(ids) and len(set(ids)) == len(ids)
+        for tid, mean, cov in p:
+            assert np.all(np.isfinite(mean)) and np.allclose(cov, cov.T) and np.all(np.linalg.eigvalsh(cov) > -1e-4)
+    # the line the visualiser would read
+    line = pz.json_line_tracks(truth[-1], tracks[:100], obs[-1])
+    arr = json.loads(line)
+    assert len(arr[1]) == 100 and len(arr[2]) == len(obs[-1])
+    # a confidently tracked target: weighted posterior position close to the truth
+    if truth[-1]:
+        tid, x = truth[-1][0]
+        pos = np.array([m[:2] for p in tracks for i, m, c in p if i >= 0])
+        assert pos.size == 0 or np.min(np.linalg.norm(pos - x[:2], axis=1)) < 3.0
+    zs.close()
+
+
+@pytest.mark.gpu
+def test_gpu_tracker_capacity_and_errors(pz):
+    zs = pz.zparticles(4096, pz.mtt(), seed=1)
+    with pytest.raises(pz.PzError) as e:
+        zs.step(np.zeros((40, 2)))           # more than m_max detections
+    assert e.value.code == -5
+    post = zs.step(np.zeros((0, 2)))          # an empty scan is a valid step
+    assert post.mean[0] == 0.0
+    with pytest.raises(pz.PzError):
+        zs.read_state()
+    zs.close()
