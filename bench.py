@@ -266,6 +266,10 @@ def run_b200(args):
 
     # every rank tears its shard down together (NCCL communicator), then rank 0 reports
     n_migrated = int(post.n_migrated)
+    if world > 1:
+        mt = torch.tensor([n_migrated], device="cuda", dtype=torch.int64)
+        dist.all_reduce(mt)
+        n_migrated = int(mt.item())
     post_step, post_mean0, post_ess = int(post.step), float(post.mean[0]), float(post.ess)
     zs.close()
     if world > 1:
@@ -303,7 +307,7 @@ def run_b200(args):
                      "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
                                          "pf_partition": float(np.mean(prof[:, 2]))}},
         "cpu_baseline": cpu,
-        "posterior_check": {"step": post_step, "mean0": post_mean0, "ess": post_ess, "n_migrated_last_step_rank0": n_migrated},
+        "posterior_check": {"step": post_step, "mean0": post_mean0, "ess": post_ess, "n_migrated_last_step_all_ranks": n_migrated},
     }
     print(json.dumps(line), flush=True)
 

@@ -242,6 +242,18 @@ inline void lg_noise(int nx, uint64_t j, uint32_t t, uint64_t seed, float* z) {
     z[0] = (l & 1) ? z1 : z0;
     return;
   }
+  if (nx == 6) {
+    // two consecutive slots share three Philox calls (12 words): the even slot takes words 0..5,
+    // the odd slot words 6..11
+    uint32_t w[12];
+    for (int k = 0; k < 3; ++k) {
+      philox((uint32_t)(j >> 1), (uint32_t)k, t, kStreamProp, seed, r);
+      for (int i = 0; i < 4; ++i) w[4 * k + i] = r[i];
+    }
+    const int o = (j & 1) ? 6 : 0;
+    for (int k = 0; k < 3; ++k) normal_pair(w[o + 2 * k], w[o + 2 * k + 1], &z[2 * k], &z[2 * k + 1]);
+    return;
+  }
   for (int k = 0; 4 * k < nx; ++k) {
     philox((uint32_t)j, (uint32_t)k, t, kStreamProp, seed, r);
     float zz[4];

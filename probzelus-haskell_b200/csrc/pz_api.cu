@@ -90,6 +90,26 @@ int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
   }
   const bool dbl = (ny == 1 && d->scalar_ll_2x);
   p->wscale = dbl ? -1.0f : -0.5f;
+  // position/velocity structure: F = [[a,b],[c,d]] (x) I_p, Q = diag(qp I, qv I), H = [I_p 0], R = r I_p
+  p->kron = 0;
+  if (nx % 2 == 0 && ny == nx / 2 && !getenv("PZ_NO_KRON")) {
+    const int P = nx / 2;
+    bool ok = true;
+    const float a = p->F[0][0], b = p->F[0][P], c = p->F[P][0], dd = p->F[P][P];
+    const float lp = p->Lq[0][0], lv = p->Lq[P][P], ri = p->Rinv[0][0];
+    for (int i = 0; i < nx && ok; ++i)
+      for (int j = 0; j < nx; ++j) {
+        const int bi = i / P, bj = j / P;
+        const float fexp = (i % P == j % P) ? (bi == 0 ? (bj == 0 ? a : b) : (bj == 0 ? c : dd)) : 0.0f;
+        const float lexp = (i == j) ? (bi == 0 ? lp : lv) : 0.0f;
+        if (p->F[i][j] != fexp || p->Lq[i][j] != lexp) { ok = false; break; }
+      }
+    for (int i = 0; i < ny && ok; ++i) {
+      for (int j = 0; j < nx; ++j) if (p->H[i][j] != ((i == j) ? 1.0f : 0.0f)) ok = false;
+      for (int j = 0; j < ny; ++j) if (p->Rinv[i][j] != ((i == j) ? ri : 0.0f)) ok = false;
+    }
+    if (ok) { p->kron = 1; p->ka = a; p->kb = b; p->kc = c; p->kd = dd; p->klp = lp; p->klv = lv; p->krinv = ri; }
+  }
   *ll_const = (dbl ? -1.0 : -0.5) * (logdet + ny * log(2 * M_PI));
   return PZ_OK;
 }
@@ -601,6 +621,18 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
     memcpy(&id, nccl_id, sizeof(id));
     ncclResult_t r = g_nccl.CommInitRank(&f->comm, world, id, rank);
     if (r != ncclSuccess) { int c = fail(PZ_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); free_filter(f); return c; }
+    // establish every peer-to-peer connection now (NCCL sets channels up lazily on first use, which
+    // would otherwise land in the first step that happens to migrate particles to a new peer)
+    {
+      bool ok = g_nccl.GroupStart() == ncclSuccess;
+      for (int peer = 0; peer < world && ok; ++peer) {
+        if (peer == rank) continue;
+        ok = g_nccl.Send(a.shard_table, 1, ncclInt32, peer, f->comm, f->stream) == ncclSuccess &&
+             g_nccl.Recv(a.shard_table + 1, 1, ncclInt32, peer, f->comm, f->stream) == ncclSuccess;
+      }
+      ok = (g_nccl.GroupEnd() == ncclSuccess) && ok;
+      if (!ok) { int c = fail(PZ_ENCCL, "NCCL peer warm-up failed"); free_filter(f); return c; }
+    }
     int n = 0;
     rc = sharded_advance(f, 0, &n);
     if (rc) { free_filter(f); return rc; }

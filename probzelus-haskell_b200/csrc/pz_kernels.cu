@@ -22,6 +22,9 @@
 //   pf_partition       merge-path split: first input block of every output tile.
 //
 // No tensor cores: the path is a streaming scan / gather; see DESIGN.md for the roofline.
+#include <cstdlib>
+#include <cstring>
+
 #include "pz_kernels.cuh"
 #include "pz_math.cuh"
 
@@ -128,6 +131,47 @@ __device__ __forceinline__ float lg_logweight(const LgDev& p, const float* xn, c
   return __fmul_rn(p.wscale, quad);
 }
 
+// position/velocity structured variants (LgDev::kron): same operations as the dense code minus the
+// terms whose coefficient is zero
+template <int NX>
+__device__ __forceinline__ void kron_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+  constexpr int P = NX / 2;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    float acc = __fmul_rn(p.ka, x[i]);
+    acc = __fmaf_rn(p.kb, x[P + i], acc);
+    xn[i] = __fmaf_rn(p.klp, z[i], acc);
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    float acc;
+    if (p.kc != 0.0f) { acc = __fmul_rn(p.kc, x[i]); acc = __fmaf_rn(p.kd, x[P + i], acc); }
+    else acc = __fmul_rn(p.kd, x[P + i]);
+    xn[P + i] = __fmaf_rn(p.klv, z[P + i], acc);
+  }
+}
+
+template <int NX, int NY>
+__device__ __forceinline__ float kron_logweight(const LgDev& p, const float* xn, const float* y) {
+  float quad = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NY; ++k) {
+    const float d = __fsub_rn(y[k], xn[k]);
+    const float t = __fmul_rn(p.krinv, d);
+    quad = (k == 0) ? __fmul_rn(d, t) : __fmaf_rn(d, t, quad);
+  }
+  return __fmul_rn(p.wscale, quad);
+}
+
+template <int NX, bool KRON>
+__device__ __forceinline__ void model_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+  if constexpr (KRON) kron_propagate<NX>(p, x, z, xn); else lg_propagate<NX>(p, x, z, xn);
+}
+template <int NX, int NY, bool KRON>
+__device__ __forceinline__ float model_logweight(const LgDev& p, const float* xn, const float* y) {
+  if constexpr (KRON) return kron_logweight<NX, NY>(p, xn, y); else return lg_logweight<NX, NY>(p, xn, y);
+}
+
 // normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]
 template <int NX>
 __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed, float (&z)[NX][4]) {
@@ -136,6 +180,21 @@ __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed,
     U4 r = philox4x32_10(j >> 2, 0u, t, kStreamProp, k0, k1);
     normal_pair(r.x, r.y, z[0][0], z[0][1]);
     normal_pair(r.z, r.w, z[0][2], z[0][3]);
+  } else if constexpr (NX == 6) {
+    // two consecutive slots share three Philox calls: even slot words 0..5, odd slot words 6..11
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+      const U4 r0 = philox4x32_10((j >> 1) + pr, 0u, t, kStreamProp, k0, k1);
+      const U4 r1 = philox4x32_10((j >> 1) + pr, 1u, t, kStreamProp, k0, k1);
+      const U4 r2 = philox4x32_10((j >> 1) + pr, 2u, t, kStreamProp, k0, k1);
+      const int s = 2 * pr;
+      normal_pair(r0.x, r0.y, z[0][s], z[1][s]);
+      normal_pair(r0.z, r0.w, z[2][s], z[3][s]);
+      normal_pair(r1.x, r1.y, z[4][s], z[5][s]);
+      normal_pair(r1.z, r1.w, z[0][s + 1], z[1][s + 1]);
+      normal_pair(r2.x, r2.y, z[2][s + 1], z[3][s + 1]);
+      normal_pair(r2.z, r2.w, z[4][s + 1], z[5][s + 1]);
+    }
   } else {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -458,7 +517,7 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
 // resample phase shared by the step and the ancestor kernels
 // ------------------------------------------------------------------------------------------
 // Sources: what one particle contributes (its weight) and what is staged for its children.
-template <int NX, int NY>
+template <int NX, int NY, bool KRON>
 struct StateSource {
   const float* x;      // X[cur]
   int64_t ld, n_local;
@@ -473,18 +532,24 @@ struct StateSource {
       const float4 f = *reinterpret_cast<const float4*>(x + (size_t)d * ld + i0);
       v[d][0] = f.x; v[d][1] = f.y; v[d][2] = f.z; v[d][3] = f.w;
     }
+    if (uniform) {  // the initial point mass: equal weights (lw = 0 -> n = 0, m = 2^23)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int32_t n; uint32_t mm;
-      if (uniform) { n = 0; mm = 1u << 23; }
-      else {
+      for (int k = 0; k < 4; ++k) q[k] = q_at(1u << 23, 0, eb);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int32_t n; uint32_t mm;
         float xs[NX];
 #pragma unroll
         for (int d = 0; d < NX; ++d) xs[d] = v[d][k];
-        weight_split(lg_logweight<NX, NY>(*m, xs, y), n, mm);
+        weight_split(model_logweight<NX, NY, KRON>(*m, xs, y), n, mm);
+        q[k] = q_at(mm, n, eb);
       }
-      q[k] = q_at(mm, n, eb);
-      if (!FULL && i0 + k >= n_local) q[k] = 0;
+    }
+    if (!FULL) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k >= n_local) q[k] = 0;
     }
   }
   __device__ __forceinline__ void put(float* s_par, int stride, uint32_t slot, int k, int64_t) const {
@@ -540,12 +605,15 @@ __device__ __forceinline__ void resample_half(Source& src, float* s_par, uint16_
     const uint32_t lo = max(o_lo, j0), hi = min(o[k], jend);
     if (lo < hi) {
       uint32_t slot = lo - j0;
-      const uint32_t slot_hi = hi - j0;
-      do {
-        s_head[slot] = (uint16_t)(slot + 1);
-        src.put(s_par, stride, slot, k, i0);
-        slot = (slot + 128u) & ~127u;
-      } while (slot < slot_hi);
+      const uint32_t slot_last = hi - j0 - 1u;
+      s_head[slot] = (uint16_t)(slot + 1);
+      src.put(s_par, stride, slot, k, i0);
+      if ((slot ^ slot_last) >> 7) {  // rare: the children span a segment boundary
+        for (slot = (slot + 128u) & ~127u; slot <= slot_last; slot += 128u) {
+          s_head[slot] = (uint16_t)(slot + 1);
+          src.put(s_par, stride, slot, k, i0);
+        }
+      }
     }
     o_lo = o[k];
   }
@@ -599,7 +667,7 @@ struct TileArgs {
 // resident CTAs per SM the register allocation is held to (NX = 1 / 4 / 6)
 constexpr int min_ctas(int nx) { return nx == 1 ? 4 : (nx <= 4 ? 3 : 2); }
 
-template <int NX, int NY, int TO, int MODE>
+template <int NX, int NY, int TO, int MODE, bool KRON>
 __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __grid_constant__ TileArgs ta) {
   extern __shared__ __align__(16) float s_par[];  // [NX][TO] parents, then [TO] head marks (u16)
   __shared__ int32_t s_eref[kWarps];
@@ -628,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
     }
     __syncthreads();
     SlotMap sm(pl, a.n_global);
-    StateSource<NX, NY> src;
+    StateSource<NX, NY, KRON> src;
     src.x = xin; src.ld = a.ld; src.n_local = a.n_local; src.m = &a.model;
     src.uniform = a.ctl->uniform_in != 0;
     const uint32_t tp = (t + kObsRing - 1) % kObsRing;
@@ -687,13 +755,18 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
         float xs[NX], zs[NX], xn[NX];
 #pragma unroll
         for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
-        lg_propagate<NX>(a.model, xs, zs, xn);
+        model_propagate<NX, KRON>(a.model, xs, zs, xn);
 #pragma unroll
         for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-        weight_split(lg_logweight<NX, NY>(a.model, xn, y_new), nn[half * 4 + k], mm[half * 4 + k]);
-        if (!full_tile && sl + k >= nslots) { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
-        emx = max(emx, nn[half * 4 + k]);
+        weight_split(model_logweight<NX, NY, KRON>(a.model, xn, y_new), nn[half * 4 + k], mm[half * 4 + k]);
       }
+      if (!full_tile) {  // only the last tile of a population whose size is not a multiple of TO
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (sl + k >= nslots) { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emx = max(emx, nn[half * 4 + k]);
       if (full_tile || sl < nslots) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
@@ -730,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
           p_sw2 = __fmaf_rn(w, w, p_sw2);
 #pragma unroll
           for (int d = 0; d < NX; ++d) {
-            const float dx = q ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
+            const float dx = __fsub_rn(xv[d][k], cen[d]);
             const float wd = __fmul_rn(w, dx);
             p_sx[d] = __fadd_rn(p_sx[d], wd);
             p_sxx[d] = __fmaf_rn(wd, dx, p_sxx[d]);
@@ -988,7 +1061,14 @@ __global__ void pf_boundary_table(const PlanDev* plan, const u64* pbx, int64_t n
 // ------------------------------------------------------------------------------------------
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-int fused_tile_out(int nx) { return nx == 1 ? 4096 : 2048; }
+// Output slots per CTA.  Larger tiles amortise the per-tile overlap of the input side (one extra
+// input block per tile on average) and the CTA-level reduction; PZ_TILE_OUT=small selects the
+// smaller instantiation (kept for A/B measurements, profiles/README.md).
+int fused_tile_out(int nx) {
+  static const bool small = [] { const char* e = getenv("PZ_TILE_OUT"); return e && !strcmp(e, "small"); }();
+  if (nx == 1) return small ? 4096 : 8192;
+  return small ? 2048 : 4096;
+}
 
 int launch_init(const StepArgs& a, cudaStream_t s) {
   int64_t m = a.nblk * kBlk;
@@ -1031,9 +1111,9 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
   return scan_partition(a, 0, tile_out, s);
 }
 
-template <int NX, int NY, int TO, int MODE>
+template <int NX, int NY, int TO, int MODE, bool KRON>
 static void launch_tile(const TileArgs& ta, cudaStream_t s) {
-  auto kern = pf_step_tile<NX, NY, TO, MODE>;
+  auto kern = pf_step_tile<NX, NY, TO, MODE, KRON>;
   size_t smem = (size_t)NX * TO * sizeof(float) + (size_t)TO * sizeof(uint16_t);
   static bool attr_done = false;
   if (!attr_done) {
@@ -1046,15 +1126,27 @@ static void launch_tile(const TileArgs& ta, cudaStream_t s) {
 static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
   const int nx = ta.a.model.nx, ny = ta.a.model.ny;
   const bool fused = (ta.anc == nullptr);
-#define PZ_DISPATCH(NXv, NYv, TOv)                                   \
-  if (nx == NXv && ny == NYv) {                                      \
-    if (fused) launch_tile<NXv, NYv, TOv, 0>(ta, s);                 \
-    else launch_tile<NXv, NYv, TOv, 1>(ta, s);                       \
+  const bool kron = ta.a.model.kron != 0;
+#define PZ_DISPATCH(NXv, NYv, TOv, KR)                               \
+  if (nx == NXv && ny == NYv && kron == KR) {                        \
+    if (fused) launch_tile<NXv, NYv, TOv, 0, KR>(ta, s);             \
+    else launch_tile<NXv, NYv, TOv, 1, KR>(ta, s);                   \
     return 1;                                                        \
   }
-  PZ_DISPATCH(1, 1, 4096)
-  PZ_DISPATCH(4, 2, 2048)
-  PZ_DISPATCH(6, 3, 2048)
+  const bool big = fused_tile_out(nx) > (nx == 1 ? 4096 : 2048);
+  if (big) {
+    PZ_DISPATCH(1, 1, 8192, false)
+    PZ_DISPATCH(4, 2, 4096, false)
+    PZ_DISPATCH(4, 2, 4096, true)
+    PZ_DISPATCH(6, 3, 4096, false)
+    PZ_DISPATCH(6, 3, 4096, true)
+  } else {
+    PZ_DISPATCH(1, 1, 4096, false)
+    PZ_DISPATCH(4, 2, 2048, false)
+    PZ_DISPATCH(4, 2, 2048, true)
+    PZ_DISPATCH(6, 3, 2048, false)
+    PZ_DISPATCH(6, 3, 2048, true)
+  }
 #undef PZ_DISPATCH
   return -1;
 }

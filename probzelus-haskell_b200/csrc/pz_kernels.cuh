@@ -37,6 +37,12 @@ struct LgDev {
   float x0[PZ_MAX_NX];
   float wscale;
   int32_t nx, ny;
+  // Position/velocity ("Kronecker") structure, detected on the host: state = (pos[p], vel[p]),
+  // F = [[a, b], [c, d]] (x) I_p, Q = diag(qp I, qv I), H = [I_p 0], R = r I_p.  The specialised
+  // code path performs exactly the operations of the dense spec that have non-zero coefficients,
+  // in the same order, so the results are bit-identical.
+  int32_t kron;
+  float ka, kb, kc, kd, klp, klv, krinv;
 };
 
 // Resampling plan + posterior moment sums of one weighted population (device resident).

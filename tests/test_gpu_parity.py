@@ -235,3 +235,30 @@ def test_large_n_properties(pz):
     zs2 = pz.zparticles(n, d, seed=5)
     zs2.run(obs)
     assert np.array_equal(zs2.read_ancestors(), anc)
+
+
+@pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
+def test_independent_of_tile_size_and_specialisation(pz, model):
+    """Launch-shape independence: the small / large output-tile instantiations and the dense /
+    position-velocity specialised model code give the same bits (separate processes: the choice is
+    read once from the environment)."""
+    import hashlib
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as g, pzhelpers as H\n"
+        "pz = g.load_package()\n"
+        "hd = {'rw1d': H.model_rw1d, 'mtt_track': H.model_mtt_track, 'stt': H.model_stt}[%r]()\n"
+        "obs, _ = H.gen_obs(hd, 5)\n"
+        "zs = pz.zparticles(50000 + 77, getattr(pz, %r)(), seed=31)\n"
+        "posts = zs.run(obs)\n"
+        "print(hashlib.sha256(zs.read_state().tobytes()).hexdigest(), posts[-1].total_weight)\n"
+    ) % (H.ROOT, H.ROOT + "/tests", model, model)
+    outs = set()
+    for env in ({}, {"PZ_TILE_OUT": "small"}, {"PZ_NO_KRON": "1"}, {"PZ_TILE_OUT": "small", "PZ_NO_KRON": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**__import__("os").environ, **env})
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.add(r.stdout.strip().split("\n")[-1])
+    assert len(outs) == 1, outs
