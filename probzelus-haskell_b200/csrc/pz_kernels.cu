@@ -803,7 +803,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
           p_sw2 = __fmaf_rn(w, w, p_sw2);
 #pragma unroll
           for (int d = 0; d < NX; ++d) {
-            const float dx = __fsub_rn(xv[d][k], cen[d]);
+            // slots past the population's end hold uninitialised staging data (weight 0, but 0 * NaN = NaN)
+            const float dx = (full_tile || sl + k < nslots) ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
             const float wd = __fmul_rn(w, dx);
             p_sx[d] = __fadd_rn(p_sx[d], wd);
             p_sxx[d] = __fmaf_rn(wd, dx, p_sxx[d]);
