@@ -35,6 +35,7 @@
 #include <algorithm>
 
 #include "../include/pzgpu.h"
+#include "../include/pz_spec_tables.h"
 
 #if defined(_OPENMP)
 #include <omp.h>
@@ -83,63 +84,61 @@ inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 constexpr float kLog2e = 0x1.715476p+0f;
-constexpr float kNeg2Ln2 = -0x1.62e430p+0f;
-constexpr float kHalfPi = 0x1.921fb6p+0f;
-constexpr float kExp2C[7] = {0x1.62e430p-1f, 0x1.ebfbe0p-3f, 0x1.c6b08ep-5f, 0x1.3b2a1cp-7f,
-                             0x1.5d8776p-10f, 0x1.444004p-13f, 0x1.00c0e6p-16f};
-constexpr float kLogC[8] = {0x1.555552p-2f, -0x1.0000c8p-2f, 0x1.99a14cp-3f, -0x1.54d54ep-3f,
-                            0x1.22dc4cp-3f, -0x1.09abe4p-3f, 0x1.04591ap-3f, -0x1.4bd700p-4f};
-constexpr float kSinC[3] = {-0x1.555552p-3f, 0x1.110c2ap-7f, -0x1.9aca02p-13f};
-constexpr float kCosC[3] = {0x1.555554p-5f, -0x1.6c12d4p-10f, 0x1.9bd8d2p-16f};
+constexpr int32_t kNZero = -(1 << 30);  // exponent marker of an empty block (every weight zero)
+constexpr int kGuard = 16;              // guard bits of the global fixed-point scale
+constexpr int kBlk = 256;
 
-constexpr int32_t kNZero = -(1 << 30);  // exponent marker of a zero weight
+static const float kIcdfTab[PZ_ICDF_ROWS][4] = PZ_ICDF_TABLE_INIT;
 
-// log-weight -> (n, m): weight = m * 2^(n-23), m in [2^22.5, 2^23.5].  Zero weight: m = 0.
-inline void weight_split(float lw, int32_t* n, uint32_t* m) {
-  *n = kNZero; *m = 0;
-  float e = lw * kLog2e;
-  if (!(fabsf(e) < 1.0e6f)) return;  // -inf, +inf, NaN, out of range -> zero weight
-  float r = rintf(e);
-  float f = e - r;
-  float p = kExp2C[6];
-  for (int i = 5; i >= 0; --i) p = fmaf(p, f, kExp2C[i]);
+// One 32-bit word -> one N(0,1) draw by the inverse CDF on dyadic segments (spec v2, DESIGN.md
+// "Canonical math"): bit 31 is the sign; v = (r << 1) | 1 is the tail probability u = v * 2^-33
+// in (0, 1/2); k = clz(v) selects the dyadic segment [2^-(k+2), 2^-(k+1)), the next 3 bits the
+// sub-segment, the following 23 bits the cubic's argument tf in [1, 2).
+inline float icdf_normal(uint32_t r) {
+  const uint32_t v = (r << 1) | 1u;
+  const int k = __builtin_clz(v);
+  const uint32_t vn = v << k;
+  const uint32_t row = ((uint32_t)k << PZ_ICDF_SUB_BITS) + ((vn >> 28) & 7u);
+  const float tf = u2f(0x3F800000u | ((vn >> 5) & 0x7FFFFFu));
+  const float* c = kIcdfTab[row];
+  const float z = fmaf(fmaf(fmaf(c[3], tf, c[2]), tf, c[1]), tf, c[0]);
+  return u2f(f2u(z) ^ (r & 0x80000000u));
+}
+
+// Block exponent n_b from the block's largest log-weight (-inf: empty block).
+inline int32_t block_exponent(float maxlw) {
+  if (!(maxlw > -INFINITY)) return kNZero;
+  float e = maxlw * kLog2e;
+  e = fminf(fmaxf(e, -262144.0f), 262144.0f);
+  return (int32_t)rintf(e);
+}
+
+// Weight of a particle relative to 2^n_b: w = 2^d, d = max(lw * log2(e) - n_b, -32), by the
+// degree-5 polynomial of include/pz_spec_tables.h, and its 16-bit fixed-point value
+// q = rint(w * 2^15) (<= 46990).  NaN log-weights give the smallest weight (q = 0).
+inline void weight_q(float lw, float nbf, float* w, uint32_t* q) {
+  float d = fmaf(lw, kLog2e, -nbf);
+  d = fminf(fmaxf(d, -32.0f), 1.0f);
+  const float t = d + 12582912.0f;
+  const float r = t - 12582912.0f;
+  const float f = d - r;
+  float p = PZ_EXP2_C5;
+  p = fmaf(p, f, PZ_EXP2_C4);
+  p = fmaf(p, f, PZ_EXP2_C3);
+  p = fmaf(p, f, PZ_EXP2_C2);
+  p = fmaf(p, f, PZ_EXP2_C1);
   p = fmaf(p, f, 1.0f);
-  *n = (int32_t)r;
-  *m = (uint32_t)(int32_t)rintf(p * 8388608.0f);
+  const float wv = u2f(f2u(p) + (f2u(t) << 23));
+  *w = wv;
+  *q = f2u(fmaf(wv, 32768.0f, 8388608.0f)) & 0x7FFFFFu;
 }
 
-// two 32-bit words -> two independent N(0,1) draws (Box-Muller on the canonical math)
-inline void normal_pair(uint32_t ra, uint32_t rb, float* z0, float* z1) {
-  float u = fmaf((float)ra, 0x1p-32f, 0x1p-33f);  // (0, 1]
-  uint32_t bits = f2u(u);
-  int32_t e = (int32_t)(bits - 0x3F3504F3u) >> 23;
-  float mant = u2f(bits - ((uint32_t)e << 23));  // [sqrt(.5), sqrt(2))
-  float t = mant - 1.0f;
-  float t2 = t * t;
-  float P = kLogC[7];
-  for (int i = 6; i >= 0; --i) P = fmaf(P, t, kLogC[i]);
-  float lnm = fmaf(t2 * t, P, fmaf(-0.5f, t2, t));
-  float rad2 = fmaf((float)e, kNeg2Ln2, -2.0f * lnm);
-  rad2 = fmaxf(rad2, 0.0f);
-  float R = sqrtf(rad2);
-  uint32_t q = rb >> 30;
-  float fr = fmaf((float)(rb & 0x3FFFFFFFu), 0x1p-30f, -0.5f);
-  float phi = fr * kHalfPi;
-  float z = phi * phi;
-  float S = fmaf(fmaf(kSinC[2], z, kSinC[1]), z, kSinC[0]);
-  float C = fmaf(fmaf(kCosC[2], z, kCosC[1]), z, kCosC[0]);
-  float s = fmaf(phi * z, S, phi);
-  float c = fmaf(z * z, C, fmaf(-0.5f, z, 1.0f));
-  float cq, sq;
-  switch (q) {
-    case 0: cq = c; sq = s; break;
-    case 1: cq = -s; sq = c; break;
-    case 2: cq = -c; sq = -s; break;
-    default: cq = s; sq = -c; break;
-  }
-  *z0 = R * cq;
-  *z1 = R * sq;
-}
+// stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)
+inline float sanitize_lw(float lw) { return (lw == lw && lw < INFINITY) ? lw : -INFINITY; }
+
+// CDF order inside a canonical block: position p <-> memory offset (two interleaved halves of
+// 128, four particles per lane): p = lane * 8 + half * 4 + k  <->  off = half * 128 + lane * 4 + k.
+inline int cdf_offset(int p) { return ((p >> 2) & 1) * 128 + (p >> 3) * 4 + (p & 3); }
 
 // ---------------------------------------------------------------------------------------
 // Linear-Gaussian model family: derived fp32 parameters.
@@ -231,94 +230,99 @@ inline float lg_logweight(const LgParams& p, const float* xn, const float* y) {
   return p.wscale * quad;
 }
 
-// normals for output slot j at step t (counter keyed on the GLOBAL slot, never on a thread id)
+// normals for output slot j at step t (counter keyed on the GLOBAL slot, never on a thread id):
+// one Philox word per normal.  nx = 1: four consecutive slots share one call; nx = 6: two
+// consecutive slots share three calls (even slot words 0..5, odd slot words 6..11); otherwise
+// ceil(nx / 4) calls per slot.
 inline void lg_noise(int nx, uint64_t j, uint32_t t, uint64_t seed, float* z) {
   uint32_t r[4];
   if (nx == 1) {
     philox((uint32_t)(j >> 2), 0, t, kStreamProp, seed, r);
-    int l = (int)(j & 3);
-    float z0, z1;
-    normal_pair(r[2 * (l >> 1)], r[2 * (l >> 1) + 1], &z0, &z1);
-    z[0] = (l & 1) ? z1 : z0;
+    z[0] = icdf_normal(r[j & 3]);
     return;
   }
   if (nx == 6) {
-    // two consecutive slots share three Philox calls (12 words): the even slot takes words 0..5,
-    // the odd slot words 6..11
     uint32_t w[12];
     for (int k = 0; k < 3; ++k) {
       philox((uint32_t)(j >> 1), (uint32_t)k, t, kStreamProp, seed, r);
       for (int i = 0; i < 4; ++i) w[4 * k + i] = r[i];
     }
     const int o = (j & 1) ? 6 : 0;
-    for (int k = 0; k < 3; ++k) normal_pair(w[o + 2 * k], w[o + 2 * k + 1], &z[2 * k], &z[2 * k + 1]);
+    for (int k = 0; k < 6; ++k) z[k] = icdf_normal(w[o + k]);
     return;
   }
   for (int k = 0; 4 * k < nx; ++k) {
     philox((uint32_t)j, (uint32_t)k, t, kStreamProp, seed, r);
-    float zz[4];
-    normal_pair(r[0], r[1], &zz[0], &zz[1]);
-    normal_pair(r[2], r[3], &zz[2], &zz[3]);
-    for (int i = 0; i < 4 && 4 * k + i < nx; ++i) z[4 * k + i] = zz[i];
+    for (int i = 0; i < 4 && 4 * k + i < nx; ++i) z[4 * k + i] = icdf_normal(r[i]);
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// Canonical fixed-point systematic resampler "PZ-SYS-256" (DESIGN.md "Resampler").
+// Canonical fixed-point systematic resampler "PZ-SYS-256/q16" (DESIGN.md "Resampler").
 // ---------------------------------------------------------------------------------------
-constexpr int kBlk = 256;
-
 struct ResamplePlan {
   int64_t n = 0, nblk = 0;
-  std::vector<int32_t> nexp;   // per particle exponent
-  std::vector<uint32_t> mant;  // per particle mantissa
-  std::vector<int32_t> eb;     // per block exponent
-  std::vector<uint64_t> sb;    // per block sum at block scale
-  std::vector<uint64_t> pb;    // per block exclusive prefix at global scale (nblk+1 entries)
+  std::vector<uint16_t> q;     // per particle 16-bit weight at its block's scale 2^(n_b - 15)
+  std::vector<float> w;        // per particle weight relative to 2^n_b
+  std::vector<int32_t> eb;     // per block exponent n_b (kNZero: empty)
+  std::vector<uint32_t> sb;    // per block sum of q
+  std::vector<uint64_t> pb;    // per block exclusive prefix at the global scale 2^(E - 31) (nblk+1 entries)
   int32_t emax = kNZero;
   uint64_t total = 0;
-  uint64_t rho = 0;  // floor(N_out * 2^(32+L) / T) + 1
-  int L = 0;         // bit length of T
+  uint64_t rho = 0;   // floor(N_out * 2^(32+L) / T) + 1
+  int L = 0;          // bit length of T
+  uint32_t Mq = 0;    // 30-bit slope multiplier, floor(rho / 2^lam) + 1
+  int h0 = 0;         // L - kGuard - lam: a block at exponent distance ksh shifts by h0 + ksh
 };
 
 inline int bitlen64(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
 
-inline uint32_t q_at(uint32_t m, int32_t n, int32_t eb) {
-  if (m == 0) return 0;
-  int64_t sh = (int64_t)eb - (int64_t)n;
-  return sh < 32 ? (m >> sh) : 0u;
+// block sum at the global scale: s * 2^(kGuard - ksh), truncated
+inline uint64_t shift_guard(uint64_t s, int64_t ksh) {
+  if (ksh <= kGuard) return s << (kGuard - ksh);
+  const int64_t sh = ksh - kGuard;
+  return sh >= 64 ? 0 : (s >> sh);
 }
 
 // returns false when every weight is zero (degenerate)
 bool build_plan(const float* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
   pl->n = n;
   pl->nblk = (n + kBlk - 1) / kBlk;
-  pl->nexp.resize(n); pl->mant.resize(n);
+  pl->q.assign(n, 0); pl->w.assign(n, 0.0f);
   pl->eb.assign(pl->nblk, kNZero); pl->sb.assign(pl->nblk, 0); pl->pb.assign(pl->nblk + 1, 0);
-  for (int64_t i = 0; i < n; ++i) weight_split(lw[i], &pl->nexp[i], &pl->mant[i]);
   pl->emax = kNZero;
   for (int64_t b = 0; b < pl->nblk; ++b) {
-    int32_t e = kNZero;
-    int64_t hi = std::min(n, (b + 1) * kBlk);
-    for (int64_t i = b * kBlk; i < hi; ++i) if (pl->mant[i]) e = std::max(e, pl->nexp[i]);
-    uint64_t s = 0;
-    for (int64_t i = b * kBlk; i < hi; ++i) s += q_at(pl->mant[i], pl->nexp[i], e);
-    pl->eb[b] = e; pl->sb[b] = s;
-    pl->emax = std::max(pl->emax, e);
+    const int64_t hi = std::min(n, (b + 1) * kBlk);
+    float mx = -INFINITY;
+    for (int64_t i = b * kBlk; i < hi; ++i) mx = fmaxf(mx, sanitize_lw(lw[i]));
+    const int32_t nb = block_exponent(mx);
+    pl->eb[b] = nb;
+    if (nb == kNZero) continue;
+    uint32_t s = 0;
+    for (int64_t i = b * kBlk; i < hi; ++i) {
+      uint32_t qi; float wi;
+      weight_q(sanitize_lw(lw[i]), (float)nb, &wi, &qi);
+      pl->q[i] = (uint16_t)qi; pl->w[i] = wi;
+      s += qi;
+    }
+    pl->sb[b] = s;
+    pl->emax = std::max(pl->emax, nb);
   }
   if (pl->emax == kNZero) return false;
   uint64_t run = 0;
   for (int64_t b = 0; b < pl->nblk; ++b) {
     pl->pb[b] = run;
-    int64_t k = (int64_t)pl->emax - (int64_t)pl->eb[b];
-    run += (pl->eb[b] == kNZero || k >= 64) ? 0 : (pl->sb[b] >> k);
+    if (pl->eb[b] != kNZero) run += shift_guard(pl->sb[b], (int64_t)pl->emax - pl->eb[b]);
   }
   pl->pb[pl->nblk] = run;
   pl->total = run;
   if (run == 0) return false;
-  int L = bitlen64(run);
+  const int L = bitlen64(run);
   pl->L = L;
   pl->rho = (uint64_t)((((u128)(uint64_t)n_out) << (32 + L)) / run) + 1;
+  const int lam = bitlen64(pl->rho) - 30;
+  pl->Mq = (uint32_t)(pl->rho >> lam) + 1u;
+  pl->h0 = L - kGuard - lam;
   return true;
 }
 
@@ -327,26 +331,47 @@ inline uint64_t pos_of(const ResamplePlan& pl, uint64_t C) {
   return (uint64_t)(((u128)(C << (64 - pl.L)) * pl.rho) >> 64);
 }
 
-// number of output slots whose threshold j * 2^32 + U lies below pos(C)
+// threshold-shifted position of a block boundary: its high word is the number of output slots
+// whose threshold j * 2^32 + U lies below pos(C)
+inline uint64_t block_pos(const ResamplePlan& pl, uint64_t C, uint32_t U) { return pos_of(pl, C) + (0xFFFFFFFFull - U); }
+
 inline int64_t slot_end(const ResamplePlan& pl, uint64_t C, uint32_t U, int64_t n_out) {
-  uint64_t o = (pos_of(pl, C) + (0xFFFFFFFFull - U)) >> 32;
-  return (int64_t)std::min<uint64_t>(o, (uint64_t)n_out);
+  return (int64_t)std::min<uint64_t>(block_pos(pl, C, U) >> 32, (uint64_t)n_out);
+}
+
+// Slots between the end of a particle's children and the end of its block's children, negated:
+// floor((A * 2^h - r * M) / 2^(h+32)), r = block mass AFTER the particle, A = low word of the
+// block-end position, M / 2^h = slots (in 2^-32 units) per unit of block-scale weight.
+inline int64_t end_delta(uint64_t r, uint32_t M, uint64_t A, int64_t h) {
+  const u128 rm = (u128)r * M;
+  if (h >= 0) {
+    u128 t;  // ceil(r * M / 2^h)
+    if (h >= 100) t = rm ? 1 : 0;
+    else t = (rm + (((u128)1) << h) - 1) >> h;
+    const __int128 num = (__int128)A - (__int128)t;
+    return (int64_t)(num >> 32);  // arithmetic shift: floor
+  }
+  const __int128 num = (__int128)A - (__int128)(rm << (-h));
+  return (int64_t)(num >> 32);
 }
 
 // ancestors of output slots [0, n_out); parent indices refer to [0, n)
 void systematic_ancestors(const ResamplePlan& pl, uint32_t U, int64_t n_out, int32_t* anc) {
   int64_t prev = 0;
   for (int64_t b = 0; b < pl.nblk; ++b) {
-    if (pl.eb[b] == kNZero) continue;
-    int64_t k = (int64_t)pl.emax - (int64_t)pl.eb[b];
+    const uint64_t X0 = block_pos(pl, pl.pb[b], U), X1 = block_pos(pl, pl.pb[b + 1], U);
+    const int64_t o0 = (int64_t)(X0 >> 32), o1 = (int64_t)(X1 >> 32);
+    if (o1 == o0) continue;  // no children (includes every empty block)
+    const int64_t h = (int64_t)pl.h0 + ((int64_t)pl.emax - pl.eb[b]);
+    const uint64_t A = X1 & 0xFFFFFFFFull;
     uint64_t c = 0;
-    int64_t hi = std::min(pl.n, (b + 1) * kBlk);
-    for (int64_t i = b * kBlk; i < hi; ++i) {
-      c += q_at(pl.mant[i], pl.nexp[i], pl.eb[b]);
-      uint64_t C = pl.pb[b] + (k >= 64 ? 0 : (c >> k));
-      int64_t o = slot_end(pl, C, U, n_out);
-      for (int64_t j = prev; j < o; ++j) anc[j] = (int32_t)i;
-      if (o > prev) prev = o;
+    for (int p = 0; p < kBlk; ++p) {
+      const int64_t i = b * kBlk + cdf_offset(p);
+      if (i >= pl.n) continue;  // padding carries no weight
+      c += pl.q[i];
+      const int64_t e = std::max(o1 + end_delta(pl.sb[b] - c, pl.Mq, A, h), o0);
+      for (int64_t j = prev; j < e; ++j) anc[j] = (int32_t)i;
+      if (e > prev) prev = e;
     }
   }
   // by construction prev == n_out (coverage lemma)
@@ -356,15 +381,15 @@ void systematic_ancestors(const ResamplePlan& pl, uint32_t U, int64_t n_out, int
 // multinomial on the same fixed-point CDF: N iid categorical draws (resample2,
 // Inference.hs:57-61), slot j uses the 64-bit uniform of Philox ctr=(j,0,t,"MULT").
 void multinomial_ancestors(const ResamplePlan& pl, uint64_t seed, uint32_t t, int64_t n_out, int32_t* anc) {
-  // full CDF (oracle can afford it)
-  std::vector<uint64_t> cdf(pl.n);
+  // full CDF in CDF order (oracle can afford it): entry (b * 256 + p)
+  std::vector<uint64_t> cdf((size_t)pl.nblk * kBlk);
   for (int64_t b = 0; b < pl.nblk; ++b) {
-    int64_t k = (int64_t)pl.emax - (int64_t)pl.eb[b];
+    const int64_t k = (int64_t)pl.emax - (int64_t)pl.eb[b];
     uint64_t c = 0;
-    int64_t hi = std::min(pl.n, (b + 1) * kBlk);
-    for (int64_t i = b * kBlk; i < hi; ++i) {
-      if (pl.eb[b] != kNZero) c += q_at(pl.mant[i], pl.nexp[i], pl.eb[b]);
-      cdf[i] = pl.pb[b] + ((pl.eb[b] == kNZero || k >= 64) ? 0 : (c >> k));
+    for (int p = 0; p < kBlk; ++p) {
+      const int64_t i = b * kBlk + cdf_offset(p);
+      if (i < pl.n && pl.eb[b] != kNZero) c += pl.q[i];
+      cdf[(size_t)b * kBlk + p] = pl.pb[b] + (pl.eb[b] == kNZero ? 0 : shift_guard(c, k));
     }
   }
   for (int64_t j = 0; j < n_out; ++j) {
@@ -372,8 +397,8 @@ void multinomial_ancestors(const ResamplePlan& pl, uint64_t seed, uint32_t t, in
     philox((uint32_t)j, 0, t, kStreamMulti, seed, r);
     uint64_t u = ((uint64_t)r[0] << 32) | r[1];
     uint64_t tau = (uint64_t)(((u128)u * pl.total) >> 64);  // [0, T)
-    int64_t i = std::upper_bound(cdf.begin(), cdf.end(), tau) - cdf.begin();  // min{i: C_i > tau}
-    anc[j] = (int32_t)i;
+    int64_t pos = std::upper_bound(cdf.begin(), cdf.end(), tau) - cdf.begin();  // min{pos: C > tau}
+    anc[j] = (int32_t)((pos / kBlk) * kBlk + cdf_offset((int)(pos % kBlk)));
   }
 }
 
@@ -393,13 +418,12 @@ struct OFilter {
 };
 
 void summarise(const OFilter& f, const ResamplePlan& pl, pz_step_summary* s, const double* center) {
-  // the same truncated fixed-point weights the resampler uses, at scale 2^(emax-23), in double
+  // the same fp32 weights the resampler quantises, at scale 2^emax, in double
   double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
   for (int64_t i = 0; i < f.n; ++i) {
     const int32_t eb = pl.eb[i / kBlk];
-    const uint32_t q = q_at(pl.mant[i], pl.nexp[i], eb);
-    if (!q) continue;
-    double w = ldexp((double)q, eb - pl.emax);
+    if (eb == kNZero) continue;
+    double w = ldexp((double)pl.w[i], eb - pl.emax);
     sw += w; sw2 += w * w;
     for (int d = 0; d < f.p.nx; ++d) {
       double dx = (double)(f.x[(size_t)d * f.n + i] - (float)center[d]);
@@ -412,7 +436,7 @@ void summarise(const OFilter& f, const ResamplePlan& pl, pz_step_summary* s, con
     s->mean[d] = (double)(float)center[d] + m;
     s->var[d] = sxx[d] / sw - m * m;
   }
-  s->log_evidence_inc = log(sw) + (pl.emax - 23) * M_LN2 - log((double)f.n) + f.p.ll_const;
+  s->log_evidence_inc = log(sw) + pl.emax * M_LN2 - log((double)f.n) + f.p.ll_const;
   s->e_max = pl.emax;
   s->total_weight = pl.total;
   s->n_migrated = 0;
@@ -431,12 +455,18 @@ void pzo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   memcpy(out, c, sizeof(c));
 }
 
-void pzo_weight_split(const float* lw, int64_t n, int32_t* nexp, uint32_t* mant) {
-  for (int64_t i = 0; i < n; ++i) weight_split(lw[i], &nexp[i], &mant[i]);
+// per-block weights of a log-weight vector: q (16-bit fixed point at the block scale), w (fp32,
+// relative to 2^n_b), eb[nblk] (block exponents)
+void pzo_block_weights(const float* lw, int64_t n, uint16_t* q, float* w, int32_t* eb) {
+  ResamplePlan pl;
+  build_plan(lw, n, n, &pl);
+  if (q) memcpy(q, pl.q.data(), n * sizeof(uint16_t));
+  if (w) memcpy(w, pl.w.data(), n * sizeof(float));
+  if (eb) memcpy(eb, pl.eb.data(), pl.nblk * sizeof(int32_t));
 }
 
-void pzo_normal_pairs(const uint32_t* ra, const uint32_t* rb, int64_t n, float* z0, float* z1) {
-  for (int64_t i = 0; i < n; ++i) normal_pair(ra[i], rb[i], &z0[i], &z1[i]);
+void pzo_icdf_normals(const uint32_t* r, int64_t n, float* z) {
+  for (int64_t i = 0; i < n; ++i) z[i] = icdf_normal(r[i]);
 }
 
 uint32_t pzo_resample_uniform(uint64_t seed, uint32_t t) {
@@ -452,7 +482,7 @@ int pzo_resample_systematic(const float* lw, int64_t n, uint32_t U, int32_t* anc
   if (!build_plan(lw, n, n, &pl)) return PZ_EDEGENERATE;
   systematic_ancestors(pl, U, n, anc);
   if (eb_out) memcpy(eb_out, pl.eb.data(), pl.nblk * sizeof(int32_t));
-  if (sb_out) memcpy(sb_out, pl.sb.data(), pl.nblk * sizeof(uint64_t));
+  if (sb_out) for (int64_t b = 0; b < pl.nblk; ++b) sb_out[b] = pl.sb[b];
   if (pb_out) memcpy(pb_out, pl.pb.data(), (pl.nblk + 1) * sizeof(uint64_t));
   if (emax) *emax = pl.emax;
   if (total) *total = pl.total;
@@ -563,7 +593,7 @@ int pzo_filter_block_stats(void* h, int32_t* eb, uint64_t* sb, int32_t* emax, ui
   ResamplePlan pl;
   bool ok = build_plan(f->lw.data(), f->n, f->n, &pl);
   if (eb) memcpy(eb, pl.eb.data(), pl.nblk * sizeof(int32_t));
-  if (sb) memcpy(sb, pl.sb.data(), pl.nblk * sizeof(uint64_t));
+  if (sb) for (int64_t b = 0; b < pl.nblk; ++b) sb[b] = pl.sb[b];
   if (emax) *emax = pl.emax;
   if (total) *total = pl.total;
   return ok ? 0 : PZ_EDEGENERATE;

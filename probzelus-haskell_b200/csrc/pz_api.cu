@@ -117,6 +117,8 @@ int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
 // scratch of the generic (stored log-weight) path
 struct GenericScratch {
   float* lw = nullptr;
+  uint16_t* q16 = nullptr;
+  uint64_t* xb = nullptr;
   int32_t* anc = nullptr;
   int32_t* eb = nullptr;
   uint64_t* sb = nullptr;
@@ -128,7 +130,7 @@ struct GenericScratch {
   CtlDev* ctl = nullptr;
   int64_t cap = 0;  // particles
   void release() {
-    cudaFree(lw); cudaFree(anc); cudaFree(eb); cudaFree(sb); cudaFree(pb); cudaFree(tile_start);
+    cudaFree(lw); cudaFree(q16); cudaFree(xb); cudaFree(anc); cudaFree(eb); cudaFree(sb); cudaFree(pb); cudaFree(tile_start);
     cudaFree(scan_status); cudaFree(scan_part); cudaFree(plan); cudaFree(ctl);
     *this = GenericScratch();
   }
@@ -141,6 +143,9 @@ int generic_alloc(GenericScratch* g, int64_t n, bool full) {
   const int64_t nscan = (nblk + kScanTile - 1) / kScanTile, ntiles = (n + kGenericTileOut - 1) / kGenericTileOut;
   PZ_CUDA(cudaMalloc(&g->lw, ld * sizeof(float)));
   PZ_CUDA(cudaMemset(g->lw, 0, ld * sizeof(float)));
+  PZ_CUDA(cudaMalloc(&g->q16, ld * sizeof(uint16_t)));
+  PZ_CUDA(cudaMemset(g->q16, 0, ld * sizeof(uint16_t)));
+  PZ_CUDA(cudaMalloc(&g->xb, (nblk + 2) * sizeof(uint64_t)));
   PZ_CUDA(cudaMalloc(&g->anc, ld * sizeof(int32_t)));
   PZ_CUDA(cudaMalloc(&g->tile_start, (ntiles + 1) * sizeof(int32_t)));
   if (full) {
@@ -179,8 +184,10 @@ struct pz_filter {
   ncclComm_t comm = nullptr;
   int64_t hb = 0;                    // halo capacity in blocks on each side
   float* xbuf[2] = {nullptr, nullptr};
+  uint16_t* qbuf[2] = {nullptr, nullptr};
   int32_t* ebbuf[2] = {nullptr, nullptr};
   uint64_t* pbxbuf = nullptr;
+  uint64_t* xbbuf = nullptr;
   int32_t* h_table = nullptr;        // pinned [2*world]
   int64_t last_migrated = 0;
   // multi-target tracker
@@ -247,7 +254,7 @@ void free_filter(pz_filter* f) {
   if (f->graph) cudaGraphExecDestroy(f->graph);
   if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
   StepArgs& a = f->a;
-  cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
+  cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->qbuf[0]); cudaFree(f->qbuf[1]); cudaFree(f->xbbuf); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
   cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
   cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec); cudaFree(a.shard_table);
   cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow);
@@ -293,9 +300,11 @@ int pending_ancestors(pz_filter* f, int* launches) {
   int rc = generic_alloc(&f->g, a.n_local, false);
   if (rc) return rc;
   int n = 0;
-  if (!f->is_mtt) n += launch_logw(a, f->g.lw, f->stream);  // the tracker stores its log-weights
   GenericArgs g{};
   g.lw = f->g.lw; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[1]; g.parity_ctl = a.ctl;
+  if (f->is_mtt) { g.q16 = f->g.q16; g.q16_alt = f->g.q16; }  // the tracker stores its log-weights (and their q16)
+  else { g.q16 = a.Q[0]; g.q16_alt = a.Q[1]; }
+  g.xb = f->g.xb;
   g.sb = a.sb; g.pb = a.pb; g.tile_start = f->g.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
   g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk;
   g.ntiles_out = (int32_t)((a.n_local + kGenericTileOut - 1) / kGenericTileOut);
@@ -307,6 +316,7 @@ int pending_ancestors(pz_filter* f, int* launches) {
     StepArgs b = a;
     b.tile_start = f->g.tile_start;
     b.ntiles_out = g.ntiles_out;
+    b.xb = f->g.xb;  // same values as a.xb; kept separate so that the filter's own plan is untouched
     n += launch_partition_only(b, kGenericTileOut, f->stream);
     n += launch_generic_ancestors(g, f->stream);
   }
@@ -353,6 +363,7 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
     return fail(PZ_ECAPACITY, "rank %d needs %lld + %lld halo blocks but the capacity is %lld (set PZ_HALO_BLOCKS)", me,
                 (long long)-ext_lo, (long long)(ext_hi - nb), (long long)f->hb);
   float* x = a.X[which];
+  uint16_t* q = a.Q[which];
   int32_t* eb = a.eb[which];
   uint64_t* pbx = const_cast<uint64_t*>(a.pbx);
   int64_t migrated = 0;
@@ -365,6 +376,7 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
       const int64_t b0 = lo - own0, cnt = hi - lo;
       for (int d = 0; d < a.model.nx; ++d)
         PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld + b0 * kBlk, cnt * kBlk, ncclFloat32, peer, f->comm, s));
+      PZ_NCCL(g_nccl.Send(q + b0 * kBlk, cnt * kBlk * 2, ncclUint8, peer, f->comm, s));
       PZ_NCCL(g_nccl.Send(eb + b0, cnt, ncclInt32, peer, f->comm, s));
       PZ_NCCL(g_nccl.Send(pbx + b0, cnt + 1, ncclUint64, peer, f->comm, s));
     }
@@ -373,6 +385,7 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
       const int64_t b0 = lo - own0, cnt = hi - lo;  // b0 < 0 (left halo) or >= nb (right halo)
       for (int d = 0; d < a.model.nx; ++d)
         PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld + b0 * kBlk, cnt * kBlk, ncclFloat32, peer, f->comm, s));
+      PZ_NCCL(g_nccl.Recv(q + b0 * kBlk, cnt * kBlk * 2, ncclUint8, peer, f->comm, s));
       PZ_NCCL(g_nccl.Recv(eb + b0, cnt, ncclInt32, peer, f->comm, s));
       // a left-halo range ends where my own prefix starts (same value), a right-halo range starts there
       PZ_NCCL(g_nccl.Recv(pbx + b0, cnt + 1, ncclUint64, peer, f->comm, s));
@@ -416,7 +429,8 @@ int enqueue_step(pz_filter* f) {
 GenericArgs mtt_generic(pz_filter* f) {
   StepArgs& a = f->a;
   GenericArgs g{};
-  g.lw = f->g.lw; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[0]; g.parity_ctl = nullptr;
+  g.lw = f->g.lw; g.q16 = f->g.q16; g.q16_alt = f->g.q16; g.xb = a.xb; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[0];
+  g.parity_ctl = nullptr;
   g.sb = a.sb; g.pb = a.pb; g.tile_start = a.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
   g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk; g.ntiles_out = a.ntiles_out; g.nscan = a.nscan;
   g.U = 0; g.seed = a.seed; g.step = f->t;
@@ -469,6 +483,8 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   PZ_TRY(cudaMalloc(&a.sb, (a.nblk + 8) * sizeof(uint64_t)));
   PZ_TRY(cudaMalloc(&a.pb, (a.nblk + 8) * sizeof(uint64_t)));
   a.pbx = a.pb; a.b_lo = 0; a.b_hi = a.nblk;
+  PZ_TRY(cudaMalloc(&f->xbbuf, (a.nblk + 8) * sizeof(uint64_t)));
+  a.xb = f->xbbuf;
   PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
   PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
   PZ_TRY(cudaMemset(a.scan_status, 0, (a.nscan + 1) * sizeof(uint64_t)));
@@ -585,6 +601,9 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
     PZ_TRY(cudaMalloc(&f->xbuf[i], xbytes));
     PZ_TRY(cudaMemset(f->xbuf[i], 0, xbytes));
     a.X[i] = f->xbuf[i] + H;
+    PZ_TRY(cudaMalloc(&f->qbuf[i], (size_t)a.ld * sizeof(uint16_t)));
+    PZ_TRY(cudaMemset(f->qbuf[i], 0, (size_t)a.ld * sizeof(uint16_t)));
+    a.Q[i] = f->qbuf[i] + H;
     PZ_TRY(cudaMalloc(&f->ebbuf[i], (a.nblk + 2 * f->hb + 8) * sizeof(int32_t)));
     a.eb[i] = f->ebbuf[i] + f->hb;
   }
@@ -601,6 +620,8 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   }
   a.b_lo = 0;
   a.b_hi = a.nblk;
+  PZ_TRY(cudaMalloc(&f->xbbuf, (a.nblk + 2 * f->hb + 8) * sizeof(uint64_t)));
+  a.xb = f->xbbuf + f->hb;
   PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
   PZ_TRY(cudaMalloc(&a.rec, (size_t)(a.ntiles_out + 1) * kMaxRec * sizeof(double)));
   PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
@@ -961,7 +982,8 @@ static int standalone(const double* logw, int64_t n, bool multinomial, uint32_t 
   for (int64_t i = 0; i < n; ++i) lw32[i] = (float)logw[i];
   cudaStream_t s = nullptr;
   GenericArgs g{};
-  g.lw = gs.lw; g.anc = gs.anc; g.eb = gs.eb; g.eb_alt = gs.eb; g.parity_ctl = nullptr; g.sb = gs.sb; g.pb = gs.pb;
+  g.lw = gs.lw; g.q16 = gs.q16; g.q16_alt = gs.q16; g.xb = gs.xb; g.anc = gs.anc; g.eb = gs.eb; g.eb_alt = gs.eb;
+  g.parity_ctl = nullptr; g.sb = gs.sb; g.pb = gs.pb;
   g.tile_start = gs.tile_start; g.scan_status = gs.scan_status; g.scan_part = gs.scan_part; g.plan = gs.plan; g.ctl = gs.ctl;
   g.n = n; g.nblk = (n + kBlk - 1) / kBlk;
   g.ntiles_out = (int32_t)((n + kGenericTileOut - 1) / kGenericTileOut);

@@ -3,23 +3,24 @@
 // One time step of zparticles' (haskell/src/Inference.hs:101-104) is three launches:
 //
 //   pf_step_tile<NX,NY,TO,MODE>   per output tile of TO slots:
-//       input side  -- merge-path locate the input blocks whose cumulative weight covers the
-//                      tile, recompute their weights from state + previous observation
-//                      (score/factor/observe, Distributions.hs:29-36,160-161;
-//                      MVDistributions.hs:45-46), warp-scan them in fixed point, and stage
-//                      every parent at the shared-memory slot of its FIRST child (head mark);
-//       output side -- a warp max-scan of the head marks gives every slot its parent
-//                      (resample2 + `fst . (xs !!)`, Inference.hs:57-61, as a systematic
-//                      resampler), then per child: Philox normals, x' = F x + L z
+//       input side  -- from the merge-path entry of the tile, read the 16-bit weights of the input
+//                      blocks whose children reach the tile, warp-scan them, map every particle's
+//                      cumulative weight to its last child slot with one 32x32+64 multiply-add, and
+//                      store the particle's state straight into the shared-memory slots of its
+//                      children (resample2 + `fst . (xs !!)`, Inference.hs:57-61, as a systematic
+//                      resampler; runs longer than 16 children go through a per-CTA queue);
+//       output side -- per child: Philox word -> inverse-CDF normal, x' = F x + L z
 //                      (noisyIntegrateGen Demo.hs:184-187; SingleTargetTracking.hs:34;
-//                      MultiTargetTracking.hs:56-67), the new log-weight, 128-bit coalesced
-//                      stores of the state, the block statistics (max exponent, fixed-point
-//                      sum) and the centred moment sums of the new population (average /
-//                      weightedAverage, Util/Numeric.hs:7-22).
+//                      MultiTargetTracking.hs:56-67), the new log-weight (score/factor/observe,
+//                      Distributions.hs:29-36,160-161; MVDistributions.hs:45-46), its block
+//                      statistics (max exponent, 16-bit weights, their sum), 128-bit coalesced
+//                      stores of the state and 64-bit stores of the weights, and the centred moment
+//                      sums of the new population (average / weightedAverage, Util/Numeric.hs:7-22).
 //   pf_scan_blocks     decoupled look-back exclusive scan of the block sums rescaled to the
 //       global exponent (normalize / shiftByMax, Inference.hs:63-66, Util/Numeric.hs:12-17),
 //       and, in the last CTA, the resampling plan and the posterior summary.
-//   pf_partition       merge-path split: first input block of every output tile.
+//   pf_partition       merge-path split (first input block of every output tile) and the slot
+//       position of every block boundary.
 //
 // No tensor cores: the path is a streaming scan / gather; see DESIGN.md for the roofline.
 #include <cstdlib>
@@ -72,15 +73,17 @@ __device__ __forceinline__ uint32_t warp_inclusive_max_u32(uint32_t v, int lane)
   }
   return v;
 }
+// 2^k as a float for k <= 0 (0 when it would underflow)
+__device__ __forceinline__ float exp2i(int k) { return k < -126 ? 0.0f : __int_as_float((127 + k) << 23); }
 // 2^k as a double (0 when it would underflow)
 __device__ __forceinline__ double pow2d(int k) {
   if (k < -1022) return 0.0;
   return __hiloint2double((1023 + k) << 20, 0);
 }
 
-// Output-slot position of a CDF value (DESIGN.md "Resampler"):
-//   pos(C) = floor(C * rho / 2^L)                 in units of 2^-32 slots, pos(T) = N * 2^32
-//   slot_end(C) = #{ j : j * 2^32 + U < pos(C) }  = hi32(pos + 2^32 - 1 - U)
+// Slot map of the block boundaries (DESIGN.md "Resampler"):
+//   pos(C)      = floor(C * rho / 2^L)            in units of 2^-32 slots, pos(T) = N * 2^32
+//   block_pos(C) = pos(C) + 2^32 - 1 - U          its high word = #{ j : j * 2^32 + U < pos(C) }
 struct SlotMap {
   u64 rho;
   u64 kadd;      // 0xFFFFFFFF - U
@@ -88,11 +91,31 @@ struct SlotMap {
   uint32_t n_out;
   __device__ __forceinline__ SlotMap(const PlanDev* pl, int64_t n_global)
       : rho(pl->rho), kadd(0xFFFFFFFFull - pl->U), lsh(64 - pl->L), n_out((uint32_t)n_global) {}
-  __device__ __forceinline__ uint32_t slot_end(u64 C) const {
-    const u64 pos = __umul64hi(C << lsh, rho);
-    return min((uint32_t)((pos + kadd) >> 32), n_out);
-  }
+  __device__ __forceinline__ u64 block_pos(u64 C) const { return __umul64hi(C << lsh, rho) + kadd; }
+  __device__ __forceinline__ uint32_t slot_end(u64 C) const { return min((uint32_t)(block_pos(C) >> 32), n_out); }
 };
+
+// Slots between the end of a particle's children and the end of its block's children, negated:
+// floor((A * 2^h - r * M) / 2^(h+32)); r = block mass after the particle, A = low word of the
+// block-end position, M / 2^h = 2^-32-slots per unit of block-scale weight.  Generic (rare) form
+// for shifts outside [0, 31]; resample_tile inlines the fast form.
+__device__ __noinline__ int32_t end_delta_generic(uint32_t r, uint32_t M, uint32_t A, int h) {
+  const u64 rm = (u64)r * M;
+  long long num;
+  if (h >= 0) {
+    const u64 t = (h >= 64) ? (rm ? 1ull : 0ull) : ((rm + ((1ull << h) - 1ull)) >> h);  // ceil(r M / 2^h)
+    num = (long long)A - (long long)t;
+  } else {
+    num = (long long)A - (long long)(rm << (-h));
+  }
+  return (int32_t)(num >> 32);
+}
+
+__device__ __forceinline__ long long mad_wide_s32(int32_t a, int32_t b, long long c) {
+  long long d;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
 
 // ------------------------------------------------------------------------------------------
 // linear-Gaussian model step (same operation order as the oracle's lg_propagate / lg_logweight)
@@ -172,14 +195,17 @@ __device__ __forceinline__ float model_logweight(const LgDev& p, const float* xn
   if constexpr (KRON) return kron_logweight<NX, NY>(p, xn, y); else return lg_logweight<NX, NY>(p, xn, y);
 }
 
-// normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]
+// normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]; one Philox word per normal
 template <int NX>
-__device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed, float (&z)[NX][4]) {
+__device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed, const float4* __restrict__ tab_m8,
+                                          float (&z)[NX][4]) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   if constexpr (NX == 1) {
-    U4 r = philox4x32_10(j >> 2, 0u, t, kStreamProp, k0, k1);
-    normal_pair(r.x, r.y, z[0][0], z[0][1]);
-    normal_pair(r.z, r.w, z[0][2], z[0][3]);
+    const U4 r = philox4x32_10(j >> 2, 0u, t, kStreamProp, k0, k1);
+    z[0][0] = icdf_normal(r.x, tab_m8);
+    z[0][1] = icdf_normal(r.y, tab_m8);
+    z[0][2] = icdf_normal(r.z, tab_m8);
+    z[0][3] = icdf_normal(r.w, tab_m8);
   } else if constexpr (NX == 6) {
     // two consecutive slots share three Philox calls: even slot words 0..5, odd slot words 6..11
 #pragma unroll
@@ -188,25 +214,23 @@ __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed,
       const U4 r1 = philox4x32_10((j >> 1) + pr, 1u, t, kStreamProp, k0, k1);
       const U4 r2 = philox4x32_10((j >> 1) + pr, 2u, t, kStreamProp, k0, k1);
       const int s = 2 * pr;
-      normal_pair(r0.x, r0.y, z[0][s], z[1][s]);
-      normal_pair(r0.z, r0.w, z[2][s], z[3][s]);
-      normal_pair(r1.x, r1.y, z[4][s], z[5][s]);
-      normal_pair(r1.z, r1.w, z[0][s + 1], z[1][s + 1]);
-      normal_pair(r2.x, r2.y, z[2][s + 1], z[3][s + 1]);
-      normal_pair(r2.z, r2.w, z[4][s + 1], z[5][s + 1]);
+      z[0][s] = icdf_normal(r0.x, tab_m8); z[1][s] = icdf_normal(r0.y, tab_m8);
+      z[2][s] = icdf_normal(r0.z, tab_m8); z[3][s] = icdf_normal(r0.w, tab_m8);
+      z[4][s] = icdf_normal(r1.x, tab_m8); z[5][s] = icdf_normal(r1.y, tab_m8);
+      z[0][s + 1] = icdf_normal(r1.z, tab_m8); z[1][s + 1] = icdf_normal(r1.w, tab_m8);
+      z[2][s + 1] = icdf_normal(r2.x, tab_m8); z[3][s + 1] = icdf_normal(r2.y, tab_m8);
+      z[4][s + 1] = icdf_normal(r2.z, tab_m8); z[5][s + 1] = icdf_normal(r2.w, tab_m8);
     }
   } else {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
 #pragma unroll
       for (int c = 0; 4 * c < NX; ++c) {
-        U4 r = philox4x32_10(j + s, (uint32_t)c, t, kStreamProp, k0, k1);
-        float zz[4];
-        normal_pair(r.x, r.y, zz[0], zz[1]);
-        normal_pair(r.z, r.w, zz[2], zz[3]);
+        const U4 r = philox4x32_10(j + s, (uint32_t)c, t, kStreamProp, k0, k1);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (4 * c + i < NX) z[4 * c + i][s] = zz[i];
+          if (4 * c + i < NX) z[4 * c + i][s] = icdf_normal(w[i], tab_m8);
       }
     }
   }
@@ -214,6 +238,7 @@ __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed,
 
 // ------------------------------------------------------------------------------------------
 // pf_init: the point-mass population before the first observation, with equal weights
+// (lw = 0 for every particle: n_b = 0, w = 1, q = 2^15)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -222,13 +247,15 @@ __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
       a.X[0][(size_t)d * a.ld + i] = a.model.x0[d];
       a.X[1][(size_t)d * a.ld + i] = a.model.x0[d];
     }
+    a.Q[0][i] = i < a.n_local ? (uint16_t)32768 : (uint16_t)0;
+    a.Q[1][i] = 0;
   }
   if (i < a.nblk) {
     int64_t cnt = a.n_local - i * kBlk;
     cnt = cnt > kBlk ? kBlk : cnt;
     a.eb[0][i] = 0;
     a.eb[1][i] = kNZero;
-    a.sb[i] = (u64)cnt << 23;  // q of lw = 0 is 2^23
+    a.sb[i] = (u64)cnt << 15;
   }
   if (i < a.nscan) a.scan_status[i] = 0ull;
   if (i == 0) {
@@ -236,7 +263,6 @@ __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
     a.ctl->emax_acc = 0;
     a.ctl->scan_counter = 0;
     a.ctl->scan_done = 0;
-    a.ctl->uniform_in = 1;
     for (int d = 0; d < 8; ++d) a.plan->center[d] = d < a.model.nx ? a.model.x0[d] : 0.0f;
   }
 }
@@ -281,9 +307,14 @@ __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint
     const int L = 64 - __clzll((long long)total);
     pl->L = L;
     pl->rho = (u64)((((unsigned __int128)(u64)n_out_global) << (32 + L)) / total) + 1ull;
+    const int lam = (64 - __clzll((long long)pl->rho)) - 30;
+    pl->Mq = (uint32_t)(pl->rho >> lam) + 1u;
+    pl->h0 = L - kGuard - lam;
   } else {
     pl->L = 1;
     pl->rho = 0;
+    pl->Mq = 0;
+    pl->h0 = 0;
   }
 }
 
@@ -300,7 +331,7 @@ __device__ void write_summary(PlanDev* pl, pz_step_summary* o, uint32_t t, int n
   if (o) {
     for (int d = nx; d < PZ_MAX_NX; ++d) { o->mean[d] = 0.0; o->var[d] = 0.0; }
     o->step = t;
-    o->log_evidence_inc = log(sw) + (double)(pl->emax - 23) * 0.6931471805599453 - log((double)n_out_global) + ll_const;
+    o->log_evidence_inc = log(sw) + (double)pl->emax * 0.6931471805599453 - log((double)n_out_global) + ll_const;
     o->ess = sw * sw / sw2;
     o->n_migrated = 0;
     o->e_max = pl->emax;
@@ -332,10 +363,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
     u64 S = 0;
     if (b < s.nblk) {
       int32_t e = ebp[b];
-      if (e != kNZero) {
-        uint32_t sh = (uint32_t)(emax - e);
-        S = sh < 64u ? (s.sb[b] >> sh) : 0ull;
-      }
+      if (e != kNZero) S = shift_guard(s.sb[b], emax - e);
     }
     v[k] = S;
     tsum += S;
@@ -471,10 +499,12 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// pf_partition: first input block of every output tile + per-step counter maintenance
+// pf_partition: first input block of every output tile, slot position of every block boundary,
+// and the per-step counter maintenance
 // ------------------------------------------------------------------------------------------
 struct PartArgs {
   const u64* pb;      // prefix array searched (absolute on a sharded filter)
+  u64* xb;            // out: block_pos(pb[b]) for b in [b_lo, b_hi]
   int64_t b_lo, b_hi; // block range searched
   int32_t* tile_start;
   u64* status;
@@ -492,8 +522,8 @@ struct PartArgs {
 __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
   const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const PlanDev* pl = p.plan;
+  SlotMap sm(pl, p.n_out_global);
   if (J < p.ntiles_out) {
-    SlotMap sm(pl, p.n_out_global);
     const uint32_t j0 = (uint32_t)(p.slot_base + J * p.tile_out);
     // min b in [b_lo, b_hi) with slot_end(pb[b+1]) > j0
     int64_t lo = p.b_lo, hi = p.b_hi;
@@ -503,158 +533,164 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
     }
     p.tile_start[J] = (int32_t)lo;
   }
+  for (int64_t b = p.b_lo + J; b <= p.b_hi; b += (int64_t)gridDim.x * kThreads) p.xb[b] = sm.block_pos(p.pb[b]);
   if (J < p.nscan) p.status[J] = 0ull;
   if (J == 0) {
     p.ctl->t += (uint32_t)p.delta;
     p.ctl->emax_acc = kNZero;
     p.ctl->scan_counter = 0;
     p.ctl->scan_done = 0;
-    if (p.delta) p.ctl->uniform_in = 0;
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // resample phase shared by the step and the ancestor kernels
 // ------------------------------------------------------------------------------------------
-// Sources: what one particle contributes (its weight) and what is staged for its children.
-template <int NX, int NY, bool KRON>
+// Runs of more than kDirectRun children are filled cooperatively after the input phase.
+constexpr int kDirectRun = 16;
+struct TileQueue {
+  int* n;      // number of queued runs
+  int* lo;     // [cap] first slot (tile relative)
+  int* hi;     // [cap] one past the last slot
+  float* x;    // [NV][cap] payload
+  int cap;     // TO / 16: a queued run has more than 16 slots, so at most TO / 17 runs exist
+};
+
+// Payload sources: what is staged for the children of a particle.
+template <int NX>
 struct StateSource {
-  const float* x;      // X[cur]
-  int64_t ld, n_local;
-  const LgDev* m;
-  float y[NY];
-  bool uniform;
+  static constexpr int NV = NX;
+  const float* x;  // X[cur]
+  int64_t ld;
   float v[NX][4];
-  template <bool FULL>
-  __device__ __forceinline__ void load(int64_t i0, int32_t eb, uint32_t (&q)[4]) {
+  __device__ __forceinline__ void load(int64_t i0) {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
       const float4 f = *reinterpret_cast<const float4*>(x + (size_t)d * ld + i0);
       v[d][0] = f.x; v[d][1] = f.y; v[d][2] = f.z; v[d][3] = f.w;
     }
-    if (uniform) {  // the initial point mass: equal weights (lw = 0 -> n = 0, m = 2^23)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) q[k] = q_at(1u << 23, 0, eb);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        int32_t n; uint32_t mm;
-        float xs[NX];
-#pragma unroll
-        for (int d = 0; d < NX; ++d) xs[d] = v[d][k];
-        weight_split(model_logweight<NX, NY, KRON>(*m, xs, y), n, mm);
-        q[k] = q_at(mm, n, eb);
-      }
-    }
-    if (!FULL) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (i0 + k >= n_local) q[k] = 0;
-    }
   }
-  __device__ __forceinline__ void put(float* s_par, int stride, uint32_t slot, int k, int64_t) const {
+  __device__ __forceinline__ void put(float* s_par, int stride, int slot, int k) const {
 #pragma unroll
     for (int d = 0; d < NX; ++d) s_par[d * stride + slot] = v[d][k];
   }
 };
 
-struct LogwSource {  // generic path: stored log-weights, payload = particle index
-  const float* lw;
-  int64_t n_local;
-  template <bool FULL>
-  __device__ __forceinline__ void load(int64_t i0, int32_t eb, uint32_t (&q)[4]) {
-    const float4 f = *reinterpret_cast<const float4*>(lw + i0);
-    const float w[4] = {f.x, f.y, f.z, f.w};
+struct IndexSource {  // generic path: payload = particle index
+  static constexpr int NV = 1;
+  float v[1][4];
+  __device__ __forceinline__ void load(int64_t i0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int32_t n; uint32_t mm;
-      weight_split(w[k], n, mm);
-      q[k] = q_at(mm, n, eb);
-      if (!FULL && i0 + k >= n_local) q[k] = 0;
-    }
+    for (int k = 0; k < 4; ++k) v[0][k] = __int_as_float((int32_t)i0 + k);
   }
-  __device__ __forceinline__ void put(float* s_par, int, uint32_t slot, int k, int64_t i0) const {
-    reinterpret_cast<int32_t*>(s_par)[slot] = (int32_t)(i0 + k);
-  }
+  __device__ __forceinline__ void put(float* s_par, int, int slot, int k) const { s_par[slot] = v[0][k]; }
 };
 
-// One half-block (128 particles, 4 per lane): fixed-point weights, warp scan, slot ranges, and
-// a head mark at the first child slot of every particle that has children in [j0, jend) -- plus
-// one at every 128-slot segment boundary its children span, so that each output segment can
-// resolve its parents with a warp-local max-scan.
-template <class Source, bool FULL>
-__device__ __forceinline__ void resample_half(Source& src, float* s_par, uint16_t* s_head, int stride, int64_t i0,
-                                              int32_t eb, uint32_t ksh, u64 Pb, const SlotMap& sm, uint32_t j0,
-                                              uint32_t jend, int lane, uint32_t& carry, uint32_t& o_prev) {
-  uint32_t q[4];
-  src.template load<FULL>(i0, eb, q);
-  const uint32_t c0 = q[0], c1 = c0 + q[1], c2 = c1 + q[2], c3 = c2 + q[3];
-  const uint32_t incl = warp_inclusive_scan_u32(c3, lane);
-  const uint32_t excl = carry + incl - c3;
-  carry += __shfl_sync(0xffffffffu, incl, 31);
-  uint32_t o[4];
-  o[0] = sm.slot_end(Pb + (u64)((excl + c0) >> ksh));
-  o[1] = sm.slot_end(Pb + (u64)((excl + c1) >> ksh));
-  o[2] = sm.slot_end(Pb + (u64)((excl + c2) >> ksh));
-  o[3] = sm.slot_end(Pb + (u64)((excl + c3) >> ksh));
-  uint32_t o_lo = __shfl_up_sync(0xffffffffu, o[3], 1);
-  if (lane == 0) o_lo = o_prev;
-  o_prev = __shfl_sync(0xffffffffu, o[3], 31);
+template <class Source>
+__device__ __forceinline__ void emit_children(const Source& src, float* s_par, int stride, const TileQueue& tq, int lo,
+                                              int hi, int k) {
+  if (hi > lo) {
+    src.put(s_par, stride, lo, k);
+    if (hi > lo + 1) {
+      src.put(s_par, stride, lo + 1, k);
+      if (hi > lo + 2) {  // rare: three or more children
+        const int stop = min(hi, lo + kDirectRun);
+        for (int s = lo + 2; s < stop; ++s) src.put(s_par, stride, s, k);
+        if (hi > stop) {
+          const int idx = atomicAdd(tq.n, 1);
+          tq.lo[idx] = stop;
+          tq.hi[idx] = hi;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t lo = max(o_lo, j0), hi = min(o[k], jend);
-    if (lo < hi) {
-      uint32_t slot = lo - j0;
-      const uint32_t slot_last = hi - j0 - 1u;
-      s_head[slot] = (uint16_t)(slot + 1);
-      src.put(s_par, stride, slot, k, i0);
-      if ((slot ^ slot_last) >> 7) {  // rare: the children span a segment boundary
-        for (slot = (slot + 128u) & ~127u; slot <= slot_last; slot += 128u) {
-          s_head[slot] = (uint16_t)(slot + 1);
-          src.put(s_par, stride, slot, k, i0);
+          for (int d = 0; d < Source::NV; ++d) tq.x[d * tq.cap + idx] = src.v[d][k];
         }
       }
     }
-    o_lo = o[k];
   }
 }
 
+// Input side of one output tile [j0, j0 + nslots): every warp takes input blocks b_first + warp,
+// + 8, ...  A lane owns 8 particles of the block -- memory offsets lane*4 + {0..3} and
+// 128 + lane*4 + {0..3} -- which are 8 CONSECUTIVE positions of the block's CDF order (the spec's
+// order: lane-major, so that one 32-bit warp scan of the lane totals suffices).  With r = the
+// block mass after a particle, the particle's children end at
+//     e = max(o1 + floor((A * 2^h - r * M) / 2^(h+32)), o0)
+// (o0 / o1: first / end slot of the block's children, A: fractional slot position of the block
+// end): one mad.wide.s32 and one arithmetic shift per particle.  Measuring from the block END
+// makes zero-weight particles childless by construction and the last weight reach o1 exactly.
 template <class Source>
-__device__ __forceinline__ void resample_tile(Source& src, float* s_par, uint16_t* s_head, int stride,
-                                              const int32_t* __restrict__ ebx, const u64* __restrict__ pbx, u64 base,
-                                              int64_t b_first, int64_t b_end, int64_t n_items, const SlotMap& sm,
-                                              int32_t emax, uint32_t j0, uint32_t jend, int lane, int warp) {
+__device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const TileQueue& tq,
+                                              const uint16_t* __restrict__ qin, const int32_t* __restrict__ ebx,
+                                              const u64* __restrict__ xb, int64_t b_first, int64_t b_end, int32_t emax,
+                                              int32_t h0, uint32_t Mq, uint32_t j0, int nslots, int lane, int warp) {
+  const uint32_t jend = j0 + (uint32_t)nslots;
   for (int64_t b = b_first + warp; b < b_end; b += kWarps) {
-    const u64 Pb = base + pbx[b];
-    uint32_t o_prev = sm.slot_end(Pb);
-    if (o_prev >= jend) break;  // this and every later block start past the tile
-    const int32_t eb = ebx[b];
-    const uint32_t ksh = (uint32_t)(emax - eb);
-    if (eb == kNZero || ksh >= 32u) continue;  // no mass at the global scale
-    uint32_t carry = 0;
-    const int64_t i0 = b * kBlk + lane * 4;
-    if ((b + 1) * kBlk <= n_items) {
-      resample_half<Source, true>(src, s_par, s_head, stride, i0, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
-      resample_half<Source, true>(src, s_par, s_head, stride, i0 + 128, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
+    const u64 X0 = xb[b], X1 = xb[b + 1];
+    const uint32_t o0 = (uint32_t)(X0 >> 32), o1 = (uint32_t)(X1 >> 32);
+    if (o0 >= jend) break;                  // this and every later block start past the tile
+    if (o1 == o0 || o1 <= j0) continue;     // no children (every empty block), or none in this tile
+    const int h = h0 + (emax - ebx[b]);
+    const int64_t ia = b * kBlk + lane * 4;
+    const uint2 qa = *reinterpret_cast<const uint2*>(qin + ia);
+    const uint2 qb = *reinterpret_cast<const uint2*>(qin + ia + 128);
+    uint32_t c[8];
+    c[0] = qa.x & 0xffffu;
+    c[1] = c[0] + (qa.x >> 16);
+    c[2] = c[1] + (qa.y & 0xffffu);
+    c[3] = c[2] + (qa.y >> 16);
+    c[4] = c[3] + (qb.x & 0xffffu);
+    c[5] = c[4] + (qb.x >> 16);
+    c[6] = c[5] + (qb.y & 0xffffu);
+    c[7] = c[6] + (qb.y >> 16);
+    const uint32_t incl = warp_inclusive_scan_u32(c[7], lane);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t rbase = total - (incl - c[7]);  // block mass from this lane's first particle on
+    const int32_t o0r = (int32_t)(o0 - j0), o1r = (int32_t)(o1 - j0);
+    const uint32_t A = (uint32_t)X1;
+    int32_t e[8];
+    if ((unsigned)h <= 31u) {
+      const long long Ah = (long long)((u64)A << h);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long res = mad_wide_s32(-(int32_t)(rbase - c[k]), (int32_t)Mq, Ah);
+        e[k] = max(o1r + ((int32_t)(res >> 32) >> h), o0r);
+      }
     } else {
-      resample_half<Source, false>(src, s_par, s_head, stride, i0, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
-      resample_half<Source, false>(src, s_par, s_head, stride, i0 + 128, eb, ksh, Pb, sm, j0, jend, lane, carry, o_prev);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = max(o1r + end_delta_generic(rbase - c[k], Mq, A, h), o0r);
+    }
+    int32_t eprev = __shfl_up_sync(0xffffffffu, e[7], 1);
+    if (lane == 0) eprev = o0r;
+    if (o0r < 0 || o1r > nslots) {  // the block's children straddle a tile edge: clip
+      eprev = min(max(eprev, 0), nslots);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
+    }
+    if (e[3] > eprev) {
+      src.load(ia);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { emit_children(src, s_par, stride, tq, eprev, e[k], k); eprev = e[k]; }
+    }
+    if (e[7] > e[3]) {
+      src.load(ia + 128);
+      eprev = e[3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { emit_children(src, s_par, stride, tq, eprev, e[4 + k], k); eprev = e[4 + k]; }
     }
   }
 }
 
-// Parent slot (+1) of the lane's 4 slots of one 128-slot segment.
-__device__ __forceinline__ void segment_parents(const uint16_t* s_head, int sl, int lane, uint32_t (&h)[4]) {
-  const uint2 hv = *reinterpret_cast<const uint2*>(&s_head[sl]);
-  h[0] = hv.x & 0xffffu;
-  h[1] = max(h[0], hv.x >> 16);
-  h[2] = max(h[1], hv.y & 0xffffu);
-  h[3] = max(h[2], hv.y >> 16);
-  const uint32_t incl = warp_inclusive_max_u32(h[3], lane);
-  uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) excl = 0;
+// Cooperative fill of the queued long runs (after a __syncthreads; followed by one).
+template <int NV>
+__device__ __forceinline__ void drain_queue(float* s_par, int stride, const TileQueue& tq, int tid) {
+  const int nq = *tq.n;
+  for (int e = 0; e < nq; ++e) {
+    const int lo = tq.lo[e], hi = tq.hi[e];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) h[k] = max(h[k], excl);
+    for (int d = 0; d < NV; ++d) {
+      const float xv = tq.x[d * tq.cap + e];
+      for (int s = lo + tid; s < hi; s += kThreads) s_par[d * stride + s] = xv;
+    }
+  }
 }
 
 struct TileArgs {
@@ -666,57 +702,66 @@ struct TileArgs {
 // MODE 1: parents gathered through a stored ancestor array (multinomial / debug path)
 // resident CTAs per SM the register allocation is held to (NX = 1 / 4 / 6)
 constexpr int min_ctas(int nx) { return nx == 1 ? 4 : (nx <= 4 ? 3 : 2); }
+#define PZ_NACC(nx) (2 + 2 * (nx))
 
 template <int NX, int NY, int TO, int MODE, bool KRON>
 __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __grid_constant__ TileArgs ta) {
-  extern __shared__ __align__(16) float s_par[];  // [NX][TO] parents, then [TO] head marks (u16)
+  extern __shared__ __align__(16) float s_par[];  // [NX][TO] parents | [256] float4 table | queue
   __shared__ int32_t s_eref[kWarps];
   __shared__ double s_red[kWarps][kMaxRec];
-  uint16_t* s_head = reinterpret_cast<uint16_t*>(s_par + NX * TO);
+  __shared__ int s_qn;
+  constexpr int QCAP = TO / 16;
+  float4* s_tab = reinterpret_cast<float4*>(s_par + NX * TO);
+  int* s_qlo = reinterpret_cast<int*>(s_tab + PZ_ICDF_ROWS);
+  int* s_qhi = s_qlo + QCAP;
+  float* s_qx = reinterpret_cast<float*>(s_qhi + QCAP);
   const StepArgs& a = ta.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t t = a.ctl->t;
   const int cur = t & 1, nxt = cur ^ 1;
   const float* __restrict__ xin = a.X[cur];
   float* __restrict__ xout = a.X[nxt];
+  uint16_t* __restrict__ qout = a.Q[nxt];
   const PlanDev* pl = a.plan;
   const int64_t j0l = (int64_t)blockIdx.x * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
-  const uint32_t j0 = (uint32_t)(a.slot_base + j0l), jend = (uint32_t)(a.slot_base + jendl);
+  const uint32_t j0 = (uint32_t)(a.slot_base + j0l);
   const int nslots = (int)(jendl - j0l);
 
   float y_new[NY];
 #pragma unroll
   for (int k = 0; k < NY; ++k) y_new[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
 
+  s_tab[tid] = g_icdf_tab[tid];  // kThreads == PZ_ICDF_ROWS
+  if (tid == 0) s_qn = 0;
+  __syncthreads();
+
   if constexpr (MODE == 0) {
-    {  // clear the head marks: TO u16 = TO/8 uint4
-      uint4* hz = reinterpret_cast<uint4*>(s_head);
-      for (int i = tid; i < TO / 8; i += kThreads) hz[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    const TileQueue tq{&s_qn, s_qlo, s_qhi, s_qx, QCAP};
+    StateSource<NX> src;
+    src.x = xin; src.ld = a.ld;
+    resample_tile(src, s_par, TO, tq, a.Q[cur], a.eb[cur], a.xb, (int64_t)a.tile_start[blockIdx.x], a.b_hi, pl->emax,
+                  pl->h0, pl->Mq, j0, nslots, lane, warp);
     __syncthreads();
-    SlotMap sm(pl, a.n_global);
-    StateSource<NX, NY, KRON> src;
-    src.x = xin; src.ld = a.ld; src.n_local = a.n_local; src.m = &a.model;
-    src.uniform = a.ctl->uniform_in != 0;
-    const uint32_t tp = (t + kObsRing - 1) % kObsRing;
-#pragma unroll
-    for (int k = 0; k < NY; ++k) src.y[k] = a.obs[(size_t)tp * PZ_MAX_NY + k];
-    resample_tile(src, s_par, s_head, TO, a.eb[cur], a.pbx, 0ull, (int64_t)a.tile_start[blockIdx.x], a.b_hi,
-                  a.world > 1 ? INT64_MAX : a.n_local, sm, pl->emax, j0, jend, lane, warp);
+    if (s_qn != 0) {
+      drain_queue<NX>(s_par, TO, tq, tid);
+      __syncthreads();
+    }
   } else {
     for (int sidx = tid; sidx < nslots; sidx += kThreads) {
       const int64_t p = ta.anc[j0l + sidx];
 #pragma unroll
       for (int d = 0; d < NX; ++d) s_par[d * TO + sidx] = xin[(size_t)d * a.ld + p];
     }
+    __syncthreads();
   }
-  __syncthreads();
 
-  // ---- output side: one warp owns one canonical output block (two segments of 128 slots)
-  double acc_sw = 0, acc_sw2 = 0, acc_sx[NX], acc_sxx[NX];
+  // ---- output side: one warp owns one canonical output block; a lane owns slots
+  //      lane*4 + {0..3} and 128 + lane*4 + {0..3} of it
+  const float4* tab_m8 = s_tab - 8;
+  float acc[PZ_NACC(NX)];  // sw, sw2, sx[NX], sxx[NX] at scale 2^aref (fp32 per lane)
 #pragma unroll
-  for (int d = 0; d < NX; ++d) { acc_sx[d] = 0; acc_sxx[d] = 0; }
+  for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0.0f;
   int32_t aref = kNZero;
   float cen[NX];
 #pragma unroll
@@ -724,8 +769,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
   const bool full_tile = (nslots == TO);
 
   for (int ob = warp; ob * kBlk < nslots; ob += kWarps) {
-    int32_t nn[8]; uint32_t mm[8];
-    int32_t emx = kNZero;
+    float lw[8];
+    float xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
+    float mx = -INFINITY;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
@@ -735,20 +781,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
         const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
         xp[d][0] = f.x; xp[d][1] = f.y; xp[d][2] = f.z; xp[d][3] = f.w;
       }
-      if constexpr (MODE == 0) {
-        uint32_t h[4];
-        segment_parents(s_head, sl, lane, h);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (h[k] != (uint32_t)(sl + k + 1) && h[k] != 0u) {
-#pragma unroll
-            for (int d = 0; d < NX; ++d) xp[d][k] = s_par[d * TO + h[k] - 1];
-          }
-        }
-        __syncwarp();  // every parent read of this segment precedes the write-back below
-      }
       float z[NX][4];
-      lg_noise4<NX>(j0 + (uint32_t)sl, t, a.seed, z);
+      lg_noise4<NX>(j0 + (uint32_t)sl, t, a.seed, tab_m8, z);
       float xo[NX][4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -758,77 +792,100 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
         model_propagate<NX, KRON>(a.model, xs, zs, xn);
 #pragma unroll
         for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-        weight_split(model_logweight<NX, NY, KRON>(a.model, xn, y_new), nn[half * 4 + k], mm[half * 4 + k]);
+        float l = model_logweight<NX, NY, KRON>(a.model, xn, y_new);
+        if (!full_tile && sl + k >= nslots) l = -INFINITY;  // past the end of the population
+        lw[half * 4 + k] = l;
+        mx = fmaxf(mx, l);
       }
-      if (!full_tile) {  // only the last tile of a population whose size is not a multiple of TO
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (sl + k >= nslots) { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) emx = max(emx, nn[half * 4 + k]);
       if (full_tile || sl < nslots) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
           const float4 f = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
           *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = f;
-          *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = f;
+          if constexpr (NX > 1) *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = f;
         }
+      }
+      if constexpr (NX == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xk[half * 4 + k] = xo[0][k];
       }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, d));
-    // block sum at the block exponent + centred moments (fp32 per lane, fp64 across blocks)
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    int32_t nb;
+    const float nbf = block_exponent(mx, nb);
     uint32_t ssum = 0;
-    if (emx != kNZero) {
-      float p_sw = 0.f, p_sw2 = 0.f, p_sx[NX], p_sxx[NX];
+    if (nb != kNZero) {
+      float p[PZ_NACC(NX)];
 #pragma unroll
-      for (int d = 0; d < NX; ++d) { p_sx[d] = 0.f; p_sxx[d] = 0.f; }
-      __syncwarp();
+      for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0.0f;
+      if constexpr (NX > 1) __syncwarp();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int sl = ob * kBlk + half * 128 + lane * 4;
         float xv[NX][4];
-#pragma unroll
-        for (int d = 0; d < NX; ++d) {
-          const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
-          xv[d][0] = f.x; xv[d][1] = f.y; xv[d][2] = f.z; xv[d][3] = f.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t q = q_at(mm[half * 4 + k], nn[half * 4 + k], emx);
-          ssum += q;
-          const float w = __uint2float_rn(q);  // exact: q < 2^24
-          p_sw = __fadd_rn(p_sw, w);
-          p_sw2 = __fmaf_rn(w, w, p_sw2);
+        if constexpr (NX > 1) {
 #pragma unroll
           for (int d = 0; d < NX; ++d) {
-            // slots past the population's end hold uninitialised staging data (weight 0, but 0 * NaN = NaN)
-            const float dx = (full_tile || sl + k < nslots) ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
+            const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
+            xv[d][0] = f.x; xv[d][1] = f.y; xv[d][2] = f.z; xv[d][3] = f.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xv[0][k] = xk[half * 4 + k];
+        }
+        uint32_t qb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float w;
+          weight_q<false>(lw[half * 4 + k], nbf, w, qb[k]);
+          const bool live = full_tile || sl + k < nslots;
+          if (!live) w = 0.0f;  // (its q is already 0: lw = -inf)
+          ssum += qb[k] & 0xffffu;
+          p[0] = __fadd_rn(p[0], w);
+          p[1] = __fmaf_rn(w, w, p[1]);
+#pragma unroll
+          for (int d = 0; d < NX; ++d) {
+            const float dx = live ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
             const float wd = __fmul_rn(w, dx);
-            p_sx[d] = __fadd_rn(p_sx[d], wd);
-            p_sxx[d] = __fmaf_rn(wd, dx, p_sxx[d]);
+            p[2 + d] = __fadd_rn(p[2 + d], wd);
+            p[2 + NX + d] = __fmaf_rn(wd, dx, p[2 + NX + d]);
           }
         }
+        if (full_tile || sl < nslots)
+          *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(__byte_perm(qb[0], qb[1], 0x5410), __byte_perm(qb[2], qb[3], 0x5410));
       }
-      double f = 1.0;
-      if (aref == kNZero) aref = emx;
-      else if (emx > aref) {
-        const double g = pow2d(aref - emx);
-        acc_sw *= g; acc_sw2 *= g * g;
+      // fold the block's sums (scale 2^nb) into the lane accumulators (scale 2^aref)
+      if (nb == aref) {
 #pragma unroll
-        for (int d = 0; d < NX; ++d) { acc_sx[d] *= g; acc_sxx[d] *= g; }
-        aref = emx;
-      } else f = pow2d(emx - aref);
-      acc_sw += f * (double)p_sw; acc_sw2 += (f * f) * (double)p_sw2;
+        for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = __fadd_rn(acc[r], p[r]);
+      } else if (aref == kNZero) {
 #pragma unroll
-      for (int d = 0; d < NX; ++d) { acc_sx[d] += f * (double)p_sx[d]; acc_sxx[d] += f * (double)p_sxx[d]; }
+        for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = p[r];
+        aref = nb;
+      } else {
+        const int32_t nref = max(aref, nb);
+        const float ga = exp2i(aref - nref), gp = exp2i(nb - nref);
+#pragma unroll
+        for (int r = 0; r < PZ_NACC(NX); ++r) {
+          const float fa = (r == 1) ? __fmul_rn(ga, ga) : ga, fp = (r == 1) ? __fmul_rn(gp, gp) : gp;
+          acc[r] = __fmaf_rn(acc[r], fa, __fmul_rn(p[r], fp));
+        }
+        aref = nref;
+      }
+    } else {
+      // empty block: every weight is zero
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int sl = ob * kBlk + half * 128 + lane * 4;
+        if (full_tile || sl < nslots) *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(0u, 0u);
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
     if (lane == 0) {
       const int64_t bo = (j0l / kBlk) + ob;
-      a.eb[nxt][bo] = emx;
+      a.eb[nxt][bo] = nb;
       a.sb[bo] = (u64)ssum;
     }
   }
@@ -841,19 +898,16 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
   for (int w = 0; w < kWarps; ++w) etile = max(etile, s_eref[w]);
   {
     const double g = (aref == kNZero) ? 0.0 : pow2d(aref - etile);
-    double vals[kMaxRec];
-    vals[0] = 0; vals[1] = acc_sw * g; vals[2] = acc_sw2 * g * g;
 #pragma unroll
-    for (int d = 0; d < NX; ++d) { vals[3 + d] = acc_sx[d] * g; vals[3 + NX + d] = acc_sxx[d] * g; }
-#pragma unroll
-    for (int r = 1; r < 3 + 2 * NX; ++r) {
-      double x = vals[r];
+    for (int r = 0; r < PZ_NACC(NX); ++r) {
+      double x = (double)acc[r] * (r == 1 ? g * g : g);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
-      if (lane == 0) s_red[warp][r] = x;
+      if (lane == 0) s_red[warp][r + 1] = x;
     }
   }
   __syncthreads();
+  // record layout (kMaxRec doubles): [0] exponent, [1] sw, [2] sw2, [3..3+NX) sx, [3+NX..3+2NX) sxx
   if (tid < 3 + 2 * NX) {
     double x = 0;
     if (tid == 0) x = (double)etile;
@@ -864,15 +918,16 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
 }
 
 // ------------------------------------------------------------------------------------------
-// generic path kernels (stored log-weights)
+// generic path kernels (stored log-weights): standalone resamplers, taps, the tracker
 // ------------------------------------------------------------------------------------------
+// One warp per canonical block: block exponent, 16-bit weights, their sum.
 __global__ void __launch_bounds__(kThreads) pf_stats_from_lw(const float* __restrict__ lw, int64_t n, int64_t nblk,
-                                                             int32_t* eb, u64* sb, CtlDev* ctl) {
+                                                             int32_t* eb, u64* sb, uint16_t* q16, CtlDev* ctl) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * kWarps + warp;
   if (b >= nblk) return;
-  int32_t nn[8]; uint32_t mm[8];
-  int32_t emx = kNZero;
+  float l[8];
+  float mx = -INFINITY;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int64_t i0 = b * kBlk + half * 128 + lane * 4;
@@ -880,56 +935,69 @@ __global__ void __launch_bounds__(kThreads) pf_stats_from_lw(const float* __rest
     const float w[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      weight_split(w[k], nn[half * 4 + k], mm[half * 4 + k]);
-      if (i0 + k >= n) { nn[half * 4 + k] = kNZero; mm[half * 4 + k] = 0; }
-      emx = max(emx, nn[half * 4 + k]);
+      l[half * 4 + k] = (i0 + k < n) ? sanitize_lw(w[k]) : -INFINITY;
+      mx = fmaxf(mx, l[half * 4 + k]);
     }
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, d));
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  int32_t nb;
+  const float nbf = block_exponent(mx, nb);
   uint32_t ssum = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) ssum += q_at(mm[k], nn[k], emx);
+  for (int half = 0; half < 2; ++half) {
+    const int64_t i0 = b * kBlk + half * 128 + lane * 4;
+    uint32_t qb[4] = {0u, 0u, 0u, 0u};
+    if (nb != kNZero) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float w;
+        weight_q<true>(l[half * 4 + k], nbf, w, qb[k]);
+        ssum += qb[k] & 0xffffu;
+      }
+    }
+    *reinterpret_cast<uint2*>(&q16[i0]) = make_uint2(__byte_perm(qb[0], qb[1], 0x5410), __byte_perm(qb[2], qb[3], 0x5410));
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
   if (lane == 0) {
-    eb[b] = emx;
-    sb[b] = (emx == kNZero) ? 0ull : (u64)ssum;
-    if (emx != kNZero) atomicMax(&ctl->emax_acc, emx);
+    eb[b] = nb;
+    sb[b] = (u64)ssum;
+    if (nb != kNZero) atomicMax(&ctl->emax_acc, nb);
   }
 }
 
-__device__ __forceinline__ const int32_t* generic_eb(const GenericArgs& g) {
-  return (g.parity_ctl && (g.parity_ctl->t & 1u)) ? g.eb_alt : g.eb;
-}
+__device__ __forceinline__ bool generic_alt(const GenericArgs& g) { return g.parity_ctl && (g.parity_ctl->t & 1u); }
+__device__ __forceinline__ const int32_t* generic_eb(const GenericArgs& g) { return generic_alt(g) ? g.eb_alt : g.eb; }
+__device__ __forceinline__ const uint16_t* generic_q(const GenericArgs& g) { return generic_alt(g) ? g.q16_alt : g.q16; }
 
 __global__ void pf_ctl_reset(CtlDev* ctl) {
-  ctl->t = 0; ctl->emax_acc = kNZero; ctl->scan_counter = 0; ctl->scan_done = 0; ctl->uniform_in = 0;
+  ctl->t = 0; ctl->emax_acc = kNZero; ctl->scan_counter = 0; ctl->scan_done = 0;
 }
 
 template <int TO>
 __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
-  __shared__ __align__(16) int32_t s_anc[TO];
-  __shared__ __align__(16) uint16_t s_head[TO];
+  constexpr int QCAP = TO / 16;
+  __shared__ __align__(16) float s_anc[TO];
+  __shared__ int s_qn, s_qlo[QCAP], s_qhi[QCAP];
+  __shared__ float s_qx[QCAP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PlanDev* pl = g.plan;
   const int64_t j0 = (int64_t)blockIdx.x * TO;
   const int64_t jend = (j0 + TO < g.n) ? j0 + TO : g.n;
-  SlotMap sm(pl, g.n);
-  LogwSource src{g.lw, g.n};
-  for (int sidx = tid; sidx < TO; sidx += kThreads) { s_anc[sidx] = -1; s_head[sidx] = 0; }
+  for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = __int_as_float(-1);
+  if (tid == 0) s_qn = 0;
   __syncthreads();
-  resample_tile(src, reinterpret_cast<float*>(s_anc), s_head, TO, generic_eb(g), g.pb, 0ull,
-                (int64_t)g.tile_start[blockIdx.x], g.nblk, g.n, sm, pl->emax, (uint32_t)j0, (uint32_t)jend, lane, warp);
+  const TileQueue tq{&s_qn, s_qlo, s_qhi, s_qx, QCAP};
+  IndexSource src;
+  resample_tile(src, s_anc, TO, tq, generic_q(g), generic_eb(g), g.xb, (int64_t)g.tile_start[blockIdx.x], g.nblk, pl->emax,
+                pl->h0, pl->Mq, (uint32_t)j0, (int)(jend - j0), lane, warp);
   __syncthreads();
-  for (int seg = warp; seg * 128 < (int)(jend - j0); seg += kWarps) {
-    const int sl = seg * 128 + lane * 4;
-    uint32_t h[4];
-    segment_parents(s_head, sl, lane, h);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (j0 + sl + k < jend) g.anc[j0 + sl + k] = h[k] ? s_anc[h[k] - 1] : -1;
+  if (s_qn != 0) {
+    drain_queue<1>(s_anc, TO, tq, tid);
+    __syncthreads();
   }
+  for (int sidx = tid; sidx < (int)(jend - j0); sidx += kThreads) g.anc[j0 + sidx] = __float_as_int(s_anc[sidx]);
 }
 
 // N iid categorical draws on the canonical fixed-point CDF (resample2, Inference.hs:57-61)
@@ -948,17 +1016,15 @@ __global__ void __launch_bounds__(kThreads) pf_multinomial(const GenericArgs g) 
     if (g.pb[mid] <= tau) lo = mid; else hi = mid;
   }
   const int64_t b = lo;
-  const int32_t eb = generic_eb(g)[b];
-  const uint32_t ksh = (uint32_t)(pl->emax - eb);
+  const int32_t ksh = pl->emax - generic_eb(g)[b];
+  const uint16_t* q = generic_q(g);
   const u64 Pb = g.pb[b];
   u64 c = 0;
-  int64_t i = b * kBlk, iend = (b + 1) * kBlk < g.n ? (b + 1) * kBlk : g.n;
-  int32_t res = (int32_t)(iend - 1);
-  for (; i < iend; ++i) {
-    int32_t n; uint32_t m;
-    weight_split(g.lw[i], n, m);
-    c += q_at(m, n, eb);
-    if (Pb + (c >> ksh) > tau) { res = (int32_t)i; break; }
+  int32_t res = -1;
+  for (int p = 0; p < kBlk; ++p) {  // the block's CDF order
+    const int64_t i = b * kBlk + cdf_offset(p);
+    c += q[i];
+    if (res < 0 && Pb + shift_guard(c, ksh) > tau) res = (int32_t)i;
   }
   g.anc[j] = res;
 }
@@ -968,7 +1034,7 @@ __global__ void __launch_bounds__(kThreads) pf_logw(StepArgs a, float* lw_out) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n_local) return;
   const uint32_t t = a.ctl->t;
-  if (a.ctl->uniform_in) { lw_out[i] = 0.0f; return; }
+  if (t == 0) { lw_out[i] = 0.0f; return; }  // the initial point mass: equal weights
   const float* x = a.X[t & 1];
   const uint32_t tp = (t + kObsRing - 1) % kObsRing;
   float xs[NX], y[NY];
@@ -1090,11 +1156,17 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   return sc;
 }
 
+static int partition_grid(int64_t ntiles, int64_t nscan, int64_t nbound) {
+  int64_t nthreads = ntiles > nscan ? ntiles : nscan;
+  if (nbound > nthreads) nthreads = nbound;  // one block boundary per thread (grid-stride beyond 4096 CTAs)
+  const int g = cdiv(nthreads, kThreads);
+  return g > 4096 ? 4096 : g;
+}
+
 static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
-  PartArgs pa{a.pbx, a.b_lo, a.b_hi, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
+  PartArgs pa{a.pbx, a.xb, a.b_lo, a.b_hi, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
               a.ntiles_out, tile_out, a.nscan, delta};
-  int nthreads = a.ntiles_out > a.nscan ? a.ntiles_out : a.nscan;
-  pf_partition<<<cdiv(nthreads, kThreads), kThreads, 0, s>>>(pa);
+  pf_partition<<<partition_grid(a.ntiles_out, a.nscan, a.b_hi - a.b_lo + 1), kThreads, 0, s>>>(pa);
   return 1;
 }
 
@@ -1115,7 +1187,8 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
 template <int NX, int NY, int TO, int MODE, bool KRON>
 static void launch_tile(const TileArgs& ta, cudaStream_t s) {
   auto kern = pf_step_tile<NX, NY, TO, MODE, KRON>;
-  size_t smem = (size_t)NX * TO * sizeof(float) + (size_t)TO * sizeof(uint16_t);
+  // parents [NX][TO] + inverse-CDF table + long-run queue (lo, hi, payload[NX]) of TO / 16 entries
+  size_t smem = (size_t)NX * TO * sizeof(float) + PZ_ICDF_ROWS * sizeof(float4) + (size_t)(TO / 16) * (2 + NX) * sizeof(int);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1202,7 +1275,7 @@ int launch_ctl_reset(CtlDev* ctl, cudaStream_t s) {
 int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s) {
   int n = 0;
   if (stats_from_lw) {
-    pf_stats_from_lw<<<cdiv(g.nblk, kWarps), kThreads, 0, s>>>(g.lw, g.n, g.nblk, g.eb, g.sb, g.ctl);
+    pf_stats_from_lw<<<cdiv(g.nblk, kWarps), kThreads, 0, s>>>(g.lw, g.n, g.nblk, g.eb, g.sb, g.q16, g.ctl);
     ++n;
   }
   ScanArgs sc{};
@@ -1211,14 +1284,13 @@ int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s
   sc.nscan = g.nscan; sc.nrec = 0; sc.nx = 0; sc.delta = 0; sc.explicit_U = 1; sc.U_value = g.U; sc.seed = g.seed;
   sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr;
   pf_scan_blocks<<<g.nscan, kThreads, 0, s>>>(sc);
-  PartArgs pa{g.pb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
-  int nthreads = g.ntiles_out > g.nscan ? g.ntiles_out : g.nscan;
-  pf_partition<<<cdiv(nthreads, kThreads), kThreads, 0, s>>>(pa);
+  PartArgs pa{g.pb, g.xb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
+  pf_partition<<<partition_grid(g.ntiles_out, g.nscan, g.nblk + 1), kThreads, 0, s>>>(pa);
   return n + 2;
 }
 
 int launch_stats_from_lw(const GenericArgs& g, cudaStream_t s) {
-  pf_stats_from_lw<<<cdiv(g.nblk, kWarps), kThreads, 0, s>>>(g.lw, g.n, g.nblk, g.eb, g.sb, g.ctl);
+  pf_stats_from_lw<<<cdiv(g.nblk, kWarps), kThreads, 0, s>>>(g.lw, g.n, g.nblk, g.eb, g.sb, g.q16, g.ctl);
   return 1;
 }
 

@@ -1,16 +1,18 @@
 // pz_kernels.cuh -- device data structures and kernel entry points of the particle-filter
 // step (one time step of zparticles', haskell/src/Inference.hs:101-104).
 //
-// HBM layout (per device, fp32 structure-of-arrays, all arrays padded to kPad particles):
-//   X[2][NX][ld]    particle state, double-buffered: step t reads X[t&1], writes X[(t+1)&1]
-//   eb[2][nblk]     per canonical block (256 particles): block exponent E_b
-//   sb[nblk]        per block: sum of the fixed-point weights at the block's own scale
+// HBM layout (per device, structure-of-arrays, all arrays padded to kPad particles):
+//   X[2][NX][ld]    fp32 particle state, double-buffered: step t reads X[t&1], writes X[(t+1)&1]
+//   Q[2][ld]        u16 fixed-point weight of every particle at its block's scale 2^(n_b - 15)
+//   eb[2][nblk]     per canonical block (256 particles): block exponent n_b
+//   sb[nblk]        per block: sum of its q
 //   pb[nblk+1]      exclusive prefix of the block sums rescaled to the global exponent
+//   xb[nblk+1]      threshold-shifted slot position of every block boundary (2^-32 slots)
 //   tile_start[]    first input block of every output tile (merge-path partition)
 //   rec[]           per output tile: centred moment partial sums for the posterior summary
-// Log-weights and ancestors are never stored on the fused path: the weight of a particle is
-// recomputed from its state and the observation it was weighted against, and the ancestor
-// gather is staged through shared memory inside the same kernel that propagates the child.
+// Log-weights and ancestors are never stored on the fused path: a particle carries its 16-bit
+// weight (4 bytes of traffic per update instead of ~19 instructions to recompute it), and the
+// ancestor gather is staged through shared memory inside the kernel that propagates the child.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -51,12 +53,14 @@ struct PlanDev {
   uint64_t base;        // CDF offset of this rank's first particle (0 on one GPU)
   uint64_t local_total; // this rank's share of T
   uint64_t rho;         // floor(N * 2^(32+L) / T) + 1: slot position of C is floor(C * rho / 2^L) * 2^-32
+  uint32_t Mq;          // 30-bit slope multiplier floor(rho / 2^lam) + 1, lam = bitlen(rho) - 30
+  int32_t h0;           // L - kGuard - lam: a block at exponent distance ksh uses the shift h0 + ksh
   int32_t L;            // bit length of T
   int32_t emax;         // global block exponent
   int32_t degenerate;   // 1 when T == 0
   uint32_t U;           // the uniform of the resample that will consume this plan
   float center[8];      // fp32 posterior mean: centring constants of the next moment sums
-  double sw, sw2;       // sum w, sum w^2 at scale 2^(emax-23)
+  double sw, sw2;       // sum w, sum w^2 at scale 2^emax
   double sx[PZ_MAX_NX], sxx[PZ_MAX_NX];  // centred first / second moment sums
 };
 
@@ -67,18 +71,19 @@ struct CtlDev {
   int32_t emax_acc;       // atomicMax target of the kernel producing block statistics
   uint32_t scan_counter;  // dynamic tile ids of pf_scan_blocks
   uint32_t scan_done;     // "last CTA" counter of pf_scan_blocks
-  uint32_t uniform_in;    // 1 while the pending population is the initial point mass
-  uint32_t pad[3];
+  uint32_t pad[4];
 };
 
 struct StepArgs {
   float* X[2];
+  uint16_t* Q[2];          // 16-bit weights of the two populations (same halo layout as X)
   int32_t* eb[2];
   uint64_t* sb;
   uint64_t* pb;            // local exclusive prefix of the rescaled block sums [nblk+1]
   const uint64_t* pbx;     // CDF prefix the step kernel reads: == pb on one GPU; on a sharded filter the
                            // ABSOLUTE prefix (rank base added), with halo entries at [-hb, 0) and (nblk, nblk+hb]
-  int64_t b_lo, b_hi;      // valid (halo-extended) block range of pbx / eb / X for the pending resample
+  uint64_t* xb;            // slot positions of the block boundaries [b_lo, b_hi], written by pf_partition
+  int64_t b_lo, b_hi;      // valid (halo-extended) block range of pbx / xb / eb / X / Q for the pending resample
   int32_t* tile_start;
   double* rec;             // [ntiles_out][kMaxRec]
   uint64_t* scan_status;   // [nscan]
@@ -121,7 +126,10 @@ int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_
 
 // Generic (stored log-weight) path: standalone resampler, ancestor taps, visualiser read.
 struct GenericArgs {
-  const float* lw;       // [n]
+  const float* lw;       // [n] stored log-weights (pf_stats_from_lw input) or nullptr
+  uint16_t* q16;         // [n] 16-bit weights: written by pf_stats_from_lw ...
+  const uint16_t* q16_alt;  // ... or, with parity_ctl set, q16 / q16_alt = the filter's buffers 0 / 1
+  uint64_t* xb;          // [nblk+1]
   int32_t* anc;          // [n_out]
   int32_t* eb;           // block exponents (standalone) ...
   int32_t* eb_alt;       // ... or, with parity_ctl set, eb / eb_alt = the filter's buffers 0 / 1
@@ -145,7 +153,7 @@ int launch_ctl_reset(CtlDev* ctl, cudaStream_t s);
 int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s);
 int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s);
 int launch_generic_multinomial(const GenericArgs& g, cudaStream_t s);
-int launch_logw(const StepArgs& a, float* lw_out, cudaStream_t s);  // log-weights of the pending population
+int launch_logw(const StepArgs& a, float* lw_out, cudaStream_t s);  // log-weights of the pending population (parity tap)
 int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, float* out,
                        cudaStream_t s);
 constexpr int kGenericTileOut = 2048;

@@ -1,4 +1,4 @@
-// pz_math.cuh -- device side of the canonical math spec (DESIGN.md "Math" and "RNG").
+// pz_math.cuh -- device side of the canonical math spec (DESIGN.md "Canonical math" and "RNG").
 //
 // Counter-based Philox4x32-10 replaces the reference's sequential MWC256 SamplerIO
 // (monad-bayes Control.Monad.Bayes.Sampler; call sites Inference.hs:30-42): a draw is a pure
@@ -7,11 +7,15 @@
 //
 // Every fp32 operation here is an individually rounded IEEE op (the translation unit is
 // compiled with -fmad=false); fused multiply-adds appear exactly where __fmaf_rn is
-// written.  The CPU oracle carries the same literals and the same operation order, which
-// is what makes whole-filter trajectories bit-comparable.
+// written.  The CPU oracle evaluates the same expressions on the same constants
+// (include/pz_spec_tables.h), which is what makes whole-filter trajectories bit-comparable.
+// No MUFU approximation, conversion or division appears on the hot path: a standard normal is
+// one table row + 3 fmaf, a weight is 5 fmaf + integer exponent arithmetic.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+
+#include "../../include/pz_spec_tables.h"
 
 namespace pz {
 
@@ -43,72 +47,66 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, u
 }
 
 constexpr float kLog2e = 0x1.715476p+0f;
-constexpr float kNeg2Ln2 = -0x1.62e430p+0f;
-constexpr float kHalfPi = 0x1.921fb6p+0f;
+constexpr int32_t kNZero = -(1 << 30);  // exponent marker of an empty block (every weight zero)
+constexpr int kGuard = 16;              // guard bits of the global fixed-point scale
 
-constexpr int32_t kNZero = -(1 << 30);  // exponent marker of a zero weight
+// Inverse normal CDF table (256 rows of 4 coefficients); the step kernel stages it in shared memory.
+static __device__ const float4 g_icdf_tab[PZ_ICDF_ROWS] = PZ_ICDF_TABLE_INIT;
 
-// log-weight -> (n, m): weight = m * 2^(n-23), m in [2^22.5, 2^23.5].
-// -inf / +inf / NaN / out-of-range -> (kNZero, 0).
-__device__ __forceinline__ void weight_split(float lw, int32_t& n, uint32_t& m) {
-  const float e = __fmul_rn(lw, kLog2e);
-  const float r = rintf(e);
-  const float f = __fsub_rn(e, r);
-  float p = 0x1.00c0e6p-16f;
-  p = __fmaf_rn(p, f, 0x1.444004p-13f);
-  p = __fmaf_rn(p, f, 0x1.5d8776p-10f);
-  p = __fmaf_rn(p, f, 0x1.3b2a1cp-7f);
-  p = __fmaf_rn(p, f, 0x1.c6b08ep-5f);
-  p = __fmaf_rn(p, f, 0x1.ebfbe0p-3f);
-  p = __fmaf_rn(p, f, 0x1.62e430p-1f);
+// One 32-bit word -> one N(0,1) draw.  Bit 31 is the sign; v = (r << 1) | 1 is the tail
+// probability u = v * 2^-33; clz(v) selects the dyadic segment, the next 3 bits the sub-segment,
+// the following 23 bits the cubic's argument tf in [1, 2).  tab_m8 = table base - 8 rows (the
+// sub-segment field carries the leading one).
+__device__ __forceinline__ float icdf_normal(uint32_t r, const float4* __restrict__ tab_m8) {
+  const uint32_t v = (r << 1) | 1u;
+  const int k = __clz(v);
+  const uint32_t vn = v << k;
+  const float4 c = tab_m8[(k << PZ_ICDF_SUB_BITS) + (vn >> 28)];
+  const float tf = __uint_as_float(0x3F800000u | ((vn >> 5) & 0x7FFFFFu));
+  const float z = __fmaf_rn(__fmaf_rn(__fmaf_rn(c.w, tf, c.z), tf, c.y), tf, c.x);
+  return __uint_as_float(__float_as_uint(z) ^ (r & 0x80000000u));
+}
+
+// Block exponent n_b (as float and int) from the block's largest log-weight; kNZero when empty.
+__device__ __forceinline__ float block_exponent(float maxlw, int32_t& nb) {
+  if (!(maxlw > -INFINITY)) { nb = kNZero; return 0.0f; }
+  const float e = fminf(fmaxf(__fmul_rn(maxlw, kLog2e), -262144.0f), 262144.0f);
+  const float nbf = rintf(e);
+  nb = __float2int_rn(nbf);
+  return nbf;
+}
+
+// Weight relative to 2^n_b and its fixed-point image: w = 2^d, d = max(lw * log2(e) - n_b, -32);
+// qbits = 0x4B000000 + rint(w * 2^15) (q <= 46990 sits in the low 16 bits).  CLAMP_HI adds the
+// upper clamp of the spec, unreachable when lw <= the block maximum and |n_b| < 2^18 (fused path).
+template <bool CLAMP_HI>
+__device__ __forceinline__ void weight_q(float lw, float nbf, float& w, uint32_t& qbits) {
+  float d = fmaxf(__fmaf_rn(lw, kLog2e, -nbf), -32.0f);
+  if (CLAMP_HI) d = fminf(d, 1.0f);
+  const float t = __fadd_rn(d, 12582912.0f);
+  const float r = __fsub_rn(t, 12582912.0f);
+  const float f = __fsub_rn(d, r);
+  float p = PZ_EXP2_C5;
+  p = __fmaf_rn(p, f, PZ_EXP2_C4);
+  p = __fmaf_rn(p, f, PZ_EXP2_C3);
+  p = __fmaf_rn(p, f, PZ_EXP2_C2);
+  p = __fmaf_rn(p, f, PZ_EXP2_C1);
   p = __fmaf_rn(p, f, 1.0f);
-  const bool ok = fabsf(e) < 1.0e6f;  // false for NaN and +-inf
-  n = ok ? __float2int_rn(r) : kNZero;
-  m = ok ? (uint32_t)__float2int_rn(__fmul_rn(p, 8388608.0f)) : 0u;
+  w = __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+  qbits = __float_as_uint(__fmaf_rn(w, 32768.0f, 8388608.0f));
 }
 
-// fixed-point weight of (n, m) at block exponent eb >= n: m >> (eb - n), 0 once the shift
-// reaches 32 (PTX shr clamps the shift amount, so no compare is needed)
-__device__ __forceinline__ uint32_t q_at(uint32_t m, int32_t n, int32_t eb) {
-  uint32_t q;
-  asm("shr.u32 %0, %1, %2;" : "=r"(q) : "r"(m), "r"((uint32_t)(eb - n)));
-  return q;
+// stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)
+__device__ __forceinline__ float sanitize_lw(float lw) { return (lw == lw && lw < INFINITY) ? lw : -INFINITY; }
+
+// block sum at the global scale: s * 2^(kGuard - ksh), truncated
+__device__ __forceinline__ uint64_t shift_guard(uint64_t s, int32_t ksh) {
+  if (ksh <= kGuard) return s << (kGuard - ksh);
+  const int32_t sh = ksh - kGuard;
+  return sh >= 64 ? 0ull : (s >> sh);
 }
 
-// two 32-bit words -> two independent N(0,1) draws
-__device__ __forceinline__ void normal_pair(uint32_t ra, uint32_t rb, float& z0, float& z1) {
-  float u = __fmaf_rn(__uint2float_rn(ra), 0x1p-32f, 0x1p-33f);
-  uint32_t bits = __float_as_uint(u);
-  int32_t e = (int32_t)(bits - 0x3F3504F3u) >> 23;
-  float mant = __uint_as_float(bits - ((uint32_t)e << 23));
-  float t = __fsub_rn(mant, 1.0f);
-  float t2 = __fmul_rn(t, t);
-  float P = -0x1.4bd700p-4f;
-  P = __fmaf_rn(P, t, 0x1.04591ap-3f);
-  P = __fmaf_rn(P, t, -0x1.09abe4p-3f);
-  P = __fmaf_rn(P, t, 0x1.22dc4cp-3f);
-  P = __fmaf_rn(P, t, -0x1.54d54ep-3f);
-  P = __fmaf_rn(P, t, 0x1.99a14cp-3f);
-  P = __fmaf_rn(P, t, -0x1.0000c8p-2f);
-  P = __fmaf_rn(P, t, 0x1.555552p-2f);
-  float lnm = __fmaf_rn(__fmul_rn(t2, t), P, __fmaf_rn(-0.5f, t2, t));
-  float rad2 = __fmaf_rn(__int2float_rn(e), kNeg2Ln2, __fmul_rn(-2.0f, lnm));
-  rad2 = fmaxf(rad2, 0.0f);
-  float R = __fsqrt_rn(rad2);
-  uint32_t q = rb >> 30;
-  float fr = __fmaf_rn(__uint2float_rn(rb & 0x3FFFFFFFu), 0x1p-30f, -0.5f);
-  float phi = __fmul_rn(fr, kHalfPi);
-  float z = __fmul_rn(phi, phi);
-  float S = __fmaf_rn(__fmaf_rn(-0x1.9aca02p-13f, z, 0x1.110c2ap-7f), z, -0x1.555552p-3f);
-  float C = __fmaf_rn(__fmaf_rn(0x1.9bd8d2p-16f, z, -0x1.6c12d4p-10f), z, 0x1.555554p-5f);
-  float s = __fmaf_rn(__fmul_rn(phi, z), S, phi);
-  float c = __fmaf_rn(__fmul_rn(z, z), C, __fmaf_rn(-0.5f, z, 1.0f));
-  float cq = (q & 1u) ? s : c;   // q=0: c   1: -s   2: -c   3: s
-  float sq = (q & 1u) ? c : s;   // q=0: s   1:  c   2: -s   3: -c
-  if (q == 1u || q == 2u) cq = -cq;
-  if (q >= 2u) sq = -sq;
-  z0 = __fmul_rn(R, cq);
-  z1 = __fmul_rn(R, sq);
-}
+// memory offset inside a canonical block of the particle at CDF position p (see resample_tile)
+__device__ __forceinline__ int cdf_offset(int p) { return ((p >> 2) & 1) * 128 + (p >> 3) * 4 + (p & 3); }
 
 }  // namespace pz

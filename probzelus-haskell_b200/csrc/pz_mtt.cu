@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) mtt_step(const __grid_constant__ Mtt
   }
 }
 
-// weighted track-count moments: sum w, sum w^2, sum w c, sum w c^2 at scale 2^(emax-23)
+// weighted track-count moments: sum w, sum w^2, sum w c, sum w c^2 at scale 2^emax
 __global__ void __launch_bounds__(kThreads) mtt_summary_reduce(const float* __restrict__ lw, const uint32_t* __restrict__ s,
                                                                int64_t n, PlanDev* plan) {
   __shared__ double s_red[kWarps][4];
@@ -252,11 +252,9 @@ __global__ void __launch_bounds__(kThreads) mtt_summary_reduce(const float* __re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double v[4] = {0, 0, 0, 0};
   if (i < n) {
-    int32_t nn; uint32_t mm;
-    weight_split(lw[i], nn, mm);
-    if (mm) {
-      const int kk = nn - plan->emax;
-      const double w = kk < -1000 ? 0.0 : (double)mm * __hiloint2double((1023 + kk) << 20, 0);
+    const float l = sanitize_lw(lw[i]);
+    if (l > -INFINITY) {
+      const double w = exp2((double)l * 1.4426950408889634 - (double)plan->emax);  // scale 2^emax
       const double c = (double)s[(size_t)i * kMttWords];
       v[0] = w; v[1] = w * w; v[2] = w * c; v[3] = w * c * c;
     }
@@ -289,7 +287,7 @@ __global__ void mtt_summary_final(PlanDev* pl, const CtlDev* ctl, pz_step_summar
   o->mean[0] = m;
   o->var[0] = pl->sxx[0] / sw - m * m;
   o->step = ctl->t;
-  o->log_evidence_inc = log(sw) + (double)(pl->emax - 23) * 0.6931471805599453 - log((double)n) + ll_const;
+  o->log_evidence_inc = log(sw) + (double)pl->emax * 0.6931471805599453 - log((double)n) + ll_const;
   o->ess = sw * sw / pl->sw2;
   o->n_migrated = 0;
   o->e_max = pl->emax;

@@ -106,8 +106,8 @@ _oracle = None
 def build_oracle():
     so = os.path.join(ORACLE_DIR, "libpzoracle.so")
     src = os.path.join(ORACLE_DIR, "pz_oracle.cpp")
-    hdr = os.path.join(ROOT, "include", "pzgpu.h")
-    if not os.path.exists(so) or (os.path.exists(src) and max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so)):
+    hdrs = [os.path.join(ROOT, "include", h) for h in ("pzgpu.h", "pz_spec_tables.h")]
+    if not os.path.exists(so) or (os.path.exists(src) and max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so)):
         subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
     return so
 
@@ -120,8 +120,10 @@ def oracle():
     lib = C.CDLL(build_oracle())
     u32p, i32p, u64p, f32p, f64p = (C.POINTER(t) for t in (C.c_uint32, C.c_int32, C.c_uint64, C.c_float, C.c_double))
     lib.pzo_philox4x32_10.argtypes = [u32p, u32p, u32p]
-    lib.pzo_weight_split.argtypes = [f32p, C.c_int64, i32p, u32p]
-    lib.pzo_normal_pairs.argtypes = [u32p, u32p, C.c_int64, f32p, f32p]
+    lib.pzo_block_weights.argtypes = [f32p, C.c_int64, C.POINTER(C.c_uint16), f32p, i32p]
+    lib.pzo_block_weights.restype = None
+    lib.pzo_icdf_normals.argtypes = [u32p, C.c_int64, f32p]
+    lib.pzo_icdf_normals.restype = None
     lib.pzo_resample_uniform.argtypes = [C.c_uint64, C.c_uint32]
     lib.pzo_resample_uniform.restype = C.c_uint32
     lib.pzo_resample_systematic.argtypes = [f32p, C.c_int64, C.c_uint32, i32p, i32p, u64p, u64p, i32p, u64p]
@@ -222,6 +224,22 @@ class OracleFilter:
         self.close()
 
 
+def cdf_position(i):
+    """CDF order inside a canonical block of 256 (DESIGN.md "Resampler"): memory index -> global CDF position."""
+    i = np.asarray(i, dtype=np.int64)
+    off = i & 255
+    return (i - off) + ((off & 127) >> 2) * 8 + (off >> 7) * 4 + (off & 3)
+
+
+def block_weights(lw32):
+    lib = oracle()
+    lw32 = np.ascontiguousarray(lw32, dtype=np.float32)
+    n = lw32.size
+    q = np.zeros(n, np.uint16); w = np.zeros(n, np.float32); eb = np.zeros((n + 255) // 256, np.int32)
+    lib.pzo_block_weights(ptr(lw32, C.c_float), n, ptr(q, C.c_uint16), ptr(w, C.c_float), ptr(eb, C.c_int32))
+    return q, w, eb
+
+
 def oracle_systematic(lw32, U):
     lib = oracle()
     lw32 = np.ascontiguousarray(lw32, dtype=np.float32)
@@ -240,7 +258,7 @@ def oracle_multinomial(lw32, seed, step):
     return rc, anc
 
 
-def assert_within_mc_tolerance(est, exact, what):
+def assert_within_mc_tolerance(est, exact, what, rel_bias_allow=0.0):
     """Monte Carlo parity gate: est[seed, step, dim] against exact[step, dim].
 
     (i)  the stated tolerance: every single run lies within 3 standard errors of the exact value,
@@ -259,7 +277,12 @@ def assert_within_mc_tolerance(est, exact, what):
     per_seed_bias = err.mean(axis=1)                       # [seed, dim]
     se_bias = per_seed_bias.std(axis=0, ddof=1) / np.sqrt(S)
     zb = per_seed_bias.mean(axis=0) / np.maximum(se_bias, 1e-300)
-    assert np.all(np.abs(zb) < 4.5), (what, "time-averaged bias beyond 4.5 SE of the seed average", zb)
+    # rel_bias_allow: the O(1/N) finite-population bias of a particle filter's VARIANCE estimate (loss of
+    # diversity under resampling; measured ~ -90/N relative on the 6-D tracker, shrinking 4x from N = 4000
+    # to 16000) is a property of the algorithm, not of the implementation; callers state it explicitly.
+    allow = rel_bias_allow * np.abs(exact).mean(axis=0)
+    excess = np.maximum(np.abs(per_seed_bias.mean(axis=0)) - allow, 0.0) / np.maximum(se_bias, 1e-300)
+    assert np.all(excess < 4.5), (what, "time-averaged bias beyond 4.5 SE of the seed average (+ stated O(1/N) allowance)", zb)
 
 
 def mtt_scenario(T, seed=5):

@@ -27,51 +27,58 @@ def test_philox_known_answers():
 def test_philox_golden_fixture():
     g = np.load(H.ROOT + "/tests/golden/philox_normal_kat.npz")
     lib = H.oracle()
-    ra, rb = g["ra"], g["rb"]
-    z0, z1 = np.zeros(ra.size, np.float32), np.zeros(ra.size, np.float32)
-    lib.pzo_normal_pairs(H.ptr(ra, C.c_uint32), H.ptr(rb, C.c_uint32), ra.size, H.ptr(z0, C.c_float), H.ptr(z1, C.c_float))
-    assert np.array_equal(z0.view(np.uint32), g["z0"].view(np.uint32))
-    assert np.array_equal(z1.view(np.uint32), g["z1"].view(np.uint32))
-    n, m = np.zeros(g["lw"].size, np.int32), np.zeros(g["lw"].size, np.uint32)
-    lib.pzo_weight_split(H.ptr(g["lw"], C.c_float), g["lw"].size, H.ptr(n, C.c_int32), H.ptr(m, C.c_uint32))
-    assert np.array_equal(n, g["n"]) and np.array_equal(m, g["m"])
+    r = g["r"]
+    z = np.zeros(r.size, np.float32)
+    lib.pzo_icdf_normals(H.ptr(r, C.c_uint32), r.size, H.ptr(z, C.c_float))
+    assert np.array_equal(z.view(np.uint32), g["z"].view(np.uint32))
+    q, w, eb = H.block_weights(g["lw"])
+    assert np.array_equal(q, g["q"]) and np.array_equal(w.view(np.uint32), g["w"].view(np.uint32)) and np.array_equal(eb, g["eb"])
 
 
-def test_normal_pair_against_libm():
+def test_icdf_normal_against_ndtri():
+    """One Philox word -> N(0,1): the piecewise-cubic inverse CDF against scipy's ndtri."""
+    from scipy.special import ndtri
     lib = H.oracle()
     rng = np.random.default_rng(0)
-    ra = rng.integers(0, 2 ** 32, 200000, dtype=np.uint32)
-    rb = rng.integers(0, 2 ** 32, 200000, dtype=np.uint32)
-    ra[:4] = [0, 1, 2 ** 32 - 1, 2 ** 31]
-    rb[:4] = [0, 2 ** 30, 2 ** 32 - 1, 2 ** 31 + 5]
-    z0, z1 = np.zeros(ra.size, np.float32), np.zeros(ra.size, np.float32)
-    lib.pzo_normal_pairs(H.ptr(ra, C.c_uint32), H.ptr(rb, C.c_uint32), ra.size, H.ptr(z0, C.c_float), H.ptr(z1, C.c_float))
-    u = (np.float32(ra) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)).astype(np.float64)  # the spec's fp32 uniform
-    R = np.sqrt(-2 * np.log(u))
-    fr = (np.float32(rb & 0x3FFFFFFF).astype(np.float64) * 2.0 ** -30) - 0.5
-    th = ((rb >> 30) + fr) * np.pi / 2
-    assert np.max(np.abs(z0 - R * np.cos(th))) < 5e-6
-    assert np.max(np.abs(z1 - R * np.sin(th))) < 5e-6
-    z = np.concatenate([z0, z1]).astype(np.float64)
-    assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.01 and abs((z ** 4).mean() - 3) < 0.05
-    assert np.all(np.isfinite(z))
+    r = rng.integers(0, 2 ** 32, 400000, dtype=np.uint32)
+    r[:8] = [0, 1, 2, 2 ** 31 - 1, 2 ** 31, 2 ** 31 + 1, 2 ** 32 - 1, 0x40000000]
+    # every dyadic segment, including the far tails random words never reach
+    tails = np.array([(1 << s) | (rng.integers(0, 1 << s) if s else 0) for s in range(31) for _ in range(64)], dtype=np.uint32)
+    r = np.concatenate([r, tails, tails | np.uint32(0x80000000)])
+    z = np.zeros(r.size, np.float32)
+    lib.pzo_icdf_normals(H.ptr(r, C.c_uint32), r.size, H.ptr(z, C.c_float))
+    # the tail probability the spec assigns to the word: the top 3 + 23 bits below the leading one of v = (r << 1) | 1
+    v = ((r.astype(np.uint64) << 1) | 1) & 0xFFFFFFFF
+    k = 31 - np.floor(np.log2(v.astype(np.float64))).astype(np.int64)
+    vn = (v << k.astype(np.uint64)) & 0xFFFFFFFF
+    frac = ((vn >> 5) & 0x3FFFFFF).astype(np.float64) / 2.0 ** 26      # 26 bits below the leading one
+    u = (1.0 + frac) * 2.0 ** -(k + 2.0)
+    ref = -ndtri(u) * np.where(r >> 31, -1.0, 1.0)
+    assert np.max(np.abs(z - ref)) < 1.5e-6
+    assert np.all(np.isfinite(z)) and np.max(np.abs(z)) < 6.35
+    zz = z[:400000].astype(np.float64)
+    assert abs(zz.mean()) < 0.006 and abs(zz.var() - 1) < 0.008 and abs((zz ** 4).mean() - 3) < 0.06
+    assert abs(np.mean(zz < -1.0) - 0.158655) < 0.003
 
 
-def test_weight_split_against_libm():
-    lib = H.oracle()
-    lw = np.concatenate([-np.random.default_rng(1).random(100000) * 80, [0.0, -1e-30, 5.0, -700.0]]).astype(np.float32)
-    n, m = np.zeros(lw.size, np.int32), np.zeros(lw.size, np.uint32)
-    lib.pzo_weight_split(H.ptr(lw, C.c_float), lw.size, H.ptr(n, C.c_int32), H.ptr(m, C.c_uint32))
-    w = m.astype(np.float64) * 2.0 ** (n.astype(np.float64) - 23)
-    rel = np.abs(w / np.exp(lw.astype(np.float64)) - 1)
-    assert np.max(rel) < 6e-5 * 1.0  # dominated by the fp32 rounding of lw * log2(e) at |lw| ~ 700
-    assert np.max(rel[np.abs(lw) < 80]) < 1e-5
-    assert m.min() >= 5931641 and m.max() <= 11863284
-    # special values -> zero weight
-    sp = np.array([-np.inf, np.inf, np.nan, -1e30], np.float32)
-    n, m = np.zeros(4, np.int32), np.zeros(4, np.uint32)
-    lib.pzo_weight_split(H.ptr(sp, C.c_float), 4, H.ptr(n, C.c_int32), H.ptr(m, C.c_uint32))
-    assert np.all(m == 0)
+def test_block_weights_against_libm():
+    rng = np.random.default_rng(1)
+    lw = np.concatenate([-rng.random(100000) * 9, [0.0, -1e-30, -0.5, -5.0]]).astype(np.float32)
+    q, w, eb = H.block_weights(lw)
+    scale = 2.0 ** eb[np.arange(lw.size) // 256].astype(np.float64)
+    rel = np.abs(w.astype(np.float64) * scale / np.exp(lw.astype(np.float64)) - 1)
+    assert np.max(rel) < 2e-6                    # fp32 weight relative to exp(lw)
+    assert np.all(np.abs(q.astype(np.float64) - w.astype(np.float64) * 32768.0) <= 0.5)   # q = rint(w * 2^15)
+    bmax = np.array([q[b * 256:(b + 1) * 256].max() for b in range(eb.size)])
+    assert bmax.min() >= 22800 and bmax.max() <= 46990   # block maximum in [2^14.48, 2^15.52]
+    # special values -> zero weight; a block of them is empty
+    sp = np.array([-np.inf, np.inf, np.nan, -np.inf] * 64, np.float32)
+    q, w, eb = H.block_weights(sp)
+    assert np.all(q == 0) and eb[0] == -(1 << 30)
+    # weights far below the block maximum flush to zero instead of wrapping
+    lw = np.zeros(256, np.float32); lw[1:] = -np.arange(1, 256, dtype=np.float32) * 3
+    q, w, eb = H.block_weights(lw)
+    assert q[0] == 32768 and np.all(np.diff(q.astype(np.int64)) <= 0) and q[-1] == 0 and np.all(w > 0)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 1000, 4097, 50000])
@@ -82,12 +89,17 @@ def test_systematic_invariants(n):
         rc, anc = H.oracle_systematic(lw, U)
         assert rc == 0
         assert anc.min() >= 0 and anc.max() < n
-        assert np.all(np.diff(anc) >= 0)  # systematic ancestors are sorted
-        # offspring counts within 1 of N * w_i (the defining property of systematic resampling)
+        assert np.all(np.diff(H.cdf_position(anc)) >= 0)  # systematic ancestors are sorted in CDF order
+        # offspring counts within 1 of N * w_i (the defining property of systematic resampling);
+        # the weights carry 15 bits relative to their block's maximum
         w = np.exp(lw.astype(np.float64) - lw.max())
         w /= w.sum()
         cnt = np.bincount(anc, minlength=n)
-        assert np.all(np.abs(cnt - n * w) < 1 + 1e-3 * n * w + 1e-6)
+        q, _, eb = H.block_weights(lw)
+        wq = q.astype(np.float64) * 2.0 ** (eb[np.arange(n) // 256] - eb.max()).astype(np.float64)
+        wq /= wq.sum()
+        assert np.all(np.abs(cnt - n * wq) < 1 + 1e-6 * n)
+        assert np.all(np.abs(cnt - n * w) < 1.05 + 1e-3 * n * w)
 
 
 def test_systematic_matches_f64_definition():
@@ -95,15 +107,17 @@ def test_systematic_matches_f64_definition():
     (monad-bayes Population.systematic lineage) except at near-ties."""
     lib = H.oracle()
     rng = np.random.default_rng(3)
-    n = 20000
+    n = 20480   # whole blocks: CDF position == rank in the spec's order
     lw = (rng.standard_normal(n) * 2).astype(np.float32)
     U = 987654321
     rc, anc = H.oracle_systematic(lw, U)
     a2 = np.zeros(n, np.int32)
-    lwd = lw.astype(np.float64)
+    order = np.argsort(H.cdf_position(np.arange(n)))       # the f64 walk in the spec's CDF order
+    lwd = lw.astype(np.float64)[order]
     lib.pzo_resample_systematic_f64(H.ptr(lwd, C.c_double), n, U / 2.0 ** 32, H.ptr(a2, C.c_int32))
-    assert np.mean(anc != a2) < 5e-3  # near-ties only: the weights carry 24 significant bits
-    assert np.max(np.abs(anc - a2)) <= 2
+    pa = H.cdf_position(anc)
+    assert np.mean(pa != a2) < 3e-2   # near-ties only: the weights carry 15 bits relative to the block maximum
+    assert np.max(np.abs(pa - a2)) <= 4
 
 
 def test_systematic_edge_cases():
@@ -117,7 +131,7 @@ def test_systematic_edge_cases():
     assert rc == H.PZ_EDEGENERATE
     # equal weights: every particle survives exactly once for a mid-range uniform
     rc, anc = H.oracle_systematic(np.zeros(5000, np.float32), 2 ** 31)
-    assert rc == 0 and np.array_equal(anc, np.arange(5000))
+    assert rc == 0 and np.array_equal(np.sort(anc), np.arange(5000))
     # huge dynamic range across blocks
     lw = np.full(2048, -600.0, np.float32)
     lw[5] = 0.0
@@ -180,7 +194,7 @@ def test_canonical_filter_matches_kalman(model):
     zv = (vars_.mean(axis=0) - kvar) / np.maximum(se_v, 1e-12)
     # 3 SE per statistic; allow the expected handful of >3 sigma events among T*nx*2 tests
     H.assert_within_mc_tolerance(means, km, "mean")
-    H.assert_within_mc_tolerance(vars_, kvar, "var")
+    H.assert_within_mc_tolerance(vars_, kvar, "var", rel_bias_allow=100.0 / n)
     if model != "rw1d":  # the doubled scalar score is not a normalised density
         se_l = lls.sum(axis=1).std(ddof=1) / np.sqrt(seeds)
         assert abs(lls.sum(axis=1).mean() - kl.sum()) < 4 * se_l + 0.05

@@ -23,16 +23,29 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _split(lw32):
-    lib = H.oracle()
-    n = np.zeros(lw32.size, np.int32); m = np.zeros(lw32.size, np.uint32)
-    lib.pzo_weight_split(H.ptr(lw32, C.c_float), lw32.size, H.ptr(n, C.c_int32), H.ptr(m, C.c_uint32))
-    return n.astype(np.int64), m.astype(np.int64)
+GUARD = 16
+
+
+def _block_weights(lw32):
+    """q (16-bit weights at the block scale) and block exponents from the oracle's spec functions."""
+    q, _, eb = H.block_weights(np.ascontiguousarray(lw32, dtype=np.float32))
+    return q.astype(np.int64), eb.astype(np.int64)
+
+
+def _shift_guard(s, ksh):
+    return (s << (GUARD - ksh)) if ksh <= GUARD else (s >> (ksh - GUARD))
+
+
+def _block_pos(Cv, rho, L, U):
+    return (((int(Cv) << (64 - L)) * rho) >> 64) + (0xFFFFFFFF - U)
 
 
 def _slot_end(Cv, rho, L, U, n_out):
-    pos = ((int(Cv) << (64 - L)) * rho) >> 64
-    return min((pos + (0xFFFFFFFF - U)) >> 32, n_out)
+    return min(_block_pos(Cv, rho, L, U) >> 32, n_out)
+
+
+def _cdf_offset(p):
+    return ((p >> 2) & 1) * 128 + (p >> 3) * 4 + (p & 3)
 
 
 def _gloo_worker(rank, world, port, n_global, seed, ret):
@@ -49,16 +62,14 @@ def _gloo_worker(rank, world, port, n_global, seed, ret):
     n_local = n_global // world
     nb = n_local // BLK
     mine = lw[rank * n_local:(rank + 1) * n_local]
-    nn, mm = _split(mine)
     NZ = -(1 << 30)
-    # per-block statistics (what the step kernel writes)
-    eb = np.array([max([nn[i] for i in range(b * BLK, (b + 1) * BLK) if mm[i]] or [NZ]) for b in range(nb)], dtype=np.int64)
-    q_loc = np.array([(int(mm[i]) >> min(int(eb[i // BLK] - nn[i]), 63)) if mm[i] else 0 for i in range(n_local)], dtype=object)
-    sb = [int(sum(q_loc[b * BLK:(b + 1) * BLK])) for b in range(nb)]
+    # per-block statistics (what the step kernel writes): 16-bit weights, block exponent, block sum
+    q_loc, eb = _block_weights(mine)
+    sb = [int(q_loc[b * BLK:(b + 1) * BLK].sum()) for b in range(nb)]
     # (1) all-reduce max of the block exponent
     e = torch.tensor([int(eb.max())]); dist.all_reduce(e, op=dist.ReduceOp.MAX); emax = int(e.item())
     # (2) local scan at the global exponent, all-gather of rank totals
-    S = [(sb[b] >> int(emax - eb[b])) if (eb[b] != NZ and emax - eb[b] < 64) else 0 for b in range(nb)]
+    S = [_shift_guard(sb[b], int(emax - eb[b])) if eb[b] != NZ else 0 for b in range(nb)]
     pb = [0]
     for v in S:
         pb.append(pb[-1] + v)
@@ -67,6 +78,7 @@ def _gloo_worker(rank, world, port, n_global, seed, ret):
     totals = [int(t.item()) for t in tot]
     base, T = sum(totals[:rank]), sum(totals)
     L = T.bit_length(); rho = ((n_global << (32 + L)) // T) + 1
+    lam = rho.bit_length() - 30; Mq = (rho >> lam) + 1; h0 = L - GUARD - lam
     pbx = [base + v for v in pb]
     # (3) boundary table: global block of the ancestor of every rank's first / last slot
     table = torch.full((2 * world,), -1, dtype=torch.int64)
@@ -78,9 +90,9 @@ def _gloo_worker(rank, world, port, n_global, seed, ret):
     dist.all_reduce(table, op=dist.ReduceOp.MAX)
     need_lo, need_hi = int(table[rank]), int(table[world + rank])
     # (4) halo plan from the C library + exchange (weights, block exponents, absolute prefixes)
-    ext = {}  # global block -> (lw[256], eb, pbx_start, pbx_end)
+    ext = {}  # global block -> (q[256], eb, pbx_start, pbx_end)
     for b in range(nb):
-        ext[rank * nb + b] = (mine[b * BLK:(b + 1) * BLK], int(eb[b]), pbx[b], pbx[b + 1])
+        ext[rank * nb + b] = (q_loc[b * BLK:(b + 1) * BLK], int(eb[b]), pbx[b], pbx[b + 1])
     reqs = []
     recv_bufs = []
     for peer in range(world):
@@ -101,21 +113,28 @@ def _gloo_worker(rank, world, port, n_global, seed, ret):
     for lo, hi, buf in recv_bufs:
         a = buf.numpy().reshape(hi - lo, BLK + 3)
         for k, gb in enumerate(range(lo, hi)):
-            ext[gb] = (a[k, :BLK].astype(np.float32), int(a[k, BLK]), int(a[k, BLK + 1]), int(a[k, BLK + 2]))
+            ext[gb] = (a[k, :BLK].astype(np.int64), int(a[k, BLK]), int(a[k, BLK + 1]), int(a[k, BLK + 2]))
             migrated += BLK
     # (5) resample my output slots from the (halo-extended) blocks
     anc = np.full(n_local, -1, dtype=np.int64)
     j_lo, j_hi = rank * n_local, (rank + 1) * n_local
     for gb in range(need_lo, need_hi + 1):
-        blw, ebb, P0, _ = ext[gb]
-        if ebb == NZ or emax - ebb >= 32:
+        bq, ebb, P0, P1 = ext[gb]
+        X0, X1 = _block_pos(P0, rho, L, U), _block_pos(P1, rho, L, U)
+        o0, o1 = X0 >> 32, X1 >> 32
+        if o1 == o0:
             continue
-        bn, bm = _split(np.ascontiguousarray(blw))
+        h = h0 + (emax - ebb)
+        A = X1 & 0xFFFFFFFF
+        sbb = int(bq.sum())
         c = 0
-        prev = _slot_end(P0, rho, L, U, n_global)
-        for i in range(BLK):
-            c += (int(bm[i]) >> min(int(ebb - bn[i]), 63)) if bm[i] else 0
-            o = _slot_end(P0 + (c >> (emax - ebb)), rho, L, U, n_global)
+        prev = o0
+        for p in range(BLK):  # the block's CDF order
+            i = _cdf_offset(p)
+            c += int(bq[i])
+            r = sbb - c
+            num = (A << h) - r * Mq if h >= 0 else A - ((r * Mq) << (-h))   # floor((A 2^h - r M) / 2^(h+32))
+            o = max(o1 + (num >> (max(h, 0) + 32)), o0)
             for j in range(max(prev, j_lo), min(o, j_hi)):
                 anc[j - j_lo] = gb * BLK + i
             prev = max(prev, o)
