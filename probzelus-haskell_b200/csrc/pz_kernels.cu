@@ -546,15 +546,13 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
 // ------------------------------------------------------------------------------------------
 // resample phase shared by the step and the ancestor kernels
 // ------------------------------------------------------------------------------------------
-// Runs of more than kDirectRun children are filled cooperatively after the input phase.
-constexpr int kDirectRun = 16;
-struct TileQueue {
-  int* n;      // number of queued runs
-  int* lo;     // [cap] first slot (tile relative)
-  int* hi;     // [cap] one past the last slot
-  float* x;    // [NV][cap] payload
-  int cap;     // TO / 16: a queued run has more than 16 slots, so at most TO / 17 runs exist
-};
+// Head marks: the input side stores a particle's payload at the slot of its FIRST child only (and
+// again at every 128-slot segment boundary the run of children crosses, so that every segment
+// starts with a head); all other slots keep the sentinel written before the input phase.  The
+// output side resolves the parent of every slot with one ballot per 128 slots (resolve_heads).
+// Work is balanced whatever the weight distribution: a particle with 10^6 children costs one
+// store per segment on the input side and nothing extra on the output side.
+constexpr uint32_t kSentinel = 0x7FC0DEADu;  // a NaN payload no arithmetic produces; index payloads use it too
 
 // Payload sources: what is staged for the children of a particle.
 template <int NX>
@@ -587,23 +585,11 @@ struct IndexSource {  // generic path: payload = particle index
 };
 
 template <class Source>
-__device__ __forceinline__ void emit_children(const Source& src, float* s_par, int stride, const TileQueue& tq, int lo,
-                                              int hi, int k) {
+__device__ __forceinline__ void emit_head(const Source& src, float* s_par, int stride, int lo, int hi, int k) {
   if (hi > lo) {
     src.put(s_par, stride, lo, k);
-    if (hi > lo + 1) {
-      src.put(s_par, stride, lo + 1, k);
-      if (hi > lo + 2) {  // rare: three or more children
-        const int stop = min(hi, lo + kDirectRun);
-        for (int s = lo + 2; s < stop; ++s) src.put(s_par, stride, s, k);
-        if (hi > stop) {
-          const int idx = atomicAdd(tq.n, 1);
-          tq.lo[idx] = stop;
-          tq.hi[idx] = hi;
-#pragma unroll
-          for (int d = 0; d < Source::NV; ++d) tq.x[d * tq.cap + idx] = src.v[d][k];
-        }
-      }
+    if ((lo ^ (hi - 1)) >> 7) {  // the children cross a 128-slot segment boundary
+      for (int s = (lo | 127) + 1; s < hi; s += 128) src.put(s_par, stride, s, k);
     }
   }
 }
@@ -618,20 +604,23 @@ __device__ __forceinline__ void emit_children(const Source& src, float* s_par, i
 // end): one mad.wide.s32 and one arithmetic shift per particle.  Measuring from the block END
 // makes zero-weight particles childless by construction and the last weight reach o1 exactly.
 template <class Source>
-__device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const TileQueue& tq,
-                                              const uint16_t* __restrict__ qin, const int32_t* __restrict__ ebx,
-                                              const u64* __restrict__ xb, int64_t b_first, int64_t b_end, int32_t emax,
-                                              int32_t h0, uint32_t Mq, uint32_t j0, int nslots, int lane, int warp) {
+__device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const uint16_t* __restrict__ qin,
+                                              const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
+                                              int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
+                                              int lane, int warp) {
   const uint32_t jend = j0 + (uint32_t)nslots;
   for (int64_t b = b_first + warp; b < b_end; b += kWarps) {
     const u64 X0 = xb[b], X1 = xb[b + 1];
-    const uint32_t o0 = (uint32_t)(X0 >> 32), o1 = (uint32_t)(X1 >> 32);
-    if (o0 >= jend) break;                  // this and every later block start past the tile
-    if (o1 == o0 || o1 <= j0) continue;     // no children (every empty block), or none in this tile
-    const int h = h0 + (emax - ebx[b]);
+    const int32_t ebb = ebx[b];
     const int64_t ia = b * kBlk + lane * 4;
     const uint2 qa = *reinterpret_cast<const uint2*>(qin + ia);
     const uint2 qb = *reinterpret_cast<const uint2*>(qin + ia + 128);
+    const uint32_t o0 = (uint32_t)(X0 >> 32), o1 = (uint32_t)(X1 >> 32);
+    if (o0 >= jend) break;                  // this and every later block start past the tile
+    if (o1 == o0 || o1 <= j0) continue;     // no children (every empty block), or none in this tile
+    Source sa = src, sb = src;
+    if constexpr (Source::NV == 1) { sa.load(ia); sb.load(ia + 128); }  // narrow payloads: load with the weights
+    const int h = h0 + (emax - ebb);
     uint32_t c[8];
     c[0] = qa.x & 0xffffu;
     c[1] = c[0] + (qa.x >> 16);
@@ -666,31 +655,33 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
       for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
     }
     if (e[3] > eprev) {
-      src.load(ia);
+      if constexpr (Source::NV != 1) sa.load(ia);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { emit_children(src, s_par, stride, tq, eprev, e[k], k); eprev = e[k]; }
+      for (int k = 0; k < 4; ++k) { emit_head(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
     }
     if (e[7] > e[3]) {
-      src.load(ia + 128);
+      if constexpr (Source::NV != 1) sb.load(ia + 128);
       eprev = e[3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { emit_children(src, s_par, stride, tq, eprev, e[4 + k], k); eprev = e[4 + k]; }
+      for (int k = 0; k < 4; ++k) { emit_head(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
     }
   }
 }
 
-// Cooperative fill of the queued long runs (after a __syncthreads; followed by one).
-template <int NV>
-__device__ __forceinline__ void drain_queue(float* s_par, int stride, const TileQueue& tq, int tid) {
-  const int nq = *tq.n;
-  for (int e = 0; e < nq; ++e) {
-    const int lo = tq.lo[e], hi = tq.hi[e];
-#pragma unroll
-    for (int d = 0; d < NV; ++d) {
-      const float xv = tq.x[d * tq.cap + e];
-      for (int s = lo + tid; s < hi; s += kThreads) s_par[d * stride + s] = xv;
-    }
-  }
+// Output side: tile-relative slot of the head of each of the lane's 4 slots sl .. sl+3 (sl = segment
+// base + lane*4; the segment = the 128 slots this warp iteration covers).  bits = the payload words
+// of dimension 0 at those slots.  The first slot of a segment always carries a head (emit_head).
+__device__ __forceinline__ void resolve_heads(const uint4& bits, int sl, int lane, int (&head)[4]) {
+  const int m0 = bits.x != kSentinel ? sl : -1;
+  const int m1 = bits.y != kSentinel ? sl + 1 : m0;
+  const int m2 = bits.z != kSentinel ? sl + 2 : m1;
+  const int m3 = bits.w != kSentinel ? sl + 3 : m2;
+  const uint32_t has = __ballot_sync(0xffffffffu, m3 >= 0);
+  const uint32_t before = has & ((1u << lane) - 1u);
+  const int src = 31 - __clz(before);            // nearest earlier lane with a head (lane 0: unused)
+  const int got = __shfl_sync(0xffffffffu, m3, src & 31);
+  const int carry = before ? got : -1;
+  head[0] = max(m0, carry); head[1] = max(m1, carry); head[2] = max(m2, carry); head[3] = max(m3, carry);
 }
 
 struct TileArgs {
@@ -698,30 +689,166 @@ struct TileArgs {
   const int32_t* anc;  // MODE 1: parents by stored ancestor index
 };
 
-// MODE 0: fused systematic resample (parents staged by resample_tile)
+// MODE 0: fused systematic resample (heads staged by resample_tile, resolved on the output side)
 // MODE 1: parents gathered through a stored ancestor array (multinomial / debug path)
 // resident CTAs per SM the register allocation is held to (NX = 1 / 4 / 6)
 constexpr int min_ctas(int nx) { return nx == 1 ? 4 : (nx <= 4 ? 3 : 2); }
 #define PZ_NACC(nx) (2 + 2 * (nx))
 
+// Output side of one canonical output block (256 slots, one warp; a lane owns slots lane*4 + {0..3}
+// and 128 + lane*4 + {0..3}).  FULL: every slot of the tile is live (all tiles but the last).
+template <int NX, int NY, int TO, int MODE, bool KRON, bool FULL>
+__device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, const float4* __restrict__ tab_m8, int ob,
+                                             int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const float* y_new,
+                                             const float* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref) {
+  float* __restrict__ xout = a.X[nxt];
+  uint16_t* __restrict__ qout = a.Q[nxt];
+  float lw[8];
+  float xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
+  float mx = -INFINITY;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
+    float xp[NX][4];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
+      xp[d][0] = f.x; xp[d][1] = f.y; xp[d][2] = f.z; xp[d][3] = f.w;
+    }
+    if constexpr (MODE == 0) {
+      int head[4];
+      const uint4 bits = make_uint4(__float_as_uint(xp[0][0]), __float_as_uint(xp[0][1]), __float_as_uint(xp[0][2]),
+                                    __float_as_uint(xp[0][3]));
+      resolve_heads(bits, sl, lane, head);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (head[k] != sl + k) {
+          const int hk = FULL ? head[k] : max(head[k], 0);
+#pragma unroll
+          for (int d = 0; d < NX; ++d) xp[d][k] = s_par[d * TO + hk];
+        }
+      }
+      if constexpr (NX > 1) __syncwarp();  // every parent read of this segment precedes the write-back below
+    }
+    float z[NX][4];
+    lg_noise4<NX>(j0 + (uint32_t)sl, t, a.seed, tab_m8, z);
+    float xo[NX][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float xs[NX], zs[NX], xn[NX];
+#pragma unroll
+      for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
+      model_propagate<NX, KRON>(a.model, xs, zs, xn);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
+      float l = model_logweight<NX, NY, KRON>(a.model, xn, y_new);
+      if (!FULL && sl + k >= nslots) l = -INFINITY;  // past the end of the population
+      lw[half * 4 + k] = l;
+      mx = fmaxf(mx, l);
+    }
+    if (FULL || sl < nslots) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        const float4 f = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
+        *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = f;
+        if constexpr (NX > 1) *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = f;
+      }
+    }
+    if constexpr (NX == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xk[half * 4 + k] = xo[0][k];
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  int32_t nb;
+  const float nbf = block_exponent(mx, nb);
+  uint32_t ssum = 0;
+  if (nb != kNZero) {
+    float p[PZ_NACC(NX)];
+#pragma unroll
+    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int sl = ob * kBlk + half * 128 + lane * 4;
+      float xv[NX][4];
+      if constexpr (NX > 1) {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
+          xv[d][0] = f.x; xv[d][1] = f.y; xv[d][2] = f.z; xv[d][3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv[0][k] = xk[half * 4 + k];
+      }
+      uint32_t qb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float w;
+        weight_q<false>(lw[half * 4 + k], nbf, w, qb[k]);
+        const bool live = FULL || sl + k < nslots;
+        if (!live) w = 0.0f;  // (its q is already 0: lw = -inf)
+        ssum += qb[k];        // raw bits 0x4B000000 + q; the bias is removed after the warp sum
+        p[0] = __fadd_rn(p[0], w);
+        p[1] = __fmaf_rn(w, w, p[1]);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          const float dx = live ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
+          const float wd = __fmul_rn(w, dx);
+          p[2 + d] = __fadd_rn(p[2 + d], wd);
+          p[2 + NX + d] = __fmaf_rn(wd, dx, p[2 + NX + d]);
+        }
+      }
+      if (FULL || sl < nslots)
+        *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(__byte_perm(qb[0], qb[1], 0x5410), __byte_perm(qb[2], qb[3], 0x5410));
+    }
+    // fold the block's sums (scale 2^nb) into the lane accumulators (scale 2^aref)
+    if (nb == aref) {
+#pragma unroll
+      for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = __fadd_rn(acc[r], p[r]);
+    } else if (aref == kNZero) {
+#pragma unroll
+      for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = p[r];
+      aref = nb;
+    } else {
+      const int32_t nref = max(aref, nb);
+      const float ga = exp2i(aref - nref), gp = exp2i(nb - nref);
+#pragma unroll
+      for (int r = 0; r < PZ_NACC(NX); ++r) {
+        const float fa = (r == 1) ? __fmul_rn(ga, ga) : ga, fp = (r == 1) ? __fmul_rn(gp, gp) : gp;
+        acc[r] = __fmaf_rn(acc[r], fa, __fmul_rn(p[r], fp));
+      }
+      aref = nref;
+    }
+  } else {
+    // empty block: every weight is zero
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int sl = ob * kBlk + half * 128 + lane * 4;
+      if (FULL || sl < nslots) *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(0u, 0u);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+  if (lane == 0) {
+    const int64_t bo = (j0l / kBlk) + ob;
+    a.eb[nxt][bo] = nb;
+    a.sb[bo] = (nb != kNZero) ? (u64)(ssum - 256u * 0x4B000000u) : 0ull;  // 256 biased terms (mod 2^32)
+  }
+}
+
 template <int NX, int NY, int TO, int MODE, bool KRON>
 __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __grid_constant__ TileArgs ta) {
-  extern __shared__ __align__(16) float s_par[];  // [NX][TO] parents | [256] float4 table | queue
+  extern __shared__ __align__(16) float s_par[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
   __shared__ int32_t s_eref[kWarps];
   __shared__ double s_red[kWarps][kMaxRec];
-  __shared__ int s_qn;
-  constexpr int QCAP = TO / 16;
   float4* s_tab = reinterpret_cast<float4*>(s_par + NX * TO);
-  int* s_qlo = reinterpret_cast<int*>(s_tab + PZ_ICDF_ROWS);
-  int* s_qhi = s_qlo + QCAP;
-  float* s_qx = reinterpret_cast<float*>(s_qhi + QCAP);
   const StepArgs& a = ta.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t t = a.ctl->t;
   const int cur = t & 1, nxt = cur ^ 1;
   const float* __restrict__ xin = a.X[cur];
-  float* __restrict__ xout = a.X[nxt];
-  uint16_t* __restrict__ qout = a.Q[nxt];
   const PlanDev* pl = a.plan;
   const int64_t j0l = (int64_t)blockIdx.x * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
@@ -733,31 +860,25 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
   for (int k = 0; k < NY; ++k) y_new[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
 
   s_tab[tid] = g_icdf_tab[tid];  // kThreads == PZ_ICDF_ROWS
-  if (tid == 0) s_qn = 0;
-  __syncthreads();
-
   if constexpr (MODE == 0) {
-    const TileQueue tq{&s_qn, s_qlo, s_qhi, s_qx, QCAP};
+    // sentinel in dimension 0 of every slot: "no head here"
+    uint4* sz = reinterpret_cast<uint4*>(s_par);
+    for (int i = tid; i < TO / 4; i += kThreads) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    __syncthreads();
     StateSource<NX> src;
     src.x = xin; src.ld = a.ld;
-    resample_tile(src, s_par, TO, tq, a.Q[cur], a.eb[cur], a.xb, (int64_t)a.tile_start[blockIdx.x], a.b_hi, pl->emax,
-                  pl->h0, pl->Mq, j0, nslots, lane, warp);
-    __syncthreads();
-    if (s_qn != 0) {
-      drain_queue<NX>(s_par, TO, tq, tid);
-      __syncthreads();
-    }
+    resample_tile(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, (int64_t)a.tile_start[blockIdx.x], a.b_hi, pl->emax, pl->h0,
+                  pl->Mq, j0, nslots, lane, warp);
   } else {
     for (int sidx = tid; sidx < nslots; sidx += kThreads) {
       const int64_t p = ta.anc[j0l + sidx];
 #pragma unroll
       for (int d = 0; d < NX; ++d) s_par[d * TO + sidx] = xin[(size_t)d * a.ld + p];
     }
-    __syncthreads();
   }
+  __syncthreads();
 
-  // ---- output side: one warp owns one canonical output block; a lane owns slots
-  //      lane*4 + {0..3} and 128 + lane*4 + {0..3} of it
+  // ---- output side
   const float4* tab_m8 = s_tab - 8;
   float acc[PZ_NACC(NX)];  // sw, sw2, sx[NX], sxx[NX] at scale 2^aref (fp32 per lane)
 #pragma unroll
@@ -766,128 +887,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
   float cen[NX];
 #pragma unroll
   for (int d = 0; d < NX; ++d) cen[d] = pl->center[d];
-  const bool full_tile = (nslots == TO);
-
-  for (int ob = warp; ob * kBlk < nslots; ob += kWarps) {
-    float lw[8];
-    float xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
-    float mx = -INFINITY;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
-      float xp[NX][4];
-#pragma unroll
-      for (int d = 0; d < NX; ++d) {
-        const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
-        xp[d][0] = f.x; xp[d][1] = f.y; xp[d][2] = f.z; xp[d][3] = f.w;
-      }
-      float z[NX][4];
-      lg_noise4<NX>(j0 + (uint32_t)sl, t, a.seed, tab_m8, z);
-      float xo[NX][4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float xs[NX], zs[NX], xn[NX];
-#pragma unroll
-        for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
-        model_propagate<NX, KRON>(a.model, xs, zs, xn);
-#pragma unroll
-        for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-        float l = model_logweight<NX, NY, KRON>(a.model, xn, y_new);
-        if (!full_tile && sl + k >= nslots) l = -INFINITY;  // past the end of the population
-        lw[half * 4 + k] = l;
-        mx = fmaxf(mx, l);
-      }
-      if (full_tile || sl < nslots) {
-#pragma unroll
-        for (int d = 0; d < NX; ++d) {
-          const float4 f = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
-          *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = f;
-          if constexpr (NX > 1) *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = f;
-        }
-      }
-      if constexpr (NX == 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xk[half * 4 + k] = xo[0][k];
-      }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    int32_t nb;
-    const float nbf = block_exponent(mx, nb);
-    uint32_t ssum = 0;
-    if (nb != kNZero) {
-      float p[PZ_NACC(NX)];
-#pragma unroll
-      for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0.0f;
-      if constexpr (NX > 1) __syncwarp();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int sl = ob * kBlk + half * 128 + lane * 4;
-        float xv[NX][4];
-        if constexpr (NX > 1) {
-#pragma unroll
-          for (int d = 0; d < NX; ++d) {
-            const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
-            xv[d][0] = f.x; xv[d][1] = f.y; xv[d][2] = f.z; xv[d][3] = f.w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) xv[0][k] = xk[half * 4 + k];
-        }
-        uint32_t qb[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float w;
-          weight_q<false>(lw[half * 4 + k], nbf, w, qb[k]);
-          const bool live = full_tile || sl + k < nslots;
-          if (!live) w = 0.0f;  // (its q is already 0: lw = -inf)
-          ssum += qb[k] & 0xffffu;
-          p[0] = __fadd_rn(p[0], w);
-          p[1] = __fmaf_rn(w, w, p[1]);
-#pragma unroll
-          for (int d = 0; d < NX; ++d) {
-            const float dx = live ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
-            const float wd = __fmul_rn(w, dx);
-            p[2 + d] = __fadd_rn(p[2 + d], wd);
-            p[2 + NX + d] = __fmaf_rn(wd, dx, p[2 + NX + d]);
-          }
-        }
-        if (full_tile || sl < nslots)
-          *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(__byte_perm(qb[0], qb[1], 0x5410), __byte_perm(qb[2], qb[3], 0x5410));
-      }
-      // fold the block's sums (scale 2^nb) into the lane accumulators (scale 2^aref)
-      if (nb == aref) {
-#pragma unroll
-        for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = __fadd_rn(acc[r], p[r]);
-      } else if (aref == kNZero) {
-#pragma unroll
-        for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = p[r];
-        aref = nb;
-      } else {
-        const int32_t nref = max(aref, nb);
-        const float ga = exp2i(aref - nref), gp = exp2i(nb - nref);
-#pragma unroll
-        for (int r = 0; r < PZ_NACC(NX); ++r) {
-          const float fa = (r == 1) ? __fmul_rn(ga, ga) : ga, fp = (r == 1) ? __fmul_rn(gp, gp) : gp;
-          acc[r] = __fmaf_rn(acc[r], fa, __fmul_rn(p[r], fp));
-        }
-        aref = nref;
-      }
-    } else {
-      // empty block: every weight is zero
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int sl = ob * kBlk + half * 128 + lane * 4;
-        if (full_tile || sl < nslots) *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(0u, 0u);
-      }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
-    if (lane == 0) {
-      const int64_t bo = (j0l / kBlk) + ob;
-      a.eb[nxt][bo] = nb;
-      a.sb[bo] = (u64)ssum;
-    }
+  if (nslots == TO) {
+    for (int ob = warp; ob < TO / kBlk; ob += kWarps)
+      output_block<NX, NY, TO, MODE, KRON, true>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+  } else {
+    for (int ob = warp; ob * kBlk < nslots; ob += kWarps)
+      output_block<NX, NY, TO, MODE, KRON, false>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   }
 
   // ---- CTA-level reduction of the moment sums -> one record per tile
@@ -977,27 +982,27 @@ __global__ void pf_ctl_reset(CtlDev* ctl) {
 
 template <int TO>
 __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
-  constexpr int QCAP = TO / 16;
   __shared__ __align__(16) float s_anc[TO];
-  __shared__ int s_qn, s_qlo[QCAP], s_qhi[QCAP];
-  __shared__ float s_qx[QCAP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PlanDev* pl = g.plan;
   const int64_t j0 = (int64_t)blockIdx.x * TO;
   const int64_t jend = (j0 + TO < g.n) ? j0 + TO : g.n;
-  for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = __int_as_float(-1);
-  if (tid == 0) s_qn = 0;
+  const int nslots = (int)(jend - j0);
+  for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = __uint_as_float(kSentinel);
   __syncthreads();
-  const TileQueue tq{&s_qn, s_qlo, s_qhi, s_qx, QCAP};
   IndexSource src;
-  resample_tile(src, s_anc, TO, tq, generic_q(g), generic_eb(g), g.xb, (int64_t)g.tile_start[blockIdx.x], g.nblk, pl->emax,
-                pl->h0, pl->Mq, (uint32_t)j0, (int)(jend - j0), lane, warp);
+  resample_tile(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, (int64_t)g.tile_start[blockIdx.x], g.nblk, pl->emax,
+                pl->h0, pl->Mq, (uint32_t)j0, nslots, lane, warp);
   __syncthreads();
-  if (s_qn != 0) {
-    drain_queue<1>(s_anc, TO, tq, tid);
-    __syncthreads();
+  for (int seg = warp; seg * 128 < nslots; seg += kWarps) {
+    const int sl = seg * 128 + lane * 4;
+    const uint4 bits = *reinterpret_cast<const uint4*>(&s_anc[sl]);
+    int head[4];
+    resolve_heads(bits, sl, lane, head);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (sl + k < nslots) g.anc[j0 + sl + k] = head[k] >= 0 ? __float_as_int(s_anc[head[k]]) : -1;
   }
-  for (int sidx = tid; sidx < (int)(jend - j0); sidx += kThreads) g.anc[j0 + sidx] = __float_as_int(s_anc[sidx]);
 }
 
 // N iid categorical draws on the canonical fixed-point CDF (resample2, Inference.hs:57-61)
@@ -1187,8 +1192,8 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
 template <int NX, int NY, int TO, int MODE, bool KRON>
 static void launch_tile(const TileArgs& ta, cudaStream_t s) {
   auto kern = pf_step_tile<NX, NY, TO, MODE, KRON>;
-  // parents [NX][TO] + inverse-CDF table + long-run queue (lo, hi, payload[NX]) of TO / 16 entries
-  size_t smem = (size_t)NX * TO * sizeof(float) + PZ_ICDF_ROWS * sizeof(float4) + (size_t)(TO / 16) * (2 + NX) * sizeof(int);
+  // staged parents [NX][TO] + inverse-CDF table
+  size_t smem = (size_t)NX * TO * sizeof(float) + PZ_ICDF_ROWS * sizeof(float4);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
