@@ -584,11 +584,14 @@ struct IndexSource {  // generic path: payload = particle index
   __device__ __forceinline__ void put(float* s_par, int, int slot, int k) const { s_par[slot] = v[0][k]; }
 };
 
-template <class Source>
+// SEGDUP = true: a head at every segment boundary any run crosses (every segment starts with a head).
+// SEGDUP = false: only runs longer than 128 slots are duplicated, so a segment whose first slots
+// have no head finds it within the previous segment (output side look-back, NX = 1).
+template <bool SEGDUP, class Source>
 __device__ __forceinline__ void emit_head(const Source& src, float* s_par, int stride, int lo, int hi, int k) {
   if (hi > lo) {
     src.put(s_par, stride, lo, k);
-    if ((lo ^ (hi - 1)) >> 7) {  // the children cross a 128-slot segment boundary
+    if (SEGDUP ? (((lo ^ (hi - 1)) >> 7) != 0) : (hi - lo > 128)) {
       for (int s = (lo | 127) + 1; s < hi; s += 128) src.put(s_par, stride, s, k);
     }
   }
@@ -603,7 +606,7 @@ __device__ __forceinline__ void emit_head(const Source& src, float* s_par, int s
 // (o0 / o1: first / end slot of the block's children, A: fractional slot position of the block
 // end): one mad.wide.s32 and one arithmetic shift per particle.  Measuring from the block END
 // makes zero-weight particles childless by construction and the last weight reach o1 exactly.
-template <class Source>
+template <bool SEGDUP, class Source>
 __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const uint16_t* __restrict__ qin,
                                               const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
                                               int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
@@ -657,13 +660,13 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
     if (e[3] > eprev) {
       if constexpr (Source::NV != 1) sa.load(ia);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { emit_head(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
+      for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
     }
     if (e[7] > e[3]) {
       if constexpr (Source::NV != 1) sb.load(ia + 128);
       eprev = e[3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { emit_head(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
+      for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
     }
   }
 }
@@ -671,17 +674,33 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
 // Output side: tile-relative slot of the head of each of the lane's 4 slots sl .. sl+3 (sl = segment
 // base + lane*4; the segment = the 128 slots this warp iteration covers).  bits = the payload words
 // of dimension 0 at those slots.  The first slot of a segment always carries a head (emit_head).
-__device__ __forceinline__ void resolve_heads(const uint4& bits, int sl, int lane, int (&head)[4]) {
+// seg_carry: head of the slots before the segment's first head (-1 when every segment starts with one);
+// returns the segment's last head.
+__device__ __forceinline__ int resolve_heads(const uint4& bits, int sl, int lane, int seg_carry, int (&head)[4]) {
   const int m0 = bits.x != kSentinel ? sl : -1;
   const int m1 = bits.y != kSentinel ? sl + 1 : m0;
   const int m2 = bits.z != kSentinel ? sl + 2 : m1;
   const int m3 = bits.w != kSentinel ? sl + 3 : m2;
   const uint32_t has = __ballot_sync(0xffffffffu, m3 >= 0);
   const uint32_t before = has & ((1u << lane) - 1u);
-  const int src = 31 - __clz(before);            // nearest earlier lane with a head (lane 0: unused)
+  const int src = 31 - __clz(before);            // nearest earlier lane with a head
   const int got = __shfl_sync(0xffffffffu, m3, src & 31);
-  const int carry = before ? got : -1;
+  const int carry = before ? got : seg_carry;
   head[0] = max(m0, carry); head[1] = max(m1, carry); head[2] = max(m2, carry); head[3] = max(m3, carry);
+  const int last = __shfl_sync(0xffffffffu, m3, (31 - __clz(has)) & 31);
+  return has ? last : seg_carry;
+}
+
+// last head of the 128-slot segment ending at slot seg_end (look-back of the NX = 1 path)
+__device__ __forceinline__ int last_head_before(const float* s_par, int seg_end, int lane) {
+  const int sl = seg_end - 128 + lane * 4;
+  const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
+  const int m0 = bits.x != kSentinel ? sl : -1;
+  const int m1 = bits.y != kSentinel ? sl + 1 : m0;
+  const int m2 = bits.z != kSentinel ? sl + 2 : m1;
+  const int m3 = bits.w != kSentinel ? sl + 3 : m2;
+  const uint32_t has = __ballot_sync(0xffffffffu, m3 >= 0);
+  return __shfl_sync(0xffffffffu, m3, (31 - __clz(has)) & 31);
 }
 
 struct TileArgs {
@@ -706,6 +725,10 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
   float lw[8];
   float xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
   float mx = -INFINITY;
+  int seg_carry = -1;
+  if constexpr (MODE == 0 && NX == 1) {
+    if (ob > 0) seg_carry = last_head_before(s_par, ob * kBlk, lane);  // runs of <= 128 slots reach back one segment
+  }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
@@ -719,7 +742,8 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
       int head[4];
       const uint4 bits = make_uint4(__float_as_uint(xp[0][0]), __float_as_uint(xp[0][1]), __float_as_uint(xp[0][2]),
                                     __float_as_uint(xp[0][3]));
-      resolve_heads(bits, sl, lane, head);
+      seg_carry = resolve_heads(bits, sl, lane, seg_carry, head);
+      if constexpr (NX != 1) seg_carry = -1;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (head[k] != sl + k) {
@@ -867,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
     __syncthreads();
     StateSource<NX> src;
     src.x = xin; src.ld = a.ld;
-    resample_tile(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, (int64_t)a.tile_start[blockIdx.x], a.b_hi, pl->emax, pl->h0,
+    resample_tile<(NX != 1)>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, (int64_t)a.tile_start[blockIdx.x], a.b_hi, pl->emax, pl->h0,
                   pl->Mq, j0, nslots, lane, warp);
   } else {
     for (int sidx = tid; sidx < nslots; sidx += kThreads) {
@@ -991,14 +1015,14 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = __uint_as_float(kSentinel);
   __syncthreads();
   IndexSource src;
-  resample_tile(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, (int64_t)g.tile_start[blockIdx.x], g.nblk, pl->emax,
+  resample_tile<true>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, (int64_t)g.tile_start[blockIdx.x], g.nblk, pl->emax,
                 pl->h0, pl->Mq, (uint32_t)j0, nslots, lane, warp);
   __syncthreads();
   for (int seg = warp; seg * 128 < nslots; seg += kWarps) {
     const int sl = seg * 128 + lane * 4;
     const uint4 bits = *reinterpret_cast<const uint4*>(&s_anc[sl]);
     int head[4];
-    resolve_heads(bits, sl, lane, head);
+    resolve_heads(bits, sl, lane, -1, head);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (sl + k < nslots) g.anc[j0 + sl + k] = head[k] >= 0 ? __float_as_int(s_anc[head[k]]) : -1;
