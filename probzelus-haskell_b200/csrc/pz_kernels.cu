@@ -606,44 +606,62 @@ __device__ __forceinline__ void emit_head(const Source& src, float* s_par, int s
 // (o0 / o1: first / end slot of the block's children, A: fractional slot position of the block
 // end): one mad.wide.s32 and one arithmetic shift per particle.  Measuring from the block END
 // makes zero-weight particles childless by construction and the last weight reach o1 exactly.
+// per-block inputs of the input side (prefetched one iteration ahead)
+struct BlockIn {
+  u64 X0, X1;
+  uint2 qa, qb;
+  int32_t ebb;
+  __device__ __forceinline__ void load(const uint16_t* __restrict__ qin, const int32_t* __restrict__ ebx,
+                                       const u64* __restrict__ xb, int64_t b, int lane) {
+    X0 = xb[b]; X1 = xb[b + 1];
+    ebb = ebx[b];
+    const int64_t ia = b * kBlk + lane * 4;
+    qa = *reinterpret_cast<const uint2*>(qin + ia);
+    qb = *reinterpret_cast<const uint2*>(qin + ia + 128);
+  }
+};
+
 template <bool SEGDUP, class Source>
 __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const uint16_t* __restrict__ qin,
                                               const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
                                               int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
                                               int lane, int warp) {
   const uint32_t jend = j0 + (uint32_t)nslots;
-  for (int64_t b = b_first + warp; b < b_end; b += kWarps) {
-    const u64 X0 = xb[b], X1 = xb[b + 1];
-    const int32_t ebb = ebx[b];
-    const int64_t ia = b * kBlk + lane * 4;
-    const uint2 qa = *reinterpret_cast<const uint2*>(qin + ia);
-    const uint2 qb = *reinterpret_cast<const uint2*>(qin + ia + 128);
-    const uint32_t o0 = (uint32_t)(X0 >> 32), o1 = (uint32_t)(X1 >> 32);
+  int64_t b = b_first + warp;
+  if (b >= b_end) return;
+  BlockIn cur;
+  cur.load(qin, ebx, xb, b, lane);
+  for (; b < b_end; b += kWarps) {
+    const BlockIn in = cur;
+    const int64_t bn = b + kWarps;
+    if (bn < b_end) cur.load(qin, ebx, xb, bn, lane);  // next iteration's inputs: in flight during this one
+    const uint32_t o0 = (uint32_t)(in.X0 >> 32), o1 = (uint32_t)(in.X1 >> 32);
     if (o0 >= jend) break;                  // this and every later block start past the tile
     if (o1 == o0 || o1 <= j0) continue;     // no children (every empty block), or none in this tile
+    const int64_t ia = b * kBlk + lane * 4;
     Source sa = src, sb = src;
-    if constexpr (Source::NV == 1) { sa.load(ia); sb.load(ia + 128); }  // narrow payloads: load with the weights
-    const int h = h0 + (emax - ebb);
+    sa.load(ia); sb.load(ia + 128);         // payload of the lane's 8 particles, in flight during the scan
+    const int h = h0 + (emax - in.ebb);
     uint32_t c[8];
-    c[0] = qa.x & 0xffffu;
-    c[1] = c[0] + (qa.x >> 16);
-    c[2] = c[1] + (qa.y & 0xffffu);
-    c[3] = c[2] + (qa.y >> 16);
-    c[4] = c[3] + (qb.x & 0xffffu);
-    c[5] = c[4] + (qb.x >> 16);
-    c[6] = c[5] + (qb.y & 0xffffu);
-    c[7] = c[6] + (qb.y >> 16);
+    c[0] = in.qa.x & 0xffffu;
+    c[1] = c[0] + (in.qa.x >> 16);
+    c[2] = c[1] + (in.qa.y & 0xffffu);
+    c[3] = c[2] + (in.qa.y >> 16);
+    c[4] = c[3] + (in.qb.x & 0xffffu);
+    c[5] = c[4] + (in.qb.x >> 16);
+    c[6] = c[5] + (in.qb.y & 0xffffu);
+    c[7] = c[6] + (in.qb.y >> 16);
     const uint32_t incl = warp_inclusive_scan_u32(c[7], lane);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t rbase = total - (incl - c[7]);  // block mass from this lane's first particle on
     const int32_t o0r = (int32_t)(o0 - j0), o1r = (int32_t)(o1 - j0);
-    const uint32_t A = (uint32_t)X1;
+    const uint32_t A = (uint32_t)in.X1;
     int32_t e[8];
     if ((unsigned)h <= 31u) {
       const long long Ah = (long long)((u64)A << h);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const long long res = mad_wide_s32(-(int32_t)(rbase - c[k]), (int32_t)Mq, Ah);
+        const long long res = mad_wide_s32((int32_t)(c[k] - rbase), (int32_t)Mq, Ah);
         e[k] = max(o1r + ((int32_t)(res >> 32) >> h), o0r);
       }
     } else {
@@ -657,17 +675,10 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
 #pragma unroll
       for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
     }
-    if (e[3] > eprev) {
-      if constexpr (Source::NV != 1) sa.load(ia);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
-    }
-    if (e[7] > e[3]) {
-      if constexpr (Source::NV != 1) sb.load(ia + 128);
-      eprev = e[3];
+    for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
-    }
+    for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
   }
 }
 
@@ -711,7 +722,16 @@ struct TileArgs {
 // MODE 0: fused systematic resample (heads staged by resample_tile, resolved on the output side)
 // MODE 1: parents gathered through a stored ancestor array (multinomial / debug path)
 // resident CTAs per SM the register allocation is held to (NX = 1 / 4 / 6)
-constexpr int min_ctas(int nx) { return nx == 1 ? 4 : (nx <= 4 ? 3 : 2); }
+#ifndef PZ_OCC1
+#define PZ_OCC1 4
+#endif
+#ifndef PZ_OCC4
+#define PZ_OCC4 3
+#endif
+#ifndef PZ_OCC6
+#define PZ_OCC6 2
+#endif
+constexpr int min_ctas(int nx) { return nx == 1 ? PZ_OCC1 : (nx <= 4 ? PZ_OCC4 : PZ_OCC6); }
 #define PZ_NACC(nx) (2 + 2 * (nx))
 
 // Output side of one canonical output block (256 slots, one warp; a lane owns slots lane*4 + {0..3}
@@ -1157,13 +1177,17 @@ __global__ void pf_boundary_table(const PlanDev* plan, const u64* pbx, int64_t n
 // ------------------------------------------------------------------------------------------
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Output slots per CTA.  Larger tiles amortise the per-tile overlap of the input side (one extra
-// input block per tile on average) and the CTA-level reduction; PZ_TILE_OUT=small selects the
-// smaller instantiation (kept for A/B measurements, profiles/README.md).
+// Output slots per CTA: 8k - 1 canonical blocks, because a tile of m output blocks draws on m + 1
+// input blocks in the typical case and the 8 warps of the CTA take input blocks round-robin (a
+// remainder of one block would leave 7 warps waiting at the barrier).  Larger tiles amortise the
+// extra input block and the CTA-level reduction; PZ_TILE_OUT=small selects the smaller
+// instantiation (kept for A/B measurements, profiles/README.md).
+constexpr int kTileBig1 = 31 * kBlk, kTileSmall1 = 15 * kBlk;   // NX = 1
+constexpr int kTileBigN = 15 * kBlk, kTileSmallN = 7 * kBlk;    // NX > 1
 int fused_tile_out(int nx) {
   static const bool small = [] { const char* e = getenv("PZ_TILE_OUT"); return e && !strcmp(e, "small"); }();
-  if (nx == 1) return small ? 4096 : 8192;
-  return small ? 2048 : 4096;
+  if (nx == 1) return small ? kTileSmall1 : kTileBig1;
+  return small ? kTileSmallN : kTileBigN;
 }
 
 int launch_init(const StepArgs& a, cudaStream_t s) {
@@ -1236,19 +1260,19 @@ static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
     else launch_tile<NXv, NYv, TOv, 1, KR>(ta, s);                   \
     return 1;                                                        \
   }
-  const bool big = fused_tile_out(nx) > (nx == 1 ? 4096 : 2048);
+  const bool big = fused_tile_out(nx) == (nx == 1 ? kTileBig1 : kTileBigN);
   if (big) {
-    PZ_DISPATCH(1, 1, 8192, false)
-    PZ_DISPATCH(4, 2, 4096, false)
-    PZ_DISPATCH(4, 2, 4096, true)
-    PZ_DISPATCH(6, 3, 4096, false)
-    PZ_DISPATCH(6, 3, 4096, true)
+    PZ_DISPATCH(1, 1, kTileBig1, false)
+    PZ_DISPATCH(4, 2, kTileBigN, false)
+    PZ_DISPATCH(4, 2, kTileBigN, true)
+    PZ_DISPATCH(6, 3, kTileBigN, false)
+    PZ_DISPATCH(6, 3, kTileBigN, true)
   } else {
-    PZ_DISPATCH(1, 1, 4096, false)
-    PZ_DISPATCH(4, 2, 2048, false)
-    PZ_DISPATCH(4, 2, 2048, true)
-    PZ_DISPATCH(6, 3, 2048, false)
-    PZ_DISPATCH(6, 3, 2048, true)
+    PZ_DISPATCH(1, 1, kTileSmall1, false)
+    PZ_DISPATCH(4, 2, kTileSmallN, false)
+    PZ_DISPATCH(4, 2, kTileSmallN, true)
+    PZ_DISPATCH(6, 3, kTileSmallN, false)
+    PZ_DISPATCH(6, 3, kTileSmallN, true)
   }
 #undef PZ_DISPATCH
   return -1;

@@ -64,6 +64,9 @@ def exported_symbols():
 
 
 def lib_path():
+    override = os.environ.get("PZ_LIB_PATH")  # A/B builds of the same ABI (tools/, profiles/README.md)
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpzgpu.so")
 
 
