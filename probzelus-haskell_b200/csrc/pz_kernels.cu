@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   __shared__ uint32_t s_tile, s_last;
   __shared__ double s_red[kWarps][kMaxRec];
   __shared__ double s_tot[kMaxRec];
+  __shared__ double s_grp[kThreads / 16][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&s.ctl->scan_counter, 1u);
   __syncthreads();
@@ -462,10 +463,18 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (have_rec && tid >= 1 && tid < R) {
+  if (have_rec) {  // per-CTA partials -> totals: 16 groups of 16 threads, fixed order (deterministic)
+    const int r = tid & 15, grp = tid >> 4;
     double x = 0;
-    for (int c = 0; c < s.nscan; ++c) x += ((volatile double*)s.part)[(size_t)c * kMaxRec + tid];
-    s_tot[tid] = x;
+    if (r >= 1 && r < R)
+      for (int c = grp; c < s.nscan; c += kThreads / 16) x += ((volatile double*)s.part)[(size_t)c * kMaxRec + r];
+    s_grp[grp][r] = x;
+    __syncthreads();
+    if (tid >= 1 && tid < R) {
+      double y = 0;
+      for (int q = 0; q < kThreads / 16; ++q) y += s_grp[q][tid];
+      s_tot[tid] = y;
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -523,15 +532,28 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
   const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const PlanDev* pl = p.plan;
   SlotMap sm(pl, p.n_out_global);
-  if (J < p.ntiles_out) {
-    const uint32_t j0 = (uint32_t)(p.slot_base + J * p.tile_out);
-    // min b in [b_lo, b_hi) with slot_end(pb[b+1]) > j0
+  // one warp per output tile: 32-ary search for min b in [b_lo, b_hi) with slot_end(pb[b+1]) > j0
+  // (b_hi when there is none); ~4 dependent rounds of loads instead of ~19
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  for (int64_t tile = J >> 5; tile < p.ntiles_out; tile += nwarps) {
+    const uint32_t j0 = (uint32_t)(p.slot_base + tile * p.tile_out);
     int64_t lo = p.b_lo, hi = p.b_hi;
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (sm.slot_end(p.pb[mid + 1]) > j0) hi = mid; else lo = mid + 1;
+    while (hi > lo) {
+      const int64_t n = hi - lo, step = (n + 31) >> 5;
+      int64_t off = (int64_t)(lane + 1) * step;
+      off = off < n ? off : n;
+      const int64_t mid = lo + off - 1;
+      const bool pred = sm.slot_end(p.pb[mid + 1]) > j0;
+      const uint32_t m = __ballot_sync(0xffffffffu, pred);
+      if (m == 0) { lo = hi; break; }
+      const int f = __ffs(m) - 1;
+      int64_t offf = (int64_t)(f + 1) * step;
+      offf = offf < n ? offf : n;
+      hi = lo + offf - 1;
+      lo = lo + (int64_t)f * step;
     }
-    p.tile_start[J] = (int32_t)lo;
+    if (lane == 0) p.tile_start[tile] = (int32_t)lo;
   }
   for (int64_t b = p.b_lo + J; b <= p.b_hi; b += (int64_t)gridDim.x * kThreads) p.xb[b] = sm.block_pos(p.pb[b]);
   if (J < p.nscan) p.status[J] = 0ull;
@@ -1210,7 +1232,7 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
 }
 
 static int partition_grid(int64_t ntiles, int64_t nscan, int64_t nbound) {
-  int64_t nthreads = ntiles > nscan ? ntiles : nscan;
+  int64_t nthreads = ntiles * 32 > nscan ? ntiles * 32 : nscan;  // one warp per output tile
   if (nbound > nthreads) nthreads = nbound;  // one block boundary per thread (grid-stride beyond 4096 CTAs)
   const int g = cdiv(nthreads, kThreads);
   return g > 4096 ? 4096 : g;
