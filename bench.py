@@ -43,35 +43,75 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML (about 1 ms per sample) when
+    nvidia_ml_py is importable, else nvidia-smi (about 50 ms per sample)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.sm_max, self.reasons, self.source = [], None, set(), "nvidia-smi"
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self.h = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.split(",")]
+        if r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        self.sm_max = float(r[1])
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._sample_nvml() if self.h is not None else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.002 if self.h is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["clock sampling unavailable"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": self.source}
+
+
+def ncu_traffic(name, n_p):
+    """dram__bytes_read + dram__bytes_write of one pf_step_tile launch from the committed ncu capture
+    (profiles/traffic.json, written by tools/ncu_buckets.py) when it was taken at this N; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh).get(name)
+        return float(t["dram_bytes"]) if t and int(t["particles"]) == int(n_p) else None
+    except Exception:
+        return None
 
 
 def model_desc(pz, name):
@@ -260,7 +300,7 @@ def run_b200(args):
         prof = np.array([[dev_ms / K, float("nan"), float("nan")]])
         kernel_src = "whole step (kernel + collectives), device events"
     t_tile_ms = float(np.mean(prof[:, 0]))
-    alg_bytes = 2.0 * nx * 4 * n_p  # read the state once, write it once
+    alg_bytes = 2.0 * nx * 4 * n_p  # read the state once, write it once; the kernel also moves 4 B of u16 weights
     achieved = alg_bytes / (t_tile_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
@@ -295,14 +335,14 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name} bootstrap particle filter, N={n_p} particles per GPU (BASELINE.json configs[1])",
                    "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp32",
-                   "weights": "u64 fixed point", "resampler": "systematic (canonical PZ-SYS-256)",
+                   "weights": "u16 fixed point per particle, u64 block prefix", "resampler": "systematic (canonical PZ-SYS-256/q16)",
                    "l2": "inputs exceed L2 (state %.0f MB per buffer)" % (nx * 4 * n_p / 1e6), "wall_s_timed": wall},
         "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 144,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "pf_step_tile", "peak_source": peak_src,
+                     "traffic": ncu_traffic(name, n_p) if world == 1 else None, "kernel": "pf_step_tile", "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": t_tile_ms, "kernel_ms_source": kernel_src,
                      "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
                                          "pf_partition": float(np.mean(prof[:, 2]))}},

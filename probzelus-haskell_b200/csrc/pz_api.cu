@@ -172,6 +172,7 @@ struct pz_filter {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t sgraph[2] = {nullptr, nullptr};  // sharded: one captured step (kernels + NCCL) per buffer parity
   float* h_obs = nullptr;            // pinned [kObsRing][PZ_MAX_NY]
   pz_step_summary* h_summ = nullptr; // pinned [kObsRing]
   float* d_obs = nullptr;
@@ -188,8 +189,7 @@ struct pz_filter {
   int32_t* ebbuf[2] = {nullptr, nullptr};
   uint64_t* pbxbuf = nullptr;
   uint64_t* xbbuf = nullptr;
-  int32_t* h_table = nullptr;        // pinned [2*world]
-  int64_t last_migrated = 0;
+  int32_t* warm = nullptr;           // sharded: scratch of the NCCL peer warm-up
   // multi-target tracker
   bool is_mtt = false;
   uint32_t* mtt_s[2] = {nullptr, nullptr};   // particle records, double-buffered
@@ -252,17 +252,18 @@ void free_filter(pz_filter* f) {
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   if (f->graph) cudaGraphExecDestroy(f->graph);
+  for (int i = 0; i < 2; ++i) if (f->sgraph[i]) cudaGraphExecDestroy(f->sgraph[i]);
   if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
   StepArgs& a = f->a;
   cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->qbuf[0]); cudaFree(f->qbuf[1]); cudaFree(f->xbbuf); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
   cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
-  cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec); cudaFree(a.shard_table);
+  cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec);
+  cudaFree(f->warm);
   cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow);
   if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
   f->g.release();
   if (f->h_obs) cudaFreeHost(f->h_obs);
   if (f->h_summ) cudaFreeHost(f->h_summ);
-  if (f->h_table) cudaFreeHost(f->h_table);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
   if (f->stream) cudaStreamDestroy(f->stream);
@@ -326,76 +327,51 @@ int pending_ancestors(pz_filter* f, int* launches) {
 }
 
 // ---- sharded filter: everything between two step kernels ---------------------------------------
-// Host-side halo plan (pure function, also exported for the CPU tests): which of `src`'s blocks
-// does `dst` need, given the global block holding the ancestor of dst's first / last slot.
-inline void halo_range(int64_t need_lo, int64_t need_hi, int64_t nb, int src, int64_t* lo, int64_t* hi) {
-  const int64_t s0 = (int64_t)src * nb, s1 = s0 + nb;
-  *lo = need_lo > s0 ? need_lo : s0;
-  *hi = (need_hi + 1) < s1 ? (need_hi + 1) : s1;
-  if (*hi < *lo) *hi = *lo;
-}
-
-// emax all-reduce -> scan -> all-gather -> plan -> boundary table -> halo exchange -> partition.
-// `delta` = 1 after a step kernel, 0 for the initial population.
+// emax all-reduce -> scan -> all-gather -> plan (+ margin check) -> fixed-margin halo exchange with the
+// two neighbours -> partition.  No host synchronisation: the sequence is stream-ordered (and captured
+// in a CUDA graph per buffer parity).  `delta` = 1 after a step kernel, 0 for the initial population.
+// A rank whose ancestors reach beyond the margins is reported by every rank in the step summary
+// (n_migrated = -1 -> PZ_ECAPACITY); migration volume is the slots whose ancestor lives on a neighbour.
 int sharded_advance(pz_filter* f, int delta, int* launches) {
   StepArgs& a = f->a;
   const int R = a.world, me = a.rank;
-  const int64_t nb = a.nblk;
+  const int64_t nb = a.nblk, m = f->hb;
   cudaStream_t s = f->stream;
   const int which = (int)((f->t + (uint32_t)delta) & 1u);  // buffer of the population just produced
   PZ_NCCL(g_nccl.AllReduce(&a.ctl->emax_acc, &a.ctl->emax_acc, 1, ncclInt32, ncclMax, f->comm, s));
   *launches += launch_scan_only(a, delta, s);
   PZ_NCCL(g_nccl.AllGather(a.shard_rec + (size_t)me * kShardRec, a.shard_rec, kShardRec, ncclUint64, f->comm, s));
   *launches += launch_plan_sharded(a, delta, s);
-  PZ_NCCL(g_nccl.AllReduce(a.shard_table, a.shard_table, 2 * R, ncclInt32, ncclMax, f->comm, s));
-  PZ_CUDA(cudaMemcpyAsync(f->h_table, a.shard_table, 2 * R * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  PZ_CUDA(cudaStreamSynchronize(s));
-  for (int q = 0; q < 2 * R; ++q)
-    if (f->h_table[q] < 0) {
-      f->t += (uint32_t)delta;  // keep the host mirror in step with nothing: the filter is dead
-      return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight on every rank", f->t);
-    }
-  const int64_t need_lo = f->h_table[me], need_hi = f->h_table[R + me];
-  const int64_t own0 = (int64_t)me * nb;
-  const int64_t ext_lo = need_lo - own0 < 0 ? need_lo - own0 : 0;             // <= 0
-  const int64_t ext_hi = need_hi + 1 - own0 > nb ? need_hi + 1 - own0 : nb;   // >= nb
-  if (-ext_lo > f->hb || ext_hi - nb > f->hb)
-    return fail(PZ_ECAPACITY, "rank %d needs %lld + %lld halo blocks but the capacity is %lld (set PZ_HALO_BLOCKS)", me,
-                (long long)-ext_lo, (long long)(ext_hi - nb), (long long)f->hb);
   float* x = a.X[which];
   uint16_t* q = a.Q[which];
   int32_t* eb = a.eb[which];
   uint64_t* pbx = const_cast<uint64_t*>(a.pbx);
-  int64_t migrated = 0;
   PZ_NCCL(g_nccl.GroupStart());
-  for (int peer = 0; peer < R; ++peer) {
-    if (peer == me) continue;
-    int64_t lo, hi;
-    halo_range(f->h_table[peer], f->h_table[R + peer], nb, me, &lo, &hi);  // my blocks that `peer` needs
-    if (hi > lo) {
-      const int64_t b0 = lo - own0, cnt = hi - lo;
-      for (int d = 0; d < a.model.nx; ++d)
-        PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld + b0 * kBlk, cnt * kBlk, ncclFloat32, peer, f->comm, s));
-      PZ_NCCL(g_nccl.Send(q + b0 * kBlk, cnt * kBlk * 2, ncclUint8, peer, f->comm, s));
-      PZ_NCCL(g_nccl.Send(eb + b0, cnt, ncclInt32, peer, f->comm, s));
-      PZ_NCCL(g_nccl.Send(pbx + b0, cnt + 1, ncclUint64, peer, f->comm, s));
+  if (me > 0) {  // my first m blocks -> the right halo of rank me-1; its last m blocks -> my left halo
+    for (int d = 0; d < a.model.nx; ++d) {
+      PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld, m * kBlk, ncclFloat32, me - 1, f->comm, s));
+      PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld - m * kBlk, m * kBlk, ncclFloat32, me - 1, f->comm, s));
     }
-    halo_range(need_lo, need_hi, nb, peer, &lo, &hi);  // `peer`'s blocks that I need
-    if (hi > lo) {
-      const int64_t b0 = lo - own0, cnt = hi - lo;  // b0 < 0 (left halo) or >= nb (right halo)
-      for (int d = 0; d < a.model.nx; ++d)
-        PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld + b0 * kBlk, cnt * kBlk, ncclFloat32, peer, f->comm, s));
-      PZ_NCCL(g_nccl.Recv(q + b0 * kBlk, cnt * kBlk * 2, ncclUint8, peer, f->comm, s));
-      PZ_NCCL(g_nccl.Recv(eb + b0, cnt, ncclInt32, peer, f->comm, s));
-      // a left-halo range ends where my own prefix starts (same value), a right-halo range starts there
-      PZ_NCCL(g_nccl.Recv(pbx + b0, cnt + 1, ncclUint64, peer, f->comm, s));
-      migrated += cnt * kBlk;
+    PZ_NCCL(g_nccl.Send(q, m * kBlk * 2, ncclUint8, me - 1, f->comm, s));
+    PZ_NCCL(g_nccl.Recv(q - m * kBlk, m * kBlk * 2, ncclUint8, me - 1, f->comm, s));
+    PZ_NCCL(g_nccl.Send(eb, m, ncclInt32, me - 1, f->comm, s));
+    PZ_NCCL(g_nccl.Recv(eb - m, m, ncclInt32, me - 1, f->comm, s));
+    PZ_NCCL(g_nccl.Send(pbx + 1, m, ncclUint64, me - 1, f->comm, s));       // pbx[1 .. m]; pbx[0] equals its pbx[nblk]
+    PZ_NCCL(g_nccl.Recv(pbx - m, m, ncclUint64, me - 1, f->comm, s));       // its pbx[nblk-m .. nblk-1]
+  }
+  if (me + 1 < R) {
+    for (int d = 0; d < a.model.nx; ++d) {
+      PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld + (nb - m) * kBlk, m * kBlk, ncclFloat32, me + 1, f->comm, s));
+      PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld + nb * kBlk, m * kBlk, ncclFloat32, me + 1, f->comm, s));
     }
+    PZ_NCCL(g_nccl.Send(q + (nb - m) * kBlk, m * kBlk * 2, ncclUint8, me + 1, f->comm, s));
+    PZ_NCCL(g_nccl.Recv(q + nb * kBlk, m * kBlk * 2, ncclUint8, me + 1, f->comm, s));
+    PZ_NCCL(g_nccl.Send(eb + (nb - m), m, ncclInt32, me + 1, f->comm, s));
+    PZ_NCCL(g_nccl.Recv(eb + nb, m, ncclInt32, me + 1, f->comm, s));
+    PZ_NCCL(g_nccl.Send(pbx + (nb - m), m, ncclUint64, me + 1, f->comm, s));
+    PZ_NCCL(g_nccl.Recv(pbx + nb + 1, m, ncclUint64, me + 1, f->comm, s));
   }
   PZ_NCCL(g_nccl.GroupEnd());
-  f->last_migrated = migrated;
-  a.b_lo = ext_lo;
-  a.b_hi = ext_hi;
   *launches += launch_partition_ext(a, fused_tile_out(a.model.nx), delta, s);
   PZ_CUDA(cudaGetLastError());
   return PZ_OK;
@@ -404,10 +380,15 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
 int enqueue_step(pz_filter* f) {
   StepArgs& a = f->a;
   if (a.world > 1) {
-    int n = launch_tile_only(a, f->stream);
-    int rc = sharded_advance(f, 1, &n);
-    f->last_launches += n;
-    if (rc) return rc;
+    if (f->sgraph[f->t & 1u]) {
+      PZ_CUDA(cudaGraphLaunch(f->sgraph[f->t & 1u], f->stream));
+      f->last_launches += f->launches_per_step;
+    } else {
+      int n = launch_tile_only(a, f->stream);
+      int rc = sharded_advance(f, 1, &n);
+      f->last_launches += n;
+      if (rc) return rc;
+    }
   } else if (a.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
     int n = 0;
     int rc = pending_ancestors(f, &n);
@@ -586,9 +567,12 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   const int to = fused_tile_out(model->nx);
   a.ntiles_out = (int32_t)((a.n_local + to - 1) / to);
   if (world > 1) {
-    int64_t hb = a.nblk / 8 > 64 ? a.nblk / 8 : 64;
+    // halo margin exchanged with each neighbour every step: nblk/32 clamped to [64, 2048] blocks
+    int64_t hb = a.nblk / 32;
+    hb = hb < 64 ? 64 : (hb > 2048 ? 2048 : hb);
     if (const char* e = getenv("PZ_HALO_BLOCKS")) hb = atoll(e) > 0 ? atoll(e) : hb;
     f->hb = hb < a.nblk ? hb : a.nblk;
+    a.margin = f->hb;
   }
   const int64_t H = f->hb * kBlk;
   a.ld = round_up(a.n_local, kPad) + 2 * H;
@@ -613,13 +597,12 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
     PZ_TRY(cudaMalloc(&f->pbxbuf, (a.nblk + 2 * f->hb + 8) * sizeof(uint64_t)));
     a.pbx = f->pbxbuf + f->hb;
     PZ_TRY(cudaMalloc(&a.shard_rec, (size_t)world * kShardRec * sizeof(uint64_t)));
-    PZ_TRY(cudaMalloc(&a.shard_table, 2 * world * sizeof(int32_t)));
-    PZ_TRY(cudaMallocHost(&f->h_table, 2 * world * sizeof(int32_t)));
+    PZ_TRY(cudaMalloc(&f->warm, 2 * sizeof(int32_t)));
   } else {
     a.pbx = a.pb;
   }
-  a.b_lo = 0;
-  a.b_hi = a.nblk;
+  a.b_lo = rank > 0 ? -f->hb : 0;                       // fixed halo-extended block range of a sharded filter
+  a.b_hi = a.nblk + (rank + 1 < world ? f->hb : 0);
   PZ_TRY(cudaMalloc(&f->xbbuf, (a.nblk + 2 * f->hb + 8) * sizeof(uint64_t)));
   a.xb = f->xbbuf + f->hb;
   PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
@@ -648,8 +631,9 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
       bool ok = g_nccl.GroupStart() == ncclSuccess;
       for (int peer = 0; peer < world && ok; ++peer) {
         if (peer == rank) continue;
-        ok = g_nccl.Send(a.shard_table, 1, ncclInt32, peer, f->comm, f->stream) == ncclSuccess &&
-             g_nccl.Recv(a.shard_table + 1, 1, ncclInt32, peer, f->comm, f->stream) == ncclSuccess;
+        if (peer != rank - 1 && peer != rank + 1) continue;  // only neighbours ever exchange halos
+        ok = g_nccl.Send(f->warm, 1, ncclInt32, peer, f->comm, f->stream) == ncclSuccess &&
+             g_nccl.Recv(f->warm + 1, 1, ncclInt32, peer, f->comm, f->stream) == ncclSuccess;
       }
       ok = (g_nccl.GroupEnd() == ncclSuccess) && ok;
       if (!ok) { int c = fail(PZ_ENCCL, "NCCL peer warm-up failed"); free_filter(f); return c; }
@@ -662,6 +646,28 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   }
   PZ_TRY(cudaGetLastError());
   PZ_TRY(cudaStreamSynchronize(f->stream));
+  if (world > 1 && !getenv("PZ_NO_SHARD_GRAPH")) {
+    // one captured graph per buffer parity: step kernel, collectives, halo exchange (NCCL calls are capturable);
+    // a failed capture leaves the eager stream-ordered path in place
+    const uint32_t t_save = f->t;
+    for (int par = 0; par < 2; ++par) {
+      cudaGraph_t graph = nullptr;
+      f->t = (uint32_t)par;  // only the parity matters for the buffers named in the captured calls
+      bool ok = cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      int n = 0;
+      if (ok) {
+        n = launch_tile_only(a, f->stream);
+        ok = sharded_advance(f, 1, &n) == PZ_OK;
+        ok = (cudaStreamEndCapture(f->stream, &graph) == cudaSuccess) && ok && graph;
+      }
+      if (ok) ok = cudaGraphInstantiate(&f->sgraph[par], graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (!ok) { cudaGetLastError(); if (f->sgraph[par]) { cudaGraphExecDestroy(f->sgraph[par]); } f->sgraph[0] = f->sgraph[1] = nullptr; break; }
+      f->launches_per_step = n;
+    }
+    f->t = t_save;
+    if (f->sgraph[0] && !f->sgraph[1]) { cudaGraphExecDestroy(f->sgraph[0]); f->sgraph[0] = nullptr; }
+  }
   // one captured graph serves every systematic step (the step index lives in ctl->t)
   if (world == 1 && a.resampler == PZ_RESAMPLE_SYSTEMATIC) {
     cudaGraph_t graph = nullptr;
@@ -769,6 +775,13 @@ int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_global, uint
 /* Host-side halo plan of the sharded filter (pure function; CPU tests drive it over gloo).
  * need_lo[q] / need_hi[q]: global block holding the ancestor of rank q's first / last slot.
  * out[2*p], out[2*p+1]: global block range [lo, hi) of rank `src` that rank `dst` must receive. */
+static inline void halo_range(int64_t need_lo, int64_t need_hi, int64_t nb, int src, int64_t* lo, int64_t* hi) {
+  const int64_t s0 = (int64_t)src * nb, s1 = s0 + nb;
+  *lo = need_lo > s0 ? need_lo : s0;
+  *hi = (need_hi + 1) < s1 ? (need_hi + 1) : s1;
+  if (*hi < *lo) *hi = *lo;
+}
+
 int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_rank, int32_t src, int64_t* lo, int64_t* hi) {
   if (!lo || !hi || blocks_per_rank < 1 || src < 0) return fail(PZ_EINVAL, "bad argument");
   halo_range(need_lo, need_hi, blocks_per_rank, src, lo, hi);
@@ -801,9 +814,10 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
   cudaEventElapsedTime(&ms, f->ev0, f->ev1);
   f->last_ms = ms;
   pz_step_summary& s = f->h_summ[t0 % kObsRing];
-  s.n_migrated = f->last_migrated;
   if (out) *out = s;
   if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t0);
+  if (s.n_migrated < 0)
+    return fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)", t0, (long long)f->hb);
   return PZ_OK;
 }
 
@@ -861,6 +875,9 @@ int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_
       if (out) out[done + i] = s;
       if (s.total_weight == 0 && status == PZ_OK)
         status = fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", (unsigned)(t0 + i));
+      if (s.n_migrated < 0 && status == PZ_OK)
+        status = fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)",
+                      (unsigned)(t0 + i), (long long)f->hb);
     }
     done += k;
   }

@@ -297,6 +297,7 @@ struct ScanArgs {
   int32_t world;
   int32_t rank;
   u64* shard_rec;  // sharded: this rank's slot of the all-gathered record
+  int64_t margin;  // sharded: halo margin in blocks (the record carries the prefix at both margin edges)
 };
 
 __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint32_t U) {
@@ -503,6 +504,10 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
         r[3 + d] = (u64)__double_as_longlong((have_rec && d < s.nx) ? pl->sx[d] : 0.0);
         r[3 + PZ_MAX_NX + d] = (u64)__double_as_longlong((have_rec && d < s.nx) ? pl->sxx[d] : 0.0);
       }
+      // local prefix where the margin this rank sends to its left / right neighbour ends / begins
+      const int64_t m = s.margin < s.nblk ? s.margin : s.nblk;
+      r[16] = ((volatile u64*)s.pb)[m];
+      r[17] = ((volatile u64*)s.pb)[s.nblk - m];
     }
   }
 }
@@ -1126,7 +1131,7 @@ __global__ void __launch_bounds__(kThreads) pf_gather_thin(StepArgs a, const int
 }
 
 // ------------------------------------------------------------------------------------------
-// sharded filter: plan from the all-gathered rank records, absolute prefixes, boundary table
+// sharded filter: plan from the all-gathered rank records, absolute prefixes, margin check
 // ------------------------------------------------------------------------------------------
 struct ShardPlanArgs {
   PlanDev* plan;
@@ -1135,12 +1140,15 @@ struct ShardPlanArgs {
   const u64* pb;       // local prefix [nblk+1]
   u64* pbx;            // absolute prefix, own entries [0, nblk]
   pz_step_summary* summ;
-  int64_t nblk, n_global;
+  int64_t nblk, n_global, n_local;
   int32_t rank, world, nx, delta;
   uint64_t seed;
   double ll_const;
 };
 
+// Every rank evaluates, for EVERY rank q, whether the fixed halo margins (the last `margin` blocks of
+// rank q-1 and the first `margin` blocks of rank q+1) cover the ancestors of q's slots -- from the
+// gathered records alone, so that all ranks reach the same verdict without another collective.
 __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs p) {
   u64 base = 0, total = 0;
   for (int q = 0; q < p.world; ++q) {
@@ -1156,6 +1164,27 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
     const uint32_t U = philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)p.seed, (uint32_t)(p.seed >> 32)).x;
     pl->base = base;
     finalize_plan(pl, total, p.n_global, U);
+    int32_t overflow = 0;
+    int64_t migrated = 0;
+    if (total != 0) {
+      SlotMap sm(pl, p.n_global);
+      u64 bq = 0;  // CDF base of rank q
+      for (int q = 0; q < p.world; ++q) {
+        const u64* r = p.rec + (size_t)q * kShardRec;
+        const u64 tq = r[0];
+        // rank q's margins serve its neighbours: its first blocks rank q-1's last slots, its last blocks rank q+1's first slots
+        if (q > 0 && sm.slot_end(bq + r[16]) < (uint32_t)((int64_t)q * p.n_local)) overflow = 1;
+        if (q + 1 < p.world && sm.slot_end(bq + r[17]) > (uint32_t)((int64_t)(q + 1) * p.n_local)) overflow = 1;
+        if (q == p.rank) {  // my slots whose ancestor is not one of my particles
+          const int64_t j_lo = (int64_t)q * p.n_local, j_hi = j_lo + p.n_local;
+          const int64_t s0 = sm.slot_end(bq), s1 = sm.slot_end(bq + tq);
+          const int64_t a0 = (s0 < j_hi ? s0 : j_hi) - j_lo, a1 = j_hi - (s1 > j_lo ? s1 : j_lo);
+          migrated = (a0 > 0 ? a0 : 0) + (a1 > 0 ? a1 : 0);
+        }
+        bq += tq;
+      }
+    }
+    pl->shard_overflow = overflow;
     if (p.delta) {  // moment sums of all ranks, in rank order (every rank computes the same value)
       double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
       for (int q = 0; q < p.world; ++q) {
@@ -1169,29 +1198,11 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
       }
       pl->sw = sw; pl->sw2 = sw2;
       for (int d = 0; d < p.nx; ++d) { pl->sx[d] = sx[d]; pl->sxx[d] = sxx[d]; }
-      write_summary(pl, p.summ ? p.summ + (p.ctl->t % kObsRing) : nullptr, p.ctl->t, p.nx, p.n_global, p.ll_const);
+      pz_step_summary* o = p.summ ? p.summ + (p.ctl->t % kObsRing) : nullptr;
+      write_summary(pl, o, p.ctl->t, p.nx, p.n_global, p.ll_const);
+      if (o) o->n_migrated = overflow ? -1 : migrated;
     }
   }
-}
-
-// For every rank q: the global block holding the ancestor of its first slot (entry q) and of
-// its last slot (entry world + q), or -1 when that ancestor is not one of this rank's particles.
-__global__ void pf_boundary_table(const PlanDev* plan, const u64* pbx, int64_t nblk, int64_t n_local, int64_t n_global,
-                                  int32_t rank, int32_t world, int32_t* table) {
-  const int q = threadIdx.x;
-  if (q >= 2 * world) return;
-  SlotMap sm(plan, n_global);
-  const uint32_t j = (q < world) ? (uint32_t)(q * n_local) : (uint32_t)((q - world + 1) * n_local - 1);
-  int32_t res = -1;
-  if (!plan->degenerate && sm.slot_end(pbx[0]) <= j && j < sm.slot_end(pbx[nblk])) {
-    int64_t lo = 0, hi = nblk;  // min b with slot_end(pbx[b+1]) > j
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (sm.slot_end(pbx[mid + 1]) > j) hi = mid; else lo = mid + 1;
-    }
-    res = (int32_t)((int64_t)rank * nblk + lo);
-  }
-  table[q] = res;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1227,7 +1238,7 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   sc.nblk = a.nblk; sc.n_out_global = a.n_global; sc.n_local = a.n_local;
   sc.nscan = a.nscan; sc.nrec = a.ntiles_out; sc.nx = a.model.nx; sc.delta = delta;
   sc.explicit_U = 0; sc.U_value = 0; sc.seed = a.seed; sc.ll_const = a.ll_const; sc.world = a.world;
-  sc.rank = a.rank; sc.shard_rec = a.shard_rec;
+  sc.rank = a.rank; sc.shard_rec = a.shard_rec; sc.margin = a.margin;
   return sc;
 }
 
@@ -1332,12 +1343,11 @@ int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s) {
 }
 
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s) {
-  ShardPlanArgs p{a.plan, a.ctl, a.shard_rec, a.pb, const_cast<u64*>(a.pbx), a.summ, a.nblk, a.n_global,
+  ShardPlanArgs p{a.plan, a.ctl, a.shard_rec, a.pb, const_cast<u64*>(a.pbx), a.summ, a.nblk, a.n_global, a.n_local,
                   a.rank, a.world, a.model.nx, delta, a.seed, a.ll_const};
   int grid = cdiv(a.nblk + 1, kThreads);
   pf_plan_sharded<<<grid > 1024 ? 1024 : grid, kThreads, 0, s>>>(p);
-  pf_boundary_table<<<1, 64, 0, s>>>(a.plan, a.pbx, a.nblk, a.n_local, a.n_global, a.rank, a.world, a.shard_table);
-  return 2;
+  return 1;
 }
 
 int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s) { return partition(a, tile_out, delta, s); }
@@ -1357,7 +1367,7 @@ int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s
   sc.eb0 = g.eb; sc.eb1 = g.eb; sc.sb = g.sb; sc.pb = g.pb; sc.status = g.scan_status; sc.part = g.scan_part; sc.rec = nullptr;
   sc.plan = g.plan; sc.ctl = g.ctl; sc.summ = nullptr; sc.nblk = g.nblk; sc.n_out_global = g.n; sc.n_local = g.n;
   sc.nscan = g.nscan; sc.nrec = 0; sc.nx = 0; sc.delta = 0; sc.explicit_U = 1; sc.U_value = g.U; sc.seed = g.seed;
-  sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr;
+  sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr; sc.margin = 0;
   pf_scan_blocks<<<g.nscan, kThreads, 0, s>>>(sc);
   PartArgs pa{g.pb, g.xb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
   pf_partition<<<partition_grid(g.ntiles_out, g.nscan, g.nblk + 1), kThreads, 0, s>>>(pa);

@@ -58,6 +58,7 @@ struct PlanDev {
   int32_t L;            // bit length of T
   int32_t emax;         // global block exponent
   int32_t degenerate;   // 1 when T == 0
+  int32_t shard_overflow;  // sharded: 1 when some rank's ancestors reach beyond the halo margins
   uint32_t U;           // the uniform of the resample that will consume this plan
   float center[8];      // fp32 posterior mean: centring constants of the next moment sums
   double sw, sw2;       // sum w, sum w^2 at scale 2^emax
@@ -104,11 +105,11 @@ struct StepArgs {
   int32_t resampler;
   int32_t world;           // > 1: the plan is finalised by pf_plan_sharded after the all-gather
   int32_t rank;
-  uint64_t* shard_rec;     // sharded: [world][kShardRec] gathered {local_total, sw, sw2, sx[], sxx[]}
-  int32_t* shard_table;    // sharded: [2*world] global block of the ancestor of every rank's first / last slot
+  uint64_t* shard_rec;     // sharded: [world][kShardRec] gathered {local_total, sw, sw2, sx[], sxx[], prefix at the margin edges}
+  int64_t margin;          // sharded: halo margin in blocks exchanged with each neighbour every step
   LgDev model;
 };
-constexpr int kShardRec = 16;  // 64-bit words per rank in the all-gathered record
+constexpr int kShardRec = 18;  // 64-bit words per rank in the all-gathered record
 
 // Host-callable launchers (pz_kernels.cu).  Each returns the number of kernels it enqueued.
 int launch_init(const StepArgs& a, cudaStream_t s);
@@ -121,7 +122,7 @@ int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]);
 // sharded filter (one process per GPU): the step is split around the NCCL collectives
 int launch_tile_only(const StepArgs& a, cudaStream_t s);                 // fused step kernel
 int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s);      // after the emax all-reduce
-int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s);   // after the all-gather: plan, absolute prefix, summary, boundary table
+int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s);   // after the all-gather: plan, absolute prefix, summary, margin check
 int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s);  // after the halo exchange
 
 // Generic (stored log-weight) path: standalone resampler, ancestor taps, visualiser read.

@@ -1,9 +1,10 @@
 """The N > 1 path: particles sharded over ranks with a GLOBAL systematic resample.
 
 CPU (gloo, world_size 2): the sharding protocol -- block statistics per rank, all-reduce of the
-block exponent, all-gather of rank totals, boundary table, halo plan (pz_shard_halo_range from
-libpzgpu.so) and halo exchange -- restated with exact Python integers over torch.distributed,
-must reproduce the single-process oracle's ancestors bit for bit.
+block exponent, all-gather of rank records (total + prefix at the margin edges), the margin check
+every rank evaluates for every rank, and the fixed-margin halo exchange with the two neighbours --
+restated with exact Python integers over torch.distributed, must reproduce the single-process
+oracle's ancestors bit for bit.
 
 GPU (-m gpu, needs >= 2 devices): the CUDA/NCCL implementation on 2 ranks equals the
 single-GPU run at the same seed bit for bit (counter-based RNG keyed on the global slot)."""
@@ -24,6 +25,7 @@ def _free_port():
 
 
 GUARD = 16
+MARGIN = 8   # halo margin in blocks of the protocol test (16 blocks per rank)
 
 
 def _block_weights(lw32):
@@ -80,44 +82,48 @@ def _gloo_worker(rank, world, port, n_global, seed, ret):
     L = T.bit_length(); rho = ((n_global << (32 + L)) // T) + 1
     lam = rho.bit_length() - 30; Mq = (rho >> lam) + 1; h0 = L - GUARD - lam
     pbx = [base + v for v in pb]
-    # (3) boundary table: global block of the ancestor of every rank's first / last slot
-    table = torch.full((2 * world,), -1, dtype=torch.int64)
-    for qi in range(2 * world):
-        j = qi * n_local if qi < world else (qi - world + 1) * n_local - 1
-        if _slot_end(pbx[0], rho, L, U, n_global) <= j < _slot_end(pbx[nb], rho, L, U, n_global):
-            b = next(b for b in range(nb) if _slot_end(pbx[b + 1], rho, L, U, n_global) > j)
-            table[qi] = rank * nb + b
-    dist.all_reduce(table, op=dist.ReduceOp.MAX)
-    need_lo, need_hi = int(table[rank]), int(table[world + rank])
-    # (4) halo plan from the C library + exchange (weights, block exponents, absolute prefixes)
+    # (3) margin check from the gathered records alone (every rank reaches the same verdict):
+    #     rank q sends its first M blocks to q-1 and its last M blocks to q+1
+    M = MARGIN
+    rec = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(rec, torch.tensor([pb[-1], pb[min(M, nb)], pb[nb - min(M, nb)]], dtype=torch.int64))
+    overflow, bq = False, 0
+    for qi in range(world):
+        tq, p_first, p_last = (int(v) for v in rec[qi])
+        if qi > 0 and _slot_end(bq + p_first, rho, L, U, n_global) < qi * n_local:
+            overflow = True
+        if qi + 1 < world and _slot_end(bq + p_last, rho, L, U, n_global) > (qi + 1) * n_local:
+            overflow = True
+        bq += tq
+    assert not overflow
+    s0, s1 = _slot_end(pbx[0], rho, L, U, n_global), _slot_end(pbx[nb], rho, L, U, n_global)
+    j_lo, j_hi = rank * n_local, (rank + 1) * n_local
+    migrated = max(0, min(s0, j_hi) - j_lo) + max(0, j_hi - max(s1, j_lo))
+    # (4) fixed-margin halo exchange with the two neighbours (weights, block exponents, absolute prefixes)
     ext = {}  # global block -> (q[256], eb, pbx_start, pbx_end)
     for b in range(nb):
         ext[rank * nb + b] = (q_loc[b * BLK:(b + 1) * BLK], int(eb[b]), pbx[b], pbx[b + 1])
-    reqs = []
-    recv_bufs = []
-    for peer in range(world):
-        if peer == rank:
+
+    def pack(blocks):
+        return torch.tensor(np.concatenate([np.concatenate([ext[gb][0].astype(np.float64), [ext[gb][1], ext[gb][2], ext[gb][3]]])
+                                            for gb in blocks]))
+    reqs, recv_bufs = [], []
+    for peer, mine_blocks, theirs in ((rank - 1, range(rank * nb, rank * nb + M), range(rank * nb - M, rank * nb)),
+                                      (rank + 1, range((rank + 1) * nb - M, (rank + 1) * nb), range((rank + 1) * nb, (rank + 1) * nb + M))):
+        if peer < 0 or peer >= world:
             continue
-        lo, hi = pz.shard_halo_range(int(table[peer]), int(table[world + peer]), nb, rank)  # my blocks for peer
-        if hi > lo:
-            pay = torch.tensor(np.concatenate([np.concatenate([ext[gb][0].astype(np.float64), [ext[gb][1], ext[gb][2], ext[gb][3]]])
-                                               for gb in range(lo, hi)]))
-            reqs.append(dist.isend(pay, peer))
-        lo, hi = pz.shard_halo_range(need_lo, need_hi, nb, peer)  # peer's blocks for me
-        if hi > lo:
-            buf = torch.zeros((hi - lo) * (BLK + 3), dtype=torch.float64)
-            reqs.append(dist.irecv(buf, peer)); recv_bufs.append((lo, hi, buf))
+        reqs.append(dist.isend(pack(mine_blocks), peer))
+        buf = torch.zeros(M * (BLK + 3), dtype=torch.float64)
+        reqs.append(dist.irecv(buf, peer)); recv_bufs.append((theirs, buf))
     for r in reqs:
         r.wait()
-    migrated = 0
-    for lo, hi, buf in recv_bufs:
-        a = buf.numpy().reshape(hi - lo, BLK + 3)
-        for k, gb in enumerate(range(lo, hi)):
+    for blocks, buf in recv_bufs:
+        a = buf.numpy().reshape(M, BLK + 3)
+        for k, gb in enumerate(blocks):
             ext[gb] = (a[k, :BLK].astype(np.int64), int(a[k, BLK]), int(a[k, BLK + 1]), int(a[k, BLK + 2]))
-            migrated += BLK
+    need_lo, need_hi = min(ext), max(ext)
     # (5) resample my output slots from the (halo-extended) blocks
     anc = np.full(n_local, -1, dtype=np.int64)
-    j_lo, j_hi = rank * n_local, (rank + 1) * n_local
     for gb in range(need_lo, need_hi + 1):
         bq, ebb, P0, P1 = ext[gb]
         X0, X1 = _block_pos(P0, rho, L, U), _block_pos(P1, rho, L, U)
@@ -156,7 +162,7 @@ def test_sharding_protocol_gloo_world2():
     port = _free_port()
     mp.spawn(_gloo_worker, args=(2, port, 8192, 17, ret), nprocs=2, join=True)
     assert ret.get("ok"), dict(ret)
-    assert ret["migrated"] > 0  # the skewed weights force rank 0 to fetch blocks from rank 1
+    assert ret["migrated"] > 0  # the skewed weights make rank 0 take ancestors from rank 1's margin
 
 
 def test_halo_range_function(pz):

@@ -1,5 +1,10 @@
-"""Summarise an ncu report: key raw metrics + executed instructions per source line."""
-import csv, subprocess, sys
+"""Summarise an ncu report: key raw metrics + executed instructions per source line.
+
+    python tools/ncu_buckets.py REPORT.ncu-rep N_PARTICLES [TOP_LINES] [MODEL]
+
+With MODEL (rw1d / lg42 / lg63) the DRAM traffic of the captured launch is recorded in
+profiles/traffic.json, which bench.py reports as roofline.traffic when it runs at the same N."""
+import csv, json, os, subprocess, sys
 rep, nparticles = sys.argv[1], float(sys.argv[2])
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines())); h = rows[0]; r = rows[2]
@@ -14,6 +19,17 @@ for k in ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.s
           'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
           'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']:
     if k in h: print(f"{k:95s} {r[h.index(k)]} {rows[1][h.index(k)]}")
+if len(sys.argv) > 4:
+    def tobytes(k):
+        v, u = float(r[h.index(k)]), rows[1][h.index(k)].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json")
+    try: tj = json.load(open(tp))
+    except Exception: tj = {}
+    tj[sys.argv[4]] = {"particles": int(nparticles), "dram_bytes": tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum'),
+                       "dram_bytes_read": tobytes('dram__bytes_read.sum'), "dram_bytes_write": tobytes('dram__bytes_write.sum'),
+                       "kernel_us_under_ncu": float(r[h.index('gpu__time_duration.sum')]), "report": os.path.basename(rep)}
+    json.dump(tj, open(tp, "w"), indent=1, sort_keys=True)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 cur = None; per = {}; hdr = None
