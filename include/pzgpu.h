@@ -102,7 +102,9 @@ typedef struct pz_step_summary {
   double ess;               /* (sum w)^2 / sum w^2                                           */
   double mean[PZ_MAX_NX];
   double var[PZ_MAX_NX];
-  int64_t n_migrated;       /* particles fetched from other ranks this step (sharded only)   */
+  int64_t n_migrated;       /* sharded: this rank's output slots whose ancestor lives on another
+                               rank; -1 = some rank's ancestors reach beyond the halo margin
+                               (PZ_ECAPACITY, the same verdict on every rank)                 */
   int32_t e_max;            /* canonical resampler diagnostics: global block exponent        */
   int32_t reserved;
   uint64_t total_weight;    /* canonical fixed-point total T                                 */
@@ -128,9 +130,10 @@ PZ_API int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_globa
                              int device, int rank, int world, const void* nccl_unique_id,
                              pz_filter** out);
 
-/* Host-side halo plan of a sharded filter (pure function, no device work): the global block
- * range [lo, hi) of rank `src` that a rank must receive when the ancestors of its first and
- * last output slots live in global blocks need_lo and need_hi.                               */
+/* Halo arithmetic of a sharded filter (pure function, no device work): the global block
+ * range [lo, hi) of rank `src` that a rank needs when the ancestors of its first and last
+ * output slots live in global blocks need_lo and need_hi.  (The filter itself exchanges fixed
+ * margins with its two neighbours and checks on the device that they cover this range.)     */
 PZ_API int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_rank, int32_t src,
                                int64_t* lo, int64_t* hi);
 
