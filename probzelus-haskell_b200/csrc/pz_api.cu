@@ -190,6 +190,9 @@ struct pz_filter {
   uint64_t* pbxbuf = nullptr;
   uint64_t* xbbuf = nullptr;
   int32_t* warm = nullptr;           // sharded: scratch of the NCCL peer warm-up
+  Mailbox* mbox = nullptr;           // sharded: this rank's mailbox (peer-memory exchange)
+  ShardP2P* d_p2p = nullptr;
+  std::vector<void*> ipc_opened;     // peer mappings to close
   // multi-target tracker
   bool is_mtt = false;
   uint32_t* mtt_s[2] = {nullptr, nullptr};   // particle records, double-buffered
@@ -259,6 +262,8 @@ void free_filter(pz_filter* f) {
   cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
   cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec);
   cudaFree(f->warm);
+  for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(f->mbox); cudaFree(f->d_p2p);
   cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow);
   if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
   f->g.release();
@@ -338,6 +343,13 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
   const int64_t nb = a.nblk, m = f->hb;
   cudaStream_t s = f->stream;
   const int which = (int)((f->t + (uint32_t)delta) & 1u);  // buffer of the population just produced
+  if (a.p2p) {  // peer-memory exchange inside the kernels: no collective call at all
+    *launches += launch_scan_only(a, delta, s);
+    *launches += launch_plan_sharded(a, delta, s);
+    *launches += launch_partition_ext(a, fused_tile_out(a.model.nx), delta, s);
+    PZ_CUDA(cudaGetLastError());
+    return PZ_OK;
+  }
   PZ_NCCL(g_nccl.AllReduce(&a.ctl->emax_acc, &a.ctl->emax_acc, 1, ncclInt32, ncclMax, f->comm, s));
   *launches += launch_scan_only(a, delta, s);
   PZ_NCCL(g_nccl.AllGather(a.shard_rec + (size_t)me * kShardRec, a.shard_rec, kShardRec, ncclUint64, f->comm, s));
@@ -521,6 +533,68 @@ int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summar
   return PZ_OK;
 }
 
+// Peer-memory exchange of a sharded filter: map every rank's mailbox and the two neighbours' particle
+// arrays with CUDA IPC (handles travel through one NCCL all-gather at creation).  All ranks must agree on
+// the outcome, so the verdict is all-reduced; on any failure the filter keeps the NCCL exchange.
+int setup_p2p(pz_filter* f) {
+  StepArgs& a = f->a;
+  const int R = a.world, me = a.rank;
+  if (getenv("PZ_SHARD_NCCL") || R > kMaxRanks) return PZ_OK;
+  struct Pack { cudaIpcMemHandle_t h[8]; };
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  Pack mine;
+  bool ok = cudaMalloc(&f->mbox, sizeof(Mailbox)) == cudaSuccess && cudaMemset(f->mbox, 0, sizeof(Mailbox)) == cudaSuccess;
+  void* bases[8] = {f->mbox, f->xbuf[0], f->xbuf[1], f->qbuf[0], f->qbuf[1], f->ebbuf[0], f->ebbuf[1], f->pbxbuf};
+  for (int i = 0; i < 8 && ok; ++i) ok = cudaIpcGetMemHandle(&mine.h[i], bases[i]) == cudaSuccess;
+  // all-gather of the handles (always executed: a collective every rank must enter)
+  unsigned char* d_all = nullptr;
+  std::vector<Pack> all((size_t)R);
+  if (cudaMalloc(&d_all, (size_t)R * sizeof(Pack)) != cudaSuccess) return fail(PZ_ECUDA, "cudaMalloc failed");
+  cudaMemcpy(d_all + (size_t)me * sizeof(Pack), &mine, sizeof(Pack), cudaMemcpyHostToDevice);
+  PZ_NCCL(g_nccl.AllGather(d_all + (size_t)me * sizeof(Pack), d_all, sizeof(Pack), ncclUint8, f->comm, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  PZ_CUDA(cudaMemcpy(all.data(), d_all, (size_t)R * sizeof(Pack), cudaMemcpyDeviceToHost));
+  cudaFree(d_all);
+  ShardP2P h{};
+  const int64_t H = f->hb * kBlk;
+  auto open = [&](const cudaIpcMemHandle_t& hd) -> void* {
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    f->ipc_opened.push_back(p);
+    return p;
+  };
+  for (int q = 0; q < R && ok; ++q) {
+    if (q == me) { h.mbox[q] = f->mbox; continue; }
+    h.mbox[q] = (Mailbox*)open(all[q].h[0]);
+    ok = h.mbox[q] != nullptr;
+  }
+  for (int side = 0; side < 2 && ok; ++side) {
+    const int q = side == 0 ? me - 1 : me + 1;
+    if (q < 0 || q >= R) continue;
+    void* p[8] = {};
+    for (int i = 1; i < 8 && ok; ++i) { p[i] = open(all[q].h[i]); ok = p[i] != nullptr; }
+    if (!ok) break;
+    for (int b = 0; b < 2; ++b) {
+      h.Xn[side][b] = (float*)p[1 + b] + H;
+      h.Qn[side][b] = (uint16_t*)p[3 + b] + H;
+      h.ebn[side][b] = (int32_t*)p[5 + b] + f->hb;
+    }
+    h.pbxn[side] = (uint64_t*)p[7] + f->hb;
+  }
+  if (ok) ok = cudaMalloc(&f->d_p2p, sizeof(ShardP2P)) == cudaSuccess &&
+               cudaMemcpy(f->d_p2p, &h, sizeof(ShardP2P), cudaMemcpyHostToDevice) == cudaSuccess;
+  // agreement: min over ranks of the local verdict
+  const int32_t verdict = ok ? 1 : 0;
+  PZ_CUDA(cudaMemcpy(f->warm, &verdict, sizeof(int32_t), cudaMemcpyHostToDevice));
+  PZ_NCCL(g_nccl.AllReduce(f->warm, f->warm, 1, ncclInt32, ncclMin, f->comm, f->stream));
+  int32_t agreed = 0;
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  PZ_CUDA(cudaMemcpy(&agreed, f->warm, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  cudaGetLastError();
+  if (agreed) a.p2p = f->d_p2p;
+  return PZ_OK;
+}
+
 int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank, int world,
                   const void* nccl_id, pz_filter** out) {
   if (!model || !out) return fail(PZ_EINVAL, "null argument");
@@ -638,6 +712,8 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
       ok = (g_nccl.GroupEnd() == ncclSuccess) && ok;
       if (!ok) { int c = fail(PZ_ENCCL, "NCCL peer warm-up failed"); free_filter(f); return c; }
     }
+    rc = setup_p2p(f);
+    if (rc) { free_filter(f); return rc; }
     int n = 0;
     rc = sharded_advance(f, 0, &n);
     if (rc) { free_filter(f); return rc; }
@@ -816,6 +892,7 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
   pz_step_summary& s = f->h_summ[t0 % kObsRing];
   if (out) *out = s;
   if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t0);
+  if (s.n_migrated == -2) return fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange", t0);
   if (s.n_migrated < 0)
     return fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)", t0, (long long)f->hb);
   return PZ_OK;

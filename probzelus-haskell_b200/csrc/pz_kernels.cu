@@ -73,6 +73,28 @@ __device__ __forceinline__ uint32_t warp_inclusive_max_u32(uint32_t v, int lane)
   }
   return v;
 }
+// system-scope flag traffic of the peer-memory exchange (sharded filter)
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// poll *p until pred(value); gives up after ~2 s (a dead peer must not hang the device)
+template <class Pred>
+__device__ __forceinline__ unsigned long long wait_sys(const unsigned long long* p, Pred pred, uint32_t* err) {
+  const long long t0 = clock64();
+  unsigned long long v = ld_sys(p);
+  while (!pred(v)) {
+    if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+    __nanosleep(64);
+    v = ld_sys(p);
+  }
+  __threadfence_system();
+  return v;
+}
 // 2^k as a float for k <= 0 (0 when it would underflow)
 __device__ __forceinline__ float exp2i(int k) { return k < -126 ? 0.0f : __int_as_float((127 + k) << 23); }
 // 2^k as a double (0 when it would underflow)
@@ -298,6 +320,7 @@ struct ScanArgs {
   int32_t rank;
   u64* shard_rec;  // sharded: this rank's slot of the all-gathered record
   int64_t margin;  // sharded: halo margin in blocks (the record carries the prefix at both margin edges)
+  const ShardP2P* p2p;  // sharded: exchange the block exponent through peer memory (nullptr: NCCL did it)
 };
 
 __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint32_t U) {
@@ -352,7 +375,27 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   if (tid == 0) s_tile = atomicAdd(&s.ctl->scan_counter, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
-  const int32_t emax = s.ctl->emax_acc;
+  int32_t emax = s.ctl->emax_acc;
+  if (s.p2p) {
+    // all-reduce(max) of the block exponent over peer memory: the first CTA stores this rank's value
+    // into every mailbox, every CTA polls its own mailbox for all ranks' values of this epoch
+    __shared__ int32_t s_emax;
+    const unsigned long long epoch = (unsigned long long)(s.ctl->t + (uint32_t)s.delta + 1u);
+    if (warp == 0) {
+      if (tile == 0 && lane < s.world) st_sys(&s.p2p->mbox[lane]->emax[s.rank], (epoch << 32) | (uint32_t)emax);
+      int32_t v = kNZero;
+      if (lane < s.world) {
+        const unsigned long long w = wait_sys(&s.p2p->mbox[s.rank]->emax[lane],
+                                              [epoch](unsigned long long x) { return (x >> 32) == epoch; }, &s.ctl->comm_error);
+        v = (int32_t)(uint32_t)w;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+      if (lane == 0) s_emax = v;
+    }
+    __syncthreads();
+    emax = s_emax;
+  }
   const int32_t* __restrict__ ebp = ((s.ctl->t + (uint32_t)s.delta) & 1u) ? s.eb1 : s.eb0;
 
   // ---- local scan of kScanItems block sums per thread
@@ -531,11 +574,22 @@ struct PartArgs {
   int32_t tile_out;
   int32_t nscan;
   int32_t delta;
+  const ShardP2P* p2p;  // sharded over peer memory: wait for the neighbours' halo stores first
+  int32_t rank, world;
 };
 
 __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
   const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const PlanDev* pl = p.plan;
+  if (p.p2p) {
+    if (threadIdx.x < 2) {
+      const int side = threadIdx.x;
+      const bool have = side == 0 ? p.rank > 0 : p.rank + 1 < p.world;
+      const unsigned long long epoch = pl->shard_epoch;
+      if (have) wait_sys(&p.p2p->mbox[p.rank]->halo_flag[side], [epoch](unsigned long long x) { return x == epoch; }, &p.ctl->comm_error);
+    }
+    __syncthreads();
+  }
   SlotMap sm(pl, p.n_out_global);
   // one warp per output tile: 32-ary search for min b in [b_lo, b_hi) with slot_end(pb[b+1]) > j0
   // (b_hi when there is none); ~4 dependent rounds of loads instead of ~19
@@ -1136,7 +1190,7 @@ __global__ void __launch_bounds__(kThreads) pf_gather_thin(StepArgs a, const int
 struct ShardPlanArgs {
   PlanDev* plan;
   CtlDev* ctl;
-  const u64* rec;      // [world][kShardRec]
+  u64* rec;            // [world][kShardRec]: gathered by NCCL, or filled here from the mailbox
   const u64* pb;       // local prefix [nblk+1]
   u64* pbx;            // absolute prefix, own entries [0, nblk]
   pz_step_summary* summ;
@@ -1144,25 +1198,95 @@ struct ShardPlanArgs {
   int32_t rank, world, nx, delta;
   uint64_t seed;
   double ll_const;
+  // peer-memory exchange (p2p != nullptr): records through the mailboxes, halo margins by peer stores
+  const ShardP2P* p2p;
+  const float* X[2];
+  const uint16_t* Q[2];
+  const int32_t* eb[2];
+  int64_t ld, margin;
 };
+
+__device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, int64_t gid, int64_t gsz) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (int64_t i = gid; i < n16; i += gsz) d[i] = s[i];
+}
 
 // Every rank evaluates, for EVERY rank q, whether the fixed halo margins (the last `margin` blocks of
 // rank q-1 and the first `margin` blocks of rank q+1) cover the ancestors of q's slots -- from the
 // gathered records alone, so that all ranks reach the same verdict without another collective.
+// With the peer-memory exchange this kernel is also the all-gather (CTA 0 stores this rank's record
+// into every mailbox, every CTA polls its own mailbox) and the halo exchange (all CTAs store the two
+// margins straight into the neighbours' halo regions; the last CTA to finish raises their flags).
 __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs p) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t epoch = p.ctl->t + (uint32_t)p.delta + 1u;
+  const u64* rec = p.rec;
+  if (p.p2p) {
+    Mailbox* mine = p.p2p->mbox[p.rank];
+    if (blockIdx.x == 0) {
+      for (int q = warp; q < p.world; q += kWarps) {
+        if (lane < kShardRec) st_sys(&p.p2p->mbox[q]->rec[p.rank][lane], p.rec[(size_t)p.rank * kShardRec + lane]);
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) st_sys(&p.p2p->mbox[q]->rec_flag[p.rank], (unsigned long long)epoch);
+      }
+    }
+    if (warp == 0)
+      for (int q = lane; q < p.world; q += 32)
+        wait_sys(&mine->rec_flag[q], [epoch](unsigned long long x) { return x == (unsigned long long)epoch; }, &p.ctl->comm_error);
+    __syncthreads();
+    rec = reinterpret_cast<const u64*>(&mine->rec[0][0]);
+  }
   u64 base = 0, total = 0;
   for (int q = 0; q < p.world; ++q) {
-    const u64 tq = p.rec[(size_t)q * kShardRec];
+    const u64 tq = ((const volatile u64*)rec)[(size_t)q * kShardRec];
     if (q < p.rank) base += tq;
     total += tq;
   }
-  const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  for (int64_t b = gid; b <= p.nblk; b += (int64_t)gridDim.x * kThreads) p.pbx[b] = base + p.pb[b];
+  const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
+  for (int64_t b = gid; b <= p.nblk; b += gsz) p.pbx[b] = base + p.pb[b];
+  if (p.p2p) {
+    // halo margins -> the neighbours' halo regions (their arrays have our layout): my first m blocks are the
+    // RIGHT halo of rank-1, my last m blocks the LEFT halo of rank+1
+    const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
+    const int64_t m = p.margin, nb = p.nblk;
+    if (p.rank > 0) {
+      for (int d = 0; d < p.nx; ++d)
+        copy16(p.p2p->Xn[0][which] + (size_t)d * p.ld + nb * kBlk, p.X[which] + (size_t)d * p.ld, m * kBlk / 4, gid, gsz);
+      copy16(p.p2p->Qn[0][which] + nb * kBlk, p.Q[which], m * kBlk / 8, gid, gsz);
+      for (int64_t i = gid; i < m; i += gsz) {
+        p.p2p->ebn[0][which][nb + i] = p.eb[which][i];
+        p.p2p->pbxn[0][nb + 1 + i] = base + p.pb[1 + i];
+      }
+    }
+    if (p.rank + 1 < p.world) {
+      for (int d = 0; d < p.nx; ++d)
+        copy16(p.p2p->Xn[1][which] + (size_t)d * p.ld - m * kBlk, p.X[which] + (size_t)d * p.ld + (nb - m) * kBlk, m * kBlk / 4, gid, gsz);
+      copy16(p.p2p->Qn[1][which] - m * kBlk, p.Q[which] + (nb - m) * kBlk, m * kBlk / 8, gid, gsz);
+      for (int64_t i = gid; i < m; i += gsz) {
+        p.p2p->ebn[1][which][i - m] = p.eb[which][nb - m + i];
+        p.p2p->pbxn[1][i - m] = base + p.pb[nb - m + i];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      Mailbox* mine = p.p2p->mbox[p.rank];
+      if (atomicAdd(&mine->push_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        __threadfence_system();
+        mine->push_done = 0ull;
+        if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->halo_flag[1], (unsigned long long)epoch);
+        if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->halo_flag[0], (unsigned long long)epoch);
+      }
+    }
+  }
   if (gid == 0) {
     PlanDev* pl = p.plan;
     const uint32_t t_next = p.ctl->t + (uint32_t)p.delta;
     const uint32_t U = philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)p.seed, (uint32_t)(p.seed >> 32)).x;
     pl->base = base;
+    pl->shard_epoch = epoch;
     finalize_plan(pl, total, p.n_global, U);
     int32_t overflow = 0;
     int64_t migrated = 0;
@@ -1170,7 +1294,7 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
       SlotMap sm(pl, p.n_global);
       u64 bq = 0;  // CDF base of rank q
       for (int q = 0; q < p.world; ++q) {
-        const u64* r = p.rec + (size_t)q * kShardRec;
+        const volatile u64* r = (const volatile u64*)rec + (size_t)q * kShardRec;
         const u64 tq = r[0];
         // rank q's margins serve its neighbours: its first blocks rank q-1's last slots, its last blocks rank q+1's first slots
         if (q > 0 && sm.slot_end(bq + r[16]) < (uint32_t)((int64_t)q * p.n_local)) overflow = 1;
@@ -1184,11 +1308,12 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
         bq += tq;
       }
     }
+    if (p.ctl->comm_error) overflow = 2;
     pl->shard_overflow = overflow;
     if (p.delta) {  // moment sums of all ranks, in rank order (every rank computes the same value)
       double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
       for (int q = 0; q < p.world; ++q) {
-        const u64* r = p.rec + (size_t)q * kShardRec;
+        const volatile u64* r = (const volatile u64*)rec + (size_t)q * kShardRec;
         sw += __longlong_as_double((long long)r[1]);
         sw2 += __longlong_as_double((long long)r[2]);
         for (int d = 0; d < p.nx; ++d) {
@@ -1200,7 +1325,7 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
       for (int d = 0; d < p.nx; ++d) { pl->sx[d] = sx[d]; pl->sxx[d] = sxx[d]; }
       pz_step_summary* o = p.summ ? p.summ + (p.ctl->t % kObsRing) : nullptr;
       write_summary(pl, o, p.ctl->t, p.nx, p.n_global, p.ll_const);
-      if (o) o->n_migrated = overflow ? -1 : migrated;
+      if (o) o->n_migrated = overflow ? -(int64_t)overflow : migrated;
     }
   }
 }
@@ -1238,7 +1363,7 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   sc.nblk = a.nblk; sc.n_out_global = a.n_global; sc.n_local = a.n_local;
   sc.nscan = a.nscan; sc.nrec = a.ntiles_out; sc.nx = a.model.nx; sc.delta = delta;
   sc.explicit_U = 0; sc.U_value = 0; sc.seed = a.seed; sc.ll_const = a.ll_const; sc.world = a.world;
-  sc.rank = a.rank; sc.shard_rec = a.shard_rec; sc.margin = a.margin;
+  sc.rank = a.rank; sc.shard_rec = a.shard_rec; sc.margin = a.margin; sc.p2p = a.p2p;
   return sc;
 }
 
@@ -1251,8 +1376,10 @@ static int partition_grid(int64_t ntiles, int64_t nscan, int64_t nbound) {
 
 static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
   PartArgs pa{a.pbx, a.xb, a.b_lo, a.b_hi, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
-              a.ntiles_out, tile_out, a.nscan, delta};
-  pf_partition<<<partition_grid(a.ntiles_out, a.nscan, a.b_hi - a.b_lo + 1), kThreads, 0, s>>>(pa);
+              a.ntiles_out, tile_out, a.nscan, delta, a.p2p, a.rank, a.world};
+  int grid = partition_grid(a.ntiles_out, a.nscan, a.b_hi - a.b_lo + 1);
+  if (a.p2p && grid > 592) grid = 592;  // every CTA polls a flag: keep the whole grid resident
+  pf_partition<<<grid, kThreads, 0, s>>>(pa);
   return 1;
 }
 
@@ -1344,9 +1471,11 @@ int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s) {
 
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s) {
   ShardPlanArgs p{a.plan, a.ctl, a.shard_rec, a.pb, const_cast<u64*>(a.pbx), a.summ, a.nblk, a.n_global, a.n_local,
-                  a.rank, a.world, a.model.nx, delta, a.seed, a.ll_const};
+                  a.rank, a.world, a.model.nx, delta, a.seed, a.ll_const, a.p2p, {a.X[0], a.X[1]}, {a.Q[0], a.Q[1]},
+                  {a.eb[0], a.eb[1]}, a.ld, a.margin};
   int grid = cdiv(a.nblk + 1, kThreads);
-  pf_plan_sharded<<<grid > 1024 ? 1024 : grid, kThreads, 0, s>>>(p);
+  grid = grid > 592 ? 592 : grid;  // every CTA polls a flag: keep the whole grid resident (148 SMs x 4)
+  pf_plan_sharded<<<grid, kThreads, 0, s>>>(p);
   return 1;
 }
 
@@ -1367,9 +1496,10 @@ int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s
   sc.eb0 = g.eb; sc.eb1 = g.eb; sc.sb = g.sb; sc.pb = g.pb; sc.status = g.scan_status; sc.part = g.scan_part; sc.rec = nullptr;
   sc.plan = g.plan; sc.ctl = g.ctl; sc.summ = nullptr; sc.nblk = g.nblk; sc.n_out_global = g.n; sc.n_local = g.n;
   sc.nscan = g.nscan; sc.nrec = 0; sc.nx = 0; sc.delta = 0; sc.explicit_U = 1; sc.U_value = g.U; sc.seed = g.seed;
-  sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr; sc.margin = 0;
+  sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr; sc.margin = 0; sc.p2p = nullptr;
   pf_scan_blocks<<<g.nscan, kThreads, 0, s>>>(sc);
-  PartArgs pa{g.pb, g.xb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0};
+  PartArgs pa{g.pb, g.xb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0,
+              nullptr, 0, 1};
   pf_partition<<<partition_grid(g.ntiles_out, g.nscan, g.nblk + 1), kThreads, 0, s>>>(pa);
   return n + 2;
 }

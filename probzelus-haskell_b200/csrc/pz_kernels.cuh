@@ -58,7 +58,8 @@ struct PlanDev {
   int32_t L;            // bit length of T
   int32_t emax;         // global block exponent
   int32_t degenerate;   // 1 when T == 0
-  int32_t shard_overflow;  // sharded: 1 when some rank's ancestors reach beyond the halo margins
+  int32_t shard_overflow;  // sharded: 1 when some rank's ancestors reach beyond the halo margins, 2: a peer never answered
+  uint32_t shard_epoch;    // sharded: epoch of the exchange that produced this plan
   uint32_t U;           // the uniform of the resample that will consume this plan
   float center[8];      // fp32 posterior mean: centring constants of the next moment sums
   double sw, sw2;       // sum w, sum w^2 at scale 2^emax
@@ -72,8 +73,11 @@ struct CtlDev {
   int32_t emax_acc;       // atomicMax target of the kernel producing block statistics
   uint32_t scan_counter;  // dynamic tile ids of pf_scan_blocks
   uint32_t scan_done;     // "last CTA" counter of pf_scan_blocks
-  uint32_t pad[4];
+  uint32_t comm_error;    // sharded: a peer-memory wait timed out
+  uint32_t pad[3];
 };
+
+struct ShardP2P;  // peer-memory exchange of a sharded filter (below)
 
 struct StepArgs {
   float* X[2];
@@ -107,9 +111,30 @@ struct StepArgs {
   int32_t rank;
   uint64_t* shard_rec;     // sharded: [world][kShardRec] gathered {local_total, sw, sw2, sx[], sxx[], prefix at the margin edges}
   int64_t margin;          // sharded: halo margin in blocks exchanged with each neighbour every step
+  const ShardP2P* p2p;     // sharded: peer-memory exchange (nullptr: NCCL collectives between the kernels)
   LgDev model;
 };
-constexpr int kShardRec = 18;  // 64-bit words per rank in the all-gathered record
+constexpr int kShardRec = 18;
+constexpr int kMaxRanks = 32;
+
+// Peer-memory exchange of a sharded filter (one process per GPU, buffers mapped with CUDA IPC over
+// NVLink): every rank owns a mailbox its peers store into, and maps the halo regions of its two
+// neighbours.  The kernels of the step push with plain 64/128-bit peer stores + a system-scope
+// fence + an epoch flag, and poll their OWN memory; no collective library call is on the path.
+struct Mailbox {
+  unsigned long long emax[kMaxRanks];            // (epoch << 32) | block exponent of rank q
+  unsigned long long rec[kMaxRanks][kShardRec];  // rank q's record (pf_scan_blocks' last CTA)
+  unsigned long long rec_flag[kMaxRanks];        // epoch of rec[q]
+  unsigned long long halo_flag[2];               // epoch of my left / right halo (written by that neighbour)
+  unsigned long long push_done;                  // CTAs of pf_plan_sharded that finished their halo stores
+};
+struct ShardP2P {
+  Mailbox* mbox[kMaxRanks];   // mbox[q]: rank q's mailbox (mbox[rank] is local memory)
+  float* Xn[2][2];            // [side 0 = left neighbour, 1 = right][buffer]: its X (same halo layout as ours)
+  uint16_t* Qn[2][2];
+  int32_t* ebn[2][2];
+  uint64_t* pbxn[2];
+};  // 64-bit words per rank in the all-gathered record
 
 // Host-callable launchers (pz_kernels.cu).  Each returns the number of kernels it enqueued.
 int launch_init(const StepArgs& a, cudaStream_t s);
