@@ -114,6 +114,23 @@ def ncu_traffic(name, n_p):
         return None
 
 
+def synth_obs(d, T, seed=0x0B5E2026):
+    """Synthetic observation stream from the generative model of the descriptor (Demo.hs:203-207,
+    SingleTargetTracking.hs:61-65): x_t ~ N(F x_{t-1}, Q), y_t ~ N(H x_t, R), numpy, fixed seed.  The GPU
+    arm must not execute anything under oracle/, so it does not use the oracle's generator."""
+    nx, ny = d.nx, d.ny
+    F = np.array(d.F[: nx * nx]).reshape(nx, nx); Q = np.array(d.Q[: nx * nx]).reshape(nx, nx)
+    Hm = np.array(d.H[: ny * nx]).reshape(ny, nx); R = np.array(d.R[: ny * ny]).reshape(ny, ny)
+    Lq = np.linalg.cholesky(Q + 1e-300 * np.eye(nx)); Lr = np.linalg.cholesky(R)
+    rng = np.random.default_rng(seed)
+    x = np.array(d.x0[:nx], dtype=np.float64)
+    obs = np.zeros((T, ny))
+    for t in range(T):
+        x = F @ x + Lq @ rng.standard_normal(nx)
+        obs[t] = Hm @ x + Lr @ rng.standard_normal(ny)
+    return obs
+
+
 def model_desc(pz, name):
     return {"rw1d": pz.rw1d, "lg42": pz.mtt_track, "lg63": pz.stt}[name]()
 
@@ -167,6 +184,41 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def synth_mtt_scenario(d, T, seed=5, m_max=32, warm_tracks=0):
+    """Detections of the tracker's generative model (sampleStep under MP.sim, MultiTargetTracking.hs:75-99,
+    126-131) in numpy: births Poisson(lambda_b) from the birth prior, motion x' ~ N(F x, Q), detection with
+    probability ps*pd (a missed track survives with (1-pd)/(1-ps*pd)), clutter Poisson(lambda_c) ~ N(0, cv I),
+    detections shuffled.  warm_tracks seeds that many tracks at t = 0 so that short benches see a populated
+    scene (configs[3]: "up to 16 targets").  The GPU arm does not execute oracle/."""
+    rng = np.random.default_rng(seed)
+    F = np.array(d.F[:16]).reshape(4, 4); Lq = np.sqrt(np.diag(np.array(d.Q[:16]).reshape(4, 4)))
+    m = d.mtt
+    pspd = m.survival_prob * m.pd
+    p_coast = (1.0 - m.pd) / (1.0 - pspd)
+    birth_sd = np.sqrt([m.birth_pos_var, m.birth_pos_var, m.birth_vel_var, m.birth_vel_var])
+    tracks = [rng.standard_normal(4) * birth_sd for _ in range(warm_tracks)]
+    out = []
+    for _ in range(T):
+        det, keep = [], []
+        for x in tracks:
+            x = F @ x + Lq * rng.standard_normal(4)
+            if rng.random() < pspd:
+                det.append(x[:2] + np.sqrt(m.meas_var) * rng.standard_normal(2)); keep.append(x)
+            elif rng.random() < p_coast:
+                keep.append(x)
+        for _ in range(rng.poisson(m.new_track_lambda)):
+            if len(keep) < 16:
+                x = rng.standard_normal(4) * birth_sd
+                det.append(x[:2] + np.sqrt(m.meas_var) * rng.standard_normal(2)); keep.append(x)
+        for _ in range(rng.poisson(m.clutter_lambda)):
+            det.append(np.sqrt(m.clutter_var) * rng.standard_normal(2))
+        tracks = keep
+        det = det[:m_max]
+        rng.shuffle(det)
+        out.append(np.array(det, dtype=np.float64).reshape(-1, 2))
+    return out
+
+
 def run_mtt(args):
     """configs[3]: the multi-target tracker (N = 10^6, up to 16 tracks), detections streamed step by step."""
     import torch
@@ -176,7 +228,8 @@ def run_mtt(args):
         raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback")
     pz = g.load_package()
     n_p, K, W = args.particles, args.steps, args.warmup
-    d, obs, truth = H.mtt_scenario(W + K, seed=5)
+    d = H.model_mtt()
+    obs = synth_mtt_scenario(pz.mtt(), W + K, seed=5, warm_tracks=args.mtt_tracks)
     zs = pz.zparticles(n_p, pz.mtt(), seed=1)
     for o in obs[:W]:
         zs.step(o)
@@ -224,7 +277,6 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
-    import pzhelpers as H
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,8 +293,7 @@ def run_b200(args):
         n_p -= n_p % 256  # a sharded filter holds whole resampling blocks (256 particles) per rank
     K, W = args.steps, args.warmup
     d = model_desc(pz, name)
-    hd = helper_desc(H, name)
-    obs, _ = H.gen_obs(hd, W + K + 2 * K + 8)
+    obs = synth_obs(d, W + K + 2 * K + 8)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -321,6 +372,7 @@ def run_b200(args):
     threads = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu:
+        import pzhelpers as H  # the CPU oracle: executed by this leg only
         n_sample = min(n_p, args.cpu_particles)
         steps_cpu = 5
         rate, dt = cpu_port_rate(H, name, n_sample, steps_cpu, threads)
@@ -362,6 +414,7 @@ def main():
     ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU")
     ap.add_argument("--cpu-particles", type=int, default=2_000_000, help="bounded CPU sample size")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mtt-tracks", type=int, default=8, help="tracker bench: targets present at t = 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -104,11 +104,19 @@ _oracle = None
 
 
 def build_oracle():
+    """(Re)build the oracle when it is missing or older than its sources; serialised with a file lock so
+    that several ranks / xdist workers starting together do not race on the output file."""
+    import fcntl
     so = os.path.join(ORACLE_DIR, "libpzoracle.so")
     src = os.path.join(ORACLE_DIR, "pz_oracle.cpp")
     hdrs = [os.path.join(ROOT, "include", h) for h in ("pzgpu.h", "pz_spec_tables.h")]
-    if not os.path.exists(so) or (os.path.exists(src) and max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so)):
-        subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+    with open(os.path.join(ORACLE_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not os.path.exists(so) or (os.path.exists(src) and max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so)):
+                subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return so
 
 
