@@ -11,11 +11,9 @@
 //   the reference's terms one by one and checks the reduction on every call);
 //   updateWithAssocs (:75-87) -> Kalman update, coasting Bernoulli((1-pd)/(1-ps pd)), births.
 //
-// Mapping: half a warp per particle, one lane per track slot.  The 16 candidate likelihoods of
-// an observation are evaluated in parallel, the categorical draw is a 16-lane inclusive scan +
-// ballot, survivors are compacted with a ballot / popc.  A particle is a 1040-byte record
-// (16-byte header + 16 x 64-byte track records), read through the stored ancestor index and
-// written contiguously, so both directions are coalesced.
+// Mapping: one thread per particle (see mtt_step).  A particle is a 1040-byte record (16-byte
+// header + 16 x 64-byte track records) read through the stored ancestor index; only the live
+// track records move (every 64-byte record is two full 32-byte sectors).
 //
 // Unlike the linear-Gaussian kernels this translation unit is NOT bound by the bit-exact fp32
 // spec (parity for MTT is statistical): it uses fast intrinsics and fmad.
@@ -98,7 +96,40 @@ struct MttArgs {
   MttDev p;
 };
 
-__global__ void __launch_bounds__(kThreads) mtt_step(const __grid_constant__ MttArgs a) {
+__device__ __forceinline__ void load_track(const uint32_t* __restrict__ rec, Track& tr) {
+  const uint4* rp = reinterpret_cast<const uint4*>(rec);
+  const uint4 w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3];
+  tr.id = (int)w0.x;
+  tr.m[0] = __uint_as_float(w0.y); tr.m[1] = __uint_as_float(w0.z); tr.m[2] = __uint_as_float(w0.w);
+  tr.m[3] = __uint_as_float(w1.x);
+  tr.c[0] = __uint_as_float(w1.y); tr.c[1] = __uint_as_float(w1.z); tr.c[2] = __uint_as_float(w1.w);
+  tr.c[3] = __uint_as_float(w2.x); tr.c[4] = __uint_as_float(w2.y); tr.c[5] = __uint_as_float(w2.z);
+  tr.c[6] = __uint_as_float(w2.w); tr.c[7] = __uint_as_float(w3.x); tr.c[8] = __uint_as_float(w3.y);
+  tr.c[9] = __uint_as_float(w3.z);
+}
+__device__ __forceinline__ void store_track(uint32_t* __restrict__ rec, const Track& x) {
+  uint4* wp = reinterpret_cast<uint4*>(rec);
+  wp[0] = make_uint4((uint32_t)x.id, __float_as_uint(x.m[0]), __float_as_uint(x.m[1]), __float_as_uint(x.m[2]));
+  wp[1] = make_uint4(__float_as_uint(x.m[3]), __float_as_uint(x.c[0]), __float_as_uint(x.c[1]), __float_as_uint(x.c[2]));
+  wp[2] = make_uint4(__float_as_uint(x.c[3]), __float_as_uint(x.c[4]), __float_as_uint(x.c[5]), __float_as_uint(x.c[6]));
+  wp[3] = make_uint4(__float_as_uint(x.c[7]), __float_as_uint(x.c[8]), __float_as_uint(x.c[9]), 0u);
+}
+
+// One THREAD per particle (the track count of a particle is small and nearly equal across the
+// particles of a warp, so the loops over tracks stay converged; a lane-per-track-slot mapping leaves
+// most lanes idle when few targets are alive).  Three passes over the particle's tracks:
+//   A  load + Kalman predict -> the 6 numbers per track the association needs (predicted position,
+//      inverse innovation covariance, log normaliser), kept in shared memory [track][thread];
+//   B  the sequential association proposal over the M detections (proposeAssocs, :111-124), weight
+//      sum_j log L_j + n_undetected log(1 - ps pd) (observingWithProposal, Metaprob.hs:157-162);
+//   C  load + predict again (the parent record is an L2 hit), Kalman update of detected tracks,
+//      coasting Bernoulli for the others, survivors compacted in id order, then births.
+// HBM traffic is the parent record read once and the child record written once.
+constexpr int kMttThreads = 128;
+constexpr int kMttDerived = 7;  // m0, m1, s00, s01, s11, lnorm, likelihood scratch
+
+__global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ MttArgs a) {
+  extern __shared__ float s_der[];  // [kMttDerived][16][kMttThreads]
   __shared__ float s_z[32][2], s_lc[32], s_ln[32];
   const int tid = threadIdx.x;
   const int M = a.n_obs;
@@ -110,138 +141,121 @@ __global__ void __launch_bounds__(kThreads) mtt_step(const __grid_constant__ Mtt
     s_ln[tid] = a.p.lb * __expf(a.p.nb_norm - 0.5f * r2 / (a.p.bp + a.p.r));
   }
   __syncthreads();
-  const int64_t jraw = (int64_t)blockIdx.x * (kThreads / 16) + (tid >> 4);
-  const bool valid = jraw < a.n;          // an odd tail keeps its partner half-warp alive for the warp-wide shuffles
-  const int64_t j = valid ? jraw : a.n - 1;
-  const int k = tid & 15;                       // track slot of this lane
-  const int hsh = (tid & 16);                   // bit offset of this half in a warp ballot
-  const uint32_t hmask = 0xFFFFu << hsh;        // lanes of this half-warp
+  const int64_t j = (int64_t)blockIdx.x * kMttThreads + tid;
+  if (j >= a.n) return;
+  auto der = [&](int f, int k) -> float& { return s_der[(f * 16 + k) * kMttThreads + tid]; };
   const uint32_t t = a.ctl->t;
   const int64_t par = a.anc[j];
   const uint32_t* __restrict__ src = a.sin + (size_t)par * kMttWords;
   uint32_t* __restrict__ dst = a.sout + (size_t)j * kMttWords;
   const uint4 hdr = *reinterpret_cast<const uint4*>(src);
   const int cnt = (int)hdr.x;
-  int next_id = (int)hdr.y;
-  const bool live = k < cnt;
+  const int next_id = (int)hdr.y;
+  const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
 
-  Track tr;
-  tr.id = 0;
-  if (live) {
-    const uint4* rp = reinterpret_cast<const uint4*>(src + 4 + 16 * k);
-    const uint4 w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3];
-    tr.id = (int)w0.x;
-    tr.m[0] = __uint_as_float(w0.y); tr.m[1] = __uint_as_float(w0.z); tr.m[2] = __uint_as_float(w0.w);
-    tr.m[3] = __uint_as_float(w1.x);
-    tr.c[0] = __uint_as_float(w1.y); tr.c[1] = __uint_as_float(w1.z); tr.c[2] = __uint_as_float(w1.w);
-    tr.c[3] = __uint_as_float(w2.x); tr.c[4] = __uint_as_float(w2.y); tr.c[5] = __uint_as_float(w2.z);
-    tr.c[6] = __uint_as_float(w2.w); tr.c[7] = __uint_as_float(w3.x); tr.c[8] = __uint_as_float(w3.y);
-    tr.c[9] = __uint_as_float(w3.z);
+  // ---- pass A: predictive density of a measurement of every track: N(z; H m, H P H^T + r I)
+  for (int k = 0; k < cnt; ++k) {
+    Track tr;
+    load_track(src + 4 + 16 * k, tr);
     predict(a.p, tr);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) tr.m[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) tr.c[i] = 0.f;
-  }
-  // predictive density of a measurement of this track: N(z; H m, H P H^T + r I)
-  float s00 = 0.f, s01 = 0.f, s11 = 0.f, lnorm = 0.f;
-  if (live) {
     const float sa = tr.c[0] + a.p.r, sb = tr.c[1], sd = tr.c[4] + a.p.r;
     const float det = sa * sd - sb * sb, idet = 1.0f / det;
-    s00 = sd * idet; s01 = -sb * idet; s11 = sa * idet;
-    lnorm = -0.5f * __logf(det) - 1.8378770664093453f;
+    der(0, k) = tr.m[0]; der(1, k) = tr.m[1];
+    der(2, k) = sd * idet; der(3, k) = -sb * idet; der(4, k) = sa * idet;
+    der(5, k) = -0.5f * __logf(det) - 1.8378770664093453f;
   }
-  // uniforms: lane l of the half draws Philox call l -> words 4l .. 4l+3 (M association draws, then 16 coasting draws)
-  const U4 rnd = philox4x32_10((uint32_t)j, (uint32_t)k, t, kStreamMtt, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-  auto uniform = [&](int idx) -> float {  // idx < 64
-    const int srcl = (idx >> 2) + hsh;
-    const uint32_t x = __shfl_sync(0xffffffffu, rnd.x, srcl), y = __shfl_sync(0xffffffffu, rnd.y, srcl);
-    const uint32_t z = __shfl_sync(0xffffffffu, rnd.z, srcl), w = __shfl_sync(0xffffffffu, rnd.w, srcl);
-    const int q = idx & 3;
-    return u01(q == 0 ? x : (q == 1 ? y : (q == 2 ? z : w)));
-  };
 
-  bool assigned = false;
-  int myobs = -1;
-  uint32_t newmask = 0;  // observations that start a new track
+  // ---- pass B: association proposal; uniforms: detection o takes word o & 3 of Philox call o >> 2
+  uint32_t assigned = 0;   // bit k: track k has a detection
+  uint32_t newmask = 0;    // bit o: detection o starts a track
+  unsigned long long obs_lo = 0, obs_hi = 0;  // detection index of track k, 5 bits each (k < 12 | k >= 12)
   float lw = 0.f;
+  U4 rnd = U4{0, 0, 0, 0};
   for (int o = 0; o < M; ++o) {
+    if ((o & 3) == 0) rnd = philox4x32_10((uint32_t)j, (uint32_t)(o >> 2), t, kStreamMtt, k0, k1);
+    const uint32_t word = (o & 3) == 0 ? rnd.x : ((o & 3) == 1 ? rnd.y : ((o & 3) == 2 ? rnd.z : rnd.w));
     const float z0 = s_z[o][0], z1 = s_z[o][1];
-    float like = 0.f;
-    if (live && !assigned) {
-      const float d0 = z0 - tr.m[0], d1 = z1 - tr.m[1];
-      const float quad = s00 * d0 * d0 + 2.0f * s01 * d0 * d1 + s11 * d1 * d1;
-      like = a.p.pspd * __expf(lnorm - 0.5f * quad);
+    float ttot = 0.f;
+    for (int k = 0; k < cnt; ++k) {
+      float like = 0.f;
+      if (!((assigned >> k) & 1u)) {
+        const float d0 = z0 - der(0, k), d1 = z1 - der(1, k);
+        const float quad = der(2, k) * d0 * d0 + 2.0f * der(3, k) * d0 * d1 + der(4, k) * d1 * d1;
+        like = a.p.pspd * __expf(der(5, k) - 0.5f * quad);
+      }
+      der(6, k) = like;
+      ttot += like;
     }
-    float incl = like;
-#pragma unroll
-    for (int d = 1; d < 16; d <<= 1) {
-      const float up = __shfl_up_sync(0xffffffffu, incl, d, 16);
-      if (k >= d) incl += up;
-    }
-    const float ttot = __shfl_sync(0xffffffffu, incl, 15, 16);
     const float lc = s_lc[o], ln = s_ln[o];
     const float tot = lc + ln + ttot;
     lw += __logf(tot);
-    const float u = uniform(o) * tot;
-    const float target = u - lc - ln;
-    // warp-wide votes are taken unconditionally: the two half-warps (two particles) may pick differently
-    uint32_t hit = (__ballot_sync(0xffffffffu, like > 0.f && incl > target) & hmask) >> hsh;
-    const uint32_t cand = (__ballot_sync(0xffffffffu, like > 0.f) & hmask) >> hsh;
+    const float u = u01(word) * tot;
     if (u < lc) {
       // clutter
     } else if (u < lc + ln) {
       newmask |= 1u << o;
     } else {
-      if (!hit && cand) hit = 1u << (31 - __clz(cand));  // round-off past the last candidate: take the last one
-      if (!hit) newmask |= 1u << o;                      // no candidate track at all: start a track
-      else if (k == __ffs(hit) - 1) { assigned = true; myobs = o; }
+      const float target = u - lc - ln;
+      float cum = 0.f;
+      int pick = -1, last = -1;
+      for (int k = 0; k < cnt; ++k) {
+        const float like = der(6, k);
+        if (like > 0.f) {
+          last = k;
+          cum += like;
+          if (pick < 0 && cum > target) pick = k;
+        }
+      }
+      if (pick < 0) pick = last;          // round-off past the last candidate: take the last one
+      if (pick < 0) newmask |= 1u << o;   // no candidate track at all: start a track
+      else {
+        assigned |= 1u << pick;
+        if (pick < 12) obs_lo |= (unsigned long long)o << (5 * pick);
+        else obs_hi |= (unsigned long long)o << (5 * (pick - 12));
+      }
     }
   }
-  const uint32_t undet = (__ballot_sync(0xffffffffu, live && !assigned) & hmask) >> hsh;
-  lw += (float)__popc(undet) * a.p.log1m_pspd;
+  const int n_undet = cnt - __popc(assigned);
+  lw += (float)n_undet * a.p.log1m_pspd;
 
-  // update / coast
-  bool survive = false;
-  if (live) {
-    if (assigned) { update(tr, s_z[myobs][0], s_z[myobs][1], a.p.r); survive = true; }
+  // ---- pass C: update / coast, survivors compacted in order; coasting draw of track k: word k & 3 of call 8 + (k >> 2)
+  int n_surv = 0;
+  for (int k = 0; k < cnt; ++k) {
+    if ((k & 3) == 0) rnd = philox4x32_10((uint32_t)j, (uint32_t)(8 + (k >> 2)), t, kStreamMtt, k0, k1);
+    const uint32_t word = (k & 3) == 0 ? rnd.x : ((k & 3) == 1 ? rnd.y : ((k & 3) == 2 ? rnd.z : rnd.w));
+    const bool det = (assigned >> k) & 1u;
+    if (!det && !(u01(word) < a.p.p_coast)) continue;  // undetected and not coasting: the track dies
+    Track tr;
+    load_track(src + 4 + 16 * k, tr);
+    predict(a.p, tr);
+    if (det) {
+      const int o = (int)((k < 12 ? obs_lo >> (5 * k) : obs_hi >> (5 * (k - 12))) & 31ull);
+      update(tr, s_z[o][0], s_z[o][1], a.p.r);
+    }
+    store_track(dst + 4 + 16 * n_surv, tr);
+    ++n_surv;
   }
-  {
-    const float uc = uniform(32 + k);  // all lanes take part in the shuffles
-    if (live && !assigned) survive = uc < a.p.p_coast;
-  }
-  const uint32_t smask = (__ballot_sync(0xffffffffu, survive) & hmask) >> hsh;
-  const int n_surv = __popc(smask);
-  auto store_track = [&](int slot, const Track& x) {
-    uint4* wp = reinterpret_cast<uint4*>(dst + 4 + 16 * slot);
-    wp[0] = make_uint4((uint32_t)x.id, __float_as_uint(x.m[0]), __float_as_uint(x.m[1]), __float_as_uint(x.m[2]));
-    wp[1] = make_uint4(__float_as_uint(x.m[3]), __float_as_uint(x.c[0]), __float_as_uint(x.c[1]), __float_as_uint(x.c[2]));
-    wp[2] = make_uint4(__float_as_uint(x.c[3]), __float_as_uint(x.c[4]), __float_as_uint(x.c[5]), __float_as_uint(x.c[6]));
-    wp[3] = make_uint4(__float_as_uint(x.c[7]), __float_as_uint(x.c[8]), __float_as_uint(x.c[9]), 0u);
-  };
-  if (survive && valid) store_track(__popc(smask & ((1u << k) - 1u)), tr);
-  // births: lane i takes the i-th new-track observation (newTrackD conditioned on it)
+  // births: the i-th new-track detection (newTrackD conditioned on it)
   const int n_new = __popc(newmask);
   const int room = 16 - n_surv;
   const int n_born = n_new < room ? n_new : room;
-  if (k < n_born && valid) {
-    const int o = __fns(newmask, 0, k + 1);
+  uint32_t nm = newmask;
+  for (int i = 0; i < n_born; ++i) {
+    const int o = __ffs(nm) - 1;
+    nm &= nm - 1;
     Track nt;
-    nt.id = next_id + k;
+    nt.id = next_id + i;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) nt.m[i] = 0.f;
+    for (int q = 0; q < 4; ++q) nt.m[q] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) nt.c[i] = 0.f;
+    for (int q = 0; q < 10; ++q) nt.c[q] = 0.f;
     nt.c[0] = a.p.bp; nt.c[4] = a.p.bp; nt.c[7] = a.p.bv; nt.c[9] = a.p.bv;
     update(nt, s_z[o][0], s_z[o][1], a.p.r);
-    store_track(n_surv + k, nt);
+    store_track(dst + 4 + 16 * (n_surv + i), nt);
   }
-  if (k == 0 && valid) {
-    *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)(n_surv + n_born), (uint32_t)(next_id + n_new), n_new > room ? 1u : 0u, 0u);
-    a.lw[j] = lw;
-    if (n_new > room) atomicAdd(a.overflow, (unsigned long long)(n_new - room));
-  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)(n_surv + n_born), (uint32_t)(next_id + n_new), n_new > room ? 1u : 0u, 0u);
+  a.lw[j] = lw;
+  if (n_new > room) atomicAdd(a.overflow, (unsigned long long)(n_new - room));
 }
 
 // weighted track-count moments: sum w, sum w^2, sum w c, sum w c^2 at scale 2^emax
@@ -331,8 +345,13 @@ int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, con
   MttArgs a;
   a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.n = n; a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
-  const int per_cta = kThreads / 16;
-  mtt_step<<<(unsigned)((n + per_cta - 1) / per_cta), kThreads, 0, s>>>(a);
+  const size_t smem = (size_t)kMttDerived * 16 * kMttThreads * sizeof(float);  // 56 KB
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(mtt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  mtt_step<<<(unsigned)((n + kMttThreads - 1) / kMttThreads), kMttThreads, smem, s>>>(a);
   return 1;
 }
 
