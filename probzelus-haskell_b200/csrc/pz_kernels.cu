@@ -672,10 +672,17 @@ template <bool SEGDUP, class Source>
 __device__ __forceinline__ void emit_head(const Source& src, float* s_par, int stride, int lo, int hi, int k) {
   if (hi > lo) {
     src.put(s_par, stride, lo, k);
-    if (SEGDUP ? (((lo ^ (hi - 1)) >> 7) != 0) : (hi - lo > 128)) {
-      for (int s = (lo | 127) + 1; s < hi; s += 128) src.put(s_par, stride, s, k);
+    if constexpr (SEGDUP) {
+      if (((lo ^ (hi - 1)) >> 7) != 0)
+        for (int s = (lo | 127) + 1; s < hi; s += 128) src.put(s_par, stride, s, k);
     }
   }
+}
+// look-back variant: duplicates of the (rare) runs longer than 128 slots, outside the per-particle fast path
+template <class Source>
+__device__ __noinline__ void emit_long_runs(const Source& src, float* s_par, int stride, int lo, int hi, int k) {
+  if (hi - lo > 128)
+    for (int s = (lo | 127) + 1; s < hi; s += 128) src.put(s_par, stride, s, k);
 }
 
 // Input side of one output tile [j0, j0 + nslots): every warp takes input blocks b_first + warp,
@@ -706,12 +713,11 @@ template <bool SEGDUP, class Source>
 __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const uint16_t* __restrict__ qin,
                                               const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
                                               int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
-                                              int lane, int warp) {
+                                              int lane, int warp, BlockIn cur) {
+  // `cur` holds the inputs of block b_first + warp (loaded by the caller before its prologue barrier)
   const uint32_t jend = j0 + (uint32_t)nslots;
   int64_t b = b_first + warp;
   if (b >= b_end) return;
-  BlockIn cur;
-  cur.load(qin, ebx, xb, b, lane);
   for (; b < b_end; b += kWarps) {
     const BlockIn in = cur;
     const int64_t bn = b + kWarps;
@@ -756,10 +762,21 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
 #pragma unroll
       for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
     }
+    const int32_t eprev0 = eprev;
 #pragma unroll
     for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
+    if constexpr (!SEGDUP) {
+      // a run longer than 128 slots needs a lane whose 8 particles cover more than 128 slots: one vote per block
+      if (__any_sync(0xffffffffu, e[7] - eprev0 > 128)) {
+        int32_t ep = eprev0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { emit_long_runs(sa, s_par, stride, ep, e[k], k); ep = e[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { emit_long_runs(sb, s_par, stride, ep, e[4 + k], k); ep = e[4 + k]; }
+      }
+    }
   }
 }
 
@@ -984,17 +1001,22 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
 #pragma unroll
   for (int k = 0; k < NY; ++k) y_new[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
 
-  s_tab[tid] = g_icdf_tab[tid];  // kThreads == PZ_ICDF_ROWS
   if constexpr (MODE == 0) {
+    // the first input block's weights: in flight during the prologue
+    const int64_t b_first = (int64_t)a.tile_start[blockIdx.x];
+    BlockIn first{};
+    if (b_first + warp < a.b_hi) first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
+    s_tab[tid] = g_icdf_tab[tid];  // kThreads == PZ_ICDF_ROWS
     // sentinel in dimension 0 of every slot: "no head here"
     uint4* sz = reinterpret_cast<uint4*>(s_par);
     for (int i = tid; i < TO / 4; i += kThreads) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
     StateSource<NX> src;
     src.x = xin; src.ld = a.ld;
-    resample_tile<(NX != 1)>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, (int64_t)a.tile_start[blockIdx.x], a.b_hi, pl->emax, pl->h0,
-                  pl->Mq, j0, nslots, lane, warp);
+    resample_tile<(NX != 1)>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
+                             lane, warp, first);
   } else {
+    s_tab[tid] = g_icdf_tab[tid];
     for (int sidx = tid; sidx < nslots; sidx += kThreads) {
       const int64_t p = ta.anc[j0l + sidx];
 #pragma unroll
@@ -1116,8 +1138,11 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = __uint_as_float(kSentinel);
   __syncthreads();
   IndexSource src;
-  resample_tile<true>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, (int64_t)g.tile_start[blockIdx.x], g.nblk, pl->emax,
-                pl->h0, pl->Mq, (uint32_t)j0, nslots, lane, warp);
+  const int64_t b_first = (int64_t)g.tile_start[blockIdx.x];
+  BlockIn first{};
+  if (b_first + warp < g.nblk) first.load(generic_q(g), generic_eb(g), g.xb, b_first + warp, lane);
+  resample_tile<true>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, b_first, g.nblk, pl->emax, pl->h0, pl->Mq, (uint32_t)j0,
+                      nslots, lane, warp, first);
   __syncthreads();
   for (int seg = warp; seg * 128 < nslots; seg += kWarps) {
     const int sl = seg * 128 + lane * 4;

@@ -174,10 +174,11 @@ def test_halo_range_function(pz):
     assert hi == lo  # nothing from rank 3
 
 
-def _gpu_worker(rank, world, port, model, n_global, seed, T, idfile, outdir):
+def _gpu_worker(rank, world, port, model, n_global, seed, T, env, outdir):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
+    os.environ.update(env or {})
     pz = g.load_package()
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -187,6 +188,17 @@ def _gpu_worker(rank, world, port, model, n_global, seed, T, idfile, outdir):
     hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
     obs, _ = H.gen_obs(hd, T)
     zs = pz.zparticles_sharded(n_global, d, ids[0], rank, world, seed=seed, device=rank)
+    if env and env.get("PZ_HALO_BLOCKS") == "1":
+        # a one-block halo margin cannot hold the migration of this stream: every rank must report it
+        codes = []
+        for y in obs:
+            try:
+                zs.step(y); codes.append(0)
+            except pz.PzError as e:
+                codes.append(e.code)
+        np.save(os.path.join(outdir, f"codes_{rank}.npy"), np.array(codes))
+        zs.close(); dist.destroy_process_group()
+        return
     posts = [zs.step(y) for y in obs]
     np.save(os.path.join(outdir, f"x_{rank}.npy"), zs.read_state())
     np.save(os.path.join(outdir, f"s_{rank}.npy"), np.array([[p.total_weight, p.e_max, p.n_migrated] + list(p.mean) for p in posts], dtype=np.float64))
@@ -195,14 +207,17 @@ def _gpu_worker(rank, world, port, model, n_global, seed, T, idfile, outdir):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["peer_memory", "nccl"])
 @pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
-def test_sharded_equals_single_gpu(pz, model, tmp_path):
+def test_sharded_equals_single_gpu(pz, model, exchange, tmp_path):
+    """Both exchange implementations (kernels over NVLink peer memory; NCCL calls between the kernels)."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world, n_global, seed, T = 2, 2 * 256 * 101, 99, 6  # partial last tile on every rank
-    mp.spawn(_gpu_worker, args=(world, _free_port(), model, n_global, seed, T, None, str(tmp_path)), nprocs=world, join=True)
+    env = {"PZ_SHARD_NCCL": "1"} if exchange == "nccl" else {}
+    mp.spawn(_gpu_worker, args=(world, _free_port(), model, n_global, seed, T, env, str(tmp_path)), nprocs=world, join=True)
     d = getattr(pz, model)()
     hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
     obs, _ = H.gen_obs(hd, T)
@@ -215,3 +230,20 @@ def test_sharded_equals_single_gpu(pz, model, tmp_path):
     for t, p in enumerate(posts):
         assert int(s0[t, 0]) == p.total_weight and int(s0[t, 1]) == p.e_max
         assert np.allclose(s0[t, 3:3 + d.nx], p.mean, rtol=1e-6, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_sharded_margin_overflow_is_reported_by_every_rank(pz, tmp_path):
+    """PZ_HALO_BLOCKS=1: the ancestors of a rank's boundary slots reach beyond a one-block margin within a
+    few steps; the verdict is computed by every rank from the gathered records, so both ranks raise
+    PZ_ECAPACITY (-5) at the same step instead of resampling from an incomplete halo."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n_global, seed, T = 2, 2 * 256 * 400, 7, 40
+    mp.spawn(_gpu_worker, args=(world, _free_port(), "rw1d", n_global, seed, T, {"PZ_HALO_BLOCKS": "1"}, str(tmp_path)),
+             nprocs=world, join=True)
+    c0, c1 = np.load(tmp_path / "codes_0.npy"), np.load(tmp_path / "codes_1.npy")
+    assert np.array_equal(c0, c1)
+    assert (c0 != 0).any() and c0[np.flatnonzero(c0)[0]] == -5   # the first failure is the capacity report
