@@ -105,6 +105,33 @@ def test_filter_trajectory_bit_exact(pz, model, n):
     zs.close(); orc.close()
 
 
+@pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
+def test_filter_outlier_observations_bit_exact(pz, model):
+    """Observations far in the tails collapse the weights onto a handful of particles: runs of thousands
+    of children (the long-run duplicates and the segment look-back of the step kernel), empty blocks,
+    shifts outside the fast range of the slot map.  Still bit-exact against the oracle."""
+    hd = MODELS[model][0]()
+    d = getattr(pz, MODELS[model][1])()
+    n = 60000 + 123
+    obs, _ = H.gen_obs(hd, 10)
+    obs = obs.copy()
+    obs[2] += 14.0; obs[3] -= 25.0; obs[6] += 40.0; obs[7] += 40.0
+    zs = pz.zparticles(n, d, seed=77)
+    orc = H.OracleFilter(hd, n, 77)
+    max_run = 0
+    for t in range(len(obs)):
+        post = zs.step(obs[t])
+        rc, s = orc.step(obs[t])
+        assert rc == 0
+        x_ref, _, anc_ref = orc.state()
+        max_run = max(max_run, int(np.bincount(anc_ref).max()))
+        assert np.array_equal(zs.read_state().view(np.uint32), x_ref.view(np.uint32)), (model, t)
+        assert post.total_weight == s.total_weight and post.e_max == s.e_max
+        assert abs(post.ess - s.ess) < 1e-4 * s.ess + 1e-6
+    assert max_run > 300   # the scenario really produced long runs
+    zs.close(); orc.close()
+
+
 def test_filter_golden_fixture(pz):
     """The committed fixture (made by tools/make_golden.py) without re-running the oracle."""
     g = np.load(H.ROOT + "/tests/golden/philox_normal_kat.npz")
