@@ -200,6 +200,30 @@ def test_posterior_matches_kalman(pz, model):
         assert abs(ll.mean() - kl.sum()) < 4 * ll.std(ddof=1) / np.sqrt(seeds) + 0.02
 
 
+def test_long_stream_stays_on_the_kalman_posterior(pz):
+    """BASELINE configs[2] shape: the 2-D position/velocity tracker over 10^4 steps (N = 10^6 here).  The
+    filter neither degenerates nor drifts: over the last 2000 steps the posterior mean tracks the exact
+    Kalman mean to Monte Carlo accuracy and the log-evidence per step matches."""
+    hd = H.model_mtt_track()
+    T, n = 10000, 1000000
+    obs, _ = H.gen_obs(hd, T)
+    km, kc, kl = H.kalman(hd, obs)
+    zs = pz.zparticles(n, pz.mtt_track(), seed=2026)
+    posts = zs.run(obs)
+    assert len(posts) == T and posts[-1].step == T - 1
+    mean = np.array([p.mean for p in posts[-2000:]])
+    var = np.array([p.var for p in posts[-2000:]])
+    ess = np.array([p.ess for p in posts[-2000:]])
+    kvar = np.array([np.diag(c) for c in kc[-2000:]])
+    err = (mean - km[-2000:]) / np.sqrt(kvar)
+    assert np.sqrt(np.mean(err ** 2)) < 0.02 and np.max(np.abs(err)) < 0.15   # ~ 1/sqrt(ESS) with path degeneracy
+    assert np.all(np.abs(var.mean(axis=0) / kvar.mean(axis=0) - 1) < 0.02)
+    assert ess.min() > 100 and np.median(ess) > 0.2 * n   # a 4-sigma innovation costs most of the ESS for one step
+    ll = np.array([p.log_evidence_inc for p in posts])
+    assert abs(ll.sum() - kl.sum()) < 1e-3 * abs(kl.sum())
+    zs.close()
+
+
 def test_multinomial_reference_mode(pz):
     """resampler = MULTINOMIAL_REF (resample2, Inference.hs:57-61): bit-exact vs the oracle and
     statistically equal to the systematic filter."""
