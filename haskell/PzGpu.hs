@@ -13,7 +13,7 @@
 -- repository's CI: the build image has no GHC (SURVEY.md section 0.9).  Every foreign import below
 -- is exercised through the identical C symbols by tests/ (ctypes) and host/examples_gpu.cpp.
 module PzGpu
-  ( ModelDesc, Posterior (..), rw1d, stt, mttTrack
+  ( ModelDesc, Posterior (..), rw1d, stt, sttDelayed, mttTrack
   , inferGPU, zparticlesGPU, runStreamGPU
   ) where
 
@@ -55,6 +55,8 @@ foreign import ccall safe "pz_filter_step"
   c_filter_step :: Ptr PzFilter -> Ptr CDouble -> Int32 -> Int32 -> Ptr () -> IO CInt
 foreign import ccall safe "pz_filter_read_particles"
   c_read_particles :: Ptr PzFilter -> Int32 -> Ptr CDouble -> Int64 -> IO CInt
+foreign import ccall safe "pz_filter_read_posterior"
+  c_read_posterior :: Ptr PzFilter -> Ptr CDouble -> Ptr CDouble -> IO CInt  -- MDistr (mean, cov) of a delayed filter
 foreign import ccall unsafe "pz_filter_n_local" c_n_local :: Ptr PzFilter -> IO Int64
 foreign import ccall unsafe "&pz_filter_destroy" p_filter_destroy :: FunPtr (Ptr PzFilter -> IO ())
 foreign import ccall unsafe "pz_last_error" c_last_error :: IO CString
@@ -74,9 +76,18 @@ mkDesc fill = do
 rw1d :: Double -> Double -> IO ModelDesc
 rw1d q r = mkDesc (\p -> c_model_rw1d p (realToFrac q) (realToFrac r))
 
--- | Examples/SingleTargetTracking.hs:28-54 with delay = False.
+-- | Examples/SingleTargetTracking.hs:28-54 with delay = False (the bootstrap filter).
 stt :: IO ModelDesc
 stt = mkDesc c_model_stt
+
+-- | The same model with delay = True (SingleTargetTracking.hs:36-38): the state stays a symbolic
+-- Gaussian marginal; every particle carries the exact Kalman posterior (pz_model_desc.delayed,
+-- a 32-bit field at byte offset 20).
+sttDelayed :: IO ModelDesc
+sttDelayed = do
+  ModelDesc fp <- stt
+  withForeignPtr fp (\p -> pokeByteOff p 20 (1 :: Int32))
+  pure (ModelDesc fp)
 
 -- | The per-track model of Examples/MultiTargetTracking.hs:56-73.
 mttTrack :: IO ModelDesc

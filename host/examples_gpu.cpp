@@ -1,8 +1,9 @@
 // examples-gpu -- the reference's CLI driver (haskell/src/test/Examples.hs:26-40) over libpzgpu.so.
 //
 //   examples-gpu mtt [N]            runMTTExample        (Examples.hs:23-24, MultiTargetTracking.hs:141-145)
-//   examples-gpu stt [delay] [N]    STT.runExample       (SingleTargetTracking.hs:61-69); only delay=False
-//                                   (the bootstrap filter) runs on the GPU
+//   examples-gpu stt [delay] [N]    STT.runExample       (SingleTargetTracking.hs:61-69); delay=True (the default,
+//                                   Examples.hs:31) is the delayed-sampling stream: every particle is the exact
+//                                   Gaussian marginal, printed as {"mean":..,"cov":..}; delay=False the bootstrap filter
 //   examples-gpu rw1d [N]           runKalman1DParticles (Examples/Demo.hs:200-210), one flat array per line
 //                                   for Generic1D.java
 // Options: --steps T (default: run until the pipe closes, as ZS.runStream does), --emit P (particles
@@ -72,6 +73,8 @@ void lg_sim_step(const pz_model_desc& d, Sim& sim, std::vector<double>& x, std::
 }
 
 int run_lg(const pz_model_desc& d, uint64_t n, long steps, int emit, uint64_t seed, bool flat) {
+  const bool delayed = d.delayed != 0;
+  std::vector<double> pmean(d.nx), pcov((size_t)d.nx * d.nx);
   pz_filter* f = nullptr;
   if (pz_filter_create(&d, n, seed, 0, &f)) die("pz_filter_create");
   Sim sim(seed ^ 0x9E3779B97F4A7C15ull);
@@ -88,6 +91,15 @@ int run_lg(const pz_model_desc& d, uint64_t n, long steps, int emit, uint64_t se
     if (flat) {  // (observedPosition, actualPosition, average particles), Demo.hs:207
       double v[3] = {y[0], x[0], s.mean[0]};
       put_vec(line, v, 3);
+    } else if (delayed) {
+      // every particle is the symbolic marginal: ToJSON MDistr, DelayedSampling.hs:69-73
+      if (pz_filter_read_posterior(f, pmean.data(), pcov.data())) die("pz_filter_read_posterior");
+      std::string node = "[[0,{\"mean\":"; put_vec(node, pmean.data(), d.nx); node += ",\"cov\":[";
+      for (int r = 0; r < d.nx; ++r) { if (r) node += ','; put_vec(node, &pcov[(size_t)r * d.nx], d.nx); }
+      node += "]}]]";
+      line += "[[[0,"; put_vec(line, x.data(), d.nx); line += "]],[";
+      for (int64_t i = 0; i < n_sel; ++i) { if (i) line += ','; line += node; }
+      line += "],["; put_vec(line, y.data(), d.ny); line += "]]";
     } else {
       if (pz_filter_read_particles(f, stride, parts.data(), (int64_t)parts.size())) die("pz_filter_read_particles");
       line += "[[[0,"; put_vec(line, x.data(), d.nx); line += "]],[";   // [(0, groundTruth)]
@@ -211,13 +223,10 @@ int main(int argc, char** argv) {
   if (pos[0] == "mtt") return run_mtt(strtoull(nth(1, "100").c_str(), nullptr, 10), steps, emit, seed);  // default N = 100, Examples.hs:30
   if (pos[0] == "stt") {
     const std::string delay = nth(1, "True");                                                         // Examples.hs:31
-    if (delay == "True") {
-      fputs("examples-gpu: stt delay=True is the exact Kalman recursion (every particle identical); the GPU path is the\n"
-            "bootstrap filter, run `examples-gpu stt False N`\n", stderr);
-      return 2;
-    }
+    if (delay != "True" && delay != "False") { usage(); return 2; }                                   // `read` of a Bool
     pz_model_desc d;
     if (pz_model_stt(&d)) die("pz_model_stt");
+    d.delayed = delay == "True";
     return run_lg(d, strtoull(nth(2, "100").c_str(), nullptr, 10), steps, emit, seed, false);
   }
   if (pos[0] == "rw1d") {

@@ -83,7 +83,12 @@ typedef struct pz_model_desc {
   int32_t scalar_ll_2x; /* 1 = reference's doubled scalar Gaussian score,
                            Distributions.hs:160-161 (only honoured when ny == 1)             */
   int32_t resampler;    /* PZ_RESAMPLE_*                                                     */
-  int32_t reserved[3];
+  int32_t delayed;      /* 1 = delayed sampling (`delay=True`, SingleTargetTracking.hs:36-38;
+                           kalman1DObservedDelayed, Demo.hs:215-242): the state stays a symbolic
+                           Gaussian marginal, so every particle carries the exact Kalman
+                           posterior (makeMarginal / makeConditional, DelayedSampling.hs:135-152)
+                           and all weights are equal.  RW1D / LINGAUSS only.                  */
+  int32_t reserved[2];
   double F[PZ_MAX_NX * PZ_MAX_NX];  /* x' ~ N(F x, Q)                                        */
   double Q[PZ_MAX_NX * PZ_MAX_NX];
   double H[PZ_MAX_NY * PZ_MAX_NX];  /* y  ~ N(H x', R)                                       */
@@ -168,6 +173,11 @@ PZ_API int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, i
  * count_out[i], id_out[i*16+k] (-1 past the count), mean_out[(i*16+k)*4..], cov_out[(i*16+k)*16..]. */
 PZ_API int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, double* mean_out,
                                  double* cov_out, int64_t n_sel_cap);
+
+/* Delayed-sampling filters (model.delayed = 1): the Gaussian marginal every particle carries,
+ * `MDistr` (mean[nx], cov[nx*nx] row-major) -- what the reference serialises per particle as
+ * {"mean":..,"cov":..} (DelayedSampling.hs:69-73).                                            */
+PZ_API int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out);
 
 /* Parity / debug taps. */
 PZ_API int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n);      /* ancestors of the pending resample */

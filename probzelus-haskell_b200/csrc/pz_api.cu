@@ -11,6 +11,7 @@
 // device is usable.
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -165,6 +166,105 @@ int generic_alloc(GenericScratch* g, int64_t n, bool full) {
 
 }  // namespace
 
+// Delayed-sampling (Rao-Blackwellised) linear-Gaussian filter: the one Gaussian marginal all particles share.
+struct RbDev {
+  double mean[PZ_MAX_NX];
+  double cov[PZ_MAX_NX * PZ_MAX_NX];
+  double F[PZ_MAX_NX * PZ_MAX_NX], Q[PZ_MAX_NX * PZ_MAX_NX], H[PZ_MAX_NY * PZ_MAX_NX], R[PZ_MAX_NY * PZ_MAX_NY];
+  double y[PZ_MAX_NY];
+  double ll_scale;   // 2 for the reference's doubled scalar score (Distributions.hs:160-161), else 1
+  int32_t nx, ny;
+  uint32_t t;
+};
+
+// One step of the delayed-sampling stream: makeMarginal = kalmanPredict (MVDistributions.hs:75-76,
+// DelayedSampling.hs:135-139), score' of the marginal predictive (DelayedSampling.hs:124-128), makeConditional
+// = kalmanUpdate (MVDistributions.hs:83-100, DelayedSampling.hs:143-152).  Every particle is identical, so the
+// whole population is this one recursion in double on one thread.
+__global__ void rb_kalman_step(RbDev* st, pz_step_summary* out, double n_particles) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int nx = st->nx, ny = st->ny;
+  double m[PZ_MAX_NX], P[PZ_MAX_NX][PZ_MAX_NX], FP[PZ_MAX_NX][PZ_MAX_NX];
+  for (int i = 0; i < nx; ++i) {
+    double s = 0;
+    for (int k = 0; k < nx; ++k) s += st->F[i * nx + k] * st->mean[k];
+    m[i] = s;
+    for (int j = 0; j < nx; ++j) {
+      double a = 0;
+      for (int k = 0; k < nx; ++k) a += st->F[i * nx + k] * st->cov[k * nx + j];
+      FP[i][j] = a;
+    }
+  }
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < nx; ++j) {
+      double a = 0;
+      for (int k = 0; k < nx; ++k) a += FP[i][k] * st->F[j * nx + k];
+      P[i][j] = a + st->Q[i * nx + j];
+    }
+  // S = R + H P H^T, innovation, Gauss-Jordan inverse (ny <= 3, SPD)
+  double PHt[PZ_MAX_NX][PZ_MAX_NY], S[PZ_MAX_NY][2 * PZ_MAX_NY], v[PZ_MAX_NY];
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < ny; ++j) {
+      double a = 0;
+      for (int k = 0; k < nx; ++k) a += P[i][k] * st->H[j * nx + k];
+      PHt[i][j] = a;
+    }
+  for (int i = 0; i < ny; ++i) {
+    for (int j = 0; j < ny; ++j) {
+      double a = 0;
+      for (int k = 0; k < nx; ++k) a += st->H[i * nx + k] * PHt[k][j];
+      S[i][j] = a + st->R[i * ny + j];
+      S[i][ny + j] = (i == j) ? 1.0 : 0.0;
+    }
+    double a = 0;
+    for (int k = 0; k < nx; ++k) a += st->H[i * nx + k] * m[k];
+    v[i] = st->y[i] - a;
+  }
+  double logdet = 0;
+  for (int c = 0; c < ny; ++c) {
+    const double piv = S[c][c];
+    logdet += log(piv);
+    for (int j = 0; j < 2 * ny; ++j) S[c][j] /= piv;
+    for (int r = 0; r < ny; ++r) {
+      if (r == c) continue;
+      const double f = S[r][c];
+      for (int j = 0; j < 2 * ny; ++j) S[r][j] -= f * S[c][j];
+    }
+  }
+  double quad = 0, Siv[PZ_MAX_NY];
+  for (int i = 0; i < ny; ++i) {
+    double a = 0;
+    for (int j = 0; j < ny; ++j) a += S[i][ny + j] * v[j];
+    Siv[i] = a;
+    quad += v[i] * a;
+  }
+  const double ll = -0.5 * (quad + logdet + ny * 1.8378770664093453);
+  for (int i = 0; i < nx; ++i) {
+    double a = 0;
+    for (int j = 0; j < ny; ++j) a += PHt[i][j] * Siv[j];
+    st->mean[i] = m[i] + a;
+  }
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < nx; ++j) {
+      double a = 0;
+      for (int k = 0; k < ny; ++k)
+        for (int l = 0; l < ny; ++l) a += PHt[i][k] * S[k][ny + l] * PHt[j][l];
+      st->cov[i * nx + j] = P[i][j] - a;
+    }
+  out->step = st->t;
+  out->log_evidence_inc = st->ll_scale * ll;
+  out->ess = n_particles;          // equal weights
+  for (int d = 0; d < PZ_MAX_NX; ++d) {
+    out->mean[d] = d < nx ? st->mean[d] : 0.0;
+    out->var[d] = d < nx ? st->cov[d * nx + d] : 0.0;
+  }
+  out->n_migrated = 0;
+  out->e_max = 0;
+  out->reserved = 0;
+  out->total_weight = (uint64_t)n_particles << 15;  // every particle at q = 2^15
+  st->t += 1;
+}
+
 struct pz_filter {
   pz_model_desc desc;
   StepArgs a;
@@ -193,6 +293,9 @@ struct pz_filter {
   Mailbox* mbox = nullptr;           // sharded: this rank's mailbox (peer-memory exchange)
   ShardP2P* d_p2p = nullptr;
   std::vector<void*> ipc_opened;     // peer mappings to close
+  // delayed-sampling linear-Gaussian filter
+  bool is_rb = false;
+  RbDev* rb = nullptr;
   // multi-target tracker
   bool is_mtt = false;
   uint32_t* mtt_s[2] = {nullptr, nullptr};   // particle records, double-buffered
@@ -261,6 +364,7 @@ void free_filter(pz_filter* f) {
   cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->qbuf[0]); cudaFree(f->qbuf[1]); cudaFree(f->xbbuf); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
   cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
   cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec);
+  cudaFree(f->rb);
   cudaFree(f->warm);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(f->mbox); cudaFree(f->d_p2p);
@@ -595,6 +699,58 @@ int setup_p2p(pz_filter* f) {
   return PZ_OK;
 }
 
+int create_rb(const pz_model_desc* model, uint64_t n, int device, pz_filter** out) {
+  const int nx = model->nx, ny = model->ny;
+  if (nx < 1 || nx > PZ_MAX_NX || ny < 1 || ny > PZ_MAX_NY) return fail(PZ_EINVAL, "unsupported dims nx=%d ny=%d", nx, ny);
+  if (n < 1 || n > (1ull << 30)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^30]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PZ_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  PZ_CUDA(cudaSetDevice(device));
+  pz_filter* f = new (std::nothrow) pz_filter();
+  if (!f) return fail(PZ_ENOMEM, "out of host memory");
+  f->desc = *model; f->device = device; f->is_rb = true;
+  memset(&f->a, 0, sizeof(f->a));
+  f->a.model.nx = nx; f->a.model.ny = ny; f->a.n_local = f->a.n_global = (int64_t)n; f->a.world = 1;
+  RbDev h{};
+  h.nx = nx; h.ny = ny; h.t = 0;
+  for (int i = 0; i < nx * nx; ++i) { h.F[i] = model->F[i]; h.Q[i] = model->Q[i]; }
+  for (int i = 0; i < ny * nx; ++i) h.H[i] = model->H[i];
+  for (int i = 0; i < ny * ny; ++i) h.R[i] = model->R[i];
+  for (int i = 0; i < nx; ++i) h.mean[i] = model->x0[i];  // point mass: zero covariance
+  h.ll_scale = (ny == 1 && model->scalar_ll_2x) ? 2.0 : 1.0;
+#define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
+  PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  PZ_TRY(cudaEventCreate(&f->ev0));
+  PZ_TRY(cudaEventCreate(&f->ev1));
+  PZ_TRY(cudaMalloc(&f->rb, sizeof(RbDev)));
+  PZ_TRY(cudaMemcpy(f->rb, &h, sizeof(RbDev), cudaMemcpyHostToDevice));
+  PZ_TRY(cudaMalloc(&f->a.summ, sizeof(pz_step_summary)));
+  PZ_TRY(cudaMallocHost(&f->h_summ, sizeof(pz_step_summary)));
+#undef PZ_TRY
+  *out = f;
+  return PZ_OK;
+}
+
+int rb_step_host(pz_filter* f, const double* obs, pz_step_summary* out) {
+  PZ_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(f->rb) + offsetof(RbDev, y), obs, f->a.model.ny * sizeof(double),
+                          cudaMemcpyHostToDevice, f->stream));
+  PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+  rb_kalman_step<<<1, 32, 0, f->stream>>>(f->rb, f->a.summ, (double)f->a.n_local);
+  PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+  PZ_CUDA(cudaMemcpyAsync(f->h_summ, f->a.summ, sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  PZ_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+  f->last_ms += ms; f->last_launches += 1;
+  f->t += 1;
+  if (out) *out = *f->h_summ;
+  if (!(f->h_summ->log_evidence_inc == f->h_summ->log_evidence_inc))
+    return fail(PZ_EDEGENERATE, "step %u: the innovation covariance is not positive definite", f->t - 1);
+  return PZ_OK;
+}
+
 int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank, int world,
                   const void* nccl_id, pz_filter** out) {
   if (!model || !out) return fail(PZ_EINVAL, "null argument");
@@ -604,6 +760,10 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
     return create_mtt(model, n_global, seed, device, out);
   }
   if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS) return fail(PZ_EINVAL, "unknown model kind %d", model->kind);
+  if (model->delayed) {
+    if (world != 1) return fail(PZ_EINVAL, "a delayed-sampling filter runs on one GPU (all particles are identical)");
+    return create_rb(model, n_global, device, out);
+  }
   if (!((model->nx == 1 && model->ny == 1) || (model->nx == 4 && model->ny == 2) || (model->nx == 6 && model->ny == 3)))
     return fail(PZ_EINVAL, "no kernel instantiated for nx=%d ny=%d (supported: (1,1), (4,2), (6,3))", model->nx, model->ny);
   if (n_global < 1 || n_global > (1ull << 30)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^30]");
@@ -875,6 +1035,7 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
   }
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d, got %d x %d", f->a.model.ny, n_obs, obs_dim);
   PZ_CUDA(cudaSetDevice(f->device));
+  if (f->is_rb) { f->last_ms = 0; f->last_launches = 0; return rb_step_host(f, obs, out); }
   const uint32_t t0 = f->t;
   f->last_launches = 0;
   int rc = stage_obs(f, obs, 1, obs_dim);
@@ -901,7 +1062,7 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
 int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, double ms[3]) {
   if (!f || !obs || !ms) return fail(PZ_EINVAL, "null argument");
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d", f->a.model.ny);
-  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1 || f->is_mtt)
+  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1 || f->is_mtt || f->is_rb)
     return fail(PZ_ESTATE, "profiled step: single-GPU systematic filters only");
   PZ_CUDA(cudaSetDevice(f->device));
   cudaEvent_t ev[4];
@@ -928,6 +1089,13 @@ int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_
   PZ_CUDA(cudaSetDevice(f->device));
   f->last_launches = 0;
   f->last_ms = 0;
+  if (f->is_rb) {
+    for (int64_t i = 0; i < n_steps; ++i) {
+      int rc = rb_step_host(f, obs + i * obs_dim, out ? out + i : nullptr);
+      if (rc) return rc;
+    }
+    return PZ_OK;
+  }
   int64_t done = 0;
   int status = PZ_OK;
   while (done < n_steps) {
@@ -972,6 +1140,7 @@ int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len) {
   if (!f || !out) return fail(PZ_EINVAL, "null argument");
   const StepArgs& a = f->a;
   if (f->is_mtt) return fail(PZ_ESTATE, "tracker state is read with pz_filter_read_tracks");
+  if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter holds no sampled state; use pz_filter_read_posterior");
   if (out_len < a.model.nx * a.n_local) return fail(PZ_EINVAL, "buffer too small: need %lld floats", (long long)(a.model.nx * a.n_local));
   PZ_CUDA(cudaSetDevice(f->device));
   PZ_CUDA(cudaStreamSynchronize(f->stream));
@@ -981,8 +1150,22 @@ int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len) {
   return PZ_OK;
 }
 
+int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out) {
+  if (!f || !mean_out || !cov_out) return fail(PZ_EINVAL, "null argument");
+  if (!f->is_rb) return fail(PZ_ESTATE, "not a delayed-sampling filter (model.delayed = 0)");
+  PZ_CUDA(cudaSetDevice(f->device));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  RbDev h;
+  PZ_CUDA(cudaMemcpy(&h, f->rb, sizeof(RbDev), cudaMemcpyDeviceToHost));
+  const int nx = h.nx;
+  for (int i = 0; i < nx; ++i) mean_out[i] = h.mean[i];
+  for (int i = 0; i < nx * nx; ++i) cov_out[i] = h.cov[i];
+  return PZ_OK;
+}
+
 int pz_filter_read_logw(pz_filter* f, float* out, int64_t n) {
   if (!f || !out) return fail(PZ_EINVAL, "null argument");
+  if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter has equal weights and no sampled state");
   if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
   PZ_CUDA(cudaSetDevice(f->device));
   int rc = generic_alloc(&f->g, f->a.n_local, false);
@@ -995,6 +1178,7 @@ int pz_filter_read_logw(pz_filter* f, float* out, int64_t n) {
 
 int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n) {
   if (!f || !out) return fail(PZ_EINVAL, "null argument");
+  if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter has equal weights and no sampled state");
   if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
   PZ_CUDA(cudaSetDevice(f->device));
   int rc = pending_ancestors(f, nullptr);
@@ -1011,6 +1195,14 @@ int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t 
   const int64_t n_sel = (a.n_local + stride - 1) / stride;
   if (out_len < n_sel * a.model.nx) return fail(PZ_EINVAL, "buffer too small: need %lld doubles", (long long)(n_sel * a.model.nx));
   PZ_CUDA(cudaSetDevice(f->device));
+  if (f->is_rb) {  // every particle is the marginal's mean (the reference emits the marginal itself per particle)
+    double mean[PZ_MAX_NX], cov[PZ_MAX_NX * PZ_MAX_NX];
+    int rc = pz_filter_read_posterior(f, mean, cov);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n_sel; ++i)
+      for (int d = 0; d < a.model.nx; ++d) out[i * a.model.nx + d] = mean[d];
+    return PZ_OK;
+  }
   int rc = pending_ancestors(f, nullptr);
   if (rc) return rc;
   float* d_out = nullptr;

@@ -28,7 +28,7 @@ class MttParams(C.Structure):
 
 class ModelDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
-                ("resampler", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("resampler", C.c_int32), ("delayed", C.c_int32), ("reserved", C.c_int32 * 2),
                 ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
                 ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
                 ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]

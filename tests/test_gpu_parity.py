@@ -224,6 +224,33 @@ def test_long_stream_stays_on_the_kalman_posterior(pz):
     zs.close()
 
 
+@pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
+def test_delayed_sampling_is_the_exact_kalman_recursion(pz, model):
+    """model.delayed = 1 (`delay=True`, SingleTargetTracking.hs:36-38; Demo.hs:215-242): every particle carries
+    the Gaussian marginal of makeMarginal / makeConditional (DelayedSampling.hs:135-152), i.e. the exact Kalman
+    posterior, with equal weights."""
+    hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
+    d = getattr(pz, model)(delay=True)
+    T, n = 60, 5000
+    obs, _ = H.gen_obs(hd, T)
+    hk = {"rw1d": lambda: H.model_rw1d(scalar_ll_2x=0), "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
+    km, kc, kl = H.kalman(hk, obs)     # the delayed posterior conditions on the true R (only the SCORE is doubled)
+    zs = pz.zparticles(n, d, seed=1)
+    for t in range(T):
+        post = zs.step(obs[t])
+        mean, cov = zs.read_posterior()
+        assert np.allclose(mean, km[t], rtol=1e-10, atol=1e-10) and np.allclose(cov, kc[t], rtol=1e-9, atol=1e-12)
+        assert np.allclose(post.mean, km[t], atol=1e-10) and np.allclose(post.var, np.diag(kc[t]), atol=1e-12)
+        assert post.ess == n and post.step == t
+        scale = 2.0 if model == "rw1d" else 1.0   # gaussian_ll' is twice the log-density (Distributions.hs:160-161)
+        assert abs(post.log_evidence_inc - scale * kl[t]) < 1e-9 * max(1.0, abs(kl[t]))
+    parts = post.particles(stride=1000)
+    assert parts.shape == (5, hd.nx) and np.allclose(parts, km[-1][None, :])
+    with pytest.raises(pz.PzError):
+        zs.read_state()
+    zs.close()
+
+
 def test_multinomial_reference_mode(pz):
     """resampler = MULTINOMIAL_REF (resample2, Inference.hs:57-61): bit-exact vs the oracle and
     statistically equal to the systematic filter."""

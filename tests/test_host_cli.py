@@ -25,8 +25,8 @@ def test_cli_builds_and_reports_usage():
     assert r.returncode == 0 and "mtt [N]" in r.stderr and "stt [delay] [N]" in r.stderr
     r = subprocess.run([EXE], capture_output=True, text=True)
     assert r.returncode == 2
-    r = subprocess.run([EXE, "stt", "True", "100"], capture_output=True, text=True)
-    assert r.returncode == 2 and "bootstrap" in r.stderr
+    r = subprocess.run([EXE, "stt", "Maybe", "100"], capture_output=True, text=True)
+    assert r.returncode == 2   # the delay flag is a Haskell Bool
 
 
 def test_cli_has_no_cpu_fallback():
@@ -76,6 +76,12 @@ def test_cli_streams_lines_the_visualiser_parses():
     for ln in r.stdout.strip().split("\n"):
         arr, n = java_app_reads(ln)
         assert len(arr[0]) == 1 and len(arr[0][0][1]) == 6 and len(arr[1]) == 20 and len(arr[2]) == 1 and len(arr[2][0]) == 3
+    # the reference's default `stt` (delay=True): every particle is the marginal {"mean":..,"cov":..}
+    r = subprocess.run([EXE, "stt", "True", "1000", "--steps", "6", "--emit", "10"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for ln in r.stdout.strip().split("\n"):
+        arr, n = java_app_reads(ln)
+        assert len(arr[1]) == 10 and all(isinstance(p[0][1], dict) and len(p[0][1]["cov"]) == 6 for p in arr[1])
     r = subprocess.run([EXE, "rw1d", "100000", "--steps", "8"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     rows = [json.loads(ln) for ln in r.stdout.strip().split("\n")]
