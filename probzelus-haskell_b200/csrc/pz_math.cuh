@@ -58,8 +58,9 @@ static __device__ const float4 g_icdf_tab[PZ_ICDF_ROWS] = PZ_ICDF_TABLE_INIT;
 // the following 23 bits the cubic's argument tf in [1, 2).  tab_m8 = table base - 8 rows (the
 // sub-segment field carries the leading one).
 __device__ __forceinline__ float icdf_normal(uint32_t r, const float4* __restrict__ tab_m8) {
-  const uint32_t v = r + r + 1u;  // (r << 1) | 1
-  const int k = __clz(v);
+  uint32_t v, k;
+  asm("mad.lo.u32 %0, %1, 2, 1;" : "=r"(v) : "r"(r));          // (r << 1) | 1 in one IMAD
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(k) : "r"(v));        // clz(v) (v != 0): FLO.SH, no 31 - x
   const uint32_t vn = v << k;
   const float4 c = tab_m8[(k << PZ_ICDF_SUB_BITS) + (vn >> 28)];
   const float tf = __uint_as_float(0x3F800000u | ((vn >> 5) & 0x7FFFFFu));
