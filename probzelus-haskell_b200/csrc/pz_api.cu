@@ -93,6 +93,10 @@ int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
   p->wscale = dbl ? -1.0f : -0.5f;
   // position/velocity structure: F = [[a,b],[c,d]] (x) I_p, Q = diag(qp I, qv I), H = [I_p 0], R = r I_p
   p->kron = 0;
+  // scalar random walk with unit F and H: multiplying by exactly 1 is exact, so the specialised path skips it
+  if (nx == 1 && ny == 1 && p->F[0][0] == 1.0f && p->H[0][0] == 1.0f && !getenv("PZ_NO_KRON")) {
+    p->kron = 1; p->klp = p->Lq[0][0]; p->krinv = p->Rinv[0][0];
+  }
   if (nx % 2 == 0 && ny == nx / 2 && !getenv("PZ_NO_KRON")) {
     const int P = nx / 2;
     bool ok = true;

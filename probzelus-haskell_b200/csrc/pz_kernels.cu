@@ -180,6 +180,10 @@ __device__ __forceinline__ float lg_logweight(const LgDev& p, const float* xn, c
 // terms whose coefficient is zero
 template <int NX>
 __device__ __forceinline__ void kron_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+  if constexpr (NX == 1) {  // F = 1: fl(1 * x) = x, so fma(L, z, fl(F x)) = fma(L, z, x)
+    xn[0] = __fmaf_rn(p.klp, z[0], x[0]);
+    return;
+  }
   constexpr int P = NX / 2;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
@@ -1448,12 +1452,14 @@ static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
   const bool big = fused_tile_out(nx) == (nx == 1 ? kTileBig1 : kTileBigN);
   if (big) {
     PZ_DISPATCH(1, 1, kTileBig1, false)
+    PZ_DISPATCH(1, 1, kTileBig1, true)
     PZ_DISPATCH(4, 2, kTileBigN, false)
     PZ_DISPATCH(4, 2, kTileBigN, true)
     PZ_DISPATCH(6, 3, kTileBigN, false)
     PZ_DISPATCH(6, 3, kTileBigN, true)
   } else {
     PZ_DISPATCH(1, 1, kTileSmall1, false)
+    PZ_DISPATCH(1, 1, kTileSmall1, true)
     PZ_DISPATCH(4, 2, kTileSmallN, false)
     PZ_DISPATCH(4, 2, kTileSmallN, true)
     PZ_DISPATCH(6, 3, kTileSmallN, false)
