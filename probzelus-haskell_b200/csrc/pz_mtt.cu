@@ -126,10 +126,53 @@ __device__ __forceinline__ void store_track(uint32_t* __restrict__ rec, const Tr
 //      coasting Bernoulli for the others, survivors compacted in id order, then births.
 // HBM traffic is the parent record read once and the child record written once.
 constexpr int kMttThreads = 128;
-constexpr int kMttDerived = 7;  // m0, m1, s00, s01, s11, lnorm, likelihood scratch
+constexpr int kMttDerived = 7;   // m0, m1, s00, s01, s11, lnorm, likelihood scratch
+constexpr int kMttFast = 8;      // track slots whose derived data live in shared memory; the rest (rare) in local memory
+
+// derived-data accessors: slots [0, 8) in shared memory [field][slot][thread], slots [8, 16) in a per-thread array
+struct DerShared {
+  float* base; int tid;
+  __device__ __forceinline__ float& operator()(int f, int k) const { return base[(f * kMttFast + k) * kMttThreads + tid]; }
+};
+struct DerLocal {
+  float* loc;
+  __device__ __forceinline__ float& operator()(int f, int k) const { return loc[f * (16 - kMttFast) + (k - kMttFast)]; }
+};
+
+template <class Der>
+__device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __restrict__ src, int k, const Der& der) {
+  Track tr;
+  load_track(src + 4 + 16 * k, tr);
+  predict(p, tr);
+  const float sa = tr.c[0] + p.r, sb = tr.c[1], sd = tr.c[4] + p.r;
+  const float det = sa * sd - sb * sb, idet = 1.0f / det;
+  der(0, k) = tr.m[0]; der(1, k) = tr.m[1];
+  der(2, k) = sd * idet; der(3, k) = -sb * idet; der(4, k) = sa * idet;
+  der(5, k) = -0.5f * __logf(det) - 1.8378770664093453f;
+}
+template <class Der>
+__device__ __forceinline__ float mtt_like(const MttDev& p, float z0, float z1, uint32_t assigned, int k, const Der& der) {
+  float like = 0.f;
+  if (!((assigned >> k) & 1u)) {
+    const float d0 = z0 - der(0, k), d1 = z1 - der(1, k);
+    const float quad = der(2, k) * d0 * d0 + 2.0f * der(3, k) * d0 * d1 + der(4, k) * d1 * d1;
+    like = p.pspd * __expf(der(5, k) - 0.5f * quad);
+  }
+  der(6, k) = like;
+  return like;
+}
+template <class Der>
+__device__ __forceinline__ void mtt_pick(float target, int k, const Der& der, float& cum, int& pick, int& last) {
+  const float like = der(6, k);
+  if (like > 0.f) {
+    last = k;
+    cum += like;
+    if (pick < 0 && cum > target) pick = k;
+  }
+}
 
 __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ MttArgs a) {
-  extern __shared__ float s_der[];  // [kMttDerived][16][kMttThreads]
+  extern __shared__ float s_der[];  // [kMttDerived][kMttFast][kMttThreads]
   __shared__ float s_z[32][2], s_lc[32], s_ln[32];
   const int tid = threadIdx.x;
   const int M = a.n_obs;
@@ -143,27 +186,22 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   __syncthreads();
   const int64_t j = (int64_t)blockIdx.x * kMttThreads + tid;
   if (j >= a.n) return;
-  auto der = [&](int f, int k) -> float& { return s_der[(f * 16 + k) * kMttThreads + tid]; };
+  float loc[kMttDerived * (16 - kMttFast)];
+  const DerShared ds{s_der, tid};
+  const DerLocal dl{loc};
   const uint32_t t = a.ctl->t;
   const int64_t par = a.anc[j];
   const uint32_t* __restrict__ src = a.sin + (size_t)par * kMttWords;
   uint32_t* __restrict__ dst = a.sout + (size_t)j * kMttWords;
   const uint4 hdr = *reinterpret_cast<const uint4*>(src);
   const int cnt = (int)hdr.x;
+  const int cnt_fast = cnt < kMttFast ? cnt : kMttFast;
   const int next_id = (int)hdr.y;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
 
   // ---- pass A: predictive density of a measurement of every track: N(z; H m, H P H^T + r I)
-  for (int k = 0; k < cnt; ++k) {
-    Track tr;
-    load_track(src + 4 + 16 * k, tr);
-    predict(a.p, tr);
-    const float sa = tr.c[0] + a.p.r, sb = tr.c[1], sd = tr.c[4] + a.p.r;
-    const float det = sa * sd - sb * sb, idet = 1.0f / det;
-    der(0, k) = tr.m[0]; der(1, k) = tr.m[1];
-    der(2, k) = sd * idet; der(3, k) = -sb * idet; der(4, k) = sa * idet;
-    der(5, k) = -0.5f * __logf(det) - 1.8378770664093453f;
-  }
+  for (int k = 0; k < cnt_fast; ++k) mtt_derive(a.p, src, k, ds);
+  for (int k = kMttFast; k < cnt; ++k) mtt_derive(a.p, src, k, dl);
 
   // ---- pass B: association proposal; uniforms: detection o takes word o & 3 of Philox call o >> 2
   uint32_t assigned = 0;   // bit k: track k has a detection
@@ -176,16 +214,8 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     const uint32_t word = (o & 3) == 0 ? rnd.x : ((o & 3) == 1 ? rnd.y : ((o & 3) == 2 ? rnd.z : rnd.w));
     const float z0 = s_z[o][0], z1 = s_z[o][1];
     float ttot = 0.f;
-    for (int k = 0; k < cnt; ++k) {
-      float like = 0.f;
-      if (!((assigned >> k) & 1u)) {
-        const float d0 = z0 - der(0, k), d1 = z1 - der(1, k);
-        const float quad = der(2, k) * d0 * d0 + 2.0f * der(3, k) * d0 * d1 + der(4, k) * d1 * d1;
-        like = a.p.pspd * __expf(der(5, k) - 0.5f * quad);
-      }
-      der(6, k) = like;
-      ttot += like;
-    }
+    for (int k = 0; k < cnt_fast; ++k) ttot += mtt_like(a.p, z0, z1, assigned, k, ds);
+    for (int k = kMttFast; k < cnt; ++k) ttot += mtt_like(a.p, z0, z1, assigned, k, dl);
     const float lc = s_lc[o], ln = s_ln[o];
     const float tot = lc + ln + ttot;
     lw += __logf(tot);
@@ -198,14 +228,8 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
       const float target = u - lc - ln;
       float cum = 0.f;
       int pick = -1, last = -1;
-      for (int k = 0; k < cnt; ++k) {
-        const float like = der(6, k);
-        if (like > 0.f) {
-          last = k;
-          cum += like;
-          if (pick < 0 && cum > target) pick = k;
-        }
-      }
+      for (int k = 0; k < cnt_fast; ++k) mtt_pick(target, k, ds, cum, pick, last);
+      for (int k = kMttFast; k < cnt; ++k) mtt_pick(target, k, dl, cum, pick, last);
       if (pick < 0) pick = last;          // round-off past the last candidate: take the last one
       if (pick < 0) newmask |= 1u << o;   // no candidate track at all: start a track
       else {
@@ -345,7 +369,7 @@ int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, con
   MttArgs a;
   a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.n = n; a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
-  const size_t smem = (size_t)kMttDerived * 16 * kMttThreads * sizeof(float);  // 56 KB
+  const size_t smem = (size_t)kMttDerived * kMttFast * kMttThreads * sizeof(float);  // 28 KB
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(mtt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
