@@ -17,6 +17,8 @@
 //
 // Unlike the linear-Gaussian kernels this translation unit is NOT bound by the bit-exact fp32
 // spec (parity for MTT is statistical): it uses fast intrinsics and fmad.
+#include <cstdlib>
+
 #include "pz_kernels.cuh"
 #include "pz_math.cuh"
 
@@ -26,6 +28,8 @@ constexpr uint32_t kStreamMtt = 0x4D545453u;  // "MTTS"
 
 struct MttDev {
   float F[4][4], Q[4][4];
+  int kron;             // F = [[a, b], [c, d]] (x) I2 and diagonal Q (the reference's constant-velocity model)
+  float fa, fb, fc, fd;
   float lc, lb, pspd, p_coast, log1m_pspd;
   float cv, bp, bv, r;
   float cl_norm, nb_norm;  // log normalisers of the clutter / new-track predictive densities
@@ -43,7 +47,31 @@ __device__ __forceinline__ int tri(int i, int j) {  // index of (i, j), i <= j
 }
 __device__ __forceinline__ float sym(const float* c, int i, int j) { return i <= j ? c[tri(i, j)] : c[tri(j, i)]; }
 
+// position/velocity structured predict: with P = [[A, B], [B^T, D]] (2x2 blocks; c[] holds A = {0,1,4},
+// B = {2,3,5,6}, D = {7,8,9}),  F P F^T = [[a^2 A + ab (B + B^T) + b^2 D, ac A + ad B + bc B^T + bd D], [., c^2 A + cd (B + B^T) + d^2 D]]
+__device__ __forceinline__ void predict_kron(const MttDev& p, Track& t) {
+  const float a = p.fa, b = p.fb, c = p.fc, d = p.fd;
+  const float m0 = a * t.m[0] + b * t.m[2], m1 = a * t.m[1] + b * t.m[3];
+  const float m2 = c * t.m[0] + d * t.m[2], m3 = c * t.m[1] + d * t.m[3];
+  t.m[0] = m0; t.m[1] = m1; t.m[2] = m2; t.m[3] = m3;
+  const float A00 = t.c[0], A01 = t.c[1], A11 = t.c[4];
+  const float B00 = t.c[2], B01 = t.c[3], B10 = t.c[5], B11 = t.c[6];
+  const float D00 = t.c[7], D01 = t.c[8], D11 = t.c[9];
+  const float aa = a * a, ab = a * b, bb = b * b, ac = a * c, ad = a * d, bc = b * c, bd = b * d, cc = c * c, cd = c * d, dd = d * d;
+  t.c[0] = aa * A00 + ab * (B00 + B00) + bb * D00 + p.Q[0][0];
+  t.c[1] = aa * A01 + ab * (B01 + B10) + bb * D01;
+  t.c[4] = aa * A11 + ab * (B11 + B11) + bb * D11 + p.Q[1][1];
+  t.c[2] = ac * A00 + ad * B00 + bc * B00 + bd * D00;
+  t.c[3] = ac * A01 + ad * B01 + bc * B10 + bd * D01;
+  t.c[5] = ac * A01 + ad * B10 + bc * B01 + bd * D01;
+  t.c[6] = ac * A11 + ad * B11 + bc * B11 + bd * D11;
+  t.c[7] = cc * A00 + cd * (B00 + B00) + dd * D00 + p.Q[2][2];
+  t.c[8] = cc * A01 + cd * (B01 + B10) + dd * D01;
+  t.c[9] = cc * A11 + cd * (B11 + B11) + dd * D11 + p.Q[3][3];
+}
+
 __device__ __forceinline__ void predict(const MttDev& p, Track& t) {
+  if (p.kron) { predict_kron(p, t); return; }
   float m[4], FP[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -353,6 +381,14 @@ int mtt_words_per_particle() { return kMttWords; }
 void mtt_fill_params(const pz_model_desc* d, void* out_mttdev) {
   MttDev& p = *reinterpret_cast<MttDev*>(out_mttdev);
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { p.F[i][j] = (float)d->F[i * 4 + j]; p.Q[i][j] = (float)d->Q[i * 4 + j]; }
+  p.fa = p.F[0][0]; p.fb = p.F[0][2]; p.fc = p.F[2][0]; p.fd = p.F[2][2];
+  p.kron = 1;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const float fexp = (i % 2 == j % 2) ? (i < 2 ? (j < 2 ? p.fa : p.fb) : (j < 2 ? p.fc : p.fd)) : 0.0f;
+      if (p.F[i][j] != fexp || (i != j && p.Q[i][j] != 0.0f)) p.kron = 0;
+    }
+  if (getenv("PZ_NO_KRON")) p.kron = 0;
   const double pspd = d->mtt.survival_prob * d->mtt.pd;
   p.lc = (float)d->mtt.clutter_lambda; p.lb = (float)d->mtt.new_track_lambda; p.pspd = (float)pspd;
   p.p_coast = (float)((1.0 - d->mtt.pd) / (1.0 - pspd));
