@@ -289,6 +289,9 @@ def run_b200(args):
     name = args.model
     nx, ny = MODELS[name]
     n_p = args.particles
+    scaling = "weak"
+    if args.total_particles:
+        n_p, scaling = args.total_particles // world, "strong"
     if world > 1:
         n_p -= n_p % 256  # a sharded filter holds whole resampling blocks (256 particles) per rank
     K, W = args.steps, args.warmup
@@ -383,7 +386,7 @@ def run_b200(args):
                                  "sample": f"configs[0]: N=1000 x 100 steps, literal O(N^2) resample2 ({fdt:.1f} s)"}}
     line = {
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name} bootstrap particle filter, N={n_p} particles per GPU (BASELINE.json configs[1])",
                    "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp32",
@@ -411,7 +414,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="rw1d", choices=list(MODELS))
-    ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU")
+    ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU (weak scaling, the default)")
+    ap.add_argument("--total-particles", type=int, default=0,
+                    help="strong scaling: the whole population, split evenly over the GPUs (overrides --particles)")
     ap.add_argument("--cpu-particles", type=int, default=2_000_000, help="bounded CPU sample size")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mtt-tracks", type=int, default=8, help="tracker bench: targets present at t = 0")
