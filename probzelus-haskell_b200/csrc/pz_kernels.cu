@@ -713,7 +713,7 @@ struct BlockIn {
   }
 };
 
-template <bool SEGDUP, class Source>
+template <bool SEGDUP, int NW, class Source>
 __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const uint16_t* __restrict__ qin,
                                               const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
                                               int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
@@ -722,9 +722,9 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
   const uint32_t jend = j0 + (uint32_t)nslots;
   int64_t b = b_first + warp;
   if (b >= b_end) return;
-  for (; b < b_end; b += kWarps) {
+  for (; b < b_end; b += NW) {
     const BlockIn in = cur;
-    const int64_t bn = b + kWarps;
+    const int64_t bn = b + NW;
     if (bn < b_end) cur.load(qin, ebx, xb, bn, lane);  // next iteration's inputs: in flight during this one
     const uint32_t o0 = (uint32_t)(in.X0 >> 32), o1 = (uint32_t)(in.X1 >> 32);
     if (o0 >= jend) break;                  // this and every later block start past the tile
@@ -984,11 +984,13 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
   }
 }
 
-template <int NX, int NY, int TO, int MODE, bool KRON>
-__global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __grid_constant__ TileArgs ta) {
+// NT threads per CTA (NW warps): 256 by default; PZ_NT1 = 128 runs the NX = 1 kernel with half-size CTAs
+template <int NX, int NY, int TO, int MODE, bool KRON, int NT>
+__global__ void __launch_bounds__(NT, min_ctas(NX) * (kThreads / NT)) pf_step_tile(const __grid_constant__ TileArgs ta) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float s_par[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
-  __shared__ int32_t s_eref[kWarps];
-  __shared__ double s_red[kWarps][kMaxRec];
+  __shared__ int32_t s_eref[NW];
+  __shared__ double s_red[NW][kMaxRec];
   float4* s_tab = reinterpret_cast<float4*>(s_par + NX * TO);
   const StepArgs& a = ta.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1010,18 +1012,18 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
     const int64_t b_first = (int64_t)a.tile_start[blockIdx.x];
     BlockIn first{};
     if (b_first + warp < a.b_hi) first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
-    s_tab[tid] = g_icdf_tab[tid];  // kThreads == PZ_ICDF_ROWS
+    for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
     // sentinel in dimension 0 of every slot: "no head here"
     uint4* sz = reinterpret_cast<uint4*>(s_par);
-    for (int i = tid; i < TO / 4; i += kThreads) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    for (int i = tid; i < TO / 4; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
     StateSource<NX> src;
     src.x = xin; src.ld = a.ld;
-    resample_tile<(NX != 1)>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
+    resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
                              lane, warp, first);
   } else {
-    s_tab[tid] = g_icdf_tab[tid];
-    for (int sidx = tid; sidx < nslots; sidx += kThreads) {
+    for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
+    for (int sidx = tid; sidx < nslots; sidx += NT) {
       const int64_t p = ta.anc[j0l + sidx];
 #pragma unroll
       for (int d = 0; d < NX; ++d) s_par[d * TO + sidx] = xin[(size_t)d * a.ld + p];
@@ -1039,10 +1041,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
 #pragma unroll
   for (int d = 0; d < NX; ++d) cen[d] = pl->center[d];
   if (nslots == TO) {
-    for (int ob = warp; ob < TO / kBlk; ob += kWarps)
+    for (int ob = warp; ob < TO / kBlk; ob += NW)
       output_block<NX, NY, TO, MODE, KRON, true>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   } else {
-    for (int ob = warp; ob * kBlk < nslots; ob += kWarps)
+    for (int ob = warp; ob * kBlk < nslots; ob += NW)
       output_block<NX, NY, TO, MODE, KRON, false>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   }
 
@@ -1051,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
   __syncthreads();
   int32_t etile = kNZero;
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) etile = max(etile, s_eref[w]);
+  for (int w = 0; w < NW; ++w) etile = max(etile, s_eref[w]);
   {
     const double g = (aref == kNZero) ? 0.0 : pow2d(aref - etile);
 #pragma unroll
@@ -1067,7 +1069,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(NX)) pf_step_tile(const __g
   if (tid < 3 + 2 * NX) {
     double x = 0;
     if (tid == 0) x = (double)etile;
-    else for (int w = 0; w < kWarps; ++w) x += s_red[w][tid];
+    else for (int w = 0; w < NW; ++w) x += s_red[w][tid];
     a.rec[(size_t)blockIdx.x * kMaxRec + tid] = x;
   }
   if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
@@ -1145,7 +1147,7 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   const int64_t b_first = (int64_t)g.tile_start[blockIdx.x];
   BlockIn first{};
   if (b_first + warp < g.nblk) first.load(generic_q(g), generic_eb(g), g.xb, b_first + warp, lane);
-  resample_tile<true>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, b_first, g.nblk, pl->emax, pl->h0, pl->Mq, (uint32_t)j0,
+  resample_tile<true, kWarps>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, b_first, g.nblk, pl->emax, pl->h0, pl->Mq, (uint32_t)j0,
                       nslots, lane, warp, first);
   __syncthreads();
   for (int seg = warp; seg * 128 < nslots; seg += kWarps) {
@@ -1364,13 +1366,27 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
 // ------------------------------------------------------------------------------------------
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Output slots per CTA: 8k - 1 canonical blocks, because a tile of m output blocks draws on m + 1
-// input blocks in the typical case and the 8 warps of the CTA take input blocks round-robin (a
-// remainder of one block would leave 7 warps waiting at the barrier).  Larger tiles amortise the
+// Output slots per CTA: (a multiple of the CTA's warp count) - 1 canonical blocks, because a tile of m
+// output blocks draws on m + 1 input blocks in the typical case and the warps of the CTA take input
+// blocks round-robin (a remainder of one block would leave the other warps waiting at the barrier).  Larger tiles amortise the
 // extra input block and the CTA-level reduction; PZ_TILE_OUT=small selects the smaller
 // instantiation (kept for A/B measurements, profiles/README.md).
-constexpr int kTileBig1 = 31 * kBlk, kTileSmall1 = 15 * kBlk;   // NX = 1
-constexpr int kTileBigN = 15 * kBlk, kTileSmallN = 7 * kBlk;    // NX > 1
+// CTA size and tile size of the step kernel (measured, profiles/README.md): half-size CTAs put twice as
+// many independent, phase-shifted tiles on an SM and halve the barrier domain.
+#ifndef PZ_NT1
+#define PZ_NT1 128   // threads per CTA, NX = 1
+#endif
+#ifndef PZ_TB1
+#define PZ_TB1 23    // output blocks per tile, NX = 1 (a multiple of the warp count, minus 1)
+#endif
+#ifndef PZ_NTN
+#define PZ_NTN 256   // threads per CTA, NX > 1
+#endif
+#ifndef PZ_TBN
+#define PZ_TBN 15    // output blocks per tile, NX > 1
+#endif
+constexpr int kTileBig1 = PZ_TB1 * kBlk, kTileSmall1 = 15 * kBlk;   // NX = 1
+constexpr int kTileBigN = PZ_TBN * kBlk, kTileSmallN = 7 * kBlk;    // NX > 1
 int fused_tile_out(int nx) {
   static const bool small = [] { const char* e = getenv("PZ_TILE_OUT"); return e && !strcmp(e, "small"); }();
   if (nx == 1) return small ? kTileSmall1 : kTileBig1;
@@ -1428,7 +1444,8 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
 
 template <int NX, int NY, int TO, int MODE, bool KRON>
 static void launch_tile(const TileArgs& ta, cudaStream_t s) {
-  auto kern = pf_step_tile<NX, NY, TO, MODE, KRON>;
+  constexpr int NT = (NX == 1) ? PZ_NT1 : PZ_NTN;
+  auto kern = pf_step_tile<NX, NY, TO, MODE, KRON, NT>;
   // staged parents [NX][TO] + inverse-CDF table
   size_t smem = (size_t)NX * TO * sizeof(float) + PZ_ICDF_ROWS * sizeof(float4);
   static bool attr_done = false;
@@ -1436,7 +1453,7 @@ static void launch_tile(const TileArgs& ta, cudaStream_t s) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  kern<<<ta.a.ntiles_out, kThreads, smem, s>>>(ta);
+  kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
 }
 
 static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
