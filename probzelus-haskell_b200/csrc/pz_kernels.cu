@@ -643,9 +643,12 @@ constexpr uint32_t kSentinel = 0x7FC0DEADu;  // a NaN payload no arithmetic prod
 template <int NX>
 struct StateSource {
   static constexpr int NV = NX;
+  static constexpr bool kPrefetch = (NX == 1);  // one word per particle: fetched one block ahead (registers)
   const float* x;  // X[cur]
   int64_t ld;
   float v[NX][4];
+  __device__ __forceinline__ float4 fetch(int64_t i0) const { return *reinterpret_cast<const float4*>(x + i0); }
+  __device__ __forceinline__ void set(const float4& f) { v[0][0] = f.x; v[0][1] = f.y; v[0][2] = f.z; v[0][3] = f.w; }
   __device__ __forceinline__ void load(int64_t i0) {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
@@ -661,7 +664,10 @@ struct StateSource {
 
 struct IndexSource {  // generic path: payload = particle index
   static constexpr int NV = 1;
+  static constexpr bool kPrefetch = false;
   float v[1][4];
+  __device__ __forceinline__ float4 fetch(int64_t) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void set(const float4&) {}
   __device__ __forceinline__ void load(int64_t i0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[0][k] = __int_as_float((int32_t)i0 + k);
@@ -722,16 +728,26 @@ __device__ __forceinline__ void resample_tile(Source& src, float* s_par, int str
   const uint32_t jend = j0 + (uint32_t)nslots;
   int64_t b = b_first + warp;
   if (b >= b_end) return;
+  // narrow payloads (one word per particle) are prefetched one block ahead together with the weights;
+  // wide ones are loaded at the top of their own iteration (registers)
+  constexpr bool kAhead = Source::kPrefetch;
+  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;   // prefetched payload of the current block
+  if constexpr (kAhead) { pa = src.fetch(b * kBlk + lane * 4); pb = src.fetch(b * kBlk + lane * 4 + 128); }
   for (; b < b_end; b += NW) {
     const BlockIn in = cur;
+    const float4 xa = pa, xb4 = pb;
     const int64_t bn = b + NW;
-    if (bn < b_end) cur.load(qin, ebx, xb, bn, lane);  // next iteration's inputs: in flight during this one
+    if (bn < b_end) {  // next iteration's inputs: in flight during this one
+      cur.load(qin, ebx, xb, bn, lane);
+      if constexpr (kAhead) { pa = src.fetch(bn * kBlk + lane * 4); pb = src.fetch(bn * kBlk + lane * 4 + 128); }
+    }
     const uint32_t o0 = (uint32_t)(in.X0 >> 32), o1 = (uint32_t)(in.X1 >> 32);
     if (o0 >= jend) break;                  // this and every later block start past the tile
     if (o1 == o0 || o1 <= j0) continue;     // no children (every empty block), or none in this tile
     const int64_t ia = b * kBlk + lane * 4;
     Source sa = src, sb = src;
-    sa.load(ia); sb.load(ia + 128);         // payload of the lane's 8 particles, in flight during the scan
+    if constexpr (kAhead) { sa.set(xa); sb.set(xb4); }
+    else { sa.load(ia); sb.load(ia + 128); }  // payload of the lane's 8 particles, in flight during the scan
     const int h = h0 + (emax - in.ebb);
     uint32_t c[8];
     c[0] = in.qa.x & 0xffffu;
