@@ -483,10 +483,14 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       int64_t J = (int64_t)tile * rpc + q;
       if (J < s.nrec) {
         const double* rc = s.rec + (size_t)J * kMaxRec;
-        double et = rc[0];
+        double v[kMaxRec];  // the whole record first: independent loads, one L2 round trip
+#pragma unroll
+        for (int r = 0; r < kMaxRec; ++r) v[r] = (r < R) ? rc[r] : 0.0;
+        const double et = v[0];
         if (et > -1.0e9) {
-          double f = pow2d((int)et - emax);
-          for (int r = 1; r < R; ++r) acc[r] += rc[r] * (r == 2 ? f * f : f);
+          const double f = pow2d((int)et - emax);
+#pragma unroll
+          for (int r = 1; r < kMaxRec; ++r) acc[r] += v[r] * (r == 2 ? f * f : f);
         }
       }
     }
@@ -514,8 +518,19 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   if (have_rec) {  // per-CTA partials -> totals: 16 groups of 16 threads, fixed order (deterministic)
     const int r = tid & 15, grp = tid >> 4;
     double x = 0;
-    if (r >= 1 && r < R)
-      for (int c = grp; c < s.nscan; c += kThreads / 16) x += ((volatile double*)s.part)[(size_t)c * kMaxRec + r];
+    if (r >= 1 && r < R) {
+      // batches of 8 independent L2 loads (a load-add-load-add chain would serialise on the L2 latency)
+      constexpr int G = kThreads / 16;
+      int c = grp;
+      for (; c + 7 * G < s.nscan; c += 8 * G) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(s.part + (size_t)(c + u * G) * kMaxRec + r);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x += v[u];
+      }
+      for (; c < s.nscan; c += G) x += __ldcg(s.part + (size_t)c * kMaxRec + r);
+    }
     s_grp[grp][r] = x;
     __syncthreads();
     if (tid >= 1 && tid < R) {
