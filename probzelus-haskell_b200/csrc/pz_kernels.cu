@@ -2,14 +2,15 @@
 //
 // One time step of zparticles' (haskell/src/Inference.hs:101-104) is three launches:
 //
-//   pf_step_tile<NX,NY,TO,MODE>   per output tile of TO slots:
+//   pf_step_tile<NX,NY,TO,MODE,KRON,NT>   per output tile of TO slots:
 //       input side  -- from the merge-path entry of the tile, read the 16-bit weights of the input
-//                      blocks whose children reach the tile, warp-scan them, map every particle's
-//                      cumulative weight to its last child slot with one 32x32+64 multiply-add, and
-//                      store the particle's state straight into the shared-memory slots of its
-//                      children (resample2 + `fst . (xs !!)`, Inference.hs:57-61, as a systematic
-//                      resampler; runs longer than 16 children go through a per-CTA queue);
-//       output side -- per child: Philox word -> inverse-CDF normal, x' = F x + L z
+//                      blocks whose children reach the tile (next block prefetched), warp-scan them,
+//                      map every particle's cumulative weight to its last child slot with one
+//                      32x32+64 multiply-add, and store the particle's state at the shared-memory
+//                      slot of its FIRST child (head mark; resample2 + `fst . (xs !!)`,
+//                      Inference.hs:57-61, as a systematic resampler);
+//       output side -- resolve the head of every slot (one ballot per 128 slots), then per child:
+//                      Philox word -> inverse-CDF normal, x' = F x + L z
 //                      (noisyIntegrateGen Demo.hs:184-187; SingleTargetTracking.hs:34;
 //                      MultiTargetTracking.hs:56-67), the new log-weight (score/factor/observe,
 //                      Distributions.hs:29-36,160-161; MVDistributions.hs:45-46), its block
