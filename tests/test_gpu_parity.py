@@ -200,6 +200,25 @@ def test_posterior_matches_kalman(pz, model):
         assert abs(ll.mean() - kl.sum()) < 4 * ll.std(ddof=1) / np.sqrt(seeds) + 0.02
 
 
+def test_quantised_weights_carry_no_visible_bias_at_large_n(pz):
+    """N = 2^28: the Monte Carlo error of the posterior mean is ~10^-4 standard deviations per step and
+    ~10^-5 for the average over 200 steps, small enough to expose a systematic effect of the 16-bit
+    block-relative weights or of the fp32 model step -- none is visible against the exact Kalman filter."""
+    hd = H.model_rw1d()
+    T, n = 200, 1 << 28
+    obs, _ = H.gen_obs(hd, T)
+    km, kc, _ = H.kalman(hd, obs)           # exact target of the doubled score (R_eff = R / 2)
+    zs = pz.zparticles(n, pz.rw1d(), seed=11)
+    posts = zs.run(obs)
+    err = np.array([p.mean[0] for p in posts]) - km[:, 0]
+    sd = np.sqrt(kc[:, 0, 0])
+    assert np.sqrt(np.mean((err[20:] / sd[20:]) ** 2)) < 4e-4    # per step: ~ sqrt(2 / N) with resampling noise
+    assert abs(np.mean(err[20:] / sd[20:])) < 6e-5               # time average: no bias at the 10^-5 level
+    verr = np.array([p.var[0] for p in posts])[20:] / kc[20:, 0, 0] - 1
+    assert abs(verr.mean()) < 2e-4
+    zs.close()
+
+
 def test_long_stream_stays_on_the_kalman_posterior(pz):
     """BASELINE configs[2] shape: the 2-D position/velocity tracker over 10^4 steps (N = 10^6 here).  The
     filter neither degenerates nor drifts: over the last 2000 steps the posterior mean tracks the exact
