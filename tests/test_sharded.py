@@ -207,15 +207,17 @@ def _gpu_worker(rank, world, port, model, n_global, seed, T, env, outdir):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["peer_memory", "nccl"])
 @pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
-def test_sharded_equals_single_gpu(pz, model, exchange, tmp_path):
-    """Both exchange implementations (kernels over NVLink peer memory; NCCL calls between the kernels)."""
+def test_sharded_equals_single_gpu(pz, model, exchange, world, tmp_path):
+    """Both exchange implementations (kernels over NVLink peer memory; NCCL calls between the kernels),
+    at every rank count the box offers."""
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world, n_global, seed, T = 2, 2 * 256 * 101, 99, 6  # partial last tile on every rank
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n_global, seed, T = world * 256 * 101, 99, 6  # partial last tile on every rank
     env = {"PZ_SHARD_NCCL": "1"} if exchange == "nccl" else {}
     mp.spawn(_gpu_worker, args=(world, _free_port(), model, n_global, seed, T, env, str(tmp_path)), nprocs=world, join=True)
     d = getattr(pz, model)()
