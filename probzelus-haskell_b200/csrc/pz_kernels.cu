@@ -378,14 +378,15 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   __shared__ double s_grp[kThreads / 16][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&s.ctl->scan_counter, 1u);
+  int32_t emax = s.ctl->emax_acc;            // in flight together with the tile-id atomic
+  const uint32_t t_pop = s.ctl->t + (uint32_t)s.delta;
   __syncthreads();
   const uint32_t tile = s_tile;
-  int32_t emax = s.ctl->emax_acc;
   if (s.p2p) {
     // all-reduce(max) of the block exponent over peer memory: the first CTA stores this rank's value
     // into every mailbox, every CTA polls its own mailbox for all ranks' values of this epoch
     __shared__ int32_t s_emax;
-    const unsigned long long epoch = (unsigned long long)(s.ctl->t + (uint32_t)s.delta + 1u);
+    const unsigned long long epoch = (unsigned long long)(t_pop + 1u);
     if (warp == 0) {
       if (tile == 0 && lane < s.world) st_sys(&s.p2p->mbox[lane]->emax[s.rank], (epoch << 32) | (uint32_t)emax);
       int32_t v = kNZero;
@@ -401,7 +402,23 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
     __syncthreads();
     emax = s_emax;
   }
-  const int32_t* __restrict__ ebp = ((s.ctl->t + (uint32_t)s.delta) & 1u) ? s.eb1 : s.eb0;
+  const int32_t* __restrict__ ebp = (t_pop & 1u) ? s.eb1 : s.eb0;
+
+  // ---- this CTA's slice of the moment records: loads issued now, folded while the look-back waits
+  const int R = 3 + 2 * s.nx;
+  const bool have_rec = (s.rec != nullptr) && (s.nrec > 0) && (s.delta != 0);
+  const int rpc = have_rec ? (s.nrec + s.nscan - 1) / s.nscan : 0;
+  double rv[kMaxRec];
+  bool rec_live = false;
+  if (have_rec && tid < rpc) {
+    const int64_t J = (int64_t)tile * rpc + tid;
+    if (J < s.nrec) {
+      rec_live = true;
+      const double* rc = s.rec + (size_t)J * kMaxRec;
+#pragma unroll
+      for (int r = 0; r < kMaxRec; ++r) rv[r] = (r < R) ? rc[r] : 0.0;
+    }
+  }
 
   // ---- local scan of kScanItems block sums per thread
   u64 v[kScanItems];
@@ -430,14 +447,46 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   }
   u64 excl = wbase + incl - tsum;
 
+  // ---- publish this tile's aggregate at once (successors can add it without waiting for our prefix)
+  volatile u64* st = s.status;
+  if (tid == 0) st[tile] = (tile == 0 ? kFlagIncl : kFlagAgg) | agg;
+
+  // ---- moment records -> per-CTA partial at the global exponent (overlaps the predecessors' progress)
+  if (have_rec) {
+    double acc[kMaxRec];
+#pragma unroll
+    for (int r = 0; r < kMaxRec; ++r) acc[r] = 0.0;
+    if (rec_live && rv[0] > -1.0e9) {
+      const double f = pow2d((int)rv[0] - emax);
+#pragma unroll
+      for (int r = 1; r < kMaxRec; ++r) acc[r] = rv[r] * (r == 2 ? f * f : f);
+    }
+    for (int q = tid + kThreads; q < rpc; q += kThreads) {  // more than 256 records per CTA: rare
+      const int64_t J = (int64_t)tile * rpc + q;
+      if (J < s.nrec) {
+        const double* rc = s.rec + (size_t)J * kMaxRec;
+        double v2[kMaxRec];
+#pragma unroll
+        for (int r = 0; r < kMaxRec; ++r) v2[r] = (r < R) ? rc[r] : 0.0;
+        if (v2[0] > -1.0e9) {
+          const double f = pow2d((int)v2[0] - emax);
+#pragma unroll
+          for (int r = 1; r < kMaxRec; ++r) acc[r] += v2[r] * (r == 2 ? f * f : f);
+        }
+      }
+    }
+    for (int r = 1; r < R; ++r) {
+      double x = acc[r];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
+      if (lane == 0) s_red[warp][r] = x;
+    }
+  }
+
   // ---- decoupled look-back (warp 0)
   if (warp == 0) {
-    volatile u64* st = s.status;
     u64 prefix = 0;
-    if (tile == 0) {
-      if (lane == 0) st[0] = kFlagIncl | agg;
-    } else {
-      if (lane == 0) st[tile] = kFlagAgg | agg;
+    if (tile != 0) {
       int64_t look = (int64_t)tile - 1;
       while (true) {
         int64_t idx = look - lane;
@@ -471,42 +520,10 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
     s.pb[s.nblk] = prefix + agg;
     s.plan->local_total = prefix + agg;
   }
-
-  // ---- moment records -> per-CTA partial at the global exponent
-  const int R = 3 + 2 * s.nx;
-  const bool have_rec = (s.rec != nullptr) && (s.nrec > 0) && (s.delta != 0);
-  if (have_rec) {
-    double acc[kMaxRec];
-#pragma unroll
-    for (int r = 0; r < kMaxRec; ++r) acc[r] = 0.0;
-    const int rpc = (s.nrec + s.nscan - 1) / s.nscan;
-    for (int q = tid; q < rpc; q += kThreads) {
-      int64_t J = (int64_t)tile * rpc + q;
-      if (J < s.nrec) {
-        const double* rc = s.rec + (size_t)J * kMaxRec;
-        double v[kMaxRec];  // the whole record first: independent loads, one L2 round trip
-#pragma unroll
-        for (int r = 0; r < kMaxRec; ++r) v[r] = (r < R) ? rc[r] : 0.0;
-        const double et = v[0];
-        if (et > -1.0e9) {
-          const double f = pow2d((int)et - emax);
-#pragma unroll
-          for (int r = 1; r < kMaxRec; ++r) acc[r] += v[r] * (r == 2 ? f * f : f);
-        }
-      }
-    }
-    for (int r = 1; r < R; ++r) {
-      double x = acc[r];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
-      if (lane == 0) s_red[warp][r] = x;
-    }
-    __syncthreads();
-    if (tid >= 1 && tid < R) {
-      double x = 0;
-      for (int w = 0; w < kWarps; ++w) x += s_red[w][tid];
-      s.part[(size_t)tile * kMaxRec + tid] = x;
-    }
+  if (have_rec && tid >= 1 && tid < R) {  // (s_red was completed before the barrier above)
+    double x = 0;
+    for (int w = 0; w < kWarps; ++w) x += s_red[w][tid];
+    s.part[(size_t)tile * kMaxRec + tid] = x;
   }
 
   // ---- last CTA: plan + posterior summary
