@@ -56,3 +56,15 @@ def test_argument_validation(pz):
     assert pz.lib().pz_filter_create(C.byref(d), 100, 0, 0, C.byref(h)) == -1
     assert b"nx=9" in pz.lib().pz_last_error()
     assert pz.lib().pz_model_rw1d(None, 1.0, 3.0) == -1
+
+
+def test_delayed_descriptor_validation(pz):
+    """model.delayed = 1 (delay=True): one GPU only (every particle is the same marginal), and the posterior
+    read-out refuses null pointers; both are argument errors, reported before any device work."""
+    d = pz.stt(delay=True)
+    assert d.delayed == 1 and pz.stt().delayed == 0
+    h = C.c_void_p()
+    ident = (C.c_char * 128)()
+    rc = pz.lib().pz_filter_create_sharded(C.byref(d), 2 * 256 * 4, 0, 0, 0, 2, ident, C.byref(h))
+    assert rc == -1 and b"delayed" in pz.lib().pz_last_error()
+    assert pz.lib().pz_filter_read_posterior(None, None, None) == -1
