@@ -1497,10 +1497,12 @@ static void launch_tile(const TileArgs& ta, cudaStream_t s) {
   auto kern = pf_step_tile<NX, NY, TO, MODE, KRON, NT>;
   // staged parents [NX][TO] + inverse-CDF table
   size_t smem = (size_t)NX * TO * sizeof(float) + PZ_ICDF_ROWS * sizeof(float4);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;  // per device (function attributes are per context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
 }

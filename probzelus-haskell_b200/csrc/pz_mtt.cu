@@ -406,10 +406,12 @@ int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, con
   a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.n = n; a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
   const size_t smem = (size_t)kMttDerived * kMttFast * kMttThreads * sizeof(float);  // 28 KB
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;  // per device (function attributes are per context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     cudaFuncSetAttribute(mtt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   mtt_step<<<(unsigned)((n + kMttThreads - 1) / kMttThreads), kMttThreads, smem, s>>>(a);
   return 1;
