@@ -270,6 +270,21 @@ def test_delayed_sampling_is_the_exact_kalman_recursion(pz, model):
     zs.close()
 
 
+def test_filters_on_two_devices_of_one_process(pz):
+    """One process, filters on device 0 and device 1 (a C host may do this): same seed, same bits."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    obs, _ = H.gen_obs(H.model_mtt_track(), 5)
+    a = pz.zparticles(30000, pz.mtt_track(), seed=5, device=0)
+    b = pz.zparticles(30000, pz.mtt_track(), seed=5, device=1)
+    for y in obs:
+        pa, pb = a.step(y), b.step(y)
+        assert pa.total_weight == pb.total_weight
+    assert np.array_equal(a.read_state().view(np.uint32), b.read_state().view(np.uint32))
+    a.close(); b.close()
+
+
 def test_multinomial_reference_mode(pz):
     """resampler = MULTINOMIAL_REF (resample2, Inference.hs:57-61): bit-exact vs the oracle and
     statistically equal to the systematic filter."""
