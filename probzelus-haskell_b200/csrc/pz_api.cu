@@ -306,6 +306,7 @@ struct pz_filter {
   float* mtt_obs = nullptr;                  // device [m_max][2]
   float* h_mtt_obs = nullptr;                // pinned
   unsigned long long* mtt_overflow = nullptr;
+  double* mtt_part = nullptr;                // per-CTA summary partials of mtt_step
   std::vector<char> mtt_params;
   int32_t mtt_mmax = 0;
 };
@@ -372,7 +373,7 @@ void free_filter(pz_filter* f) {
   cudaFree(f->warm);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(f->mbox); cudaFree(f->d_p2p);
-  cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow);
+  cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow); cudaFree(f->mtt_part);
   if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
   f->g.release();
   if (f->h_obs) cudaFreeHost(f->h_obs);
@@ -545,7 +546,7 @@ int mtt_plan(pz_filter* f, int delta, double ll_const) {
   int n = launch_stats_from_lw(g, f->stream);
   n += launch_scan_only(a, delta, f->stream);
   if (delta)
-    n += launch_mtt_summary(f->g.lw, f->mtt_s[(f->t + 1) & 1], a.n_local, a.plan, a.ctl, a.summ, ll_const, f->mtt_overflow, f->stream);
+    n += launch_mtt_summary(f->mtt_part, a.n_local, a.plan, a.ctl, a.summ, ll_const, f->mtt_overflow, f->stream);
   n += launch_partition_ext(a, kGenericTileOut, delta, f->stream);
   return n;
 }
@@ -600,6 +601,7 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   PZ_TRY(cudaMallocHost(&f->h_mtt_obs, 64 * sizeof(float)));
   PZ_TRY(cudaMalloc(&f->mtt_overflow, sizeof(unsigned long long)));
   PZ_TRY(cudaMemset(f->mtt_overflow, 0, sizeof(unsigned long long)));
+  PZ_TRY(cudaMalloc(&f->mtt_part, (size_t)mtt_step_ctas(a.n_local) * 5 * sizeof(double)));
   {
     int rc = generic_alloc(&f->g, a.n_local, false);  // stored log-weights (all 0: equal weights) + ancestors
     if (rc) { free_filter(f); return rc; }
@@ -623,7 +625,7 @@ int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summar
   GenericArgs g = mtt_generic(f);
   int n = launch_generic_ancestors(g, f->stream);
   n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
-                       f->mtt_overflow, a.n_local, n_obs, a.seed, f->stream);
+                       f->mtt_overflow, f->mtt_part, a.n_local, n_obs, a.seed, f->stream);
   // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
   const double ll_const = -(f->desc.mtt.clutter_lambda + f->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
   n += mtt_plan(f, 1, ll_const);

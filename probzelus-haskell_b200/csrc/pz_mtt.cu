@@ -118,6 +118,7 @@ struct MttArgs {
   const float* obs;      // [m_max][2]
   const CtlDev* ctl;
   unsigned long long* overflow;  // counter of dropped births
+  double* part;          // [gridDim.x][5]: per-CTA (max lw, sum w, sum w^2, sum w c, sum w c^2), w = exp(lw - max)
   int64_t n;
   int32_t n_obs;
   uint64_t seed;
@@ -213,7 +214,9 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   }
   __syncthreads();
   const int64_t j = (int64_t)blockIdx.x * kMttThreads + tid;
-  if (j >= a.n) return;
+  float out_lw = -INFINITY, out_cnt = 0.f;  // this particle's log-weight and track count (summary below)
+  do {
+  if (j >= a.n) break;
   float loc[kMttDerived * (16 - kMttFast)];
   const DerShared ds{s_der, tid};
   const DerLocal dl{loc};
@@ -308,22 +311,26 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)(n_surv + n_born), (uint32_t)(next_id + n_new), n_new > room ? 1u : 0u, 0u);
   a.lw[j] = lw;
   if (n_new > room) atomicAdd(a.overflow, (unsigned long long)(n_new - room));
-}
+  out_lw = sanitize_lw(lw);
+  out_cnt = (float)(n_surv + n_born);
+  } while (0);
 
-// weighted track-count moments: sum w, sum w^2, sum w c, sum w c^2 at scale 2^emax
-__global__ void __launch_bounds__(kThreads) mtt_summary_reduce(const float* __restrict__ lw, const uint32_t* __restrict__ s,
-                                                               int64_t n, PlanDev* plan) {
-  __shared__ double s_red[kWarps][4];
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- per-CTA partial of the weighted track-count moments (no separate pass over the particles)
+  __shared__ float s_mx[kMttThreads / 32];
+  __shared__ double s_sum[kMttThreads / 32][4];
+  const int lane = tid & 31, warp = tid >> 5;
+  float mx = out_lw;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if (lane == 0) s_mx[warp] = mx;
+  __syncthreads();
+  mx = s_mx[0];
+#pragma unroll
+  for (int w = 1; w < kMttThreads / 32; ++w) mx = fmaxf(mx, s_mx[w]);
   double v[4] = {0, 0, 0, 0};
-  if (i < n) {
-    const float l = sanitize_lw(lw[i]);
-    if (l > -INFINITY) {
-      const double w = exp2((double)l * 1.4426950408889634 - (double)plan->emax);  // scale 2^emax
-      const double c = (double)s[(size_t)i * kMttWords];
-      v[0] = w; v[1] = w * w; v[2] = w * c; v[3] = w * c * c;
-    }
+  if (out_lw > -INFINITY) {
+    const double w = exp((double)out_lw - (double)mx), c = (double)out_cnt;
+    v[0] = w; v[1] = w * w; v[2] = w * c; v[3] = w * c * c;
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -334,32 +341,70 @@ __global__ void __launch_bounds__(kThreads) mtt_summary_reduce(const float* __re
       const int lo = __shfl_xor_sync(0xffffffffu, (int)y, d), hi = __shfl_xor_sync(0xffffffffu, (int)(y >> 32), d);
       x += __longlong_as_double(((long long)hi << 32) | (unsigned int)lo);
     }
-    if (lane == 0) s_red[warp][r] = x;
+    if (lane == 0) s_sum[warp][r] = x;
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
-    double x = 0;
-    for (int w = 0; w < kWarps; ++w) x += s_red[w][threadIdx.x];
-    double* dstp = threadIdx.x == 0 ? &plan->sw : (threadIdx.x == 1 ? &plan->sw2 : (threadIdx.x == 2 ? &plan->sx[0] : &plan->sxx[0]));
-    atomicAdd(dstp, x);
+  if (tid < 5) {
+    double x = (double)mx;
+    if (tid > 0) { x = 0; for (int w = 0; w < kMttThreads / 32; ++w) x += s_sum[w][tid - 1]; }
+    a.part[(size_t)blockIdx.x * 5 + tid] = x;
   }
 }
 
-__global__ void mtt_summary_final(PlanDev* pl, const CtlDev* ctl, pz_step_summary* summ, int64_t n, double ll_const,
-                                  const unsigned long long* overflow) {
+// combine the per-CTA partials (log-sum-exp over their maxima) into the step summary
+constexpr int kFinalThreads = 1024, kFinalWarps = kFinalThreads / 32;
+__global__ void __launch_bounds__(kFinalThreads) mtt_summary_final(PlanDev* pl, const CtlDev* ctl, pz_step_summary* summ, int64_t n,
+                                                              double ll_const, const unsigned long long* overflow,
+                                                              const double* __restrict__ part, int32_t ncta) {
+  __shared__ double s_m[kFinalWarps], s_v[kFinalWarps][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto shfl_d = [](double x, int d) {
+    const long long y = __double_as_longlong(x);
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)y, d), hi = __shfl_xor_sync(0xffffffffu, (int)(y >> 32), d);
+    return __longlong_as_double(((long long)hi << 32) | (unsigned int)lo);
+  };
+  double M = -INFINITY;
+  for (int c = tid; c < ncta; c += kFinalThreads) M = fmax(M, part[(size_t)c * 5]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) M = fmax(M, shfl_d(M, d));
+  if (lane == 0) s_m[warp] = M;
+  __syncthreads();
+  M = s_m[0];
+  for (int w = 1; w < kFinalWarps; ++w) M = fmax(M, s_m[w]);
+  double v[4] = {0, 0, 0, 0};
+  for (int c = tid; c < ncta; c += kFinalThreads) {
+    const double m = part[(size_t)c * 5];
+    if (m > -INFINITY) {
+      const double f = exp(m - M);
+      v[0] += f * part[(size_t)c * 5 + 1];
+      v[1] += f * f * part[(size_t)c * 5 + 2];
+      v[2] += f * part[(size_t)c * 5 + 3];
+      v[3] += f * part[(size_t)c * 5 + 4];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double x = v[r];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += shfl_d(x, d);
+    if (lane == 0) s_v[warp][r] = x;
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  double sw = 0, sw2 = 0, sc = 0, scc = 0;
+  for (int w = 0; w < kFinalWarps; ++w) { sw += s_v[w][0]; sw2 += s_v[w][1]; sc += s_v[w][2]; scc += s_v[w][3]; }
   pz_step_summary* o = summ + (ctl->t % kObsRing);
-  const double sw = pl->sw, m = pl->sx[0] / sw;
+  const double m = sc / sw;
   for (int d = 0; d < PZ_MAX_NX; ++d) { o->mean[d] = 0; o->var[d] = 0; }
   o->mean[0] = m;
-  o->var[0] = pl->sxx[0] / sw - m * m;
+  o->var[0] = scc / sw - m * m;
   o->step = ctl->t;
-  o->log_evidence_inc = log(sw) + (double)pl->emax * 0.6931471805599453 - log((double)n) + ll_const;
-  o->ess = sw * sw / pl->sw2;
+  o->log_evidence_inc = M + log(sw) - log((double)n) + ll_const;
+  o->ess = sw * sw / sw2;
   o->n_migrated = 0;
   o->e_max = pl->emax;
   o->reserved = (int32_t)(*overflow > 0x7fffffffull ? 0x7fffffff : *overflow);
   o->total_weight = pl->total;
-  pl->sw = 0; pl->sw2 = 0; pl->sx[0] = 0; pl->sxx[0] = 0;
 }
 
 // thinned read of the resampled population: every stride-th output slot's parent record
@@ -400,10 +445,14 @@ void mtt_fill_params(const pz_model_desc* d, void* out_mttdev) {
 
 size_t mtt_params_size() { return sizeof(MttDev); }
 
+int mtt_step_ctas(int64_t n) { return (int)((n + kMttThreads - 1) / kMttThreads); }
+
 int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
-                    const CtlDev* ctl, unsigned long long* overflow, int64_t n, int32_t n_obs, uint64_t seed, cudaStream_t s) {
+                    const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
+                    cudaStream_t s) {
   MttArgs a;
-  a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.n = n; a.n_obs = n_obs;
+  a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
+  a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
   const size_t smem = (size_t)kMttDerived * kMttFast * kMttThreads * sizeof(float);  // 28 KB
   static unsigned long long attr_done = 0;  // per device (function attributes are per context)
@@ -417,11 +466,10 @@ int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, con
   return 1;
 }
 
-int launch_mtt_summary(const float* lw, const uint32_t* sdata, int64_t n, PlanDev* plan, const CtlDev* ctl, pz_step_summary* summ,
-                       double ll_const, const unsigned long long* overflow, cudaStream_t s) {
-  mtt_summary_reduce<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(lw, sdata, n, plan);
-  mtt_summary_final<<<1, 1, 0, s>>>(plan, ctl, summ, n, ll_const, overflow);
-  return 2;
+int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDev* ctl, pz_step_summary* summ, double ll_const,
+                       const unsigned long long* overflow, cudaStream_t s) {
+  mtt_summary_final<<<1, kFinalThreads, 0, s>>>(plan, ctl, summ, n, ll_const, overflow, part, mtt_step_ctas(n));
+  return 1;
 }
 
 int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
