@@ -275,8 +275,16 @@ struct pz_filter {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t push_stream = nullptr;                 // sharded, peer memory: pf_halo_push runs beside the scan
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaGraphExec_t sgraph[2] = {nullptr, nullptr};  // sharded: one captured step (kernels + NCCL) per buffer parity
+  // PZ_SHARD_TIMING=1 (implies no graph): events between the kernels of a sharded step, averages printed at destroy
+  bool shard_timing = false;
+  cudaEvent_t tev[5] = {};
+  double tacc[4] = {0, 0, 0, 0};
+  int64_t tcount = 0;
+  bool tpending = false;
   float* h_obs = nullptr;            // pinned [kObsRing][PZ_MAX_NY]
   pz_step_summary* h_summ = nullptr; // pinned [kObsRing]
   float* d_obs = nullptr;
@@ -358,12 +366,41 @@ int load_nccl() {
     if (r_ != ncclSuccess) return fail(PZ_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
   } while (0)
 
+void shard_timing_collect(pz_filter* f) {
+  if (!f->tpending) return;
+  f->tpending = false;
+  if (cudaEventSynchronize(f->tev[4]) != cudaSuccess) { cudaGetLastError(); return; }
+  for (int i = 0; i < 4; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, f->tev[i], f->tev[i + 1]) == cudaSuccess) f->tacc[i] += ms;
+  }
+  f->tcount += 1;
+}
+
 void free_filter(pz_filter* f) {
   if (!f) return;
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   if (f->graph) cudaGraphExecDestroy(f->graph);
   for (int i = 0; i < 2; ++i) if (f->sgraph[i]) cudaGraphExecDestroy(f->sgraph[i]);
+#ifdef PZ_DBG_STAMPS
+  if (f->a.world > 1) {
+    unsigned long long st[16] = {};
+    cudaStreamSynchronize(f->stream);
+    dbg_read_stamps(st);
+    fprintf(stderr, "[pz stamps] rank %d (ns after scan start):", f->a.rank);
+    for (int i = 0; i < 11; ++i) fprintf(stderr, " [%d]=%lld", i, (long long)(st[i] - st[0]));
+    fprintf(stderr, "  abs0=%llu\n", st[0]);
+  }
+#endif
+  if (f->shard_timing) {
+    shard_timing_collect(f);
+    if (f->tcount)
+      fprintf(stderr, "[pz shard timing] rank %d of %d, %lld steps: step kernel %.1f us, scan %.1f us, plan+halo push %.1f us, partition %.1f us\n",
+              f->a.rank, f->a.world, (long long)f->tcount, 1e3 * f->tacc[0] / f->tcount, 1e3 * f->tacc[1] / f->tcount,
+              1e3 * f->tacc[2] / f->tcount, 1e3 * f->tacc[3] / f->tcount);
+    for (auto& e : f->tev) if (e) cudaEventDestroy(e);
+  }
   if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(f->comm);
   StepArgs& a = f->a;
   cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->qbuf[0]); cudaFree(f->qbuf[1]); cudaFree(f->xbbuf); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
@@ -380,6 +417,9 @@ void free_filter(pz_filter* f) {
   if (f->h_summ) cudaFreeHost(f->h_summ);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->push_stream) cudaStreamDestroy(f->push_stream);
+  if (f->ev_fork) cudaEventDestroy(f->ev_fork);
+  if (f->ev_join) cudaEventDestroy(f->ev_join);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
 }
@@ -453,9 +493,19 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
   cudaStream_t s = f->stream;
   const int which = (int)((f->t + (uint32_t)delta) & 1u);  // buffer of the population just produced
   if (a.p2p) {  // peer-memory exchange inside the kernels: no collective call at all
+    const bool tm = f->shard_timing && delta;
+    // fork: the X / Q / eb margins travel to the neighbours while this rank scans
+    PZ_CUDA(cudaEventRecord(f->ev_fork, s));
+    PZ_CUDA(cudaStreamWaitEvent(f->push_stream, f->ev_fork, 0));
+    *launches += launch_halo_push(a, delta, f->push_stream);
+    PZ_CUDA(cudaEventRecord(f->ev_join, f->push_stream));
     *launches += launch_scan_only(a, delta, s);
+    if (tm) cudaEventRecord(f->tev[2], s);
     *launches += launch_plan_sharded(a, delta, s);
+    if (tm) cudaEventRecord(f->tev[3], s);
+    PZ_CUDA(cudaStreamWaitEvent(s, f->ev_join, 0));  // join (pf_partition advances ctl->t, which pf_halo_push reads)
     *launches += launch_partition_ext(a, fused_tile_out(a.model.nx), delta, s);
+    if (tm) { cudaEventRecord(f->tev[4], s); f->tpending = true; }
     PZ_CUDA(cudaGetLastError());
     return PZ_OK;
   }
@@ -505,7 +555,9 @@ int enqueue_step(pz_filter* f) {
       PZ_CUDA(cudaGraphLaunch(f->sgraph[f->t & 1u], f->stream));
       f->last_launches += f->launches_per_step;
     } else {
+      if (f->shard_timing) { shard_timing_collect(f); cudaEventRecord(f->tev[0], f->stream); }
       int n = launch_tile_only(a, f->stream);
+      if (f->shard_timing) cudaEventRecord(f->tev[1], f->stream);
       int rc = sharded_advance(f, 1, &n);
       f->last_launches += n;
       if (rc) return rc;
@@ -693,6 +745,9 @@ int setup_p2p(pz_filter* f) {
   }
   if (ok) ok = cudaMalloc(&f->d_p2p, sizeof(ShardP2P)) == cudaSuccess &&
                cudaMemcpy(f->d_p2p, &h, sizeof(ShardP2P), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) ok = cudaStreamCreateWithFlags(&f->push_stream, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming) == cudaSuccess;
   // agreement: min over ranks of the local verdict
   const int32_t verdict = ok ? 1 : 0;
   PZ_CUDA(cudaMemcpy(f->warm, &verdict, sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -888,7 +943,11 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   }
   PZ_TRY(cudaGetLastError());
   PZ_TRY(cudaStreamSynchronize(f->stream));
-  if (world > 1 && !getenv("PZ_NO_SHARD_GRAPH")) {
+  if (world > 1 && a.p2p && getenv("PZ_SHARD_TIMING")) {
+    f->shard_timing = true;
+    for (auto& e : f->tev) PZ_TRY(cudaEventCreate(&e));
+  }
+  if (world > 1 && !f->shard_timing && !getenv("PZ_NO_SHARD_GRAPH")) {
     // one captured graph per buffer parity: step kernel, collectives, halo exchange (NCCL calls are capturable);
     // a failed capture leaves the eager stream-ordered path in place
     const uint32_t t_save = f->t;

@@ -83,8 +83,21 @@ __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+#ifdef PZ_DBG_STAMPS
+// debug build only: %globaltimer stamps of the sharded step's exchange phases (last step wins), printed at destroy
+__device__ unsigned long long g_stamp[16];
+__device__ __forceinline__ void stamp(int i) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_stamp[i] = t;
+}
+#define PZ_STAMP(cond, i) do { if (cond) stamp(i); } while (0)
+#else
+#define PZ_STAMP(cond, i) do { } while (0)
+#endif
 // poll *p until pred(value); gives up after ~2 s (a dead peer must not hang the device)
-template <class Pred>
+// ACQUIRE = false for self-validating words (the payload is in the polled word: nothing to order)
+template <bool ACQUIRE = true, class Pred>
 __device__ __forceinline__ unsigned long long wait_sys(const unsigned long long* p, Pred pred, uint32_t* err) {
   const long long t0 = clock64();
   unsigned long long v = ld_sys(p);
@@ -93,7 +106,7 @@ __device__ __forceinline__ unsigned long long wait_sys(const unsigned long long*
     __nanosleep(64);
     v = ld_sys(p);
   }
-  __threadfence_system();
+  if (ACQUIRE) __threadfence_system();
   return v;
 }
 // 2^k as a float for k <= 0 (0 when it would underflow)
@@ -382,6 +395,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   const uint32_t t_pop = s.ctl->t + (uint32_t)s.delta;
   __syncthreads();
   const uint32_t tile = s_tile;
+  PZ_STAMP(tile == 0 && tid == 0, 0);
   if (s.p2p) {
     // all-reduce(max) of the block exponent over peer memory: the first CTA stores this rank's value
     // into every mailbox, every CTA polls its own mailbox for all ranks' values of this epoch
@@ -391,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       if (tile == 0 && lane < s.world) st_sys(&s.p2p->mbox[lane]->emax[s.rank], (epoch << 32) | (uint32_t)emax);
       int32_t v = kNZero;
       if (lane < s.world) {
-        const unsigned long long w = wait_sys(&s.p2p->mbox[s.rank]->emax[lane],
+        const unsigned long long w = wait_sys<false>(&s.p2p->mbox[s.rank]->emax[lane],
                                               [epoch](unsigned long long x) { return (x >> 32) == epoch; }, &s.ctl->comm_error);
         v = (int32_t)(uint32_t)w;
       }
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
     }
     __syncthreads();
     emax = s_emax;
+    PZ_STAMP(tile == 0 && tid == 0, 1);
   }
   const int32_t* __restrict__ ebp = (t_pop & 1u) ? s.eb1 : s.eb0;
 
@@ -532,6 +547,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   if (tid == 0) s_last = (atomicAdd(&s.ctl->scan_done, 1u) == (uint32_t)(s.nscan - 1));
   __syncthreads();
   if (!s_last) return;
+  PZ_STAMP(tid == 0, 2);
   __threadfence();
   if (have_rec) {  // per-CTA partials -> totals: 16 groups of 16 threads, fixed order (deterministic)
     const int r = tid & 15, grp = tid >> 4;
@@ -618,14 +634,19 @@ struct PartArgs {
 __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
   const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const PlanDev* pl = p.plan;
+  PZ_STAMP(J == 0, 9);
   if (p.p2p) {
-    if (threadIdx.x < 2) {
-      const int side = threadIdx.x;
+    if (threadIdx.x < 4) {  // both neighbours' margins: X / Q / eb (pf_halo_push) and prefixes (pf_plan_sharded)
+      const int side = threadIdx.x & 1;
       const bool have = side == 0 ? p.rank > 0 : p.rank + 1 < p.world;
       const unsigned long long epoch = pl->shard_epoch;
-      if (have) wait_sys(&p.p2p->mbox[p.rank]->halo_flag[side], [epoch](unsigned long long x) { return x == epoch; }, &p.ctl->comm_error);
+      Mailbox* mine = p.p2p->mbox[p.rank];
+      if (have)
+        wait_sys(threadIdx.x < 2 ? &mine->halo_flag[side] : &mine->pbx_flag[side], [epoch](unsigned long long x) { return x == epoch; },
+                 &p.ctl->comm_error);
     }
     __syncthreads();
+    PZ_STAMP(J == 0, 10);
   }
   SlotMap sm(pl, p.n_out_global);
   // one warp per output tile: 32-ary search for min b in [b_lo, b_hi) with slot_end(pb[b+1]) > j0
@@ -1292,6 +1313,49 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, 
   for (int64_t i = gid; i < n16; i += gsz) d[i] = s[i];
 }
 
+// Peer-memory exchange: the X / Q / eb margins of the population just produced go straight into the
+// neighbours' halo regions (their arrays have our layout).  Independent of the scan, so the host forks
+// this kernel beside pf_scan_blocks / pf_plan_sharded; the last CTA to finish raises the neighbours' flags.
+struct HaloPushArgs {
+  const CtlDev* ctl;
+  const ShardP2P* p2p;
+  const float* X[2];
+  const uint16_t* Q[2];
+  const int32_t* eb[2];
+  int64_t nblk, ld, margin;
+  int32_t rank, world, nx, delta;
+};
+__global__ void __launch_bounds__(kThreads) pf_halo_push(const HaloPushArgs p) {
+  const int tid = threadIdx.x;
+  const uint32_t epoch = p.ctl->t + (uint32_t)p.delta + 1u;
+  const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
+  const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
+  const int64_t m = p.margin, nb = p.nblk;
+  if (p.rank > 0) {  // my first m blocks: the RIGHT halo of rank-1
+    for (int d = 0; d < p.nx; ++d)
+      copy16(p.p2p->Xn[0][which] + (size_t)d * p.ld + nb * kBlk, p.X[which] + (size_t)d * p.ld, m * kBlk / 4, gid, gsz);
+    copy16(p.p2p->Qn[0][which] + nb * kBlk, p.Q[which], m * kBlk / 8, gid, gsz);
+    for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[0][which][nb + i] = p.eb[which][i];
+  }
+  if (p.rank + 1 < p.world) {  // my last m blocks: the LEFT halo of rank+1
+    for (int d = 0; d < p.nx; ++d)
+      copy16(p.p2p->Xn[1][which] + (size_t)d * p.ld - m * kBlk, p.X[which] + (size_t)d * p.ld + (nb - m) * kBlk, m * kBlk / 4, gid, gsz);
+    copy16(p.p2p->Qn[1][which] - m * kBlk, p.Q[which] + (nb - m) * kBlk, m * kBlk / 8, gid, gsz);
+    for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[1][which][i - m] = p.eb[which][nb - m + i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    Mailbox* mine = p.p2p->mbox[p.rank];
+    if (atomicAdd(&mine->push_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      __threadfence_system();
+      mine->push_done = 0ull;
+      if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->halo_flag[1], (unsigned long long)epoch);
+      if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->halo_flag[0], (unsigned long long)epoch);
+    }
+  }
+}
+
 // Every rank evaluates, for EVERY rank q, whether the fixed halo margins (the last `margin` blocks of
 // rank q-1 and the first `margin` blocks of rank q+1) cover the ancestors of q's slots -- from the
 // gathered records alone, so that all ranks reach the same verdict without another collective.
@@ -1299,24 +1363,32 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, 
 // into every mailbox, every CTA polls its own mailbox) and the halo exchange (all CTAs store the two
 // margins straight into the neighbours' halo regions; the last CTA to finish raises their flags).
 __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs p) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const uint32_t epoch = p.ctl->t + (uint32_t)p.delta + 1u;
   const u64* rec = p.rec;
+  __shared__ u64 s_rec[kMaxRanks * kShardRec];
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 3);
   if (p.p2p) {
+    // all-gather of the records over peer memory: CTA 0 stores this rank's record into every mailbox as
+    // self-validating half-words, every CTA polls its own mailbox until all of this epoch are there
     Mailbox* mine = p.p2p->mbox[p.rank];
+    const int nw = p.world * 2 * kShardRec;
     if (blockIdx.x == 0) {
-      for (int q = warp; q < p.world; q += kWarps) {
-        if (lane < kShardRec) st_sys(&p.p2p->mbox[q]->rec[p.rank][lane], p.rec[(size_t)p.rank * kShardRec + lane]);
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) st_sys(&p.p2p->mbox[q]->rec_flag[p.rank], (unsigned long long)epoch);
+      for (int i = tid; i < nw; i += kThreads) {
+        const int q = i / (2 * kShardRec), w = i % (2 * kShardRec);
+        const u64 v = p.rec[(size_t)p.rank * kShardRec + (w >> 1)];
+        st_sys(&p.p2p->mbox[q]->rec2[p.rank][w], ((u64)epoch << 32) | (uint32_t)((w & 1) ? (v >> 32) : v));
       }
     }
-    if (warp == 0)
-      for (int q = lane; q < p.world; q += 32)
-        wait_sys(&mine->rec_flag[q], [epoch](unsigned long long x) { return x == (unsigned long long)epoch; }, &p.ctl->comm_error);
+    uint32_t* s_half = reinterpret_cast<uint32_t*>(s_rec);  // little endian: half w of word k of rank q = s_half[(q * kShardRec + k) * 2 + (w & 1)]
+    for (int i = tid; i < nw; i += kThreads) {
+      const u64 x = wait_sys<false>(&mine->rec2[i / (2 * kShardRec)][i % (2 * kShardRec)],
+                                    [epoch](unsigned long long x) { return (uint32_t)(x >> 32) == epoch; }, &p.ctl->comm_error);
+      s_half[i] = (uint32_t)x;
+    }
     __syncthreads();
-    rec = reinterpret_cast<const u64*>(&mine->rec[0][0]);
+    rec = s_rec;
+    PZ_STAMP(blockIdx.x == 0 && tid == 0, 4);
   }
   u64 base = 0, total = 0;
   for (int q = 0; q < p.world; ++q) {
@@ -1326,38 +1398,30 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
   }
   const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
   for (int64_t b = gid; b <= p.nblk; b += gsz) p.pbx[b] = base + p.pb[b];
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 5);
   if (p.p2p) {
-    // halo margins -> the neighbours' halo regions (their arrays have our layout): my first m blocks are the
-    // RIGHT halo of rank-1, my last m blocks the LEFT halo of rank+1
-    const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
+    // prefix margins -> the neighbours' halo regions (my first m blocks are the RIGHT halo of rank-1, my last
+    // m blocks the LEFT halo of rank+1); the X / Q / eb margins went out in pf_halo_push, beside the scan
     const int64_t m = p.margin, nb = p.nblk;
-    if (p.rank > 0) {
-      for (int d = 0; d < p.nx; ++d)
-        copy16(p.p2p->Xn[0][which] + (size_t)d * p.ld + nb * kBlk, p.X[which] + (size_t)d * p.ld, m * kBlk / 4, gid, gsz);
-      copy16(p.p2p->Qn[0][which] + nb * kBlk, p.Q[which], m * kBlk / 8, gid, gsz);
+    const int npush = (int)((m + kThreads - 1) / kThreads);  // CTAs that have prefix entries to store
+    if ((int)blockIdx.x < npush) {
       for (int64_t i = gid; i < m; i += gsz) {
-        p.p2p->ebn[0][which][nb + i] = p.eb[which][i];
-        p.p2p->pbxn[0][nb + 1 + i] = base + p.pb[1 + i];
+        if (p.rank > 0) p.p2p->pbxn[0][nb + 1 + i] = base + p.pb[1 + i];
+        if (p.rank + 1 < p.world) p.p2p->pbxn[1][i - m] = base + p.pb[nb - m + i];
       }
-    }
-    if (p.rank + 1 < p.world) {
-      for (int d = 0; d < p.nx; ++d)
-        copy16(p.p2p->Xn[1][which] + (size_t)d * p.ld - m * kBlk, p.X[which] + (size_t)d * p.ld + (nb - m) * kBlk, m * kBlk / 4, gid, gsz);
-      copy16(p.p2p->Qn[1][which] - m * kBlk, p.Q[which] + (nb - m) * kBlk, m * kBlk / 8, gid, gsz);
-      for (int64_t i = gid; i < m; i += gsz) {
-        p.p2p->ebn[1][which][i - m] = p.eb[which][nb - m + i];
-        p.p2p->pbxn[1][i - m] = base + p.pb[nb - m + i];
-      }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      Mailbox* mine = p.p2p->mbox[p.rank];
-      if (atomicAdd(&mine->push_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
-        __threadfence_system();
-        mine->push_done = 0ull;
-        if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->halo_flag[1], (unsigned long long)epoch);
-        if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->halo_flag[0], (unsigned long long)epoch);
+      PZ_STAMP(blockIdx.x == 0 && tid == 0, 6);
+      __threadfence_system();
+      __syncthreads();
+      PZ_STAMP(blockIdx.x == 0 && tid == 0, 7);
+      if (tid == 0) {
+        Mailbox* mine = p.p2p->mbox[p.rank];
+        if (atomicAdd(&mine->pbx_done, 1ull) == (unsigned long long)npush - 1ull) {
+          PZ_STAMP(true, 8);
+          __threadfence_system();
+          mine->pbx_done = 0ull;
+          if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->pbx_flag[1], (unsigned long long)epoch);
+          if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->pbx_flag[0], (unsigned long long)epoch);
+        }
       }
     }
   }
@@ -1565,6 +1629,20 @@ int launch_tile_only(const StepArgs& a, cudaStream_t s) {
 int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s) {
   ScanArgs sc = make_scan(a, delta, delta == 1);
   pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  return 1;
+}
+
+#ifdef PZ_DBG_STAMPS
+void dbg_read_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_stamp, sizeof(g_stamp)); }
+#endif
+
+int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s) {
+  HaloPushArgs p{a.ctl, a.p2p, {a.X[0], a.X[1]}, {a.Q[0], a.Q[1]}, {a.eb[0], a.eb[1]}, a.nblk, a.ld, a.margin,
+                 a.rank, a.world, a.model.nx, delta};
+  // 16-byte stores per margin and side: nx * m * 64 (X) + m * 32 (Q); two per thread, at most two CTAs per SM beside the scan
+  int grid = cdiv((int64_t)(a.model.nx * 64 + 32) * a.margin, 2 * kThreads);
+  grid = grid < 1 ? 1 : (grid > 296 ? 296 : grid);
+  pf_halo_push<<<grid, kThreads, 0, s>>>(p);
   return 1;
 }
 

@@ -119,14 +119,17 @@ constexpr int kMaxRanks = 32;
 
 // Peer-memory exchange of a sharded filter (one process per GPU, buffers mapped with CUDA IPC over
 // NVLink): every rank owns a mailbox its peers store into, and maps the halo regions of its two
-// neighbours.  The kernels of the step push with plain 64/128-bit peer stores + a system-scope
-// fence + an epoch flag, and poll their OWN memory; no collective library call is on the path.
+// neighbours.  Small messages (block exponent, records) travel as self-validating 64-bit words,
+// (epoch << 32) | 32 payload bits, so neither side needs a fence or a flag; the halo margins are
+// plain 128-bit peer stores + a system-scope fence + an epoch flag.  Every rank polls its OWN
+// memory; no collective library call is on the path.
 struct Mailbox {
-  unsigned long long emax[kMaxRanks];            // (epoch << 32) | block exponent of rank q
-  unsigned long long rec[kMaxRanks][kShardRec];  // rank q's record (pf_scan_blocks' last CTA)
-  unsigned long long rec_flag[kMaxRanks];        // epoch of rec[q]
-  unsigned long long halo_flag[2];               // epoch of my left / right halo (written by that neighbour)
-  unsigned long long push_done;                  // CTAs of pf_plan_sharded that finished their halo stores
+  unsigned long long emax[kMaxRanks];                // (epoch << 32) | block exponent of rank q
+  unsigned long long rec2[kMaxRanks][2 * kShardRec]; // rank q's record (pf_scan_blocks' last CTA): (epoch << 32) | low / high half of each word
+  unsigned long long halo_flag[2];                   // epoch of the X / Q / eb margins in my left / right halo (written by that neighbour's pf_halo_push)
+  unsigned long long pbx_flag[2];                    // epoch of the prefix margins in my left / right halo (that neighbour's pf_plan_sharded)
+  unsigned long long push_done;                      // CTAs of pf_halo_push that finished their stores
+  unsigned long long pbx_done;                       // CTAs of pf_plan_sharded that finished their prefix stores
 };
 struct ShardP2P {
   Mailbox* mbox[kMaxRanks];   // mbox[q]: rank q's mailbox (mbox[rank] is local memory)
@@ -148,6 +151,7 @@ int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]);
 int launch_tile_only(const StepArgs& a, cudaStream_t s);                 // fused step kernel
 int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s);      // after the emax all-reduce
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s);   // after the all-gather: plan, absolute prefix, summary, margin check
+int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s);      // peer memory: X / Q / eb margins -> the neighbours (independent of the scan)
 int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s);  // after the halo exchange
 
 // Generic (stored log-weight) path: standalone resampler, ancestor taps, visualiser read.
@@ -189,6 +193,9 @@ int launch_stats_from_lw(const GenericArgs& g, cudaStream_t s);
 int mtt_words_per_particle();
 size_t mtt_params_size();
 void mtt_fill_params(const pz_model_desc* d, void* out_mttdev);
+#ifdef PZ_DBG_STAMPS
+void dbg_read_stamps(unsigned long long* out);  // debug build: %globaltimer stamps of the sharded exchange phases
+#endif
 int mtt_step_ctas(int64_t n);  // CTAs of mtt_step = rows of its per-CTA summary partials (5 doubles each)
 int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
