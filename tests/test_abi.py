@@ -68,3 +68,52 @@ def test_delayed_descriptor_validation(pz):
     rc = pz.lib().pz_filter_create_sharded(C.byref(d), 2 * 256 * 4, 0, 0, 0, 2, ident, C.byref(h))
     assert rc == -1 and b"delayed" in pz.lib().pz_last_error()
     assert pz.lib().pz_filter_read_posterior(None, None, None) == -1
+
+
+def _header_layout(tmp_path):
+    """sizeof / offsetof as a C compiler sees include/pzgpu.h (also proves the header is plain C99)."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "pzgpu.h"\n'
+        "#define O(s, f) printf(#s \".\" #f \" %zu\\n\", offsetof(s, f))\n"
+        "int main(void) {\n"
+        '  printf("pz_model_desc %zu\\n", sizeof(pz_model_desc));\n'
+        '  printf("pz_step_summary %zu\\n", sizeof(pz_step_summary));\n'
+        '  printf("pz_mtt_params %zu\\n", sizeof(pz_mtt_params));\n'
+        "  O(pz_model_desc, kind); O(pz_model_desc, nx); O(pz_model_desc, ny); O(pz_model_desc, scalar_ll_2x);\n"
+        "  O(pz_model_desc, resampler); O(pz_model_desc, delayed); O(pz_model_desc, F); O(pz_model_desc, Q);\n"
+        "  O(pz_model_desc, H); O(pz_model_desc, R); O(pz_model_desc, x0); O(pz_model_desc, mtt);\n"
+        "  O(pz_step_summary, step); O(pz_step_summary, log_evidence_inc); O(pz_step_summary, ess);\n"
+        "  O(pz_step_summary, mean); O(pz_step_summary, var); O(pz_step_summary, n_migrated);\n"
+        "  O(pz_step_summary, e_max); O(pz_step_summary, total_weight);\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(H.ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    return {k: int(v) for k, v in (line.split() for line in out.splitlines())}
+
+
+def test_every_binding_agrees_with_the_compiled_header(pz, tmp_path):
+    """The three bindings of the boundary (ctypes host mirror, the tests' oracle mirror, the Haskell
+    FFI module) use the sizes and byte offsets a C compiler derives from include/pzgpu.h."""
+    lay = _header_layout(tmp_path)
+    for mirror in (pz, H):
+        assert C.sizeof(mirror.ModelDesc) == lay["pz_model_desc"]
+        assert C.sizeof(mirror.StepSummary) == lay["pz_step_summary"]
+        for f in ("kind", "nx", "ny", "scalar_ll_2x", "resampler", "delayed", "F", "Q", "H", "R", "x0", "mtt"):
+            assert getattr(mirror.ModelDesc, f).offset == lay[f"pz_model_desc.{f}"], f
+        for f in ("step", "log_evidence_inc", "ess", "mean", "var", "n_migrated", "e_max", "total_weight"):
+            assert getattr(mirror.StepSummary, f).offset == lay[f"pz_step_summary.{f}"], f
+    hs = open(os.path.join(H.ROOT, "haskell", "PzGpu.hs")).read()
+    assert int(re.search(r"sizeofModelDesc = (\d+)", hs).group(1)) == lay["pz_model_desc"]
+    assert int(re.search(r"sizeofSummary = (\d+)", hs).group(1)) == lay["pz_step_summary"]
+    assert f"pokeByteOff p {lay['pz_model_desc.delayed']} (1 :: Int32)" in hs
+    for field, ty in (("step", "Int64"), ("log_evidence_inc", "CDouble"), ("ess", "CDouble")):
+        assert re.search(rf"peekByteOff ps {lay['pz_step_summary.' + field]} :: IO {ty}", hs), field
+    assert f"ps `plusPtr` {lay['pz_step_summary.mean']}" in hs and f"ps `plusPtr` {lay['pz_step_summary.var']}" in hs
+    # every symbol the Haskell module imports is declared by the header
+    hdr = open(os.path.join(H.ROOT, "include", "pzgpu.h")).read()
+    for sym in re.findall(r'foreign import ccall \w+ "&?(pz_\w+)"', hs):
+        assert re.search(rf"\b{sym}\(", hdr), f"PzGpu.hs imports {sym}, which include/pzgpu.h does not declare"
