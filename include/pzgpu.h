@@ -16,7 +16,11 @@
  *   - pz_last_error() returns a thread-local message for the last failing call;
  *   - the caller owns all host buffers; the library owns device memory, streams, NCCL;
  *   - a pz_filter handle is NOT thread-safe (the reference is single-threaded,
- *     haskell/package.yaml:49-52); calls on one handle must be serialised.
+ *     haskell/package.yaml:49-52); calls on one handle must be serialised;
+ *   - a call on a handle makes the filter's device the calling thread's current CUDA
+ *     device and leaves it current (restoring the previous one would create a context on
+ *     a device the host never asked for); handles on different devices may be used from
+ *     one thread or from several.
  */
 #ifndef PZGPU_H
 #define PZGPU_H

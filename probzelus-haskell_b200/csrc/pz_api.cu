@@ -14,6 +14,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -338,6 +339,8 @@ struct NcclApi {
 NcclApi g_nccl;
 
 int load_nccl() {
+  static std::mutex mu;  // two threads may create their first sharded filters at the same time
+  std::lock_guard<std::mutex> lock(mu);
   if (g_nccl.handle) return PZ_OK;
   void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -388,9 +391,10 @@ void free_filter(pz_filter* f) {
     unsigned long long st[16] = {};
     cudaStreamSynchronize(f->stream);
     dbg_read_stamps(st);
-    fprintf(stderr, "[pz stamps] rank %d (ns after scan start):", f->a.rank);
-    for (int i = 0; i < 11; ++i) fprintf(stderr, " [%d]=%lld", i, (long long)(st[i] - st[0]));
-    fprintf(stderr, "  abs0=%llu\n", st[0]);
+    char line[512];
+    int o = snprintf(line, sizeof(line), "[pz stamps] rank %d (ns after scan start):", f->a.rank);
+    for (int i = 0; i < 11; ++i) o += snprintf(line + o, sizeof(line) - o, " [%d]=%lld", i, (long long)(st[i] - st[0]));
+    fprintf(stderr, "%s\n", line);
   }
 #endif
   if (f->shard_timing) {
@@ -712,11 +716,16 @@ int setup_p2p(pz_filter* f) {
   unsigned char* d_all = nullptr;
   std::vector<Pack> all((size_t)R);
   if (cudaMalloc(&d_all, (size_t)R * sizeof(Pack)) != cudaSuccess) return fail(PZ_ECUDA, "cudaMalloc failed");
-  cudaMemcpy(d_all + (size_t)me * sizeof(Pack), &mine, sizeof(Pack), cudaMemcpyHostToDevice);
-  PZ_NCCL(g_nccl.AllGather(d_all + (size_t)me * sizeof(Pack), d_all, sizeof(Pack), ncclUint8, f->comm, f->stream));
-  PZ_CUDA(cudaStreamSynchronize(f->stream));
-  PZ_CUDA(cudaMemcpy(all.data(), d_all, (size_t)R * sizeof(Pack), cudaMemcpyDeviceToHost));
-  cudaFree(d_all);
+  {
+    cudaError_t e = cudaMemcpy(d_all + (size_t)me * sizeof(Pack), &mine, sizeof(Pack), cudaMemcpyHostToDevice);
+    ncclResult_t r = e == cudaSuccess
+        ? g_nccl.AllGather(d_all + (size_t)me * sizeof(Pack), d_all, sizeof(Pack), ncclUint8, f->comm, f->stream) : ncclSuccess;
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(f->stream);
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpy(all.data(), d_all, (size_t)R * sizeof(Pack), cudaMemcpyDeviceToHost);
+    cudaFree(d_all);
+    if (r != ncclSuccess) return fail(PZ_ENCCL, "all-gather of the IPC handles failed: %s", g_nccl.GetErrorString(r));
+    if (e != cudaSuccess) return fail(PZ_ECUDA, "all-gather of the IPC handles failed: %s", cudaGetErrorString(e));
+  }
   ShardP2P h{};
   const int64_t H = f->hb * kBlk;
   auto open = [&](const cudaIpcMemHandle_t& hd) -> void* {
@@ -1130,21 +1139,24 @@ int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32
   if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1 || f->is_mtt || f->is_rb)
     return fail(PZ_ESTATE, "profiled step: single-GPU systematic filters only");
   PZ_CUDA(cudaSetDevice(f->device));
-  cudaEvent_t ev[4];
-  for (int i = 0; i < 4; ++i) PZ_CUDA(cudaEventCreate(&ev[i]));
-  int rc = stage_obs(f, obs, 1, obs_dim);
-  if (rc) return rc;
-  f->last_launches = launch_step_profiled(f->a, f->stream, ev);
-  f->t += 1;
-  PZ_CUDA(cudaGetLastError());
-  PZ_CUDA(cudaStreamSynchronize(f->stream));
-  for (int i = 0; i < 3; ++i) {
+  cudaEvent_t ev[4] = {};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ev[i]);
+  int rc = e == cudaSuccess ? stage_obs(f, obs, 1, obs_dim) : fail(PZ_ECUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+  if (rc == PZ_OK) {
+    f->last_launches = launch_step_profiled(f->a, f->stream, ev);
+    f->t += 1;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+    if (e != cudaSuccess) rc = fail(PZ_ECUDA, "profiled step failed: %s", cudaGetErrorString(e));
+  }
+  for (int i = 0; i < 3 && rc == PZ_OK; ++i) {
     float x = 0;
     cudaEventElapsedTime(&x, ev[i], ev[i + 1]);
     ms[i] = x;
   }
-  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
-  return PZ_OK;
+  for (int i = 0; i < 4; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_dim, pz_step_summary* out) {
@@ -1185,6 +1197,8 @@ int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_
       if (out) out[done + i] = s;
       if (s.total_weight == 0 && status == PZ_OK)
         status = fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", (unsigned)(t0 + i));
+      if (s.n_migrated == -2 && status == PZ_OK)
+        status = fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange", (unsigned)(t0 + i));
       if (s.n_migrated < 0 && status == PZ_OK)
         status = fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)",
                       (unsigned)(t0 + i), (long long)f->hb);
