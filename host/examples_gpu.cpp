@@ -37,7 +37,8 @@ void put_vec(std::string& s, const double* v, int n) {
   char buf[40];
   s += '[';
   for (int i = 0; i < n; ++i) {
-    snprintf(buf, sizeof(buf), "%.9g", v[i]);
+    if (std::isfinite(v[i])) snprintf(buf, sizeof(buf), "%.9g", v[i]);
+    else snprintf(buf, sizeof(buf), "null");  // aeson encodes NaN / Infinity as null
     if (i) s += ',';
     s += buf;
   }

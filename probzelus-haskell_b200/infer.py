@@ -334,7 +334,8 @@ def resample_multinomial(logw, seed, step):
 
 # ---- output encoding (the JSON lines the Java glimpsetracks visualiser reads) -------------------
 def _num(x):
-    return repr(float(x))
+    x = float(x)
+    return repr(x) if x == x and abs(x) != float("inf") else "null"   # aeson encodes NaN / Infinity as null
 
 
 def json_line_tracks(ground_truth, particles, observations):

@@ -75,6 +75,8 @@ def test_json_line_matches_java_parser(pz):
     assert arr[1][1] == [] and arr[2] == [[0.5, -0.5], [3.0, 4.0]]
     flat = json.loads(pz.json_line_generic1d([1.0, 2.5, -3.0]))     # Generic1D.java:333-348
     assert flat == [1.0, 2.5, -3.0]
+    # a degenerate step (NaN mean) must still be a JSON line: aeson writes non-finite doubles as null
+    assert json.loads(pz.json_line_generic1d([float("nan"), float("inf"), 1.0])) == [None, None, 1.0]
 
 
 @pytest.mark.gpu
