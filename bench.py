@@ -397,6 +397,9 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # also against the nominal 8 TB/s, and for the whole step (value x B_alg per GPU)
+                     "frac_nominal_8TBs": achieved / 8000.0,
+                     "whole_step": {"achieved": value / world * 8 * nx / 1e9, "frac": value / world * 8 * nx / 1e9 / peak},
                      "traffic": ncu_traffic(name, n_p) if world == 1 else None, "kernel": "pf_step_tile", "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": t_tile_ms, "kernel_ms_source": kernel_src,
                      "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
