@@ -139,16 +139,18 @@ def helper_desc(H, name):
     return {"rw1d": H.model_rw1d, "lg42": H.model_mtt_track, "lg63": H.model_stt}[name]()
 
 
-def cpu_port_rate(H, name, n_sample, steps, threads, faithful=False):
+def cpu_port_rate(H, name, n_sample, steps, threads, faithful=False, optimised=False):
     """particle-updates/s of the CPU port.  faithful=False: the reference's algorithm (double,
     log-domain normalise, multinomial draws) with the O(N) per-draw CDF walk replaced by a binary
     search (identical ancestors) and OpenMP over particles; faithful=True: the literal O(N^2) walk,
-    one thread."""
+    one thread; optimised=True: SURVEY.md 8(d)(ii), not the reference's algorithm but the best a host
+    does with the same step (max-shifted weights, one O(N) systematic resample over a parallel prefix
+    sum, every loop over all cores)."""
     lib = H.oracle()
     d = helper_desc(H, name)
     obs, _ = H.gen_obs(d, steps)
     t0 = time.perf_counter()
-    rc = lib.pzo_refpf_run(C.byref(d), n_sample, 1, H.ptr(obs, C.c_double), steps, 0 if faithful else 1, None, None,
+    rc = lib.pzo_refpf_run(C.byref(d), n_sample, 1, H.ptr(obs, C.c_double), steps, 2 if optimised else (0 if faithful else 1), None, None,
                            1 if faithful else threads)
     dt = time.perf_counter() - t0
     assert rc == 0
@@ -166,6 +168,7 @@ def run_reference(args):
     K, W = args.steps, args.warmup
     cpu_port_rate(H, args.model, n_sample, max(1, min(W, 2)), threads)  # warm-up
     rate, dt = cpu_port_rate(H, args.model, n_sample, K, threads)
+    orate, odt = cpu_port_rate(H, args.model, n_sample, K, threads, optimised=True)
     nx, _ = MODELS[args.model]
     line = {
         "impl": "reference", "metric": "particle-updates/sec", "value": rate, "unit": "particle-updates/s",
@@ -177,7 +180,10 @@ def run_reference(args):
                          "sample": f"N={n_sample} particles x {K} steps of the same model; reference algorithm "
                                    "(Inference.hs:57-66,101-104: double, logaddexp normalise, multinomial resample2) "
                                    "with the O(N) per-draw CDF walk replaced by a binary search and OpenMP over particles; "
-                                   "the literal O(N^2) reference cannot finish one step at this N"},
+                                   "the literal O(N^2) reference cannot finish one step at this N",
+                         "optimised_systematic": {"value": orate, "cores": threads,
+                                                  "sample": f"same sample; not the reference's algorithm: max-shifted weights, O(N) systematic "
+                                                            f"resampling over a parallel prefix sum, all loops over all cores ({odt:.1f} s)"}},
         "e2e": {"value": rate, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -380,10 +386,14 @@ def run_b200(args):
         steps_cpu = 5
         rate, dt = cpu_port_rate(H, name, n_sample, steps_cpu, threads)
         frate, fdt = cpu_port_rate(H, name, 1000, 100, 1, faithful=True)
+        orate, odt = cpu_port_rate(H, name, n_sample, steps_cpu, threads, optimised=True)
         cpu = {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": "port",
                "sample": f"N={n_sample} x {steps_cpu} steps, reference algorithm in double with binary-search multinomial + OpenMP ({dt:.1f} s)",
                "faithful_o_n2": {"value": frate, "cores": 1,
-                                 "sample": f"configs[0]: N=1000 x 100 steps, literal O(N^2) resample2 ({fdt:.1f} s)"}}
+                                 "sample": f"configs[0]: N=1000 x 100 steps, literal O(N^2) resample2 ({fdt:.1f} s)"},
+               "optimised_systematic": {"value": orate, "cores": threads,
+                                        "sample": f"same sample; not the reference's algorithm: max-shifted weights, O(N) systematic "
+                                                  f"resampling over a parallel prefix sum, all loops over all cores ({odt:.1f} s)"}}
     line = {
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,

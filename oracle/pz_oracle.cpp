@@ -769,6 +769,59 @@ int pzo_refpf_run(const pz_model_desc* d, int64_t n, uint64_t seed, const double
       for (int a = 0; a < ny; ++a) { double s = 0; for (int k = 0; k < ny; ++k) s += Rinv[a][k] * dd[k]; quad += dd[a] * s; }
       lw[i] = wscale * quad + llc;  // score accumulated by `observe`
     }
+    if (mode == 2) {
+      // "optimised CPU" row of SURVEY.md 8(d)(ii): not the reference's algorithm but the best a host
+      // does with the same step -- max-shifted weights (Util/Numeric.hs:12-17), one O(N) systematic
+      // resample from a chunked parallel prefix sum, parallel gather; every loop over all cores.
+      double mx = -INFINITY;
+#pragma omp parallel for schedule(static) reduction(max : mx)
+      for (int64_t i = 0; i < n; ++i) mx = lw[i] > mx ? lw[i] : mx;
+      if (!(mx > -INFINITY)) return PZ_EDEGENERATE;
+      int nchunk = 1;
+#if defined(_OPENMP)
+      nchunk = omp_get_max_threads();
+#endif
+      if ((int64_t)nchunk > n) nchunk = (int)n;
+      std::vector<double> csum((size_t)nchunk + 1, 0.0);
+      const int64_t per = (n + nchunk - 1) / nchunk;
+#pragma omp parallel for schedule(static, 1)
+      for (int c = 0; c < nchunk; ++c) {
+        const int64_t lo = c * per, hi = std::min<int64_t>(n, lo + per);
+        double acc = 0;
+        for (int64_t i = lo; i < hi; ++i) { acc += exp(lw[i] - mx); cdf[i] = acc; }
+        csum[c + 1] = acc;
+      }
+      for (int c = 0; c < nchunk; ++c) csum[c + 1] += csum[c];
+      const double total = csum[nchunk];
+#pragma omp parallel for schedule(static, 1)
+      for (int c = 1; c < nchunk; ++c) {
+        const int64_t lo = c * per, hi = std::min<int64_t>(n, lo + per);
+        for (int64_t i = lo; i < hi; ++i) cdf[i] += csum[c];
+      }
+      uint32_t r[4];
+      philox(0u, 0u, (uint32_t)t, kStreamMulti, seed ^ 0x5EEDull, r);
+      const double u = ((double)r[0] + 0.5) * 0x1p-32, stepw = total / (double)n;
+#pragma omp parallel for schedule(static, 1)
+      for (int c = 0; c < nchunk; ++c) {  // slots [lo, hi): one search, then a merge walk
+        const int64_t lo = c * per, hi = std::min<int64_t>(n, lo + per);
+        if (lo >= hi) continue;
+        int64_t k = std::upper_bound(cdf.begin(), cdf.end(), ((double)lo + u) * stepw) - cdf.begin();
+        for (int64_t j = lo; j < hi; ++j) {
+          const double pos = ((double)j + u) * stepw;
+          while (k < n - 1 && cdf[k] <= pos) ++k;
+          anc[j] = k < n ? k : n - 1;
+        }
+      }
+      for (int a = 0; a < nx; ++a) {
+        double s1 = 0, s2 = 0;
+        double* dst = &x[(size_t)a * n]; const double* src = &xn[(size_t)a * n];
+#pragma omp parallel for schedule(static) reduction(+ : s1, s2)
+        for (int64_t j = 0; j < n; ++j) { const double v = src[anc[j]]; dst[j] = v; s1 += v; s2 += v * v; }
+        if (mean_out) mean_out[t * nx + a] = s1 / n;
+        if (var_out) var_out[t * nx + a] = s2 / n - (s1 / n) * (s1 / n);
+      }
+      continue;
+    }
     // normalize: totalMass = sum (map snd xs)  -- left fold of Log's (+)
     double tot = -INFINITY;
     for (int64_t i = 0; i < n; ++i) tot = logaddexp(tot, lw[i]);

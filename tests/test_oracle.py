@@ -216,6 +216,25 @@ def test_refpf_faithful_matches_kalman_and_fast_mode():
     assert np.max(np.abs(m0 - km)) < 6 * np.sqrt(kc[-1, 0, 0] / n) * 2.5
 
 
+def test_refpf_optimised_cpu_mode_tracks_the_exact_posterior():
+    """Mode 2 of the CPU port (the "optimised CPU" baseline row of SURVEY.md 8(d)(ii): max-shifted weights,
+    one O(N) systematic resample over a chunked parallel prefix sum) is a correct filter, for every model and
+    for any thread count (the chunking must not change which ancestors are drawn)."""
+    lib = H.oracle()
+    for d, n, T in ((H.model_rw1d(), 4000, 25), (H.model_mtt_track(), 6000, 12), (H.model_stt(), 6000, 12)):
+        obs, _ = H.gen_obs(d, T)
+        km, kc, _ = H.kalman(d, obs)
+        nx = d.nx
+        runs = []
+        for threads in (1, 3):
+            m, v = np.zeros((T, nx)), np.zeros((T, nx))
+            assert lib.pzo_refpf_run(C.byref(d), n, 21, H.ptr(obs, C.c_double), T, 2, H.ptr(m, C.c_double), H.ptr(v, C.c_double), threads) == 0
+            runs.append(m)
+            sd = np.sqrt(np.array([np.diag(kc[t])[:nx] for t in range(T)]))
+            assert np.max(np.abs(m - km[:, :nx]) / sd) < 6 * 2.5 / np.sqrt(n) * np.sqrt(nx) * 2
+        assert np.allclose(runs[0], runs[1], rtol=0, atol=1e-9)
+
+
 def test_canonical_vs_refpf_distribution():
     """PF-versus-PF (gate 3): canonical fp32 systematic filter vs the
     reference-faithful double multinomial filter agree within Monte Carlo error."""
