@@ -400,7 +400,7 @@ void free_filter(pz_filter* f) {
   if (f->shard_timing) {
     shard_timing_collect(f);
     if (f->tcount)
-      fprintf(stderr, "[pz shard timing] rank %d of %d, %lld steps: step kernel %.1f us, scan %.1f us, plan+halo push %.1f us, partition %.1f us\n",
+      fprintf(stderr, "[pz shard timing] rank %d of %d, %lld steps: step kernel %.1f us, scan %.1f us, plan + prefix margins %.1f us, join + partition %.1f us (pf_halo_push runs beside scan and plan)\n",
               f->a.rank, f->a.world, (long long)f->tcount, 1e3 * f->tacc[0] / f->tcount, 1e3 * f->tacc[1] / f->tcount,
               1e3 * f->tacc[2] / f->tcount, 1e3 * f->tacc[3] / f->tcount);
     for (auto& e : f->tev) if (e) cudaEventDestroy(e);
