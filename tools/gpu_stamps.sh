@@ -1,5 +1,6 @@
 #!/bin/bash
-# gpurun --gpus N: phase stamps of the sharded exchange (debug build with -DPZ_DBG_STAMPS in build/variants)
+# gpurun --gpus N: phase stamps of the sharded exchange (debug build with -DPZ_DBG_STAMPS in build/variants:
+# run `make -C probzelus-haskell_b200/csrc stamps` before sending the tree)
 set -u
 mkdir -p gpurun_out
 N=${1:-2}
