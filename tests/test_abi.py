@@ -58,6 +58,69 @@ def test_argument_validation(pz):
     assert pz.lib().pz_model_rw1d(None, 1.0, 3.0) == -1
 
 
+def test_every_argument_error_is_reported_before_device_work(pz):
+    """Error behaviour of the boundary: bad descriptors, sizes, ranks and null
+    pointers are PZ_EINVAL (-1) with a message, on a machine with or without a GPU; nothing is created."""
+    L = pz.lib()
+    ident = (C.c_char * 128)()
+
+    def create(d, n, rank=0, world=1, nccl=ident):
+        h = C.c_void_p()
+        if world == 1:
+            rc = L.pz_filter_create(C.byref(d), n, 0, 0, C.byref(h))
+        else:
+            rc = L.pz_filter_create_sharded(C.byref(d), n, 0, 0, rank, world, nccl, C.byref(h))
+        assert not h.value
+        return rc, L.pz_last_error()
+
+    d = pz.rw1d(); d.kind = 77
+    assert create(d, 1000) == (-1, b"unknown model kind 77")
+    d = pz.rw1d(); d.nx, d.ny = 2, 1
+    rc, msg = create(d, 1000)
+    assert rc == -1 and b"no kernel instantiated for nx=2 ny=1" in msg
+    rc, msg = create(pz.rw1d(), 0)
+    assert rc == -1 and b"n_particles" in msg
+    rc, msg = create(pz.rw1d(), (1 << 30) + 1)
+    assert rc == -1 and b"2^30" in msg
+    # sharded: rank / world, whole resampling blocks per rank, systematic resampler only, an id is required
+    rc, msg = create(pz.rw1d(), 2 * 256 * 8, rank=2, world=2)
+    assert rc == -1 and b"bad rank 2 / world 2" in msg
+    rc, msg = create(pz.rw1d(), 2 * 256 * 8 + 256, rank=0, world=2)
+    assert rc == -1 and b"divisible by world * 256" in msg
+    rc, msg = create(pz.rw1d(resampler=pz.PZ_RESAMPLE_MULTINOMIAL_REF), 2 * 256 * 8, rank=0, world=2)
+    assert rc == -1 and b"systematic" in msg
+    rc, msg = create(pz.rw1d(), 2 * 256 * 8, rank=0, world=2, nccl=None)
+    assert rc == -1 and b"nccl_unique_id" in msg
+    rc, msg = create(pz.rw1d(), 33 * 256, rank=0, world=33)
+    assert rc == -1 and b"at most 32 ranks" in msg
+    # tracker: fixed capacities, one GPU
+    m = pz.mtt(); m.mtt.k_max = 8
+    rc, msg = create(m, 1000)
+    assert rc == -1 and b"k_max" in msg
+    m = pz.mtt(); m.mtt.m_max = 33
+    rc, msg = create(m, 1000)
+    assert rc == -1 and b"m_max" in msg
+    rc, msg = create(pz.mtt(), (1 << 28) + 1)
+    assert rc == -1 and b"2^28" in msg
+    rc, msg = create(pz.mtt(), 2 * 256 * 8, rank=0, world=2)
+    assert rc == -1 and b"one GPU" in msg
+    # null handles / buffers
+    s = pz.StepSummary()
+    y = (C.c_double * 1)(0.0)
+    assert L.pz_filter_step(None, y, 1, 1, C.byref(s)) == -1
+    assert L.pz_filter_run(None, y, 1, 1, None) == -1
+    assert L.pz_filter_read_particles(None, 1, None, 0) == -1
+    assert L.pz_filter_read_ancestors(None, None, 0) == -1
+    assert L.pz_filter_read_state(None, None, 0) == -1
+    assert L.pz_filter_last_timing(None, None, None) == -1
+    assert L.pz_filter_n_local(None) == 0
+    assert L.pz_comm_unique_id(None) == -1
+    L.pz_filter_destroy(None)   # a no-op, like free(NULL)
+    lo, hi = C.c_int64(), C.c_int64()
+    assert L.pz_shard_halo_range(0, 1, 0, 0, C.byref(lo), C.byref(hi)) == -1
+    assert L.pz_shard_halo_range(0, 1, 16, 0, None, None) == -1
+
+
 def test_delayed_descriptor_validation(pz):
     """model.delayed = 1 (delay=True): one GPU only (every particle is the same marginal), and the posterior
     read-out refuses null pointers; both are argument errors, reported before any device work."""
