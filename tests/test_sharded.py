@@ -50,16 +50,16 @@ def _cdf_offset(p):
     return ((p >> 2) & 1) * 128 + (p >> 3) * 4 + (p & 3)
 
 
-def _gloo_worker(rank, world, port, n_global, seed, ret):
+def _gloo_worker(rank, world, port, n_global, seed, sigma, shift, ret):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
     pz = g.load_package()
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     rng = np.random.default_rng(seed)
-    lw = (rng.standard_normal(n_global) * 3).astype(np.float32)
+    lw = (rng.standard_normal(n_global) * sigma).astype(np.float32)
     lw[rng.random(n_global) < 0.05] = -np.inf
-    lw[: n_global // 3] -= 6.0   # unbalanced rank totals => real migration
+    lw[: n_global // 3] -= shift   # unbalanced rank totals => real migration
     U = 0x12345678
     n_local = n_global // world
     nb = n_local // BLK
@@ -150,8 +150,8 @@ def _gloo_worker(rank, world, port, n_global, seed, ret):
         full = np.concatenate([t.numpy() for t in out])
         rc, ref = H.oracle_systematic(lw, U)
         ret["ok"] = bool(rc == 0 and np.array_equal(full, ref))
-        ret["migrated"] = migrated
         ret["mismatch"] = int(np.sum(full != ref))
+    ret["migrated%d" % rank] = migrated
     dist.destroy_process_group()
 
 
@@ -160,9 +160,22 @@ def test_sharding_protocol_gloo_world2():
     mgr = mp.Manager()
     ret = mgr.dict()
     port = _free_port()
-    mp.spawn(_gloo_worker, args=(2, port, 8192, 17, ret), nprocs=2, join=True)
+    mp.spawn(_gloo_worker, args=(2, port, 8192, 17, 3.0, 6.0, ret), nprocs=2, join=True)
     assert ret.get("ok"), dict(ret)
-    assert ret["migrated"] > 0  # the skewed weights make rank 0 take ancestors from rank 1's margin
+    assert ret["migrated0"] > 0  # the skewed weights make rank 0 take ancestors from rank 1's margin
+
+
+def test_sharding_protocol_gloo_world4_middle_ranks():
+    """Four ranks: the two middle ranks exchange margins with BOTH neighbours and take ancestors across both of
+    their boundaries (a milder tilt than the world-2 case keeps every boundary inside the 8-block margin)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_gloo_worker, args=(4, port, 16384, 23, 0.5, 0.25, ret), nprocs=4, join=True)
+    assert ret.get("ok"), dict(ret)
+    # the tilt shifts ancestry towards the later ranks: ranks 0..2 take ancestors from their right neighbour's margin
+    assert all(ret["migrated%d" % r] > 0 for r in range(3)), dict(ret)
 
 
 def test_halo_range_function(pz):
