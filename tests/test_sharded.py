@@ -165,17 +165,19 @@ def test_sharding_protocol_gloo_world2():
     assert ret["migrated0"] > 0  # the skewed weights make rank 0 take ancestors from rank 1's margin
 
 
-def test_sharding_protocol_gloo_world4_middle_ranks():
-    """Four ranks: the two middle ranks exchange margins with BOTH neighbours and take ancestors across both of
-    their boundaries (a milder tilt than the world-2 case keeps every boundary inside the 8-block margin)."""
+@pytest.mark.parametrize("shift", [0.25, -0.25])
+def test_sharding_protocol_gloo_world4_middle_ranks(shift):
+    """Four ranks: the two middle ranks exchange margins with BOTH neighbours.  Tilting the weights towards the
+    later (shift > 0) or the earlier (shift < 0) particles moves ancestry across every boundary to the right or to
+    the left, so both halos of the middle ranks are read (the tilt is mild enough for the 8-block margin)."""
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     ret = mgr.dict()
     port = _free_port()
-    mp.spawn(_gloo_worker, args=(4, port, 16384, 23, 0.5, 0.25, ret), nprocs=4, join=True)
+    mp.spawn(_gloo_worker, args=(4, port, 16384, 23, 0.5, shift, ret), nprocs=4, join=True)
     assert ret.get("ok"), dict(ret)
-    # the tilt shifts ancestry towards the later ranks: ranks 0..2 take ancestors from their right neighbour's margin
-    assert all(ret["migrated%d" % r] > 0 for r in range(3)), dict(ret)
+    takers = range(3) if shift > 0 else range(1, 4)   # ranks whose slots reach into a neighbour's margin
+    assert all(ret["migrated%d" % r] > 0 for r in takers), dict(ret)
 
 
 def test_halo_range_function(pz):
