@@ -131,8 +131,8 @@ def synth_obs(d, T, seed=0x0B5E2026):
     return obs
 
 
-def model_desc(pz, name):
-    return {"rw1d": pz.rw1d, "lg42": pz.mtt_track, "lg63": pz.stt}[name]()
+def model_desc(pz, name, f64=False):
+    return {"rw1d": pz.rw1d, "lg42": pz.mtt_track, "lg63": pz.stt}[name](f64=f64)
 
 
 def helper_desc(H, name):
@@ -301,7 +301,9 @@ def run_b200(args):
     if world > 1:
         n_p -= n_p % 256  # a sharded filter holds whole resampling blocks (256 particles) per rank
     K, W = args.steps, args.warmup
-    d = model_desc(pz, name)
+    f64 = args.dtype == "f64"
+    esz = 8 if f64 else 4
+    d = model_desc(pz, name, f64)
     obs = synth_obs(d, W + K + 2 * K + 8)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -360,7 +362,7 @@ def run_b200(args):
         prof = np.array([[dev_ms / K, float("nan"), float("nan")]])
         kernel_src = "whole step (kernel + collectives), device events"
     t_tile_ms = float(np.mean(prof[:, 0]))
-    alg_bytes = 2.0 * nx * 4 * n_p  # read the state once, write it once; the kernel also moves 4 B of u16 weights
+    alg_bytes = 2.0 * nx * esz * n_p  # read the state once, write it once; the kernel also moves 4 B of u16 weights
     achieved = alg_bytes / (t_tile_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
@@ -397,11 +399,11 @@ def run_b200(args):
     line = {
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"{name} bootstrap particle filter, N={n_p} particles per GPU (BASELINE.json configs[1])",
-                   "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp32",
+                   "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp64" if f64 else "fp32",
                    "weights": "u16 fixed point per particle, u64 block prefix", "resampler": "systematic (canonical PZ-SYS-256/q16)",
-                   "l2": "inputs exceed L2 (state %.0f MB per buffer)" % (nx * 4 * n_p / 1e6), "wall_s_timed": wall},
+                   "l2": "inputs exceed L2 (state %.0f MB per buffer)" % (nx * esz * n_p / 1e6), "wall_s_timed": wall},
         "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 144,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": int(launches),
@@ -409,7 +411,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # also against the nominal 8 TB/s, and for the whole step (value x B_alg per GPU)
                      "frac_nominal_8TBs": achieved / 8000.0,
-                     "whole_step": {"achieved": value / world * 8 * nx / 1e9, "frac": value / world * 8 * nx / 1e9 / peak},
+                     "whole_step": {"achieved": value / world * 2 * esz * nx / 1e9, "frac": value / world * 2 * esz * nx / 1e9 / peak},
                      "traffic": ncu_traffic(name, n_p) if world == 1 else None, "kernel": "pf_step_tile", "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "kernel_ms": t_tile_ms, "kernel_ms_source": kernel_src,
                      "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
@@ -427,6 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="rw1d", choices=list(MODELS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="state storage and arithmetic (descriptor flag state_f64)")
     ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU (weak scaling, the default)")
     ap.add_argument("--total-particles", type=int, default=0,
                     help="strong scaling: the whole population, split evenly over the GPUs (overrides --particles)")

@@ -92,7 +92,11 @@ typedef struct pz_model_desc {
                            Gaussian marginal, so every particle carries the exact Kalman
                            posterior (makeMarginal / makeConditional, DelayedSampling.hs:135-152)
                            and all weights are equal.  RW1D / LINGAUSS only.                  */
-  int32_t reserved[2];
+  int32_t state_f64;    /* 1 = particle state, model arithmetic, log-weights and moment sums in double,
+                           the reference's own precision (Inference.hs:28 `type Weight = Log Double`,
+                           Distributions.hs:157-166); 0 = fp32 state (half the HBM traffic).  The integer
+                           resampler is the same in both.  RW1D / LINGAUSS only.                */
+  int32_t reserved;
   double F[PZ_MAX_NX * PZ_MAX_NX];  /* x' ~ N(F x, Q)                                        */
   double Q[PZ_MAX_NX * PZ_MAX_NX];
   double H[PZ_MAX_NY * PZ_MAX_NX];  /* y  ~ N(H x', R)                                       */
@@ -185,8 +189,10 @@ PZ_API int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_
 
 /* Parity / debug taps. */
 PZ_API int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n);      /* ancestors of the pending resample */
-PZ_API int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len);       /* pre-resample population, SoA [nx][N] */
+PZ_API int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len);       /* pre-resample population, SoA [nx][N] (fp32 filters) */
 PZ_API int pz_filter_read_logw(pz_filter* f, float* out, int64_t n);              /* log-weights of that population */
+PZ_API int pz_filter_read_state_f64(pz_filter* f, double* out, int64_t out_len);  /* the same, exact for state_f64 filters (widened for fp32 ones) */
+PZ_API int pz_filter_read_logw_f64(pz_filter* f, double* out, int64_t n);
 PZ_API int64_t pz_filter_n_local(const pz_filter* f);
 
 /* Standalone canonical systematic resampler on stored log-weights (bit-exact tests):

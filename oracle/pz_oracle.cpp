@@ -116,8 +116,7 @@ inline int32_t block_exponent(float maxlw) {
 // Weight of a particle relative to 2^n_b: w = 2^d, d = max(lw * log2(e) - n_b, -32), by the
 // degree-5 polynomial of include/pz_spec_tables.h, and its 16-bit fixed-point value
 // q = rint(w * 2^15) (<= 46990).  NaN log-weights give the smallest weight (q = 0).
-inline void weight_q(float lw, float nbf, float* w, uint32_t* q) {
-  float d = fmaf(lw, kLog2e, -nbf);
+inline void weight_q_from_arg(float d, float* w, uint32_t* q) {
   d = fminf(fmaxf(d, -32.0f), 1.0f);
   const float t = d + 12582912.0f;
   const float r = t - 12582912.0f;
@@ -132,9 +131,23 @@ inline void weight_q(float lw, float nbf, float* w, uint32_t* q) {
   *w = wv;
   *q = f2u(fmaf(wv, 32768.0f, 8388608.0f)) & 0x7FFFFFu;
 }
+inline void weight_q(float lw, float nbf, float* w, uint32_t* q) { weight_q_from_arg(fmaf(lw, kLog2e, -nbf), w, q); }
+// f64 filters (descriptor flag state_f64): the block exponent and the argument of the weight polynomial
+// are formed in double and the argument is rounded to fp32 once; everything after that is the fp32 spec.
+constexpr double kLog2eD = 0x1.71547652b82fep+0;
+inline int32_t block_exponent(double maxlw) {
+  if (!(maxlw > -INFINITY)) return kNZero;
+  double e = maxlw * kLog2eD;
+  e = fmin(fmax(e, -262144.0), 262144.0);
+  return (int32_t)rint(e);
+}
+inline void weight_q(double lw, double nbf, float* w, uint32_t* q) { weight_q_from_arg((float)fma(lw, kLog2eD, -nbf), w, q); }
 
 // stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)
 inline float sanitize_lw(float lw) { return (lw == lw && lw < INFINITY) ? lw : -INFINITY; }
+inline double sanitize_lw(double lw) { return (lw == lw && lw < INFINITY) ? lw : -INFINITY; }
+inline float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
+inline double t_fma(double a, double b, double c) { return fma(a, b, c); }
 
 // CDF order inside a canonical block: position p <-> memory offset (two interleaved halves of
 // 128, four particles per lane): p = lane * 8 + half * 4 + k  <->  off = half * 128 + lane * 4 + k.
@@ -143,23 +156,26 @@ inline int cdf_offset(int p) { return ((p >> 2) & 1) * 128 + (p >> 3) * 4 + (p &
 // ---------------------------------------------------------------------------------------
 // Linear-Gaussian model family: derived fp32 parameters.
 // ---------------------------------------------------------------------------------------
-struct LgParams {
+template <class T>
+struct LgParamsT {
   int nx = 0, ny = 0;
-  float F[PZ_MAX_NX][PZ_MAX_NX];
-  float Lq[PZ_MAX_NX][PZ_MAX_NX];  // lower Cholesky factor of Q (sampleNormalDist uses hmatrix's
+  T F[PZ_MAX_NX][PZ_MAX_NX];
+  T Lq[PZ_MAX_NX][PZ_MAX_NX];  // lower Cholesky factor of Q (sampleNormalDist uses hmatrix's
                                    // UPPER factor, MVDistributions.hs:40; identical for the diagonal
                                    // Q of every in-scope model)
-  float H[PZ_MAX_NY][PZ_MAX_NX];
-  float Rinv[PZ_MAX_NY][PZ_MAX_NY];
-  float x0[PZ_MAX_NX];
-  float wscale;     // -0.5 (mvNormal_ll0) or -1.0 (doubled scalar score, Distributions.hs:160-161)
+  T H[PZ_MAX_NY][PZ_MAX_NX];
+  T Rinv[PZ_MAX_NY][PZ_MAX_NY];
+  T x0[PZ_MAX_NX];
+  T wscale;         // -0.5 (mvNormal_ll0) or -1.0 (doubled scalar score, Distributions.hs:160-161)
   double ll_const;  // additive constant of the score dropped from the per-particle weight
 };
+typedef LgParamsT<float> LgParams;
 
-bool derive_lg(const pz_model_desc* d, LgParams* p) {
+template <class T>
+bool derive_lg(const pz_model_desc* d, LgParamsT<T>* p) {
   int nx = d->nx, ny = d->ny;
   if (nx < 1 || nx > PZ_MAX_NX || ny < 1 || ny > PZ_MAX_NY) return false;
-  *p = LgParams();
+  *p = LgParamsT<T>();
   p->nx = nx; p->ny = ny;
   double L[PZ_MAX_NX][PZ_MAX_NX] = {};
   for (int j = 0; j < nx; ++j) {
@@ -192,40 +208,42 @@ bool derive_lg(const pz_model_desc* d, LgParams* p) {
     }
   }
   for (int i = 0; i < nx; ++i) {
-    for (int j = 0; j < nx; ++j) { p->F[i][j] = (float)d->F[i * nx + j]; p->Lq[i][j] = (float)L[i][j]; }
-    p->x0[i] = (float)d->x0[i];
+    for (int j = 0; j < nx; ++j) { p->F[i][j] = (T)d->F[i * nx + j]; p->Lq[i][j] = (T)L[i][j]; }
+    p->x0[i] = (T)d->x0[i];
   }
   for (int i = 0; i < ny; ++i) {
-    for (int j = 0; j < nx; ++j) p->H[i][j] = (float)d->H[i * nx + j];
-    for (int j = 0; j < ny; ++j) p->Rinv[i][j] = (float)A[i][ny + j];
+    for (int j = 0; j < nx; ++j) p->H[i][j] = (T)d->H[i * nx + j];
+    for (int j = 0; j < ny; ++j) p->Rinv[i][j] = (T)A[i][ny + j];
   }
   bool dbl = (ny == 1 && d->scalar_ll_2x);
-  p->wscale = dbl ? -1.0f : -0.5f;
+  p->wscale = dbl ? (T)-1.0 : (T)-0.5;
   p->ll_const = (dbl ? -1.0 : -0.5) * (logdet + ny * log(2 * M_PI));
   return true;
 }
 
-inline void lg_propagate(const LgParams& p, const float* x, const float* z, float* xn) {
+template <class T>
+inline void lg_propagate(const LgParamsT<T>& p, const T* x, const T* z, T* xn) {
   for (int r = 0; r < p.nx; ++r) {
-    float acc = p.F[r][0] * x[0];
-    for (int c = 1; c < p.nx; ++c) acc = fmaf(p.F[r][c], x[c], acc);
-    for (int c = 0; c <= r; ++c) acc = fmaf(p.Lq[r][c], z[c], acc);
+    T acc = p.F[r][0] * x[0];
+    for (int c = 1; c < p.nx; ++c) acc = t_fma(p.F[r][c], x[c], acc);
+    for (int c = 0; c <= r; ++c) acc = t_fma(p.Lq[r][c], z[c], acc);
     xn[r] = acc;
   }
 }
 
-inline float lg_logweight(const LgParams& p, const float* xn, const float* y) {
-  float d[PZ_MAX_NY];
+template <class T>
+inline T lg_logweight(const LgParamsT<T>& p, const T* xn, const T* y) {
+  T d[PZ_MAX_NY];
   for (int k = 0; k < p.ny; ++k) {
-    float acc = p.H[k][0] * xn[0];
-    for (int c = 1; c < p.nx; ++c) acc = fmaf(p.H[k][c], xn[c], acc);
+    T acc = p.H[k][0] * xn[0];
+    for (int c = 1; c < p.nx; ++c) acc = t_fma(p.H[k][c], xn[c], acc);
     d[k] = y[k] - acc;
   }
-  float quad = 0.0f;
+  T quad = 0;
   for (int k = 0; k < p.ny; ++k) {
-    float t = p.Rinv[k][0] * d[0];
-    for (int l = 1; l < p.ny; ++l) t = fmaf(p.Rinv[k][l], d[l], t);
-    quad = (k == 0) ? d[0] * t : fmaf(d[k], t, quad);
+    T t = p.Rinv[k][0] * d[0];
+    for (int l = 1; l < p.ny; ++l) t = t_fma(p.Rinv[k][l], d[l], t);
+    quad = (k == 0) ? d[0] * t : t_fma(d[k], t, quad);
   }
   return p.wscale * quad;
 }
@@ -285,7 +303,8 @@ inline uint64_t shift_guard(uint64_t s, int64_t ksh) {
 }
 
 // returns false when every weight is zero (degenerate)
-bool build_plan(const float* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
+template <class T>
+bool build_plan(const T* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
   pl->n = n;
   pl->nblk = (n + kBlk - 1) / kBlk;
   pl->q.assign(n, 0); pl->w.assign(n, 0.0f);
@@ -293,15 +312,15 @@ bool build_plan(const float* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
   pl->emax = kNZero;
   for (int64_t b = 0; b < pl->nblk; ++b) {
     const int64_t hi = std::min(n, (b + 1) * kBlk);
-    float mx = -INFINITY;
-    for (int64_t i = b * kBlk; i < hi; ++i) mx = fmaxf(mx, sanitize_lw(lw[i]));
+    T mx = -INFINITY;
+    for (int64_t i = b * kBlk; i < hi; ++i) mx = std::max(mx, sanitize_lw(lw[i]));
     const int32_t nb = block_exponent(mx);
     pl->eb[b] = nb;
     if (nb == kNZero) continue;
     uint32_t s = 0;
     for (int64_t i = b * kBlk; i < hi; ++i) {
       uint32_t qi; float wi;
-      weight_q(sanitize_lw(lw[i]), (float)nb, &wi, &qi);
+      weight_q(sanitize_lw(lw[i]), (T)nb, &wi, &qi);
       pl->q[i] = (uint16_t)qi; pl->w[i] = wi;
       s += qi;
     }
@@ -402,44 +421,144 @@ void multinomial_ancestors(const ResamplePlan& pl, uint64_t seed, uint32_t t, in
   }
 }
 
+inline uint32_t resample_uniform(uint64_t seed, uint32_t t) {
+  uint32_t r[4];
+  philox(0, 0, t, kStreamResample, seed, r);
+  return r[0];
+}
+
 // ---------------------------------------------------------------------------------------
 // The canonical filter (bit-exact twin of the CUDA path).
 // ---------------------------------------------------------------------------------------
-struct OFilter {
+struct OFilterBase {
+  virtual ~OFilterBase() {}
+  virtual int step(const double* obs, pz_step_summary* out) = 0;
+  virtual void state32(float* x, float* lw, int32_t* anc) = 0;
+  virtual void state64(double* x, double* lw, int32_t* anc) = 0;
+  virtual int block_stats(int32_t* eb, uint64_t* sb, int32_t* emax, uint64_t* total) = 0;
+  virtual void derived(float* F, float* Lq, float* H, float* Rinv, float* wscale, double* ll_const) = 0;
+};
+
+template <class T>
+struct OFilterT : OFilterBase {
   pz_model_desc desc;
-  LgParams p;
+  LgParamsT<T> p;
   int64_t n = 0;
   uint64_t seed = 0;
   uint32_t t = 0;
-  std::vector<float> x;    // SoA [nx][n], population the pending weights refer to
-  std::vector<float> lw;   // its log-weights
+  std::vector<T> x;    // SoA [nx][n], population the pending weights refer to
+  std::vector<T> lw;   // its log-weights
   std::vector<int32_t> anc;  // ancestors used by the last step
   double center[PZ_MAX_NX];  // centring constants of the moment sums (previous posterior mean)
+
+  void summarise(const ResamplePlan& pl, pz_step_summary* s) const {
+    // the same fp32 weights the resampler quantises, at scale 2^emax, in double
+    double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
+    for (int64_t i = 0; i < n; ++i) {
+      const int32_t eb = pl.eb[i / kBlk];
+      if (eb == kNZero) continue;
+      double w = ldexp((double)pl.w[i], eb - pl.emax);
+      sw += w; sw2 += w * w;
+      for (int d = 0; d < p.nx; ++d) {
+        double dx = (double)(T)(x[(size_t)d * n + i] - (T)center[d]);
+        sx[d] += w * dx; sxx[d] += w * dx * dx;
+      }
+    }
+    s->ess = sw * sw / sw2;
+    for (int d = 0; d < p.nx; ++d) {
+      double m = sx[d] / sw;
+      s->mean[d] = (double)(T)center[d] + m;
+      s->var[d] = sxx[d] / sw - m * m;
+    }
+    s->log_evidence_inc = log(sw) + pl.emax * M_LN2 - log((double)n) + p.ll_const;
+    s->e_max = pl.emax;
+    s->total_weight = pl.total;
+    s->n_migrated = 0;
+  }
+
+  // One step of zparticles' (Inference.hs:101-104) in the cross-step order of the CUDA path:
+  // resample the pending population by its weights, propagate every child, weight it by the
+  // new observation.  (The reference weights first and resamples at the end of the same step;
+  // the populations and weights visited are identical, only the step boundary moves.)
+  int step(const double* obs, pz_step_summary* out) override {
+    ResamplePlan pl;
+    if (!build_plan(lw.data(), n, n, &pl)) return PZ_EDEGENERATE;
+    if (desc.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
+      multinomial_ancestors(pl, seed, t, n, anc.data());
+    } else {
+      uint32_t U = resample_uniform(seed, t);
+      systematic_ancestors(pl, U, n, anc.data());
+    }
+    T y[PZ_MAX_NY];
+    for (int k = 0; k < p.ny; ++k) y[k] = (T)obs[k];
+    std::vector<T> xn((size_t)p.nx * n);
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < n; ++j) {
+      T xp[PZ_MAX_NX], z[PZ_MAX_NX + 2], xo[PZ_MAX_NX];
+      float zf[PZ_MAX_NX + 2];
+      int64_t a = anc[j];
+      for (int d = 0; d < p.nx; ++d) xp[d] = x[(size_t)d * n + a];
+      lg_noise(p.nx, (uint64_t)j, t, seed, zf);
+      for (int d = 0; d < p.nx; ++d) z[d] = (T)zf[d];   // a double filter uses the same fp32 table normals
+      lg_propagate(p, xp, z, xo);
+      for (int d = 0; d < p.nx; ++d) xn[(size_t)d * n + j] = xo[d];
+      lw[j] = lg_logweight(p, xo, y);
+    }
+    x.swap(xn);
+    ResamplePlan pl2;
+    bool ok = build_plan(lw.data(), n, n, &pl2);
+    if (out) {
+      memset(out, 0, sizeof(*out));
+      out->step = t;
+      if (ok) {
+        summarise(pl2, out);
+        for (int d = 0; d < p.nx; ++d) center[d] = out->mean[d];
+      }
+    }
+    t += 1;
+    return ok ? 0 : PZ_EDEGENERATE;
+  }
+  void state32(float* xo, float* lwo, int32_t* ao) override {
+    if (xo) for (size_t i = 0; i < x.size(); ++i) xo[i] = (float)x[i];
+    if (lwo) for (size_t i = 0; i < lw.size(); ++i) lwo[i] = (float)lw[i];
+    if (ao) memcpy(ao, anc.data(), anc.size() * sizeof(int32_t));
+  }
+  void state64(double* xo, double* lwo, int32_t* ao) override {
+    if (xo) for (size_t i = 0; i < x.size(); ++i) xo[i] = (double)x[i];
+    if (lwo) for (size_t i = 0; i < lw.size(); ++i) lwo[i] = (double)lw[i];
+    if (ao) memcpy(ao, anc.data(), anc.size() * sizeof(int32_t));
+  }
+  int block_stats(int32_t* eb, uint64_t* sb, int32_t* emax, uint64_t* total) override {
+    ResamplePlan pl;
+    bool ok = build_plan(lw.data(), n, n, &pl);
+    if (eb) memcpy(eb, pl.eb.data(), pl.nblk * sizeof(int32_t));
+    if (sb) for (int64_t b = 0; b < pl.nblk; ++b) sb[b] = pl.sb[b];
+    if (emax) *emax = pl.emax;
+    if (total) *total = pl.total;
+    return ok ? 0 : PZ_EDEGENERATE;
+  }
+  void derived(float* F, float* Lq, float* H, float* Rinv, float* wscale, double* ll_const) override {
+    for (int i = 0; i < PZ_MAX_NX; ++i) for (int j = 0; j < PZ_MAX_NX; ++j) { F[i * PZ_MAX_NX + j] = (float)p.F[i][j]; Lq[i * PZ_MAX_NX + j] = (float)p.Lq[i][j]; }
+    for (int i = 0; i < PZ_MAX_NY; ++i) for (int j = 0; j < PZ_MAX_NX; ++j) H[i * PZ_MAX_NX + j] = (float)p.H[i][j];
+    for (int i = 0; i < PZ_MAX_NY; ++i) for (int j = 0; j < PZ_MAX_NY; ++j) Rinv[i * PZ_MAX_NY + j] = (float)p.Rinv[i][j];
+    *wscale = (float)p.wscale; *ll_const = p.ll_const;
+  }
 };
 
-void summarise(const OFilter& f, const ResamplePlan& pl, pz_step_summary* s, const double* center) {
-  // the same fp32 weights the resampler quantises, at scale 2^emax, in double
-  double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
-  for (int64_t i = 0; i < f.n; ++i) {
-    const int32_t eb = pl.eb[i / kBlk];
-    if (eb == kNZero) continue;
-    double w = ldexp((double)pl.w[i], eb - pl.emax);
-    sw += w; sw2 += w * w;
-    for (int d = 0; d < f.p.nx; ++d) {
-      double dx = (double)(f.x[(size_t)d * f.n + i] - (float)center[d]);
-      sx[d] += w * dx; sxx[d] += w * dx * dx;
-    }
+template <class T>
+OFilterBase* make_filter(const pz_model_desc* d, int64_t n, uint64_t seed) {
+  OFilterT<T>* f = new OFilterT<T>();
+  f->desc = *d;
+  if (!derive_lg(d, &f->p) || n < 1) { delete f; return nullptr; }
+  f->n = n; f->seed = seed; f->t = 0;
+  f->x.assign((size_t)f->p.nx * n, (T)0);
+  for (int k = 0; k < f->p.nx; ++k) {
+    for (int64_t i = 0; i < n; ++i) f->x[(size_t)k * n + i] = f->p.x0[k];
+    f->center[k] = d->x0[k];
   }
-  s->ess = sw * sw / sw2;
-  for (int d = 0; d < f.p.nx; ++d) {
-    double m = sx[d] / sw;
-    s->mean[d] = (double)(float)center[d] + m;
-    s->var[d] = sxx[d] / sw - m * m;
-  }
-  s->log_evidence_inc = log(sw) + pl.emax * M_LN2 - log((double)f.n) + f.p.ll_const;
-  s->e_max = pl.emax;
-  s->total_weight = pl.total;
-  s->n_migrated = 0;
+  f->lw.assign(n, (T)0);  // equal weights before the first observation
+  f->anc.assign(n, 0);
+  return f;
 }
 
 }  // namespace
@@ -469,11 +588,7 @@ void pzo_icdf_normals(const uint32_t* r, int64_t n, float* z) {
   for (int64_t i = 0; i < n; ++i) z[i] = icdf_normal(r[i]);
 }
 
-uint32_t pzo_resample_uniform(uint64_t seed, uint32_t t) {
-  uint32_t r[4];
-  philox(0, 0, t, kStreamResample, seed, r);
-  return r[0];
-}
+uint32_t pzo_resample_uniform(uint64_t seed, uint32_t t) { return resample_uniform(seed, t); }
 
 // canonical systematic ancestors from fp32 log-weights; optional diagnostics
 int pzo_resample_systematic(const float* lw, int64_t n, uint32_t U, int32_t* anc, int32_t* eb_out,
@@ -513,90 +628,23 @@ void pzo_resample_systematic_f64(const double* logw, int64_t n, double u, int32_
 }
 
 void* pzo_filter_create(const pz_model_desc* d, int64_t n, uint64_t seed) {
-  OFilter* f = new OFilter();
-  f->desc = *d;
-  if (!derive_lg(d, &f->p) || n < 1) { delete f; return nullptr; }
-  f->n = n; f->seed = seed; f->t = 0;
-  f->x.assign((size_t)f->p.nx * n, 0.0f);
-  for (int k = 0; k < f->p.nx; ++k) {
-    for (int64_t i = 0; i < n; ++i) f->x[(size_t)k * n + i] = f->p.x0[k];
-    f->center[k] = d->x0[k];
-  }
-  f->lw.assign(n, 0.0f);  // equal weights before the first observation
-  f->anc.assign(n, 0);
-  return f;
+  return d->state_f64 ? make_filter<double>(d, n, seed) : make_filter<float>(d, n, seed);
 }
 
-void pzo_filter_destroy(void* h) { delete (OFilter*)h; }
+void pzo_filter_destroy(void* h) { delete (OFilterBase*)h; }
 
 void pzo_filter_derived(void* h, float* F, float* Lq, float* H, float* Rinv, float* wscale, double* ll_const) {
-  OFilter* f = (OFilter*)h;
-  memcpy(F, f->p.F, sizeof(f->p.F)); memcpy(Lq, f->p.Lq, sizeof(f->p.Lq));
-  memcpy(H, f->p.H, sizeof(f->p.H)); memcpy(Rinv, f->p.Rinv, sizeof(f->p.Rinv));
-  *wscale = f->p.wscale; *ll_const = f->p.ll_const;
+  ((OFilterBase*)h)->derived(F, Lq, H, Rinv, wscale, ll_const);
 }
 
-// One step of zparticles' (Inference.hs:101-104) in the cross-step order of the CUDA path:
-// resample the pending population by its weights, propagate every child, weight it by the
-// new observation.  (The reference weights first and resamples at the end of the same step;
-// the populations and weights visited are identical, only the step boundary moves.)
-int pzo_filter_step(void* h, const double* obs, pz_step_summary* out) {
-  OFilter* f = (OFilter*)h;
-  const LgParams& p = f->p;
-  int64_t n = f->n;
-  ResamplePlan pl;
-  if (!build_plan(f->lw.data(), n, n, &pl)) return PZ_EDEGENERATE;
-  if (f->desc.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
-    multinomial_ancestors(pl, f->seed, f->t, n, f->anc.data());
-  } else {
-    uint32_t U = pzo_resample_uniform(f->seed, f->t);
-    systematic_ancestors(pl, U, n, f->anc.data());
-  }
-  float y[PZ_MAX_NY];
-  for (int k = 0; k < p.ny; ++k) y[k] = (float)obs[k];
-  std::vector<float> xn((size_t)p.nx * n);
-#pragma omp parallel for schedule(static)
-  for (int64_t j = 0; j < n; ++j) {
-    float xp[PZ_MAX_NX], z[PZ_MAX_NX + 2], xo[PZ_MAX_NX];
-    int64_t a = f->anc[j];
-    for (int d = 0; d < p.nx; ++d) xp[d] = f->x[(size_t)d * n + a];
-    lg_noise(p.nx, (uint64_t)j, f->t, f->seed, z);
-    lg_propagate(p, xp, z, xo);
-    for (int d = 0; d < p.nx; ++d) xn[(size_t)d * n + j] = xo[d];
-    f->lw[j] = lg_logweight(p, xo, y);
-  }
-  f->x.swap(xn);
-  ResamplePlan pl2;
-  bool ok = build_plan(f->lw.data(), n, n, &pl2);
-  if (out) {
-    memset(out, 0, sizeof(*out));
-    out->step = f->t;
-    if (ok) {
-      summarise(*f, pl2, out, f->center);
-      for (int d = 0; d < p.nx; ++d) f->center[d] = out->mean[d];
-    }
-  }
-  f->t += 1;
-  return ok ? 0 : PZ_EDEGENERATE;
-}
+int pzo_filter_step(void* h, const double* obs, pz_step_summary* out) { return ((OFilterBase*)h)->step(obs, out); }
 
-void pzo_filter_state(void* h, float* x, float* lw, int32_t* anc) {
-  OFilter* f = (OFilter*)h;
-  if (x) memcpy(x, f->x.data(), f->x.size() * sizeof(float));
-  if (lw) memcpy(lw, f->lw.data(), f->lw.size() * sizeof(float));
-  if (anc) memcpy(anc, f->anc.data(), f->anc.size() * sizeof(int32_t));
-}
+void pzo_filter_state(void* h, float* x, float* lw, int32_t* anc) { ((OFilterBase*)h)->state32(x, lw, anc); }
+void pzo_filter_state_f64(void* h, double* x, double* lw, int32_t* anc) { ((OFilterBase*)h)->state64(x, lw, anc); }
 
 // block statistics of the pending population (parity tap for the fused kernel's metadata)
 int pzo_filter_block_stats(void* h, int32_t* eb, uint64_t* sb, int32_t* emax, uint64_t* total) {
-  OFilter* f = (OFilter*)h;
-  ResamplePlan pl;
-  bool ok = build_plan(f->lw.data(), f->n, f->n, &pl);
-  if (eb) memcpy(eb, pl.eb.data(), pl.nblk * sizeof(int32_t));
-  if (sb) for (int64_t b = 0; b < pl.nblk; ++b) sb[b] = pl.sb[b];
-  if (emax) *emax = pl.emax;
-  if (total) *total = pl.total;
-  return ok ? 0 : PZ_EDEGENERATE;
+  return ((OFilterBase*)h)->block_stats(eb, sb, emax, total);
 }
 
 // ---------------------------------------------------------------------------------------

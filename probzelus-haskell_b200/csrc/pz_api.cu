@@ -45,13 +45,46 @@ int fail(int code, const char* fmt, ...) {
 
 int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
-// Derived fp32 model parameters: Cholesky of Q, inverse and log-determinant of R in double,
-// rounded once to fp32 (DESIGN.md "Model descriptor").
-int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
+// Position/velocity ("Kronecker") structure of a derived parameter set: F = [[a,b],[c,d]] (x) I_p,
+// Q = diag(qp I, qv I), H = [I_p 0], R = r I_p; and the scalar random walk with unit F and H (multiplying by
+// exactly 1 is exact, so the specialised path skips it).
+template <class T>
+void detect_structure(LgDevT<T>* p) {
+  const int nx = p->nx, ny = p->ny;
+  p->kron = 0;
+  if (getenv("PZ_NO_KRON")) return;
+  if (nx == 1 && ny == 1 && p->F[0][0] == (T)1 && p->H[0][0] == (T)1) {
+    p->kron = 1; p->klp = p->Lq[0][0]; p->krinv = p->Rinv[0][0];
+  }
+  if (nx % 2 == 0 && ny == nx / 2) {
+    const int P = nx / 2;
+    bool ok = true;
+    const T a = p->F[0][0], b = p->F[0][P], c = p->F[P][0], dd = p->F[P][P];
+    const T lp = p->Lq[0][0], lv = p->Lq[P][P], ri = p->Rinv[0][0];
+    for (int i = 0; i < nx && ok; ++i)
+      for (int j = 0; j < nx; ++j) {
+        const int bi = i / P, bj = j / P;
+        const T fexp = (i % P == j % P) ? (bi == 0 ? (bj == 0 ? a : b) : (bj == 0 ? c : dd)) : (T)0;
+        const T lexp = (i == j) ? (bi == 0 ? lp : lv) : (T)0;
+        if (p->F[i][j] != fexp || p->Lq[i][j] != lexp) { ok = false; break; }
+      }
+    for (int i = 0; i < ny && ok; ++i) {
+      for (int j = 0; j < nx; ++j) if (p->H[i][j] != ((i == j) ? (T)1 : (T)0)) ok = false;
+      for (int j = 0; j < ny; ++j) if (p->Rinv[i][j] != ((i == j) ? ri : (T)0)) ok = false;
+    }
+    if (ok) { p->kron = 1; p->ka = a; p->kb = b; p->kc = c; p->kd = dd; p->klp = lp; p->klv = lv; p->krinv = ri; }
+  }
+}
+
+// Derived model parameters: Cholesky of Q, inverse and log-determinant of R in double; the fp32 set is
+// rounded once (DESIGN.md "Model descriptor"), the f64 set is kept as computed.
+int derive_lg(const pz_model_desc* d, LgDev* p, LgDevD* pd, double* ll_const) {
   const int nx = d->nx, ny = d->ny;
   if (nx < 1 || nx > PZ_MAX_NX || ny < 1 || ny > PZ_MAX_NY) return fail(PZ_EINVAL, "unsupported dims nx=%d ny=%d", nx, ny);
   memset(p, 0, sizeof(*p));
+  memset(pd, 0, sizeof(*pd));
   p->nx = nx; p->ny = ny;
+  pd->nx = nx; pd->ny = ny;
   double L[PZ_MAX_NX][PZ_MAX_NX] = {};
   for (int j = 0; j < nx; ++j) {
     double s = d->Q[j * nx + j];
@@ -83,39 +116,22 @@ int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
     }
   }
   for (int i = 0; i < nx; ++i) {
-    for (int j = 0; j < nx; ++j) { p->F[i][j] = (float)d->F[i * nx + j]; p->Lq[i][j] = (float)L[i][j]; }
+    for (int j = 0; j < nx; ++j) {
+      p->F[i][j] = (float)d->F[i * nx + j]; p->Lq[i][j] = (float)L[i][j];
+      pd->F[i][j] = d->F[i * nx + j]; pd->Lq[i][j] = L[i][j];
+    }
     p->x0[i] = (float)d->x0[i];
+    pd->x0[i] = d->x0[i];
   }
   for (int i = 0; i < ny; ++i) {
-    for (int j = 0; j < nx; ++j) p->H[i][j] = (float)d->H[i * nx + j];
-    for (int j = 0; j < ny; ++j) p->Rinv[i][j] = (float)A[i][ny + j];
+    for (int j = 0; j < nx; ++j) { p->H[i][j] = (float)d->H[i * nx + j]; pd->H[i][j] = d->H[i * nx + j]; }
+    for (int j = 0; j < ny; ++j) { p->Rinv[i][j] = (float)A[i][ny + j]; pd->Rinv[i][j] = A[i][ny + j]; }
   }
   const bool dbl = (ny == 1 && d->scalar_ll_2x);
   p->wscale = dbl ? -1.0f : -0.5f;
-  // position/velocity structure: F = [[a,b],[c,d]] (x) I_p, Q = diag(qp I, qv I), H = [I_p 0], R = r I_p
-  p->kron = 0;
-  // scalar random walk with unit F and H: multiplying by exactly 1 is exact, so the specialised path skips it
-  if (nx == 1 && ny == 1 && p->F[0][0] == 1.0f && p->H[0][0] == 1.0f && !getenv("PZ_NO_KRON")) {
-    p->kron = 1; p->klp = p->Lq[0][0]; p->krinv = p->Rinv[0][0];
-  }
-  if (nx % 2 == 0 && ny == nx / 2 && !getenv("PZ_NO_KRON")) {
-    const int P = nx / 2;
-    bool ok = true;
-    const float a = p->F[0][0], b = p->F[0][P], c = p->F[P][0], dd = p->F[P][P];
-    const float lp = p->Lq[0][0], lv = p->Lq[P][P], ri = p->Rinv[0][0];
-    for (int i = 0; i < nx && ok; ++i)
-      for (int j = 0; j < nx; ++j) {
-        const int bi = i / P, bj = j / P;
-        const float fexp = (i % P == j % P) ? (bi == 0 ? (bj == 0 ? a : b) : (bj == 0 ? c : dd)) : 0.0f;
-        const float lexp = (i == j) ? (bi == 0 ? lp : lv) : 0.0f;
-        if (p->F[i][j] != fexp || p->Lq[i][j] != lexp) { ok = false; break; }
-      }
-    for (int i = 0; i < ny && ok; ++i) {
-      for (int j = 0; j < nx; ++j) if (p->H[i][j] != ((i == j) ? 1.0f : 0.0f)) ok = false;
-      for (int j = 0; j < ny; ++j) if (p->Rinv[i][j] != ((i == j) ? ri : 0.0f)) ok = false;
-    }
-    if (ok) { p->kron = 1; p->ka = a; p->kb = b; p->kc = c; p->kd = dd; p->klp = lp; p->klv = lv; p->krinv = ri; }
-  }
+  pd->wscale = dbl ? -1.0 : -0.5;
+  detect_structure(p);
+  detect_structure(pd);
   *ll_const = (dbl ? -1.0 : -0.5) * (logdet + ny * log(2 * M_PI));
   return PZ_OK;
 }
@@ -123,6 +139,9 @@ int derive_lg(const pz_model_desc* d, LgDev* p, double* ll_const) {
 // scratch of the generic (stored log-weight) path
 struct GenericScratch {
   float* lw = nullptr;
+  double* lw64 = nullptr;       // f64 filters: exact log-weight tap
+  double* thin = nullptr;       // read_particles scratch (grown on demand)
+  int64_t thin_cap = 0;
   uint16_t* q16 = nullptr;
   uint64_t* xb = nullptr;
   int32_t* anc = nullptr;
@@ -136,21 +155,21 @@ struct GenericScratch {
   CtlDev* ctl = nullptr;
   int64_t cap = 0;  // particles
   void release() {
-    cudaFree(lw); cudaFree(q16); cudaFree(xb); cudaFree(anc); cudaFree(eb); cudaFree(sb); cudaFree(pb); cudaFree(tile_start);
+    cudaFree(lw); cudaFree(lw64); cudaFree(thin); cudaFree(q16); cudaFree(xb); cudaFree(anc); cudaFree(eb); cudaFree(sb); cudaFree(pb); cudaFree(tile_start);
     cudaFree(scan_status); cudaFree(scan_part); cudaFree(plan); cudaFree(ctl);
     *this = GenericScratch();
   }
 };
 
-int generic_alloc(GenericScratch* g, int64_t n, bool full) {
+int generic_alloc(GenericScratch* g, int64_t n, bool full, cudaStream_t st) {
   if (g->cap >= n && (!full || g->eb)) return PZ_OK;
   g->release();
   const int64_t ld = round_up(n, kPad), nblk = (n + kBlk - 1) / kBlk;
   const int64_t nscan = (nblk + kScanTile - 1) / kScanTile, ntiles = (n + kGenericTileOut - 1) / kGenericTileOut;
   PZ_CUDA(cudaMalloc(&g->lw, ld * sizeof(float)));
-  PZ_CUDA(cudaMemset(g->lw, 0, ld * sizeof(float)));
+  PZ_CUDA(cudaMemsetAsync(g->lw, 0, ld * sizeof(float), st));
   PZ_CUDA(cudaMalloc(&g->q16, ld * sizeof(uint16_t)));
-  PZ_CUDA(cudaMemset(g->q16, 0, ld * sizeof(uint16_t)));
+  PZ_CUDA(cudaMemsetAsync(g->q16, 0, ld * sizeof(uint16_t), st));
   PZ_CUDA(cudaMalloc(&g->xb, (nblk + 2) * sizeof(uint64_t)));
   PZ_CUDA(cudaMalloc(&g->anc, ld * sizeof(int32_t)));
   PZ_CUDA(cudaMalloc(&g->tile_start, (ntiles + 1) * sizeof(int32_t)));
@@ -159,11 +178,12 @@ int generic_alloc(GenericScratch* g, int64_t n, bool full) {
     PZ_CUDA(cudaMalloc(&g->sb, (nblk + 1) * sizeof(uint64_t)));
     PZ_CUDA(cudaMalloc(&g->pb, (nblk + 2) * sizeof(uint64_t)));
     PZ_CUDA(cudaMalloc(&g->scan_status, (nscan + 1) * sizeof(uint64_t)));
-    PZ_CUDA(cudaMemset(g->scan_status, 0, (nscan + 1) * sizeof(uint64_t)));
+    PZ_CUDA(cudaMemsetAsync(g->scan_status, 0, (nscan + 1) * sizeof(uint64_t), st));
     PZ_CUDA(cudaMalloc(&g->scan_part, (nscan + 1) * kMaxRec * sizeof(double)));
     PZ_CUDA(cudaMalloc(&g->plan, sizeof(PlanDev)));
-    PZ_CUDA(cudaMemset(g->plan, 0, sizeof(PlanDev)));
+    PZ_CUDA(cudaMemsetAsync(g->plan, 0, sizeof(PlanDev), st));
     PZ_CUDA(cudaMalloc(&g->ctl, sizeof(CtlDev)));
+    PZ_CUDA(cudaMemsetAsync(g->ctl, 0, sizeof(CtlDev), st));
   }
   g->cap = n;
   return PZ_OK;
@@ -297,7 +317,9 @@ struct pz_filter {
   // sharded filter (one process per GPU)
   ncclComm_t comm = nullptr;
   int64_t hb = 0;                    // halo capacity in blocks on each side
-  float* xbuf[2] = {nullptr, nullptr};
+  void* xbuf[2] = {nullptr, nullptr};   // float or double [nx][ld]
+  double* d_obs64 = nullptr;
+  double* h_obs64 = nullptr;            // pinned [kObsRing][PZ_MAX_NY]
   uint16_t* qbuf[2] = {nullptr, nullptr};
   int32_t* ebbuf[2] = {nullptr, nullptr};
   uint64_t* pbxbuf = nullptr;
@@ -309,6 +331,7 @@ struct pz_filter {
   // delayed-sampling linear-Gaussian filter
   bool is_rb = false;
   RbDev* rb = nullptr;
+  bool is_gen = false;               // generic-path filter (stored log-weights): carried weights, adaptive resampling, Walker
   // multi-target tracker
   bool is_mtt = false;
   uint32_t* mtt_s[2] = {nullptr, nullptr};   // particle records, double-buffered
@@ -409,7 +432,7 @@ void free_filter(pz_filter* f) {
   StepArgs& a = f->a;
   cudaFree(f->xbuf[0]); cudaFree(f->xbuf[1]); cudaFree(f->qbuf[0]); cudaFree(f->qbuf[1]); cudaFree(f->xbbuf); cudaFree(f->ebbuf[0]); cudaFree(f->ebbuf[1]); cudaFree(a.sb); cudaFree(a.pb);
   cudaFree(f->pbxbuf); cudaFree(a.tile_start); cudaFree(a.rec); cudaFree(a.scan_status); cudaFree(a.scan_part);
-  cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(a.summ); cudaFree(a.shard_rec);
+  cudaFree(a.plan); cudaFree(a.ctl); cudaFree(f->d_obs); cudaFree(f->d_obs64); cudaFree(a.summ); cudaFree(a.shard_rec);
   cudaFree(f->rb);
   cudaFree(f->warm);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -418,6 +441,7 @@ void free_filter(pz_filter* f) {
   if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
   f->g.release();
   if (f->h_obs) cudaFreeHost(f->h_obs);
+  if (f->h_obs64) cudaFreeHost(f->h_obs64);
   if (f->h_summ) cudaFreeHost(f->h_summ);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
@@ -430,12 +454,23 @@ void free_filter(pz_filter* f) {
 
 int stage_obs(pz_filter* f, const double* obs, int64_t k, int32_t obs_dim) {
   // rows for steps [t, t+k) -> ring rows (t+i) % kObsRing
+  const int64_t r0 = f->t % kObsRing;
+  const int64_t first = (r0 + k <= kObsRing) ? k : kObsRing - r0;
+  if (f->a.f64) {  // a double filter reads the observations unrounded
+    for (int64_t i = 0; i < k; ++i) {
+      double* row = f->h_obs64 + ((f->t + i) % kObsRing) * PZ_MAX_NY;
+      for (int c = 0; c < PZ_MAX_NY; ++c) row[c] = c < obs_dim ? obs[i * obs_dim + c] : 0.0;
+    }
+    const size_t rowb = PZ_MAX_NY * sizeof(double);
+    PZ_CUDA(cudaMemcpyAsync(f->d_obs64 + r0 * PZ_MAX_NY, f->h_obs64 + r0 * PZ_MAX_NY, first * rowb, cudaMemcpyHostToDevice, f->stream));
+    if (first < k)
+      PZ_CUDA(cudaMemcpyAsync(f->d_obs64, f->h_obs64, (k - first) * rowb, cudaMemcpyHostToDevice, f->stream));
+    return PZ_OK;
+  }
   for (int64_t i = 0; i < k; ++i) {
     float* row = f->h_obs + ((f->t + i) % kObsRing) * PZ_MAX_NY;
     for (int c = 0; c < PZ_MAX_NY; ++c) row[c] = c < obs_dim ? (float)obs[i * obs_dim + c] : 0.0f;
   }
-  const int64_t r0 = f->t % kObsRing;
-  const int64_t first = (r0 + k <= kObsRing) ? k : kObsRing - r0;
   const size_t rowb = PZ_MAX_NY * sizeof(float);
   PZ_CUDA(cudaMemcpyAsync(f->d_obs + r0 * PZ_MAX_NY, f->h_obs + r0 * PZ_MAX_NY, first * rowb, cudaMemcpyHostToDevice, f->stream));
   if (first < k)
@@ -456,7 +491,7 @@ int fetch_summaries(pz_filter* f, uint32_t t0, int64_t k) {
 int pending_ancestors(pz_filter* f, int* launches) {
   StepArgs& a = f->a;
   if (a.world > 1) return fail(PZ_ESTATE, "ancestor / particle taps are not available on a sharded filter");
-  int rc = generic_alloc(&f->g, a.n_local, false);
+  int rc = generic_alloc(&f->g, a.n_local, false, f->stream);
   if (rc) return rc;
   int n = 0;
   GenericArgs g{};
@@ -508,7 +543,7 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
     *launches += launch_plan_sharded(a, delta, s);
     if (tm) cudaEventRecord(f->tev[3], s);
     PZ_CUDA(cudaStreamWaitEvent(s, f->ev_join, 0));  // join (pf_partition advances ctl->t, which pf_halo_push reads)
-    *launches += launch_partition_ext(a, fused_tile_out(a.model.nx), delta, s);
+    *launches += launch_partition_ext(a, fused_tile_out(a.model.nx, a.f64), delta, s);
     if (tm) { cudaEventRecord(f->tev[4], s); f->tpending = true; }
     PZ_CUDA(cudaGetLastError());
     return PZ_OK;
@@ -517,15 +552,16 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
   *launches += launch_scan_only(a, delta, s);
   PZ_NCCL(g_nccl.AllGather(a.shard_rec + (size_t)me * kShardRec, a.shard_rec, kShardRec, ncclUint64, f->comm, s));
   *launches += launch_plan_sharded(a, delta, s);
-  float* x = a.X[which];
+  char* x = reinterpret_cast<char*>(a.X[which]);
+  const size_t es = a.f64 ? 8 : 4;
   uint16_t* q = a.Q[which];
   int32_t* eb = a.eb[which];
   uint64_t* pbx = const_cast<uint64_t*>(a.pbx);
   PZ_NCCL(g_nccl.GroupStart());
   if (me > 0) {  // my first m blocks -> the right halo of rank me-1; its last m blocks -> my left halo
     for (int d = 0; d < a.model.nx; ++d) {
-      PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld, m * kBlk, ncclFloat32, me - 1, f->comm, s));
-      PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld - m * kBlk, m * kBlk, ncclFloat32, me - 1, f->comm, s));
+      PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld * es, m * kBlk * es, ncclUint8, me - 1, f->comm, s));
+      PZ_NCCL(g_nccl.Recv(x + ((size_t)d * a.ld - m * kBlk) * es, m * kBlk * es, ncclUint8, me - 1, f->comm, s));
     }
     PZ_NCCL(g_nccl.Send(q, m * kBlk * 2, ncclUint8, me - 1, f->comm, s));
     PZ_NCCL(g_nccl.Recv(q - m * kBlk, m * kBlk * 2, ncclUint8, me - 1, f->comm, s));
@@ -536,8 +572,8 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
   }
   if (me + 1 < R) {
     for (int d = 0; d < a.model.nx; ++d) {
-      PZ_NCCL(g_nccl.Send(x + (size_t)d * a.ld + (nb - m) * kBlk, m * kBlk, ncclFloat32, me + 1, f->comm, s));
-      PZ_NCCL(g_nccl.Recv(x + (size_t)d * a.ld + nb * kBlk, m * kBlk, ncclFloat32, me + 1, f->comm, s));
+      PZ_NCCL(g_nccl.Send(x + ((size_t)d * a.ld + (nb - m) * kBlk) * es, m * kBlk * es, ncclUint8, me + 1, f->comm, s));
+      PZ_NCCL(g_nccl.Recv(x + ((size_t)d * a.ld + nb * kBlk) * es, m * kBlk * es, ncclUint8, me + 1, f->comm, s));
     }
     PZ_NCCL(g_nccl.Send(q + (nb - m) * kBlk, m * kBlk * 2, ncclUint8, me + 1, f->comm, s));
     PZ_NCCL(g_nccl.Recv(q + nb * kBlk, m * kBlk * 2, ncclUint8, me + 1, f->comm, s));
@@ -547,7 +583,7 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
     PZ_NCCL(g_nccl.Recv(pbx + nb + 1, m, ncclUint64, me + 1, f->comm, s));
   }
   PZ_NCCL(g_nccl.GroupEnd());
-  *launches += launch_partition_ext(a, fused_tile_out(a.model.nx), delta, s);
+  *launches += launch_partition_ext(a, fused_tile_out(a.model.nx, a.f64), delta, s);
   PZ_CUDA(cudaGetLastError());
   return PZ_OK;
 }
@@ -635,7 +671,7 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
   PZ_TRY(cudaEventCreate(&f->ev1));
-  for (int i = 0; i < 2; ++i) { PZ_TRY(cudaMalloc(&f->mtt_s[i], sbytes)); PZ_TRY(cudaMemset(f->mtt_s[i], 0, sbytes)); }
+  for (int i = 0; i < 2; ++i) { PZ_TRY(cudaMalloc(&f->mtt_s[i], sbytes)); PZ_TRY(cudaMemsetAsync(f->mtt_s[i], 0, sbytes, f->stream)); }
   PZ_TRY(cudaMalloc(&f->ebbuf[0], (a.nblk + 8) * sizeof(int32_t)));
   a.eb[0] = a.eb[1] = f->ebbuf[0];
   PZ_TRY(cudaMalloc(&a.sb, (a.nblk + 8) * sizeof(uint64_t)));
@@ -645,21 +681,22 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   a.xb = f->xbbuf;
   PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
   PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
-  PZ_TRY(cudaMemset(a.scan_status, 0, (a.nscan + 1) * sizeof(uint64_t)));
+  PZ_TRY(cudaMemsetAsync(a.scan_status, 0, (a.nscan + 1) * sizeof(uint64_t), f->stream));
   PZ_TRY(cudaMalloc(&a.scan_part, (size_t)(a.nscan + 1) * kMaxRec * sizeof(double)));
   PZ_TRY(cudaMalloc(&a.plan, sizeof(PlanDev)));
-  PZ_TRY(cudaMemset(a.plan, 0, sizeof(PlanDev)));
+  PZ_TRY(cudaMemsetAsync(a.plan, 0, sizeof(PlanDev), f->stream));
   PZ_TRY(cudaMalloc(&a.ctl, sizeof(CtlDev)));
+  PZ_TRY(cudaMemsetAsync(a.ctl, 0, sizeof(CtlDev), f->stream));
   PZ_TRY(cudaMalloc(&a.summ, (size_t)kObsRing * sizeof(pz_step_summary)));
-  PZ_TRY(cudaMemset(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMemsetAsync(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary), f->stream));
   PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
   PZ_TRY(cudaMalloc(&f->mtt_obs, 64 * sizeof(float)));
   PZ_TRY(cudaMallocHost(&f->h_mtt_obs, 64 * sizeof(float)));
   PZ_TRY(cudaMalloc(&f->mtt_overflow, sizeof(unsigned long long)));
-  PZ_TRY(cudaMemset(f->mtt_overflow, 0, sizeof(unsigned long long)));
+  PZ_TRY(cudaMemsetAsync(f->mtt_overflow, 0, sizeof(unsigned long long), f->stream));
   PZ_TRY(cudaMalloc(&f->mtt_part, (size_t)mtt_step_ctas(a.n_local) * 5 * sizeof(double)));
   {
-    int rc = generic_alloc(&f->g, a.n_local, false);  // stored log-weights (all 0: equal weights) + ancestors
+    int rc = generic_alloc(&f->g, a.n_local, false, f->stream);  // stored log-weights (all 0: equal weights) + ancestors
     if (rc) { free_filter(f); return rc; }
   }
   launch_ctl_reset(a.ctl, f->stream);
@@ -746,7 +783,7 @@ int setup_p2p(pz_filter* f) {
     for (int i = 1; i < 8 && ok; ++i) { p[i] = open(all[q].h[i]); ok = p[i] != nullptr; }
     if (!ok) break;
     for (int b = 0; b < 2; ++b) {
-      h.Xn[side][b] = (float*)p[1 + b] + H;
+      h.Xn[side][b] = (char*)p[1 + b] + (size_t)H * (a.f64 ? 8 : 4);
       h.Qn[side][b] = (uint16_t*)p[3 + b] + H;
       h.ebn[side][b] = (int32_t*)p[5 + b] + f->hb;
     }
@@ -857,8 +894,16 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   f->device = device;
   StepArgs& a = f->a;
   memset(&a, 0, sizeof(a));
-  int rc = derive_lg(model, &a.model, &a.ll_const);
+  int rc = derive_lg(model, &a.model, &a.modeld, &a.ll_const);
   if (rc) { delete f; return rc; }
+  a.f64 = model->state_f64 ? 1 : 0;
+  {
+    // peer-memory polls give up after PZ_P2P_TIMEOUT_S seconds (default 120; 0 = never): the hosts of the ranks
+    // drive their steps independently and may be skewed by seconds
+    double secs = 120.0;
+    if (const char* e = getenv("PZ_P2P_TIMEOUT_S")) secs = atof(e);
+    a.wait_ticks = secs > 0 ? (unsigned long long)(secs * 1.9e9) : 0ull;
+  }
   a.n_global = (int64_t)n_global;
   a.n_local = (int64_t)(n_global / (uint64_t)world);
   a.slot_base = (int64_t)rank * a.n_local;
@@ -868,7 +913,7 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   a.resampler = model->resampler;
   a.nblk = (a.n_local + kBlk - 1) / kBlk;
   a.nscan = (int32_t)((a.nblk + kScanTile - 1) / kScanTile);
-  const int to = fused_tile_out(model->nx);
+  const int to = fused_tile_out(model->nx, a.f64);
   a.ntiles_out = (int32_t)((a.n_local + to - 1) / to);
   if (world > 1) {
     // halo margin exchanged with each neighbour every step: nblk/32 clamped to [64, 2048] blocks
@@ -880,17 +925,19 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   }
   const int64_t H = f->hb * kBlk;
   a.ld = round_up(a.n_local, kPad) + 2 * H;
-  const size_t xbytes = (size_t)model->nx * a.ld * sizeof(float);
+  const size_t esz = a.f64 ? sizeof(double) : sizeof(float);
+  const size_t xbytes = (size_t)model->nx * a.ld * esz;
 #define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
   PZ_TRY(cudaEventCreate(&f->ev1));
   for (int i = 0; i < 2; ++i) {
+    // every initialising memset is ordered on the filter's own (non-blocking) stream, ahead of pf_init
     PZ_TRY(cudaMalloc(&f->xbuf[i], xbytes));
-    PZ_TRY(cudaMemset(f->xbuf[i], 0, xbytes));
-    a.X[i] = f->xbuf[i] + H;
+    PZ_TRY(cudaMemsetAsync(f->xbuf[i], 0, xbytes, f->stream));
+    a.X[i] = (char*)f->xbuf[i] + (size_t)H * esz;
     PZ_TRY(cudaMalloc(&f->qbuf[i], (size_t)a.ld * sizeof(uint16_t)));
-    PZ_TRY(cudaMemset(f->qbuf[i], 0, (size_t)a.ld * sizeof(uint16_t)));
+    PZ_TRY(cudaMemsetAsync(f->qbuf[i], 0, (size_t)a.ld * sizeof(uint16_t), f->stream));
     a.Q[i] = f->qbuf[i] + H;
     PZ_TRY(cudaMalloc(&f->ebbuf[i], (a.nblk + 2 * f->hb + 8) * sizeof(int32_t)));
     a.eb[i] = f->ebbuf[i] + f->hb;
@@ -912,16 +959,22 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
   PZ_TRY(cudaMalloc(&a.rec, (size_t)(a.ntiles_out + 1) * kMaxRec * sizeof(double)));
   PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
+  PZ_TRY(cudaMemsetAsync(a.scan_status, 0, (a.nscan + 1) * sizeof(uint64_t), f->stream));
   PZ_TRY(cudaMalloc(&a.scan_part, (size_t)(a.nscan + 1) * kMaxRec * sizeof(double)));
   PZ_TRY(cudaMalloc(&a.plan, sizeof(PlanDev)));
-  PZ_TRY(cudaMemset(a.plan, 0, sizeof(PlanDev)));
+  PZ_TRY(cudaMemsetAsync(a.plan, 0, sizeof(PlanDev), f->stream));
   PZ_TRY(cudaMalloc(&a.ctl, sizeof(CtlDev)));
+  PZ_TRY(cudaMemsetAsync(a.ctl, 0, sizeof(CtlDev), f->stream));
   PZ_TRY(cudaMalloc(&f->d_obs, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
-  PZ_TRY(cudaMemset(f->d_obs, 0, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
+  PZ_TRY(cudaMemsetAsync(f->d_obs, 0, (size_t)kObsRing * PZ_MAX_NY * sizeof(float), f->stream));
   a.obs = f->d_obs;
+  PZ_TRY(cudaMalloc(&f->d_obs64, (size_t)kObsRing * PZ_MAX_NY * sizeof(double)));
+  PZ_TRY(cudaMemsetAsync(f->d_obs64, 0, (size_t)kObsRing * PZ_MAX_NY * sizeof(double), f->stream));
+  a.obs64 = f->d_obs64;
   PZ_TRY(cudaMalloc(&a.summ, (size_t)kObsRing * sizeof(pz_step_summary)));
-  PZ_TRY(cudaMemset(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary)));
+  PZ_TRY(cudaMemsetAsync(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary), f->stream));
   PZ_TRY(cudaMallocHost(&f->h_obs, (size_t)kObsRing * PZ_MAX_NY * sizeof(float)));
+  PZ_TRY(cudaMallocHost(&f->h_obs64, (size_t)kObsRing * PZ_MAX_NY * sizeof(double)));
   PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
   launch_init(a, f->stream);
   if (world > 1) {
@@ -1215,19 +1268,34 @@ int pz_filter_last_timing(pz_filter* f, double* ms, int64_t* launches) {
   return PZ_OK;
 }
 
-int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len) {
-  if (!f || !out) return fail(PZ_EINVAL, "null argument");
+static int read_state_common(pz_filter* f, float* out32, double* out64, int64_t out_len) {
+  if (!f || (!out32 && !out64)) return fail(PZ_EINVAL, "null argument");
   const StepArgs& a = f->a;
   if (f->is_mtt) return fail(PZ_ESTATE, "tracker state is read with pz_filter_read_tracks");
   if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter holds no sampled state; use pz_filter_read_posterior");
-  if (out_len < a.model.nx * a.n_local) return fail(PZ_EINVAL, "buffer too small: need %lld floats", (long long)(a.model.nx * a.n_local));
+  if (f->is_gen) return fail(PZ_ESTATE, "this filter's state is read with pz_filter_read_particles");
+  if (out_len < a.model.nx * a.n_local) return fail(PZ_EINVAL, "buffer too small: need %lld scalars", (long long)(a.model.nx * a.n_local));
+  if (out32 && a.f64) return fail(PZ_ESTATE, "the filter stores its state in double (state_f64 = 1): use pz_filter_read_state_f64");
   PZ_CUDA(cudaSetDevice(f->device));
   PZ_CUDA(cudaStreamSynchronize(f->stream));
-  const float* x = a.X[f->t & 1];
+  const size_t es = a.f64 ? 8 : 4;
+  const char* x = reinterpret_cast<const char*>(a.X[f->t & 1]);
+  if (out64 && !a.f64) {  // widen on the host
+    std::vector<float> tmp((size_t)a.n_local);
+    for (int d = 0; d < a.model.nx; ++d) {
+      PZ_CUDA(cudaMemcpy(tmp.data(), x + (size_t)d * a.ld * es, a.n_local * es, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < a.n_local; ++i) out64[(size_t)d * a.n_local + i] = (double)tmp[i];
+    }
+    return PZ_OK;
+  }
+  char* out = out64 ? reinterpret_cast<char*>(out64) : reinterpret_cast<char*>(out32);
   for (int d = 0; d < a.model.nx; ++d)
-    PZ_CUDA(cudaMemcpy(out + (size_t)d * a.n_local, x + (size_t)d * a.ld, a.n_local * sizeof(float), cudaMemcpyDeviceToHost));
+    PZ_CUDA(cudaMemcpy(out + (size_t)d * a.n_local * es, x + (size_t)d * a.ld * es, a.n_local * es, cudaMemcpyDeviceToHost));
   return PZ_OK;
 }
+
+int pz_filter_read_state(pz_filter* f, float* out, int64_t out_len) { return read_state_common(f, out, nullptr, out_len); }
+int pz_filter_read_state_f64(pz_filter* f, double* out, int64_t out_len) { return read_state_common(f, nullptr, out, out_len); }
 
 int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out) {
   if (!f || !mean_out || !cov_out) return fail(PZ_EINVAL, "null argument");
@@ -1242,18 +1310,34 @@ int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out) {
   return PZ_OK;
 }
 
-int pz_filter_read_logw(pz_filter* f, float* out, int64_t n) {
-  if (!f || !out) return fail(PZ_EINVAL, "null argument");
+static int read_logw_common(pz_filter* f, float* out32, double* out64, int64_t n) {
+  if (!f || (!out32 && !out64)) return fail(PZ_EINVAL, "null argument");
   if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter has equal weights and no sampled state");
   if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
   PZ_CUDA(cudaSetDevice(f->device));
-  int rc = generic_alloc(&f->g, f->a.n_local, false);
+  int rc = generic_alloc(&f->g, f->a.n_local, false, f->stream);
   if (rc) return rc;
-  if (!f->is_mtt) launch_logw(f->a, f->g.lw, f->stream);
-  PZ_CUDA(cudaMemcpyAsync(out, f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  if (out64) {
+    if (!f->g.lw64) PZ_CUDA(cudaMalloc(&f->g.lw64, (size_t)round_up(f->a.n_local, kPad) * sizeof(double)));
+    if (f->is_mtt || f->is_gen) {  // stored fp32 log-weights: widen on the host
+      std::vector<float> tmp((size_t)f->a.n_local);
+      PZ_CUDA(cudaMemcpyAsync(tmp.data(), f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+      PZ_CUDA(cudaStreamSynchronize(f->stream));
+      for (int64_t i = 0; i < f->a.n_local; ++i) out64[i] = (double)tmp[i];
+      return PZ_OK;
+    }
+    launch_logw(f->a, nullptr, f->g.lw64, f->stream);
+    PZ_CUDA(cudaMemcpyAsync(out64, f->g.lw64, f->a.n_local * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  } else {
+    if (!f->is_mtt && !f->is_gen) launch_logw(f->a, f->g.lw, nullptr, f->stream);
+    PZ_CUDA(cudaMemcpyAsync(out32, f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  }
   PZ_CUDA(cudaStreamSynchronize(f->stream));
   return PZ_OK;
 }
+
+int pz_filter_read_logw(pz_filter* f, float* out, int64_t n) { return read_logw_common(f, out, nullptr, n); }
+int pz_filter_read_logw_f64(pz_filter* f, double* out, int64_t n) { return read_logw_common(f, nullptr, out, n); }
 
 int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n) {
   if (!f || !out) return fail(PZ_EINVAL, "null argument");
@@ -1284,15 +1368,15 @@ int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t 
   }
   int rc = pending_ancestors(f, nullptr);
   if (rc) return rc;
-  float* d_out = nullptr;
-  PZ_CUDA(cudaMalloc(&d_out, n_sel * a.model.nx * sizeof(float)));
-  launch_gather_thin(a, f->g.anc, stride, n_sel, d_out, f->stream);
-  std::vector<float> h((size_t)n_sel * a.model.nx);
-  cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(float), cudaMemcpyDeviceToHost, f->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
-  cudaFree(d_out);
-  if (e != cudaSuccess) return fail(PZ_ECUDA, "read_particles: %s", cudaGetErrorString(e));
-  for (size_t i = 0; i < h.size(); ++i) out[i] = (double)h[i];
+  // device scratch kept with the filter (the visualiser reads every step)
+  if (f->g.thin_cap < n_sel * a.model.nx) {
+    cudaFree(f->g.thin); f->g.thin = nullptr; f->g.thin_cap = 0;
+    PZ_CUDA(cudaMalloc(&f->g.thin, (size_t)n_sel * a.model.nx * sizeof(double)));
+    f->g.thin_cap = n_sel * a.model.nx;
+  }
+  launch_gather_thin(a, f->g.anc, stride, n_sel, f->g.thin, f->stream);
+  PZ_CUDA(cudaMemcpyAsync(out, f->g.thin, (size_t)n_sel * a.model.nx * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
   return PZ_OK;
 }
 
@@ -1341,7 +1425,7 @@ static int standalone(const double* logw, int64_t n, bool multinomial, uint32_t 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
   GenericScratch gs;
-  int rc = generic_alloc(&gs, n, true);
+  int rc = generic_alloc(&gs, n, true, nullptr);
   if (rc) { gs.release(); return rc; }
   std::vector<float> lw32((size_t)n);
   for (int64_t i = 0; i < n; ++i) lw32[i] = (float)logw[i];

@@ -24,6 +24,8 @@
 //       position of every block boundary.
 //
 // No tensor cores: the path is a streaming scan / gather; see DESIGN.md for the roofline.
+#include <atomic>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 
@@ -95,14 +97,17 @@ __device__ __forceinline__ void stamp(int i) {
 #else
 #define PZ_STAMP(cond, i) do { } while (0)
 #endif
-// poll *p until pred(value); gives up after ~2 s (a dead peer must not hang the device)
+// poll *p until pred(value); gives up after `limit` clock64 ticks (a dead peer must not hang the device for
+// ever; the host sets the limit -- PZ_P2P_TIMEOUT_S, default 120 s, 0 = never -- because the ranks' hosts
+// drive their steps independently and may be skewed by seconds: GC pauses, I/O, first-step graph upload).
 // ACQUIRE = false for self-validating words (the payload is in the polled word: nothing to order)
 template <bool ACQUIRE = true, class Pred>
-__device__ __forceinline__ unsigned long long wait_sys(const unsigned long long* p, Pred pred, uint32_t* err) {
+__device__ __forceinline__ unsigned long long wait_sys(const unsigned long long* p, Pred pred, uint32_t* err,
+                                                       unsigned long long limit) {
   const long long t0 = clock64();
   unsigned long long v = ld_sys(p);
   while (!pred(v)) {
-    if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+    if (limit && (unsigned long long)(clock64() - t0) > limit) { atomicExch(err, 1u); break; }
     __nanosleep(64);
     v = ld_sys(p);
   }
@@ -152,100 +157,132 @@ __device__ __forceinline__ long long mad_wide_s32(int32_t a, int32_t b, long lon
   asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ long long mad_wide_u32(uint32_t a, uint32_t b, long long c) {
+  long long d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// individually rounded IEEE operations in the filter's arithmetic type (float or double)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float r_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double r_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float r_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double r_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float r_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double r_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float r_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double r_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
+template <class T> __device__ __forceinline__ const LgDevT<T>& model_of(const StepArgs& a);
+template <> __device__ __forceinline__ const LgDevT<float>& model_of<float>(const StepArgs& a) { return a.model; }
+template <> __device__ __forceinline__ const LgDevT<double>& model_of<double>(const StepArgs& a) { return a.modeld; }
+// observation row of step t in the filter's arithmetic type
+template <class T, int NY>
+__device__ __forceinline__ void load_obs(const StepArgs& a, uint32_t t, T (&y)[NY]) {
+#pragma unroll
+  for (int k = 0; k < NY; ++k) {
+    if constexpr (sizeof(T) == 8) y[k] = a.obs64[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
+    else y[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // linear-Gaussian model step (same operation order as the oracle's lg_propagate / lg_logweight)
 // ------------------------------------------------------------------------------------------
-template <int NX>
-__device__ __forceinline__ void lg_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+template <int NX, class T>
+__device__ __forceinline__ void lg_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
 #pragma unroll
   for (int r = 0; r < NX; ++r) {
-    float acc = __fmul_rn(p.F[r][0], x[0]);
+    T acc = r_mul(p.F[r][0], x[0]);
 #pragma unroll
-    for (int c = 1; c < NX; ++c) acc = __fmaf_rn(p.F[r][c], x[c], acc);
+    for (int c = 1; c < NX; ++c) acc = r_fma(p.F[r][c], x[c], acc);
 #pragma unroll
-    for (int c = 0; c <= r; ++c) acc = __fmaf_rn(p.Lq[r][c], z[c], acc);
+    for (int c = 0; c <= r; ++c) acc = r_fma(p.Lq[r][c], z[c], acc);
     xn[r] = acc;
   }
 }
 
-template <int NX, int NY>
-__device__ __forceinline__ float lg_logweight(const LgDev& p, const float* xn, const float* y) {
-  float d[NY];
+template <int NX, int NY, class T>
+__device__ __forceinline__ T lg_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
+  T d[NY];
 #pragma unroll
   for (int k = 0; k < NY; ++k) {
-    float acc = __fmul_rn(p.H[k][0], xn[0]);
+    T acc = r_mul(p.H[k][0], xn[0]);
 #pragma unroll
-    for (int c = 1; c < NX; ++c) acc = __fmaf_rn(p.H[k][c], xn[c], acc);
-    d[k] = __fsub_rn(y[k], acc);
+    for (int c = 1; c < NX; ++c) acc = r_fma(p.H[k][c], xn[c], acc);
+    d[k] = r_sub(y[k], acc);
   }
-  float quad = 0.0f;
+  T quad = 0;
 #pragma unroll
   for (int k = 0; k < NY; ++k) {
-    float t = __fmul_rn(p.Rinv[k][0], d[0]);
+    T t = r_mul(p.Rinv[k][0], d[0]);
 #pragma unroll
-    for (int l = 1; l < NY; ++l) t = __fmaf_rn(p.Rinv[k][l], d[l], t);
-    quad = (k == 0) ? __fmul_rn(d[0], t) : __fmaf_rn(d[k], t, quad);
+    for (int l = 1; l < NY; ++l) t = r_fma(p.Rinv[k][l], d[l], t);
+    quad = (k == 0) ? r_mul(d[0], t) : r_fma(d[k], t, quad);
   }
-  return __fmul_rn(p.wscale, quad);
+  return r_mul(p.wscale, quad);
 }
 
 // position/velocity structured variants (LgDev::kron): same operations as the dense code minus the
 // terms whose coefficient is zero
-template <int NX>
-__device__ __forceinline__ void kron_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+template <int NX, class T>
+__device__ __forceinline__ void kron_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
   if constexpr (NX == 1) {  // F = 1: fl(1 * x) = x, so fma(L, z, fl(F x)) = fma(L, z, x)
-    xn[0] = __fmaf_rn(p.klp, z[0], x[0]);
+    xn[0] = r_fma(p.klp, z[0], x[0]);
     return;
   }
   constexpr int P = NX / 2;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    float acc = __fmul_rn(p.ka, x[i]);
-    acc = __fmaf_rn(p.kb, x[P + i], acc);
-    xn[i] = __fmaf_rn(p.klp, z[i], acc);
+    T acc = r_mul(p.ka, x[i]);
+    acc = r_fma(p.kb, x[P + i], acc);
+    xn[i] = r_fma(p.klp, z[i], acc);
   }
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    float acc;
-    if (p.kc != 0.0f) { acc = __fmul_rn(p.kc, x[i]); acc = __fmaf_rn(p.kd, x[P + i], acc); }
-    else acc = __fmul_rn(p.kd, x[P + i]);
-    xn[P + i] = __fmaf_rn(p.klv, z[P + i], acc);
+    T acc;
+    if (p.kc != (T)0) { acc = r_mul(p.kc, x[i]); acc = r_fma(p.kd, x[P + i], acc); }
+    else acc = r_mul(p.kd, x[P + i]);
+    xn[P + i] = r_fma(p.klv, z[P + i], acc);
   }
 }
 
-template <int NX, int NY>
-__device__ __forceinline__ float kron_logweight(const LgDev& p, const float* xn, const float* y) {
-  float quad = 0.0f;
+template <int NX, int NY, class T>
+__device__ __forceinline__ T kron_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
+  T quad = 0;
 #pragma unroll
   for (int k = 0; k < NY; ++k) {
-    const float d = __fsub_rn(y[k], xn[k]);
-    const float t = __fmul_rn(p.krinv, d);
-    quad = (k == 0) ? __fmul_rn(d, t) : __fmaf_rn(d, t, quad);
+    const T d = r_sub(y[k], xn[k]);
+    const T t = r_mul(p.krinv, d);
+    quad = (k == 0) ? r_mul(d, t) : r_fma(d, t, quad);
   }
-  return __fmul_rn(p.wscale, quad);
+  return r_mul(p.wscale, quad);
 }
 
-template <int NX, bool KRON>
-__device__ __forceinline__ void model_propagate(const LgDev& p, const float* x, const float* z, float* xn) {
+template <int NX, bool KRON, class T>
+__device__ __forceinline__ void model_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
   if constexpr (KRON) kron_propagate<NX>(p, x, z, xn); else lg_propagate<NX>(p, x, z, xn);
 }
-template <int NX, int NY, bool KRON>
-__device__ __forceinline__ float model_logweight(const LgDev& p, const float* xn, const float* y) {
+template <int NX, int NY, bool KRON, class T>
+__device__ __forceinline__ T model_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
   if constexpr (KRON) return kron_logweight<NX, NY>(p, xn, y); else return lg_logweight<NX, NY>(p, xn, y);
 }
 
-// normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]; one Philox word per normal
-template <int NX>
+// normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]; one Philox word per normal.  A double
+// filter uses the same fp32 table normals, converted exactly.
+template <int NX, class T>
 __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed, const float4* __restrict__ tab_m8,
-                                          float (&z)[NX][4]) {
+                                          T (&z)[NX][4]) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   if constexpr (NX == 1) {
     const U4 r = philox4x32_10(j >> 2, 0u, t, kStreamProp, k0, k1);
-    z[0][0] = icdf_normal(r.x, tab_m8);
-    z[0][1] = icdf_normal(r.y, tab_m8);
-    z[0][2] = icdf_normal(r.z, tab_m8);
-    z[0][3] = icdf_normal(r.w, tab_m8);
+    z[0][0] = (T)icdf_normal(r.x, tab_m8);
+    z[0][1] = (T)icdf_normal(r.y, tab_m8);
+    z[0][2] = (T)icdf_normal(r.z, tab_m8);
+    z[0][3] = (T)icdf_normal(r.w, tab_m8);
   } else if constexpr (NX == 6) {
     // two consecutive slots share three Philox calls: even slot words 0..5, odd slot words 6..11
 #pragma unroll
@@ -254,12 +291,12 @@ __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed,
       const U4 r1 = philox4x32_10((j >> 1) + pr, 1u, t, kStreamProp, k0, k1);
       const U4 r2 = philox4x32_10((j >> 1) + pr, 2u, t, kStreamProp, k0, k1);
       const int s = 2 * pr;
-      z[0][s] = icdf_normal(r0.x, tab_m8); z[1][s] = icdf_normal(r0.y, tab_m8);
-      z[2][s] = icdf_normal(r0.z, tab_m8); z[3][s] = icdf_normal(r0.w, tab_m8);
-      z[4][s] = icdf_normal(r1.x, tab_m8); z[5][s] = icdf_normal(r1.y, tab_m8);
-      z[0][s + 1] = icdf_normal(r1.z, tab_m8); z[1][s + 1] = icdf_normal(r1.w, tab_m8);
-      z[2][s + 1] = icdf_normal(r2.x, tab_m8); z[3][s + 1] = icdf_normal(r2.y, tab_m8);
-      z[4][s + 1] = icdf_normal(r2.z, tab_m8); z[5][s + 1] = icdf_normal(r2.w, tab_m8);
+      z[0][s] = (T)icdf_normal(r0.x, tab_m8); z[1][s] = (T)icdf_normal(r0.y, tab_m8);
+      z[2][s] = (T)icdf_normal(r0.z, tab_m8); z[3][s] = (T)icdf_normal(r0.w, tab_m8);
+      z[4][s] = (T)icdf_normal(r1.x, tab_m8); z[5][s] = (T)icdf_normal(r1.y, tab_m8);
+      z[0][s + 1] = (T)icdf_normal(r1.z, tab_m8); z[1][s + 1] = (T)icdf_normal(r1.w, tab_m8);
+      z[2][s + 1] = (T)icdf_normal(r2.x, tab_m8); z[3][s + 1] = (T)icdf_normal(r2.y, tab_m8);
+      z[4][s + 1] = (T)icdf_normal(r2.z, tab_m8); z[5][s + 1] = (T)icdf_normal(r2.w, tab_m8);
     }
   } else {
 #pragma unroll
@@ -270,11 +307,48 @@ __device__ __forceinline__ void lg_noise4(uint32_t j, uint32_t t, uint64_t seed,
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (4 * c + i < NX) z[4 * c + i][s] = icdf_normal(w[i], tab_m8);
+          if (4 * c + i < NX) z[4 * c + i][s] = (T)icdf_normal(w[i], tab_m8);
       }
     }
   }
 }
+
+// 4 consecutive state scalars: one 128-bit (float) or 256-bit (double) access
+template <class T> struct Quad { T v[4]; };
+__device__ __forceinline__ Quad<float> ld_quad(const float* p) {
+  const float4 f = *reinterpret_cast<const float4*>(p);
+  return Quad<float>{{f.x, f.y, f.z, f.w}};
+}
+__device__ __forceinline__ Quad<double> ld_quad(const double* p) {
+  Quad<double> q;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q.v[0]), "=d"(q.v[1]), "=d"(q.v[2]), "=d"(q.v[3]) : "l"(p));
+  return q;
+}
+__device__ __forceinline__ void st_quad(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st_quad(double* p, const double (&v)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+// shared-memory quads
+__device__ __forceinline__ Quad<float> lds_quad(const float* p) {
+  const float4 f = *reinterpret_cast<const float4*>(p);
+  return Quad<float>{{f.x, f.y, f.z, f.w}};
+}
+__device__ __forceinline__ Quad<double> lds_quad(const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  return Quad<double>{{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void sts_quad(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void sts_quad(double* p, const double (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+// the 32-bit word of a staged scalar that carries the head-mark sentinel (the float itself / the double's high word)
+__device__ __forceinline__ uint32_t mark_word(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t mark_word(double v) { return (uint32_t)__double2hiint(v); }
 
 // ------------------------------------------------------------------------------------------
 // pf_init: the point-mass population before the first observation, with equal weights
@@ -284,8 +358,13 @@ __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i < a.nblk * kBlk) {
     for (int d = 0; d < a.model.nx; ++d) {
-      a.X[0][(size_t)d * a.ld + i] = a.model.x0[d];
-      a.X[1][(size_t)d * a.ld + i] = a.model.x0[d];
+      if (a.f64) {
+        ((double*)a.X[0])[(size_t)d * a.ld + i] = a.modeld.x0[d];
+        ((double*)a.X[1])[(size_t)d * a.ld + i] = a.modeld.x0[d];
+      } else {
+        ((float*)a.X[0])[(size_t)d * a.ld + i] = a.model.x0[d];
+        ((float*)a.X[1])[(size_t)d * a.ld + i] = a.model.x0[d];
+      }
     }
     a.Q[0][i] = i < a.n_local ? (uint16_t)32768 : (uint16_t)0;
     a.Q[1][i] = 0;
@@ -303,7 +382,13 @@ __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
     a.ctl->emax_acc = 0;
     a.ctl->scan_counter = 0;
     a.ctl->scan_done = 0;
-    for (int d = 0; d < 8; ++d) a.plan->center[d] = d < a.model.nx ? a.model.x0[d] : 0.0f;
+    a.ctl->comm_error = 0;
+    a.ctl->ess_resampled = 1;
+    a.ctl->pad[0] = a.ctl->pad[1] = 0;
+    for (int d = 0; d < 8; ++d) {
+      a.plan->center[d] = d < a.model.nx ? a.model.x0[d] : 0.0f;
+      a.plan->center64[d] = d < a.model.nx ? a.modeld.x0[d] : 0.0;
+    }
   }
 }
 
@@ -339,6 +424,8 @@ struct ScanArgs {
   u64* shard_rec;  // sharded: this rank's slot of the all-gathered record
   int64_t margin;  // sharded: halo margin in blocks (the record carries the prefix at both margin edges)
   const ShardP2P* p2p;  // sharded: exchange the block exponent through peer memory (nullptr: NCCL did it)
+  int32_t f64;
+  unsigned long long wait_ticks;
 };
 
 __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint32_t U) {
@@ -361,13 +448,14 @@ __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint
 }
 
 // posterior summary from the centred moment sums in the plan (also re-centres for the next step)
-__device__ void write_summary(PlanDev* pl, pz_step_summary* o, uint32_t t, int nx, int64_t n_out_global, double ll_const) {
+__device__ void write_summary(PlanDev* pl, pz_step_summary* o, uint32_t t, int nx, int64_t n_out_global, double ll_const, int f64) {
   const double sw = pl->sw, sw2 = pl->sw2;
   for (int d = 0; d < nx; ++d) {
-    const float cen = pl->center[d];
+    const double cen = f64 ? pl->center64[d] : (double)pl->center[d];
     const double m = pl->sx[d] / sw;
-    const double mean = (double)cen + m, var = pl->sxx[d] / sw - m * m;
+    const double mean = cen + m, var = pl->sxx[d] / sw - m * m;
     pl->center[d] = (float)mean;
+    pl->center64[d] = mean;
     if (o) { o->mean[d] = mean; o->var[d] = var; }
   }
   if (o) {
@@ -406,7 +494,8 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       int32_t v = kNZero;
       if (lane < s.world) {
         const unsigned long long w = wait_sys<false>(&s.p2p->mbox[s.rank]->emax[lane],
-                                              [epoch](unsigned long long x) { return (x >> 32) == epoch; }, &s.ctl->comm_error);
+                                              [epoch](unsigned long long x) { return (x >> 32) == epoch; }, &s.ctl->comm_error,
+                                              s.wait_ticks);
         v = (int32_t)(uint32_t)w;
       }
 #pragma unroll
@@ -589,7 +678,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       pl->sw = s_tot[1]; pl->sw2 = s_tot[2];
       for (int d = 0; d < s.nx; ++d) { pl->sx[d] = s_tot[3 + d]; pl->sxx[d] = s_tot[3 + s.nx + d]; }
       if (s.world <= 1)
-        write_summary(pl, s.summ ? s.summ + (s.ctl->t % kObsRing) : nullptr, s.ctl->t, s.nx, s.n_out_global, s.ll_const);
+        write_summary(pl, s.summ ? s.summ + (s.ctl->t % kObsRing) : nullptr, s.ctl->t, s.nx, s.n_out_global, s.ll_const, s.f64);
     }
     if (s.world > 1) {  // this rank's record for the all-gather
       u64* r = s.shard_rec + (size_t)s.rank * kShardRec;
@@ -604,6 +693,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       const int64_t m = s.margin < s.nblk ? s.margin : s.nblk;
       r[16] = ((volatile u64*)s.pb)[m];
       r[17] = ((volatile u64*)s.pb)[s.nblk - m];
+      r[18] = (u64)((volatile CtlDev*)s.ctl)->comm_error;  // a timeout seen by this rank: every rank reports it
     }
   }
 }
@@ -629,6 +719,7 @@ struct PartArgs {
   int32_t delta;
   const ShardP2P* p2p;  // sharded over peer memory: wait for the neighbours' halo stores first
   int32_t rank, world;
+  unsigned long long wait_ticks;
 };
 
 __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
@@ -643,7 +734,7 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
       Mailbox* mine = p.p2p->mbox[p.rank];
       if (have)
         wait_sys(threadIdx.x < 2 ? &mine->halo_flag[side] : &mine->pbx_flag[side], [epoch](unsigned long long x) { return x == epoch; },
-                 &p.ctl->comm_error);
+                 &p.ctl->comm_error, p.wait_ticks);
     }
     __syncthreads();
     PZ_STAMP(J == 0, 10);
@@ -694,46 +785,51 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
 constexpr uint32_t kSentinel = 0x7FC0DEADu;  // a NaN payload no arithmetic produces; index payloads use it too
 
 // Payload sources: what is staged for the children of a particle.
-template <int NX>
+template <int NX, class T>
 struct StateSource {
+  typedef T Scalar;
   static constexpr int NV = NX;
   static constexpr bool kPrefetch = (NX == 1);  // one word per particle: fetched one block ahead (registers)
-  const float* x;  // X[cur]
+  const T* x;  // X[cur]
   int64_t ld;
-  float v[NX][4];
-  __device__ __forceinline__ float4 fetch(int64_t i0) const { return *reinterpret_cast<const float4*>(x + i0); }
-  __device__ __forceinline__ void set(const float4& f) { v[0][0] = f.x; v[0][1] = f.y; v[0][2] = f.z; v[0][3] = f.w; }
+  T v[NX][4];
+  __device__ __forceinline__ Quad<T> fetch(int64_t i0) const { return ld_quad(x + i0); }
+  __device__ __forceinline__ void set(const Quad<T>& f) { v[0][0] = f.v[0]; v[0][1] = f.v[1]; v[0][2] = f.v[2]; v[0][3] = f.v[3]; }
   __device__ __forceinline__ void load(int64_t i0) {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
-      const float4 f = *reinterpret_cast<const float4*>(x + (size_t)d * ld + i0);
-      v[d][0] = f.x; v[d][1] = f.y; v[d][2] = f.z; v[d][3] = f.w;
+      const Quad<T> f = ld_quad(x + (size_t)d * ld + i0);
+      v[d][0] = f.v[0]; v[d][1] = f.v[1]; v[d][2] = f.v[2]; v[d][3] = f.v[3];
     }
   }
-  __device__ __forceinline__ void put(float* s_par, int stride, int slot, int k) const {
+  __device__ __forceinline__ void put(T* s_par, int stride, int slot, int k) const {
 #pragma unroll
     for (int d = 0; d < NX; ++d) s_par[d * stride + slot] = v[d][k];
   }
+  // dimension 0 only (the rare long-run duplicates of the NX = 1 look-back variant)
+  __device__ __forceinline__ T first(int k) const { return v[0][k]; }
 };
 
 struct IndexSource {  // generic path: payload = particle index
+  typedef float Scalar;
   static constexpr int NV = 1;
   static constexpr bool kPrefetch = false;
   float v[1][4];
-  __device__ __forceinline__ float4 fetch(int64_t) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
-  __device__ __forceinline__ void set(const float4&) {}
+  __device__ __forceinline__ Quad<float> fetch(int64_t) const { return Quad<float>{{0.f, 0.f, 0.f, 0.f}}; }
+  __device__ __forceinline__ void set(const Quad<float>&) {}
   __device__ __forceinline__ void load(int64_t i0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[0][k] = __int_as_float((int32_t)i0 + k);
   }
   __device__ __forceinline__ void put(float* s_par, int, int slot, int k) const { s_par[slot] = v[0][k]; }
+  __device__ __forceinline__ float first(int k) const { return v[0][k]; }
 };
 
 // SEGDUP = true: a head at every segment boundary any run crosses (every segment starts with a head).
 // SEGDUP = false: only runs longer than 128 slots are duplicated, so a segment whose first slots
 // have no head finds it within the previous segment (output side look-back, NX = 1).
 template <bool SEGDUP, class Source>
-__device__ __forceinline__ void emit_head(const Source& src, float* s_par, int stride, int lo, int hi, int k) {
+__device__ __forceinline__ void emit_head(const Source& src, typename Source::Scalar* s_par, int stride, int lo, int hi, int k) {
   if (hi > lo) {
     src.put(s_par, stride, lo, k);
     if constexpr (SEGDUP) {
@@ -742,11 +838,11 @@ __device__ __forceinline__ void emit_head(const Source& src, float* s_par, int s
     }
   }
 }
-// look-back variant: duplicates of the (rare) runs longer than 128 slots, outside the per-particle fast path
-template <class Source>
-__device__ __noinline__ void emit_long_runs(const Source& src, float* s_par, int stride, int lo, int hi, int k) {
-  if (hi - lo > 128)
-    for (int s = (lo | 127) + 1; s < hi; s += 128) src.put(s_par, stride, s, k);
+// look-back variant (one word per particle): duplicates of the (rare) runs longer than 128 slots, outside the
+// per-particle fast path.  The payload travels by value, so the caller's sources stay in registers.
+template <class S>
+__device__ __noinline__ void emit_long_runs(S payload, S* s_par, int lo, int hi) {
+  for (int s = (lo | 127) + 1; s < hi; s += 128) s_par[s] = payload;
 }
 
 // Input side of one output tile [j0, j0 + nslots): every warp takes input blocks b_first + warp,
@@ -773,84 +869,107 @@ struct BlockIn {
   }
 };
 
+// One input block of the input side (see resample_tile).  Returns true when this and every later block start
+// past the tile.
+template <bool SEGDUP, class Source>
+__device__ __forceinline__ bool resample_block(const Source& src, typename Source::Scalar* s_par, int stride, const BlockIn& in,
+                                               const Quad<typename Source::Scalar>& xa, const Quad<typename Source::Scalar>& xb4,
+                                               int64_t b, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots, int lane) {
+  constexpr bool kAhead = Source::kPrefetch;
+  const uint32_t jend = j0 + (uint32_t)nslots;
+  const uint32_t o0 = (uint32_t)(in.X0 >> 32), o1 = (uint32_t)(in.X1 >> 32);
+  if (o0 >= jend) return true;                // this and every later block start past the tile
+  if (o1 == o0 || o1 <= j0) return false;     // no children (every empty block), or none in this tile
+  const int64_t ia = b * kBlk + lane * 4;
+  Source sa = src, sb = src;
+  if constexpr (kAhead) { sa.set(xa); sb.set(xb4); }
+  else { sa.load(ia); sb.load(ia + 128); }  // payload of the lane's 8 particles, in flight during the scan
+  const int h = h0 + (emax - in.ebb);
+  uint32_t c[8];
+  c[0] = in.qa.x & 0xffffu;
+  c[1] = c[0] + (in.qa.x >> 16);
+  c[2] = c[1] + (in.qa.y & 0xffffu);
+  c[3] = c[2] + (in.qa.y >> 16);
+  c[4] = c[3] + (in.qb.x & 0xffffu);
+  c[5] = c[4] + (in.qb.x >> 16);
+  c[6] = c[5] + (in.qb.y & 0xffffu);
+  c[7] = c[6] + (in.qb.y >> 16);
+  const uint32_t incl = warp_inclusive_scan_u32(c[7], lane);
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t rbase = total - (incl - c[7]);  // block mass from this lane's first particle on
+  const int32_t o0r = (int32_t)(o0 - j0), o1r = (int32_t)(o1 - j0);
+  const uint32_t A = (uint32_t)in.X1;
+  int32_t e[8];
+  if ((unsigned)h <= 31u) {
+    // (c - rbase) * M + A * 2^h as c * M + base: one 32x32+64 multiply-add per particle
+    const long long base = mad_wide_s32(-(int32_t)rbase, (int32_t)Mq, (long long)((u64)A << h));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long res = mad_wide_u32(c[k], Mq, base);
+      e[k] = max(o1r + ((int32_t)(res >> 32) >> h), o0r);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = max(o1r + end_delta_generic(rbase - c[k], Mq, A, h), o0r);
+  }
+  int32_t eprev = __shfl_up_sync(0xffffffffu, e[7], 1);
+  if (lane == 0) eprev = o0r;
+  if (o0r < 0 || o1r > nslots) {  // the block's children straddle a tile edge: clip
+    eprev = min(max(eprev, 0), nslots);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
+  }
+  const int32_t eprev0 = eprev;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
+  if constexpr (!SEGDUP) {
+    // a run longer than 128 slots needs a lane whose 8 particles cover more than 128 slots: one vote per block
+    if (__any_sync(0xffffffffu, e[7] - eprev0 > 128)) {
+      int32_t ep = eprev0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { if (e[k] - ep > 128) emit_long_runs(sa.first(k), s_par, ep, e[k]); ep = e[k]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { if (e[4 + k] - ep > 128) emit_long_runs(sb.first(k), s_par, ep, e[4 + k]); ep = e[4 + k]; }
+    }
+  }
+  return false;
+}
+
+// The warp's input blocks b_first + warp, + NW, ...: the inputs of the next block (weights, boundary positions,
+// and narrow payloads) are loaded one block ahead into a second register set (the loop is unrolled by two so
+// that the two sets alternate without register moves).
 template <bool SEGDUP, int NW, class Source>
-__device__ __forceinline__ void resample_tile(Source& src, float* s_par, int stride, const uint16_t* __restrict__ qin,
+__device__ __forceinline__ void resample_tile(Source& src, typename Source::Scalar* s_par, int stride, const uint16_t* __restrict__ qin,
                                               const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
                                               int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
-                                              int lane, int warp, BlockIn cur) {
-  // `cur` holds the inputs of block b_first + warp (loaded by the caller before its prologue barrier)
-  const uint32_t jend = j0 + (uint32_t)nslots;
+                                              int lane, int warp, const BlockIn& first) {
+  // `first` holds the inputs of block b_first + warp (loaded by the caller before its prologue barrier)
   int64_t b = b_first + warp;
   if (b >= b_end) return;
-  // narrow payloads (one word per particle) are prefetched one block ahead together with the weights;
-  // wide ones are loaded at the top of their own iteration (registers)
   constexpr bool kAhead = Source::kPrefetch;
-  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;   // prefetched payload of the current block
-  if constexpr (kAhead) { pa = src.fetch(b * kBlk + lane * 4); pb = src.fetch(b * kBlk + lane * 4 + 128); }
-  for (; b < b_end; b += NW) {
-    const BlockIn in = cur;
-    const float4 xa = pa, xb4 = pb;
-    const int64_t bn = b + NW;
-    if (bn < b_end) {  // next iteration's inputs: in flight during this one
-      cur.load(qin, ebx, xb, bn, lane);
-      if constexpr (kAhead) { pa = src.fetch(bn * kBlk + lane * 4); pb = src.fetch(bn * kBlk + lane * 4 + 128); }
+  typedef Quad<typename Source::Scalar> QuadS;
+  BlockIn inA = first, inB{};
+  QuadS a0{}, a1{}, b0{}, b1{};
+  if constexpr (kAhead) { a0 = src.fetch(b * kBlk + lane * 4); a1 = src.fetch(b * kBlk + lane * 4 + 128); }
+  while (true) {
+    int64_t bn = b + NW;
+    if (bn < b_end) {
+      inB.load(qin, ebx, xb, bn, lane);
+      if constexpr (kAhead) { b0 = src.fetch(bn * kBlk + lane * 4); b1 = src.fetch(bn * kBlk + lane * 4 + 128); }
     }
-    const uint32_t o0 = (uint32_t)(in.X0 >> 32), o1 = (uint32_t)(in.X1 >> 32);
-    if (o0 >= jend) break;                  // this and every later block start past the tile
-    if (o1 == o0 || o1 <= j0) continue;     // no children (every empty block), or none in this tile
-    const int64_t ia = b * kBlk + lane * 4;
-    Source sa = src, sb = src;
-    if constexpr (kAhead) { sa.set(xa); sb.set(xb4); }
-    else { sa.load(ia); sb.load(ia + 128); }  // payload of the lane's 8 particles, in flight during the scan
-    const int h = h0 + (emax - in.ebb);
-    uint32_t c[8];
-    c[0] = in.qa.x & 0xffffu;
-    c[1] = c[0] + (in.qa.x >> 16);
-    c[2] = c[1] + (in.qa.y & 0xffffu);
-    c[3] = c[2] + (in.qa.y >> 16);
-    c[4] = c[3] + (in.qb.x & 0xffffu);
-    c[5] = c[4] + (in.qb.x >> 16);
-    c[6] = c[5] + (in.qb.y & 0xffffu);
-    c[7] = c[6] + (in.qb.y >> 16);
-    const uint32_t incl = warp_inclusive_scan_u32(c[7], lane);
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t rbase = total - (incl - c[7]);  // block mass from this lane's first particle on
-    const int32_t o0r = (int32_t)(o0 - j0), o1r = (int32_t)(o1 - j0);
-    const uint32_t A = (uint32_t)in.X1;
-    int32_t e[8];
-    if ((unsigned)h <= 31u) {
-      const long long Ah = (long long)((u64)A << h);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const long long res = mad_wide_s32((int32_t)(c[k] - rbase), (int32_t)Mq, Ah);
-        e[k] = max(o1r + ((int32_t)(res >> 32) >> h), o0r);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) e[k] = max(o1r + end_delta_generic(rbase - c[k], Mq, A, h), o0r);
+    if (resample_block<SEGDUP>(src, s_par, stride, inA, a0, a1, b, emax, h0, Mq, j0, nslots, lane)) break;
+    b = bn;
+    if (b >= b_end) break;
+    bn = b + NW;
+    if (bn < b_end) {
+      inA.load(qin, ebx, xb, bn, lane);
+      if constexpr (kAhead) { a0 = src.fetch(bn * kBlk + lane * 4); a1 = src.fetch(bn * kBlk + lane * 4 + 128); }
     }
-    int32_t eprev = __shfl_up_sync(0xffffffffu, e[7], 1);
-    if (lane == 0) eprev = o0r;
-    if (o0r < 0 || o1r > nslots) {  // the block's children straddle a tile edge: clip
-      eprev = min(max(eprev, 0), nslots);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
-    }
-    const int32_t eprev0 = eprev;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sb, s_par, stride, eprev, e[4 + k], k); eprev = e[4 + k]; }
-    if constexpr (!SEGDUP) {
-      // a run longer than 128 slots needs a lane whose 8 particles cover more than 128 slots: one vote per block
-      if (__any_sync(0xffffffffu, e[7] - eprev0 > 128)) {
-        int32_t ep = eprev0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { emit_long_runs(sa, s_par, stride, ep, e[k], k); ep = e[k]; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { emit_long_runs(sb, s_par, stride, ep, e[4 + k], k); ep = e[4 + k]; }
-      }
-    }
+    if (resample_block<SEGDUP>(src, s_par, stride, inB, b0, b1, b, emax, h0, Mq, j0, nslots, lane)) break;
+    b = bn;
+    if (b >= b_end) break;
   }
 }
 
@@ -875,9 +994,11 @@ __device__ __forceinline__ int resolve_heads(const uint4& bits, int sl, int lane
 }
 
 // last head of the 128-slot segment ending at slot seg_end (look-back of the NX = 1 path)
-__device__ __forceinline__ int last_head_before(const float* s_par, int seg_end, int lane) {
+template <class T>
+__device__ __forceinline__ int last_head_before(const T* s_par, int seg_end, int lane) {
   const int sl = seg_end - 128 + lane * 4;
-  const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
+  const Quad<T> qd = lds_quad(&s_par[sl]);
+  const uint4 bits = make_uint4(mark_word(qd.v[0]), mark_word(qd.v[1]), mark_word(qd.v[2]), mark_word(qd.v[3]));
   const int m0 = bits.x != kSentinel ? sl : -1;
   const int m1 = bits.y != kSentinel ? sl + 1 : m0;
   const int m2 = bits.z != kSentinel ? sl + 2 : m1;
@@ -906,17 +1027,36 @@ struct TileArgs {
 constexpr int min_ctas(int nx) { return nx == 1 ? PZ_OCC1 : (nx <= 4 ? PZ_OCC4 : PZ_OCC6); }
 #define PZ_NACC(nx) (2 + 2 * (nx))
 
+template <class T> __device__ __forceinline__ T exp2t(int k);
+template <> __device__ __forceinline__ float exp2t<float>(int k) { return exp2i(k); }
+template <> __device__ __forceinline__ double exp2t<double>(int k) { return pow2d(k); }
+// warp shuffles in the filter's arithmetic type
+__device__ __forceinline__ float shfl_xor_t(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_xor_t(double v, int m) { return shfl_xor_f64(v, m); }
+// block exponent from the block's largest log-weight in double: the same definition evaluated in double
+__device__ __forceinline__ double block_exponent(double maxlw, int32_t& nb) {
+  if (!(maxlw > -INFINITY)) { nb = kNZero; return 0.0; }
+  const double e = fmin(fmax(__dmul_rn(maxlw, kLog2eD), -262144.0), 262144.0);
+  const double nbf = rint(e);
+  nb = __double2int_rn(nbf);
+  return nbf;
+}
+// d = lw * log2(e) - n_b, as the fp32 argument of the weight polynomial
+__device__ __forceinline__ float weight_arg(float lw, float nbf) { return __fmaf_rn(lw, kLog2e, -nbf); }
+__device__ __forceinline__ float weight_arg(double lw, double nbf) { return __double2float_rn(__fma_rn(lw, kLog2eD, -nbf)); }
+
 // Output side of one canonical output block (256 slots, one warp; a lane owns slots lane*4 + {0..3}
 // and 128 + lane*4 + {0..3}).  FULL: every slot of the tile is live (all tiles but the last).
-template <int NX, int NY, int TO, int MODE, bool KRON, bool FULL>
-__device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, const float4* __restrict__ tab_m8, int ob,
-                                             int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const float* y_new,
-                                             const float* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref) {
-  float* __restrict__ xout = a.X[nxt];
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL>
+__device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const float4* __restrict__ tab_m8, int ob,
+                                             int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const T* y_new,
+                                             const T* cen, int lane, T (&acc)[PZ_NACC(NX)], int32_t& aref) {
+  T* __restrict__ xout = reinterpret_cast<T*>(a.X[nxt]);
   uint16_t* __restrict__ qout = a.Q[nxt];
-  float lw[8];
-  float xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
-  float mx = -INFINITY;
+  const LgDevT<T>& model = model_of<T>(a);
+  T lw[8];
+  T xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
+  T mx = -INFINITY;
   int seg_carry = -1;
   if constexpr (MODE == 0 && NX == 1) {
     if (ob > 0) seg_carry = last_head_before(s_par, ob * kBlk, lane);  // runs of <= 128 slots reach back one segment
@@ -924,16 +1064,15 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
-    float xp[NX][4];
+    T xp[NX][4];
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
-      const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
-      xp[d][0] = f.x; xp[d][1] = f.y; xp[d][2] = f.z; xp[d][3] = f.w;
+      const Quad<T> f = lds_quad(&s_par[d * TO + sl]);
+      xp[d][0] = f.v[0]; xp[d][1] = f.v[1]; xp[d][2] = f.v[2]; xp[d][3] = f.v[3];
     }
     if constexpr (MODE == 0) {
       int head[4];
-      const uint4 bits = make_uint4(__float_as_uint(xp[0][0]), __float_as_uint(xp[0][1]), __float_as_uint(xp[0][2]),
-                                    __float_as_uint(xp[0][3]));
+      const uint4 bits = make_uint4(mark_word(xp[0][0]), mark_word(xp[0][1]), mark_word(xp[0][2]), mark_word(xp[0][3]));
       seg_carry = resolve_heads(bits, sl, lane, seg_carry, head);
       if constexpr (NX != 1) seg_carry = -1;
 #pragma unroll
@@ -946,28 +1085,27 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
       }
       if constexpr (NX > 1) __syncwarp();  // every parent read of this segment precedes the write-back below
     }
-    float z[NX][4];
-    lg_noise4<NX>(j0 + (uint32_t)sl, t, a.seed, tab_m8, z);
-    float xo[NX][4];
+    T z[NX][4];
+    lg_noise4<NX, T>(j0 + (uint32_t)sl, t, a.seed, tab_m8, z);
+    T xo[NX][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float xs[NX], zs[NX], xn[NX];
+      T xs[NX], zs[NX], xn[NX];
 #pragma unroll
       for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
-      model_propagate<NX, KRON>(a.model, xs, zs, xn);
+      model_propagate<NX, KRON>(model, xs, zs, xn);
 #pragma unroll
       for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-      float l = model_logweight<NX, NY, KRON>(a.model, xn, y_new);
+      T l = model_logweight<NX, NY, KRON>(model, xn, y_new);
       if (!FULL && sl + k >= nslots) l = -INFINITY;  // past the end of the population
       lw[half * 4 + k] = l;
-      mx = fmaxf(mx, l);
+      mx = r_max(mx, l);
     }
     if (FULL || sl < nslots) {
 #pragma unroll
       for (int d = 0; d < NX; ++d) {
-        const float4 f = make_float4(xo[d][0], xo[d][1], xo[d][2], xo[d][3]);
-        *reinterpret_cast<float4*>(&xout[(size_t)d * a.ld + j0l + sl]) = f;
-        if constexpr (NX > 1) *reinterpret_cast<float4*>(&s_par[d * TO + sl]) = f;
+        st_quad(&xout[(size_t)d * a.ld + j0l + sl], xo[d]);
+        if constexpr (NX > 1) sts_quad(&s_par[d * TO + sl], xo[d]);
       }
     }
     if constexpr (NX == 1) {
@@ -976,23 +1114,23 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
     }
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  for (int d = 16; d > 0; d >>= 1) mx = r_max(mx, shfl_xor_t(mx, d));
   int32_t nb;
-  const float nbf = block_exponent(mx, nb);
+  const T nbf = block_exponent(mx, nb);
   uint32_t ssum = 0;
   if (nb != kNZero) {
-    float p[PZ_NACC(NX)];
+    T p[PZ_NACC(NX)];
 #pragma unroll
-    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0.0f;
+    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int sl = ob * kBlk + half * 128 + lane * 4;
-      float xv[NX][4];
+      T xv[NX][4];
       if constexpr (NX > 1) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          const float4 f = *reinterpret_cast<const float4*>(&s_par[d * TO + sl]);
-          xv[d][0] = f.x; xv[d][1] = f.y; xv[d][2] = f.z; xv[d][3] = f.w;
+          const Quad<T> f = lds_quad(&s_par[d * TO + sl]);
+          xv[d][0] = f.v[0]; xv[d][1] = f.v[1]; xv[d][2] = f.v[2]; xv[d][3] = f.v[3];
         }
       } else {
 #pragma unroll
@@ -1001,19 +1139,20 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
       uint32_t qb[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float w;
-        weight_q<false>(lw[half * 4 + k], nbf, w, qb[k]);
+        float wf;
+        weight_q_from_arg<false>(weight_arg(lw[half * 4 + k], nbf), wf, qb[k]);
         const bool live = FULL || sl + k < nslots;
-        if (!live) w = 0.0f;  // (its q is already 0: lw = -inf)
+        if (!live) wf = 0.0f;  // (its q is already 0: lw = -inf)
+        const T w = (T)wf;
         ssum += qb[k];        // raw bits 0x4B000000 + q; the bias is removed after the warp sum
-        p[0] = __fadd_rn(p[0], w);
-        p[1] = __fmaf_rn(w, w, p[1]);
+        p[0] = r_add(p[0], w);
+        p[1] = r_fma(w, w, p[1]);
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          const float dx = live ? __fsub_rn(xv[d][k], cen[d]) : 0.0f;
-          const float wd = __fmul_rn(w, dx);
-          p[2 + d] = __fadd_rn(p[2 + d], wd);
-          p[2 + NX + d] = __fmaf_rn(wd, dx, p[2 + NX + d]);
+          const T dx = live ? r_sub(xv[d][k], cen[d]) : (T)0;
+          const T wd = r_mul(w, dx);
+          p[2 + d] = r_add(p[2 + d], wd);
+          p[2 + NX + d] = r_fma(wd, dx, p[2 + NX + d]);
         }
       }
       if (FULL || sl < nslots)
@@ -1022,18 +1161,18 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
     // fold the block's sums (scale 2^nb) into the lane accumulators (scale 2^aref)
     if (nb == aref) {
 #pragma unroll
-      for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = __fadd_rn(acc[r], p[r]);
+      for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = r_add(acc[r], p[r]);
     } else if (aref == kNZero) {
 #pragma unroll
       for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = p[r];
       aref = nb;
     } else {
       const int32_t nref = max(aref, nb);
-      const float ga = exp2i(aref - nref), gp = exp2i(nb - nref);
+      const T ga = exp2t<T>(aref - nref), gp = exp2t<T>(nb - nref);
 #pragma unroll
       for (int r = 0; r < PZ_NACC(NX); ++r) {
-        const float fa = (r == 1) ? __fmul_rn(ga, ga) : ga, fp = (r == 1) ? __fmul_rn(gp, gp) : gp;
-        acc[r] = __fmaf_rn(acc[r], fa, __fmul_rn(p[r], fp));
+        const T fa = (r == 1) ? r_mul(ga, ga) : ga, fp = (r == 1) ? r_mul(gp, gp) : gp;
+        acc[r] = r_fma(acc[r], fa, r_mul(p[r], fp));
       }
       aref = nref;
     }
@@ -1055,10 +1194,11 @@ __device__ __forceinline__ void output_block(const StepArgs& a, float* s_par, co
 }
 
 // NT threads per CTA (NW warps): 256 by default; PZ_NT1 = 128 runs the NX = 1 kernel with half-size CTAs
-template <int NX, int NY, int TO, int MODE, bool KRON, int NT>
-__global__ void __launch_bounds__(NT, min_ctas(NX) * (kThreads / NT)) pf_step_tile(const __grid_constant__ TileArgs ta) {
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__ TileArgs ta) {
   constexpr int NW = NT / 32;
-  extern __shared__ __align__(16) float s_par[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
+  extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
+  T* s_par = reinterpret_cast<T*>(s_raw);
   __shared__ int32_t s_eref[NW];
   __shared__ double s_red[NW][kMaxRec];
   float4* s_tab = reinterpret_cast<float4*>(s_par + NX * TO);
@@ -1066,16 +1206,15 @@ __global__ void __launch_bounds__(NT, min_ctas(NX) * (kThreads / NT)) pf_step_ti
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t t = a.ctl->t;
   const int cur = t & 1, nxt = cur ^ 1;
-  const float* __restrict__ xin = a.X[cur];
+  const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[cur]);
   const PlanDev* pl = a.plan;
   const int64_t j0l = (int64_t)blockIdx.x * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
   const uint32_t j0 = (uint32_t)(a.slot_base + j0l);
   const int nslots = (int)(jendl - j0l);
 
-  float y_new[NY];
-#pragma unroll
-  for (int k = 0; k < NY; ++k) y_new[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
+  T y_new[NY];
+  load_obs<T, NY>(a, t, y_new);
 
   if constexpr (MODE == 0) {
     // the first input block's weights: in flight during the prologue
@@ -1083,11 +1222,11 @@ __global__ void __launch_bounds__(NT, min_ctas(NX) * (kThreads / NT)) pf_step_ti
     BlockIn first{};
     if (b_first + warp < a.b_hi) first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
     for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
-    // sentinel in dimension 0 of every slot: "no head here"
+    // sentinel in (the mark word of) dimension 0 of every slot: "no head here"
     uint4* sz = reinterpret_cast<uint4*>(s_par);
-    for (int i = tid; i < TO / 4; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
-    StateSource<NX> src;
+    StateSource<NX, T> src;
     src.x = xin; src.ld = a.ld;
     resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
                              lane, warp, first);
@@ -1103,19 +1242,21 @@ __global__ void __launch_bounds__(NT, min_ctas(NX) * (kThreads / NT)) pf_step_ti
 
   // ---- output side
   const float4* tab_m8 = s_tab - 8;
-  float acc[PZ_NACC(NX)];  // sw, sw2, sx[NX], sxx[NX] at scale 2^aref (fp32 per lane)
+  T acc[PZ_NACC(NX)];  // sw, sw2, sx[NX], sxx[NX] at scale 2^aref (per lane, in the filter's arithmetic type)
 #pragma unroll
-  for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0.0f;
+  for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0;
   int32_t aref = kNZero;
-  float cen[NX];
+  T cen[NX];
 #pragma unroll
-  for (int d = 0; d < NX; ++d) cen[d] = pl->center[d];
+  for (int d = 0; d < NX; ++d) {
+    if constexpr (sizeof(T) == 8) cen[d] = pl->center64[d]; else cen[d] = pl->center[d];
+  }
   if (nslots == TO) {
     for (int ob = warp; ob < TO / kBlk; ob += NW)
-      output_block<NX, NY, TO, MODE, KRON, true>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+      output_block<T, NX, NY, TO, MODE, KRON, true>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   } else {
     for (int ob = warp; ob * kBlk < nslots; ob += NW)
-      output_block<NX, NY, TO, MODE, KRON, false>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+      output_block<T, NX, NY, TO, MODE, KRON, false>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   }
 
   // ---- CTA-level reduction of the moment sums -> one record per tile
@@ -1201,6 +1342,7 @@ __device__ __forceinline__ const uint16_t* generic_q(const GenericArgs& g) { ret
 
 __global__ void pf_ctl_reset(CtlDev* ctl) {
   ctl->t = 0; ctl->emax_acc = kNZero; ctl->scan_counter = 0; ctl->scan_done = 0;
+  ctl->comm_error = 0; ctl->ess_resampled = 1; ctl->pad[0] = ctl->pad[1] = 0;
 }
 
 template <int TO>
@@ -1260,29 +1402,35 @@ __global__ void __launch_bounds__(kThreads) pf_multinomial(const GenericArgs g) 
   g.anc[j] = res;
 }
 
-template <int NX, int NY>
-__global__ void __launch_bounds__(kThreads) pf_logw(StepArgs a, float* lw_out) {
+// log-weights of the pending population (parity tap): lw_out32 (rounded to float when the filter is f64) and /
+// or lw_out64 (exact in both cases)
+template <class T, int NX, int NY>
+__global__ void __launch_bounds__(kThreads) pf_logw(StepArgs a, float* lw_out32, double* lw_out64) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.n_local) return;
   const uint32_t t = a.ctl->t;
-  if (t == 0) { lw_out[i] = 0.0f; return; }  // the initial point mass: equal weights
-  const float* x = a.X[t & 1];
-  const uint32_t tp = (t + kObsRing - 1) % kObsRing;
-  float xs[NX], y[NY];
+  T l = 0;  // the initial point mass: equal weights
+  if (t != 0) {
+    const T* x = reinterpret_cast<const T*>(a.X[t & 1]);
+    T xs[NX], y[NY];
 #pragma unroll
-  for (int d = 0; d < NX; ++d) xs[d] = x[(size_t)d * a.ld + i];
-#pragma unroll
-  for (int k = 0; k < NY; ++k) y[k] = a.obs[(size_t)tp * PZ_MAX_NY + k];
-  lw_out[i] = lg_logweight<NX, NY>(a.model, xs, y);
+    for (int d = 0; d < NX; ++d) xs[d] = x[(size_t)d * a.ld + i];
+    load_obs<T, NY>(a, t + kObsRing - 1, y);
+    l = lg_logweight<NX, NY>(model_of<T>(a), xs, y);
+  }
+  if (lw_out32) lw_out32[i] = (float)l;
+  if (lw_out64) lw_out64[i] = (double)l;
 }
 
+// every stride-th resampled particle, slot-major, as doubles
 __global__ void __launch_bounds__(kThreads) pf_gather_thin(StepArgs a, const int32_t* anc, int32_t stride, int64_t n_sel,
-                                                           float* out) {
+                                                           double* out) {
   const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (s >= n_sel) return;
-  const float* x = a.X[a.ctl->t & 1];
   const int64_t p = anc[s * stride];
-  for (int d = 0; d < a.model.nx; ++d) out[s * a.model.nx + d] = x[(size_t)d * a.ld + p];
+  for (int d = 0; d < a.model.nx; ++d)
+    out[s * a.model.nx + d] = a.f64 ? reinterpret_cast<const double*>(a.X[a.ctl->t & 1])[(size_t)d * a.ld + p]
+                                    : (double)reinterpret_cast<const float*>(a.X[a.ctl->t & 1])[(size_t)d * a.ld + p];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1301,10 +1449,9 @@ struct ShardPlanArgs {
   double ll_const;
   // peer-memory exchange (p2p != nullptr): records through the mailboxes, halo margins by peer stores
   const ShardP2P* p2p;
-  const float* X[2];
-  const uint16_t* Q[2];
-  const int32_t* eb[2];
-  int64_t ld, margin;
+  int64_t margin;
+  int32_t f64;
+  unsigned long long wait_ticks;
 };
 
 __device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, int64_t gid, int64_t gsz) {
@@ -1319,7 +1466,8 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, 
 struct HaloPushArgs {
   const CtlDev* ctl;
   const ShardP2P* p2p;
-  const float* X[2];
+  const void* X[2];
+  int32_t esz;  // bytes per state scalar
   const uint16_t* Q[2];
   const int32_t* eb[2];
   int64_t nblk, ld, margin;
@@ -1331,15 +1479,19 @@ __global__ void __launch_bounds__(kThreads) pf_halo_push(const HaloPushArgs p) {
   const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
   const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
   const int64_t m = p.margin, nb = p.nblk;
+  const size_t es = (size_t)p.esz;
+  const char* xmine = reinterpret_cast<const char*>(p.X[which]);
   if (p.rank > 0) {  // my first m blocks: the RIGHT halo of rank-1
+    char* xn = reinterpret_cast<char*>(p.p2p->Xn[0][which]);
     for (int d = 0; d < p.nx; ++d)
-      copy16(p.p2p->Xn[0][which] + (size_t)d * p.ld + nb * kBlk, p.X[which] + (size_t)d * p.ld, m * kBlk / 4, gid, gsz);
+      copy16(xn + ((size_t)d * p.ld + nb * kBlk) * es, xmine + (size_t)d * p.ld * es, m * kBlk * p.esz / 16, gid, gsz);
     copy16(p.p2p->Qn[0][which] + nb * kBlk, p.Q[which], m * kBlk / 8, gid, gsz);
     for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[0][which][nb + i] = p.eb[which][i];
   }
   if (p.rank + 1 < p.world) {  // my last m blocks: the LEFT halo of rank+1
+    char* xn = reinterpret_cast<char*>(p.p2p->Xn[1][which]);
     for (int d = 0; d < p.nx; ++d)
-      copy16(p.p2p->Xn[1][which] + (size_t)d * p.ld - m * kBlk, p.X[which] + (size_t)d * p.ld + (nb - m) * kBlk, m * kBlk / 4, gid, gsz);
+      copy16(xn + ((ptrdiff_t)d * p.ld - m * kBlk) * (ptrdiff_t)es, xmine + ((size_t)d * p.ld + (nb - m) * kBlk) * es, m * kBlk * p.esz / 16, gid, gsz);
     copy16(p.p2p->Qn[1][which] - m * kBlk, p.Q[which] + (nb - m) * kBlk, m * kBlk / 8, gid, gsz);
     for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[1][which][i - m] = p.eb[which][nb - m + i];
   }
@@ -1383,7 +1535,8 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
     uint32_t* s_half = reinterpret_cast<uint32_t*>(s_rec);  // little endian: half w of word k of rank q = s_half[(q * kShardRec + k) * 2 + (w & 1)]
     for (int i = tid; i < nw; i += kThreads) {
       const u64 x = wait_sys<false>(&mine->rec2[i / (2 * kShardRec)][i % (2 * kShardRec)],
-                                    [epoch](unsigned long long x) { return (uint32_t)(x >> 32) == epoch; }, &p.ctl->comm_error);
+                                    [epoch](unsigned long long x) { return (uint32_t)(x >> 32) == epoch; }, &p.ctl->comm_error,
+                                    p.wait_ticks);
       s_half[i] = (uint32_t)x;
     }
     __syncthreads();
@@ -1452,7 +1605,9 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
         bq += tq;
       }
     }
-    if (p.ctl->comm_error) overflow = 2;
+    bool comm_err = p.ctl->comm_error != 0;
+    for (int q = 0; q < p.world; ++q) comm_err = comm_err || ((const volatile u64*)rec)[(size_t)q * kShardRec + 18] != 0;
+    if (comm_err) overflow = 2;
     pl->shard_overflow = overflow;
     if (p.delta) {  // moment sums of all ranks, in rank order (every rank computes the same value)
       double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
@@ -1468,7 +1623,7 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
       pl->sw = sw; pl->sw2 = sw2;
       for (int d = 0; d < p.nx; ++d) { pl->sx[d] = sx[d]; pl->sxx[d] = sxx[d]; }
       pz_step_summary* o = p.summ ? p.summ + (p.ctl->t % kObsRing) : nullptr;
-      write_summary(pl, o, p.ctl->t, p.nx, p.n_global, p.ll_const);
+      write_summary(pl, o, p.ctl->t, p.nx, p.n_global, p.ll_const, p.f64);
       if (o) o->n_migrated = overflow ? -(int64_t)overflow : migrated;
     }
   }
@@ -1482,29 +1637,41 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // Output slots per CTA: (a multiple of the CTA's warp count) - 1 canonical blocks, because a tile of m
 // output blocks draws on m + 1 input blocks in the typical case and the warps of the CTA take input
 // blocks round-robin (a remainder of one block would leave the other warps waiting at the barrier).  Larger tiles amortise the
-// extra input block and the CTA-level reduction; PZ_TILE_OUT=small selects the smaller
-// instantiation (kept for A/B measurements, profiles/README.md).
+// extra input block and the CTA-level reduction.
 // CTA size and tile size of the step kernel (measured, profiles/README.md): half-size CTAs put twice as
-// many independent, phase-shifted tiles on an SM and halve the barrier domain.
+// many independent, phase-shifted tiles on an SM and halve the barrier domain.  A double filter stages
+// 8 bytes per slot and dimension, so its tiles are about half as long for the same shared memory.
 #ifndef PZ_NT1
 #define PZ_NT1 128   // threads per CTA, NX = 1
 #endif
 #ifndef PZ_TB1
-#define PZ_TB1 23    // output blocks per tile, NX = 1 (a multiple of the warp count, minus 1)
+#define PZ_TB1 23    // output blocks per tile, NX = 1, float (a multiple of the warp count, minus 1)
+#endif
+#ifndef PZ_TB1D
+#define PZ_TB1D 15   // output blocks per tile, NX = 1, double
 #endif
 #ifndef PZ_NTN
 #define PZ_NTN 256   // threads per CTA, NX > 1
 #endif
 #ifndef PZ_TBN
-#define PZ_TBN 15    // output blocks per tile, NX > 1
+#define PZ_TBN 15    // output blocks per tile, NX > 1, float
 #endif
-constexpr int kTileBig1 = PZ_TB1 * kBlk, kTileSmall1 = 15 * kBlk;   // NX = 1
-constexpr int kTileBigN = PZ_TBN * kBlk, kTileSmallN = 7 * kBlk;    // NX > 1
-int fused_tile_out(int nx) {
-  static const bool small = [] { const char* e = getenv("PZ_TILE_OUT"); return e && !strcmp(e, "small"); }();
-  if (nx == 1) return small ? kTileSmall1 : kTileBig1;
-  return small ? kTileSmallN : kTileBigN;
+#ifndef PZ_TBND
+#define PZ_TBND 7    // output blocks per tile, NX > 1, double
+#endif
+#ifndef PZ_OCC1D
+#define PZ_OCC1D 3   // resident 256-thread-equivalents per SM the double NX = 1 kernel's registers are held to
+#endif
+// small = true: the second tile size (PZ_TILE_OUT=small), kept so that the tests can check that results do
+// not depend on the tiling
+constexpr int tile_blocks(int nx, bool f64, bool small) {
+  return nx == 1 ? (f64 ? (small ? 7 : PZ_TB1D) : (small ? 15 : PZ_TB1)) : (f64 ? (small ? 3 : PZ_TBND) : (small ? 7 : PZ_TBN));
 }
+static bool tile_small() {
+  static const bool small = [] { const char* e = getenv("PZ_TILE_OUT"); return e && !strcmp(e, "small"); }();
+  return small;
+}
+int fused_tile_out(int nx, int f64) { return tile_blocks(nx, f64 != 0, tile_small()) * kBlk; }
 
 int launch_init(const StepArgs& a, cudaStream_t s) {
   int64_t m = a.nblk * kBlk;
@@ -1522,6 +1689,7 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   sc.nscan = a.nscan; sc.nrec = a.ntiles_out; sc.nx = a.model.nx; sc.delta = delta;
   sc.explicit_U = 0; sc.U_value = 0; sc.seed = a.seed; sc.ll_const = a.ll_const; sc.world = a.world;
   sc.rank = a.rank; sc.shard_rec = a.shard_rec; sc.margin = a.margin; sc.p2p = a.p2p;
+  sc.f64 = a.f64; sc.wait_ticks = a.wait_ticks;
   return sc;
 }
 
@@ -1534,7 +1702,7 @@ static int partition_grid(int64_t ntiles, int64_t nscan, int64_t nbound) {
 
 static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
   PartArgs pa{a.pbx, a.xb, a.b_lo, a.b_hi, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
-              a.ntiles_out, tile_out, a.nscan, delta, a.p2p, a.rank, a.world};
+              a.ntiles_out, tile_out, a.nscan, delta, a.p2p, a.rank, a.world, a.wait_ticks};
   int grid = partition_grid(a.ntiles_out, a.nscan, a.b_hi - a.b_lo + 1);
   if (a.p2p && grid > 592) grid = 592;  // every CTA polls a flag: keep the whole grid resident
   pf_partition<<<grid, kThreads, 0, s>>>(pa);
@@ -1555,18 +1723,23 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
   return scan_partition(a, 0, tile_out, s);
 }
 
-template <int NX, int NY, int TO, int MODE, bool KRON>
+template <class T, int NX, int NY, int MODE, bool KRON, bool SMALL>
 static void launch_tile(const TileArgs& ta, cudaStream_t s) {
+  constexpr bool F64 = sizeof(T) == 8;
   constexpr int NT = (NX == 1) ? PZ_NT1 : PZ_NTN;
-  auto kern = pf_step_tile<NX, NY, TO, MODE, KRON, NT>;
+  constexpr int TO = tile_blocks(NX, F64, SMALL) * kBlk;
+  constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : 2) : min_ctas(NX);
+  auto kern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT)>;
   // staged parents [NX][TO] + inverse-CDF table
-  size_t smem = (size_t)NX * TO * sizeof(float) + PZ_ICDF_ROWS * sizeof(float4);
-  static unsigned long long attr_done = 0;  // per device (function attributes are per context)
+  const size_t smem = (size_t)NX * TO * sizeof(T) + PZ_ICDF_ROWS * sizeof(float4);
+  // function attributes are per context (device); concurrent first launches set the same value
+  static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done |= 1ull << (dev & 63);
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
 }
@@ -1575,28 +1748,31 @@ static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
   const int nx = ta.a.model.nx, ny = ta.a.model.ny;
   const bool fused = (ta.anc == nullptr);
   const bool kron = ta.a.model.kron != 0;
-#define PZ_DISPATCH(NXv, NYv, TOv, KR)                               \
-  if (nx == NXv && ny == NYv && kron == KR) {                        \
-    if (fused) launch_tile<NXv, NYv, TOv, 0, KR>(ta, s);             \
-    else launch_tile<NXv, NYv, TOv, 1, KR>(ta, s);                   \
-    return 1;                                                        \
+  const bool f64 = ta.a.f64 != 0;
+  const bool small = tile_small();
+#define PZ_DISPATCH(Tv, NXv, NYv, KR)                                     \
+  if (f64 == (sizeof(Tv) == 8) && nx == NXv && ny == NYv && kron == KR) { \
+    if (small) {                                                          \
+      if (fused) launch_tile<Tv, NXv, NYv, 0, KR, true>(ta, s);           \
+      else launch_tile<Tv, NXv, NYv, 1, KR, true>(ta, s);                 \
+    } else {                                                              \
+      if (fused) launch_tile<Tv, NXv, NYv, 0, KR, false>(ta, s);          \
+      else launch_tile<Tv, NXv, NYv, 1, KR, false>(ta, s);                \
+    }                                                                     \
+    return 1;                                                             \
   }
-  const bool big = fused_tile_out(nx) == (nx == 1 ? kTileBig1 : kTileBigN);
-  if (big) {
-    PZ_DISPATCH(1, 1, kTileBig1, false)
-    PZ_DISPATCH(1, 1, kTileBig1, true)
-    PZ_DISPATCH(4, 2, kTileBigN, false)
-    PZ_DISPATCH(4, 2, kTileBigN, true)
-    PZ_DISPATCH(6, 3, kTileBigN, false)
-    PZ_DISPATCH(6, 3, kTileBigN, true)
-  } else {
-    PZ_DISPATCH(1, 1, kTileSmall1, false)
-    PZ_DISPATCH(1, 1, kTileSmall1, true)
-    PZ_DISPATCH(4, 2, kTileSmallN, false)
-    PZ_DISPATCH(4, 2, kTileSmallN, true)
-    PZ_DISPATCH(6, 3, kTileSmallN, false)
-    PZ_DISPATCH(6, 3, kTileSmallN, true)
-  }
+  PZ_DISPATCH(float, 1, 1, false)
+  PZ_DISPATCH(float, 1, 1, true)
+  PZ_DISPATCH(float, 4, 2, false)
+  PZ_DISPATCH(float, 4, 2, true)
+  PZ_DISPATCH(float, 6, 3, false)
+  PZ_DISPATCH(float, 6, 3, true)
+  PZ_DISPATCH(double, 1, 1, false)
+  PZ_DISPATCH(double, 1, 1, true)
+  PZ_DISPATCH(double, 4, 2, false)
+  PZ_DISPATCH(double, 4, 2, true)
+  PZ_DISPATCH(double, 6, 3, false)
+  PZ_DISPATCH(double, 6, 3, true)
 #undef PZ_DISPATCH
   return -1;
 }
@@ -1605,7 +1781,7 @@ static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
 int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s) {
   TileArgs ta{a, anc};
   if (dispatch_tile(ta, s) < 0) return -1;
-  return 1 + scan_partition(a, 1, fused_tile_out(a.model.nx), s);
+  return 1 + scan_partition(a, 1, fused_tile_out(a.model.nx, a.f64), s);
 }
 
 int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
@@ -1616,7 +1792,7 @@ int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
   ScanArgs sc = make_scan(a, 1, true);
   pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
   cudaEventRecord(ev[2], s);
-  partition(a, fused_tile_out(a.model.nx), 1, s);
+  partition(a, fused_tile_out(a.model.nx, a.f64), 1, s);
   cudaEventRecord(ev[3], s);
   return 3;
 }
@@ -1637,10 +1813,11 @@ void dbg_read_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_stam
 #endif
 
 int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s) {
-  HaloPushArgs p{a.ctl, a.p2p, {a.X[0], a.X[1]}, {a.Q[0], a.Q[1]}, {a.eb[0], a.eb[1]}, a.nblk, a.ld, a.margin,
+  const int esz = a.f64 ? 8 : 4;
+  HaloPushArgs p{a.ctl, a.p2p, {a.X[0], a.X[1]}, esz, {a.Q[0], a.Q[1]}, {a.eb[0], a.eb[1]}, a.nblk, a.ld, a.margin,
                  a.rank, a.world, a.model.nx, delta};
-  // 16-byte stores per margin and side: nx * m * 64 (X) + m * 32 (Q); two per thread, at most two CTAs per SM beside the scan
-  int grid = cdiv((int64_t)(a.model.nx * 64 + 32) * a.margin, 2 * kThreads);
+  // 16-byte stores per margin and side: nx * m * 16 * esz (X) + m * 32 (Q); two per thread, at most two CTAs per SM beside the scan
+  int grid = cdiv((int64_t)(a.model.nx * 16 * esz + 32) * a.margin, 2 * kThreads);
   grid = grid < 1 ? 1 : (grid > 296 ? 296 : grid);
   pf_halo_push<<<grid, kThreads, 0, s>>>(p);
   return 1;
@@ -1648,8 +1825,7 @@ int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s) {
 
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s) {
   ShardPlanArgs p{a.plan, a.ctl, a.shard_rec, a.pb, const_cast<u64*>(a.pbx), a.summ, a.nblk, a.n_global, a.n_local,
-                  a.rank, a.world, a.model.nx, delta, a.seed, a.ll_const, a.p2p, {a.X[0], a.X[1]}, {a.Q[0], a.Q[1]},
-                  {a.eb[0], a.eb[1]}, a.ld, a.margin};
+                  a.rank, a.world, a.model.nx, delta, a.seed, a.ll_const, a.p2p, a.margin, a.f64, a.wait_ticks};
   int grid = cdiv(a.nblk + 1, kThreads);
   grid = grid > 592 ? 592 : grid;  // every CTA polls a flag: keep the whole grid resident (148 SMs x 4)
   pf_plan_sharded<<<grid, kThreads, 0, s>>>(p);
@@ -1674,9 +1850,10 @@ int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s
   sc.plan = g.plan; sc.ctl = g.ctl; sc.summ = nullptr; sc.nblk = g.nblk; sc.n_out_global = g.n; sc.n_local = g.n;
   sc.nscan = g.nscan; sc.nrec = 0; sc.nx = 0; sc.delta = 0; sc.explicit_U = 1; sc.U_value = g.U; sc.seed = g.seed;
   sc.ll_const = 0; sc.world = 1; sc.rank = 0; sc.shard_rec = nullptr; sc.margin = 0; sc.p2p = nullptr;
+  sc.f64 = 0; sc.wait_ticks = 0;
   pf_scan_blocks<<<g.nscan, kThreads, 0, s>>>(sc);
   PartArgs pa{g.pb, g.xb, 0, g.nblk, g.tile_start, g.scan_status, g.plan, g.ctl, g.nblk, 0, g.n, g.ntiles_out, kGenericTileOut, g.nscan, 0,
-              nullptr, 0, 1};
+              nullptr, 0, 1, 0ull};
   pf_partition<<<partition_grid(g.ntiles_out, g.nscan, g.nblk + 1), kThreads, 0, s>>>(pa);
   return n + 2;
 }
@@ -1696,17 +1873,26 @@ int launch_generic_multinomial(const GenericArgs& g, cudaStream_t s) {
   return 1;
 }
 
-int launch_logw(const StepArgs& a, float* lw_out, cudaStream_t s) {
+int launch_logw(const StepArgs& a, float* lw_out32, double* lw_out64, cudaStream_t s) {
   const int nx = a.model.nx, ny = a.model.ny;
   int grid = cdiv(a.n_local, kThreads);
-  if (nx == 1 && ny == 1) pf_logw<1, 1><<<grid, kThreads, 0, s>>>(a, lw_out);
-  else if (nx == 4 && ny == 2) pf_logw<4, 2><<<grid, kThreads, 0, s>>>(a, lw_out);
-  else if (nx == 6 && ny == 3) pf_logw<6, 3><<<grid, kThreads, 0, s>>>(a, lw_out);
-  else return -1;
+#define PZ_LOGW(Tv, NXv, NYv) pf_logw<Tv, NXv, NYv><<<grid, kThreads, 0, s>>>(a, lw_out32, lw_out64)
+  if (a.f64) {
+    if (nx == 1 && ny == 1) PZ_LOGW(double, 1, 1);
+    else if (nx == 4 && ny == 2) PZ_LOGW(double, 4, 2);
+    else if (nx == 6 && ny == 3) PZ_LOGW(double, 6, 3);
+    else return -1;
+  } else {
+    if (nx == 1 && ny == 1) PZ_LOGW(float, 1, 1);
+    else if (nx == 4 && ny == 2) PZ_LOGW(float, 4, 2);
+    else if (nx == 6 && ny == 3) PZ_LOGW(float, 6, 3);
+    else return -1;
+  }
+#undef PZ_LOGW
   return 1;
 }
 
-int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, float* out,
+int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, double* out,
                        cudaStream_t s) {
   pf_gather_thin<<<cdiv(n_sel, kThreads), kThreads, 0, s>>>(a, anc, stride, n_sel, out);
   return 1;

@@ -30,22 +30,27 @@ constexpr int kPad = 2048;       // allocation granularity in particles
 constexpr int kObsRing = 4096;   // rows of the device observation / summary rings
 constexpr int kMaxRec = 3 + 2 * PZ_MAX_NX;  // doubles per moment record
 
-// Derived fp32 parameters of the linear-Gaussian family (RW1D = LG(1,1)).
-struct LgDev {
-  float F[PZ_MAX_NX][PZ_MAX_NX];
-  float Lq[PZ_MAX_NX][PZ_MAX_NX];
-  float H[PZ_MAX_NY][PZ_MAX_NX];
-  float Rinv[PZ_MAX_NY][PZ_MAX_NY];
-  float x0[PZ_MAX_NX];
-  float wscale;
+// Derived parameters of the linear-Gaussian family (RW1D = LG(1,1)) in the arithmetic type of the
+// filter: T = float (state_f64 = 0) or double (state_f64 = 1, the reference's own precision,
+// Inference.hs:28 `type Weight = Log Double`).
+template <class T>
+struct LgDevT {
+  T F[PZ_MAX_NX][PZ_MAX_NX];
+  T Lq[PZ_MAX_NX][PZ_MAX_NX];
+  T H[PZ_MAX_NY][PZ_MAX_NX];
+  T Rinv[PZ_MAX_NY][PZ_MAX_NY];
+  T x0[PZ_MAX_NX];
+  T wscale;
   int32_t nx, ny;
   // Position/velocity ("Kronecker") structure, detected on the host: state = (pos[p], vel[p]),
   // F = [[a, b], [c, d]] (x) I_p, Q = diag(qp I, qv I), H = [I_p 0], R = r I_p.  The specialised
   // code path performs exactly the operations of the dense spec that have non-zero coefficients,
   // in the same order, so the results are bit-identical.
   int32_t kron;
-  float ka, kb, kc, kd, klp, klv, krinv;
+  T ka, kb, kc, kd, klp, klv, krinv;
 };
+typedef LgDevT<float> LgDev;
+typedef LgDevT<double> LgDevD;
 
 // Resampling plan + posterior moment sums of one weighted population (device resident).
 struct PlanDev {
@@ -62,6 +67,7 @@ struct PlanDev {
   uint32_t shard_epoch;    // sharded: epoch of the exchange that produced this plan
   uint32_t U;           // the uniform of the resample that will consume this plan
   float center[8];      // fp32 posterior mean: centring constants of the next moment sums
+  double center64[8];   // the same in double (f64 filters centre on the unrounded mean)
   double sw, sw2;       // sum w, sum w^2 at scale 2^emax
   double sx[PZ_MAX_NX], sxx[PZ_MAX_NX];  // centred first / second moment sums
 };
@@ -74,13 +80,14 @@ struct CtlDev {
   uint32_t scan_counter;  // dynamic tile ids of pf_scan_blocks
   uint32_t scan_done;     // "last CTA" counter of pf_scan_blocks
   uint32_t comm_error;    // sharded: a peer-memory wait timed out
-  uint32_t pad[3];
+  uint32_t ess_resampled; // adaptive resampling (generic path): 1 when the last step resampled
+  uint32_t pad[2];
 };
 
 struct ShardP2P;  // peer-memory exchange of a sharded filter (below)
 
 struct StepArgs {
-  float* X[2];
+  void* X[2];              // particle state [NX][ld] of float (f64 = 0) or double (f64 = 1), halo layout as Q
   uint16_t* Q[2];          // 16-bit weights of the two populations (same halo layout as X)
   int32_t* eb[2];
   uint64_t* sb;
@@ -96,6 +103,7 @@ struct StepArgs {
   PlanDev* plan;
   CtlDev* ctl;
   const float* obs;        // ring [kObsRing][PZ_MAX_NY]
+  const double* obs64;     // the same observations in double (f64 filters)
   pz_step_summary* summ;   // ring [kObsRing]
   int64_t ld;              // leading dimension of X (particles)
   int64_t n_local;         // particles on this rank (input and output)
@@ -112,9 +120,12 @@ struct StepArgs {
   uint64_t* shard_rec;     // sharded: [world][kShardRec] gathered {local_total, sw, sw2, sx[], sxx[], prefix at the margin edges}
   int64_t margin;          // sharded: halo margin in blocks exchanged with each neighbour every step
   const ShardP2P* p2p;     // sharded: peer-memory exchange (nullptr: NCCL collectives between the kernels)
+  int32_t f64;             // 1: state storage and model arithmetic in double (descriptor flag state_f64)
+  unsigned long long wait_ticks;  // sharded: clock64 ticks a peer-memory poll may take before the step is failed (0: no limit)
   LgDev model;
+  LgDevD modeld;           // the same parameters unrounded (used when f64)
 };
-constexpr int kShardRec = 18;
+constexpr int kShardRec = 19;  // word 18: comm_error of the sending rank (so that every rank reports a timeout)
 constexpr int kMaxRanks = 32;
 
 // Peer-memory exchange of a sharded filter (one process per GPU, buffers mapped with CUDA IPC over
@@ -133,7 +144,7 @@ struct Mailbox {
 };
 struct ShardP2P {
   Mailbox* mbox[kMaxRanks];   // mbox[q]: rank q's mailbox (mbox[rank] is local memory)
-  float* Xn[2][2];            // [side 0 = left neighbour, 1 = right][buffer]: its X (same halo layout as ours)
+  void* Xn[2][2];             // [side 0 = left neighbour, 1 = right][buffer]: its X (same halo layout as ours)
   uint16_t* Qn[2][2];
   int32_t* ebn[2][2];
   uint64_t* pbxn[2];
@@ -144,7 +155,7 @@ int launch_init(const StepArgs& a, cudaStream_t s);
 int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s);
 int launch_partition_only(const StepArgs& a, int tile_out, cudaStream_t s);  // a.tile_start / a.ntiles_out for another tile size
 int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s);  // step tile kernel + scan + partition
-int fused_tile_out(int nx);
+int fused_tile_out(int nx, int f64);
 // same as launch_step(a, nullptr, s) with an event recorded after each of the three kernels
 int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]);
 // sharded filter (one process per GPU): the step is split around the NCCL collectives
@@ -183,8 +194,8 @@ int launch_ctl_reset(CtlDev* ctl, cudaStream_t s);
 int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s);
 int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s);
 int launch_generic_multinomial(const GenericArgs& g, cudaStream_t s);
-int launch_logw(const StepArgs& a, float* lw_out, cudaStream_t s);  // log-weights of the pending population (parity tap)
-int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, float* out,
+int launch_logw(const StepArgs& a, float* lw_out32, double* lw_out64, cudaStream_t s);  // log-weights of the pending population (parity tap)
+int launch_gather_thin(const StepArgs& a, const int32_t* anc, int32_t stride, int64_t n_sel, double* out,
                        cudaStream_t s);
 constexpr int kGenericTileOut = 2048;
 int launch_stats_from_lw(const GenericArgs& g, cudaStream_t s);

@@ -47,6 +47,7 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, u
 }
 
 constexpr float kLog2e = 0x1.715476p+0f;
+constexpr double kLog2eD = 0x1.71547652b82fep+0;  // log2(e) rounded to double (f64 filters)
 constexpr int32_t kNZero = -(1 << 30);  // exponent marker of an empty block (every weight zero)
 constexpr int kGuard = 16;              // guard bits of the global fixed-point scale
 
@@ -80,9 +81,10 @@ __device__ __forceinline__ float block_exponent(float maxlw, int32_t& nb) {
 // Weight relative to 2^n_b and its fixed-point image: w = 2^d, d = max(lw * log2(e) - n_b, -32);
 // qbits = 0x4B000000 + rint(w * 2^15) (q <= 46990 sits in the low 16 bits).  CLAMP_HI adds the
 // upper clamp of the spec, unreachable when lw <= the block maximum and |n_b| < 2^18 (fused path).
+// weight_q_from_arg takes d0 = lw * log2(e) - n_b already rounded to fp32 (an f64 filter forms it in double).
 template <bool CLAMP_HI>
-__device__ __forceinline__ void weight_q(float lw, float nbf, float& w, uint32_t& qbits) {
-  float d = fmaxf(__fmaf_rn(lw, kLog2e, -nbf), -32.0f);
+__device__ __forceinline__ void weight_q_from_arg(float d0, float& w, uint32_t& qbits) {
+  float d = fmaxf(d0, -32.0f);
   if (CLAMP_HI) d = fminf(d, 1.0f);
   const float t = __fadd_rn(d, 12582912.0f);
   const float r = __fsub_rn(t, 12582912.0f);
@@ -95,6 +97,10 @@ __device__ __forceinline__ void weight_q(float lw, float nbf, float& w, uint32_t
   p = __fmaf_rn(p, f, 1.0f);
   w = __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
   qbits = __float_as_uint(__fmaf_rn(w, 32768.0f, 8388608.0f));
+}
+template <bool CLAMP_HI>
+__device__ __forceinline__ void weight_q(float lw, float nbf, float& w, uint32_t& qbits) {
+  weight_q_from_arg<CLAMP_HI>(__fmaf_rn(lw, kLog2e, -nbf), w, qbits);
 }
 
 // stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)

@@ -36,7 +36,7 @@ class MttParams(C.Structure):
 class ModelDesc(C.Structure):
     """pz_model_desc (include/pzgpu.h)."""
     _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
-                ("resampler", C.c_int32), ("delayed", C.c_int32), ("reserved", C.c_int32 * 2),
+                ("resampler", C.c_int32), ("delayed", C.c_int32), ("state_f64", C.c_int32), ("reserved", C.c_int32),
                 ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
                 ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
                 ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]
@@ -53,7 +53,7 @@ _SYMBOLS = [
     "pz_abi_version", "pz_last_error", "pz_model_rw1d", "pz_model_stt", "pz_model_mtt_track", "pz_model_mtt",
     "pz_filter_create", "pz_comm_unique_id", "pz_filter_create_sharded", "pz_filter_step", "pz_filter_run",
     "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_tracks", "pz_filter_read_ancestors", "pz_filter_read_state",
-    "pz_filter_read_logw", "pz_filter_read_posterior", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
+    "pz_filter_read_logw", "pz_filter_read_state_f64", "pz_filter_read_logw_f64", "pz_filter_read_posterior", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
     "pz_filter_destroy", "pz_shard_halo_range",
 ]
 
@@ -100,6 +100,8 @@ def lib():
     L.pz_filter_read_ancestors.argtypes = [C.c_void_p, i32p, C.c_int64]
     L.pz_filter_read_state.argtypes = [C.c_void_p, f32p, C.c_int64]
     L.pz_filter_read_logw.argtypes = [C.c_void_p, f32p, C.c_int64]
+    L.pz_filter_read_state_f64.argtypes = [C.c_void_p, f64p, C.c_int64]
+    L.pz_filter_read_logw_f64.argtypes = [C.c_void_p, f64p, C.c_int64]
     L.pz_filter_read_posterior.argtypes = [C.c_void_p, f64p, f64p]
     L.pz_filter_n_local.argtypes = [C.c_void_p]
     L.pz_filter_n_local.restype = C.c_int64
@@ -122,29 +124,30 @@ def _ptr(a, t):
 
 
 # ---- model descriptors (kernel-side plugin surface) -------------------------------------------
-def rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=True, resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False):
+def rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=True, resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False):
     """1-D Gaussian random walk + noisy observation: kalman1DObserved, Examples/Demo.hs:184-198
-    (delay=True: kalman1DObservedDelayed, Demo.hs:215-242)."""
+    (delay=True: kalman1DObservedDelayed, Demo.hs:215-242).  f64=True: state and arithmetic in double, the
+    reference's own precision (Inference.hs:28)."""
     d = ModelDesc()
     _check(lib().pz_model_rw1d(C.byref(d), q_var, r_var))
-    d.scalar_ll_2x, d.resampler, d.delayed = int(scalar_ll_2x), resampler, int(delay)
+    d.scalar_ll_2x, d.resampler, d.delayed, d.state_f64 = int(scalar_ll_2x), resampler, int(delay), int(f64)
     return d
 
 
-def stt(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False):
+def stt(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False):
     """Single-target tracker: Examples/SingleTargetTracking.hs:28-54.  delay=False is the bootstrap filter,
     delay=True the delayed-sampling stream in which every particle carries the exact Kalman marginal."""
     d = ModelDesc()
     _check(lib().pz_model_stt(C.byref(d)))
-    d.resampler, d.delayed = resampler, int(delay)
+    d.resampler, d.delayed, d.state_f64 = resampler, int(delay), int(f64)
     return d
 
 
-def mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False):
+def mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False):
     """2-D position/velocity track model of the multi-target tracker: MultiTargetTracking.hs:56-73."""
     d = ModelDesc()
     _check(lib().pz_model_mtt_track(C.byref(d)))
-    d.resampler, d.delayed = resampler, int(delay)
+    d.resampler, d.delayed, d.state_f64 = resampler, int(delay), int(f64)
     return d
 
 
@@ -202,7 +205,7 @@ class ZStream:
             rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double) if y.size else None, y.size // 2, 2, C.byref(s))
         else:
             rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double), 1, y.size, C.byref(s))
-        if rc == 0 or rc == -4:
+        if rc in (0, -3, -4, -5):   # the library advanced its step for every one of these codes
             self.t += 1
         _check(rc)
         return Posterior(self, s)
@@ -251,6 +254,11 @@ class ZStream:
         return out
 
     def read_state(self):
+        """Pre-resample population, SoA [nx, n], in the filter's storage type."""
+        if self.model.state_f64:
+            out = np.zeros((self.nx, self.n), dtype=np.float64)
+            _check(lib().pz_filter_read_state_f64(self._h, _ptr(out, C.c_double), out.size))
+            return out
         out = np.zeros((self.nx, self.n), dtype=np.float32)
         _check(lib().pz_filter_read_state(self._h, _ptr(out, C.c_float), out.size))
         return out
@@ -262,6 +270,10 @@ class ZStream:
         return mean, cov
 
     def read_logw(self):
+        if self.model.state_f64:
+            out = np.zeros(self.n, dtype=np.float64)
+            _check(lib().pz_filter_read_logw_f64(self._h, _ptr(out, C.c_double), out.size))
+            return out
         out = np.zeros(self.n, dtype=np.float32)
         _check(lib().pz_filter_read_logw(self._h, _ptr(out, C.c_float), out.size))
         return out

@@ -28,7 +28,7 @@ class MttParams(C.Structure):
 
 class ModelDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
-                ("resampler", C.c_int32), ("delayed", C.c_int32), ("reserved", C.c_int32 * 2),
+                ("resampler", C.c_int32), ("delayed", C.c_int32), ("state_f64", C.c_int32), ("reserved", C.c_int32),
                 ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
                 ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
                 ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]
@@ -40,11 +40,11 @@ class StepSummary(C.Structure):
                 ("e_max", C.c_int32), ("reserved", C.c_int32), ("total_weight", C.c_uint64)]
 
 
-def _fill(desc, kind, F, Q, H, R, x0=None, scalar_ll_2x=1, resampler=PZ_RESAMPLE_SYSTEMATIC):
+def _fill(desc, kind, F, Q, H, R, x0=None, scalar_ll_2x=1, resampler=PZ_RESAMPLE_SYSTEMATIC, f64=False):
     F, Q, H, R = (np.atleast_2d(np.asarray(a, dtype=np.float64)) for a in (F, Q, H, R))
     nx, ny = F.shape[0], H.shape[0]
     desc.kind, desc.nx, desc.ny = kind, nx, ny
-    desc.scalar_ll_2x, desc.resampler = scalar_ll_2x, resampler
+    desc.scalar_ll_2x, desc.resampler, desc.state_f64 = scalar_ll_2x, resampler, int(f64)
     for name, a in (("F", F), ("Q", Q), ("H", H), ("R", R)):
         flat = a.reshape(-1)
         arr = getattr(desc, name)
@@ -56,28 +56,28 @@ def _fill(desc, kind, F, Q, H, R, x0=None, scalar_ll_2x=1, resampler=PZ_RESAMPLE
     return desc
 
 
-def model_rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=1, resampler=PZ_RESAMPLE_SYSTEMATIC):
+def model_rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=1, resampler=PZ_RESAMPLE_SYSTEMATIC, f64=False):
     """noisyIntegrateGen + observe (normal x 3): Examples/Demo.hs:184-198 (x0 = 0, var 1, obs var 3)."""
     return _fill(ModelDesc(), PZ_MODEL_RW1D, [[1.0]], [[q_var]], [[1.0]], [[r_var]],
-                 scalar_ll_2x=scalar_ll_2x, resampler=resampler)
+                 scalar_ll_2x=scalar_ll_2x, resampler=resampler, f64=f64)
 
 
-def model_stt(resampler=PZ_RESAMPLE_SYSTEMATIC):
+def model_stt(resampler=PZ_RESAMPLE_SYSTEMATIC, f64=False):
     """Examples/SingleTargetTracking.hs:39-54: R^6 constant-velocity, tdiff=1, obs cov 10 I3."""
     I3, Z3 = np.eye(3), np.zeros((3, 3))
     F = np.block([[I3, I3], [Z3, I3]])
     Q = np.block([[0.01 * I3, Z3], [Z3, 0.1 * I3]])
     H = np.block([I3, Z3])
-    return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, 10.0 * I3, resampler=resampler)
+    return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, 10.0 * I3, resampler=resampler, f64=f64)
 
 
-def model_mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC):
+def model_mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, f64=False):
     """Examples/MultiTargetTracking.hs:56-73: R^4 damped position/velocity track, obs cov I2."""
     I2, Z2 = np.eye(2), np.zeros((2, 2))
     F = np.eye(4) + np.block([[Z2, I2], [-0.01 * I2, -0.1 * I2]])
     Q = np.block([[0.01 * I2, Z2], [Z2, 0.1 * I2]])
     H = np.block([I2, Z2])
-    return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, I2, resampler=resampler)
+    return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, I2, resampler=resampler, f64=f64)
 
 
 def model_mtt():
@@ -143,6 +143,7 @@ def oracle():
     lib.pzo_filter_destroy.argtypes = [C.c_void_p]
     lib.pzo_filter_step.argtypes = [C.c_void_p, f64p, C.POINTER(StepSummary)]
     lib.pzo_filter_state.argtypes = [C.c_void_p, f32p, f32p, i32p]
+    lib.pzo_filter_state_f64.argtypes = [C.c_void_p, f64p, f64p, i32p]
     lib.pzo_filter_block_stats.argtypes = [C.c_void_p, i32p, u64p, i32p, u64p]
     lib.pzo_filter_derived.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, f32p, f64p]
     lib.pzo_kalman_step.argtypes = [C.POINTER(ModelDesc), f64p, f64p, f64p, f64p]
@@ -209,9 +210,15 @@ class OracleFilter:
         return rc, s
 
     def state(self):
+        """(x [nx, n], log-weights, ancestors) in the filter's storage type (float32, or float64 for state_f64)."""
+        anc = np.zeros(self.n, dtype=np.int32)
+        if self.desc.state_f64:
+            x = np.zeros((self.nx, self.n), dtype=np.float64)
+            lw = np.zeros(self.n, dtype=np.float64)
+            self.lib.pzo_filter_state_f64(self.h, ptr(x, C.c_double), ptr(lw, C.c_double), ptr(anc, C.c_int32))
+            return x, lw, anc
         x = np.zeros((self.nx, self.n), dtype=np.float32)
         lw = np.zeros(self.n, dtype=np.float32)
-        anc = np.zeros(self.n, dtype=np.int32)
         self.lib.pzo_filter_state(self.h, ptr(x, C.c_float), ptr(lw, C.c_float), ptr(anc, C.c_int32))
         return x, lw, anc
 

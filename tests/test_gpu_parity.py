@@ -71,13 +71,19 @@ def test_resample_multinomial_bit_exact(pz, n):
 MODELS = {"rw1d": (H.model_rw1d, "rw1d"), "lg42": (H.model_mtt_track, "mtt_track"), "lg63": (H.model_stt, "stt")}
 
 
+def bits(a):
+    """Bit pattern of a float32 / float64 array (bit-exact comparisons)."""
+    return a.view(np.uint64 if a.dtype == np.float64 else np.uint32)
+
+
+@pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
 @pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
 @pytest.mark.parametrize("n", [1, 300, 4096, 10007, 200000])
-def test_filter_trajectory_bit_exact(pz, model, n):
-    """Whole-filter parity: after every step the fp32 population, the fixed-point total and
-    the global exponent equal the oracle's bit for bit; summaries agree to 1e-9."""
-    hd = MODELS[model][0]()
-    d = getattr(pz, MODELS[model][1])()
+def test_filter_trajectory_bit_exact(pz, model, n, f64):
+    """Whole-filter parity: after every step the population (fp32, or double for state_f64 filters), the
+    fixed-point total and the global exponent equal the oracle's bit for bit; summaries agree to 1e-9."""
+    hd = MODELS[model][0](f64=f64)
+    d = getattr(pz, MODELS[model][1])(f64=f64)
     T = 8
     obs, _ = H.gen_obs(hd, T)
     zs = pz.zparticles(n, d, seed=4242)
@@ -93,8 +99,9 @@ def test_filter_trajectory_bit_exact(pz, model, n):
         if t in (0, 3):
             assert np.array_equal(anc_gpu, anc_ref), (model, n, t)
         x = zs.read_state()
-        assert np.array_equal(x.view(np.uint32), x_ref.view(np.uint32)), (model, n, t)
-        assert np.array_equal(zs.read_logw().view(np.uint32), lw_ref.view(np.uint32))
+        assert x.dtype == x_ref.dtype == (np.float64 if f64 else np.float32)
+        assert np.array_equal(bits(x), bits(x_ref)), (model, n, t)
+        assert np.array_equal(bits(zs.read_logw()), bits(lw_ref))
         assert post.total_weight == s.total_weight and post.e_max == s.e_max and post.step == t
         nx = hd.nx
         # summaries are floating reductions (fp32 per-lane partials, fp64 above): tolerance, not bits
@@ -105,13 +112,14 @@ def test_filter_trajectory_bit_exact(pz, model, n):
     zs.close(); orc.close()
 
 
+@pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
 @pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
-def test_filter_outlier_observations_bit_exact(pz, model):
+def test_filter_outlier_observations_bit_exact(pz, model, f64):
     """Observations far in the tails collapse the weights onto a handful of particles: runs of thousands
     of children (the long-run duplicates and the segment look-back of the step kernel), empty blocks,
     shifts outside the fast range of the slot map.  Still bit-exact against the oracle."""
-    hd = MODELS[model][0]()
-    d = getattr(pz, MODELS[model][1])()
+    hd = MODELS[model][0](f64=f64)
+    d = getattr(pz, MODELS[model][1])(f64=f64)
     n = 60000 + 123
     obs, _ = H.gen_obs(hd, 10)
     obs = obs.copy()
@@ -125,7 +133,7 @@ def test_filter_outlier_observations_bit_exact(pz, model):
         assert rc == 0
         x_ref, _, anc_ref = orc.state()
         max_run = max(max_run, int(np.bincount(anc_ref).max()))
-        assert np.array_equal(zs.read_state().view(np.uint32), x_ref.view(np.uint32)), (model, t)
+        assert np.array_equal(bits(zs.read_state()), bits(x_ref)), (model, t)
         assert post.total_weight == s.total_weight and post.e_max == s.e_max
         assert abs(post.ess - s.ess) < 1e-4 * s.ess + 1e-6
     assert max_run > 300   # the scenario really produced long runs
@@ -145,15 +153,16 @@ def test_filter_golden_fixture(pz):
         zs.close()
 
 
-def test_run_equals_step(pz):
+@pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
+def test_run_equals_step(pz, f64):
     """runStream over a staged observation array == repeated ZStream.step (bitwise)."""
-    d = pz.rw1d()
+    d = pz.rw1d(f64=f64)
     obs, _ = H.gen_obs(H.model_rw1d(), 40)
     a = pz.zparticles(50000, d, seed=9)
     b = pz.zparticles(50000, d, seed=9)
     pa = [a.step(y) for y in obs]
     pb = b.run(obs)
-    assert np.array_equal(a.read_state().view(np.uint32), b.read_state().view(np.uint32))
+    assert np.array_equal(bits(a.read_state()), bits(b.read_state()))
     for x, y in zip(pa, pb):
         assert x.total_weight == y.total_weight and x.mean[0] == y.mean[0] and x.step == y.step  # same kernels: bitwise
     ms, launches = b.last_timing()
@@ -172,12 +181,12 @@ def test_reproducible_and_seed_sensitive(pz):
     assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
 
 
-@pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
-def test_posterior_matches_kalman(pz, model):
+@pytest.mark.parametrize("model,f64", [("rw1d", False), ("lg42", False), ("lg63", False), ("rw1d", True), ("lg63", True)])
+def test_posterior_matches_kalman(pz, model, f64):
     """Posterior mean / variance within 3 SE of the exact Kalman filter over 20 seeds at
     N = 10^5 (BASELINE.md section 5 gate 2); also the log-evidence for the properly normalised scores."""
-    hd = MODELS[model][0]()
-    d = getattr(pz, MODELS[model][1])()
+    hd = MODELS[model][0](f64=f64)
+    d = getattr(pz, MODELS[model][1])(f64=f64)
     T, n, seeds = 30, 100000, 20
     obs, _ = H.gen_obs(hd, T)
     km, kc, kl = H.kalman(hd, obs)
@@ -349,8 +358,9 @@ def test_large_n_properties(pz):
     assert np.array_equal(zs2.read_ancestors(), anc)
 
 
+@pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
 @pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
-def test_independent_of_tile_size_and_specialisation(pz, model):
+def test_independent_of_tile_size_and_specialisation(pz, model, f64):
     """Launch-shape independence: the small / large output-tile instantiations and the dense /
     position-velocity specialised model code give the same bits (separate processes: the choice is
     read once from the environment)."""
@@ -364,10 +374,10 @@ def test_independent_of_tile_size_and_specialisation(pz, model):
         "pz = g.load_package()\n"
         "hd = {'rw1d': H.model_rw1d, 'mtt_track': H.model_mtt_track, 'stt': H.model_stt}[%r]()\n"
         "obs, _ = H.gen_obs(hd, 5)\n"
-        "zs = pz.zparticles(50000 + 77, getattr(pz, %r)(), seed=31)\n"
+        "zs = pz.zparticles(50000 + 77, getattr(pz, %r)(f64=%r), seed=31)\n"
         "posts = zs.run(obs)\n"
         "print(hashlib.sha256(zs.read_state().tobytes()).hexdigest(), posts[-1].total_weight)\n"
-    ) % (H.ROOT, H.ROOT + "/tests", model, model)
+    ) % (H.ROOT, H.ROOT + "/tests", model, model, f64)
     outs = set()
     for env in ({}, {"PZ_TILE_OUT": "small"}, {"PZ_NO_KRON": "1"}, {"PZ_TILE_OUT": "small", "PZ_NO_KRON": "1"}):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={**__import__("os").environ, **env})
