@@ -5,14 +5,20 @@
     python bench.py --impl reference --gpus N --steps K ...  (CPU port of the reference path)
 
 A "step" is one pass of the hot path (resample + gather + propagate + weight + normalise,
-zparticles', haskell/src/Inference.hs:101-104) over all N_p particles.  Workload at 1 GPU:
-BASELINE.json configs[1], the 1-D Gaussian random-walk model at N_p = 10^8 on one B200.
+zparticles', haskell/src/Inference.hs:101-104) over all N_p particles.  Headline workload at 1 GPU:
+BASELINE.json configs[1], the 1-D Gaussian random-walk model at N_p = 10^8 on one B200, state and
+arithmetic in double (the reference's precision, Inference.hs:28; `--dtype f32` selects fp32 state).
 
 value : N_p * K / (device time of K back-to-back steps), observations resident in HBM.
 e2e   : the same through the public API with HOST observation buffers, one ZStream.step
         per observation (pinned H2D of the observation + D2H of the posterior summary + sync
         inside the timed region).
 roofline / cpu_baseline: see DESIGN.md "Measurement".
+legs  : (1 GPU, default run) the other single-GPU configurations in the same JSON line: the fp32 variant
+        of the headline, configs[2] (LG(4,2) and LG(6,3), N = 10^7, both storage types), configs[3]
+        (multi-target tracker, N = 10^6) and a sustained leg (10^3 steps with clocks and power).
+sharded_parity : (N > 1) before timing, the live ranks run a small sharded filter next to a single-GPU
+        filter of the same population on rank 0 and compare state bits, totals and exponents.
 
 The CPU oracle (oracle/) is executed only by the cpu_baseline leg and by --impl reference.
 """
@@ -32,18 +38,19 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 MODELS = {"rw1d": (1, 1), "lg42": (4, 2), "lg63": (6, 3), "mtt": (4, 2)}
+HEADLINE_PARTICLES = 100_000_000
 
 
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons sampled DURING the timed region: NVML (about 1 ms per sample) when
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML (about 1 ms per sample) when
     nvidia_ml_py is importable, else nvidia-smi (about 50 ms per sample)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -51,7 +58,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, threading.Event()
-        self.sm, self.sm_max, self.reasons, self.source = [], None, set(), "nvidia-smi"
+        self.sm, self.pw, self.sm_max, self.reasons, self.source = [], [], None, set(), "nvidia-smi"
         self.h = None
         try:
             import pynvml
@@ -66,6 +73,10 @@ class ClockSampler(threading.Thread):
     def _sample_nvml(self):
         nv = self.nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
         r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
             else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
@@ -81,6 +92,10 @@ class ClockSampler(threading.Thread):
         if r[0].replace(".", "").isdigit():
             self.sm.append(float(r[0]))
         self.sm_max = float(r[1])
+        try:
+            self.pw.append(float(r[2]))
+        except ValueError:
+            pass
         for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
             if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
                 self.reasons.add(name)
@@ -99,19 +114,24 @@ class ClockSampler(threading.Thread):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["clock sampling unavailable"], "samples": 0}
         sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm),
-                "source": self.source}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+               "samples": len(sm), "source": self.source}
+        if self.pw:
+            out["power_w_median"] = sorted(self.pw)[len(self.pw) // 2]
+            out["power_w_max"] = max(self.pw)
+        return out
 
 
-def ncu_traffic(name, n_p):
-    """dram__bytes_read + dram__bytes_write of one pf_step_tile launch from the committed ncu capture
-    (profiles/traffic.json, written by tools/ncu_buckets.py) when it was taken at this N; else None."""
+def ncu_traffic(name, dtype, n_p):
+    """dram__bytes_read + dram__bytes_write of one pf_step_tile launch from the committed ncu capture of this
+    model / dtype (profiles/traffic.json, written by tools/ncu_buckets.py) when it was taken at this N; else None.
+    Not measured in this run: the source is named in roofline.traffic_source."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            t = json.load(fh).get(name)
-        return float(t["dram_bytes"]) if t and int(t["particles"]) == int(n_p) else None
+            t = json.load(fh).get(f"{name}_{dtype}")
+        return (float(t["dram_bytes"]), t.get("report")) if t and int(t["particles"]) == int(n_p) else (None, None)
     except Exception:
-        return None
+        return None, None
 
 
 def synth_obs(d, T, seed=0x0B5E2026):
@@ -139,13 +159,31 @@ def helper_desc(H, name):
     return {"rw1d": H.model_rw1d, "lg42": H.model_mtt_track, "lg63": H.model_stt}[name]()
 
 
+def make_config(args):
+    """The workload description shared verbatim by both arms (the driver compares them)."""
+    nx, ny = MODELS[args.model]
+    n_p = args.total_particles // max(args.gpus, 1) if args.total_particles else args.particles
+    esz = 8 if args.dtype == "f64" else 4
+    return {
+        "workload": f"{args.model} bootstrap particle filter, N={n_p} particles per GPU x {args.gpus} GPU(s), "
+                    f"one observation per step (BASELINE.json configs[1]; configs[4] when sharded)",
+        "model": args.model, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny,
+        "state_storage": "fp64" if args.dtype == "f64" else "fp32",
+        "weights": "u16 fixed point per particle, u64 block prefix", "resampler": "systematic (canonical PZ-SYS-256/q16)",
+        "l2": "inputs exceed L2 (state %.0f MB per buffer); no flush needed" % (nx * esz * n_p / 1e6),
+        "reference_arm": "`--impl reference` times the CPU port of the reference algorithm (double, multinomial resample2) "
+                         "on a BOUNDED SAMPLE of this workload: the same model and stream at the N stated in its "
+                         "cpu_baseline.sample, sized so that its K + W steps take about a minute on the host cores",
+    }
+
+
 def cpu_port_rate(H, name, n_sample, steps, threads, faithful=False, optimised=False):
     """particle-updates/s of the CPU port.  faithful=False: the reference's algorithm (double,
     log-domain normalise, multinomial draws) with the O(N) per-draw CDF walk replaced by a binary
-    search (identical ancestors) and OpenMP over particles; faithful=True: the literal O(N^2) walk,
-    one thread; optimised=True: SURVEY.md 8(d)(ii), not the reference's algorithm but the best a host
-    does with the same step (max-shifted weights, one O(N) systematic resample over a parallel prefix
-    sum, every loop over all cores)."""
+    search and every loop (fold, CDF build, draws, gather) chunked over the cores with OpenMP;
+    faithful=True: the literal O(N^2) walk, one thread; optimised=True: SURVEY.md 8(d)(ii), not the
+    reference's algorithm but the best a host does with the same step (max-shifted weights, one O(N)
+    systematic resample over a parallel prefix sum)."""
     lib = H.oracle()
     d = helper_desc(H, name)
     obs, _ = H.gen_obs(d, steps)
@@ -158,29 +196,35 @@ def cpu_port_rate(H, name, n_sample, steps, threads, faithful=False, optimised=F
 
 
 def run_reference(args):
-    """--impl reference: the CPU port of the reference's path on the host cores."""
+    """--impl reference: the CPU port of the reference's path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import pzhelpers as H
     threads = os.cpu_count() or 1
-    n_sample = min(args.particles, args.cpu_particles)
     K, W = args.steps, args.warmup
-    cpu_port_rate(H, args.model, n_sample, max(1, min(W, 2)), threads)  # warm-up
+    n_full = make_config(args)["particles_per_gpu"]
+    # size the sample so that K + W steps take about 40 s: calibrate on two steps at 10^6 particles
+    n_cal = min(n_full, 1_000_000)
+    cpu_port_rate(H, args.model, n_cal, 1, threads)
+    rate_cal, _ = cpu_port_rate(H, args.model, n_cal, 2, threads)
+    n_sample = int(min(n_full, max(100_000, rate_cal * 40.0 / (K + W))))
+    if args.cpu_particles:
+        n_sample = min(n_full, args.cpu_particles)
+    cpu_port_rate(H, args.model, n_sample, max(1, W), threads)  # W warm-up steps
     rate, dt = cpu_port_rate(H, args.model, n_sample, K, threads)
     orate, odt = cpu_port_rate(H, args.model, n_sample, K, threads, optimised=True)
-    nx, _ = MODELS[args.model]
     line = {
         "impl": "reference", "metric": "particle-updates/sec", "value": rate, "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.model} bootstrap particle filter, N={args.particles} per GPU (configs[1])",
-                   "model": args.model, "particles_per_gpu": args.particles, "state_dim": nx},
+        "scaling": "strong" if args.total_particles else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": make_config(args),
+        "sample": {"particles": n_sample, "steps": K, "of_particles_per_gpu": n_full},
         "cpu_baseline": {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": "port",
-                         "sample": f"N={n_sample} particles x {K} steps of the same model; reference algorithm "
+                         "sample": f"N={n_sample} particles (of the workload's {n_full}) x {K} steps of the same model and stream; reference algorithm "
                                    "(Inference.hs:57-66,101-104: double, logaddexp normalise, multinomial resample2) "
-                                   "with the O(N) per-draw CDF walk replaced by a binary search and OpenMP over particles; "
-                                   "the literal O(N^2) reference cannot finish one step at this N",
+                                   "with the O(N) per-draw CDF walk replaced by a binary search; fold, CDF build, draws and gather "
+                                   "chunked over all cores with OpenMP; the literal O(N^2) reference cannot finish one step at this N",
                          "optimised_systematic": {"value": orate, "cores": threads,
                                                   "sample": f"same sample; not the reference's algorithm: max-shifted weights, O(N) systematic "
                                                             f"resampling over a parallel prefix sum, all loops over all cores ({odt:.1f} s)"}},
@@ -225,21 +269,13 @@ def synth_mtt_scenario(d, T, seed=5, m_max=32, warm_tracks=0):
     return out
 
 
-def run_mtt(args):
+def measure_mtt(pz, n_p, K, W, tracks, with_cpu):
     """configs[3]: the multi-target tracker (N = 10^6, up to 16 tracks), detections streamed step by step."""
     import torch
-    import __graft_entry__ as g
-    import pzhelpers as H
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback")
-    pz = g.load_package()
-    n_p, K, W = args.particles, args.steps, args.warmup
-    d = H.model_mtt()
-    obs = synth_mtt_scenario(pz.mtt(), W + K, seed=5, warm_tracks=args.mtt_tracks)
+    obs = synth_mtt_scenario(pz.mtt(), W + K, seed=5, warm_tracks=tracks)
     zs = pz.zparticles(n_p, pz.mtt(), seed=1)
     for o in obs[:W]:
         zs.step(o)
-    sampler = ClockSampler(0); sampler.start()
     torch.cuda.synchronize()
     dev_ms, launches, bytes_alg = 0.0, 0, 0.0
     t0 = time.perf_counter()
@@ -250,33 +286,123 @@ def run_mtt(args):
         bytes_alg += 2.0 * n_p * (16 + 64 * post.mean[0])  # header + live track records, read + written
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    clocks = sampler.summary()
+    zs.close()
     peak, peak_src = measured_peak()
     achieved = bytes_alg / (dev_ms * 1e-3) / 1e9
-    lib = H.oracle()
-    n_cpu = 2000
-    orc = H.OracleMtt(d, n_cpu, 1)
-    t0 = time.perf_counter()
-    for o in obs[: W + K]:
-        orc.step(o)
-    cpu_dt = time.perf_counter() - t0
-    line = {
-        "metric": "particle-updates/sec", "value": n_p * K / (dev_ms * 1e-3), "unit": "particle-updates/s", "n_gpus": 1,
-        "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"multi-target tracker (MultiTargetTracking.hs), N={n_p} particles, up to 16 Rao-Blackwellised tracks (BASELINE.json configs[3])",
-                   "model": "mtt", "particles_per_gpu": n_p, "mean_tracks_last_step": float(post.mean[0]),
-                   "l2": "particle records exceed L2 (1040 B per particle)"},
+    out = {
+        "value": n_p * K / (dev_ms * 1e-3), "unit": "particle-updates/s", "ms_per_step": dev_ms / K, "dtype": "f32",
+        "workload": f"multi-target tracker (MultiTargetTracking.hs), N={n_p} particles, up to 16 Rao-Blackwellised tracks (BASELINE.json configs[3])",
+        "mean_tracks_last_step": float(post.mean[0]), "steps": K,
         "e2e": {"value": n_p * K / wall, "unit": "particle-updates/s", "h2d_bytes_per_step": 8 * int(np.mean([len(o) for o in obs[W:]])),
                 "d2h_bytes_per_step": 144, "ms_per_step": wall / K * 1e3},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "mtt_step (+ resample kernels)", "peak_source": peak_src, "alg_bytes_per_launch": bytes_alg / K,
-                     "kernel_ms": dev_ms / K, "kernel_ms_source": "whole step, device events"},
-        "cpu_baseline": {"value": n_cpu * (W + K) / cpu_dt, "unit": "particle-updates/s", "cores": 1, "kind": "port",
-                         "sample": f"N={n_cpu} x {W + K} steps of the same detection stream, oracle restatement in double, 1 thread ({cpu_dt:.1f} s)"},
+                     "kernel_ms": dev_ms / K, "kernel_ms_source": "whole step, device events",
+                     "alg_bytes_definition": "live track records (64 B each) + 16 B header per particle, read once and written once"},
     }
-    print(json.dumps(line), flush=True)
+    if with_cpu:
+        import pzhelpers as H
+        n_cpu = 2000
+        orc = H.OracleMtt(H.model_mtt(), n_cpu, 1)
+        t0 = time.perf_counter()
+        for o in obs[: W + K]:
+            orc.step(o)
+        cpu_dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu * (W + K) / cpu_dt, "unit": "particle-updates/s", "cores": 1, "kind": "port",
+                               "sample": f"N={n_cpu} x {W + K} steps of the same detection stream, oracle restatement in double, 1 thread ({cpu_dt:.1f} s)"}
+    return out
+
+
+def measure_lg(pz, name, dtype, n_p, K, W, device=0, profile=True, sustained=0):
+    """One single-GPU leg: device-resident K steps, end-to-end K steps, per-kernel events."""
+    import torch
+    nx, ny = MODELS[name]
+    esz = 8 if dtype == "f64" else 4
+    d = model_desc(pz, name, dtype == "f64")
+    obs = synth_obs(d, W + 2 * K + 16 + sustained)
+    zs = pz.zparticles(n_p, d, seed=1, device=device)
+    zs.run(obs[:W], want_summaries=False)
+    torch.cuda.synchronize()
+    zs.run(obs[W:W + K], want_summaries=False)
+    torch.cuda.synchronize()
+    dev_ms, launches = zs.last_timing()
+    off = W + K
+    for i in range(3):
+        zs.step(obs[off + i])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        zs.step(obs[off + 3 + i])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    out = {"value": n_p * K / (dev_ms * 1e-3), "unit": "particle-updates/s", "ms_per_step": dev_ms / K, "dtype": dtype, "steps": K,
+           "workload": f"{name} bootstrap particle filter, N={n_p}, state {'fp64' if esz == 8 else 'fp32'}",
+           "e2e": {"value": n_p * K / e2e_s, "unit": "particle-updates/s", "h2d_bytes_per_step": 8 * ny, "d2h_bytes_per_step": 144,
+                   "ms_per_step": e2e_s / K * 1e3},
+           "gpu_launches": int(launches)}
+    if profile:
+        prof = np.array([zs.step_profile(obs[off + 3 + K + i]) for i in range(10)])
+        peak, peak_src = measured_peak()
+        t_tile = float(np.mean(prof[:, 0]))
+        alg = 2.0 * nx * esz * n_p
+        tr, rep = ncu_traffic(name, dtype, n_p)
+        out["roofline"] = {"bound": "hbm", "achieved": alg / (t_tile * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": alg / (t_tile * 1e-3) / 1e9 / peak, "traffic": tr,
+                           "traffic_source": f"ncu capture of one launch at this N, committed under profiles/ ({rep}); not measured in this run" if tr else None,
+                           "kernel": "pf_step_tile", "alg_bytes_per_launch": alg, "kernel_ms": t_tile,
+                           "step_kernels_ms": {"pf_step_tile": t_tile, "pf_scan_blocks": float(np.mean(prof[:, 1])),
+                                               "pf_partition": float(np.mean(prof[:, 2]))}}
+    if sustained:
+        # the configs[1] stream length: 10^3 back-to-back steps, clocks and power sampled during the run
+        so = obs[-sustained:]
+        sampler = ClockSampler(device); sampler.start()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        zs.run(so, want_summaries=False)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms, _ = zs.last_timing()
+        out["sustained"] = {"steps": sustained, "value": n_p * sustained / (ms * 1e-3), "ms_per_step": ms / sustained,
+                            "wall_s": wall, "clocks": sampler.summary()}
+    zs.close()
+    return out
+
+
+def sharded_parity(pz, dist, torch, rank, world, local_rank, nccl_id_fn):
+    """Bit-equality of the sharded filter with the single-GPU filter on the LIVE ranks: world * 256 * 101 particles,
+    6 steps, rw1d and lg42 (fp32) plus rw1d in double; rank 0 runs the single-GPU filter, the shards are all-gathered."""
+    out = {}
+    n = world * 256 * 101
+    for name, dtype in (("rw1d", "f32"), ("lg42", "f32"), ("rw1d", "f64")):
+        d = model_desc(pz, name, dtype == "f64")
+        obs = synth_obs(d, 6, seed=77)
+        zs = pz.zparticles_sharded(n, d, nccl_id_fn(), rank, world, seed=4242, device=local_rank)
+        ref = pz.zparticles(n, d, seed=4242, device=local_rank) if rank == 0 else None
+        verdict = "bit-exact"
+        bt = np.uint64 if dtype == "f64" else np.uint32
+        for t in range(6):
+            post = zs.step(obs[t])
+            mine = torch.from_numpy(zs.read_state().copy()).to(f"cuda:{local_rank}")
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            if rank == 0 and verdict == "bit-exact":
+                pr = ref.step(obs[t])
+                full = torch.cat(parts, dim=1).cpu().numpy()
+                same = np.array_equal(np.ascontiguousarray(full).view(bt), ref.read_state().view(bt))
+                same = same and post.total_weight == pr.total_weight and post.e_max == pr.e_max
+                if not same:
+                    verdict = f"MISMATCH at step {t}"
+        flag = torch.tensor([1 if verdict == "bit-exact" else 0], device=f"cuda:{local_rank}")
+        dist.broadcast(flag, 0)
+        zs.close()
+        if ref is not None:
+            ref.close()
+        dist.barrier()
+        out[f"{name}_{dtype}"] = verdict if rank == 0 else ("bit-exact" if int(flag.item()) else "MISMATCH")
+    out["particles"] = n
+    out["steps"] = 6
+    return out
 
 
 def run_b200(args):
@@ -294,23 +420,29 @@ def run_b200(args):
     pz = g.load_package()
     name = args.model
     nx, ny = MODELS[name]
-    n_p = args.particles
-    scaling = "weak"
-    if args.total_particles:
-        n_p, scaling = args.total_particles // world, "strong"
+    cfg = make_config(args)
+    n_p = cfg["particles_per_gpu"]
+    scaling = "strong" if args.total_particles else "weak"
     if world > 1:
         n_p -= n_p % 256  # a sharded filter holds whole resampling blocks (256 particles) per rank
     K, W = args.steps, args.warmup
     f64 = args.dtype == "f64"
     esz = 8 if f64 else 4
     d = model_desc(pz, name, f64)
-    obs = synth_obs(d, W + K + 2 * K + 8)
-    if world > 1:
+    obs = synth_obs(d, W + K + 2 * K + 16)
+
+    def nccl_id():
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(pz.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        zs = pz.zparticles_sharded(n_p * world, d, bytes(idt.cpu().numpy().tobytes()), rank, world, seed=1, device=local_rank)
+        return bytes(idt.cpu().numpy().tobytes())
+
+    parity = None
+    if world > 1:
+        if not args.no_parity:
+            parity = sharded_parity(pz, dist, torch, rank, world, local_rank, nccl_id)
+        zs = pz.zparticles_sharded(n_p * world, d, nccl_id(), rank, world, seed=1, device=local_rank)
     else:
         zs = pz.zparticles(n_p, d, seed=1, device=local_rank)
 
@@ -356,17 +488,17 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (fused resample+propagate+weight), CUDA events on its stream
     if world == 1:
-        prof = np.array([zs.step_profile(obs[off + 3 + K + i]) for i in range(min(K, 10))])
+        prof = np.array([zs.step_profile(obs[off + 3 + K + i]) for i in range(10)])
         kernel_src = "CUDA events around pf_step_tile on its stream (10 steps outside the graph)"
-    else:  # sharded: the step is interleaved with NCCL calls; bound the kernel by the whole step
+    else:  # sharded: the step kernel is interleaved with the exchange kernels; bound the kernel by the whole step
         prof = np.array([[dev_ms / K, float("nan"), float("nan")]])
-        kernel_src = "whole step (kernel + collectives), device events"
+        kernel_src = "whole step (kernel + exchange), device events"
     t_tile_ms = float(np.mean(prof[:, 0]))
     alg_bytes = 2.0 * nx * esz * n_p  # read the state once, write it once; the kernel also moves 4 B of u16 weights
     achieved = alg_bytes / (t_tile_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
-    # every rank tears its shard down together (NCCL communicator), then rank 0 reports
+    # every rank tears its shard down together, then rank 0 reports
     n_migrated = int(post.n_migrated)
     if world > 1:
         mt = torch.tensor([n_migrated], device="cuda", dtype=torch.int64)
@@ -379,46 +511,85 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+
+    # ---- the other single-GPU configurations (default run only): fp32 twin, configs[2], configs[3], sustained
+    legs = None
+    if world == 1 and not args.no_legs and name == "rw1d" and n_p == HEADLINE_PARTICLES:
+        legs = {}
+        kl = min(K, 20)
+        other = "f32" if f64 else "f64"
+        legs[f"rw1d_{other}"] = measure_lg(pz, "rw1d", other, n_p, kl, 3)
+        for m in ("lg42", "lg63"):
+            for dt in ("f32", "f64"):
+                legs[f"{m}_{dt}"] = measure_lg(pz, m, dt, 10_000_000, kl, 3)
+        legs["mtt_f32"] = measure_mtt(pz, 1_000_000, 10, 3, args.mtt_tracks, with_cpu=False)
+        legs["sustained_rw1d_" + args.dtype] = measure_lg(pz, "rw1d", args.dtype, n_p, 5, 3, profile=False, sustained=1000)["sustained"]
+
     # ---- CPU baseline on this box's host cores (bounded sample)
     threads = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu:
         import pzhelpers as H  # the CPU oracle: executed by this leg only
-        n_sample = min(n_p, args.cpu_particles)
+        n_sample = min(n_p, args.cpu_particles or 2_000_000)
         steps_cpu = 5
         rate, dt = cpu_port_rate(H, name, n_sample, steps_cpu, threads)
         frate, fdt = cpu_port_rate(H, name, 1000, 100, 1, faithful=True)
         orate, odt = cpu_port_rate(H, name, n_sample, steps_cpu, threads, optimised=True)
         cpu = {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": "port",
-               "sample": f"N={n_sample} x {steps_cpu} steps, reference algorithm in double with binary-search multinomial + OpenMP ({dt:.1f} s)",
+               "sample": f"N={n_sample} x {steps_cpu} steps, reference algorithm in double, binary-search multinomial, every loop over all cores with OpenMP ({dt:.1f} s)",
                "faithful_o_n2": {"value": frate, "cores": 1,
                                  "sample": f"configs[0]: N=1000 x 100 steps, literal O(N^2) resample2 ({fdt:.1f} s)"},
                "optimised_systematic": {"value": orate, "cores": threads,
                                         "sample": f"same sample; not the reference's algorithm: max-shifted weights, O(N) systematic "
                                                   f"resampling over a parallel prefix sum, all loops over all cores ({odt:.1f} s)"}}
+    tr, rep = ncu_traffic(name, args.dtype, n_p) if world == 1 else (None, None)
     line = {
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{name} bootstrap particle filter, N={n_p} particles per GPU (BASELINE.json configs[1])",
-                   "model": name, "particles_per_gpu": n_p, "state_dim": nx, "obs_dim": ny, "state_storage": "fp64" if f64 else "fp32",
-                   "weights": "u16 fixed point per particle, u64 block prefix", "resampler": "systematic (canonical PZ-SYS-256/q16)",
-                   "l2": "inputs exceed L2 (state %.0f MB per buffer)" % (nx * esz * n_p / 1e6), "wall_s_timed": wall},
-        "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 144,
+        "config": cfg,
+        "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 8 * ny, "d2h_bytes_per_step": 144,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "wall_s_timed": wall,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # also against the nominal 8 TB/s, and for the whole step (value x B_alg per GPU)
                      "frac_nominal_8TBs": achieved / 8000.0,
                      "whole_step": {"achieved": value / world * 2 * esz * nx / 1e9, "frac": value / world * 2 * esz * nx / 1e9 / peak},
-                     "traffic": ncu_traffic(name, n_p) if world == 1 else None, "kernel": "pf_step_tile", "peak_source": peak_src,
-                     "alg_bytes_per_launch": alg_bytes, "kernel_ms": t_tile_ms, "kernel_ms_source": kernel_src,
+                     "traffic": tr,
+                     "traffic_source": f"ncu capture of one launch at this N, committed under profiles/ ({rep}); not measured in this run" if tr else None,
+                     "kernel": "pf_step_tile", "peak_source": peak_src,
+                     "alg_bytes_per_launch": alg_bytes, "alg_bytes_per_update": 2 * esz * nx, "kernel_ms": t_tile_ms, "kernel_ms_source": kernel_src,
                      "step_kernels_ms": {"pf_step_tile": t_tile_ms, "pf_scan_blocks": float(np.mean(prof[:, 1])),
                                          "pf_partition": float(np.mean(prof[:, 2]))}},
         "cpu_baseline": cpu,
         "posterior_check": {"step": post_step, "mean0": post_mean0, "ess": post_ess, "n_migrated_last_step_all_ranks": n_migrated},
+        "parity": "partial: bit-exact against this repository's CPU oracle; unpinned against the Haskell binary (no GHC, no reference-held vectors)",
     }
+    if parity is not None:
+        line["sharded_parity"] = parity
+    if legs is not None:
+        line["legs"] = legs
+    print(json.dumps(line), flush=True)
+
+
+def run_mtt(args):
+    import torch
+    import __graft_entry__ as g
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback")
+    pz = g.load_package()
+    sampler = ClockSampler(0); sampler.start()
+    leg = measure_mtt(pz, args.particles, args.steps, args.warmup, args.mtt_tracks, with_cpu=not args.no_cpu)
+    clocks = sampler.summary()
+    line = {"metric": "particle-updates/sec", "value": leg["value"], "unit": leg["unit"], "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": leg["workload"], "model": "mtt", "particles_per_gpu": args.particles,
+                       "mean_tracks_last_step": leg["mean_tracks_last_step"], "l2": "particle records exceed L2 (1040 B per particle)"},
+            "e2e": leg["e2e"], "gpu_launches": leg["gpu_launches"], "clocks": clocks, "roofline": leg["roofline"],
+            "cpu_baseline": leg.get("cpu_baseline")}
     print(json.dumps(line), flush=True)
 
 
@@ -429,18 +600,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="rw1d", choices=list(MODELS))
-    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="state storage and arithmetic (descriptor flag state_f64)")
-    ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU (weak scaling, the default)")
+    ap.add_argument("--dtype", default="f64", choices=["f32", "f64"], help="state storage and arithmetic (descriptor flag state_f64)")
+    ap.add_argument("--particles", type=int, default=HEADLINE_PARTICLES, help="particles per GPU (weak scaling, the default)")
     ap.add_argument("--total-particles", type=int, default=0,
                     help="strong scaling: the whole population, split evenly over the GPUs (overrides --particles)")
-    ap.add_argument("--cpu-particles", type=int, default=2_000_000, help="bounded CPU sample size")
+    ap.add_argument("--cpu-particles", type=int, default=0, help="CPU sample size (0: sized automatically)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra single-GPU legs of the default run")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded bit-equality check before the timed region")
     ap.add_argument("--mtt-tracks", type=int, default=8, help="tracker bench: targets present at t = 0")
     args = ap.parse_args()
+    args.gpus = int(os.environ.get("WORLD_SIZE", args.gpus))
     if args.impl == "reference":
         run_reference(args)
     elif args.model == "mtt":
-        if args.particles == 100_000_000:
+        if args.particles == HEADLINE_PARTICLES:
             args.particles = 1_000_000
         run_mtt(args)
     else:

@@ -135,12 +135,9 @@ inline void weight_q(float lw, float nbf, float* w, uint32_t* q) { weight_q_from
 // f64 filters (descriptor flag state_f64): the block exponent and the argument of the weight polynomial
 // are formed in double and the argument is rounded to fp32 once; everything after that is the fp32 spec.
 constexpr double kLog2eD = 0x1.71547652b82fep+0;
-inline int32_t block_exponent(double maxlw) {
-  if (!(maxlw > -INFINITY)) return kNZero;
-  double e = maxlw * kLog2eD;
-  e = fmin(fmax(e, -262144.0), 262144.0);
-  return (int32_t)rint(e);
-}
+// (the block exponent of an f64 filter is the fp32 definition applied to the log-weights rounded to fp32)
+inline float lw_key(float lw) { return lw; }
+inline float lw_key(double lw) { return (float)lw; }
 inline void weight_q(double lw, double nbf, float* w, uint32_t* q) { weight_q_from_arg((float)fma(lw, kLog2eD, -nbf), w, q); }
 
 // stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)
@@ -312,8 +309,8 @@ bool build_plan(const T* lw, int64_t n, int64_t n_out, ResamplePlan* pl) {
   pl->emax = kNZero;
   for (int64_t b = 0; b < pl->nblk; ++b) {
     const int64_t hi = std::min(n, (b + 1) * kBlk);
-    T mx = -INFINITY;
-    for (int64_t i = b * kBlk; i < hi; ++i) mx = std::max(mx, sanitize_lw(lw[i]));
+    float mx = -INFINITY;
+    for (int64_t i = b * kBlk; i < hi; ++i) mx = fmaxf(mx, lw_key(sanitize_lw(lw[i])));
     const int32_t nb = block_exponent(mx);
     pl->eb[b] = nb;
     if (nb == kNZero) continue;
@@ -870,9 +867,25 @@ int pzo_refpf_run(const pz_model_desc* d, int64_t n, uint64_t seed, const double
       }
       continue;
     }
-    // normalize: totalMass = sum (map snd xs)  -- left fold of Log's (+)
+    // normalize: totalMass = sum (map snd xs)  -- left fold of Log's (+).  mode 0 keeps the literal serial
+    // fold; mode 1 (the all-cores port) folds per-thread chunks with the same logaddexp and combines the
+    // chunk totals in order (the same sum up to rounding).
     double tot = -INFINITY;
-    for (int64_t i = 0; i < n; ++i) tot = logaddexp(tot, lw[i]);
+    int nchunk = 1;
+#if defined(_OPENMP)
+    if (mode == 1) nchunk = omp_get_max_threads();
+#endif
+    if ((int64_t)nchunk > n) nchunk = (int)n;
+    const int64_t per = (n + nchunk - 1) / nchunk;
+    std::vector<double> ctot((size_t)nchunk, -INFINITY);
+#pragma omp parallel for schedule(static, 1) if (mode == 1)
+    for (int c = 0; c < nchunk; ++c) {
+      const int64_t lo = c * per, hi = std::min<int64_t>(n, lo + per);
+      double acc = -INFINITY;
+      for (int64_t i = lo; i < hi; ++i) acc = logaddexp(acc, lw[i]);
+      ctot[c] = acc;
+    }
+    for (int c = 0; c < nchunk; ++c) tot = logaddexp(tot, ctot[c]);
     if (!(tot > -INFINITY)) return PZ_EDEGENERATE;
     // replicateM N (labeledLogCategorical normalized)
     if (mode == 0) {
@@ -886,8 +899,22 @@ int pzo_refpf_run(const pz_model_desc* d, int64_t n, uint64_t seed, const double
         anc[j] = k;
       }
     } else {
-      double c = 0;
-      for (int64_t i = 0; i < n; ++i) { c += exp(lw[i] - tot); cdf[i] = c; }
+      // the CDF every draw of logCategorical walks, built once (chunked over the cores), then one binary
+      // search per draw instead of the O(N) walk: identical ancestors up to the rounding of the partial sums
+      std::vector<double> csum((size_t)nchunk + 1, 0.0);
+#pragma omp parallel for schedule(static, 1)
+      for (int c = 0; c < nchunk; ++c) {
+        const int64_t lo = c * per, hi = std::min<int64_t>(n, lo + per);
+        double acc = 0;
+        for (int64_t i = lo; i < hi; ++i) { acc += exp(lw[i] - tot); cdf[i] = acc; }
+        csum[c + 1] = acc;
+      }
+      for (int c = 0; c < nchunk; ++c) csum[c + 1] += csum[c];
+#pragma omp parallel for schedule(static, 1)
+      for (int c = 1; c < nchunk; ++c) {
+        const int64_t lo = c * per, hi = std::min<int64_t>(n, lo + per);
+        for (int64_t i = lo; i < hi; ++i) cdf[i] += csum[c];
+      }
 #pragma omp parallel for schedule(static)
       for (int64_t j = 0; j < n; ++j) {
         uint32_t r[4];
@@ -901,6 +928,7 @@ int pzo_refpf_run(const pz_model_desc* d, int64_t n, uint64_t seed, const double
     for (int a = 0; a < nx; ++a) {
       double s = 0, s2 = 0;
       double* dst = &x[(size_t)a * n]; const double* src = &xn[(size_t)a * n];
+#pragma omp parallel for schedule(static) reduction(+ : s, s2) if (mode == 1)
       for (int64_t j = 0; j < n; ++j) { double v = src[anc[j]]; dst[j] = v; s += v; s2 += v * v; }
       if (mean_out) mean_out[t * nx + a] = s / n;
       if (var_out) var_out[t * nx + a] = s2 / n - (s / n) * (s / n);

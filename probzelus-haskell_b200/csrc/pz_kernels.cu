@@ -938,38 +938,29 @@ __device__ __forceinline__ bool resample_block(const Source& src, typename Sourc
 }
 
 // The warp's input blocks b_first + warp, + NW, ...: the inputs of the next block (weights, boundary positions,
-// and narrow payloads) are loaded one block ahead into a second register set (the loop is unrolled by two so
-// that the two sets alternate without register moves).
+// and narrow payloads) are loaded one block ahead.  (A two-register-set unrolling that avoids the ~20 register
+// moves per block was measured slower: it spills at 64 registers.)
 template <bool SEGDUP, int NW, class Source>
 __device__ __forceinline__ void resample_tile(Source& src, typename Source::Scalar* s_par, int stride, const uint16_t* __restrict__ qin,
                                               const int32_t* __restrict__ ebx, const u64* __restrict__ xb, int64_t b_first,
                                               int64_t b_end, int32_t emax, int32_t h0, uint32_t Mq, uint32_t j0, int nslots,
-                                              int lane, int warp, const BlockIn& first) {
-  // `first` holds the inputs of block b_first + warp (loaded by the caller before its prologue barrier)
+                                              int lane, int warp, BlockIn cur, Quad<typename Source::Scalar> pa,
+                                              Quad<typename Source::Scalar> pb) {
+  // `cur` / `pa`, `pb` hold the inputs / narrow payload of block b_first + warp (loaded by the caller before its
+  // prologue barrier, so that their DRAM latency overlaps the prologue)
   int64_t b = b_first + warp;
   if (b >= b_end) return;
   constexpr bool kAhead = Source::kPrefetch;
   typedef Quad<typename Source::Scalar> QuadS;
-  BlockIn inA = first, inB{};
-  QuadS a0{}, a1{}, b0{}, b1{};
-  if constexpr (kAhead) { a0 = src.fetch(b * kBlk + lane * 4); a1 = src.fetch(b * kBlk + lane * 4 + 128); }
-  while (true) {
-    int64_t bn = b + NW;
-    if (bn < b_end) {
-      inB.load(qin, ebx, xb, bn, lane);
-      if constexpr (kAhead) { b0 = src.fetch(bn * kBlk + lane * 4); b1 = src.fetch(bn * kBlk + lane * 4 + 128); }
+  for (; b < b_end; b += NW) {
+    const BlockIn in = cur;
+    const QuadS xa = pa, xb4 = pb;
+    const int64_t bn = b + NW;
+    if (bn < b_end) {  // next iteration's inputs: in flight during this one
+      cur.load(qin, ebx, xb, bn, lane);
+      if constexpr (kAhead) { pa = src.fetch(bn * kBlk + lane * 4); pb = src.fetch(bn * kBlk + lane * 4 + 128); }
     }
-    if (resample_block<SEGDUP>(src, s_par, stride, inA, a0, a1, b, emax, h0, Mq, j0, nslots, lane)) break;
-    b = bn;
-    if (b >= b_end) break;
-    bn = b + NW;
-    if (bn < b_end) {
-      inA.load(qin, ebx, xb, bn, lane);
-      if constexpr (kAhead) { a0 = src.fetch(bn * kBlk + lane * 4); a1 = src.fetch(bn * kBlk + lane * 4 + 128); }
-    }
-    if (resample_block<SEGDUP>(src, s_par, stride, inB, b0, b1, b, emax, h0, Mq, j0, nslots, lane)) break;
-    b = bn;
-    if (b >= b_end) break;
+    if (resample_block<SEGDUP>(src, s_par, stride, in, xa, xb4, b, emax, h0, Mq, j0, nslots, lane)) break;
   }
 }
 
@@ -1033,14 +1024,11 @@ template <> __device__ __forceinline__ double exp2t<double>(int k) { return pow2
 // warp shuffles in the filter's arithmetic type
 __device__ __forceinline__ float shfl_xor_t(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double shfl_xor_t(double v, int m) { return shfl_xor_f64(v, m); }
-// block exponent from the block's largest log-weight in double: the same definition evaluated in double
-__device__ __forceinline__ double block_exponent(double maxlw, int32_t& nb) {
-  if (!(maxlw > -INFINITY)) { nb = kNZero; return 0.0; }
-  const double e = fmin(fmax(__dmul_rn(maxlw, kLog2eD), -262144.0), 262144.0);
-  const double nbf = rint(e);
-  nb = __double2int_rn(nbf);
-  return nbf;
-}
+// A double filter forms its block exponent from the log-weights ROUNDED TO FP32 (the fp32 definition applied
+// to fl32(lw): a double maximum costs ~12 instructions per particle, the exponent only has to be within a
+// fraction of a unit of the true one).  lw_key is the value that enters the block maximum.
+__device__ __forceinline__ float lw_key(float lw) { return lw; }
+__device__ __forceinline__ float lw_key(double lw) { return __double2float_rn(lw); }
 // d = lw * log2(e) - n_b, as the fp32 argument of the weight polynomial
 __device__ __forceinline__ float weight_arg(float lw, float nbf) { return __fmaf_rn(lw, kLog2e, -nbf); }
 __device__ __forceinline__ float weight_arg(double lw, double nbf) { return __double2float_rn(__fma_rn(lw, kLog2eD, -nbf)); }
@@ -1056,7 +1044,7 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
   const LgDevT<T>& model = model_of<T>(a);
   T lw[8];
   T xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
-  T mx = -INFINITY;
+  float mx = -INFINITY;
   int seg_carry = -1;
   if constexpr (MODE == 0 && NX == 1) {
     if (ob > 0) seg_carry = last_head_before(s_par, ob * kBlk, lane);  // runs of <= 128 slots reach back one segment
@@ -1099,7 +1087,7 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       T l = model_logweight<NX, NY, KRON>(model, xn, y_new);
       if (!FULL && sl + k >= nslots) l = -INFINITY;  // past the end of the population
       lw[half * 4 + k] = l;
-      mx = r_max(mx, l);
+      mx = fmaxf(mx, lw_key(l));
     }
     if (FULL || sl < nslots) {
 #pragma unroll
@@ -1114,9 +1102,9 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
     }
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = r_max(mx, shfl_xor_t(mx, d));
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
   int32_t nb;
-  const T nbf = block_exponent(mx, nb);
+  const T nbf = (T)block_exponent(mx, nb);
   uint32_t ssum = 0;
   if (nb != kNZero) {
     T p[PZ_NACC(NX)];
@@ -1220,16 +1208,31 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     // the first input block's weights: in flight during the prologue
     const int64_t b_first = (int64_t)a.tile_start[blockIdx.x];
     BlockIn first{};
-    if (b_first + warp < a.b_hi) first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
+    StateSource<NX, T> src;
+    src.x = xin; src.ld = a.ld;
+    Quad<T> pa{}, pb{};
+    if (b_first + warp < a.b_hi) {
+      first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
+      // fp32 payloads of the first block are fetched here too; for doubles the 16 extra registers across the
+      // barrier cost more than the exposed latency (measured: 0.568 ms hoisted vs 0.544 ms not, N = 10^8)
+      if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 4) {
+        pa = src.fetch((b_first + warp) * kBlk + lane * 4);
+        pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
+      }
+    }
     for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
     // sentinel in (the mark word of) dimension 0 of every slot: "no head here"
     uint4* sz = reinterpret_cast<uint4*>(s_par);
     for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
-    StateSource<NX, T> src;
-    src.x = xin; src.ld = a.ld;
+    if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 8) {
+      if (b_first + warp < a.b_hi) {
+        pa = src.fetch((b_first + warp) * kBlk + lane * 4);
+        pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
+      }
+    }
     resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
-                             lane, warp, first);
+                             lane, warp, first, pa, pb);
   } else {
     for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
     for (int sidx = tid; sidx < nslots; sidx += NT) {
@@ -1360,7 +1363,7 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   BlockIn first{};
   if (b_first + warp < g.nblk) first.load(generic_q(g), generic_eb(g), g.xb, b_first + warp, lane);
   resample_tile<true, kWarps>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, b_first, g.nblk, pl->emax, pl->h0, pl->Mq, (uint32_t)j0,
-                      nslots, lane, warp, first);
+                      nslots, lane, warp, first, Quad<float>{}, Quad<float>{});
   __syncthreads();
   for (int seg = warp; seg * 128 < nslots; seg += kWarps) {
     const int sl = seg * 128 + lane * 4;
