@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PZ_ABI_VERSION 1
+#define PZ_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PZ_API __attribute__((visibility("default")))
@@ -56,7 +56,12 @@ extern "C" {
 enum {
   PZ_MODEL_RW1D = 1,     /* Examples/Demo.hs:184-201 (kalman1D*), Inference.hs:143-147 (rw)         */
   PZ_MODEL_LINGAUSS = 2, /* Examples/SingleTargetTracking.hs:28-54; per-track model of MTT :56-73    */
-  PZ_MODEL_MTT = 3       /* Examples/MultiTargetTracking.hs:26-145                                   */
+  PZ_MODEL_MTT = 3,      /* Examples/MultiTargetTracking.hs:26-145                                   */
+  PZ_MODEL_WALKER = 4,   /* Examples/Walker.hs:20-148: hybrid discrete / continuous walker under the MStream
+                            `particles` filter (Inference.hs:73-86): weights carried across resampling          */
+  PZ_MODEL_BETA_BERNOULLI = 5 /* Examples/DelayedSamplingAbstract.hs:57-69 betaBernoulli under delayed sampling:
+                            Beta prior, Bernoulli observations, conjugate update (DelayedSampling.hs:140,150-151;
+                            SymbolicDistr.hs:165-188)                                                         */
 };
 
 enum {
@@ -77,6 +82,21 @@ typedef struct pz_mtt_params {
   int32_t k_max;           /* fixed per-particle track capacity (<= 16)           */
   int32_t m_max;           /* max observations per step (<= 32)                   */
 } pz_mtt_params;
+
+/* Walker constants, Examples/Walker.hs:28-96.  Motion types 0 = Stationary, 1 = Walking, 2 = Running. */
+typedef struct pz_walker_params {
+  double pos_noise;        /* posNoise = 0.01 (:28-29); coast passes sqrt(dt) * posNoise as the VARIANCE of D.normal (:33-39) */
+  double obs_std;          /* positionStdDev = 10 (:85-86); the observation variance is obs_std^2 (:90-91)   */
+  double dt;               /* time between measurements, 10 s (:123)                                         */
+  double p_init[3];        /* walkerInit: 0.7 / 0.25 / 0.05 (:107-111)                                        */
+  double half_life[3][3];  /* motionTypeTransition (:43-49): half_life[from][to] in seconds, 0 = no transition */
+  double speed_lo[3];      /* initVelocity (:51-64): speed ~ U(lo, hi) at a uniform angle; Stationary 0..0     */
+  double speed_hi[3];
+  int32_t exp_mean_as_written; /* 1 = reference behaviour (:69): tTransition = -log(u) * sum(rates), because
+                                  D.exponential takes a RATE (Distributions.hs:209-212) and is handed
+                                  recip(sum rates); 0 = the intended -log(u) / sum(rates)                   */
+  int32_t reserved;
+} pz_walker_params;
 
 /* Kernel-side model descriptor.  Matrices are row-major, leading dimension = the
  * logical column count (nx for F/Q/P0, nx for H, ny for R).                                 */
@@ -103,6 +123,16 @@ typedef struct pz_model_desc {
   double R[PZ_MAX_NY * PZ_MAX_NY];
   double x0[PZ_MAX_NX];             /* initial state (the reference starts at a point mass)  */
   pz_mtt_params mtt;
+  /* ---- ABI 2 ---- */
+  double ess_threshold;  /* > 0: adaptive resampling (not in the reference): the population is
+                            resampled only when ESS < ess_threshold * N, otherwise particles keep their slot and
+                            their log-weights accumulate; after a resample the weights restart from 1.        */
+  int32_t carry_weights; /* 1 = the MStream `particles` semantics (Inference.hs:73-86, streamWeights): resample
+                            every step, but a child inherits its parent's CUMULATIVE weight.  RW1D / LINGAUSS
+                            fp32 / WALKER; runs on the stored-log-weight path.                                */
+  int32_t reserved2;
+  pz_walker_params walker;
+  double beta_a, beta_b; /* PZ_MODEL_BETA_BERNOULLI: the Beta(a, b) prior                                    */
 } pz_model_desc;
 
 /* Posterior summary of one step: the weighted particle approximation of
@@ -130,10 +160,20 @@ PZ_API int pz_model_rw1d(pz_model_desc* d, double q_var, double r_var);       /*
 PZ_API int pz_model_stt(pz_model_desc* d);                                    /* SingleTargetTracking.hs:39-54 */
 PZ_API int pz_model_mtt_track(pz_model_desc* d);                              /* MultiTargetTracking.hs:56-73  */
 PZ_API int pz_model_mtt(pz_model_desc* d);                                    /* MultiTargetTracking.hs:36-145 */
+PZ_API int pz_model_walker(pz_model_desc* d);                                 /* Walker.hs:20-148 (carry_weights = 1) */
+PZ_API int pz_model_beta_bernoulli(pz_model_desc* d, double a, double b);     /* DelayedSamplingAbstract.hs:57-69 (delayed = 1) */
 
 /* zparticles / zdsparticles: a filter over n_particles copies of the model on one device. */
 PZ_API int pz_filter_create(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int device,
                      pz_filter** out);
+
+/* The same over n_devices GPUs driven by ONE host thread of one process (what a single-threaded
+ * Haskell host calls): the particles are sharded over the devices, resampling is global, the exchange runs over
+ * NVLink peer memory inside the step kernels; pz_filter_step / pz_filter_run / pz_filter_read_state /
+ * pz_filter_destroy apply to the returned handle unchanged (the taps that address one device's memory do not).
+ * n_particles must be divisible by n_devices * 256.  RW1D / LINGAUSS.                                       */
+PZ_API int pz_filter_create_multi(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int n_devices,
+                                  const int* device_ids, pz_filter** out);
 
 /* One rank of a filter whose n_global particles are sharded over `world` GPUs (one process
  * per GPU).  nccl_unique_id is the 128-byte ncclUniqueId produced by pz_comm_unique_id() on
@@ -184,7 +224,8 @@ PZ_API int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_ou
 
 /* Delayed-sampling filters (model.delayed = 1): the Gaussian marginal every particle carries,
  * `MDistr` (mean[nx], cov[nx*nx] row-major) -- what the reference serialises per particle as
- * {"mean":..,"cov":..} (DelayedSampling.hs:69-73).                                            */
+ * {"mean":..,"cov":..} (DelayedSampling.hs:69-73).  For PZ_MODEL_BETA_BERNOULLI the marginal is
+ * MBeta: mean_out[0] = alpha, mean_out[1] = beta, cov_out[0] = the Beta variance.              */
 PZ_API int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out);
 
 /* Parity / debug taps. */
@@ -200,6 +241,24 @@ PZ_API int64_t pz_filter_n_local(const pz_filter* f);
 PZ_API int pz_resample_systematic(const double* logw, int64_t n, double u, int32_t* anc_out);
 PZ_API int pz_resample_multinomial(const double* logw, int64_t n, uint64_t seed, uint32_t step,
                             int32_t* anc_out);
+
+/* importanceResampling (Inference.hs:68-71): k iid draws from Categorical(exp(logw - max)) on the canonical
+ * fixed-point CDF; `resample` (Inference.hs:51-52) is the k = n case = pz_resample_multinomial.             */
+PZ_API int pz_importance_resampling(const double* logw, int64_t n, uint64_t seed, uint32_t step, int64_t k,
+                                    int32_t* idx_out);
+
+/* The distribution primitives of Distributions.hs as device functions (sample on the GPU from Philox words,
+ * score = log-density): parity taps for SURVEY 8a row a11.  params: BERNOULLI {p}; CATEGORICAL {p_0..p_{np-1}};
+ * POISSON {lambda}; UNIFORM {a, b}; EXPONENTIAL {rate}; NORMAL {mu, sigma^2} (score doubled as the reference's
+ * gaussian_ll', Distributions.hs:160-161).  Samples and arguments of the discrete ones are integers in doubles. */
+enum { PZ_DIST_BERNOULLI = 1, PZ_DIST_CATEGORICAL = 2, PZ_DIST_POISSON = 3, PZ_DIST_UNIFORM = 4,
+       PZ_DIST_EXPONENTIAL = 5, PZ_DIST_NORMAL = 6 };
+PZ_API int pz_dist_sample(int32_t kind, const double* params, int32_t n_params, uint64_t seed, int64_t n, double* out);
+PZ_API int pz_dist_score(int32_t kind, const double* params, int32_t n_params, const double* x, int64_t n, double* out);
+
+/* Back to the prior at step 0 (same model, new seed): the way on after PZ_EDEGENERATE / PZ_ECAPACITY, which
+ * leave the populations overwritten.  Single-GPU filters.                                                    */
+PZ_API int pz_filter_reset(pz_filter* f, uint64_t seed);
 
 PZ_API void pz_filter_destroy(pz_filter* f);
 PZ_API const char* pz_last_error(void);

@@ -447,6 +447,40 @@ struct OFilterT : OFilterBase {
   std::vector<T> lw;   // its log-weights
   std::vector<int32_t> anc;  // ancestors used by the last step
   double center[PZ_MAX_NX];  // centring constants of the moment sums (previous posterior mean)
+  // stored-log-weight variants (descriptor flags carry_weights / ess_threshold; pz_generic.cu)
+  bool resample_next = true;   // the adaptive rule's decision for the next resample
+  double prev_log = 0;         // log of the sum of the stored weights of the pending population
+  int32_t prev_emax = 0;
+
+  bool generic() const { return desc.carry_weights || desc.ess_threshold > 0; }
+
+  // summary of the stored-log-weight path: the QUANTISED weights, centred on the previous mean
+  void summarise_generic(const ResamplePlan& pl, bool carried, pz_step_summary* s) {
+    double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
+    for (int64_t i = 0; i < n; ++i) {
+      const int32_t eb = pl.eb[i / kBlk];
+      if (eb == kNZero) continue;
+      const double w = ldexp((double)pl.q[i], eb - pl.emax - 15);
+      sw += w; sw2 += w * w;
+      for (int d = 0; d < p.nx; ++d) {
+        const double dx = (double)x[(size_t)d * n + i] - center[d];
+        sx[d] += w * dx; sxx[d] += w * dx * dx;
+      }
+    }
+    s->ess = sw * sw / sw2;
+    for (int d = 0; d < p.nx; ++d) {
+      const double m = sx[d] / sw;
+      s->mean[d] = center[d] + m;
+      s->var[d] = sxx[d] / sw - m * m;
+    }
+    const double cur_log = log(sw) + pl.emax * 0.6931471805599453;
+    const double rebase = (double)((float)prev_emax * 0x1.62e43p-1f);
+    s->log_evidence_inc = (carried ? cur_log - (prev_log - rebase) : cur_log - log((double)n)) + p.ll_const;
+    s->e_max = pl.emax;
+    s->total_weight = pl.total;
+    s->n_migrated = 0;
+    prev_log = cur_log; prev_emax = pl.emax;
+  }
 
   void summarise(const ResamplePlan& pl, pz_step_summary* s) const {
     // the same fp32 weights the resampler quantises, at scale 2^emax, in double
@@ -480,12 +514,21 @@ struct OFilterT : OFilterBase {
   int step(const double* obs, pz_step_summary* out) override {
     ResamplePlan pl;
     if (!build_plan(lw.data(), n, n, &pl)) return PZ_EDEGENERATE;
-    if (desc.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
+    const bool resampled = !(desc.ess_threshold > 0) || resample_next;
+    if (!resampled) {
+      for (int64_t j = 0; j < n; ++j) anc[j] = (int32_t)j;   // the adaptive rule keeps every particle in its slot
+    } else if (desc.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) {
       multinomial_ancestors(pl, seed, t, n, anc.data());
     } else {
       uint32_t U = resample_uniform(seed, t);
       systematic_ancestors(pl, U, n, anc.data());
     }
+    // MStream `particles` (Inference.hs:73-86): a child inherits its parent's cumulative weight; without a
+    // resample the weights accumulate as well.  The carried fp32 log-weight is re-based by emax * ln 2.
+    const bool carried = generic() && (desc.carry_weights || !resampled);
+    const T rebase = (T)((float)pl.emax * 0x1.62e43p-1f);
+    std::vector<T> lw_old;
+    if (carried) lw_old = lw;
     T y[PZ_MAX_NY];
     for (int k = 0; k < p.ny; ++k) y[k] = (T)obs[k];
     std::vector<T> xn((size_t)p.nx * n);
@@ -499,18 +542,25 @@ struct OFilterT : OFilterBase {
       for (int d = 0; d < p.nx; ++d) z[d] = (T)zf[d];   // a double filter uses the same fp32 table normals
       lg_propagate(p, xp, z, xo);
       for (int d = 0; d < p.nx; ++d) xn[(size_t)d * n + j] = xo[d];
-      lw[j] = lg_logweight(p, xo, y);
+      const T inc = lg_logweight(p, xo, y);
+      lw[j] = carried ? (T)((lw_old[a] - rebase) + inc) : inc;
     }
     x.swap(xn);
     ResamplePlan pl2;
     bool ok = build_plan(lw.data(), n, n, &pl2);
-    if (out) {
-      memset(out, 0, sizeof(*out));
-      out->step = t;
-      if (ok) {
+    pz_step_summary tmp;
+    if (!out) out = &tmp;
+    memset(out, 0, sizeof(*out));
+    out->step = t;
+    if (ok) {
+      if (generic()) {
+        summarise_generic(pl2, carried, out);
+        out->reserved = resampled ? 1 : 0;
+        resample_next = !(desc.ess_threshold > 0) || out->ess < desc.ess_threshold * (double)n;
+      } else {
         summarise(pl2, out);
-        for (int d = 0; d < p.nx; ++d) center[d] = out->mean[d];
       }
+      for (int d = 0; d < p.nx; ++d) center[d] = out->mean[d];
     }
     t += 1;
     return ok ? 0 : PZ_EDEGENERATE;
@@ -555,6 +605,7 @@ OFilterBase* make_filter(const pz_model_desc* d, int64_t n, uint64_t seed) {
   }
   f->lw.assign(n, (T)0);  // equal weights before the first observation
   f->anc.assign(n, 0);
+  f->prev_log = log((double)n);
   return f;
 }
 
@@ -643,6 +694,233 @@ void pzo_filter_state_f64(void* h, double* x, double* lw, int32_t* anc) { ((OFil
 int pzo_filter_block_stats(void* h, int32_t* eb, uint64_t* sb, int32_t* emax, uint64_t* total) {
   return ((OFilterBase*)h)->block_stats(eb, sb, emax, total);
 }
+
+}  // extern "C"
+
+// =========================================================================================
+// Distribution primitives (Distributions.hs:127-212) on Philox words: the CPU twin of
+// probzelus-haskell_b200/csrc/pz_dist.cuh.
+// =========================================================================================
+namespace {
+
+constexpr uint32_t kStreamDist = 0x44495354u, kStreamWalker = 0x57414C4Bu, kStreamWalkInit = 0x57494E49u;
+
+struct PhiloxSeq {  // sequential words of one counter family: ctr = (slot, call, step, stream)
+  uint64_t seed; uint32_t slot, step, stream, call = 0; int have = 0; uint32_t r[4];
+  PhiloxSeq(uint64_t s, uint32_t sl, uint32_t st, uint32_t strm) : seed(s), slot(sl), step(st), stream(strm) {}
+  uint32_t next() {
+    if (!have) { philox(slot, call++, step, stream, seed, r); have = 4; }
+    return r[4 - have--];
+  }
+  double uniform01() { return ((double)next() + 0.5) * 0x1p-32; }
+};
+
+int sample_bernoulli(PhiloxSeq& g, double p) { return g.uniform01() < p ? 1 : 0; }            // B.bernoulli
+double score_bernoulli(double p, double b) { return b * log(p) + (1.0 - b) * log(1.0 - p); }   // bernoulli_ll :148-149
+int sample_categorical(PhiloxSeq& g, const double* ps, int n) {   // mwc-random categorical: first i with cum_i >= u * total
+  double total = 0;
+  for (int i = 0; i < n; ++i) total += ps[i];
+  const double u = g.uniform01() * total;
+  double c = 0;
+  for (int i = 0; i < n; ++i) { c += ps[i]; if (c >= u) return i; }
+  return n - 1;
+}
+double score_categorical(const double* ps, int n, double i) {     // log (ps !! i) :141-142
+  const int k = (int)i;
+  return (k >= 0 && k < n && (double)k == i) ? log(ps[k]) : -INFINITY;
+}
+int sample_poisson(PhiloxSeq& g, double lambda) {
+  const double u = g.uniform01();
+  double p = exp(-lambda), c = p;
+  int k = 0;
+  while (u > c && k < 100000) { ++k; p *= lambda / (double)k; c += p; }
+  return k;
+}
+double score_poisson(double lambda, double k) { return k * log(lambda) - lambda - lgamma(k + 1.0); }   // poisson_ll :168-169
+double sample_uniform(PhiloxSeq& g, double a, double b) { return a + (b - a) * g.uniform01(); }
+double score_uniform(double a, double b, double x) { return (a <= x && x <= b) ? -log(b - a) : -INFINITY; }   // :174-180
+double sample_exponential(PhiloxSeq& g, double rate) { return -log(g.uniform01()) / rate; }   // :209-212
+double sample_normal(PhiloxSeq& g, double mu, double sigma2) { return mu + sqrt(sigma2) * (double)icdf_normal(g.next()); }   // :163-164
+double score_normal_2x(double mu, double sigma2, double x) {    // gaussian_ll' :160-161
+  const double d = x - mu;
+  return -(d * d) / sigma2 - 1.8378770664093453 - log(sigma2);
+}
+
+// ---- Walker (Examples/Walker.hs) ----
+struct WalkerState { double x, y, vx, vy; int mt; };
+
+void walker_init_velocity(const pz_walker_params& w, PhiloxSeq& rng, int mt, double& vx, double& vy) {   // :51-64
+  if (w.speed_hi[mt] <= 0.0) { vx = 0.0; vy = 0.0; return; }
+  const double speed = sample_uniform(rng, w.speed_lo[mt], w.speed_hi[mt]);
+  const double angle = sample_uniform(rng, 0.0, 6.283185307179586);
+  vx = speed * cos(angle);
+  vy = speed * sin(angle);
+}
+void walker_coast(const pz_walker_params& w, PhiloxSeq& rng, double dt, WalkerState& s) {   // :31-41 (variance = sqrt dt * posNoise)
+  const double var = sqrt(dt) * w.pos_noise;
+  s.x = sample_normal(rng, s.x + s.vx * dt, var);
+  s.y = sample_normal(rng, s.y + s.vy * dt, var);
+}
+void walker_motion(const pz_walker_params& w, PhiloxSeq& rng, WalkerState& s) {   // :67-81
+  double dt = w.dt;
+  for (int it = 0; it < 100000; ++it) {
+    double rates[3], sum = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      rates[k] = w.half_life[s.mt][k] > 0.0 ? 0.6931471805599453 / w.half_life[s.mt][k] : 0.0;
+      sum += rates[k];
+    }
+    const double lambda = w.exp_mean_as_written ? 1.0 / sum : sum;
+    const double t_tr = sum > 0.0 ? sample_exponential(rng, lambda) : INFINITY;
+    if (t_tr > dt) { walker_coast(w, rng, dt, s); return; }
+    walker_coast(w, rng, t_tr, s);
+    s.mt = sample_categorical(rng, rates, 3);
+    walker_init_velocity(w, rng, s.mt, s.vx, s.vy);
+    dt -= t_tr;
+  }
+}
+
+struct OWalker {
+  pz_model_desc desc;
+  int64_t n; uint64_t seed; uint32_t t = 0;
+  std::vector<WalkerState> s;
+  std::vector<float> lw;
+  std::vector<int32_t> anc;
+  bool resample_next = true;
+};
+
+}  // namespace
+
+extern "C" {
+
+int pzo_dist_sample(int32_t kind, const double* p, int32_t np, uint64_t seed, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    PhiloxSeq g(seed, (uint32_t)i, 0u, kStreamDist);
+    switch (kind) {
+      case PZ_DIST_BERNOULLI: out[i] = sample_bernoulli(g, p[0]); break;
+      case PZ_DIST_CATEGORICAL: out[i] = sample_categorical(g, p, np); break;
+      case PZ_DIST_POISSON: out[i] = sample_poisson(g, p[0]); break;
+      case PZ_DIST_UNIFORM: out[i] = sample_uniform(g, p[0], p[1]); break;
+      case PZ_DIST_EXPONENTIAL: out[i] = sample_exponential(g, p[0]); break;
+      case PZ_DIST_NORMAL: out[i] = sample_normal(g, p[0], p[1]); break;
+      default: return PZ_EINVAL;
+    }
+  }
+  return 0;
+}
+
+int pzo_dist_score(int32_t kind, const double* p, int32_t np, const double* x, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    switch (kind) {
+      case PZ_DIST_BERNOULLI: out[i] = score_bernoulli(p[0], x[i]); break;
+      case PZ_DIST_CATEGORICAL: out[i] = score_categorical(p, np, x[i]); break;
+      case PZ_DIST_POISSON: out[i] = score_poisson(p[0], x[i]); break;
+      case PZ_DIST_UNIFORM: out[i] = score_uniform(p[0], p[1], x[i]); break;
+      case PZ_DIST_EXPONENTIAL: out[i] = x[i] >= 0 ? log(p[0]) - p[0] * x[i] : -INFINITY; break;
+      case PZ_DIST_NORMAL: out[i] = score_normal_2x(p[0], p[1], x[i]); break;
+      default: return PZ_EINVAL;
+    }
+  }
+  return 0;
+}
+
+// importanceResampling (Inference.hs:68-71) / resample (:51-52): k iid categorical draws on the canonical CDF
+int pzo_importance_resampling(const float* lw, int64_t n, uint64_t seed, uint32_t t, int64_t k, int32_t* idx) {
+  ResamplePlan pl;
+  if (!build_plan(lw, n, n, &pl)) return PZ_EDEGENERATE;
+  std::vector<int32_t> anc(n);
+  multinomial_ancestors(pl, seed, t, n, anc.data());   // slot j uses its own counter: the first k slots are the k draws
+  for (int64_t j = 0; j < k; ++j) idx[j] = anc[j];
+  return 0;
+}
+
+void* pzo_walker_create(const pz_model_desc* d, int64_t n, uint64_t seed) {
+  OWalker* f = new OWalker();
+  f->desc = *d; f->n = n; f->seed = seed;
+  f->s.resize(n); f->lw.assign(n, 0.0f); f->anc.assign(n, 0);
+  for (int64_t j = 0; j < n; ++j) {   // walkerInit (Walker.hs:105-111)
+    PhiloxSeq rng(seed, (uint32_t)j, 0u, kStreamWalkInit);
+    WalkerState& s = f->s[j];
+    s.x = 0; s.y = 0;
+    s.mt = sample_categorical(rng, d->walker.p_init, 3);
+    walker_init_velocity(d->walker, rng, s.mt, s.vx, s.vy);
+  }
+  return f;
+}
+void pzo_walker_destroy(void* h) { delete (OWalker*)h; }
+
+// one step of `particles N (walkerSimulate measurements)` (Walker.hs:113-131; Inference.hs:73-86)
+int pzo_walker_step(void* h, const double* obs, double* ess_out, int32_t* resampled_out) {
+  OWalker* f = (OWalker*)h;
+  const int64_t n = f->n;
+  ResamplePlan pl;
+  if (!build_plan(f->lw.data(), n, n, &pl)) return PZ_EDEGENERATE;
+  const bool resampled = !(f->desc.ess_threshold > 0) || f->resample_next;
+  if (!resampled) for (int64_t j = 0; j < n; ++j) f->anc[j] = (int32_t)j;
+  else if (f->desc.resampler == PZ_RESAMPLE_MULTINOMIAL_REF) multinomial_ancestors(pl, f->seed, f->t, n, f->anc.data());
+  else systematic_ancestors(pl, resample_uniform(f->seed, f->t), n, f->anc.data());
+  const bool carried = f->desc.carry_weights || !resampled;
+  const float rebase = (float)pl.emax * 0x1.62e43p-1f;
+  std::vector<WalkerState> sn(n);
+  std::vector<float> lwn(n);
+  const double v = f->desc.walker.obs_std * f->desc.walker.obs_std;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t j = 0; j < n; ++j) {
+    const int64_t a = f->anc[j];
+    WalkerState s = f->s[a];
+    PhiloxSeq rng(f->seed, (uint32_t)j, f->t, kStreamWalker);
+    walker_motion(f->desc.walker, rng, s);
+    const double inc = score_normal_2x(s.x, v, obs[0]) + score_normal_2x(s.y, v, obs[1]);   // walkerMeasure :88-94
+    sn[j] = s;
+    lwn[j] = carried ? (f->lw[a] - rebase) + (float)inc : (float)inc;
+  }
+  f->s.swap(sn); f->lw.swap(lwn);
+  ResamplePlan pl2;
+  const bool ok = build_plan(f->lw.data(), n, n, &pl2);
+  double sw = 0, sw2 = 0;
+  if (ok) for (int64_t i = 0; i < n; ++i) {
+    const int32_t eb = pl2.eb[i / kBlk];
+    if (eb == kNZero) continue;
+    const double w = ldexp((double)pl2.q[i], eb - pl2.emax - 15);
+    sw += w; sw2 += w * w;
+  }
+  const double ess = ok ? sw * sw / sw2 : 0;
+  if (ess_out) *ess_out = ess;
+  if (resampled_out) *resampled_out = resampled ? 1 : 0;
+  f->resample_next = !(f->desc.ess_threshold > 0) || ess < f->desc.ess_threshold * (double)n;
+  f->t += 1;
+  return ok ? 0 : PZ_EDEGENERATE;
+}
+
+// state as SoA [5][n] (x, y, vx, vy, motion type) and the stored log-weights
+void pzo_walker_state(void* h, double* x, float* lw, int32_t* anc) {
+  OWalker* f = (OWalker*)h;
+  const int64_t n = f->n;
+  if (x) for (int64_t j = 0; j < n; ++j) {
+    x[j] = f->s[j].x; x[n + j] = f->s[j].y; x[2 * n + j] = f->s[j].vx; x[3 * n + j] = f->s[j].vy; x[4 * n + j] = f->s[j].mt;
+  }
+  if (lw) memcpy(lw, f->lw.data(), n * sizeof(float));
+  if (anc) memcpy(anc, f->anc.data(), n * sizeof(int32_t));
+}
+
+// observation stream of the walker's generative model (generateWalker, Walker.hs:113-123): (dt, measured position)
+int pzo_walker_generate(const pz_model_desc* d, uint64_t seed, int64_t T, double* obs, double* truth) {
+  PhiloxSeq rng(seed, 0u, 0u, kStreamObs);
+  WalkerState s;
+  s.x = 0; s.y = 0;
+  s.mt = sample_categorical(rng, d->walker.p_init, 3);
+  walker_init_velocity(d->walker, rng, s.mt, s.vx, s.vy);
+  for (int64_t t = 0; t < T; ++t) {
+    walker_motion(d->walker, rng, s);
+    obs[2 * t] = sample_normal(rng, s.x, d->walker.obs_std);      // walkerGenMeasurement: D.normal x positionStdDev (variance = 10)
+    obs[2 * t + 1] = sample_normal(rng, s.y, d->walker.obs_std);
+    if (truth) { truth[5 * t] = s.x; truth[5 * t + 1] = s.y; truth[5 * t + 2] = s.vx; truth[5 * t + 3] = s.vy; truth[5 * t + 4] = s.mt; }
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---------------------------------------------------------------------------------------
 // Exact Kalman filter, kalmanPredict / kalmanUpdate (MVDistributions.hs:75-100), double.

@@ -21,6 +21,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is loaded with dlopen when a sharded filter is created
 
+#include "pz_generic.cuh"
 #include "pz_kernels.cuh"
 
 using namespace pz;
@@ -332,6 +333,16 @@ struct pz_filter {
   bool is_rb = false;
   RbDev* rb = nullptr;
   bool is_gen = false;               // generic-path filter (stored log-weights): carried weights, adaptive resampling, Walker
+  GenArgs ga;
+  float* gen_lw[2] = {nullptr, nullptr};
+  double* gen_obs = nullptr;         // device [PZ_MAX_NY]
+  double* h_gen_obs = nullptr;       // pinned
+  double* gen_part = nullptr;
+  GenState* gen_state = nullptr;
+  bool is_beta = false;              // Beta-Bernoulli under delayed sampling
+  BetaDev* beta = nullptr;
+  bool is_multi = false;             // single-process multi-device filter: the shards (one per device) do the work
+  std::vector<pz_filter*> shards;
   // multi-target tracker
   bool is_mtt = false;
   uint32_t* mtt_s[2] = {nullptr, nullptr};   // particle records, double-buffered
@@ -405,6 +416,12 @@ void shard_timing_collect(pz_filter* f) {
 
 void free_filter(pz_filter* f) {
   if (!f) return;
+  if (f->is_multi) {
+    for (pz_filter* sh : f->shards) if (sh && sh->stream) { cudaSetDevice(sh->device); cudaStreamSynchronize(sh->stream); }
+    for (pz_filter* sh : f->shards) free_filter(sh);
+    delete f;
+    return;
+  }
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   if (f->graph) cudaGraphExecDestroy(f->graph);
@@ -438,6 +455,8 @@ void free_filter(pz_filter* f) {
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(f->mbox); cudaFree(f->d_p2p);
   cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow); cudaFree(f->mtt_part);
+  cudaFree(f->gen_lw[0]); cudaFree(f->gen_lw[1]); cudaFree(f->gen_obs); cudaFree(f->gen_part); cudaFree(f->gen_state); cudaFree(f->beta);
+  if (f->h_gen_obs) cudaFreeHost(f->h_gen_obs);
   if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
   f->g.release();
   if (f->h_obs) cudaFreeHost(f->h_obs);
@@ -488,6 +507,8 @@ int fetch_summaries(pz_filter* f, uint32_t t0, int64_t k) {
 }
 
 // ancestors of the pending resample into f->g.anc (systematic: canonical; multinomial: step t)
+int sharded_advance(pz_filter* f, int delta, int* launches);
+
 int pending_ancestors(pz_filter* f, int* launches) {
   StepArgs& a = f->a;
   if (a.world > 1) return fail(PZ_ESTATE, "ancestor / particle taps are not available on a sharded filter");
@@ -496,8 +517,9 @@ int pending_ancestors(pz_filter* f, int* launches) {
   int n = 0;
   GenericArgs g{};
   g.lw = f->g.lw; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[1]; g.parity_ctl = a.ctl;
-  if (f->is_mtt) { g.q16 = f->g.q16; g.q16_alt = f->g.q16; }  // the tracker stores its log-weights (and their q16)
-  else { g.q16 = a.Q[0]; g.q16_alt = a.Q[1]; }
+  if (f->is_mtt || f->is_gen) {   // stored log-weights (and their q16); one eb buffer
+    g.q16 = f->g.q16; g.q16_alt = f->g.q16; g.eb = a.eb[0]; g.eb_alt = a.eb[0]; g.parity_ctl = nullptr;
+  } else { g.q16 = a.Q[0]; g.q16_alt = a.Q[1]; }
   g.xb = f->g.xb;
   g.sb = a.sb; g.pb = a.pb; g.tile_start = f->g.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
   g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk;
@@ -514,6 +536,7 @@ int pending_ancestors(pz_filter* f, int* launches) {
     n += launch_partition_only(b, kGenericTileOut, f->stream);
     n += launch_generic_ancestors(g, f->stream);
   }
+  if (f->is_gen && f->ga.ess_threshold > 0) n += launch_gen_anc_identity(f->ga, f->stream);  // no resample decided: the population itself
   if (launches) *launches += n;
   PZ_CUDA(cudaGetLastError());
   return PZ_OK;
@@ -585,6 +608,15 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
   PZ_NCCL(g_nccl.GroupEnd());
   *launches += launch_partition_ext(a, fused_tile_out(a.model.nx, a.f64), delta, s);
   PZ_CUDA(cudaGetLastError());
+  return PZ_OK;
+}
+
+// the error a step's summary implies (the same verdict on every rank)
+int report_step(pz_filter* f, const pz_step_summary& s, uint32_t t) {
+  if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t);
+  if (s.n_migrated == -2) return fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange", t);
+  if (s.n_migrated < 0)
+    return fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)", t, (long long)f->hb);
   return PZ_OK;
 }
 
@@ -858,15 +890,227 @@ int rb_step_host(pz_filter* f, const double* obs, pz_step_summary* out) {
   return PZ_OK;
 }
 
+
+// ---- generic-path filters (stored log-weights): carried weights, adaptive resampling, the walker ----------
+GenericArgs gen_generic(pz_filter* f) {
+  StepArgs& a = f->a;
+  GenericArgs g{};
+  g.lw = f->gen_lw[f->t & 1]; g.q16 = f->g.q16; g.q16_alt = f->g.q16; g.xb = a.xb; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[0];
+  g.parity_ctl = nullptr;
+  g.sb = a.sb; g.pb = a.pb; g.tile_start = a.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
+  g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk; g.ntiles_out = a.ntiles_out; g.nscan = a.nscan;
+  g.U = 0; g.seed = a.seed; g.step = f->t;
+  return g;
+}
+
+// stats of the stored log-weights of buffer `which` -> scan -> (summary) -> partition
+int gen_plan(pz_filter* f, int which, int delta) {
+  StepArgs& a = f->a;
+  GenericArgs g = gen_generic(f);
+  g.lw = f->gen_lw[which];
+  int n = launch_stats_from_lw(g, f->stream);
+  n += launch_scan_only(a, delta, f->stream);
+  if (delta) n += launch_gen_summary(f->ga, f->stream);
+  n += launch_partition_ext(a, kGenericTileOut, delta, f->stream);
+  return n;
+}
+
+int gen_start(pz_filter* f) {  // the prior population and its (trivial) plan
+  launch_ctl_reset(f->a.ctl, f->stream);
+  launch_gen_init(f->ga, f->stream);
+  gen_plan(f, 0, 0);
+  f->t = 0;
+  PZ_CUDA(cudaGetLastError());
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  return PZ_OK;
+}
+
+int create_gen(const pz_model_desc* model, uint64_t n, uint64_t seed, int device, pz_filter** out) {
+  const bool walker = model->kind == PZ_MODEL_WALKER;
+  if (!walker) {
+    if (!((model->nx == 1 && model->ny == 1) || (model->nx == 4 && model->ny == 2) || (model->nx == 6 && model->ny == 3)))
+      return fail(PZ_EINVAL, "no kernel instantiated for nx=%d ny=%d (supported: (1,1), (4,2), (6,3))", model->nx, model->ny);
+    if (model->state_f64) return fail(PZ_EINVAL, "carry_weights / ess_threshold filters store fp32 state (state_f64 = 0)");
+  }
+  if (n < 1 || n > (1ull << 28)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^28] on the stored-log-weight path");
+  if (!(model->ess_threshold >= 0.0 && model->ess_threshold <= 1.0)) return fail(PZ_EINVAL, "ess_threshold must be in [0, 1]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PZ_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  PZ_CUDA(cudaSetDevice(device));
+  pz_filter* f = new (std::nothrow) pz_filter();
+  if (!f) return fail(PZ_ENOMEM, "out of host memory");
+  f->desc = *model; f->device = device; f->is_gen = true;
+  StepArgs& a = f->a;
+  memset(&a, 0, sizeof(a));
+  double ll_const = 0;
+  if (walker) {
+    a.model.nx = 5; a.model.ny = 2; a.f64 = 1;
+    // two doubled scalar scores per step: each -log(2 pi) - log(sigma^2) (Distributions.hs:160-161)
+    const double v = model->walker.obs_std * model->walker.obs_std;
+    if (!(v > 0) || !(model->walker.dt > 0)) { delete f; return fail(PZ_EINVAL, "bad walker parameters"); }
+    ll_const = 0.0;  // the constant is inside score_normal_2x already
+  } else {
+    int rc = derive_lg(model, &a.model, &a.modeld, &ll_const);
+    if (rc) { delete f; return rc; }
+  }
+  a.ll_const = ll_const;
+  a.n_global = a.n_local = (int64_t)n; a.world = 1; a.seed = seed; a.resampler = model->resampler;
+  a.nblk = (a.n_local + kBlk - 1) / kBlk;
+  a.nscan = (int32_t)((a.nblk + kScanTile - 1) / kScanTile);
+  a.ntiles_out = (int32_t)((a.n_local + kGenericTileOut - 1) / kGenericTileOut);
+  a.ld = round_up(a.n_local, kPad);
+  const size_t esz = a.f64 ? 8 : 4;
+  const size_t xbytes = (size_t)a.model.nx * a.ld * esz;
+#define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
+  PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  PZ_TRY(cudaEventCreate(&f->ev0));
+  PZ_TRY(cudaEventCreate(&f->ev1));
+  for (int i = 0; i < 2; ++i) {
+    PZ_TRY(cudaMalloc(&f->xbuf[i], xbytes));
+    PZ_TRY(cudaMemsetAsync(f->xbuf[i], 0, xbytes, f->stream));
+    a.X[i] = f->xbuf[i];
+    PZ_TRY(cudaMalloc(&f->gen_lw[i], (size_t)a.ld * sizeof(float)));
+    PZ_TRY(cudaMemsetAsync(f->gen_lw[i], 0, (size_t)a.ld * sizeof(float), f->stream));
+  }
+  PZ_TRY(cudaMalloc(&f->ebbuf[0], (a.nblk + 8) * sizeof(int32_t)));
+  a.eb[0] = a.eb[1] = f->ebbuf[0];
+  PZ_TRY(cudaMalloc(&a.sb, (a.nblk + 8) * sizeof(uint64_t)));
+  PZ_TRY(cudaMalloc(&a.pb, (a.nblk + 8) * sizeof(uint64_t)));
+  a.pbx = a.pb; a.b_lo = 0; a.b_hi = a.nblk;
+  PZ_TRY(cudaMalloc(&f->xbbuf, (a.nblk + 8) * sizeof(uint64_t)));
+  a.xb = f->xbbuf;
+  PZ_TRY(cudaMalloc(&a.tile_start, (a.ntiles_out + 1) * sizeof(int32_t)));
+  PZ_TRY(cudaMalloc(&a.scan_status, (a.nscan + 1) * sizeof(uint64_t)));
+  PZ_TRY(cudaMemsetAsync(a.scan_status, 0, (a.nscan + 1) * sizeof(uint64_t), f->stream));
+  PZ_TRY(cudaMalloc(&a.scan_part, (size_t)(a.nscan + 1) * kMaxRec * sizeof(double)));
+  PZ_TRY(cudaMalloc(&a.plan, sizeof(PlanDev)));
+  PZ_TRY(cudaMemsetAsync(a.plan, 0, sizeof(PlanDev), f->stream));
+  PZ_TRY(cudaMalloc(&a.ctl, sizeof(CtlDev)));
+  PZ_TRY(cudaMemsetAsync(a.ctl, 0, sizeof(CtlDev), f->stream));
+  PZ_TRY(cudaMalloc(&a.summ, sizeof(pz_step_summary)));
+  PZ_TRY(cudaMemsetAsync(a.summ, 0, sizeof(pz_step_summary), f->stream));
+  PZ_TRY(cudaMallocHost(&f->h_summ, sizeof(pz_step_summary)));
+  PZ_TRY(cudaMalloc(&f->gen_obs, PZ_MAX_NY * sizeof(double)));
+  PZ_TRY(cudaMallocHost(&f->h_gen_obs, PZ_MAX_NY * sizeof(double)));
+  PZ_TRY(cudaMalloc(&f->gen_part, (size_t)gen_summary_parts(a.n_local) * gen_summary_rec() * sizeof(double)));
+  PZ_TRY(cudaMalloc(&f->gen_state, sizeof(GenState)));
+  {
+    int rc = generic_alloc(&f->g, a.n_local, false, f->stream);  // q16 + ancestors (+ an unused lw buffer)
+    if (rc) { free_filter(f); return rc; }
+  }
+  GenArgs& g = f->ga;
+  memset(&g, 0, sizeof(g));
+  g.kind = model->kind; g.carry_weights = model->carry_weights ? 1 : 0;
+  g.n_summary = walker ? 6 : a.model.nx;
+  g.ess_threshold = model->ess_threshold;
+  g.X[0] = a.X[0]; g.X[1] = a.X[1]; g.lw[0] = f->gen_lw[0]; g.lw[1] = f->gen_lw[1];
+  g.q16 = f->g.q16; g.eb = a.eb[0]; g.anc = f->g.anc; g.obs = f->gen_obs; g.plan = a.plan; g.ctl = a.ctl; g.gen = f->gen_state;
+  g.summ = a.summ; g.part = f->gen_part; g.n = a.n_local; g.ld = a.ld; g.seed = seed; g.ll_const = ll_const;
+  g.model = a.model; g.walker = model->walker;
+  {
+    int rc = gen_start(f);
+    if (rc) { free_filter(f); return rc; }
+  }
+#undef PZ_TRY
+  *out = f;
+  return PZ_OK;
+}
+
+int gen_step_host(pz_filter* f, const double* obs, int32_t obs_dim, pz_step_summary* out) {
+  StepArgs& a = f->a;
+  const uint32_t t0 = f->t;
+  for (int i = 0; i < PZ_MAX_NY; ++i) f->h_gen_obs[i] = i < obs_dim ? obs[i] : 0.0;
+  PZ_CUDA(cudaMemcpyAsync(f->gen_obs, f->h_gen_obs, PZ_MAX_NY * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+  int n = 0;
+  int rc = pending_ancestors(f, &n);   // canonical systematic (or multinomial) ancestors; identity when the adaptive rule says so
+  if (rc) return rc;
+  n += launch_gen_step(f->ga, f->stream);
+  n += gen_plan(f, (int)((t0 + 1) & 1u), 1);
+  f->t += 1;
+  PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+  PZ_CUDA(cudaMemcpyAsync(f->h_summ, a.summ, sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  PZ_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+  f->last_ms = ms; f->last_launches = n;
+  if (out) *out = *f->h_summ;
+  if (f->h_summ->total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", t0);
+  return PZ_OK;
+}
+
+int create_beta(const pz_model_desc* model, uint64_t n, int device, pz_filter** out) {
+  if (!(model->beta_a > 0) || !(model->beta_b > 0)) return fail(PZ_EINVAL, "the Beta prior needs a, b > 0");
+  if (!model->delayed) return fail(PZ_EINVAL, "the Beta-Bernoulli descriptor runs under delayed sampling (delayed = 1)");
+  if (n < 1 || n > (1ull << 30)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^30]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PZ_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  PZ_CUDA(cudaSetDevice(device));
+  pz_filter* f = new (std::nothrow) pz_filter();
+  if (!f) return fail(PZ_ENOMEM, "out of host memory");
+  f->desc = *model; f->device = device; f->is_rb = true; f->is_beta = true;
+  memset(&f->a, 0, sizeof(f->a));
+  f->a.model.nx = 1; f->a.model.ny = 1; f->a.n_local = f->a.n_global = (int64_t)n; f->a.world = 1;
+  BetaDev h{};
+  h.a = model->beta_a; h.b = model->beta_b; h.t = 0;
+#define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
+  PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  PZ_TRY(cudaEventCreate(&f->ev0));
+  PZ_TRY(cudaEventCreate(&f->ev1));
+  PZ_TRY(cudaMalloc(&f->beta, sizeof(BetaDev)));
+  PZ_TRY(cudaMemcpy(f->beta, &h, sizeof(BetaDev), cudaMemcpyHostToDevice));
+  PZ_TRY(cudaMalloc(&f->a.summ, sizeof(pz_step_summary)));
+  PZ_TRY(cudaMallocHost(&f->h_summ, sizeof(pz_step_summary)));
+#undef PZ_TRY
+  *out = f;
+  return PZ_OK;
+}
+
+int beta_step_host(pz_filter* f, const double* obs, pz_step_summary* out) {
+  if (!(obs[0] == 0.0 || obs[0] == 1.0)) return fail(PZ_EINVAL, "a Bernoulli observation is 0 or 1");
+  PZ_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(f->beta) + offsetof(BetaDev, y), obs, sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+  launch_beta_bernoulli(f->beta, f->a.summ, (double)f->a.n_local, f->stream);
+  PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+  PZ_CUDA(cudaMemcpyAsync(f->h_summ, f->a.summ, sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  PZ_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+  f->last_ms += ms; f->last_launches += 1;
+  f->t += 1;
+  if (out) *out = *f->h_summ;
+  return PZ_OK;
+}
+
+int capture_sharded_graphs(pz_filter* f);
+
+// shard_only: one shard of a single-process multi-device filter (pz_filter_create_multi): allocate and initialise,
+// leave the peer wiring, the first plan and the graph capture to the caller
 int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank, int world,
-                  const void* nccl_id, pz_filter** out) {
+                  const void* nccl_id, pz_filter** out, bool shard_only = false) {
   if (!model || !out) return fail(PZ_EINVAL, "null argument");
   *out = nullptr;
   if (model->kind == PZ_MODEL_MTT) {
     if (world != 1) return fail(PZ_EINVAL, "the tracker runs on one GPU");
     return create_mtt(model, n_global, seed, device, out);
   }
+  if (model->kind == PZ_MODEL_BETA_BERNOULLI) {
+    if (world != 1) return fail(PZ_EINVAL, "a delayed-sampling filter runs on one GPU (all particles are identical)");
+    return create_beta(model, n_global, device, out);
+  }
+  if (model->kind == PZ_MODEL_WALKER) {
+    if (world != 1) return fail(PZ_EINVAL, "the walker runs on one GPU");
+    return create_gen(model, n_global, seed, device, out);
+  }
   if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS) return fail(PZ_EINVAL, "unknown model kind %d", model->kind);
+  if (!model->delayed && (model->carry_weights || model->ess_threshold > 0)) {
+    if (world != 1) return fail(PZ_EINVAL, "carry_weights / ess_threshold filters run on one GPU (stored-log-weight path)");
+    return create_gen(model, n_global, seed, device, out);
+  }
   if (model->delayed) {
     if (world != 1) return fail(PZ_EINVAL, "a delayed-sampling filter runs on one GPU (all particles are identical)");
     return create_rb(model, n_global, device, out);
@@ -880,9 +1124,11 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
     if (n_global % ((uint64_t)world * kBlk) != 0)
       return fail(PZ_EINVAL, "a sharded filter needs n_particles divisible by world * 256 (whole resampling blocks per rank)");
     if (model->resampler != PZ_RESAMPLE_SYSTEMATIC) return fail(PZ_EINVAL, "sharded filters use the systematic resampler");
-    if (!nccl_id) return fail(PZ_EINVAL, "null nccl_unique_id");
-    int rc = load_nccl();
-    if (rc) return rc;
+    if (!shard_only) {
+      if (!nccl_id) return fail(PZ_EINVAL, "null nccl_unique_id");
+      int rc = load_nccl();
+      if (rc) return rc;
+    }
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
@@ -977,6 +1223,12 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
   PZ_TRY(cudaMallocHost(&f->h_obs64, (size_t)kObsRing * PZ_MAX_NY * sizeof(double)));
   PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
   launch_init(a, f->stream);
+  if (shard_only) {
+    PZ_TRY(cudaGetLastError());
+    PZ_TRY(cudaStreamSynchronize(f->stream));
+    *out = f;
+    return PZ_OK;
+  }
   if (world > 1) {
     ncclUniqueId id;
     memcpy(&id, nccl_id, sizeof(id));
@@ -1009,28 +1261,7 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
     f->shard_timing = true;
     for (auto& e : f->tev) PZ_TRY(cudaEventCreate(&e));
   }
-  if (world > 1 && !f->shard_timing && !getenv("PZ_NO_SHARD_GRAPH")) {
-    // one captured graph per buffer parity: step kernel, collectives, halo exchange (NCCL calls are capturable);
-    // a failed capture leaves the eager stream-ordered path in place
-    const uint32_t t_save = f->t;
-    for (int par = 0; par < 2; ++par) {
-      cudaGraph_t graph = nullptr;
-      f->t = (uint32_t)par;  // only the parity matters for the buffers named in the captured calls
-      bool ok = cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-      int n = 0;
-      if (ok) {
-        n = launch_tile_only(a, f->stream);
-        ok = sharded_advance(f, 1, &n) == PZ_OK;
-        ok = (cudaStreamEndCapture(f->stream, &graph) == cudaSuccess) && ok && graph;
-      }
-      if (ok) ok = cudaGraphInstantiate(&f->sgraph[par], graph, 0) == cudaSuccess;
-      if (graph) cudaGraphDestroy(graph);
-      if (!ok) { cudaGetLastError(); if (f->sgraph[par]) { cudaGraphExecDestroy(f->sgraph[par]); } f->sgraph[0] = f->sgraph[1] = nullptr; break; }
-      f->launches_per_step = n;
-    }
-    f->t = t_save;
-    if (f->sgraph[0] && !f->sgraph[1]) { cudaGraphExecDestroy(f->sgraph[0]); f->sgraph[0] = nullptr; }
-  }
+  if (world > 1 && !f->shard_timing) capture_sharded_graphs(f);
   // one captured graph serves every systematic step (the step index lives in ctl->t)
   if (world == 1 && a.resampler == PZ_RESAMPLE_SYSTEMATIC) {
     cudaGraph_t graph = nullptr;
@@ -1043,6 +1274,185 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
 #undef PZ_TRY
   *out = f;
   return PZ_OK;
+}
+
+
+// One captured graph per buffer parity: step kernel, exchange kernels (or NCCL calls, which are capturable); a failed
+// capture leaves the eager stream-ordered path in place.
+int capture_sharded_graphs(pz_filter* f) {
+  if (getenv("PZ_NO_SHARD_GRAPH")) return PZ_OK;
+  StepArgs& a = f->a;
+  const uint32_t t_save = f->t;
+  for (int par = 0; par < 2; ++par) {
+    cudaGraph_t graph = nullptr;
+    f->t = (uint32_t)par;  // only the parity matters for the buffers named in the captured calls
+    bool ok = cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int n = 0;
+    if (ok) {
+      n = launch_tile_only(a, f->stream);
+      ok = sharded_advance(f, 1, &n) == PZ_OK;
+      ok = (cudaStreamEndCapture(f->stream, &graph) == cudaSuccess) && ok && graph;
+    }
+    if (ok) ok = cudaGraphInstantiate(&f->sgraph[par], graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      for (int i = 0; i < 2; ++i) if (f->sgraph[i]) { cudaGraphExecDestroy(f->sgraph[i]); f->sgraph[i] = nullptr; }
+      break;
+    }
+    f->launches_per_step = n;
+  }
+  f->t = t_save;
+  return PZ_OK;
+}
+
+// ---- single-process multi-device filter (one host thread, the filter owns every device it is given) ----
+// The shards are the same sharded filters a multi-process host creates, wired with direct peer pointers
+// (cudaDeviceEnablePeerAccess) instead of CUDA IPC, and driven from one thread: every shard's step is enqueued
+// on its own device's stream (the kernels of different devices wait for each other through the mailboxes),
+// then all are awaited.
+int create_multi(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int n_devices, const int* device_ids, pz_filter** out) {
+  if (!model || !out || !device_ids) return fail(PZ_EINVAL, "null argument");
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > kMaxRanks) return fail(PZ_EINVAL, "n_devices must be in [1, %d]", kMaxRanks);
+  if (n_devices == 1) return create_common(model, n_global, seed, device_ids[0], 0, 1, nullptr, out);
+  for (int i = 0; i < n_devices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (device_ids[i] == device_ids[j]) return fail(PZ_EINVAL, "device %d listed twice", device_ids[i]);
+  if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS)
+    return fail(PZ_EINVAL, "multi-device filters: the linear-Gaussian families (RW1D / LINGAUSS)");
+  if (model->delayed || model->carry_weights || model->ess_threshold > 0)
+    return fail(PZ_EINVAL, "delayed-sampling / stored-log-weight filters run on one GPU");
+  pz_filter* parent = new (std::nothrow) pz_filter();
+  if (!parent) return fail(PZ_ENOMEM, "out of host memory");
+  parent->desc = *model; parent->is_multi = true; parent->device = device_ids[0];
+  memset(&parent->a, 0, sizeof(parent->a));
+  const int R = n_devices;
+  auto bail = [&](int code) { free_filter(parent); return code; };
+  for (int r = 0; r < R; ++r) {
+    pz_filter* sh = nullptr;
+    int rc = create_common(model, n_global, seed, device_ids[r], r, R, nullptr, &sh, true);
+    if (rc) return bail(rc);
+    parent->shards.push_back(sh);
+  }
+  parent->a = parent->shards[0]->a;   // model, sizes (a.n_local = particles per shard)
+  parent->a.world = R;
+  // peer access between every pair (mailboxes are all-to-all)
+  for (int r = 0; r < R; ++r) {
+    cudaSetDevice(device_ids[r]);
+    for (int q = 0; q < R; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, device_ids[r], device_ids[q]);
+      if (!can) return bail(fail(PZ_ECUDA, "device %d cannot access device %d (no peer path)", device_ids[r], device_ids[q]));
+      cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[q], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return bail(fail(PZ_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device_ids[r], device_ids[q], cudaGetErrorString(e)));
+      cudaGetLastError();
+    }
+  }
+#define PZ_TRYM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+  for (int r = 0; r < R; ++r) {
+    pz_filter* sh = parent->shards[r];
+    PZ_TRYM(cudaSetDevice(sh->device));
+    PZ_TRYM(cudaMalloc(&sh->mbox, sizeof(Mailbox)));
+    PZ_TRYM(cudaMemset(sh->mbox, 0, sizeof(Mailbox)));
+    PZ_TRYM(cudaStreamCreateWithFlags(&sh->push_stream, cudaStreamNonBlocking));
+    PZ_TRYM(cudaEventCreateWithFlags(&sh->ev_fork, cudaEventDisableTiming));
+    PZ_TRYM(cudaEventCreateWithFlags(&sh->ev_join, cudaEventDisableTiming));
+    PZ_TRYM(cudaDeviceSynchronize());
+  }
+  for (int r = 0; r < R; ++r) {
+    pz_filter* sh = parent->shards[r];
+    PZ_TRYM(cudaSetDevice(sh->device));
+    ShardP2P h{};
+    const size_t esz = sh->a.f64 ? 8 : 4;
+    const int64_t H = sh->hb * kBlk;
+    for (int q = 0; q < R; ++q) h.mbox[q] = parent->shards[q]->mbox;
+    for (int side = 0; side < 2; ++side) {
+      const int q = side == 0 ? r - 1 : r + 1;
+      if (q < 0 || q >= R) continue;
+      pz_filter* nb = parent->shards[q];
+      for (int b = 0; b < 2; ++b) {
+        h.Xn[side][b] = (char*)nb->xbuf[b] + (size_t)H * esz;
+        h.Qn[side][b] = nb->qbuf[b] + H;
+        h.ebn[side][b] = nb->ebbuf[b] + nb->hb;
+      }
+      h.pbxn[side] = nb->pbxbuf + nb->hb;
+    }
+    PZ_TRYM(cudaMalloc(&sh->d_p2p, sizeof(ShardP2P)));
+    PZ_TRYM(cudaMemcpy(sh->d_p2p, &h, sizeof(ShardP2P), cudaMemcpyHostToDevice));
+    sh->a.p2p = sh->d_p2p;
+  }
+  // the plan of the prior population: every shard's exchange kernels are enqueued before any is awaited
+  for (int r = 0; r < R; ++r) {
+    pz_filter* sh = parent->shards[r];
+    PZ_TRYM(cudaSetDevice(sh->device));
+    int n = 0;
+    int rc = sharded_advance(sh, 0, &n);
+    if (rc) return bail(rc);
+  }
+  for (int r = 0; r < R; ++r) {
+    pz_filter* sh = parent->shards[r];
+    PZ_TRYM(cudaSetDevice(sh->device));
+    PZ_TRYM(cudaStreamSynchronize(sh->stream));
+  }
+  for (int r = 0; r < R; ++r) {
+    pz_filter* sh = parent->shards[r];
+    PZ_TRYM(cudaSetDevice(sh->device));
+    capture_sharded_graphs(sh);
+  }
+#undef PZ_TRYM
+  *out = parent;
+  return PZ_OK;
+}
+
+int report_step(pz_filter* f, const pz_step_summary& s, uint32_t t);
+
+// one or k steps on every shard: enqueue everywhere, then await everywhere
+int multi_advance(pz_filter* p, const double* obs, int64_t k, int32_t obs_dim, pz_step_summary* out, bool run) {
+  const uint32_t t0 = p->t;
+  for (pz_filter* sh : p->shards) {
+    PZ_CUDA(cudaSetDevice(sh->device));
+    sh->last_launches = 0;
+    int rc = stage_obs(sh, obs, k, obs_dim);
+    if (rc) return rc;
+    PZ_CUDA(cudaEventRecord(sh->ev0, sh->stream));
+    for (int64_t i = 0; i < k; ++i) {
+      rc = enqueue_step(sh);
+      if (rc) return rc;
+    }
+    PZ_CUDA(cudaEventRecord(sh->ev1, sh->stream));
+    rc = fetch_summaries(sh, t0, k);
+    if (rc) return rc;
+  }
+  double ms_max = 0;
+  int64_t launches = 0;
+  for (pz_filter* sh : p->shards) {
+    PZ_CUDA(cudaSetDevice(sh->device));
+    PZ_CUDA(cudaStreamSynchronize(sh->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sh->ev0, sh->ev1);
+    ms_max = ms > ms_max ? ms : ms_max;
+    launches += sh->last_launches;
+  }
+  p->t += (uint32_t)k;
+  p->last_ms = run ? p->last_ms + ms_max : ms_max;
+  p->last_launches = run ? p->last_launches + launches : launches;
+  int status = PZ_OK;
+  for (int64_t i = 0; i < k; ++i) {
+    pz_step_summary s = p->shards[0]->h_summ[(t0 + i) % kObsRing];   // every shard derives the same posterior summary
+    int64_t mig = 0;
+    for (pz_filter* sh : p->shards) {
+      const int64_t m = sh->h_summ[(t0 + i) % kObsRing].n_migrated;
+      if (m < 0) { mig = m; break; }   // an error verdict (the same on every shard)
+      mig += m;
+    }
+    s.n_migrated = mig;
+    if (out) out[i] = s;
+    if (status == PZ_OK) status = report_step(p->shards[0], s, t0 + (uint32_t)i);
+  }
+  return status;
 }
 
 }  // namespace
@@ -1115,8 +1525,36 @@ int pz_model_mtt(pz_model_desc* d) {
   return PZ_OK;
 }
 
+int pz_model_walker(pz_model_desc* d) {
+  if (!d) return fail(PZ_EINVAL, "null descriptor");
+  fill_common(d, PZ_MODEL_WALKER, 5, 2);
+  d->carry_weights = 1;                 // runOurFilter = particles 1000 (Walker.hs:129-131; Inference.hs:85-86)
+  pz_walker_params& w = d->walker;
+  w.pos_noise = 0.01; w.obs_std = 10.0; w.dt = 10.0;
+  w.p_init[0] = 0.7; w.p_init[1] = 0.25; w.p_init[2] = 0.05;
+  // motionTypeTransition (Walker.hs:45-49): half lives in seconds, [from][to]
+  w.half_life[0][1] = 30.0; w.half_life[0][2] = 300.0;
+  w.half_life[1][1] = 1.0; w.half_life[1][0] = 10.0; w.half_life[1][2] = 60.0;
+  w.half_life[2][2] = 0.5; w.half_life[2][1] = 2.0;
+  w.speed_lo[1] = 0.0; w.speed_hi[1] = 2.0; w.speed_lo[2] = 2.0; w.speed_hi[2] = 7.0;
+  w.exp_mean_as_written = 1;
+  return PZ_OK;
+}
+
+int pz_model_beta_bernoulli(pz_model_desc* d, double a, double b) {
+  if (!d || !(a > 0) || !(b > 0)) return fail(PZ_EINVAL, "bad Beta parameters");
+  fill_common(d, PZ_MODEL_BETA_BERNOULLI, 1, 1);
+  d->delayed = 1; d->beta_a = a; d->beta_b = b;
+  return PZ_OK;
+}
+
 int pz_filter_create(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int device, pz_filter** out) {
   return create_common(model, n_particles, seed, device, 0, 1, nullptr, out);
+}
+
+int pz_filter_create_multi(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int n_devices, const int* device_ids,
+                           pz_filter** out) {
+  return create_multi(model, n_particles, seed, n_devices, device_ids, out);
 }
 
 int pz_comm_unique_id(void* out128) {
@@ -1151,7 +1589,10 @@ int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_ran
   return PZ_OK;
 }
 
-int64_t pz_filter_n_local(const pz_filter* f) { return f ? f->a.n_local : 0; }
+int64_t pz_filter_n_local(const pz_filter* f) {
+  if (!f) return 0;
+  return f->is_multi ? f->a.n_local * (int64_t)f->shards.size() : f->a.n_local;   // a multi-device handle holds the whole population
+}
 
 int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, pz_step_summary* out) {
   if (!f || (!obs && n_obs > 0)) return fail(PZ_EINVAL, "null argument");
@@ -1161,8 +1602,11 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
     return mtt_step_host(f, obs, n_obs, out);
   }
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d, got %d x %d", f->a.model.ny, n_obs, obs_dim);
+  if (f->is_multi) return multi_advance(f, obs, 1, obs_dim, out, false);
   PZ_CUDA(cudaSetDevice(f->device));
+  if (f->is_beta) { f->last_ms = 0; f->last_launches = 0; return beta_step_host(f, obs, out); }
   if (f->is_rb) { f->last_ms = 0; f->last_launches = 0; return rb_step_host(f, obs, out); }
+  if (f->is_gen) return gen_step_host(f, obs, obs_dim, out);
   const uint32_t t0 = f->t;
   f->last_launches = 0;
   int rc = stage_obs(f, obs, 1, obs_dim);
@@ -1179,17 +1623,13 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
   f->last_ms = ms;
   pz_step_summary& s = f->h_summ[t0 % kObsRing];
   if (out) *out = s;
-  if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t0);
-  if (s.n_migrated == -2) return fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange", t0);
-  if (s.n_migrated < 0)
-    return fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)", t0, (long long)f->hb);
-  return PZ_OK;
+  return report_step(f, s, t0);
 }
 
 int pz_filter_step_profile(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, double ms[3]) {
   if (!f || !obs || !ms) return fail(PZ_EINVAL, "null argument");
   if (n_obs != 1 || obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected 1 observation of dim %d", f->a.model.ny);
-  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1 || f->is_mtt || f->is_rb)
+  if (f->a.resampler != PZ_RESAMPLE_SYSTEMATIC || f->a.world > 1 || f->is_mtt || f->is_rb || f->is_gen || f->is_multi)
     return fail(PZ_ESTATE, "profiled step: single-GPU systematic filters only");
   PZ_CUDA(cudaSetDevice(f->device));
   cudaEvent_t ev[4] = {};
@@ -1216,14 +1656,31 @@ int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_
   if (!f || !obs || n_steps < 0) return fail(PZ_EINVAL, "bad argument");
   if (f->is_mtt) return fail(PZ_ESTATE, "pz_filter_run: the tracker takes a variable number of observations per step; use pz_filter_step");
   if (obs_dim != f->a.model.ny) return fail(PZ_EINVAL, "expected observations of dim %d", f->a.model.ny);
-  PZ_CUDA(cudaSetDevice(f->device));
   f->last_launches = 0;
   f->last_ms = 0;
-  if (f->is_rb) {
-    for (int64_t i = 0; i < n_steps; ++i) {
-      int rc = rb_step_host(f, obs + i * obs_dim, out ? out + i : nullptr);
-      if (rc) return rc;
+  if (f->is_multi) {
+    int64_t done = 0;
+    int status = PZ_OK;
+    while (done < n_steps) {
+      const int64_t k = (n_steps - done) < (kObsRing - 1) ? (n_steps - done) : (kObsRing - 1);
+      int rc = multi_advance(f, obs + done * obs_dim, k, obs_dim, out ? out + done : nullptr, true);
+      if (rc && status == PZ_OK) status = rc;
+      if (rc == PZ_ECUDA || rc == PZ_EINVAL) return rc;
+      done += k;
     }
+    return status;
+  }
+  PZ_CUDA(cudaSetDevice(f->device));
+  if (f->is_rb || f->is_gen) {
+    double ms = 0; int64_t nl = 0;
+    for (int64_t i = 0; i < n_steps; ++i) {
+      int rc = f->is_beta ? beta_step_host(f, obs + i * obs_dim, out ? out + i : nullptr)
+               : f->is_rb ? rb_step_host(f, obs + i * obs_dim, out ? out + i : nullptr)
+                          : gen_step_host(f, obs + i * obs_dim, obs_dim, out ? out + i : nullptr);
+      if (rc) return rc;
+      if (f->is_gen) { ms += f->last_ms; nl += f->last_launches; }
+    }
+    if (f->is_gen) { f->last_ms = ms; f->last_launches = nl; }
     return PZ_OK;
   }
   int64_t done = 0;
@@ -1248,13 +1705,7 @@ int pz_filter_run(pz_filter* f, const double* obs, int64_t n_steps, int32_t obs_
     for (int64_t i = 0; i < k; ++i) {
       const pz_step_summary& s = f->h_summ[(t0 + i) % kObsRing];
       if (out) out[done + i] = s;
-      if (s.total_weight == 0 && status == PZ_OK)
-        status = fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", (unsigned)(t0 + i));
-      if (s.n_migrated == -2 && status == PZ_OK)
-        status = fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange", (unsigned)(t0 + i));
-      if (s.n_migrated < 0 && status == PZ_OK)
-        status = fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)",
-                      (unsigned)(t0 + i), (long long)f->hb);
+      if (status == PZ_OK) status = report_step(f, s, t0 + (uint32_t)i);
     }
     done += k;
   }
@@ -1270,10 +1721,25 @@ int pz_filter_last_timing(pz_filter* f, double* ms, int64_t* launches) {
 
 static int read_state_common(pz_filter* f, float* out32, double* out64, int64_t out_len) {
   if (!f || (!out32 && !out64)) return fail(PZ_EINVAL, "null argument");
+  if (f->is_multi) {   // shard after shard: out[d][r * n_shard + i]
+    const int R = (int)f->shards.size(), nx = f->a.model.nx;
+    const int64_t ns = f->a.n_local, n = ns * R;
+    if (out_len < nx * n) return fail(PZ_EINVAL, "buffer too small: need %lld scalars", (long long)(nx * n));
+    std::vector<float> t32(out32 ? (size_t)nx * ns : 0);
+    std::vector<double> t64(out64 ? (size_t)nx * ns : 0);
+    for (int r = 0; r < R; ++r) {
+      int rc = read_state_common(f->shards[r], out32 ? t32.data() : nullptr, out64 ? t64.data() : nullptr, nx * ns);
+      if (rc) return rc;
+      for (int d = 0; d < nx; ++d) {
+        if (out32) memcpy(out32 + (size_t)d * n + (size_t)r * ns, t32.data() + (size_t)d * ns, ns * sizeof(float));
+        if (out64) memcpy(out64 + (size_t)d * n + (size_t)r * ns, t64.data() + (size_t)d * ns, ns * sizeof(double));
+      }
+    }
+    return PZ_OK;
+  }
   const StepArgs& a = f->a;
   if (f->is_mtt) return fail(PZ_ESTATE, "tracker state is read with pz_filter_read_tracks");
   if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter holds no sampled state; use pz_filter_read_posterior");
-  if (f->is_gen) return fail(PZ_ESTATE, "this filter's state is read with pz_filter_read_particles");
   if (out_len < a.model.nx * a.n_local) return fail(PZ_EINVAL, "buffer too small: need %lld scalars", (long long)(a.model.nx * a.n_local));
   if (out32 && a.f64) return fail(PZ_ESTATE, "the filter stores its state in double (state_f64 = 1): use pz_filter_read_state_f64");
   PZ_CUDA(cudaSetDevice(f->device));
@@ -1302,6 +1768,13 @@ int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out) {
   if (!f->is_rb) return fail(PZ_ESTATE, "not a delayed-sampling filter (model.delayed = 0)");
   PZ_CUDA(cudaSetDevice(f->device));
   PZ_CUDA(cudaStreamSynchronize(f->stream));
+  if (f->is_beta) {   // MBeta alpha beta (DelayedSampling.hs:63,72)
+    BetaDev h;
+    PZ_CUDA(cudaMemcpy(&h, f->beta, sizeof(BetaDev), cudaMemcpyDeviceToHost));
+    const double s = h.a + h.b;
+    mean_out[0] = h.a; mean_out[1] = h.b; cov_out[0] = h.a * h.b / (s * s * (s + 1.0));
+    return PZ_OK;
+  }
   RbDev h;
   PZ_CUDA(cudaMemcpy(&h, f->rb, sizeof(RbDev), cudaMemcpyDeviceToHost));
   const int nx = h.nx;
@@ -1312,6 +1785,7 @@ int pz_filter_read_posterior(pz_filter* f, double* mean_out, double* cov_out) {
 
 static int read_logw_common(pz_filter* f, float* out32, double* out64, int64_t n) {
   if (!f || (!out32 && !out64)) return fail(PZ_EINVAL, "null argument");
+  if (f->is_multi) return fail(PZ_ESTATE, "log-weight taps are per shard; not available on a multi-device handle");
   if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter has equal weights and no sampled state");
   if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
   PZ_CUDA(cudaSetDevice(f->device));
@@ -1321,7 +1795,7 @@ static int read_logw_common(pz_filter* f, float* out32, double* out64, int64_t n
     if (!f->g.lw64) PZ_CUDA(cudaMalloc(&f->g.lw64, (size_t)round_up(f->a.n_local, kPad) * sizeof(double)));
     if (f->is_mtt || f->is_gen) {  // stored fp32 log-weights: widen on the host
       std::vector<float> tmp((size_t)f->a.n_local);
-      PZ_CUDA(cudaMemcpyAsync(tmp.data(), f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+      PZ_CUDA(cudaMemcpyAsync(tmp.data(), f->is_gen ? f->gen_lw[f->t & 1] : f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
       PZ_CUDA(cudaStreamSynchronize(f->stream));
       for (int64_t i = 0; i < f->a.n_local; ++i) out64[i] = (double)tmp[i];
       return PZ_OK;
@@ -1330,7 +1804,7 @@ static int read_logw_common(pz_filter* f, float* out32, double* out64, int64_t n
     PZ_CUDA(cudaMemcpyAsync(out64, f->g.lw64, f->a.n_local * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   } else {
     if (!f->is_mtt && !f->is_gen) launch_logw(f->a, f->g.lw, nullptr, f->stream);
-    PZ_CUDA(cudaMemcpyAsync(out32, f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+    PZ_CUDA(cudaMemcpyAsync(out32, f->is_gen ? f->gen_lw[f->t & 1] : f->g.lw, f->a.n_local * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
   }
   PZ_CUDA(cudaStreamSynchronize(f->stream));
   return PZ_OK;
@@ -1362,6 +1836,7 @@ int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t 
     double mean[PZ_MAX_NX], cov[PZ_MAX_NX * PZ_MAX_NX];
     int rc = pz_filter_read_posterior(f, mean, cov);
     if (rc) return rc;
+    if (f->is_beta) mean[0] = mean[0] / (mean[0] + mean[1]);
     for (int64_t i = 0; i < n_sel; ++i)
       for (int d = 0; d < a.model.nx; ++d) out[i * a.model.nx + d] = mean[d];
     return PZ_OK;
@@ -1420,8 +1895,8 @@ void pz_filter_destroy(pz_filter* f) { free_filter(f); }
 
 // ---- standalone resamplers on stored log-weights --------------------------------------------
 static int standalone(const double* logw, int64_t n, bool multinomial, uint32_t U, uint64_t seed, uint32_t step,
-                      int32_t* anc_out) {
-  if (!logw || !anc_out || n < 1 || n > (1ll << 30)) return fail(PZ_EINVAL, "bad argument");
+                      int32_t* anc_out, int64_t n_draws = 0) {
+  if (!logw || !anc_out || n < 1 || n > (1ll << 30) || n_draws < 0 || n_draws > n) return fail(PZ_EINVAL, "bad argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
   GenericScratch gs;
@@ -1437,7 +1912,7 @@ static int standalone(const double* logw, int64_t n, bool multinomial, uint32_t 
   g.n = n; g.nblk = (n + kBlk - 1) / kBlk;
   g.ntiles_out = (int32_t)((n + kGenericTileOut - 1) / kGenericTileOut);
   g.nscan = (int32_t)((g.nblk + kScanTile - 1) / kScanTile);
-  g.U = U; g.seed = seed; g.step = step;
+  g.U = U; g.seed = seed; g.step = step; g.n_draws = n_draws;
   PlanDev plan;
   cudaError_t e = cudaMemcpy(gs.lw, lw32.data(), n * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
@@ -1448,7 +1923,7 @@ static int standalone(const double* logw, int64_t n, bool multinomial, uint32_t 
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(&plan, gs.plan, sizeof(plan), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && !plan.degenerate) e = cudaMemcpy(anc_out, gs.anc, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && !plan.degenerate) e = cudaMemcpy(anc_out, gs.anc, (n_draws > 0 ? n_draws : n) * sizeof(int32_t), cudaMemcpyDeviceToHost);
   gs.release();
   if (e != cudaSuccess) return fail(PZ_ECUDA, "resample: %s", cudaGetErrorString(e));
   if (plan.degenerate) return fail(PZ_EDEGENERATE, "every log-weight is -inf or NaN");
@@ -1462,6 +1937,86 @@ int pz_resample_systematic(const double* logw, int64_t n, double u, int32_t* anc
 
 int pz_resample_multinomial(const double* logw, int64_t n, uint64_t seed, uint32_t step, int32_t* anc_out) {
   return standalone(logw, n, true, 0, seed, step, anc_out);
+}
+
+int pz_importance_resampling(const double* logw, int64_t n, uint64_t seed, uint32_t step, int64_t k, int32_t* idx_out) {
+  if (k < 1) return fail(PZ_EINVAL, "k must be at least 1");
+  return standalone(logw, n, true, 0, seed, step, idx_out, k);
+}
+
+static int dist_tap(bool sample, int32_t kind, const double* params, int32_t np, uint64_t seed, const double* x, int64_t n, double* out) {
+  static const int need[7] = {0, 1, 1, 1, 2, 1, 2};
+  if (!params || !out || n < 1 || kind < 1 || kind > 6 || np < need[kind] || np > 8 || (!sample && !x)) return fail(PZ_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PZ_ECUDA, "no CUDA device (this library has no CPU fallback)");
+  double *d_x = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, n * sizeof(double));
+  if (e == cudaSuccess && !sample) e = cudaMalloc(&d_x, n * sizeof(double));
+  if (e == cudaSuccess && !sample) e = cudaMemcpy(d_x, x, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_dist(sample, kind, params, np, seed, n, d_x, d_out, nullptr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_x); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(PZ_ECUDA, "pz_dist: %s", cudaGetErrorString(e));
+  return PZ_OK;
+}
+
+int pz_dist_sample(int32_t kind, const double* params, int32_t n_params, uint64_t seed, int64_t n, double* out) {
+  return dist_tap(true, kind, params, n_params, seed, nullptr, n, out);
+}
+
+int pz_dist_score(int32_t kind, const double* params, int32_t n_params, const double* x, int64_t n, double* out) {
+  return dist_tap(false, kind, params, n_params, 0, x, n, out);
+}
+
+int pz_filter_reset(pz_filter* f, uint64_t seed) {
+  if (!f) return fail(PZ_EINVAL, "null filter");
+  if (f->a.world > 1 || f->is_multi) return fail(PZ_ESTATE, "pz_filter_reset: single-GPU filters only (destroy and re-create the shards together)");
+  PZ_CUDA(cudaSetDevice(f->device));
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  cudaGetLastError();
+  if (f->is_beta) {
+    BetaDev h{};
+    h.a = f->desc.beta_a; h.b = f->desc.beta_b;
+    PZ_CUDA(cudaMemcpy(f->beta, &h, sizeof(h), cudaMemcpyHostToDevice));
+    f->t = 0;
+    return PZ_OK;
+  }
+  if (f->is_rb) {
+    RbDev h;
+    PZ_CUDA(cudaMemcpy(&h, f->rb, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < PZ_MAX_NX; ++i) h.mean[i] = i < h.nx ? f->desc.x0[i] : 0.0;
+    memset(h.cov, 0, sizeof(h.cov));
+    h.t = 0;
+    PZ_CUDA(cudaMemcpy(f->rb, &h, sizeof(h), cudaMemcpyHostToDevice));
+    f->t = 0;
+    return PZ_OK;
+  }
+  if (f->is_mtt) return fail(PZ_ESTATE, "pz_filter_reset: not available for the tracker (destroy and re-create)");
+  if (f->is_gen) {
+    f->a.seed = seed; f->ga.seed = seed;
+    return gen_start(f);
+  }
+  StepArgs& a = f->a;
+  a.seed = seed;
+  launch_init(a, f->stream);
+  launch_scan_partition(a, fused_tile_out(a.model.nx, a.f64), f->stream);
+  PZ_CUDA(cudaGetLastError());
+  PZ_CUDA(cudaStreamSynchronize(f->stream));
+  f->t = 0;
+  if (f->graph) {   // the captured step carries the seed by value: capture it again
+    cudaGraphExecDestroy(f->graph);
+    f->graph = nullptr;
+    cudaGraph_t graph = nullptr;
+    PZ_CUDA(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+    f->launches_per_step = launch_step(a, nullptr, f->stream);
+    PZ_CUDA(cudaStreamEndCapture(f->stream, &graph));
+    PZ_CUDA(cudaGraphInstantiate(&f->graph, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  return PZ_OK;
 }
 
 }  // extern "C"

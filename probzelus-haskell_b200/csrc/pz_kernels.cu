@@ -31,6 +31,7 @@
 
 #include "pz_kernels.cuh"
 #include "pz_math.cuh"
+#include "pz_model.cuh"
 
 namespace pz {
 
@@ -161,114 +162,6 @@ __device__ __forceinline__ long long mad_wide_u32(uint32_t a, uint32_t b, long l
   long long d;
   asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
   return d;
-}
-
-// ------------------------------------------------------------------------------------------
-// individually rounded IEEE operations in the filter's arithmetic type (float or double)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float r_mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double r_mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float r_add(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double r_add(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float r_sub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double r_sub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ float r_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ double r_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
-__device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
-template <class T> __device__ __forceinline__ const LgDevT<T>& model_of(const StepArgs& a);
-template <> __device__ __forceinline__ const LgDevT<float>& model_of<float>(const StepArgs& a) { return a.model; }
-template <> __device__ __forceinline__ const LgDevT<double>& model_of<double>(const StepArgs& a) { return a.modeld; }
-// observation row of step t in the filter's arithmetic type
-template <class T, int NY>
-__device__ __forceinline__ void load_obs(const StepArgs& a, uint32_t t, T (&y)[NY]) {
-#pragma unroll
-  for (int k = 0; k < NY; ++k) {
-    if constexpr (sizeof(T) == 8) y[k] = a.obs64[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
-    else y[k] = a.obs[(size_t)(t % kObsRing) * PZ_MAX_NY + k];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// linear-Gaussian model step (same operation order as the oracle's lg_propagate / lg_logweight)
-// ------------------------------------------------------------------------------------------
-template <int NX, class T>
-__device__ __forceinline__ void lg_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
-#pragma unroll
-  for (int r = 0; r < NX; ++r) {
-    T acc = r_mul(p.F[r][0], x[0]);
-#pragma unroll
-    for (int c = 1; c < NX; ++c) acc = r_fma(p.F[r][c], x[c], acc);
-#pragma unroll
-    for (int c = 0; c <= r; ++c) acc = r_fma(p.Lq[r][c], z[c], acc);
-    xn[r] = acc;
-  }
-}
-
-template <int NX, int NY, class T>
-__device__ __forceinline__ T lg_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
-  T d[NY];
-#pragma unroll
-  for (int k = 0; k < NY; ++k) {
-    T acc = r_mul(p.H[k][0], xn[0]);
-#pragma unroll
-    for (int c = 1; c < NX; ++c) acc = r_fma(p.H[k][c], xn[c], acc);
-    d[k] = r_sub(y[k], acc);
-  }
-  T quad = 0;
-#pragma unroll
-  for (int k = 0; k < NY; ++k) {
-    T t = r_mul(p.Rinv[k][0], d[0]);
-#pragma unroll
-    for (int l = 1; l < NY; ++l) t = r_fma(p.Rinv[k][l], d[l], t);
-    quad = (k == 0) ? r_mul(d[0], t) : r_fma(d[k], t, quad);
-  }
-  return r_mul(p.wscale, quad);
-}
-
-// position/velocity structured variants (LgDev::kron): same operations as the dense code minus the
-// terms whose coefficient is zero
-template <int NX, class T>
-__device__ __forceinline__ void kron_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
-  if constexpr (NX == 1) {  // F = 1: fl(1 * x) = x, so fma(L, z, fl(F x)) = fma(L, z, x)
-    xn[0] = r_fma(p.klp, z[0], x[0]);
-    return;
-  }
-  constexpr int P = NX / 2;
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    T acc = r_mul(p.ka, x[i]);
-    acc = r_fma(p.kb, x[P + i], acc);
-    xn[i] = r_fma(p.klp, z[i], acc);
-  }
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    T acc;
-    if (p.kc != (T)0) { acc = r_mul(p.kc, x[i]); acc = r_fma(p.kd, x[P + i], acc); }
-    else acc = r_mul(p.kd, x[P + i]);
-    xn[P + i] = r_fma(p.klv, z[P + i], acc);
-  }
-}
-
-template <int NX, int NY, class T>
-__device__ __forceinline__ T kron_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
-  T quad = 0;
-#pragma unroll
-  for (int k = 0; k < NY; ++k) {
-    const T d = r_sub(y[k], xn[k]);
-    const T t = r_mul(p.krinv, d);
-    quad = (k == 0) ? r_mul(d, t) : r_fma(d, t, quad);
-  }
-  return r_mul(p.wscale, quad);
-}
-
-template <int NX, bool KRON, class T>
-__device__ __forceinline__ void model_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
-  if constexpr (KRON) kron_propagate<NX>(p, x, z, xn); else lg_propagate<NX>(p, x, z, xn);
-}
-template <int NX, int NY, bool KRON, class T>
-__device__ __forceinline__ T model_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
-  if constexpr (KRON) return kron_logweight<NX, NY>(p, xn, y); else return lg_logweight<NX, NY>(p, xn, y);
 }
 
 // normals of the 4 consecutive slots j..j+3 (j % 4 == 0): z[d][k]; one Philox word per normal.  A double
@@ -1379,7 +1272,7 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
 // N iid categorical draws on the canonical fixed-point CDF (resample2, Inference.hs:57-61)
 __global__ void __launch_bounds__(kThreads) pf_multinomial(const GenericArgs g) {
   const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (j >= g.n) return;
+  if (j >= (g.n_draws > 0 ? g.n_draws : g.n)) return;
   const PlanDev* pl = g.plan;
   const u64 total = pl->total;
   U4 r = philox4x32_10((uint32_t)j, 0u, g.step, kStreamMulti, (uint32_t)g.seed, (uint32_t)(g.seed >> 32));
@@ -1872,7 +1765,7 @@ int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s) {
 }
 
 int launch_generic_multinomial(const GenericArgs& g, cudaStream_t s) {
-  pf_multinomial<<<cdiv(g.n, kThreads), kThreads, 0, s>>>(g);
+  pf_multinomial<<<cdiv(g.n_draws > 0 ? g.n_draws : g.n, kThreads), kThreads, 0, s>>>(g);
   return 1;
 }
 

@@ -189,6 +189,7 @@ struct GenericArgs {
   uint32_t U;            // explicit uniform (standalone API)
   uint64_t seed;         // multinomial
   uint32_t step;
+  int64_t n_draws;       // multinomial: number of iid draws (0: n)
 };
 int launch_ctl_reset(CtlDev* ctl, cudaStream_t s);
 int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s);

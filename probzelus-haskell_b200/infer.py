@@ -16,7 +16,8 @@ import numpy as np
 
 PZ_MAX_NX, PZ_MAX_NY = 6, 3
 PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF = 0, 1
-PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT = 1, 2, 3
+PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT, PZ_MODEL_WALKER, PZ_MODEL_BETA_BERNOULLI = 1, 2, 3, 4, 5
+PZ_DIST = {"bernoulli": 1, "categorical": 2, "poisson": 3, "uniform": 4, "exponential": 5, "normal": 6}
 _ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENCCL", -4: "EDEGENERATE", -5: "ECAPACITY", -6: "ENOMEM", -7: "ESTATE"}
 
 
@@ -33,13 +34,22 @@ class MttParams(C.Structure):
                 ("m_max", C.c_int32)]
 
 
+class WalkerParams(C.Structure):
+    """pz_walker_params (include/pzgpu.h): Examples/Walker.hs constants."""
+    _fields_ = [("pos_noise", C.c_double), ("obs_std", C.c_double), ("dt", C.c_double), ("p_init", C.c_double * 3),
+                ("half_life", (C.c_double * 3) * 3), ("speed_lo", C.c_double * 3), ("speed_hi", C.c_double * 3),
+                ("exp_mean_as_written", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ModelDesc(C.Structure):
     """pz_model_desc (include/pzgpu.h)."""
     _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
                 ("resampler", C.c_int32), ("delayed", C.c_int32), ("state_f64", C.c_int32), ("reserved", C.c_int32),
                 ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
                 ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
-                ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]
+                ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams),
+                ("ess_threshold", C.c_double), ("carry_weights", C.c_int32), ("reserved2", C.c_int32),
+                ("walker", WalkerParams), ("beta_a", C.c_double), ("beta_b", C.c_double)]
 
 
 class StepSummary(C.Structure):
@@ -54,7 +64,8 @@ _SYMBOLS = [
     "pz_filter_create", "pz_comm_unique_id", "pz_filter_create_sharded", "pz_filter_step", "pz_filter_run",
     "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_tracks", "pz_filter_read_ancestors", "pz_filter_read_state",
     "pz_filter_read_logw", "pz_filter_read_state_f64", "pz_filter_read_logw_f64", "pz_filter_read_posterior", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
-    "pz_filter_destroy", "pz_shard_halo_range",
+    "pz_filter_destroy", "pz_shard_halo_range", "pz_model_walker", "pz_model_beta_bernoulli", "pz_importance_resampling",
+    "pz_dist_sample", "pz_dist_score", "pz_filter_reset", "pz_filter_create_multi",
 ]
 
 
@@ -110,6 +121,13 @@ def lib():
     L.pz_shard_halo_range.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pz_filter_destroy.argtypes = [C.c_void_p]
     L.pz_filter_destroy.restype = None
+    L.pz_model_walker.argtypes = [C.POINTER(ModelDesc)]
+    L.pz_model_beta_bernoulli.argtypes = [C.POINTER(ModelDesc), C.c_double, C.c_double]
+    L.pz_importance_resampling.argtypes = [f64p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int64, i32p]
+    L.pz_dist_sample.argtypes = [C.c_int32, f64p, C.c_int32, C.c_uint64, C.c_int64, f64p]
+    L.pz_dist_score.argtypes = [C.c_int32, f64p, C.c_int32, f64p, C.c_int64, f64p]
+    L.pz_filter_reset.argtypes = [C.c_void_p, C.c_uint64]
+    L.pz_filter_create_multi.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -124,31 +142,53 @@ def _ptr(a, t):
 
 
 # ---- model descriptors (kernel-side plugin surface) -------------------------------------------
-def rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=True, resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False):
+def _variants(d, carry_weights, ess_threshold):
+    d.carry_weights, d.ess_threshold = int(carry_weights), float(ess_threshold)
+    return d
+
+
+def walker(resampler=PZ_RESAMPLE_SYSTEMATIC, carry_weights=True, ess_threshold=0.0, exp_mean_as_written=True):
+    """Examples/Walker.hs:20-148 under `particles N` (cumulative weights, Inference.hs:73-86)."""
+    d = ModelDesc()
+    _check(lib().pz_model_walker(C.byref(d)))
+    d.resampler = resampler
+    d.walker.exp_mean_as_written = int(exp_mean_as_written)
+    return _variants(d, carry_weights, ess_threshold)
+
+
+def beta_bernoulli(a=1.0, b=1.0):
+    """betaBernoulli a b (Examples/DelayedSamplingAbstract.hs:57-69) under delayed sampling."""
+    d = ModelDesc()
+    _check(lib().pz_model_beta_bernoulli(C.byref(d), a, b))
+    return d
+
+
+def rw1d(q_var=1.0, r_var=3.0, scalar_ll_2x=True, resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False,
+         carry_weights=False, ess_threshold=0.0):
     """1-D Gaussian random walk + noisy observation: kalman1DObserved, Examples/Demo.hs:184-198
     (delay=True: kalman1DObservedDelayed, Demo.hs:215-242).  f64=True: state and arithmetic in double, the
     reference's own precision (Inference.hs:28)."""
     d = ModelDesc()
     _check(lib().pz_model_rw1d(C.byref(d), q_var, r_var))
     d.scalar_ll_2x, d.resampler, d.delayed, d.state_f64 = int(scalar_ll_2x), resampler, int(delay), int(f64)
-    return d
+    return _variants(d, carry_weights, ess_threshold)
 
 
-def stt(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False):
+def stt(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False, carry_weights=False, ess_threshold=0.0):
     """Single-target tracker: Examples/SingleTargetTracking.hs:28-54.  delay=False is the bootstrap filter,
     delay=True the delayed-sampling stream in which every particle carries the exact Kalman marginal."""
     d = ModelDesc()
     _check(lib().pz_model_stt(C.byref(d)))
     d.resampler, d.delayed, d.state_f64 = resampler, int(delay), int(f64)
-    return d
+    return _variants(d, carry_weights, ess_threshold)
 
 
-def mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False):
+def mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False, carry_weights=False, ess_threshold=0.0):
     """2-D position/velocity track model of the multi-target tracker: MultiTargetTracking.hs:56-73."""
     d = ModelDesc()
     _check(lib().pz_model_mtt_track(C.byref(d)))
     d.resampler, d.delayed, d.state_f64 = resampler, int(delay), int(f64)
-    return d
+    return _variants(d, carry_weights, ess_threshold)
 
 
 def mtt():
@@ -173,6 +213,7 @@ class Posterior:
         self.e_max = summary.e_max
         self.total_weight = summary.total_weight
         self.n_migrated = summary.n_migrated
+        self.resampled = bool(summary.reserved)   # stored-log-weight filters: this step's population came from a resample
 
     def particles(self, stride=1):
         """The reference's `[b]`: equally weighted particles after resampling (every stride-th)."""
@@ -184,12 +225,15 @@ class Posterior:
 class ZStream:
     """ZStream IO Obs Posterior built around pz_filter_step (Util/ZStream.hs:16-21)."""
 
-    def __init__(self, model, n_particles, seed=0, device=0, rank=0, world=1, nccl_id=None):
+    def __init__(self, model, n_particles, seed=0, device=0, rank=0, world=1, nccl_id=None, devices=None):
         self.model, self.nx, self.ny = model, model.nx, model.ny
         self.t = 0
         self.rank, self.world = rank, world
         self._h = C.c_void_p()
-        if world > 1:
+        if devices is not None:   # one process, several devices (pz_filter_create_multi)
+            ids = (C.c_int * len(devices))(*devices)
+            _check(lib().pz_filter_create_multi(C.byref(model), int(n_particles), seed, len(devices), ids, C.byref(self._h)))
+        elif world > 1:
             buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
             _check(lib().pz_filter_create_sharded(C.byref(model), int(n_particles), seed, device, rank, world, buf,
                                                   C.byref(self._h)))
@@ -255,7 +299,7 @@ class ZStream:
 
     def read_state(self):
         """Pre-resample population, SoA [nx, n], in the filter's storage type."""
-        if self.model.state_f64:
+        if self.model.state_f64 or self.model.kind == PZ_MODEL_WALKER:
             out = np.zeros((self.nx, self.n), dtype=np.float64)
             _check(lib().pz_filter_read_state_f64(self._h, _ptr(out, C.c_double), out.size))
             return out
@@ -277,6 +321,11 @@ class ZStream:
         out = np.zeros(self.n, dtype=np.float32)
         _check(lib().pz_filter_read_logw(self._h, _ptr(out, C.c_float), out.size))
         return out
+
+    def reset(self, seed=0):
+        """Back to the prior at step 0 (pz_filter_reset): the way on after a degenerate step."""
+        _check(lib().pz_filter_reset(self._h, seed))
+        self.t = 0
 
     def close(self):
         if self._h:
@@ -314,6 +363,12 @@ def shard_halo_range(need_lo, need_hi, blocks_per_rank, src):
     return lo.value, hi.value
 
 
+def zparticles_multi(num_particles, model, devices, seed=0):
+    """zparticles over several GPUs driven by THIS process (one host thread): global resampling, the exchange
+    over NVLink peer memory; step / run / read_state as on one GPU."""
+    return ZStream(model, num_particles, seed, devices=list(devices))
+
+
 def zdsparticles(num_particles, model, seed=0, device=0):
     """zdsparticles (Inference.hs:113-114): the per-particle heap is the fixed-capacity state."""
     return ZStream(model, num_particles, seed, device)
@@ -335,6 +390,31 @@ def resample_systematic(logw, u):
     anc = np.zeros(lw.size, dtype=np.int32)
     _check(lib().pz_resample_systematic(_ptr(lw, C.c_double), lw.size, float(u), _ptr(anc, C.c_int32)))
     return anc
+
+
+def importance_resampling(logw, seed, step, k=1):
+    """importanceResampling (Inference.hs:68-71): k draws from Categorical(exp(logw - max))."""
+    lw = np.ascontiguousarray(logw, dtype=np.float64)
+    idx = np.zeros(k, dtype=np.int32)
+    _check(lib().pz_importance_resampling(_ptr(lw, C.c_double), lw.size, seed, step, k, _ptr(idx, C.c_int32)))
+    return idx
+
+
+def dist_sample(kind, params, seed, n):
+    """n draws of a Distributions.hs primitive on the GPU (pz_dist_sample)."""
+    p = np.ascontiguousarray(params, dtype=np.float64)
+    out = np.zeros(n)
+    _check(lib().pz_dist_sample(PZ_DIST[kind], _ptr(p, C.c_double), p.size, seed, n, _ptr(out, C.c_double)))
+    return out
+
+
+def dist_score(kind, params, x):
+    """log-densities of a Distributions.hs primitive on the GPU (pz_dist_score)."""
+    p = np.ascontiguousarray(params, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros(x.size)
+    _check(lib().pz_dist_score(PZ_DIST[kind], _ptr(p, C.c_double), p.size, _ptr(x, C.c_double), x.size, _ptr(out, C.c_double)))
+    return out
 
 
 def resample_multinomial(logw, seed, step):

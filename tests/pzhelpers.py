@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 
 PZ_MAX_NX, PZ_MAX_NY = 6, 3
-PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT = 1, 2, 3
+PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT, PZ_MODEL_WALKER, PZ_MODEL_BETA_BERNOULLI = 1, 2, 3, 4, 5
+PZ_DIST = {"bernoulli": 1, "categorical": 2, "poisson": 3, "uniform": 4, "exponential": 5, "normal": 6}
 PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF = 0, 1
 PZ_EDEGENERATE = -4
 
@@ -26,12 +27,21 @@ class MttParams(C.Structure):
                 ("m_max", C.c_int32)]
 
 
+class WalkerParams(C.Structure):
+    """pz_walker_params (include/pzgpu.h): Examples/Walker.hs constants."""
+    _fields_ = [("pos_noise", C.c_double), ("obs_std", C.c_double), ("dt", C.c_double), ("p_init", C.c_double * 3),
+                ("half_life", (C.c_double * 3) * 3), ("speed_lo", C.c_double * 3), ("speed_hi", C.c_double * 3),
+                ("exp_mean_as_written", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ModelDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("scalar_ll_2x", C.c_int32),
                 ("resampler", C.c_int32), ("delayed", C.c_int32), ("state_f64", C.c_int32), ("reserved", C.c_int32),
                 ("F", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)), ("Q", C.c_double * (PZ_MAX_NX * PZ_MAX_NX)),
                 ("H", C.c_double * (PZ_MAX_NY * PZ_MAX_NX)), ("R", C.c_double * (PZ_MAX_NY * PZ_MAX_NY)),
-                ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams)]
+                ("x0", C.c_double * PZ_MAX_NX), ("mtt", MttParams),
+                ("ess_threshold", C.c_double), ("carry_weights", C.c_int32), ("reserved2", C.c_int32),
+                ("walker", WalkerParams), ("beta_a", C.c_double), ("beta_b", C.c_double)]
 
 
 class StepSummary(C.Structure):
@@ -78,6 +88,22 @@ def model_mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, f64=False):
     Q = np.block([[0.01 * I2, Z2], [Z2, 0.1 * I2]])
     H = np.block([I2, Z2])
     return _fill(ModelDesc(), PZ_MODEL_LINGAUSS, F, Q, H, I2, resampler=resampler, f64=f64)
+
+
+def model_walker(carry_weights=1, ess_threshold=0.0, resampler=PZ_RESAMPLE_SYSTEMATIC, exp_mean_as_written=1):
+    """Examples/Walker.hs:28-111 constants."""
+    d = ModelDesc()
+    d.kind, d.nx, d.ny, d.scalar_ll_2x, d.resampler = PZ_MODEL_WALKER, 5, 2, 1, resampler
+    d.carry_weights, d.ess_threshold = carry_weights, ess_threshold
+    w = d.walker
+    w.pos_noise, w.obs_std, w.dt = 0.01, 10.0, 10.0
+    w.p_init[0], w.p_init[1], w.p_init[2] = 0.7, 0.25, 0.05
+    w.half_life[0][1], w.half_life[0][2] = 30.0, 300.0
+    w.half_life[1][1], w.half_life[1][0], w.half_life[1][2] = 1.0, 10.0, 60.0
+    w.half_life[2][2], w.half_life[2][1] = 0.5, 2.0
+    w.speed_lo[1], w.speed_hi[1], w.speed_lo[2], w.speed_hi[2] = 0.0, 2.0, 2.0, 7.0
+    w.exp_mean_as_written = exp_mean_as_written
+    return d
 
 
 def model_mtt():
@@ -160,6 +186,15 @@ def oracle():
     lib.pzo_mtt_logw.argtypes = [C.c_void_p, f32p]
     lib.pzo_mtt_particle.argtypes = [C.c_void_p, C.c_int64, i32p, f64p, f64p]
     lib.pzo_mtt_track_posterior.argtypes = [C.c_void_p, C.c_int32, f64p, f64p]
+    lib.pzo_dist_sample.argtypes = [C.c_int32, f64p, C.c_int32, C.c_uint64, C.c_int64, f64p]
+    lib.pzo_dist_score.argtypes = [C.c_int32, f64p, C.c_int32, f64p, C.c_int64, f64p]
+    lib.pzo_importance_resampling.argtypes = [f32p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int64, i32p]
+    lib.pzo_walker_create.restype = C.c_void_p
+    lib.pzo_walker_create.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64]
+    lib.pzo_walker_destroy.argtypes = [C.c_void_p]
+    lib.pzo_walker_step.argtypes = [C.c_void_p, f64p, f64p, i32p]
+    lib.pzo_walker_state.argtypes = [C.c_void_p, f64p, f32p, i32p]
+    lib.pzo_walker_generate.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_int64, f64p, f64p]
     _oracle = lib
     return lib
 
@@ -337,3 +372,49 @@ class OracleMtt:
     def close(self):
         if self.h:
             self.lib.pzo_mtt_destroy(self.h); self.h = None
+
+
+def oracle_dist_sample(kind, params, seed, n):
+    p = np.ascontiguousarray(params, dtype=np.float64); out = np.zeros(n)
+    assert oracle().pzo_dist_sample(PZ_DIST[kind], ptr(p, C.c_double), p.size, seed, n, ptr(out, C.c_double)) == 0
+    return out
+
+
+def oracle_dist_score(kind, params, x):
+    p = np.ascontiguousarray(params, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64); out = np.zeros(x.size)
+    assert oracle().pzo_dist_score(PZ_DIST[kind], ptr(p, C.c_double), p.size, ptr(x, C.c_double), x.size, ptr(out, C.c_double)) == 0
+    return out
+
+
+def oracle_importance_resampling(lw32, seed, step, k):
+    lw32 = np.ascontiguousarray(lw32, dtype=np.float32); idx = np.zeros(k, dtype=np.int32)
+    rc = oracle().pzo_importance_resampling(ptr(lw32, C.c_float), lw32.size, seed, step, k, ptr(idx, C.c_int32))
+    return rc, idx
+
+
+def walker_obs(desc, T, seed=OBS_SEED):
+    """generateWalker (Walker.hs:113-123): measured positions [T, 2] and the true states [T, 5]."""
+    obs = np.zeros((T, 2)); truth = np.zeros((T, 5))
+    oracle().pzo_walker_generate(C.byref(desc), seed, T, ptr(obs, C.c_double), ptr(truth, C.c_double))
+    return obs, truth
+
+
+class OracleWalker:
+    def __init__(self, desc, n, seed):
+        self.lib = oracle(); self.n = n
+        self.h = self.lib.pzo_walker_create(C.byref(desc), n, seed)
+
+    def step(self, y):
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        ess, rs = C.c_double(), C.c_int32()
+        rc = self.lib.pzo_walker_step(self.h, ptr(y, C.c_double), C.byref(ess), C.byref(rs))
+        return rc, ess.value, bool(rs.value)
+
+    def state(self):
+        x = np.zeros((5, self.n)); lw = np.zeros(self.n, np.float32); anc = np.zeros(self.n, np.int32)
+        self.lib.pzo_walker_state(self.h, ptr(x, C.c_double), ptr(lw, C.c_float), ptr(anc, C.c_int32))
+        return x, lw, anc
+
+    def close(self):
+        if self.h:
+            self.lib.pzo_walker_destroy(self.h); self.h = None

@@ -19,12 +19,13 @@ def test_exports_every_declared_symbol(pz):
     for sym in declared:
         assert hasattr(L, sym), f"libpzgpu.so does not export {sym}"
     assert declared == set(pz.exported_symbols()) | {"pz_abi_version", "pz_last_error"} or declared >= set(pz.exported_symbols())
-    assert L.pz_abi_version() == 1
+    assert L.pz_abi_version() == 2
 
 
 def test_struct_layout_matches_header(pz):
     # the ctypes mirrors used by the host side and by the oracle binding must agree
-    assert C.sizeof(pz.ModelDesc) == C.sizeof(H.ModelDesc) == 8 * 4 + 8 * (36 + 36 + 18 + 9 + 6) + C.sizeof(H.MttParams)
+    assert C.sizeof(pz.ModelDesc) == C.sizeof(H.ModelDesc) == 8 * 4 + 8 * (36 + 36 + 18 + 9 + 6) + C.sizeof(H.MttParams) + 8 + 4 + 4 + C.sizeof(H.WalkerParams) + 16
+    assert C.sizeof(pz.WalkerParams) == C.sizeof(H.WalkerParams) == 8 * (3 + 3 + 9 + 3 + 3) + 8
     assert C.sizeof(pz.StepSummary) == C.sizeof(H.StepSummary) == 8 + 8 + 8 + 48 + 48 + 8 + 4 + 4 + 8
 
 

@@ -87,3 +87,65 @@ def test_cli_streams_lines_the_visualiser_parses():
     rows = [json.loads(ln) for ln in r.stdout.strip().split("\n")]
     assert len(rows) == 8 and all(len(v) == 3 for v in rows)        # Generic1D.java: one double per series
     assert all(abs(v[2] - v[1]) < 6.0 for v in rows)                 # the posterior mean follows the truth
+
+
+MIRROR = os.path.join(H.ROOT, "host", "shim-mirror")
+
+
+def test_shim_mirror_covers_every_haskell_import():
+    """haskell/PzGpu.hs cannot be compiled here (no GHC); host/shim_mirror.c makes the same calls in C.  Every symbol the
+    Haskell module imports must be called by the mirror, with the same descriptor / summary sizes and byte offsets."""
+    import re
+    hs = open(os.path.join(H.ROOT, "haskell", "PzGpu.hs")).read()
+    c = open(os.path.join(H.ROOT, "host", "shim_mirror.c")).read()
+    for sym in set(re.findall(r'foreign import ccall \w+ "&?(pz_\w+)"', hs)):
+        assert re.search(rf"\b{sym}\(", c), f"shim_mirror.c never calls {sym}"
+    assert int(re.search(r"sizeofModelDesc = (\d+)", hs).group(1)) == int(re.search(r"SIZEOF_MODEL_DESC (\d+)", c).group(1))
+    assert int(re.search(r"sizeofSummary = (\d+)", hs).group(1)) == int(re.search(r"SIZEOF_SUMMARY (\d+)", c).group(1))
+    for off in (4, 20, 24):   # nx, delayed, state_f64: the descriptor bytes the Haskell module reads / pokes
+        assert re.search(rf"(peekByteOff|pokeByteOff) p {off} ", hs) and re.search(rf"(\+ {off},|, {off},)", c)
+    build()
+    assert os.path.exists(MIRROR)
+
+
+@pytest.mark.gpu
+def test_shim_mirror_runs_the_haskell_call_sequence(pz):
+    """The C mirror of the Haskell module against the ctypes host on the same inputs: same summaries (bitwise: same
+    kernels), particle rows chunked by the descriptor's nx, the tracker's track maps, the Beta posterior."""
+    import numpy as np
+    import torch
+    build()
+    ndev = min(torch.cuda.device_count(), 2)
+    r = subprocess.run([MIRROR, str(ndev)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sc = {d["scenario"]: d for d in (json.loads(ln) for ln in r.stdout.strip().split("\n"))}
+    obs = lambda t: [0.3 * (t + 1), -0.2 * t, 0.1]
+    for name, mk, kw in (("rw1d", pz.rw1d, {}), ("rw1d_double", pz.rw1d, {"f64": True}), ("mtt_track", pz.mtt_track, {}), ("stt", pz.stt, {}),
+                         ("stt_delayed", pz.stt, {"delay": True}), ("walker", pz.walker, {})):
+        d = mk(**kw)
+        zs = pz.zparticles(10000, d, seed=7)
+        assert sc[name]["nx"] == d.nx
+        for t in range(4):
+            post = zs.step(obs(t)[:d.ny])
+            got = sc[name]["steps"][t]
+            assert got["step"] == t and got["le"] == post.log_evidence_inc and got["ess"] == post.ess
+            assert got["mean"] == list(post.mean) and got["var"] == list(post.var)
+        stride = {"mtt_track": 999, "stt_delayed": 5000}.get(name, 1000)
+        parts = zs.read_particles(stride)
+        assert sc[name]["rows"] == parts.shape[0] and len(sc[name]["first_particle"]) == d.nx
+        assert np.array_equal(sc[name]["first_particle"], parts[0]) and np.array_equal(sc[name]["last_particle"], parts[-1])
+        zs.close()
+    zs = pz.zparticles(10000, pz.rw1d(), seed=7)
+    posts = zs.run(np.array([[0.3], [0.6], [0.9], [1.2]]))
+    assert [s["mean"][0] for s in sc["run_all"]["steps"]] == [p.mean[0] for p in posts]
+    assert sc["beta_bernoulli"] == {"scenario": "beta_bernoulli", "alpha": 3.0, "beta": 2.0}
+    m = sc["mtt"]
+    assert m["rows"] == 8 and len(m["particles"]) == 8 and any(len(p) > 0 for p in m["particles"])
+    for p in m["particles"]:
+        for tid, mean, var in p:
+            assert tid >= 0 and all(np.isfinite(mean)) and var > 0
+    if ndev > 1:   # withDevices: the posterior of the multi-device handle equals the single-device one
+        a, b = sc["multi_mtt_track"], sc["single_mtt_track_same_n"]
+        assert a["n_local"] == 256 * 40 * ndev
+        for sa, sb in zip(a["steps"], b["steps"]):
+            assert np.allclose(sa["mean"], sb["mean"], rtol=1e-9, atol=1e-12) and abs(sa["ess"] - sb["ess"]) < 1e-6 * sb["ess"]

@@ -264,3 +264,39 @@ def test_sharded_margin_overflow_is_reported_by_every_rank(pz, tmp_path):
     c0, c1 = np.load(tmp_path / "codes_0.npy"), np.load(tmp_path / "codes_1.npy")
     assert np.array_equal(c0, c1)
     assert (c0 != 0).any() and c0[np.flatnonzero(c0)[0]] == -5   # the first failure is the capacity report
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
+@pytest.mark.parametrize("model", ["rw1d", "mtt_track", "stt"])
+def test_multi_device_single_process_equals_single_gpu(pz, model, f64):
+    """pz_filter_create_multi (one host thread, every device of the box): the same shards wired with
+    direct peer pointers and driven from this process; bit-equal to the single-GPU filter, per step and over a
+    pz_filter_run batch, at every device count the box offers."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
+    T = 8
+    obs, _ = H.gen_obs(hd, T)
+    bt = np.uint64 if f64 else np.uint32
+    for world in [w for w in (2, 4, 8) if w <= ndev]:
+        n = world * 256 * 101
+        d = getattr(pz, model)(f64=f64)
+        one = pz.zparticles(n, d, seed=99)
+        many = pz.zparticles_multi(n, d, list(range(world)), seed=99)
+        assert many.n == n
+        for t in range(4):
+            pa, pb = one.step(obs[t]), many.step(obs[t])
+            assert pa.total_weight == pb.total_weight and pa.e_max == pb.e_max and pb.step == t and pb.n_migrated >= 0
+            assert np.allclose(pa.mean, pb.mean, rtol=1e-6, atol=2e-6)
+            assert np.array_equal(one.read_state().view(bt), many.read_state().view(bt)), (model, world, t)
+        pa, pb = one.run(obs[4:]), many.run(obs[4:])
+        assert [p.total_weight for p in pa] == [p.total_weight for p in pb]
+        assert np.array_equal(one.read_state().view(bt), many.read_state().view(bt))
+        ms, launches = many.last_timing()
+        assert ms > 0 and launches >= 4 * world * 4
+        with pytest.raises(pz.PzError):
+            many.read_ancestors()
+        one.close(); many.close()
