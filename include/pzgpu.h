@@ -183,13 +183,6 @@ PZ_API int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_globa
                              int device, int rank, int world, const void* nccl_unique_id,
                              pz_filter** out);
 
-/* Halo arithmetic of a sharded filter (pure function, no device work): the global block
- * range [lo, hi) of rank `src` that a rank needs when the ancestors of its first and last
- * output slots live in global blocks need_lo and need_hi.  (The filter itself exchanges fixed
- * margins with its two neighbours and checks on the device that they cover this range.)     */
-PZ_API int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_rank, int32_t src,
-                               int64_t* lo, int64_t* hi);
-
 /* ZStream.step (Util/ZStream.hs:16): assimilate one observation, return the posterior.
  * obs is n_obs rows of obs_dim doubles (n_obs == 1 except for MTT).  Blocks until the
  * summary is on the host.                                                                    */

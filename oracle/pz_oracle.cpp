@@ -132,13 +132,12 @@ inline void weight_q_from_arg(float d, float* w, uint32_t* q) {
   *q = f2u(fmaf(wv, 32768.0f, 8388608.0f)) & 0x7FFFFFu;
 }
 inline void weight_q(float lw, float nbf, float* w, uint32_t* q) { weight_q_from_arg(fmaf(lw, kLog2e, -nbf), w, q); }
-// f64 filters (descriptor flag state_f64): the block exponent and the argument of the weight polynomial
-// are formed in double and the argument is rounded to fp32 once; everything after that is the fp32 spec.
-constexpr double kLog2eD = 0x1.71547652b82fep+0;
+// f64 filters (descriptor flag state_f64): the log-weight is evaluated in double and rounded to fp32 once;
+// block exponent, weight and quantisation are the fp32 spec applied to that value.
 // (the block exponent of an f64 filter is the fp32 definition applied to the log-weights rounded to fp32)
 inline float lw_key(float lw) { return lw; }
 inline float lw_key(double lw) { return (float)lw; }
-inline void weight_q(double lw, double nbf, float* w, uint32_t* q) { weight_q_from_arg((float)fma(lw, kLog2eD, -nbf), w, q); }
+inline void weight_q(double lw, double nbf, float* w, uint32_t* q) { weight_q((float)lw, (float)nbf, w, q); }
 
 // stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)
 inline float sanitize_lw(float lw) { return (lw == lw && lw < INFINITY) ? lw : -INFINITY; }

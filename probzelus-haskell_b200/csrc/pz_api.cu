@@ -433,7 +433,7 @@ void free_filter(pz_filter* f) {
     dbg_read_stamps(st);
     char line[512];
     int o = snprintf(line, sizeof(line), "[pz stamps] rank %d (ns after scan start):", f->a.rank);
-    for (int i = 0; i < 11; ++i) o += snprintf(line + o, sizeof(line) - o, " [%d]=%lld", i, (long long)(st[i] - st[0]));
+    for (int i = 0; i < 15; ++i) o += snprintf(line + o, sizeof(line) - o, " [%d]=%lld", i, (long long)(st[i] - st[0]));
     fprintf(stderr, "%s\n", line);
   }
 #endif
@@ -562,11 +562,9 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
     *launches += launch_halo_push(a, delta, f->push_stream);
     PZ_CUDA(cudaEventRecord(f->ev_join, f->push_stream));
     *launches += launch_scan_only(a, delta, s);
-    if (tm) cudaEventRecord(f->tev[2], s);
-    *launches += launch_plan_sharded(a, delta, s);
-    if (tm) cudaEventRecord(f->tev[3], s);
-    PZ_CUDA(cudaStreamWaitEvent(s, f->ev_join, 0));  // join (pf_partition advances ctl->t, which pf_halo_push reads)
-    *launches += launch_partition_ext(a, fused_tile_out(a.model.nx, a.f64), delta, s);
+    if (tm) { cudaEventRecord(f->tev[2], s); cudaEventRecord(f->tev[3], s); }
+    PZ_CUDA(cudaStreamWaitEvent(s, f->ev_join, 0));  // join (pf_partition_sharded advances ctl->t, which pf_halo_push reads)
+    *launches += launch_partition_sharded(a, fused_tile_out(a.model.nx, a.f64), delta, s);
     if (tm) { cudaEventRecord(f->tev[4], s); f->tpending = true; }
     PZ_CUDA(cudaGetLastError());
     return PZ_OK;
@@ -614,9 +612,16 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
 // the error a step's summary implies (the same verdict on every rank)
 int report_step(pz_filter* f, const pz_step_summary& s, uint32_t t) {
   if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight (all -inf or NaN log-weights)", t);
-  if (s.n_migrated == -2) return fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange", t);
+  if (s.n_migrated == -2) {
+    CtlDev c{};
+    cudaMemcpy(&c, f->a.ctl, sizeof(c), cudaMemcpyDeviceToHost);
+    cudaGetLastError();
+    return fail(PZ_ENCCL, "step %u: a peer rank never answered the peer-memory exchange (rank %d, wait mask 0x%x: 1 exponent, 2 records, "
+                "4/0x40 state margins, 8/0x10/0x80 boundary positions; 0 = reported by a peer)", t, f->a.rank, c.comm_error);
+  }
   if (s.n_migrated < 0)
-    return fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (set PZ_HALO_BLOCKS)", t, (long long)f->hb);
+    return fail(PZ_ECAPACITY, "step %u: a rank's ancestors reach beyond the halo margin of %lld blocks (NCCL exchange path: set PZ_HALO_BLOCKS; "
+                "the peer-memory path reads remote blocks instead)", t, (long long)f->hb);
   return PZ_OK;
 }
 
@@ -698,7 +703,7 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   a.ld = round_up(a.n_local, kPad);
   f->mtt_params.resize(mtt_params_size());
   mtt_fill_params(model, f->mtt_params.data());
-  const size_t sbytes = (size_t)a.n_local * mtt_words_per_particle() * sizeof(uint32_t);
+  const size_t sbytes = (size_t)a.ld * mtt_words_per_particle() * sizeof(uint32_t);   // [field][ld]
 #define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
@@ -749,7 +754,7 @@ int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summar
   PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
   GenericArgs g = mtt_generic(f);
   int n = launch_generic_ancestors(g, f->stream);
-  n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
+  n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], a.ld, f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
                        f->mtt_overflow, f->mtt_part, a.n_local, n_obs, a.seed, f->stream);
   // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
   const double ll_const = -(f->desc.mtt.clutter_lambda + f->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
@@ -775,65 +780,88 @@ int setup_p2p(pz_filter* f) {
   StepArgs& a = f->a;
   const int R = a.world, me = a.rank;
   if (getenv("PZ_SHARD_NCCL") || R > kMaxRanks) return PZ_OK;
-  struct Pack { cudaIpcMemHandle_t h[8]; };
+  // buffers of every rank are mapped by every rank: the mailbox, and -- for the remote-read fallback and the
+  // neighbours' halos -- state, weights, exponents, boundary positions and local prefixes
+  constexpr int NH = 10;
+  struct Pack { cudaIpcMemHandle_t h[NH]; };
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   Pack mine;
+  memset(&mine, 0, sizeof(mine));
   bool ok = cudaMalloc(&f->mbox, sizeof(Mailbox)) == cudaSuccess && cudaMemset(f->mbox, 0, sizeof(Mailbox)) == cudaSuccess;
-  void* bases[8] = {f->mbox, f->xbuf[0], f->xbuf[1], f->qbuf[0], f->qbuf[1], f->ebbuf[0], f->ebbuf[1], f->pbxbuf};
-  for (int i = 0; i < 8 && ok; ++i) ok = cudaIpcGetMemHandle(&mine.h[i], bases[i]) == cudaSuccess;
-  // all-gather of the handles (always executed: a collective every rank must enter)
+  void* bases[NH] = {f->mbox, f->xbuf[0], f->xbuf[1], f->qbuf[0], f->qbuf[1], f->ebbuf[0], f->ebbuf[1], f->pbxbuf, f->xbbuf, a.pb};
+  for (int i = 0; i < NH && ok; ++i) ok = cudaIpcGetMemHandle(&mine.h[i], bases[i]) == cudaSuccess;
+  // all-gather of the handles.  Every rank must enter both collectives below whatever failed locally: a local failure
+  // only lowers this rank's verdict.
   unsigned char* d_all = nullptr;
   std::vector<Pack> all((size_t)R);
-  if (cudaMalloc(&d_all, (size_t)R * sizeof(Pack)) != cudaSuccess) return fail(PZ_ECUDA, "cudaMalloc failed");
+  int fatal = PZ_OK;
+  if (cudaMalloc(&d_all, (size_t)R * sizeof(Pack)) != cudaSuccess) { ok = false; d_all = nullptr; cudaGetLastError(); }
   {
-    cudaError_t e = cudaMemcpy(d_all + (size_t)me * sizeof(Pack), &mine, sizeof(Pack), cudaMemcpyHostToDevice);
-    ncclResult_t r = e == cudaSuccess
-        ? g_nccl.AllGather(d_all + (size_t)me * sizeof(Pack), d_all, sizeof(Pack), ncclUint8, f->comm, f->stream) : ncclSuccess;
-    if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(f->stream);
-    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpy(all.data(), d_all, (size_t)R * sizeof(Pack), cudaMemcpyDeviceToHost);
-    cudaFree(d_all);
-    if (r != ncclSuccess) return fail(PZ_ENCCL, "all-gather of the IPC handles failed: %s", g_nccl.GetErrorString(r));
-    if (e != cudaSuccess) return fail(PZ_ECUDA, "all-gather of the IPC handles failed: %s", cudaGetErrorString(e));
+    // (without the staging buffer this rank still joins the collective, in place on its handle-free scratch)
+    unsigned char* buf = d_all;
+    if (buf && cudaMemcpy(buf + (size_t)me * sizeof(Pack), &mine, sizeof(Pack), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    if (buf) {
+      ncclResult_t r = g_nccl.AllGather(buf + (size_t)me * sizeof(Pack), buf, sizeof(Pack), ncclUint8, f->comm, f->stream);
+      if (r != ncclSuccess) { ok = false; fatal = fail(PZ_ENCCL, "all-gather of the IPC handles failed: %s", g_nccl.GetErrorString(r)); }
+      if (cudaStreamSynchronize(f->stream) != cudaSuccess) ok = false;
+      if (cudaMemcpy(all.data(), buf, (size_t)R * sizeof(Pack), cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+      cudaFree(buf);
+    } else {
+      fatal = fail(PZ_ECUDA, "cudaMalloc of the IPC staging buffer failed");   // the peers' all-gather cannot complete without this rank
+    }
+    cudaGetLastError();
   }
+  if (fatal != PZ_OK) return fatal;
   ShardP2P h{};
   const int64_t H = f->hb * kBlk;
+  const size_t esz = a.f64 ? 8 : 4;
   auto open = [&](const cudaIpcMemHandle_t& hd) -> void* {
     void* p = nullptr;
     if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     f->ipc_opened.push_back(p);
     return p;
   };
+  std::vector<std::vector<void*>> peer((size_t)R, std::vector<void*>(NH, nullptr));
   for (int q = 0; q < R && ok; ++q) {
-    if (q == me) { h.mbox[q] = f->mbox; continue; }
-    h.mbox[q] = (Mailbox*)open(all[q].h[0]);
-    ok = h.mbox[q] != nullptr;
+    if (q == me) { for (int i = 0; i < NH; ++i) peer[q][i] = bases[i]; continue; }
+    for (int i = 0; i < NH && ok; ++i) { peer[q][i] = open(all[q].h[i]); ok = peer[q][i] != nullptr; }
+  }
+  for (int q = 0; q < R && ok; ++q) {
+    void** p = peer[q].data();
+    h.mbox[q] = (Mailbox*)p[0];
+    for (int b = 0; b < 2; ++b) {
+      h.Xall[q][b] = (char*)p[1 + b] + (size_t)H * esz;
+      h.Qall[q][b] = (uint16_t*)p[3 + b] + H;
+      h.eball[q][b] = (int32_t*)p[5 + b] + f->hb;
+    }
+    h.xball[q] = (uint64_t*)p[8] + f->hb;
+    h.pball[q] = (uint64_t*)p[9];
   }
   for (int side = 0; side < 2 && ok; ++side) {
     const int q = side == 0 ? me - 1 : me + 1;
     if (q < 0 || q >= R) continue;
-    void* p[8] = {};
-    for (int i = 1; i < 8 && ok; ++i) { p[i] = open(all[q].h[i]); ok = p[i] != nullptr; }
-    if (!ok) break;
-    for (int b = 0; b < 2; ++b) {
-      h.Xn[side][b] = (char*)p[1 + b] + (size_t)H * (a.f64 ? 8 : 4);
-      h.Qn[side][b] = (uint16_t*)p[3 + b] + H;
-      h.ebn[side][b] = (int32_t*)p[5 + b] + f->hb;
-    }
+    void** p = peer[q].data();
+    for (int b = 0; b < 2; ++b) { h.Xn[side][b] = h.Xall[q][b]; h.Qn[side][b] = h.Qall[q][b]; h.ebn[side][b] = h.eball[q][b]; }
     h.pbxn[side] = (uint64_t*)p[7] + f->hb;
+    h.xbn[side] = h.xball[q];
   }
   if (ok) ok = cudaMalloc(&f->d_p2p, sizeof(ShardP2P)) == cudaSuccess &&
                cudaMemcpy(f->d_p2p, &h, sizeof(ShardP2P), cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) ok = cudaStreamCreateWithFlags(&f->push_stream, cudaStreamNonBlocking) == cudaSuccess &&
                cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
                cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming) == cudaSuccess;
-  // agreement: min over ranks of the local verdict
-  const int32_t verdict = ok ? 1 : 0;
-  PZ_CUDA(cudaMemcpy(f->warm, &verdict, sizeof(int32_t), cudaMemcpyHostToDevice));
-  PZ_NCCL(g_nccl.AllReduce(f->warm, f->warm, 1, ncclInt32, ncclMin, f->comm, f->stream));
-  int32_t agreed = 0;
-  PZ_CUDA(cudaStreamSynchronize(f->stream));
-  PZ_CUDA(cudaMemcpy(&agreed, f->warm, sizeof(int32_t), cudaMemcpyDeviceToHost));
   cudaGetLastError();
+  // agreement: min over ranks of the local verdict (every rank enters the all-reduce)
+  const int32_t verdict = ok ? 1 : 0;
+  int32_t agreed = 0;
+  const bool staged = cudaMemcpy(f->warm, &verdict, sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+  ncclResult_t r = g_nccl.AllReduce(f->warm, f->warm, 1, ncclInt32, ncclMin, f->comm, f->stream);
+  const bool synced = cudaStreamSynchronize(f->stream) == cudaSuccess;
+  if (r != ncclSuccess) return fail(PZ_ENCCL, "all-reduce of the peer-memory verdict failed: %s", g_nccl.GetErrorString(r));
+  if (!staged || !synced || cudaMemcpy(&agreed, f->warm, sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PZ_ECUDA, "peer-memory set-up: the verdict all-reduce could not be staged on this rank");
+  }
   if (agreed) a.p2p = f->d_p2p;
   return PZ_OK;
 }
@@ -1368,7 +1396,13 @@ int create_multi(const pz_model_desc* model, uint64_t n_global, uint64_t seed, i
     ShardP2P h{};
     const size_t esz = sh->a.f64 ? 8 : 4;
     const int64_t H = sh->hb * kBlk;
-    for (int q = 0; q < R; ++q) h.mbox[q] = parent->shards[q]->mbox;
+    for (int q = 0; q < R; ++q) {
+      pz_filter* o = parent->shards[q];
+      h.mbox[q] = o->mbox;
+      for (int b = 0; b < 2; ++b) { h.Xall[q][b] = o->a.X[b]; h.Qall[q][b] = o->a.Q[b]; h.eball[q][b] = o->a.eb[b]; }
+      h.xball[q] = o->a.xb;
+      h.pball[q] = o->a.pb;
+    }
     for (int side = 0; side < 2; ++side) {
       const int q = side == 0 ? r - 1 : r + 1;
       if (q < 0 || q >= R) continue;
@@ -1379,6 +1413,7 @@ int create_multi(const pz_model_desc* model, uint64_t n_global, uint64_t seed, i
         h.ebn[side][b] = nb->ebbuf[b] + nb->hb;
       }
       h.pbxn[side] = nb->pbxbuf + nb->hb;
+      h.xbn[side] = nb->xbbuf + nb->hb;
     }
     PZ_TRYM(cudaMalloc(&sh->d_p2p, sizeof(ShardP2P)));
     PZ_TRYM(cudaMemcpy(sh->d_p2p, &h, sizeof(ShardP2P), cudaMemcpyHostToDevice));
@@ -1571,22 +1606,6 @@ int pz_comm_unique_id(void* out128) {
 int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_global, uint64_t seed, int device, int rank,
                              int world, const void* nccl_unique_id, pz_filter** out) {
   return create_common(model, n_global, seed, device, rank, world, nccl_unique_id, out);
-}
-
-/* Host-side halo plan of the sharded filter (pure function; CPU tests drive it over gloo).
- * need_lo[q] / need_hi[q]: global block holding the ancestor of rank q's first / last slot.
- * out[2*p], out[2*p+1]: global block range [lo, hi) of rank `src` that rank `dst` must receive. */
-static inline void halo_range(int64_t need_lo, int64_t need_hi, int64_t nb, int src, int64_t* lo, int64_t* hi) {
-  const int64_t s0 = (int64_t)src * nb, s1 = s0 + nb;
-  *lo = need_lo > s0 ? need_lo : s0;
-  *hi = (need_hi + 1) < s1 ? (need_hi + 1) : s1;
-  if (*hi < *lo) *hi = *lo;
-}
-
-int pz_shard_halo_range(int64_t need_lo, int64_t need_hi, int64_t blocks_per_rank, int32_t src, int64_t* lo, int64_t* hi) {
-  if (!lo || !hi || blocks_per_rank < 1 || src < 0) return fail(PZ_EINVAL, "bad argument");
-  halo_range(need_lo, need_hi, blocks_per_rank, src, lo, hi);
-  return PZ_OK;
 }
 
 int64_t pz_filter_n_local(const pz_filter* f) {
@@ -1868,7 +1887,7 @@ int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int3
   const int W = mtt_words_per_particle();
   uint32_t* d_out = nullptr;
   PZ_CUDA(cudaMalloc(&d_out, (size_t)n_sel * W * sizeof(uint32_t)));
-  launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream);
+  launch_mtt_gather(f->mtt_s[f->t & 1], a.ld, f->g.anc, stride, n_sel, d_out, f->stream);
   std::vector<uint32_t> h((size_t)n_sel * W);
   cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);

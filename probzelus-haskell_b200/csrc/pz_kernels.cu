@@ -102,13 +102,15 @@ __device__ __forceinline__ void stamp(int i) {
 // ever; the host sets the limit -- PZ_P2P_TIMEOUT_S, default 120 s, 0 = never -- because the ranks' hosts
 // drive their steps independently and may be skewed by seconds: GC pauses, I/O, first-step graph upload).
 // ACQUIRE = false for self-validating words (the payload is in the polled word: nothing to order)
+// `code` names the wait in the sticky error word (bit mask: 1 exponent all-reduce, 2 record all-gather, 4 state margins,
+// 8 boundary-position margins), reported by pz_last_error.
 template <bool ACQUIRE = true, class Pred>
 __device__ __forceinline__ unsigned long long wait_sys(const unsigned long long* p, Pred pred, uint32_t* err,
-                                                       unsigned long long limit) {
+                                                       unsigned long long limit, uint32_t code = 1u) {
   const long long t0 = clock64();
   unsigned long long v = ld_sys(p);
   while (!pred(v)) {
-    if (limit && (unsigned long long)(clock64() - t0) > limit) { atomicExch(err, 1u); break; }
+    if (limit && (unsigned long long)(clock64() - t0) > limit) { atomicOr(err, code); break; }
     __nanosleep(64);
     v = ld_sys(p);
   }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
       if (lane < s.world) {
         const unsigned long long w = wait_sys<false>(&s.p2p->mbox[s.rank]->emax[lane],
                                               [epoch](unsigned long long x) { return (x >> 32) == epoch; }, &s.ctl->comm_error,
-                                              s.wait_ticks);
+                                              s.wait_ticks, 1u);
         v = (int32_t)(uint32_t)w;
       }
 #pragma unroll
@@ -626,8 +628,8 @@ __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
       const unsigned long long epoch = pl->shard_epoch;
       Mailbox* mine = p.p2p->mbox[p.rank];
       if (have)
-        wait_sys(threadIdx.x < 2 ? &mine->halo_flag[side] : &mine->pbx_flag[side], [epoch](unsigned long long x) { return x == epoch; },
-                 &p.ctl->comm_error, p.wait_ticks);
+        wait_sys(threadIdx.x < 2 ? &mine->halo_flag[side] : &mine->pbx_flag[side], [epoch](unsigned long long x) { return x >= epoch; },
+                 &p.ctl->comm_error, p.wait_ticks, threadIdx.x < 2 ? 4u : 8u);
     }
     __syncthreads();
     PZ_STAMP(J == 0, 10);
@@ -857,6 +859,27 @@ __device__ __forceinline__ void resample_tile(Source& src, typename Source::Scal
   }
 }
 
+// Input side of the REMOTE step kernel (a sharded filter whose pending resample reaches beyond the halo margins):
+// the tile's input blocks are GLOBAL block indices; each is read from its owner's arrays over NVLink (or from this
+// rank's own).  No prefetch pipeline: this is the fallback path, it only has to be right.
+template <bool SEGDUP, int NW, class Source>
+__device__ __forceinline__ void resample_tile_remote(Source& src, typename Source::Scalar* s_par, int stride, const ShardP2P* p2p,
+                                                     int cur, int64_t nblk, int world, int64_t gb_first, int32_t emax, int32_t h0,
+                                                     uint32_t Mq, uint32_t j0, int nslots, int lane, int warp) {
+  typedef typename Source::Scalar S;
+  const int64_t gb_end = (int64_t)world * nblk;
+  for (int64_t gb = gb_first + warp; gb < gb_end; gb += NW) {
+    const int q = (int)(gb / nblk);
+    const int64_t lb = gb - (int64_t)q * nblk;
+    BlockIn in;
+    in.load(p2p->Qall[q][cur], p2p->eball[q][cur], p2p->xball[q], lb, lane);
+    src.x = reinterpret_cast<const S*>(p2p->Xall[q][cur]);
+    Quad<S> xa{}, xb4{};
+    if constexpr (Source::kPrefetch) { xa = src.fetch(lb * kBlk + lane * 4); xb4 = src.fetch(lb * kBlk + lane * 4 + 128); }
+    if (resample_block<SEGDUP>(src, s_par, stride, in, xa, xb4, lb, emax, h0, Mq, j0, nslots, lane)) break;
+  }
+}
+
 // Output side: tile-relative slot of the head of each of the lane's 4 slots sl .. sl+3 (sl = segment
 // base + lane*4; the segment = the 128 slots this warp iteration covers).  bits = the payload words
 // of dimension 0 at those slots.  The first slot of a segment always carries a head (emit_head).
@@ -911,32 +934,27 @@ struct TileArgs {
 constexpr int min_ctas(int nx) { return nx == 1 ? PZ_OCC1 : (nx <= 4 ? PZ_OCC4 : PZ_OCC6); }
 #define PZ_NACC(nx) (2 + 2 * (nx))
 
-template <class T> __device__ __forceinline__ T exp2t(int k);
-template <> __device__ __forceinline__ float exp2t<float>(int k) { return exp2i(k); }
-template <> __device__ __forceinline__ double exp2t<double>(int k) { return pow2d(k); }
-// warp shuffles in the filter's arithmetic type
-__device__ __forceinline__ float shfl_xor_t(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-__device__ __forceinline__ double shfl_xor_t(double v, int m) { return shfl_xor_f64(v, m); }
 // A double filter forms its block exponent from the log-weights ROUNDED TO FP32 (the fp32 definition applied
 // to fl32(lw): a double maximum costs ~12 instructions per particle, the exponent only has to be within a
 // fraction of a unit of the true one).  lw_key is the value that enters the block maximum.
 __device__ __forceinline__ float lw_key(float lw) { return lw; }
 __device__ __forceinline__ float lw_key(double lw) { return __double2float_rn(lw); }
-// d = lw * log2(e) - n_b, as the fp32 argument of the weight polynomial
-__device__ __forceinline__ float weight_arg(float lw, float nbf) { return __fmaf_rn(lw, kLog2e, -nbf); }
-__device__ __forceinline__ float weight_arg(double lw, double nbf) { return __double2float_rn(__fma_rn(lw, kLog2eD, -nbf)); }
 
 // Output side of one canonical output block (256 slots, one warp; a lane owns slots lane*4 + {0..3}
 // and 128 + lane*4 + {0..3}).  FULL: every slot of the tile is live (all tiles but the last).
+// A double filter (T = double) propagates and evaluates the log-weight in double; from there on it is the fp32
+// machinery: the log-weight rounded to fp32 enters the block maximum and the weight polynomial, the centred state
+// x' - c (formed in double) is rounded to fp32 for the moment sums.  (Keeping those in double costs 24 registers
+// and an occupancy step for nothing the 16-bit weights or the fp64 tile totals could show.)
 template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL>
 __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const float4* __restrict__ tab_m8, int ob,
                                              int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const T* y_new,
-                                             const T* cen, int lane, T (&acc)[PZ_NACC(NX)], int32_t& aref) {
+                                             const T* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref) {
   T* __restrict__ xout = reinterpret_cast<T*>(a.X[nxt]);
   uint16_t* __restrict__ qout = a.Q[nxt];
   const LgDevT<T>& model = model_of<T>(a);
-  T lw[8];
-  T xk[NX == 1 ? 8 : 1];  // NX = 1 keeps the new state in registers; wider states go through s_par
+  float lw[8];
+  float dxk[NX == 1 ? 8 : 1];  // NX = 1 keeps the centred new state in registers; wider states go through s_par
   float mx = -INFINITY;
   int seg_carry = -1;
   if constexpr (MODE == 0 && NX == 1) {
@@ -977,10 +995,10 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       model_propagate<NX, KRON>(model, xs, zs, xn);
 #pragma unroll
       for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-      T l = model_logweight<NX, NY, KRON>(model, xn, y_new);
+      float l = lw_key(model_logweight<NX, NY, KRON>(model, xn, y_new));
       if (!FULL && sl + k >= nslots) l = -INFINITY;  // past the end of the population
       lw[half * 4 + k] = l;
-      mx = fmaxf(mx, lw_key(l));
+      mx = fmaxf(mx, l);
     }
     if (FULL || sl < nslots) {
 #pragma unroll
@@ -991,49 +1009,49 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
     }
     if constexpr (NX == 1) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) xk[half * 4 + k] = xo[0][k];
+      for (int k = 0; k < 4; ++k) dxk[half * 4 + k] = (float)r_sub(xo[0][k], cen[0]);
     }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
   int32_t nb;
-  const T nbf = (T)block_exponent(mx, nb);
+  const float nbf = block_exponent(mx, nb);
   uint32_t ssum = 0;
   if (nb != kNZero) {
-    T p[PZ_NACC(NX)];
+    float p[PZ_NACC(NX)];
 #pragma unroll
-    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0;
+    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0.0f;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int sl = ob * kBlk + half * 128 + lane * 4;
-      T xv[NX][4];
+      float dxv[NX][4];
       if constexpr (NX > 1) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
           const Quad<T> f = lds_quad(&s_par[d * TO + sl]);
-          xv[d][0] = f.v[0]; xv[d][1] = f.v[1]; xv[d][2] = f.v[2]; xv[d][3] = f.v[3];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dxv[d][k] = (float)r_sub(f.v[k], cen[d]);
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xv[0][k] = xk[half * 4 + k];
+        for (int k = 0; k < 4; ++k) dxv[0][k] = dxk[half * 4 + k];
       }
       uint32_t qb[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float wf;
-        weight_q_from_arg<false>(weight_arg(lw[half * 4 + k], nbf), wf, qb[k]);
+        float w;
+        weight_q<false>(lw[half * 4 + k], nbf, w, qb[k]);
         const bool live = FULL || sl + k < nslots;
-        if (!live) wf = 0.0f;  // (its q is already 0: lw = -inf)
-        const T w = (T)wf;
+        if (!live) w = 0.0f;  // (its q is already 0: lw = -inf)
         ssum += qb[k];        // raw bits 0x4B000000 + q; the bias is removed after the warp sum
-        p[0] = r_add(p[0], w);
-        p[1] = r_fma(w, w, p[1]);
+        p[0] = __fadd_rn(p[0], w);
+        p[1] = __fmaf_rn(w, w, p[1]);
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          const T dx = live ? r_sub(xv[d][k], cen[d]) : (T)0;
-          const T wd = r_mul(w, dx);
-          p[2 + d] = r_add(p[2 + d], wd);
-          p[2 + NX + d] = r_fma(wd, dx, p[2 + NX + d]);
+          const float dx = live ? dxv[d][k] : 0.0f;
+          const float wd = __fmul_rn(w, dx);
+          p[2 + d] = __fadd_rn(p[2 + d], wd);
+          p[2 + NX + d] = __fmaf_rn(wd, dx, p[2 + NX + d]);
         }
       }
       if (FULL || sl < nslots)
@@ -1042,18 +1060,18 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
     // fold the block's sums (scale 2^nb) into the lane accumulators (scale 2^aref)
     if (nb == aref) {
 #pragma unroll
-      for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = r_add(acc[r], p[r]);
+      for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = __fadd_rn(acc[r], p[r]);
     } else if (aref == kNZero) {
 #pragma unroll
       for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = p[r];
       aref = nb;
     } else {
       const int32_t nref = max(aref, nb);
-      const T ga = exp2t<T>(aref - nref), gp = exp2t<T>(nb - nref);
+      const float ga = exp2i(aref - nref), gp = exp2i(nb - nref);
 #pragma unroll
       for (int r = 0; r < PZ_NACC(NX); ++r) {
-        const T fa = (r == 1) ? r_mul(ga, ga) : ga, fp = (r == 1) ? r_mul(gp, gp) : gp;
-        acc[r] = r_fma(acc[r], fa, r_mul(p[r], fp));
+        const float fa = (r == 1) ? __fmul_rn(ga, ga) : ga, fp = (r == 1) ? __fmul_rn(gp, gp) : gp;
+        acc[r] = __fmaf_rn(acc[r], fa, __fmul_rn(p[r], fp));
       }
       aref = nref;
     }
@@ -1075,7 +1093,11 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
 }
 
 // NT threads per CTA (NW warps): 256 by default; PZ_NT1 = 128 runs the NX = 1 kernel with half-size CTAs
-template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB>
+// REMOTE: the fallback of a sharded filter for a resample whose ancestors reach beyond the halo margins (verdict
+// plan->shard_overflow == 1, the same on every rank): a small persistent grid loops over the tiles, tile_start
+// holds GLOBAL block indices and the input side reads every block from its owner.  The regular kernel exits at
+// once in that case, the remote one in every other.
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB, bool REMOTE = false>
 __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__ TileArgs ta) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
@@ -1089,22 +1111,60 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   const int cur = t & 1, nxt = cur ^ 1;
   const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[cur]);
   const PlanDev* pl = a.plan;
-  const int64_t j0l = (int64_t)blockIdx.x * TO;  // local slot
+  if constexpr (MODE == 0) {
+    if (a.p2p != nullptr) {
+      const int32_t ov = pl->shard_overflow;
+      if (REMOTE ? ov != 1 : ov != 0) return;
+    }
+  }
+  if constexpr (REMOTE) {
+    // every rank's boundary positions of this epoch must be complete before any block is read
+    if (tid < a.world) {
+      const Mailbox* mine = a.p2p->mbox[a.rank];
+      const unsigned long long epoch = (unsigned long long)(t + 1u);
+      wait_sys(&mine->xb_done[tid], [epoch](unsigned long long x) { return x >= epoch; }, &a.ctl->comm_error, a.wait_ticks, 0x20u);
+    }
+    __syncthreads();
+  }
+  int tile = blockIdx.x;
+  do {   // one tile per CTA (REMOTE: a persistent grid strides over the tiles)
+  const int64_t j0l = (int64_t)tile * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
   const uint32_t j0 = (uint32_t)(a.slot_base + j0l);
   const int nslots = (int)(jendl - j0l);
 
   T y_new[NY];
   load_obs<T, NY>(a, t, y_new);
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 11);
+  PZ_STAMP(blockIdx.x == gridDim.x - 1 && tid == 0, 14);
 
   if constexpr (MODE == 0) {
     // the first input block's weights: in flight during the prologue
-    const int64_t b_first = (int64_t)a.tile_start[blockIdx.x];
+    const int64_t b_first = (int64_t)a.tile_start[tile];
+    if (!REMOTE && a.p2p != nullptr) {
+      // sharded over peer memory: a boundary tile (its input blocks reach into a halo) waits here for the
+      // neighbour's margins of this epoch (state / weights / exponents from pf_halo_push, boundary positions from
+      // pf_partition_sharded); interior tiles -- nearly all -- start at once.  The flags hold the LATEST epoch: a
+      // neighbour that runs ahead may already have pushed the next step's state margins (into the other buffer
+      // parity -- it cannot get further: its next exchange needs this rank's record), hence >=.
+      const int64_t b_next = (tile + 1 < a.ntiles_out) ? (int64_t)a.tile_start[tile + 1] : a.b_hi;
+      if (tid < 4) {
+        const int side = tid & 1;
+        const bool need = side == 0 ? (a.rank > 0 && b_first < 0) : (a.rank + 1 < a.world && b_next >= a.nblk);
+        if (need) {
+          const Mailbox* mine = a.p2p->mbox[a.rank];
+          const unsigned long long epoch = (unsigned long long)(t + 1u);
+          wait_sys(tid < 2 ? &mine->halo_flag[side] : &mine->pbx_flag[side], [epoch](unsigned long long x) { return x >= epoch; },
+                   &a.ctl->comm_error, a.wait_ticks, tid < 2 ? 0x40u : 0x80u);
+        }
+      }
+      __syncthreads();
+    }
     BlockIn first{};
     StateSource<NX, T> src;
     src.x = xin; src.ld = a.ld;
     Quad<T> pa{}, pb{};
-    if (b_first + warp < a.b_hi) {
+    if (!REMOTE && b_first + warp < a.b_hi) {
       first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
       // fp32 payloads of the first block are fetched here too; for doubles the 16 extra registers across the
       // barrier cost more than the exposed latency (measured: 0.568 ms hoisted vs 0.544 ms not, N = 10^8)
@@ -1118,14 +1178,19 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     uint4* sz = reinterpret_cast<uint4*>(s_par);
     for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
-    if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 8) {
-      if (b_first + warp < a.b_hi) {
-        pa = src.fetch((b_first + warp) * kBlk + lane * 4);
-        pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
+    if constexpr (REMOTE) {
+      resample_tile_remote<(NX != 1), NW>(src, s_par, TO, a.p2p, cur, a.nblk, a.world, b_first, pl->emax, pl->h0, pl->Mq, j0, nslots,
+                                          lane, warp);
+    } else {
+      if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 8) {
+        if (b_first + warp < a.b_hi) {
+          pa = src.fetch((b_first + warp) * kBlk + lane * 4);
+          pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
+        }
       }
+      resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
+                               lane, warp, first, pa, pb);
     }
-    resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
-                             lane, warp, first, pa, pb);
   } else {
     for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
     for (int sidx = tid; sidx < nslots; sidx += NT) {
@@ -1138,9 +1203,9 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
 
   // ---- output side
   const float4* tab_m8 = s_tab - 8;
-  T acc[PZ_NACC(NX)];  // sw, sw2, sx[NX], sxx[NX] at scale 2^aref (per lane, in the filter's arithmetic type)
+  float acc[PZ_NACC(NX)];  // sw, sw2, sx[NX], sxx[NX] at scale 2^aref (fp32 per lane)
 #pragma unroll
-  for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0;
+  for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0.0f;
   int32_t aref = kNZero;
   T cen[NX];
 #pragma unroll
@@ -1177,9 +1242,11 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     double x = 0;
     if (tid == 0) x = (double)etile;
     else for (int w = 0; w < NW; ++w) x += s_red[w][tid];
-    a.rec[(size_t)blockIdx.x * kMaxRec + tid] = x;
+    a.rec[(size_t)tile * kMaxRec + tid] = x;
   }
   if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
+  if constexpr (REMOTE) __syncthreads();   // the staging buffer and the reduction scratch are reused by the next tile
+  } while (REMOTE && (tile += (int)gridDim.x) < a.ntiles_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1371,6 +1438,7 @@ struct HaloPushArgs {
 };
 __global__ void __launch_bounds__(kThreads) pf_halo_push(const HaloPushArgs p) {
   const int tid = threadIdx.x;
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 12);
   const uint32_t epoch = p.ctl->t + (uint32_t)p.delta + 1u;
   const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
   const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
@@ -1398,6 +1466,7 @@ __global__ void __launch_bounds__(kThreads) pf_halo_push(const HaloPushArgs p) {
     if (atomicAdd(&mine->push_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
       __threadfence_system();
       mine->push_done = 0ull;
+      PZ_STAMP(true, 13);
       if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->halo_flag[1], (unsigned long long)epoch);
       if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->halo_flag[0], (unsigned long long)epoch);
     }
@@ -1432,7 +1501,7 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
     for (int i = tid; i < nw; i += kThreads) {
       const u64 x = wait_sys<false>(&mine->rec2[i / (2 * kShardRec)][i % (2 * kShardRec)],
                                     [epoch](unsigned long long x) { return (uint32_t)(x >> 32) == epoch; }, &p.ctl->comm_error,
-                                    p.wait_ticks);
+                                    p.wait_ticks, 2u);
       s_half[i] = (uint32_t)x;
     }
     __syncthreads();
@@ -1525,6 +1594,237 @@ __global__ void __launch_bounds__(kThreads) pf_plan_sharded(const ShardPlanArgs 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// pf_partition_sharded (peer-memory exchange): everything between the scan and the next step kernel in ONE
+// launch -- the all-gather of the rank records through the mailboxes, the plan (every CTA derives it from the
+// gathered records; CTA 0 stores it, the posterior summary and the margin verdict), the boundary positions of
+// this rank's blocks (xb = block_pos(base + local prefix)) with the two margins stored straight into the
+// neighbours' halos, and the merge-path split.  Nothing here waits for a neighbour's margins except the (few)
+// boundary tiles whose first input block lies in a halo; the step kernel's boundary CTAs wait for their halos
+// themselves, so the halo latency hides behind the interior tiles.
+// ------------------------------------------------------------------------------------------
+struct PartShardArgs {
+  PlanDev* plan;
+  CtlDev* ctl;
+  u64* rec;            // [world][kShardRec]: this rank's record (written by pf_scan_blocks)
+  const u64* pb;       // local prefix [nblk+1]
+  u64* xb;             // boundary positions, own entries [0, nblk], halo entries [b_lo, 0) and (nblk, b_hi]
+  int32_t* tile_start;
+  u64* status;
+  pz_step_summary* summ;
+  int64_t nblk, n_global, n_local, slot_base, b_lo, b_hi, margin;
+  int32_t rank, world, nx, delta, ntiles_out, tile_out, nscan, f64;
+  uint64_t seed;
+  double ll_const;
+  const ShardP2P* p2p;
+  unsigned long long wait_ticks;
+};
+
+__global__ void __launch_bounds__(kThreads) pf_partition_sharded(const PartShardArgs p) {
+  __shared__ u64 s_rec[kMaxRanks * kShardRec];
+  __shared__ u64 s_base[kMaxRanks + 1];   // CDF base of every rank
+  __shared__ PlanDev s_plan;
+  __shared__ int32_t s_overflow;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t t_cur = ((volatile CtlDev*)p.ctl)->t;
+  const uint32_t epoch = t_cur + (uint32_t)p.delta + 1u;
+  Mailbox* mine = p.p2p->mbox[p.rank];
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 3);
+  // ---- all-gather of the records: CTA 0 stores this rank's record into every mailbox as self-validating
+  // half-words, every CTA polls its own mailbox until all of this epoch are there
+  {
+    const int nw = p.world * 2 * kShardRec;
+    if (blockIdx.x == 0) {
+      for (int i = tid; i < nw; i += kThreads) {
+        const int q = i / (2 * kShardRec), w = i % (2 * kShardRec);
+        const u64 v = p.rec[(size_t)p.rank * kShardRec + (w >> 1)];
+        st_sys(&p.p2p->mbox[q]->rec2[p.rank][w], ((u64)epoch << 32) | (uint32_t)((w & 1) ? (v >> 32) : v));
+      }
+    }
+    uint32_t* s_half = reinterpret_cast<uint32_t*>(s_rec);
+    for (int i = tid; i < nw; i += kThreads) {
+      const u64 x = wait_sys<false>(&mine->rec2[i / (2 * kShardRec)][i % (2 * kShardRec)],
+                                    [epoch](unsigned long long x) { return (uint32_t)(x >> 32) == epoch; }, &p.ctl->comm_error,
+                                    p.wait_ticks, 2u);
+      s_half[i] = (uint32_t)x;
+    }
+    __syncthreads();
+  }
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 4);
+  u64 base = 0, total = 0;
+  for (int q = 0; q < p.world; ++q) {
+    const u64 tq = s_rec[(size_t)q * kShardRec];
+    if (q < p.rank) base += tq;
+    total += tq;
+  }
+  // ---- the plan: every CTA derives it (one 128-bit division), CTA 0 publishes it
+  if (tid == 0) {
+    const uint32_t t_next = t_cur + (uint32_t)p.delta;
+    const uint32_t U = philox4x32_10(0u, 0u, t_next, kStreamResample, (uint32_t)p.seed, (uint32_t)(p.seed >> 32)).x;
+    s_plan.base = base;
+    s_plan.emax = ((volatile PlanDev*)p.plan)->emax;
+    finalize_plan(&s_plan, total, p.n_global, U);
+    // margin verdict from the gathered records alone (the same on every rank, in every CTA): do the fixed margins
+    // (the last `margin` blocks of rank q-1, the first of rank q+1) cover the ancestors of every rank's slots?
+    int32_t overflow = 0;
+    u64 bq = 0;
+    SlotMap sm0(&s_plan, p.n_global);
+    for (int q = 0; q < p.world; ++q) {
+      const u64* r = s_rec + (size_t)q * kShardRec;
+      s_base[q] = bq;
+      if (total != 0) {
+        if (q > 0 && sm0.slot_end(bq + r[16]) < (uint32_t)((int64_t)q * p.n_local)) overflow = 1;
+        if (q + 1 < p.world && sm0.slot_end(bq + r[17]) > (uint32_t)((int64_t)(q + 1) * p.n_local)) overflow = 1;
+      }
+      bq += r[0];
+    }
+    s_base[p.world] = bq;
+    s_overflow = overflow;
+  }
+  __syncthreads();
+  SlotMap sm(&s_plan, p.n_global);
+  const bool remote = s_overflow != 0;   // the next resample reads remote blocks directly
+  const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
+  const int64_t nb = p.nblk, m = p.margin;
+  // ---- boundary positions of my blocks; the margins also go into the neighbours' halos (my boundaries 1..m are
+  // the RIGHT halo of rank-1 at its indices nb+1..nb+m; my boundaries nb-m..nb-1 the LEFT halo of rank+1 at -m..-1)
+  for (int64_t b = gid; b <= nb; b += gsz) {
+    const u64 v = total != 0 ? sm.block_pos(base + p.pb[b]) : 0ull;
+    p.xb[b] = v;
+    if (p.rank > 0 && b >= 1 && b <= m) p.p2p->xbn[0][nb + b] = v;
+    if (p.rank + 1 < p.world && b >= nb - m && b < nb) p.p2p->xbn[1][b - nb] = v;
+  }
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 6);
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    if (atomicAdd(&mine->pbx_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      __threadfence_system();
+      mine->pbx_done = 0ull;
+      if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->pbx_flag[1], (unsigned long long)epoch);
+      if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->pbx_flag[0], (unsigned long long)epoch);
+      for (int q = 0; q < p.world; ++q) st_sys(&p.p2p->mbox[q]->xb_done[p.rank], (unsigned long long)epoch);  // my xb is complete
+      PZ_STAMP(true, 8);
+    }
+  }
+  // ---- CTA 0: plan, posterior summary, margin verdict (from the gathered records alone: the same on every rank)
+  if (gid == 0) {
+    PlanDev* pl = p.plan;
+    pl->base = base;
+    pl->shard_epoch = epoch;
+    pl->total = s_plan.total; pl->degenerate = s_plan.degenerate; pl->U = s_plan.U; pl->L = s_plan.L; pl->rho = s_plan.rho;
+    pl->Mq = s_plan.Mq; pl->h0 = s_plan.h0;
+    int32_t overflow = s_overflow;
+    int64_t migrated = 0;
+    if (total != 0) {  // my slots whose ancestor is not one of my particles
+      const int64_t j_lo = (int64_t)p.rank * p.n_local, j_hi = j_lo + p.n_local;
+      const int64_t s0 = sm.slot_end(base), s1 = sm.slot_end(base + s_rec[(size_t)p.rank * kShardRec]);
+      const int64_t a0 = (s0 < j_hi ? s0 : j_hi) - j_lo, a1 = j_hi - (s1 > j_lo ? s1 : j_lo);
+      migrated = (a0 > 0 ? a0 : 0) + (a1 > 0 ? a1 : 0);
+    }
+    bool comm_err = ((volatile CtlDev*)p.ctl)->comm_error != 0;
+    for (int q = 0; q < p.world; ++q) comm_err = comm_err || s_rec[(size_t)q * kShardRec + 18] != 0;
+    if (comm_err) overflow = 2;
+    pl->shard_overflow = overflow;
+    if (p.delta) {  // moment sums of all ranks, in rank order (every rank computes the same value)
+      double sw = 0, sw2 = 0, sx[PZ_MAX_NX] = {}, sxx[PZ_MAX_NX] = {};
+      for (int q = 0; q < p.world; ++q) {
+        const u64* r = s_rec + (size_t)q * kShardRec;
+        sw += __longlong_as_double((long long)r[1]);
+        sw2 += __longlong_as_double((long long)r[2]);
+        for (int d = 0; d < p.nx; ++d) {
+          sx[d] += __longlong_as_double((long long)r[3 + d]);
+          sxx[d] += __longlong_as_double((long long)r[3 + PZ_MAX_NX + d]);
+        }
+      }
+      pl->sw = sw; pl->sw2 = sw2;
+      for (int d = 0; d < p.nx; ++d) { pl->sx[d] = sx[d]; pl->sxx[d] = sxx[d]; }
+      pz_step_summary* o = p.summ ? p.summ + (t_cur % kObsRing) : nullptr;
+      write_summary(pl, o, t_cur, p.nx, p.n_global, p.ll_const, p.f64);
+      // (margins too small -- overflow == 1 -- is not an error: the next step takes the remote-read path)
+      if (o) o->n_migrated = overflow == 2 ? -2 : migrated;
+    }
+  }
+  // ---- merge-path split: one warp per output tile.  The first input block of a tile lies among my own blocks
+  // unless the tile starts before my first block's children end (left halo) or after my last block's (right halo)
+  const u64 P0 = base, PN = base + p.pb[nb];
+  const uint32_t end0 = total != 0 ? sm.slot_end(P0) : 0u, endN = total != 0 ? sm.slot_end(PN) : 0u;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  for (int64_t tile = gid >> 5; tile < p.ntiles_out; tile += nwarps) {
+    const uint32_t j0 = (uint32_t)(p.slot_base + tile * p.tile_out);
+    int64_t lo, hi;
+    if (remote) {
+      // the margins do not cover this resample: GLOBAL split over the blocks of all ranks, reading the owners' local
+      // prefixes over NVLink (they are final: every rank's record has been gathered)
+      lo = 0; hi = (int64_t)p.world * nb;
+      while (hi > lo) {
+        const int64_t n = hi - lo, step = (n + 31) >> 5;
+        int64_t off = (int64_t)(lane + 1) * step;
+        off = off < n ? off : n;
+        const int64_t mid = lo + off - 1, gb1 = mid + 1;          // boundary gb1 = end of global block mid
+        const int q = (int)(gb1 / nb);
+        const u64 C = q >= p.world ? total : s_base[q] + ((volatile const u64*)p.p2p->pball[q])[gb1 - (int64_t)q * nb];
+        const bool pred = total != 0 && sm.slot_end(C) > j0;
+        const uint32_t mk = __ballot_sync(0xffffffffu, pred);
+        if (mk == 0) { lo = hi; break; }
+        const int f = __ffs(mk) - 1;
+        int64_t offf = (int64_t)(f + 1) * step;
+        offf = offf < n ? offf : n;
+        hi = lo + offf - 1;
+        lo = lo + (int64_t)f * step;
+      }
+      if (lane == 0) p.tile_start[tile] = (int32_t)lo;   // a GLOBAL block index
+      continue;
+    }
+    int side = -1;   // -1: own blocks; 0 / 1: the left / right halo
+    if (p.rank > 0 && end0 > j0) { lo = p.b_lo; hi = 0; side = 0; }
+    else if (p.rank + 1 < p.world && endN <= j0) { lo = nb; hi = p.b_hi; side = 1; }
+    else { lo = 0; hi = nb; }
+    if (side >= 0) {  // this epoch's boundary positions from the neighbour
+      if (lane == 0)
+        wait_sys(&mine->pbx_flag[side], [epoch](unsigned long long x) { return x >= (unsigned long long)epoch; }, &p.ctl->comm_error, p.wait_ticks, 0x10u);
+      __syncwarp();
+      __threadfence_system();
+    }
+    // 32-ary search for min b in [lo, hi) with slot_end(boundary b + 1) > j0 (hi when there is none)
+    while (hi > lo) {
+      const int64_t n = hi - lo, step = (n + 31) >> 5;
+      int64_t off = (int64_t)(lane + 1) * step;
+      off = off < n ? off : n;
+      const int64_t mid = lo + off - 1;
+      uint32_t se;
+      if (side < 0 || mid + 1 == 0 || mid + 1 == nb) se = sm.slot_end(base + p.pb[mid + 1]);    // my own boundaries (0 and nb included)
+      else se = min((uint32_t)(((volatile u64*)p.xb)[mid + 1] >> 32), (uint32_t)p.n_global);  // a halo entry
+      const bool pred = total != 0 && se > j0;
+      const uint32_t mk = __ballot_sync(0xffffffffu, pred);
+      if (mk == 0) { lo = hi; break; }
+      const int f = __ffs(mk) - 1;
+      int64_t offf = (int64_t)(f + 1) * step;
+      offf = offf < n ? offf : n;
+      hi = lo + offf - 1;
+      lo = lo + (int64_t)f * step;
+    }
+    // (a tile of the left-halo case whose search found nothing starts at my block 0; of the right-halo case: b_hi)
+    if (lane == 0) p.tile_start[tile] = (int32_t)lo;
+  }
+  if (gid < p.nscan) p.status[gid] = 0ull;
+  PZ_STAMP(blockIdx.x == 0 && tid == 0, 10);
+  // ---- the last CTA to finish advances the step counter (every CTA read it above)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&mine->part_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      mine->part_done = 0ull;
+      PZ_STAMP(true, 9);
+      p.ctl->t = t_cur + (uint32_t)p.delta;
+      p.ctl->emax_acc = kNZero;
+      p.ctl->scan_counter = 0;
+      p.ctl->scan_done = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
@@ -1554,6 +1854,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 #endif
 #ifndef PZ_TBND
 #define PZ_TBND 7    // output blocks per tile, NX > 1, double
+#endif
+#ifndef PZ_OCC4D
+#define PZ_OCC4D 2   // resident CTAs per SM of the double NX = 4 kernel
 #endif
 #ifndef PZ_OCC1D
 #define PZ_OCC1D 3   // resident 256-thread-equivalents per SM the double NX = 1 kernel's registers are held to
@@ -1620,11 +1923,11 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
 }
 
 template <class T, int NX, int NY, int MODE, bool KRON, bool SMALL>
-static void launch_tile(const TileArgs& ta, cudaStream_t s) {
+static int launch_tile(const TileArgs& ta, cudaStream_t s) {
   constexpr bool F64 = sizeof(T) == 8;
   constexpr int NT = (NX == 1) ? PZ_NT1 : PZ_NTN;
   constexpr int TO = tile_blocks(NX, F64, SMALL) * kBlk;
-  constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : 2) : min_ctas(NX);
+  constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : (NX <= 4 ? PZ_OCC4D : 2)) : min_ctas(NX);
   auto kern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT)>;
   // staged parents [NX][TO] + inverse-CDF table
   const size_t smem = (size_t)NX * TO * sizeof(T) + PZ_ICDF_ROWS * sizeof(float4);
@@ -1638,6 +1941,20 @@ static void launch_tile(const TileArgs& ta, cudaStream_t s) {
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
+  if constexpr (MODE == 0) {
+    if (ta.a.p2p != nullptr) {   // sharded over peer memory: the remote-read fallback follows (it exits at once unless the margins overflowed)
+      auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT), true>;
+      static std::atomic<unsigned long long> rattr_done{0};
+      if (!(rattr_done.load(std::memory_order_acquire) & bit)) {
+        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rattr_done.fetch_or(bit, std::memory_order_release);
+      }
+      const int rgrid = ta.a.ntiles_out < 296 ? ta.a.ntiles_out : 296;
+      rkern<<<rgrid, NT, smem, s>>>(ta);
+      return 2;
+    }
+  }
+  return 1;
 }
 
 static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
@@ -1649,13 +1966,11 @@ static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
 #define PZ_DISPATCH(Tv, NXv, NYv, KR)                                     \
   if (f64 == (sizeof(Tv) == 8) && nx == NXv && ny == NYv && kron == KR) { \
     if (small) {                                                          \
-      if (fused) launch_tile<Tv, NXv, NYv, 0, KR, true>(ta, s);           \
-      else launch_tile<Tv, NXv, NYv, 1, KR, true>(ta, s);                 \
-    } else {                                                              \
-      if (fused) launch_tile<Tv, NXv, NYv, 0, KR, false>(ta, s);          \
-      else launch_tile<Tv, NXv, NYv, 1, KR, false>(ta, s);                \
+      if (fused) return launch_tile<Tv, NXv, NYv, 0, KR, true>(ta, s);    \
+      return launch_tile<Tv, NXv, NYv, 1, KR, true>(ta, s);               \
     }                                                                     \
-    return 1;                                                             \
+    if (fused) return launch_tile<Tv, NXv, NYv, 0, KR, false>(ta, s);     \
+    return launch_tile<Tv, NXv, NYv, 1, KR, false>(ta, s);                \
   }
   PZ_DISPATCH(float, 1, 1, false)
   PZ_DISPATCH(float, 1, 1, true)
@@ -1676,8 +1991,9 @@ static int dispatch_tile(const TileArgs& ta, cudaStream_t s) {
 // anc == nullptr: fused systematic step; else parents come from the stored ancestor array.
 int launch_step(const StepArgs& a, const int32_t* anc, cudaStream_t s) {
   TileArgs ta{a, anc};
-  if (dispatch_tile(ta, s) < 0) return -1;
-  return 1 + scan_partition(a, 1, fused_tile_out(a.model.nx, a.f64), s);
+  const int nt = dispatch_tile(ta, s);
+  if (nt < 0) return -1;
+  return nt + scan_partition(a, 1, fused_tile_out(a.model.nx, a.f64), s);
 }
 
 int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
@@ -1729,6 +2045,19 @@ int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s) {
 }
 
 int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s) { return partition(a, tile_out, delta, s); }
+
+int launch_partition_sharded(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
+  PartShardArgs p{};
+  p.plan = a.plan; p.ctl = a.ctl; p.rec = a.shard_rec; p.pb = a.pb; p.xb = a.xb; p.tile_start = a.tile_start; p.status = a.scan_status;
+  p.summ = a.summ; p.nblk = a.nblk; p.n_global = a.n_global; p.n_local = a.n_local; p.slot_base = a.slot_base; p.b_lo = a.b_lo; p.b_hi = a.b_hi;
+  p.margin = a.margin; p.rank = a.rank; p.world = a.world; p.nx = a.model.nx; p.delta = delta; p.ntiles_out = a.ntiles_out; p.tile_out = tile_out;
+  p.nscan = a.nscan; p.f64 = a.f64; p.seed = a.seed; p.ll_const = a.ll_const; p.p2p = a.p2p; p.wait_ticks = a.wait_ticks;
+  int grid = partition_grid(a.ntiles_out, a.nscan, a.nblk + 1);
+  if (grid > 592) grid = 592;  // every CTA polls its mailbox: keep the whole grid resident (148 SMs x 4)
+  pf_partition_sharded<<<grid, kThreads, 0, s>>>(p);
+  return 1;
+}
+
 
 int launch_ctl_reset(CtlDev* ctl, cudaStream_t s) {
   pf_ctl_reset<<<1, 1, 0, s>>>(ctl);

@@ -138,9 +138,11 @@ struct Mailbox {
   unsigned long long emax[kMaxRanks];                // (epoch << 32) | block exponent of rank q
   unsigned long long rec2[kMaxRanks][2 * kShardRec]; // rank q's record (pf_scan_blocks' last CTA): (epoch << 32) | low / high half of each word
   unsigned long long halo_flag[2];                   // epoch of the X / Q / eb margins in my left / right halo (written by that neighbour's pf_halo_push)
-  unsigned long long pbx_flag[2];                    // epoch of the prefix margins in my left / right halo (that neighbour's pf_plan_sharded)
+  unsigned long long pbx_flag[2];                    // epoch of the boundary-position (xb) margins in my left / right halo (that neighbour's pf_partition_sharded)
   unsigned long long push_done;                      // CTAs of pf_halo_push that finished their stores
-  unsigned long long pbx_done;                       // CTAs of pf_plan_sharded that finished their prefix stores
+  unsigned long long pbx_done;                       // CTAs of pf_partition_sharded that finished their margin stores
+  unsigned long long part_done;                      // CTAs of pf_partition_sharded that finished (the last one advances the step counter)
+  unsigned long long xb_done[kMaxRanks];             // epoch of rank q's complete boundary-position array (read by the remote step kernel)
 };
 struct ShardP2P {
   Mailbox* mbox[kMaxRanks];   // mbox[q]: rank q's mailbox (mbox[rank] is local memory)
@@ -148,6 +150,14 @@ struct ShardP2P {
   uint16_t* Qn[2][2];
   int32_t* ebn[2][2];
   uint64_t* pbxn[2];
+  uint64_t* xbn[2];           // the neighbours' boundary-position arrays (halo layout as ours)
+  // every rank's arrays (own regions), for the step whose ancestors reach beyond the halo margins: the remote
+  // step kernel and the global merge-path split read any block of any rank directly over NVLink
+  void* Xall[kMaxRanks][2];
+  uint16_t* Qall[kMaxRanks][2];
+  int32_t* eball[kMaxRanks][2];
+  uint64_t* xball[kMaxRanks];
+  uint64_t* pball[kMaxRanks];  // local prefixes (final once the rank's record is gathered)
 };  // 64-bit words per rank in the all-gathered record
 
 // Host-callable launchers (pz_kernels.cu).  Each returns the number of kernels it enqueued.
@@ -162,6 +172,8 @@ int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]);
 int launch_tile_only(const StepArgs& a, cudaStream_t s);                 // fused step kernel
 int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s);      // after the emax all-reduce
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s);   // after the all-gather: plan, absolute prefix, summary, margin check
+// peer memory: record all-gather + plan + summary + margin check + boundary positions (own and pushed margins) + merge-path split, one kernel
+int launch_partition_sharded(const StepArgs& a, int tile_out, int delta, cudaStream_t s);
 int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s);      // peer memory: X / Q / eb margins -> the neighbours (independent of the scan)
 int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s);  // after the halo exchange
 
@@ -209,11 +221,11 @@ void mtt_fill_params(const pz_model_desc* d, void* out_mttdev);
 void dbg_read_stamps(unsigned long long* out);  // debug build: %globaltimer stamps of the sharded exchange phases
 #endif
 int mtt_step_ctas(int64_t n);  // CTAs of mtt_step = rows of its per-CTA summary partials (5 doubles each)
-int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
+int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, int64_t ld, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
                     cudaStream_t s);
 int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDev* ctl, pz_step_summary* summ, double ll_const,
                        const unsigned long long* overflow, cudaStream_t s);
-int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
+int launch_mtt_gather(const uint32_t* sdata, int64_t ld, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
 
 }  // namespace pz

@@ -47,7 +47,6 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, u
 }
 
 constexpr float kLog2e = 0x1.715476p+0f;
-constexpr double kLog2eD = 0x1.71547652b82fep+0;  // log2(e) rounded to double (f64 filters)
 constexpr int32_t kNZero = -(1 << 30);  // exponent marker of an empty block (every weight zero)
 constexpr int kGuard = 16;              // guard bits of the global fixed-point scale
 

@@ -11,12 +11,17 @@
 //   the reference's terms one by one and checks the reduction on every call);
 //   updateWithAssocs (:75-87) -> Kalman update, coasting Bernoulli((1-pd)/(1-ps pd)), births.
 //
-// Mapping: one thread per particle (see mtt_step).  A particle is a 1040-byte record (16-byte
-// header + 16 x 64-byte track records) read through the stored ancestor index; only the live
-// track records move (every 64-byte record is two full 32-byte sectors).
+// Mapping: one thread per particle (see mtt_step).  A particle is a record of 260 32-bit fields (4 header
+// fields + 16 tracks x 16 fields) stored STRUCTURE-OF-ARRAYS, S[field][particle]: thread j reads field f of its
+// parent at S[f * ld + anc[j]] -- ancestors are sorted, so the 32 loads of a warp fall into a handful of
+// consecutive 128-byte lines -- and writes its own at S[f * ld + j], fully coalesced.  (The first layout, one
+// contiguous 1040-byte record per particle read with 128-bit loads, touched 32 different sectors per warp
+// load: 0.31 of the HBM rate on live-record bytes, stalled on the memory pipeline.)  Only the fields of live
+// tracks move.
 //
 // Unlike the linear-Gaussian kernels this translation unit is NOT bound by the bit-exact fp32
 // spec (parity for MTT is statistical): it uses fast intrinsics and fmad.
+#include <atomic>
 #include <cstdlib>
 
 #include "pz_kernels.cuh"
@@ -111,8 +116,9 @@ __device__ __forceinline__ void update(Track& t, float z0, float z1, float r) {
 constexpr int kMttWords = 4 + 16 * 16;  // 32-bit words per particle record
 
 struct MttArgs {
-  const uint32_t* sin;   // [N][kMttWords]
+  const uint32_t* sin;   // [kMttWords][ld]
   uint32_t* sout;
+  int64_t ld;            // particles per field row
   const int32_t* anc;    // [N]
   float* lw;             // [N]
   const float* obs;      // [m_max][2]
@@ -125,23 +131,25 @@ struct MttArgs {
   MttDev p;
 };
 
-__device__ __forceinline__ void load_track(const uint32_t* __restrict__ rec, Track& tr) {
-  const uint4* rp = reinterpret_cast<const uint4*>(rec);
-  const uint4 w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3];
-  tr.id = (int)w0.x;
-  tr.m[0] = __uint_as_float(w0.y); tr.m[1] = __uint_as_float(w0.z); tr.m[2] = __uint_as_float(w0.w);
-  tr.m[3] = __uint_as_float(w1.x);
-  tr.c[0] = __uint_as_float(w1.y); tr.c[1] = __uint_as_float(w1.z); tr.c[2] = __uint_as_float(w1.w);
-  tr.c[3] = __uint_as_float(w2.x); tr.c[4] = __uint_as_float(w2.y); tr.c[5] = __uint_as_float(w2.z);
-  tr.c[6] = __uint_as_float(w2.w); tr.c[7] = __uint_as_float(w3.x); tr.c[8] = __uint_as_float(w3.y);
-  tr.c[9] = __uint_as_float(w3.z);
+// track k of particle `par`: fields 4 + 16 k + {0: id, 1..4: mean, 5..14: covariance triangle}
+__device__ __forceinline__ void load_track(const uint32_t* __restrict__ s, int64_t ld, int64_t par, int k, Track& tr) {
+  const uint32_t* __restrict__ r = s + (size_t)(4 + 16 * k) * ld + par;
+  uint32_t w[15];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) w[i] = r[(size_t)i * ld];   // 15 independent loads in flight
+  tr.id = (int)w[0];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tr.m[i] = __uint_as_float(w[1 + i]);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) tr.c[i] = __uint_as_float(w[5 + i]);
 }
-__device__ __forceinline__ void store_track(uint32_t* __restrict__ rec, const Track& x) {
-  uint4* wp = reinterpret_cast<uint4*>(rec);
-  wp[0] = make_uint4((uint32_t)x.id, __float_as_uint(x.m[0]), __float_as_uint(x.m[1]), __float_as_uint(x.m[2]));
-  wp[1] = make_uint4(__float_as_uint(x.m[3]), __float_as_uint(x.c[0]), __float_as_uint(x.c[1]), __float_as_uint(x.c[2]));
-  wp[2] = make_uint4(__float_as_uint(x.c[3]), __float_as_uint(x.c[4]), __float_as_uint(x.c[5]), __float_as_uint(x.c[6]));
-  wp[3] = make_uint4(__float_as_uint(x.c[7]), __float_as_uint(x.c[8]), __float_as_uint(x.c[9]), 0u);
+__device__ __forceinline__ void store_track(uint32_t* __restrict__ s, int64_t ld, int64_t j, int k, const Track& x) {
+  uint32_t* __restrict__ r = s + (size_t)(4 + 16 * k) * ld + j;
+  r[0] = (uint32_t)x.id;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[(size_t)(1 + i) * ld] = __float_as_uint(x.m[i]);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) r[(size_t)(5 + i) * ld] = __float_as_uint(x.c[i]);
 }
 
 // One THREAD per particle (the track count of a particle is small and nearly equal across the
@@ -169,9 +177,9 @@ struct DerLocal {
 };
 
 template <class Der>
-__device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __restrict__ src, int k, const Der& der) {
+__device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __restrict__ sin, int64_t ld, int64_t par, int k, const Der& der) {
   Track tr;
-  load_track(src + 4 + 16 * k, tr);
+  load_track(sin, ld, par, k, tr);
   predict(p, tr);
   const float sa = tr.c[0] + p.r, sb = tr.c[1], sd = tr.c[4] + p.r;
   const float det = sa * sd - sb * sb, idet = 1.0f / det;
@@ -222,17 +230,14 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   const DerLocal dl{loc};
   const uint32_t t = a.ctl->t;
   const int64_t par = a.anc[j];
-  const uint32_t* __restrict__ src = a.sin + (size_t)par * kMttWords;
-  uint32_t* __restrict__ dst = a.sout + (size_t)j * kMttWords;
-  const uint4 hdr = *reinterpret_cast<const uint4*>(src);
-  const int cnt = (int)hdr.x;
+  const int cnt = (int)a.sin[par];                       // header fields 0: track count, 1: next track id, 2: births dropped
   const int cnt_fast = cnt < kMttFast ? cnt : kMttFast;
-  const int next_id = (int)hdr.y;
+  const int next_id = (int)a.sin[(size_t)a.ld + par];
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
 
   // ---- pass A: predictive density of a measurement of every track: N(z; H m, H P H^T + r I)
-  for (int k = 0; k < cnt_fast; ++k) mtt_derive(a.p, src, k, ds);
-  for (int k = kMttFast; k < cnt; ++k) mtt_derive(a.p, src, k, dl);
+  for (int k = 0; k < cnt_fast; ++k) mtt_derive(a.p, a.sin, a.ld, par, k, ds);
+  for (int k = kMttFast; k < cnt; ++k) mtt_derive(a.p, a.sin, a.ld, par, k, dl);
 
   // ---- pass B: association proposal; uniforms: detection o takes word o & 3 of Philox call o >> 2
   uint32_t assigned = 0;   // bit k: track k has a detection
@@ -281,13 +286,13 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     const bool det = (assigned >> k) & 1u;
     if (!det && !(u01(word) < a.p.p_coast)) continue;  // undetected and not coasting: the track dies
     Track tr;
-    load_track(src + 4 + 16 * k, tr);
+    load_track(a.sin, a.ld, par, k, tr);
     predict(a.p, tr);
     if (det) {
       const int o = (int)((k < 12 ? obs_lo >> (5 * k) : obs_hi >> (5 * (k - 12))) & 31ull);
       update(tr, s_z[o][0], s_z[o][1], a.p.r);
     }
-    store_track(dst + 4 + 16 * n_surv, tr);
+    store_track(a.sout, a.ld, j, n_surv, tr);
     ++n_surv;
   }
   // births: the i-th new-track detection (newTrackD conditioned on it)
@@ -306,9 +311,11 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     for (int q = 0; q < 10; ++q) nt.c[q] = 0.f;
     nt.c[0] = a.p.bp; nt.c[4] = a.p.bp; nt.c[7] = a.p.bv; nt.c[9] = a.p.bv;
     update(nt, s_z[o][0], s_z[o][1], a.p.r);
-    store_track(dst + 4 + 16 * (n_surv + i), nt);
+    store_track(a.sout, a.ld, j, n_surv + i, nt);
   }
-  *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)(n_surv + n_born), (uint32_t)(next_id + n_new), n_new > room ? 1u : 0u, 0u);
+  a.sout[j] = (uint32_t)(n_surv + n_born);
+  a.sout[(size_t)a.ld + j] = (uint32_t)(next_id + n_new);
+  a.sout[(size_t)2 * a.ld + j] = n_new > room ? 1u : 0u;
   a.lw[j] = lw;
   if (n_new > room) atomicAdd(a.overflow, (unsigned long long)(n_new - room));
   out_lw = sanitize_lw(lw);
@@ -407,13 +414,18 @@ __global__ void __launch_bounds__(kFinalThreads) mtt_summary_final(PlanDev* pl, 
   o->total_weight = pl->total;
 }
 
-// thinned read of the resampled population: every stride-th output slot's parent record
-__global__ void mtt_gather_thin(const uint32_t* __restrict__ s, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
+// thinned read of the resampled population: every stride-th output slot's parent record, assembled as one
+// contiguous 260-word record per selected particle (the host unpacks it)
+__global__ void mtt_gather_thin(const uint32_t* __restrict__ s, int64_t ld, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
                                 uint32_t* __restrict__ out) {
   const int64_t sel = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (sel >= n_sel) return;
   const int64_t p = anc[sel * stride];
-  for (int w = threadIdx.x & 31; w < kMttWords; w += 32) out[(size_t)sel * kMttWords + w] = s[(size_t)p * kMttWords + w];
+  const int cnt = (int)s[p];
+  for (int w = threadIdx.x & 31; w < kMttWords; w += 32) {
+    const bool live = w < 4 || (w - 4) / 16 < cnt;    // fields of dead track slots hold stale data
+    out[(size_t)sel * kMttWords + w] = live ? s[(size_t)w * ld + p] : 0u;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -447,20 +459,21 @@ size_t mtt_params_size() { return sizeof(MttDev); }
 
 int mtt_step_ctas(int64_t n) { return (int)((n + kMttThreads - 1) / kMttThreads); }
 
-int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
+int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, int64_t ld, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
                     cudaStream_t s) {
   MttArgs a;
-  a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
+  a.sin = sin; a.sout = sout; a.ld = ld; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
   a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
   const size_t smem = (size_t)kMttDerived * kMttFast * kMttThreads * sizeof(float);  // 28 KB
-  static unsigned long long attr_done = 0;  // per device (function attributes are per context)
+  static std::atomic<unsigned long long> attr_done{0};  // per device (function attributes are per context)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!((attr_done >> (dev & 63)) & 1ull)) {
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     cudaFuncSetAttribute(mtt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done |= 1ull << (dev & 63);
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   mtt_step<<<(unsigned)((n + kMttThreads - 1) / kMttThreads), kMttThreads, smem, s>>>(a);
   return 1;
@@ -472,9 +485,9 @@ int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDe
   return 1;
 }
 
-int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
+int launch_mtt_gather(const uint32_t* sdata, int64_t ld, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
   const int per_cta = kThreads / 32;
-  mtt_gather_thin<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sdata, anc, stride, n_sel, out);
+  mtt_gather_thin<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sdata, ld, anc, stride, n_sel, out);
   return 1;
 }
 

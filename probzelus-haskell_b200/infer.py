@@ -64,7 +64,7 @@ _SYMBOLS = [
     "pz_filter_create", "pz_comm_unique_id", "pz_filter_create_sharded", "pz_filter_step", "pz_filter_run",
     "pz_filter_last_timing", "pz_filter_step_profile", "pz_filter_read_particles", "pz_filter_read_tracks", "pz_filter_read_ancestors", "pz_filter_read_state",
     "pz_filter_read_logw", "pz_filter_read_state_f64", "pz_filter_read_logw_f64", "pz_filter_read_posterior", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
-    "pz_filter_destroy", "pz_shard_halo_range", "pz_model_walker", "pz_model_beta_bernoulli", "pz_importance_resampling",
+    "pz_filter_destroy", "pz_model_walker", "pz_model_beta_bernoulli", "pz_importance_resampling",
     "pz_dist_sample", "pz_dist_score", "pz_filter_reset", "pz_filter_create_multi",
 ]
 
@@ -118,7 +118,6 @@ def lib():
     L.pz_filter_n_local.restype = C.c_int64
     L.pz_resample_systematic.argtypes = [f64p, C.c_int64, C.c_double, i32p]
     L.pz_resample_multinomial.argtypes = [f64p, C.c_int64, C.c_uint64, C.c_uint32, i32p]
-    L.pz_shard_halo_range.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.pz_filter_destroy.argtypes = [C.c_void_p]
     L.pz_filter_destroy.restype = None
     L.pz_model_walker.argtypes = [C.POINTER(ModelDesc)]
@@ -204,7 +203,7 @@ class Posterior:
 
     def __init__(self, stream, summary):
         self._stream = stream
-        nx = stream.nx
+        nx = 6 if stream.model.kind == PZ_MODEL_WALKER else stream.nx   # the walker summarises x, y, vx, vy, P(walking), P(running)
         self.step = summary.step
         self.mean = np.array(summary.mean[:nx])
         self.var = np.array(summary.var[:nx])
@@ -355,12 +354,6 @@ def zparticles_sharded(num_particles, model, nccl_id, rank, world, seed=0, devic
     """zparticles over `world` GPUs, one process per GPU: this rank holds global slots
     [rank * N / world, (rank + 1) * N / world); resampling is global."""
     return ZStream(model, num_particles, seed, device, rank, world, nccl_id)
-
-
-def shard_halo_range(need_lo, need_hi, blocks_per_rank, src):
-    lo, hi = C.c_int64(), C.c_int64()
-    _check(lib().pz_shard_halo_range(need_lo, need_hi, blocks_per_rank, src, C.byref(lo), C.byref(hi)))
-    return lo.value, hi.value
 
 
 def zparticles_multi(num_particles, model, devices, seed=0):

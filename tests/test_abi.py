@@ -118,8 +118,6 @@ def test_every_argument_error_is_reported_before_device_work(pz):
     assert L.pz_comm_unique_id(None) == -1
     L.pz_filter_destroy(None)   # a no-op, like free(NULL)
     lo, hi = C.c_int64(), C.c_int64()
-    assert L.pz_shard_halo_range(0, 1, 0, 0, C.byref(lo), C.byref(hi)) == -1
-    assert L.pz_shard_halo_range(0, 1, 16, 0, None, None) == -1
 
 
 def test_delayed_descriptor_validation(pz):

@@ -129,7 +129,7 @@ def test_shim_mirror_runs_the_haskell_call_sequence(pz):
             post = zs.step(obs(t)[:d.ny])
             got = sc[name]["steps"][t]
             assert got["step"] == t and got["le"] == post.log_evidence_inc and got["ess"] == post.ess
-            assert got["mean"] == list(post.mean) and got["var"] == list(post.var)
+            assert got["mean"] == list(post.mean)[:d.nx] and got["var"] == list(post.var)[:d.nx]   # the Haskell side reads nx entries
         stride = {"mtt_track": 999, "stt_delayed": 5000}.get(name, 1000)
         parts = zs.read_particles(stride)
         assert sc[name]["rows"] == parts.shape[0] and len(sc[name]["first_particle"]) == d.nx
@@ -148,4 +148,5 @@ def test_shim_mirror_runs_the_haskell_call_sequence(pz):
         a, b = sc["multi_mtt_track"], sc["single_mtt_track_same_n"]
         assert a["n_local"] == 256 * 40 * ndev
         for sa, sb in zip(a["steps"], b["steps"]):
-            assert np.allclose(sa["mean"], sb["mean"], rtol=1e-9, atol=1e-12) and abs(sa["ess"] - sb["ess"]) < 1e-6 * sb["ess"]
+            # (fp32 per-lane partial sums grouped by tile: the shards' tiles differ from the single filter's)
+                assert np.allclose(sa["mean"], sb["mean"], rtol=1e-5, atol=1e-7) and abs(sa["ess"] - sb["ess"]) < 1e-6 * sb["ess"]

@@ -180,15 +180,6 @@ def test_sharding_protocol_gloo_world4_middle_ranks(shift):
     assert all(ret["migrated%d" % r] > 0 for r in takers), dict(ret)
 
 
-def test_halo_range_function(pz):
-    # rank 1 of 4 (100 blocks each) needs global blocks 95..210: 5 from rank 0, its own, 11 from rank 2
-    assert pz.shard_halo_range(95, 210, 100, 0) == (95, 100)
-    assert pz.shard_halo_range(95, 210, 100, 1) == (100, 200)
-    assert pz.shard_halo_range(95, 210, 100, 2) == (200, 211)
-    lo, hi = pz.shard_halo_range(95, 210, 100, 3)
-    assert hi == lo  # nothing from rank 3
-
-
 def _gpu_worker(rank, world, port, model, n_global, seed, T, env, outdir):
     import torch
     import torch.distributed as dist
@@ -203,8 +194,8 @@ def _gpu_worker(rank, world, port, model, n_global, seed, T, env, outdir):
     hd = {"rw1d": H.model_rw1d, "mtt_track": H.model_mtt_track, "stt": H.model_stt}[model]()
     obs, _ = H.gen_obs(hd, T)
     zs = pz.zparticles_sharded(n_global, d, ids[0], rank, world, seed=seed, device=rank)
-    if env and env.get("PZ_HALO_BLOCKS") == "1":
-        # a one-block halo margin cannot hold the migration of this stream: every rank must report it
+    if env and env.get("PZ_HALO_BLOCKS") == "1" and env.get("PZ_SHARD_NCCL"):
+        # a one-block halo margin cannot hold the migration of this stream: on the NCCL exchange path every rank reports it
         codes = []
         for y in obs:
             try:
@@ -250,20 +241,72 @@ def test_sharded_equals_single_gpu(pz, model, exchange, world, tmp_path):
 
 
 @pytest.mark.gpu
-def test_sharded_margin_overflow_is_reported_by_every_rank(pz, tmp_path):
-    """PZ_HALO_BLOCKS=1: the ancestors of a rank's boundary slots reach beyond a one-block margin within a
-    few steps; the verdict is computed by every rank from the gathered records, so both ranks raise
-    PZ_ECAPACITY (-5) at the same step instead of resampling from an incomplete halo."""
+def test_sharded_margin_overflow_nccl_path_reports_it_on_every_rank(pz, tmp_path):
+    """PZ_HALO_BLOCKS=1 on the NCCL exchange path (kept for A/B): the ancestors of a rank's boundary slots reach beyond a
+    one-block margin within a few steps; the verdict is computed by every rank from the gathered records, so both ranks
+    raise PZ_ECAPACITY (-5) at the same step instead of resampling from an incomplete halo."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world, n_global, seed, T = 2, 2 * 256 * 400, 7, 40
-    mp.spawn(_gpu_worker, args=(world, _free_port(), "rw1d", n_global, seed, T, {"PZ_HALO_BLOCKS": "1"}, str(tmp_path)),
+    mp.spawn(_gpu_worker, args=(world, _free_port(), "rw1d", n_global, seed, T, {"PZ_HALO_BLOCKS": "1", "PZ_SHARD_NCCL": "1"}, str(tmp_path)),
              nprocs=world, join=True)
     c0, c1 = np.load(tmp_path / "codes_0.npy"), np.load(tmp_path / "codes_1.npy")
     assert np.array_equal(c0, c1)
     assert (c0 != 0).any() and c0[np.flatnonzero(c0)[0]] == -5   # the first failure is the capacity report
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["rw1d", "stt"])
+def test_sharded_margin_overflow_falls_back_to_remote_reads(pz, model, tmp_path):
+    """The peer-memory path never fails on imbalance (the reference's resample has no such failure mode,
+    Inference.hs:60-61): with a one-block margin (PZ_HALO_BLOCKS=1) the ancestors of boundary slots reach beyond it
+    within a few steps; those steps run the remote-read kernels (global merge-path split, blocks read from their
+    owners over NVLink) and the run stays bit-equal to the single-GPU filter."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    n_global, seed, T = world * 256 * 400, 7, 40
+    mp.spawn(_gpu_worker, args=(world, _free_port(), model, n_global, seed, T, {"PZ_HALO_BLOCKS": "1"}, str(tmp_path)), nprocs=world, join=True)
+    d = getattr(pz, model)()
+    hd = {"rw1d": H.model_rw1d, "stt": H.model_stt}[model]()
+    obs, _ = H.gen_obs(hd, T)
+    zs = pz.zparticles(n_global, d, seed=seed)
+    posts = [zs.step(y) for y in obs]
+    xs = np.concatenate([np.load(tmp_path / f"x_{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(xs.view(np.uint32), zs.read_state().view(np.uint32))
+    s0 = np.load(tmp_path / "s_0.npy")
+    assert [int(v) for v in s0[:, 0]] == [p.total_weight for p in posts]
+    assert s0[:, 2].min() >= 0 and s0[:, 2].max() > 256      # migration counts, some beyond one block: the margin did overflow
+
+
+@pytest.mark.gpu
+def test_multi_device_margin_overflow_falls_back_to_remote_reads(pz, monkeypatch):
+    """The same through pz_filter_create_multi (one process), on a stream with outliers that unbalances the ranks."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("PZ_HALO_BLOCKS", "1")
+    hd = H.model_mtt_track()
+    T = 30
+    obs, _ = H.gen_obs(hd, T)
+    obs = obs.copy(); obs[5] += 6.0; obs[17] -= 9.0
+    world = 2 if ndev < 4 else 4
+    n = world * 256 * 300
+    one = pz.zparticles(n, pz.mtt_track(), seed=5)
+    many = pz.zparticles_multi(n, pz.mtt_track(), list(range(world)), seed=5)
+    mig = 0
+    for t in range(T):
+        pa, pb = one.step(obs[t]), many.step(obs[t])
+        assert pa.total_weight == pb.total_weight and pb.n_migrated >= 0, t
+        mig = max(mig, pb.n_migrated)
+        assert np.array_equal(one.read_state().view(np.uint32), many.read_state().view(np.uint32)), t
+    assert mig > 256 * world
+    one.close(); many.close()
 
 
 @pytest.mark.gpu
