@@ -297,7 +297,7 @@ struct pz_filter {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaStream_t push_stream = nullptr;                 // sharded, peer memory: pf_halo_push runs beside the scan
+  cudaStream_t push_stream = nullptr;                 // (unused since the margin push moved into the scan kernel)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaGraphExec_t sgraph[2] = {nullptr, nullptr};  // sharded: one captured step (kernels + NCCL) per buffer parity
@@ -440,7 +440,7 @@ void free_filter(pz_filter* f) {
   if (f->shard_timing) {
     shard_timing_collect(f);
     if (f->tcount)
-      fprintf(stderr, "[pz shard timing] rank %d of %d, %lld steps: step kernel %.1f us, scan %.1f us, plan + prefix margins %.1f us, join + partition %.1f us (pf_halo_push runs beside scan and plan)\n",
+      fprintf(stderr, "[pz shard timing] rank %d of %d, %lld steps: step kernels %.1f us, scan + margin push %.1f us, (unused) %.1f us, plan + partition %.1f us\n",
               f->a.rank, f->a.world, (long long)f->tcount, 1e3 * f->tacc[0] / f->tcount, 1e3 * f->tacc[1] / f->tcount,
               1e3 * f->tacc[2] / f->tcount, 1e3 * f->tacc[3] / f->tcount);
     for (auto& e : f->tev) if (e) cudaEventDestroy(e);
@@ -556,14 +556,9 @@ int sharded_advance(pz_filter* f, int delta, int* launches) {
   const int which = (int)((f->t + (uint32_t)delta) & 1u);  // buffer of the population just produced
   if (a.p2p) {  // peer-memory exchange inside the kernels: no collective call at all
     const bool tm = f->shard_timing && delta;
-    // fork: the X / Q / eb margins travel to the neighbours while this rank scans
-    PZ_CUDA(cudaEventRecord(f->ev_fork, s));
-    PZ_CUDA(cudaStreamWaitEvent(f->push_stream, f->ev_fork, 0));
-    *launches += launch_halo_push(a, delta, f->push_stream);
-    PZ_CUDA(cudaEventRecord(f->ev_join, f->push_stream));
+    // the X / Q / eb margins travel to the neighbours while this rank scans: extra CTAs of the scan kernel push them
     *launches += launch_scan_only(a, delta, s);
     if (tm) { cudaEventRecord(f->tev[2], s); cudaEventRecord(f->tev[3], s); }
-    PZ_CUDA(cudaStreamWaitEvent(s, f->ev_join, 0));  // join (pf_partition_sharded advances ctl->t, which pf_halo_push reads)
     *launches += launch_partition_sharded(a, fused_tile_out(a.model.nx, a.f64), delta, s);
     if (tm) { cudaEventRecord(f->tev[4], s); f->tpending = true; }
     PZ_CUDA(cudaGetLastError());

@@ -292,6 +292,66 @@ __global__ void __launch_bounds__(kThreads) pf_init(StepArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr u64 kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
 
+__device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, int64_t gid, int64_t gsz) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (int64_t i = gid; i < n16; i += gsz) d[i] = s[i];
+}
+
+// Peer-memory exchange: the X / Q / eb margins of the population just produced go straight into the
+// neighbours' halo regions (their arrays have our layout).  Independent of the scan, so extra CTAs of
+// pf_scan_blocks do it beside the scan (no forked stream, no join: the step stays a linear chain of launches);
+// the last of them to finish raises the neighbours' flags.
+struct HaloPushArgs {
+  const CtlDev* ctl;
+  const ShardP2P* p2p;
+  const void* X[2];
+  int32_t esz;  // bytes per state scalar
+  const uint16_t* Q[2];
+  const int32_t* eb[2];
+  int64_t nblk, ld, margin;
+  int32_t rank, world, nx, delta;
+};
+__device__ __forceinline__ void halo_push_body(const HaloPushArgs& p, int cta, int ncta) {
+  const int tid = threadIdx.x;
+  PZ_STAMP(cta == 0 && tid == 0, 12);
+  const uint32_t epoch = p.ctl->t + (uint32_t)p.delta + 1u;
+  const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
+  const int64_t gid = (int64_t)cta * kThreads + tid, gsz = (int64_t)ncta * kThreads;
+  const int64_t m = p.margin, nb = p.nblk;
+  const size_t es = (size_t)p.esz;
+  const char* xmine = reinterpret_cast<const char*>(p.X[which]);
+  if (p.rank > 0) {  // my first m blocks: the RIGHT halo of rank-1
+    char* xn = reinterpret_cast<char*>(p.p2p->Xn[0][which]);
+    for (int d = 0; d < p.nx; ++d)
+      copy16(xn + ((size_t)d * p.ld + nb * kBlk) * es, xmine + (size_t)d * p.ld * es, m * kBlk * p.esz / 16, gid, gsz);
+    copy16(p.p2p->Qn[0][which] + nb * kBlk, p.Q[which], m * kBlk / 8, gid, gsz);
+    for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[0][which][nb + i] = p.eb[which][i];
+  }
+  if (p.rank + 1 < p.world) {  // my last m blocks: the LEFT halo of rank+1
+    char* xn = reinterpret_cast<char*>(p.p2p->Xn[1][which]);
+    for (int d = 0; d < p.nx; ++d)
+      copy16(xn + ((ptrdiff_t)d * p.ld - m * kBlk) * (ptrdiff_t)es, xmine + ((size_t)d * p.ld + (nb - m) * kBlk) * es, m * kBlk * p.esz / 16, gid, gsz);
+    copy16(p.p2p->Qn[1][which] - m * kBlk, p.Q[which] + (nb - m) * kBlk, m * kBlk / 8, gid, gsz);
+    for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[1][which][i - m] = p.eb[which][nb - m + i];
+  }
+  // the CTA barrier orders every thread's peer stores before thread 0's fence, and a fence is cumulative: one
+  // system-scope fence per CTA (75 000 of them, one per thread, cost ~10 us of the step)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    Mailbox* mine = p.p2p->mbox[p.rank];
+    if (atomicAdd(&mine->push_done, 1ull) == (unsigned long long)ncta - 1ull) {
+      __threadfence_system();
+      mine->push_done = 0ull;
+      PZ_STAMP(true, 13);
+      if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->halo_flag[1], (unsigned long long)epoch);
+      if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->halo_flag[0], (unsigned long long)epoch);
+    }
+  }
+}
+
+
 struct ScanArgs {
   const int32_t* eb0;  // block exponents of buffer 0 / 1; the population scanned is (ctl->t + delta) & 1
   const int32_t* eb1;
@@ -321,6 +381,8 @@ struct ScanArgs {
   const ShardP2P* p2p;  // sharded: exchange the block exponent through peer memory (nullptr: NCCL did it)
   int32_t f64;
   unsigned long long wait_ticks;
+  HaloPushArgs push;   // sharded over peer memory: CTAs [nscan, nscan + npush) push the margins
+  int32_t npush;
 };
 
 __device__ void finalize_plan(PlanDev* pl, u64 total, int64_t n_out_global, uint32_t U) {
@@ -373,6 +435,10 @@ __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
   __shared__ double s_tot[kMaxRec];
   __shared__ double s_grp[kThreads / 16][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((int)blockIdx.x >= s.nscan) {   // a margin-push CTA (uniform per CTA)
+    halo_push_body(s.push, (int)blockIdx.x - s.nscan, s.npush);
+    return;
+  }
   if (tid == 0) s_tile = atomicAdd(&s.ctl->scan_counter, 1u);
   int32_t emax = s.ctl->emax_acc;            // in flight together with the tile-id atomic
   const uint32_t t_pop = s.ctl->t + (uint32_t)s.delta;
@@ -1093,11 +1159,11 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
 }
 
 // NT threads per CTA (NW warps): 256 by default; PZ_NT1 = 128 runs the NX = 1 kernel with half-size CTAs
-// REMOTE: the fallback of a sharded filter for a resample whose ancestors reach beyond the halo margins (verdict
-// plan->shard_overflow == 1, the same on every rank): a small persistent grid loops over the tiles, tile_start
-// holds GLOBAL block indices and the input side reads every block from its owner.  The regular kernel exits at
-// once in that case, the remote one in every other.
-template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB, bool REMOTE = false>
+// Sharded filters: when the previous plan found that the ancestors of some rank reach beyond the halo margins
+// (plan->shard_overflow == 1, the same verdict on every rank) the step takes the remote-read input side:
+// tile_start holds GLOBAL block indices and every block is read from its owner over NVLink.  A uniform branch
+// of the same kernel (no extra launch on the common path).
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__ TileArgs ta) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
@@ -1111,23 +1177,24 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   const int cur = t & 1, nxt = cur ^ 1;
   const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[cur]);
   const PlanDev* pl = a.plan;
+  bool remote = false;
   if constexpr (MODE == 0) {
     if (a.p2p != nullptr) {
       const int32_t ov = pl->shard_overflow;
-      if (REMOTE ? ov != 1 : ov != 0) return;
+      if (ov == 2) return;   // a peer never answered: the error is already reported, nothing sane to compute
+      remote = ov == 1;
+      if (remote) {
+        // every rank's boundary positions of this epoch must be complete before any block is read
+        if (tid < a.world) {
+          const Mailbox* mine = a.p2p->mbox[a.rank];
+          const unsigned long long epoch = (unsigned long long)(t + 1u);
+          wait_sys(&mine->xb_done[tid], [epoch](unsigned long long x) { return x >= epoch; }, &a.ctl->comm_error, a.wait_ticks, 0x20u);
+        }
+        __syncthreads();
+      }
     }
   }
-  if constexpr (REMOTE) {
-    // every rank's boundary positions of this epoch must be complete before any block is read
-    if (tid < a.world) {
-      const Mailbox* mine = a.p2p->mbox[a.rank];
-      const unsigned long long epoch = (unsigned long long)(t + 1u);
-      wait_sys(&mine->xb_done[tid], [epoch](unsigned long long x) { return x >= epoch; }, &a.ctl->comm_error, a.wait_ticks, 0x20u);
-    }
-    __syncthreads();
-  }
-  int tile = blockIdx.x;
-  do {   // one tile per CTA (REMOTE: a persistent grid strides over the tiles)
+  const int tile = blockIdx.x;
   const int64_t j0l = (int64_t)tile * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
   const uint32_t j0 = (uint32_t)(a.slot_base + j0l);
@@ -1141,7 +1208,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   if constexpr (MODE == 0) {
     // the first input block's weights: in flight during the prologue
     const int64_t b_first = (int64_t)a.tile_start[tile];
-    if (!REMOTE && a.p2p != nullptr) {
+    if (!remote && a.p2p != nullptr) {
       // sharded over peer memory: a boundary tile (its input blocks reach into a halo) waits here for the
       // neighbour's margins of this epoch (state / weights / exponents from pf_halo_push, boundary positions from
       // pf_partition_sharded); interior tiles -- nearly all -- start at once.  The flags hold the LATEST epoch: a
@@ -1164,7 +1231,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     StateSource<NX, T> src;
     src.x = xin; src.ld = a.ld;
     Quad<T> pa{}, pb{};
-    if (!REMOTE && b_first + warp < a.b_hi) {
+    if (!remote && b_first + warp < a.b_hi) {
       first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
       // fp32 payloads of the first block are fetched here too; for doubles the 16 extra registers across the
       // barrier cost more than the exposed latency (measured: 0.568 ms hoisted vs 0.544 ms not, N = 10^8)
@@ -1178,7 +1245,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     uint4* sz = reinterpret_cast<uint4*>(s_par);
     for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
-    if constexpr (REMOTE) {
+    if (remote) {
       resample_tile_remote<(NX != 1), NW>(src, s_par, TO, a.p2p, cur, a.nblk, a.world, b_first, pl->emax, pl->h0, pl->Mq, j0, nslots,
                                           lane, warp);
     } else {
@@ -1245,8 +1312,6 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     a.rec[(size_t)tile * kMaxRec + tid] = x;
   }
   if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
-  if constexpr (REMOTE) __syncthreads();   // the staging buffer and the reduction scratch are reused by the next tile
-  } while (REMOTE && (tile += (int)gridDim.x) < a.ntiles_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1416,62 +1481,6 @@ struct ShardPlanArgs {
   int32_t f64;
   unsigned long long wait_ticks;
 };
-
-__device__ __forceinline__ void copy16(void* dst, const void* src, int64_t n16, int64_t gid, int64_t gsz) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  for (int64_t i = gid; i < n16; i += gsz) d[i] = s[i];
-}
-
-// Peer-memory exchange: the X / Q / eb margins of the population just produced go straight into the
-// neighbours' halo regions (their arrays have our layout).  Independent of the scan, so the host forks
-// this kernel beside pf_scan_blocks / pf_plan_sharded; the last CTA to finish raises the neighbours' flags.
-struct HaloPushArgs {
-  const CtlDev* ctl;
-  const ShardP2P* p2p;
-  const void* X[2];
-  int32_t esz;  // bytes per state scalar
-  const uint16_t* Q[2];
-  const int32_t* eb[2];
-  int64_t nblk, ld, margin;
-  int32_t rank, world, nx, delta;
-};
-__global__ void __launch_bounds__(kThreads) pf_halo_push(const HaloPushArgs p) {
-  const int tid = threadIdx.x;
-  PZ_STAMP(blockIdx.x == 0 && tid == 0, 12);
-  const uint32_t epoch = p.ctl->t + (uint32_t)p.delta + 1u;
-  const int which = (int)((p.ctl->t + (uint32_t)p.delta) & 1u);
-  const int64_t gid = (int64_t)blockIdx.x * kThreads + tid, gsz = (int64_t)gridDim.x * kThreads;
-  const int64_t m = p.margin, nb = p.nblk;
-  const size_t es = (size_t)p.esz;
-  const char* xmine = reinterpret_cast<const char*>(p.X[which]);
-  if (p.rank > 0) {  // my first m blocks: the RIGHT halo of rank-1
-    char* xn = reinterpret_cast<char*>(p.p2p->Xn[0][which]);
-    for (int d = 0; d < p.nx; ++d)
-      copy16(xn + ((size_t)d * p.ld + nb * kBlk) * es, xmine + (size_t)d * p.ld * es, m * kBlk * p.esz / 16, gid, gsz);
-    copy16(p.p2p->Qn[0][which] + nb * kBlk, p.Q[which], m * kBlk / 8, gid, gsz);
-    for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[0][which][nb + i] = p.eb[which][i];
-  }
-  if (p.rank + 1 < p.world) {  // my last m blocks: the LEFT halo of rank+1
-    char* xn = reinterpret_cast<char*>(p.p2p->Xn[1][which]);
-    for (int d = 0; d < p.nx; ++d)
-      copy16(xn + ((ptrdiff_t)d * p.ld - m * kBlk) * (ptrdiff_t)es, xmine + ((size_t)d * p.ld + (nb - m) * kBlk) * es, m * kBlk * p.esz / 16, gid, gsz);
-    copy16(p.p2p->Qn[1][which] - m * kBlk, p.Q[which] + (nb - m) * kBlk, m * kBlk / 8, gid, gsz);
-    for (int64_t i = gid; i < m; i += gsz) p.p2p->ebn[1][which][i - m] = p.eb[which][nb - m + i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {
-    Mailbox* mine = p.p2p->mbox[p.rank];
-    if (atomicAdd(&mine->push_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
-      __threadfence_system();
-      mine->push_done = 0ull;
-      PZ_STAMP(true, 13);
-      if (p.rank > 0) st_sys(&p.p2p->mbox[p.rank - 1]->halo_flag[1], (unsigned long long)epoch);
-      if (p.rank + 1 < p.world) st_sys(&p.p2p->mbox[p.rank + 1]->halo_flag[0], (unsigned long long)epoch);
-    }
-  }
-}
 
 // Every rank evaluates, for EVERY rank q, whether the fixed halo margins (the last `margin` blocks of
 // rank q-1 and the first `margin` blocks of rank q+1) cover the ancestors of q's slots -- from the
@@ -1689,16 +1698,22 @@ __global__ void __launch_bounds__(kThreads) pf_partition_sharded(const PartShard
   const int64_t nb = p.nblk, m = p.margin;
   // ---- boundary positions of my blocks; the margins also go into the neighbours' halos (my boundaries 1..m are
   // the RIGHT halo of rank-1 at its indices nb+1..nb+m; my boundaries nb-m..nb-1 the LEFT halo of rank+1 at -m..-1)
-  for (int64_t b = gid; b <= nb; b += gsz) {
-    const u64 v = total != 0 ? sm.block_pos(base + p.pb[b]) : 0ull;
-    p.xb[b] = v;
-    if (p.rank > 0 && b >= 1 && b <= m) p.p2p->xbn[0][nb + b] = v;
-    if (p.rank + 1 < p.world && b >= nb - m && b < nb) p.p2p->xbn[1][b - nb] = v;
+  // (the first npush CTAs store the margins -- and only they pay a system-scope fence, one per CTA)
+  const int npush = (int)min((int64_t)gridDim.x, (m + kThreads - 1) / kThreads);
+  if ((int)blockIdx.x < npush) {
+    for (int64_t i = gid; i < m; i += (int64_t)npush * kThreads) {
+      if (p.rank > 0) p.p2p->xbn[0][nb + 1 + i] = total != 0 ? sm.block_pos(base + p.pb[1 + i]) : 0ull;
+      if (p.rank + 1 < p.world) p.p2p->xbn[1][i - m] = total != 0 ? sm.block_pos(base + p.pb[nb - m + i]) : 0ull;
+    }
   }
+  for (int64_t b = gid; b <= nb; b += gsz) p.xb[b] = total != 0 ? sm.block_pos(base + p.pb[b]) : 0ull;
   PZ_STAMP(blockIdx.x == 0 && tid == 0, 6);
-  __threadfence_system();
   __syncthreads();
   if (tid == 0) {
+    // "my xb is complete" needs every CTA; the margin flags only the pushing ones.  One counter: every CTA arrives
+    // (device-scope fence: its xb stores are in L2, where the peers' NVLink reads go), the pushing ones after a
+    // system-scope fence; the last arrival raises all flags.
+    if ((int)blockIdx.x < npush) __threadfence_system(); else __threadfence();
     if (atomicAdd(&mine->pbx_done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
       __threadfence_system();
       mine->pbx_done = 0ull;
@@ -1889,6 +1904,15 @@ static ScanArgs make_scan(const StepArgs& a, int delta, bool with_rec) {
   sc.explicit_U = 0; sc.U_value = 0; sc.seed = a.seed; sc.ll_const = a.ll_const; sc.world = a.world;
   sc.rank = a.rank; sc.shard_rec = a.shard_rec; sc.margin = a.margin; sc.p2p = a.p2p;
   sc.f64 = a.f64; sc.wait_ticks = a.wait_ticks;
+  sc.npush = 0;
+  if (a.p2p != nullptr) {
+    const int esz = a.f64 ? 8 : 4;
+    sc.push = HaloPushArgs{a.ctl, a.p2p, {a.X[0], a.X[1]}, esz, {a.Q[0], a.Q[1]}, {a.eb[0], a.eb[1]}, a.nblk, a.ld, a.margin,
+                           a.rank, a.world, a.model.nx, delta};
+    // 16-byte stores per margin and side: nx * m * 16 * esz (X) + m * 32 (Q); two per thread, at most two CTAs per SM beside the scan
+    int grid = cdiv((int64_t)(a.model.nx * 16 * esz + 32) * a.margin, 2 * kThreads);
+    sc.npush = grid < 1 ? 1 : (grid > 296 ? 296 : grid);
+  }
   return sc;
 }
 
@@ -1913,7 +1937,7 @@ int launch_partition_only(const StepArgs& a, int tile_out, cudaStream_t s) { ret
 // Scan + partition of the population in buffer (ctl->t + delta) & 1.  delta = 1 after a step.
 static int scan_partition(const StepArgs& a, int delta, int tile_out, cudaStream_t s) {
   ScanArgs sc = make_scan(a, delta, delta == 1);
-  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  pf_scan_blocks<<<a.nscan + sc.npush, kThreads, 0, s>>>(sc);
   partition(a, tile_out, delta, s);
   return 2;
 }
@@ -1941,19 +1965,6 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
-  if constexpr (MODE == 0) {
-    if (ta.a.p2p != nullptr) {   // sharded over peer memory: the remote-read fallback follows (it exits at once unless the margins overflowed)
-      auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT), true>;
-      static std::atomic<unsigned long long> rattr_done{0};
-      if (!(rattr_done.load(std::memory_order_acquire) & bit)) {
-        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        rattr_done.fetch_or(bit, std::memory_order_release);
-      }
-      const int rgrid = ta.a.ntiles_out < 296 ? ta.a.ntiles_out : 296;
-      rkern<<<rgrid, NT, smem, s>>>(ta);
-      return 2;
-    }
-  }
   return 1;
 }
 
@@ -2002,7 +2013,7 @@ int launch_step_profiled(const StepArgs& a, cudaStream_t s, cudaEvent_t ev[4]) {
   if (dispatch_tile(ta, s) < 0) return -1;
   cudaEventRecord(ev[1], s);
   ScanArgs sc = make_scan(a, 1, true);
-  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  pf_scan_blocks<<<a.nscan + sc.npush, kThreads, 0, s>>>(sc);
   cudaEventRecord(ev[2], s);
   partition(a, fused_tile_out(a.model.nx, a.f64), 1, s);
   cudaEventRecord(ev[3], s);
@@ -2016,24 +2027,13 @@ int launch_tile_only(const StepArgs& a, cudaStream_t s) {
 
 int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s) {
   ScanArgs sc = make_scan(a, delta, delta == 1);
-  pf_scan_blocks<<<a.nscan, kThreads, 0, s>>>(sc);
+  pf_scan_blocks<<<a.nscan + sc.npush, kThreads, 0, s>>>(sc);
   return 1;
 }
 
 #ifdef PZ_DBG_STAMPS
 void dbg_read_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_stamp, sizeof(g_stamp)); }
 #endif
-
-int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s) {
-  const int esz = a.f64 ? 8 : 4;
-  HaloPushArgs p{a.ctl, a.p2p, {a.X[0], a.X[1]}, esz, {a.Q[0], a.Q[1]}, {a.eb[0], a.eb[1]}, a.nblk, a.ld, a.margin,
-                 a.rank, a.world, a.model.nx, delta};
-  // 16-byte stores per margin and side: nx * m * 16 * esz (X) + m * 32 (Q); two per thread, at most two CTAs per SM beside the scan
-  int grid = cdiv((int64_t)(a.model.nx * 16 * esz + 32) * a.margin, 2 * kThreads);
-  grid = grid < 1 ? 1 : (grid > 296 ? 296 : grid);
-  pf_halo_push<<<grid, kThreads, 0, s>>>(p);
-  return 1;
-}
 
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s) {
   ShardPlanArgs p{a.plan, a.ctl, a.shard_rec, a.pb, const_cast<u64*>(a.pbx), a.summ, a.nblk, a.n_global, a.n_local,

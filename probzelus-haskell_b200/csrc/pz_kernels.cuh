@@ -174,7 +174,6 @@ int launch_scan_only(const StepArgs& a, int delta, cudaStream_t s);      // afte
 int launch_plan_sharded(const StepArgs& a, int delta, cudaStream_t s);   // after the all-gather: plan, absolute prefix, summary, margin check
 // peer memory: record all-gather + plan + summary + margin check + boundary positions (own and pushed margins) + merge-path split, one kernel
 int launch_partition_sharded(const StepArgs& a, int tile_out, int delta, cudaStream_t s);
-int launch_halo_push(const StepArgs& a, int delta, cudaStream_t s);      // peer memory: X / Q / eb margins -> the neighbours (independent of the scan)
 int launch_partition_ext(const StepArgs& a, int tile_out, int delta, cudaStream_t s);  // after the halo exchange
 
 // Generic (stored log-weight) path: standalone resampler, ancestor taps, visualiser read.

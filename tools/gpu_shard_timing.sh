@@ -7,7 +7,7 @@ M=${2:-rw1d}
 P=10000000; [ $M = rw1d ] && P=100000000
 for tm in 0 1; do
   if [ $tm = 1 ]; then export PZ_SHARD_TIMING=1; else unset PZ_SHARD_TIMING; fi
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --model $M --particles $P --steps 30 --warmup 3 --no-cpu > gpurun_out/shard_timing_${M}_g${N}_$tm.json 2> gpurun_out/shard_timing_${M}_g${N}_$tm.err; echo "rc=$?"
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --model $M --particles $P --steps 30 --warmup 3 --no-cpu --no-parity --dtype f32 > gpurun_out/shard_timing_${M}_g${N}_$tm.json 2> gpurun_out/shard_timing_${M}_g${N}_$tm.err; echo "rc=$?"
   python - <<PY
 import json
 for l in open('gpurun_out/shard_timing_${M}_g${N}_$tm.json'):
