@@ -698,7 +698,7 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   a.ld = round_up(a.n_local, kPad);
   f->mtt_params.resize(mtt_params_size());
   mtt_fill_params(model, f->mtt_params.data());
-  const size_t sbytes = (size_t)a.ld * mtt_words_per_particle() * sizeof(uint32_t);   // [field][ld]
+  const size_t sbytes = (size_t)a.n_local * mtt_words_per_particle() * sizeof(uint32_t);
 #define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
@@ -749,7 +749,7 @@ int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summar
   PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
   GenericArgs g = mtt_generic(f);
   int n = launch_generic_ancestors(g, f->stream);
-  n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], a.ld, f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
+  n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
                        f->mtt_overflow, f->mtt_part, a.n_local, n_obs, a.seed, f->stream);
   // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
   const double ll_const = -(f->desc.mtt.clutter_lambda + f->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
@@ -1882,7 +1882,7 @@ int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int3
   const int W = mtt_words_per_particle();
   uint32_t* d_out = nullptr;
   PZ_CUDA(cudaMalloc(&d_out, (size_t)n_sel * W * sizeof(uint32_t)));
-  launch_mtt_gather(f->mtt_s[f->t & 1], a.ld, f->g.anc, stride, n_sel, d_out, f->stream);
+  launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream);
   std::vector<uint32_t> h((size_t)n_sel * W);
   cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);

@@ -1159,11 +1159,12 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
 }
 
 // NT threads per CTA (NW warps): 256 by default; PZ_NT1 = 128 runs the NX = 1 kernel with half-size CTAs
-// Sharded filters: when the previous plan found that the ancestors of some rank reach beyond the halo margins
-// (plan->shard_overflow == 1, the same verdict on every rank) the step takes the remote-read input side:
-// tile_start holds GLOBAL block indices and every block is read from its owner over NVLink.  A uniform branch
-// of the same kernel (no extra launch on the common path).
-template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB>
+// REMOTE: the fallback of a sharded filter for a resample whose ancestors reach beyond the halo margins (verdict
+// plan->shard_overflow == 1, the same on every rank): tile_start holds GLOBAL block indices and the input side reads
+// every block from its owner over NVLink.  A separate instantiation launched after the regular one on a small
+// persistent grid: the regular kernel exits at once when the margins overflowed, the remote one in every other
+// case (~3 us per step).  (As a uniform runtime branch of ONE kernel it cost the register-bound wide models 6-11 %.)
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB, bool REMOTE = false>
 __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__ TileArgs ta) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
@@ -1177,24 +1178,24 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   const int cur = t & 1, nxt = cur ^ 1;
   const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[cur]);
   const PlanDev* pl = a.plan;
-  bool remote = false;
+  constexpr bool remote = REMOTE;
   if constexpr (MODE == 0) {
     if (a.p2p != nullptr) {
       const int32_t ov = pl->shard_overflow;
-      if (ov == 2) return;   // a peer never answered: the error is already reported, nothing sane to compute
-      remote = ov == 1;
-      if (remote) {
-        // every rank's boundary positions of this epoch must be complete before any block is read
-        if (tid < a.world) {
-          const Mailbox* mine = a.p2p->mbox[a.rank];
-          const unsigned long long epoch = (unsigned long long)(t + 1u);
-          wait_sys(&mine->xb_done[tid], [epoch](unsigned long long x) { return x >= epoch; }, &a.ctl->comm_error, a.wait_ticks, 0x20u);
-        }
-        __syncthreads();
-      }
+      if (REMOTE ? ov != 1 : ov != 0) return;   // (2: a peer never answered -- the error is reported, neither kernel runs)
     }
   }
-  const int tile = blockIdx.x;
+  if constexpr (REMOTE) {
+    // every rank's boundary positions of this epoch must be complete before any block is read
+    if (tid < a.world) {
+      const Mailbox* mine = a.p2p->mbox[a.rank];
+      const unsigned long long epoch = (unsigned long long)(t + 1u);
+      wait_sys(&mine->xb_done[tid], [epoch](unsigned long long x) { return x >= epoch; }, &a.ctl->comm_error, a.wait_ticks, 0x20u);
+    }
+    __syncthreads();
+  }
+  int tile = blockIdx.x;
+  do {   // one tile per CTA (REMOTE: a persistent grid strides over the tiles)
   const int64_t j0l = (int64_t)tile * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
   const uint32_t j0 = (uint32_t)(a.slot_base + j0l);
@@ -1245,7 +1246,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     uint4* sz = reinterpret_cast<uint4*>(s_par);
     for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
-    if (remote) {
+    if constexpr (REMOTE) {
       resample_tile_remote<(NX != 1), NW>(src, s_par, TO, a.p2p, cur, a.nblk, a.world, b_first, pl->emax, pl->h0, pl->Mq, j0, nslots,
                                           lane, warp);
     } else {
@@ -1312,6 +1313,8 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     a.rec[(size_t)tile * kMaxRec + tid] = x;
   }
   if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
+  if constexpr (REMOTE) __syncthreads();   // the staging buffer and the reduction scratch are reused by the next tile
+  } while (REMOTE && (tile += (int)gridDim.x) < a.ntiles_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1965,6 +1968,19 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
+  if constexpr (MODE == 0) {
+    if (ta.a.p2p != nullptr) {   // sharded over peer memory: the remote-read fallback follows (it exits at once unless the margins overflowed)
+      auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT), true>;
+      static std::atomic<unsigned long long> rattr_done{0};
+      if (!(rattr_done.load(std::memory_order_acquire) & bit)) {
+        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        rattr_done.fetch_or(bit, std::memory_order_release);
+      }
+      const int rgrid = ta.a.ntiles_out < 148 ? ta.a.ntiles_out : 148;
+      rkern<<<rgrid, NT, smem, s>>>(ta);
+      return 2;
+    }
+  }
   return 1;
 }
 

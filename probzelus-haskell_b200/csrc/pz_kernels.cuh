@@ -220,11 +220,11 @@ void mtt_fill_params(const pz_model_desc* d, void* out_mttdev);
 void dbg_read_stamps(unsigned long long* out);  // debug build: %globaltimer stamps of the sharded exchange phases
 #endif
 int mtt_step_ctas(int64_t n);  // CTAs of mtt_step = rows of its per-CTA summary partials (5 doubles each)
-int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, int64_t ld, const int32_t* anc, float* lw, const float* obs,
+int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
                     cudaStream_t s);
 int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDev* ctl, pz_step_summary* summ, double ll_const,
                        const unsigned long long* overflow, cudaStream_t s);
-int launch_mtt_gather(const uint32_t* sdata, int64_t ld, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
+int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
 
 }  // namespace pz

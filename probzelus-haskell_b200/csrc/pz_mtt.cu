@@ -11,15 +11,13 @@
 //   the reference's terms one by one and checks the reduction on every call);
 //   updateWithAssocs (:75-87) -> Kalman update, coasting Bernoulli((1-pd)/(1-ps pd)), births.
 //
-// Mapping: one thread per particle (see mtt_step).  A particle is a record of 65 16-byte quads (1 header quad +
-// 16 tracks x 4 quads: id + mean + covariance triangle) stored as an ARRAY OF STRUCTURES OF ARRAYS over groups of
-// 32 particles, S[group][quad][lane]: thread j reads quad u of its parent p at S[((p / 32) * 65 + u) * 32 + p % 32]
-// with one 128-bit load -- the ancestors of a warp are sorted and span a few consecutive groups, so a warp load
-// falls into one or two 512-byte runs -- and writes its own quads as full 512-byte runs; the quads of a group are
-// contiguous (33 KB), so consecutive accesses stay in the same DRAM pages.  (Measured, N = 10^6, 8 targets: one
-// contiguous 1040-byte record per particle -- 32 different sectors per warp load -- 0.42 ms per step; plain
-// S[field][particle] with scalar loads -- every field of a warp in a different DRAM page -- 0.53 ms; S[group][field][lane]
-// with scalar loads 0.51 ms.)  Only the quads of live tracks move.
+// Mapping: one thread per particle (see mtt_step).  A particle is a 1040-byte record (16-byte
+// header + 16 x 64-byte track records) read through the stored ancestor index; only the live
+// track records move (every 64-byte record is two full 32-byte sectors).  Array-of-structures on purpose:
+// the gather is by ANCESTOR, and the 32 parents of a warp are whichever particles survived, so a layout that
+// interleaves neighbouring particles fetches lines it uses half of.  Measured at N = 10^6, 8 targets: this
+// layout 0.42 ms per step; S[field][particle] with scalar loads 0.53 ms; S[group of 32][field][lane] 0.51 ms;
+// S[group of 32][16-byte quad][lane] with 128-bit loads 0.45 ms.
 //
 // Unlike the linear-Gaussian kernels this translation unit is NOT bound by the bit-exact fp32
 // spec (parity for MTT is statistical): it uses fast intrinsics and fmad.
@@ -118,9 +116,8 @@ __device__ __forceinline__ void update(Track& t, float z0, float z1, float r) {
 constexpr int kMttWords = 4 + 16 * 16;  // 32-bit words per particle record
 
 struct MttArgs {
-  const uint32_t* sin;   // [ld / 32][65 quads][32 lanes] of uint4
+  const uint32_t* sin;   // [N][kMttWords]
   uint32_t* sout;
-  int64_t ld;            // allocated particles (a multiple of 32)
   const int32_t* anc;    // [N]
   float* lw;             // [N]
   const float* obs;      // [m_max][2]
@@ -133,16 +130,9 @@ struct MttArgs {
   MttDev p;
 };
 
-// track k of particle `par`: fields 4 + 16 k + {0: id, 1..4: mean, 5..14: covariance triangle}
-constexpr int kMttGroup = 32;                              // particles per group of the AoSoA layout
-constexpr int kMttQuads = 65;                              // 16-byte quads per particle record
-__device__ __forceinline__ size_t mtt_quad(int64_t par, int u) {   // uint4 index of quad u of particle par
-  return ((size_t)(par >> 5) * kMttQuads + (size_t)u) * kMttGroup + (size_t)(par & 31);
-}
-// track k of particle `par`: quads 1 + 4 k + {0..3} = (id, m0, m1, m2 | m3, c0, c1, c2 | c3..c6 | c7, c8, c9, -)
-__device__ __forceinline__ void load_track(const uint32_t* __restrict__ s, int64_t par, int k, Track& tr) {
-  const uint4* __restrict__ rp = reinterpret_cast<const uint4*>(s) + mtt_quad(par, 1 + 4 * k);
-  const uint4 w0 = rp[0], w1 = rp[kMttGroup], w2 = rp[2 * kMttGroup], w3 = rp[3 * kMttGroup];
+__device__ __forceinline__ void load_track(const uint32_t* __restrict__ rec, Track& tr) {
+  const uint4* rp = reinterpret_cast<const uint4*>(rec);
+  const uint4 w0 = rp[0], w1 = rp[1], w2 = rp[2], w3 = rp[3];
   tr.id = (int)w0.x;
   tr.m[0] = __uint_as_float(w0.y); tr.m[1] = __uint_as_float(w0.z); tr.m[2] = __uint_as_float(w0.w);
   tr.m[3] = __uint_as_float(w1.x);
@@ -151,12 +141,12 @@ __device__ __forceinline__ void load_track(const uint32_t* __restrict__ s, int64
   tr.c[6] = __uint_as_float(w2.w); tr.c[7] = __uint_as_float(w3.x); tr.c[8] = __uint_as_float(w3.y);
   tr.c[9] = __uint_as_float(w3.z);
 }
-__device__ __forceinline__ void store_track(uint32_t* __restrict__ s, int64_t j, int k, const Track& x) {
-  uint4* __restrict__ wp = reinterpret_cast<uint4*>(s) + mtt_quad(j, 1 + 4 * k);
+__device__ __forceinline__ void store_track(uint32_t* __restrict__ rec, const Track& x) {
+  uint4* wp = reinterpret_cast<uint4*>(rec);
   wp[0] = make_uint4((uint32_t)x.id, __float_as_uint(x.m[0]), __float_as_uint(x.m[1]), __float_as_uint(x.m[2]));
-  wp[kMttGroup] = make_uint4(__float_as_uint(x.m[3]), __float_as_uint(x.c[0]), __float_as_uint(x.c[1]), __float_as_uint(x.c[2]));
-  wp[2 * kMttGroup] = make_uint4(__float_as_uint(x.c[3]), __float_as_uint(x.c[4]), __float_as_uint(x.c[5]), __float_as_uint(x.c[6]));
-  wp[3 * kMttGroup] = make_uint4(__float_as_uint(x.c[7]), __float_as_uint(x.c[8]), __float_as_uint(x.c[9]), 0u);
+  wp[1] = make_uint4(__float_as_uint(x.m[3]), __float_as_uint(x.c[0]), __float_as_uint(x.c[1]), __float_as_uint(x.c[2]));
+  wp[2] = make_uint4(__float_as_uint(x.c[3]), __float_as_uint(x.c[4]), __float_as_uint(x.c[5]), __float_as_uint(x.c[6]));
+  wp[3] = make_uint4(__float_as_uint(x.c[7]), __float_as_uint(x.c[8]), __float_as_uint(x.c[9]), 0u);
 }
 
 // One THREAD per particle (the track count of a particle is small and nearly equal across the
@@ -184,9 +174,9 @@ struct DerLocal {
 };
 
 template <class Der>
-__device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __restrict__ sin, int64_t par, int k, const Der& der) {
+__device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __restrict__ src, int k, const Der& der) {
   Track tr;
-  load_track(sin, par, k, tr);
+  load_track(src + 4 + 16 * k, tr);
   predict(p, tr);
   const float sa = tr.c[0] + p.r, sb = tr.c[1], sd = tr.c[4] + p.r;
   const float det = sa * sd - sb * sb, idet = 1.0f / det;
@@ -237,15 +227,17 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   const DerLocal dl{loc};
   const uint32_t t = a.ctl->t;
   const int64_t par = a.anc[j];
-  const uint4 hdr = reinterpret_cast<const uint4*>(a.sin)[mtt_quad(par, 0)];   // header quad: track count, next track id, births dropped
+  const uint32_t* __restrict__ src = a.sin + (size_t)par * kMttWords;
+  uint32_t* __restrict__ dst = a.sout + (size_t)j * kMttWords;
+  const uint4 hdr = *reinterpret_cast<const uint4*>(src);
   const int cnt = (int)hdr.x;
   const int cnt_fast = cnt < kMttFast ? cnt : kMttFast;
   const int next_id = (int)hdr.y;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
 
   // ---- pass A: predictive density of a measurement of every track: N(z; H m, H P H^T + r I)
-  for (int k = 0; k < cnt_fast; ++k) mtt_derive(a.p, a.sin, par, k, ds);
-  for (int k = kMttFast; k < cnt; ++k) mtt_derive(a.p, a.sin, par, k, dl);
+  for (int k = 0; k < cnt_fast; ++k) mtt_derive(a.p, src, k, ds);
+  for (int k = kMttFast; k < cnt; ++k) mtt_derive(a.p, src, k, dl);
 
   // ---- pass B: association proposal; uniforms: detection o takes word o & 3 of Philox call o >> 2
   uint32_t assigned = 0;   // bit k: track k has a detection
@@ -294,13 +286,13 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     const bool det = (assigned >> k) & 1u;
     if (!det && !(u01(word) < a.p.p_coast)) continue;  // undetected and not coasting: the track dies
     Track tr;
-    load_track(a.sin, par, k, tr);
+    load_track(src + 4 + 16 * k, tr);
     predict(a.p, tr);
     if (det) {
       const int o = (int)((k < 12 ? obs_lo >> (5 * k) : obs_hi >> (5 * (k - 12))) & 31ull);
       update(tr, s_z[o][0], s_z[o][1], a.p.r);
     }
-    store_track(a.sout, j, n_surv, tr);
+    store_track(dst + 4 + 16 * n_surv, tr);
     ++n_surv;
   }
   // births: the i-th new-track detection (newTrackD conditioned on it)
@@ -319,9 +311,9 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     for (int q = 0; q < 10; ++q) nt.c[q] = 0.f;
     nt.c[0] = a.p.bp; nt.c[4] = a.p.bp; nt.c[7] = a.p.bv; nt.c[9] = a.p.bv;
     update(nt, s_z[o][0], s_z[o][1], a.p.r);
-    store_track(a.sout, j, n_surv + i, nt);
+    store_track(dst + 4 + 16 * (n_surv + i), nt);
   }
-  reinterpret_cast<uint4*>(a.sout)[mtt_quad(j, 0)] = make_uint4((uint32_t)(n_surv + n_born), (uint32_t)(next_id + n_new), n_new > room ? 1u : 0u, 0u);
+  *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)(n_surv + n_born), (uint32_t)(next_id + n_new), n_new > room ? 1u : 0u, 0u);
   a.lw[j] = lw;
   if (n_new > room) atomicAdd(a.overflow, (unsigned long long)(n_new - room));
   out_lw = sanitize_lw(lw);
@@ -420,19 +412,13 @@ __global__ void __launch_bounds__(kFinalThreads) mtt_summary_final(PlanDev* pl, 
   o->total_weight = pl->total;
 }
 
-// thinned read of the resampled population: every stride-th output slot's parent record, assembled as one
-// contiguous 260-word record per selected particle (the host unpacks it)
-__global__ void mtt_gather_thin(const uint32_t* __restrict__ s, int64_t ld, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
+// thinned read of the resampled population: every stride-th output slot's parent record
+__global__ void mtt_gather_thin(const uint32_t* __restrict__ s, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
                                 uint32_t* __restrict__ out) {
   const int64_t sel = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (sel >= n_sel) return;
   const int64_t p = anc[sel * stride];
-  const uint4* __restrict__ sq = reinterpret_cast<const uint4*>(s);
-  const int cnt = (int)sq[mtt_quad(p, 0)].x;
-  for (int u = threadIdx.x & 31; u < kMttQuads; u += 32) {
-    const bool live = u == 0 || (u - 1) / 4 < cnt;    // quads of dead track slots hold stale data
-    reinterpret_cast<uint4*>(out)[(size_t)sel * kMttQuads + u] = live ? sq[mtt_quad(p, u)] : make_uint4(0u, 0u, 0u, 0u);
-  }
+  for (int w = threadIdx.x & 31; w < kMttWords; w += 32) out[(size_t)sel * kMttWords + w] = s[(size_t)p * kMttWords + w];
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -466,11 +452,11 @@ size_t mtt_params_size() { return sizeof(MttDev); }
 
 int mtt_step_ctas(int64_t n) { return (int)((n + kMttThreads - 1) / kMttThreads); }
 
-int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, int64_t ld, const int32_t* anc, float* lw, const float* obs,
+int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
                     cudaStream_t s) {
   MttArgs a;
-  a.sin = sin; a.sout = sout; a.ld = ld; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
+  a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
   a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
   const size_t smem = (size_t)kMttDerived * kMttFast * kMttThreads * sizeof(float);  // 28 KB
@@ -492,9 +478,9 @@ int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDe
   return 1;
 }
 
-int launch_mtt_gather(const uint32_t* sdata, int64_t ld, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
+int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
   const int per_cta = kThreads / 32;
-  mtt_gather_thin<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sdata, ld, anc, stride, n_sel, out);
+  mtt_gather_thin<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sdata, anc, stride, n_sel, out);
   return 1;
 }
 

@@ -113,6 +113,30 @@ def test_filter_trajectory_bit_exact(pz, model, n, f64):
 
 
 @pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
+def test_filter_bit_exact_at_16m_particles(pz, f64):
+    """Bit parity at N = 2^24 (the oracle's step is an OpenMP loop: a few seconds): state, log-weights, ancestors,
+    totals -- the same bar as the small sizes, two thousand tiles instead of a handful."""
+    n = 1 << 24
+    hd = H.model_rw1d(f64=f64)
+    obs, _ = H.gen_obs(hd, 3)
+    zs = pz.zparticles(n, pz.rw1d(f64=f64), seed=2024)
+    orc = H.OracleFilter(hd, n, 2024)
+    for t in range(3):
+        anc_gpu = zs.read_ancestors() if t == 2 else None
+        post = zs.step(obs[t])
+        rc, s = orc.step(obs[t])
+        assert rc == 0
+        x_ref, lw_ref, anc_ref = orc.state()
+        if anc_gpu is not None:
+            assert np.array_equal(anc_gpu, anc_ref)
+        assert np.array_equal(bits(zs.read_state()), bits(x_ref)), t
+        assert post.total_weight == s.total_weight and post.e_max == s.e_max
+        assert abs(post.mean[0] - s.mean[0]) < 2e-6 and abs(post.ess - s.ess) < 1e-5 * s.ess
+    assert np.array_equal(bits(zs.read_logw()), bits(lw_ref))
+    zs.close(); orc.close()
+
+
+@pytest.mark.parametrize("f64", [False, True], ids=["f32", "f64"])
 @pytest.mark.parametrize("model", ["rw1d", "lg42", "lg63"])
 def test_filter_outlier_observations_bit_exact(pz, model, f64):
     """Observations far in the tails collapse the weights onto a handful of particles: runs of thousands
@@ -229,11 +253,11 @@ def test_quantised_weights_carry_no_visible_bias_at_large_n(pz):
 
 
 def test_long_stream_stays_on_the_kalman_posterior(pz):
-    """BASELINE configs[2] shape: the 2-D position/velocity tracker over 10^4 steps (N = 10^6 here).  The
+    """BASELINE configs[2] at full size: the 2-D position/velocity tracker, N = 10^7 particles over 10^4 steps.  The
     filter neither degenerates nor drifts: over the last 2000 steps the posterior mean tracks the exact
     Kalman mean to Monte Carlo accuracy and the log-evidence per step matches."""
     hd = H.model_mtt_track()
-    T, n = 10000, 1000000
+    T, n = 10000, 10000000
     obs, _ = H.gen_obs(hd, T)
     km, kc, kl = H.kalman(hd, obs)
     zs = pz.zparticles(n, pz.mtt_track(), seed=2026)
@@ -244,7 +268,7 @@ def test_long_stream_stays_on_the_kalman_posterior(pz):
     ess = np.array([p.ess for p in posts[-2000:]])
     kvar = np.array([np.diag(c) for c in kc[-2000:]])
     err = (mean - km[-2000:]) / np.sqrt(kvar)
-    assert np.sqrt(np.mean(err ** 2)) < 0.02 and np.max(np.abs(err)) < 0.15   # ~ 1/sqrt(ESS) with path degeneracy
+    assert np.sqrt(np.mean(err ** 2)) < 0.01 and np.max(np.abs(err)) < 0.08   # ~ 1/sqrt(ESS) with path degeneracy
     assert np.all(np.abs(var.mean(axis=0) / kvar.mean(axis=0) - 1) < 0.02)
     assert ess.min() > 100 and np.median(ess) > 0.2 * n   # a 4-sigma innovation costs most of the ESS for one step
     ll = np.array([p.log_evidence_inc for p in posts])
