@@ -352,6 +352,15 @@ struct pz_filter {
   double* mtt_part = nullptr;                // per-CTA summary partials of mtt_step
   std::vector<char> mtt_params;
   int32_t mtt_mmax = 0;
+  // multi-device tracker (a shard of a pz_filter_create_multi tracker): this device owns particles [mtt_j0, mtt_jend) of
+  // the global population; the gathered arrays (16-bit weights, block exponents / sums, summary partials, dropped-birth
+  // counters) exist once per step parity, so that a peer's push of step t+1 never lands in what step t still reads
+  int mtt_world = 1, mtt_rank = 0;
+  int64_t mtt_j0 = 0, mtt_jend = 0, mtt_per = 0;
+  uint16_t* mtt_q16b = nullptr;
+  uint64_t* mtt_sbb = nullptr;
+  double* mtt_partb = nullptr;
+  unsigned long long* mtt_ovf[2] = {nullptr, nullptr};   // [kMttMaxDevices] counters each
 };
 
 namespace {
@@ -455,6 +464,7 @@ void free_filter(pz_filter* f) {
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(f->mbox); cudaFree(f->d_p2p);
   cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow); cudaFree(f->mtt_part);
+  cudaFree(f->mtt_q16b); cudaFree(f->mtt_sbb); cudaFree(f->mtt_partb); cudaFree(f->mtt_ovf[0]); cudaFree(f->mtt_ovf[1]);
   cudaFree(f->gen_lw[0]); cudaFree(f->gen_lw[1]); cudaFree(f->gen_obs); cudaFree(f->gen_part); cudaFree(f->gen_state); cudaFree(f->beta);
   if (f->h_gen_obs) cudaFreeHost(f->h_gen_obs);
   if (f->h_mtt_obs) cudaFreeHost(f->h_mtt_obs);
@@ -652,30 +662,59 @@ int enqueue_step(pz_filter* f) {
   return PZ_OK;
 }
 
-GenericArgs mtt_generic(pz_filter* f) {
+// the gathered arrays of step parity `par` (a single-device tracker has one set)
+struct MttBufs { uint16_t* q16; int32_t* eb; uint64_t* sb; double* part; unsigned long long* ovf; };
+MttBufs mtt_bufs(pz_filter* f, int par) {
+  if (f->mtt_world <= 1) return MttBufs{f->g.q16, f->ebbuf[0], f->a.sb, f->mtt_part, f->mtt_overflow};
+  return MttBufs{par ? f->mtt_q16b : f->g.q16, f->ebbuf[par], par ? f->mtt_sbb : f->a.sb, par ? f->mtt_partb : f->mtt_part, f->mtt_ovf[par]};
+}
+
+GenericArgs mtt_generic(pz_filter* f, int par) {
   StepArgs& a = f->a;
+  const MttBufs b = mtt_bufs(f, par);
   GenericArgs g{};
-  g.lw = f->g.lw; g.q16 = f->g.q16; g.q16_alt = f->g.q16; g.xb = a.xb; g.anc = f->g.anc; g.eb = a.eb[0]; g.eb_alt = a.eb[0];
+  g.lw = f->g.lw; g.q16 = b.q16; g.q16_alt = b.q16; g.xb = a.xb; g.anc = f->g.anc; g.eb = b.eb; g.eb_alt = b.eb;
   g.parity_ctl = nullptr;
-  g.sb = a.sb; g.pb = a.pb; g.tile_start = a.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
+  g.sb = b.sb; g.pb = a.pb; g.tile_start = a.tile_start; g.scan_status = a.scan_status; g.scan_part = a.scan_part;
   g.plan = a.plan; g.ctl = a.ctl; g.n = a.n_local; g.nblk = a.nblk; g.ntiles_out = a.ntiles_out; g.nscan = a.nscan;
   g.U = 0; g.seed = a.seed; g.step = f->t;
   return g;
 }
 
-// stats of the stored log-weights -> scan -> (summary) -> partition
-int mtt_plan(pz_filter* f, int delta, double ll_const) {
-  StepArgs& a = f->a;
-  GenericArgs g = mtt_generic(f);
-  int n = launch_stats_from_lw(g, f->stream);
-  n += launch_scan_only(a, delta, f->stream);
+// block statistics of this device's stored log-weights (its slice of the global arrays of parity `par`)
+int mtt_stats(pz_filter* f, int par) {
+  GenericArgs g = mtt_generic(f, par);
+  if (f->mtt_world > 1) {
+    const int64_t b0 = f->mtt_j0 / kBlk;
+    g.lw += f->mtt_j0; g.q16 += f->mtt_j0; g.eb += b0; g.sb += b0;
+    g.n = f->mtt_jend - f->mtt_j0; g.nblk = (g.n + kBlk - 1) / kBlk;
+  }
+  return launch_stats_from_lw(g, f->stream);
+}
+
+// scan -> (summary) -> partition over the (gathered) arrays of parity `par`
+int mtt_plan_global(pz_filter* f, int par, int delta, double ll_const) {
+  StepArgs b = f->a;
+  const MttBufs mb = mtt_bufs(f, par);
+  b.eb[0] = b.eb[1] = mb.eb; b.sb = mb.sb;
+  int n = 0;
+  if (f->mtt_world > 1) n += launch_emax_from_eb(mb.eb, b.nblk, b.ctl, f->stream);   // the other devices' exponents
+  n += launch_scan_only(b, delta, f->stream);
   if (delta)
-    n += launch_mtt_summary(f->mtt_part, a.n_local, a.plan, a.ctl, a.summ, ll_const, f->mtt_overflow, f->stream);
-  n += launch_partition_ext(a, kGenericTileOut, delta, f->stream);
+    n += launch_mtt_summary(mb.part, b.n_local, b.plan, b.ctl, b.summ, ll_const, mb.ovf, f->stream, f->mtt_world > 1 ? f->mtt_world : 1);
+  n += launch_partition_ext(b, kGenericTileOut, delta, f->stream);
   return n;
 }
 
-int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device, pz_filter** out) {
+// stats of the stored log-weights -> scan -> (summary) -> partition
+int mtt_plan(pz_filter* f, int delta, double ll_const) {
+  return mtt_stats(f, 0) + mtt_plan_global(f, 0, delta, ll_const);
+}
+
+// rank / world / per: a shard of a multi-device tracker owns particles [rank * per, min((rank + 1) * per, n)); its plan
+// arrays cover the whole population (every device derives the global plan from the gathered block statistics)
+int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device, pz_filter** out, int rank = 0, int world = 1,
+               int64_t per = 0) {
   if (model->nx != 4 || model->ny != 2) return fail(PZ_EINVAL, "the MTT descriptor needs the (4,2) track model");
   if (model->mtt.k_max != 16) return fail(PZ_EINVAL, "k_max must be 16 (one lane per track slot)");
   if (model->mtt.m_max < 1 || model->mtt.m_max > 32) return fail(PZ_EINVAL, "m_max must be in [1, 32]");
@@ -688,6 +727,9 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   pz_filter* f = new (std::nothrow) pz_filter();
   if (!f) return fail(PZ_ENOMEM, "out of host memory");
   f->desc = *model; f->device = device; f->is_mtt = true; f->mtt_mmax = model->mtt.m_max;
+  f->mtt_world = world; f->mtt_rank = rank; f->mtt_per = world > 1 ? per : 0;
+  f->mtt_j0 = world > 1 ? rank * per : 0;
+  f->mtt_jend = world > 1 ? (((int64_t)(rank + 1) * per < (int64_t)n) ? (rank + 1) * per : (int64_t)n) : (int64_t)n;
   StepArgs& a = f->a;
   memset(&a, 0, sizeof(a));
   a.model.nx = 4; a.model.ny = 2;
@@ -698,7 +740,7 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   a.ld = round_up(a.n_local, kPad);
   f->mtt_params.resize(mtt_params_size());
   mtt_fill_params(model, f->mtt_params.data());
-  const size_t sbytes = (size_t)a.n_local * mtt_words_per_particle() * sizeof(uint32_t);
+  const size_t sbytes = (size_t)(f->mtt_jend - f->mtt_j0) * mtt_words_per_particle() * sizeof(uint32_t);
 #define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
@@ -732,6 +774,21 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
     if (rc) { free_filter(f); return rc; }
   }
   launch_ctl_reset(a.ctl, f->stream);
+  if (world > 1) {   // second parity of the gathered arrays; the first plan follows in create_mtt_multi (it needs every shard)
+    PZ_TRY(cudaMalloc(&f->ebbuf[1], (a.nblk + 8) * sizeof(int32_t)));
+    PZ_TRY(cudaMalloc(&f->mtt_sbb, (a.nblk + 8) * sizeof(uint64_t)));
+    PZ_TRY(cudaMalloc(&f->mtt_q16b, (size_t)a.ld * sizeof(uint16_t)));
+    PZ_TRY(cudaMemsetAsync(f->mtt_q16b, 0, (size_t)a.ld * sizeof(uint16_t), f->stream));
+    PZ_TRY(cudaMalloc(&f->mtt_partb, (size_t)mtt_step_ctas(a.n_local) * 5 * sizeof(double)));
+    for (int i = 0; i < 2; ++i) {
+      PZ_TRY(cudaMalloc(&f->mtt_ovf[i], kMttMaxDevices * sizeof(unsigned long long)));
+      PZ_TRY(cudaMemsetAsync(f->mtt_ovf[i], 0, kMttMaxDevices * sizeof(unsigned long long), f->stream));
+    }
+    PZ_TRY(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+    PZ_TRY(cudaStreamSynchronize(f->stream));
+    *out = f;
+    return PZ_OK;
+  }
   mtt_plan(f, 0, 0.0);
   PZ_TRY(cudaGetLastError());
   PZ_TRY(cudaStreamSynchronize(f->stream));
@@ -747,7 +804,7 @@ int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summar
   for (int i = 0; i < 2 * n_obs; ++i) f->h_mtt_obs[i] = (float)obs[i];
   if (n_obs) PZ_CUDA(cudaMemcpyAsync(f->mtt_obs, f->h_mtt_obs, 2 * n_obs * sizeof(float), cudaMemcpyHostToDevice, f->stream));
   PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
-  GenericArgs g = mtt_generic(f);
+  GenericArgs g = mtt_generic(f, 0);
   int n = launch_generic_ancestors(g, f->stream);
   n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
                        f->mtt_overflow, f->mtt_part, a.n_local, n_obs, a.seed, f->stream);
@@ -763,6 +820,168 @@ int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summar
   cudaEventElapsedTime(&ms, f->ev0, f->ev1);
   f->last_ms = ms; f->last_launches = n;
   const pz_step_summary& s = f->h_summ[t0 % kObsRing];
+  if (out) *out = s;
+  if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", t0);
+  return PZ_OK;
+}
+
+// ---- multi-device tracker (one process, D devices; MultiTargetTracking.hs:133-145 under zdsparticles) ------------
+// Device r owns particles and output slots [r * per, (r + 1) * per).  A step on every device:
+//   pf_ancestors over its own output tiles (global ancestor indices from the global plan) -> mtt_step over its own
+//   particles, parent records read from their owners over NVLink -> block statistics of its own log-weights ->
+//   pf_push_slices: its slices of the 16-bit weights, block exponents / sums, summary partials and dropped-birth counter
+//   stored into every peer (the all-gather) -> [wait for every peer's push] -> global exponent, scan, summary and
+//   partition over the gathered arrays, redundantly on every device (the scan of 4 * 10^5 blocks takes 25 us).
+// Particles, Philox counters and summary partials are keyed on GLOBAL indices: the run equals the one-device run bit
+// for bit (tests/test_mtt.py::test_multi_device_tracker_equals_single_device).
+int mtt_push(pz_filter* parent, int r, int par) {
+  pz_filter* sh = parent->shards[r];
+  const int D = (int)parent->shards.size();
+  const MttBufs mine = mtt_bufs(sh, par);
+  const int64_t j0 = sh->mtt_j0, cnt = sh->mtt_jend - sh->mtt_j0;
+  const int64_t b0 = j0 / kBlk, nb = (cnt + kBlk - 1) / kBlk;
+  const int64_t c0 = j0 / 128, nc = mtt_step_ctas(cnt);
+  PushArgs p{};
+  p.n_arr = 4;
+  p.src[0] = mine.q16 + j0;  p.bytes[0] = nb * kBlk * (int64_t)sizeof(uint16_t);
+  p.src[1] = mine.eb + b0;   p.bytes[1] = nb * (int64_t)sizeof(int32_t);
+  p.src[2] = mine.sb + b0;   p.bytes[2] = nb * (int64_t)sizeof(uint64_t);
+  p.src[3] = mine.part + c0 * 5; p.bytes[3] = nc * 5 * (int64_t)sizeof(double);
+  PushArgs o{};   // the dropped-birth counter goes to every device, this one included
+  o.n_arr = 1; o.src[0] = sh->mtt_overflow; o.bytes[0] = sizeof(unsigned long long);
+  for (int q = 0; q < D; ++q) {
+    const MttBufs theirs = mtt_bufs(parent->shards[q], par);
+    o.dst[o.n_peers++][0] = theirs.ovf + r;
+    if (q == r) continue;
+    void** d = p.dst[p.n_peers++];
+    d[0] = theirs.q16 + j0; d[1] = theirs.eb + b0; d[2] = theirs.sb + b0; d[3] = theirs.part + c0 * 5;
+  }
+  int n = launch_push_slices(p, sh->stream);
+  n += launch_push_slices(o, sh->stream);
+  PZ_CUDA(cudaEventRecord(sh->ev_fork, sh->stream));
+  return n;
+}
+
+int enable_peer_access(int n_devices, const int* device_ids) {
+  for (int r = 0; r < n_devices; ++r) {
+    cudaSetDevice(device_ids[r]);
+    for (int q = 0; q < n_devices; ++q) {
+      if (q == r || device_ids[q] == device_ids[r]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, device_ids[r], device_ids[q]);
+      if (!can) return fail(PZ_ECUDA, "device %d cannot access device %d (no peer path)", device_ids[r], device_ids[q]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[q], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(PZ_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device_ids[r], device_ids[q], cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  }
+  return PZ_OK;
+}
+
+int create_mtt_multi(const pz_model_desc* model, uint64_t n, uint64_t seed, int n_devices, const int* device_ids, pz_filter** out) {
+  const int D = n_devices;
+  if (D > kMttMaxDevices) return fail(PZ_EINVAL, "the multi-device tracker takes up to %d devices", kMttMaxDevices);
+  // whole resampling tiles (2048 slots = 8 blocks = 16 mtt_step CTAs) per device
+  const int64_t per = round_up(((int64_t)n + D - 1) / D, (int64_t)kGenericTileOut);
+  if ((int64_t)(D - 1) * per >= (int64_t)n) return fail(PZ_EINVAL, "%llu particles are too few for %d devices (%d per tile)", (unsigned long long)n, D, kGenericTileOut);
+  pz_filter* parent = new (std::nothrow) pz_filter();
+  if (!parent) return fail(PZ_ENOMEM, "out of host memory");
+  parent->desc = *model; parent->is_multi = true; parent->is_mtt = true; parent->device = device_ids[0];
+  parent->mtt_mmax = model->mtt.m_max; parent->mtt_world = D; parent->mtt_per = per;
+  memset(&parent->a, 0, sizeof(parent->a));
+  auto bail = [&](int code) { free_filter(parent); return code; };
+  for (int r = 0; r < D; ++r) {
+    pz_filter* sh = nullptr;
+    int rc = create_mtt(model, n, seed, device_ids[r], &sh, r, D, per);
+    if (rc) return bail(rc);
+    parent->shards.push_back(sh);
+  }
+  parent->a = parent->shards[0]->a;
+  parent->a.world = 1;   // (the plan is global on every device: no halo exchange, no rank-relative indices)
+  int rc = enable_peer_access(D, device_ids);
+  if (rc) return bail(rc);
+  // the plan of the prior population (all log-weights 0)
+  for (int r = 0; r < D; ++r) {
+    pz_filter* sh = parent->shards[r];
+    if (cudaSetDevice(sh->device) != cudaSuccess) return bail(fail(PZ_ECUDA, "cudaSetDevice(%d) failed", sh->device));
+    mtt_stats(sh, 0);
+    rc = mtt_push(parent, r, 0);
+    if (rc < 0) return bail(rc);
+  }
+  for (int q = 0; q < D; ++q) {
+    pz_filter* sh = parent->shards[q];
+    cudaSetDevice(sh->device);
+    for (int r = 0; r < D; ++r) if (r != q) cudaStreamWaitEvent(sh->stream, parent->shards[r]->ev_fork, 0);
+    mtt_plan_global(sh, 0, 0, 0.0);
+  }
+  for (int q = 0; q < D; ++q) {
+    pz_filter* sh = parent->shards[q];
+    cudaSetDevice(sh->device);
+    cudaError_t e = cudaStreamSynchronize(sh->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(PZ_ECUDA, "multi-device tracker: first plan on device %d: %s", sh->device, cudaGetErrorString(e)));
+  }
+  *out = parent;
+  return PZ_OK;
+}
+
+MttShard mtt_shard_view(pz_filter* parent, pz_filter* sh, int rec_parity) {
+  MttShard ms;
+  ms.j0 = sh->mtt_j0; ms.j_end = sh->mtt_jend; ms.n_per = parent->mtt_per;
+  for (size_t q = 0; q < parent->shards.size(); ++q) ms.sin_all[q] = parent->shards[q]->mtt_s[rec_parity];
+  return ms;
+}
+
+int mtt_multi_step_host(pz_filter* p, const double* obs, int32_t n_obs, pz_step_summary* out) {
+  if (n_obs < 0 || n_obs > p->mtt_mmax) return fail(PZ_ECAPACITY, "%d observations exceed m_max = %d", n_obs, p->mtt_mmax);
+  const int D = (int)p->shards.size();
+  const uint32_t t0 = p->t;
+  const int pin = (int)(t0 & 1u), pout = pin ^ 1;
+  // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
+  const double ll_const = -(p->desc.mtt.clutter_lambda + p->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
+  int64_t launches = 0;
+  for (int r = 0; r < D; ++r) {   // own slots: ancestors -> tracker step -> statistics -> push
+    pz_filter* f = p->shards[r];
+    PZ_CUDA(cudaSetDevice(f->device));
+    for (int i = 0; i < 2 * n_obs; ++i) f->h_mtt_obs[i] = (float)obs[i];
+    if (n_obs) PZ_CUDA(cudaMemcpyAsync(f->mtt_obs, f->h_mtt_obs, 2 * n_obs * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
+    GenericArgs g = mtt_generic(f, pin);
+    g.tile0 = (int32_t)(f->mtt_j0 / kGenericTileOut);
+    g.ntiles_out = (int32_t)((f->mtt_jend - f->mtt_j0 + kGenericTileOut - 1) / kGenericTileOut);
+    launches += launch_generic_ancestors(g, f->stream);
+    const MttShard ms = mtt_shard_view(p, f, (int)(t0 & 1u));
+    launches += launch_mtt_step(f->mtt_params.data(), nullptr, f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, f->a.ctl,
+                                f->mtt_overflow, mtt_bufs(f, pout).part + (f->mtt_j0 / 128) * 5, f->a.n_local, n_obs, f->a.seed,
+                                f->stream, &ms);
+    launches += mtt_stats(f, pout);
+    int rc = mtt_push(p, r, pout);
+    if (rc < 0) return rc;
+    launches += rc;
+  }
+  for (int q = 0; q < D; ++q) {   // the global plan, on every device, once every push has landed
+    pz_filter* f = p->shards[q];
+    PZ_CUDA(cudaSetDevice(f->device));
+    for (int r = 0; r < D; ++r) if (r != q) PZ_CUDA(cudaStreamWaitEvent(f->stream, p->shards[r]->ev_fork, 0));
+    launches += mtt_plan_global(f, pout, 1, ll_const);
+    f->t += 1;
+    PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
+    PZ_CUDA(cudaMemcpyAsync(f->h_summ + (t0 % kObsRing), f->a.summ + (t0 % kObsRing), sizeof(pz_step_summary), cudaMemcpyDeviceToHost, f->stream));
+  }
+  double ms_max = 0;
+  for (int q = 0; q < D; ++q) {
+    pz_filter* f = p->shards[q];
+    PZ_CUDA(cudaSetDevice(f->device));
+    PZ_CUDA(cudaStreamSynchronize(f->stream));
+    PZ_CUDA(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, f->ev0, f->ev1);
+    ms_max = ms > ms_max ? ms : ms_max;
+  }
+  p->t += 1;
+  p->last_ms = ms_max; p->last_launches = launches;
+  const pz_step_summary& s = p->shards[0]->h_summ[t0 % kObsRing];   // every device derives the same summary
   if (out) *out = s;
   if (s.total_weight == 0) return fail(PZ_EDEGENERATE, "step %u: every particle has zero weight", t0);
   return PZ_OK;
@@ -1339,11 +1558,15 @@ int create_multi(const pz_model_desc* model, uint64_t n_global, uint64_t seed, i
   *out = nullptr;
   if (n_devices < 1 || n_devices > kMaxRanks) return fail(PZ_EINVAL, "n_devices must be in [1, %d]", kMaxRanks);
   if (n_devices == 1) return create_common(model, n_global, seed, device_ids[0], 0, 1, nullptr, out);
+  // (test hook: PZ_MULTI_SAME_DEVICE=1 lets the shards of a multi-device TRACKER share a device -- its exchange is ordered by
+  // events, not by spinning kernels -- so that the sharded path runs on a one-GPU box)
+  const bool same_ok = model->kind == PZ_MODEL_MTT && getenv("PZ_MULTI_SAME_DEVICE") != nullptr;
   for (int i = 0; i < n_devices; ++i)
     for (int j = 0; j < i; ++j)
-      if (device_ids[i] == device_ids[j]) return fail(PZ_EINVAL, "device %d listed twice", device_ids[i]);
+      if (device_ids[i] == device_ids[j] && !same_ok) return fail(PZ_EINVAL, "device %d listed twice", device_ids[i]);
+  if (model->kind == PZ_MODEL_MTT) return create_mtt_multi(model, n_global, seed, n_devices, device_ids, out);
   if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS)
-    return fail(PZ_EINVAL, "multi-device filters: the linear-Gaussian families (RW1D / LINGAUSS)");
+    return fail(PZ_EINVAL, "multi-device filters: the linear-Gaussian families (RW1D / LINGAUSS) and the tracker (MTT)");
   if (model->delayed || model->carry_weights || model->ess_threshold > 0)
     return fail(PZ_EINVAL, "delayed-sampling / stored-log-weight filters run on one GPU");
   pz_filter* parent = new (std::nothrow) pz_filter();
@@ -1605,6 +1828,7 @@ int pz_filter_create_sharded(const pz_model_desc* model, uint64_t n_global, uint
 
 int64_t pz_filter_n_local(const pz_filter* f) {
   if (!f) return 0;
+  if (f->is_multi && f->is_mtt) return f->a.n_global;
   return f->is_multi ? f->a.n_local * (int64_t)f->shards.size() : f->a.n_local;   // a multi-device handle holds the whole population
 }
 
@@ -1612,6 +1836,7 @@ int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_d
   if (!f || (!obs && n_obs > 0)) return fail(PZ_EINVAL, "null argument");
   if (f->is_mtt) {
     if (obs_dim != 2) return fail(PZ_EINVAL, "tracker observations are rows of 2 doubles");
+    if (f->is_multi) return mtt_multi_step_host(f, obs, n_obs, out);
     PZ_CUDA(cudaSetDevice(f->device));
     return mtt_step_host(f, obs, n_obs, out);
   }
@@ -1876,13 +2101,20 @@ int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int3
   const StepArgs& a = f->a;
   const int64_t n_sel = (a.n_local + stride - 1) / stride;
   if (n_sel_cap < n_sel) return fail(PZ_EINVAL, "buffers too small: need %lld particles", (long long)n_sel);
+  pz_filter* parent = f;
+  if (f->is_multi) f = f->shards[0];   // every device holds the global plan: device 0 derives all ancestors and gathers from the owners
   PZ_CUDA(cudaSetDevice(f->device));
-  int rc = pending_ancestors(f, nullptr);
+  int rc = PZ_OK;
+  if (parent->is_multi) {
+    GenericArgs g = mtt_generic(f, (int)(parent->t & 1u));
+    launch_generic_ancestors(g, f->stream);
+  } else rc = pending_ancestors(f, nullptr);
   if (rc) return rc;
   const int W = mtt_words_per_particle();
   uint32_t* d_out = nullptr;
   PZ_CUDA(cudaMalloc(&d_out, (size_t)n_sel * W * sizeof(uint32_t)));
-  launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream);
+  if (parent->is_multi) launch_mtt_gather_multi(mtt_shard_view(parent, f, (int)(parent->t & 1u)), f->g.anc, stride, n_sel, d_out, f->stream);
+  else launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream);
   std::vector<uint32_t> h((size_t)n_sel * W);
   cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);

@@ -118,6 +118,12 @@ __device__ __forceinline__ unsigned long long wait_sys(const unsigned long long*
   return v;
 }
 // 2^k as a float for k <= 0 (0 when it would underflow)
+// warp maximum in one instruction (CREDUX.MAX.F32, sm_100a): NaN inputs are ignored, as by the fmaxf butterfly it replaces
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
 __device__ __forceinline__ float exp2i(int k) { return k < -126 ? 0.0f : __int_as_float((127 + k) << 23); }
 // 2^k as a double (0 when it would underflow)
 __device__ __forceinline__ double pow2d(int k) {
@@ -997,6 +1003,17 @@ struct TileArgs {
 #ifndef PZ_OCC6
 #define PZ_OCC6 2
 #endif
+// packed fp32 model step (two slots per FFMA2 / FADD2 / FMUL2) for fp32 states: PZ_PACK_MODEL is a bit mask over
+// NX = 1 / 4 / 6 (1 | 2 | 4): measured, only LG(4,2) gains (0.1452 -> 0.1432 ms at N = 10^7; LG(6,3) loses 4 % to register
+// pressure, RW1D is neutral); the weights and moments are packed for every type
+#ifndef PZ_PACK_MODEL
+#define PZ_PACK_MODEL 2
+#endif
+// persistent grid (a CTA strides over the tiles; table, observation and plan constants fetched once per CTA): measured at
+// N = 10^7 / 10^8 -- LG(4,2) f64 0.2293 -> 0.2242 ms, LG(6,3) f64 0.3594 -> 0.3508, LG(6,3) f32 0.1992 -> 0.1972, but
+// RW1D f64 0.5176 -> 0.5611, RW1D f32 0.4142 -> 0.4613, LG(4,2) f32 0.1501 -> 0.1561: the one-word states keep one CTA per tile
+template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE || (NX > 1 && (sizeof(T) == 8 || NX > 4));
+template <int NX> constexpr bool kPackModel = ((PZ_PACK_MODEL) >> (NX == 1 ? 0 : (NX <= 4 ? 1 : 2))) & 1;
 constexpr int min_ctas(int nx) { return nx == 1 ? PZ_OCC1 : (nx <= 4 ? PZ_OCC4 : PZ_OCC6); }
 #define PZ_NACC(nx) (2 + 2 * (nx))
 
@@ -1053,18 +1070,36 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
     T z[NX][4];
     lg_noise4<NX, T>(j0 + (uint32_t)sl, t, a.seed, tab_m8, z);
     T xo[NX][4];
+    if constexpr (sizeof(T) == 4 && kPackModel<NX>) {
+      // fp32 state: slots k, k+1 share packed instructions (same individually rounded operations per slot)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      T xs[NX], zs[NX], xn[NX];
+      for (int k = 0; k < 4; k += 2) {
+        float2 xs[NX], zs[NX], xn[NX];
 #pragma unroll
-      for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
-      model_propagate<NX, KRON>(model, xs, zs, xn);
+        for (int d = 0; d < NX; ++d) { xs[d] = make_float2(xp[d][k], xp[d][k + 1]); zs[d] = make_float2(z[d][k], z[d][k + 1]); }
+        model_propagate<NX, KRON>(model, xs, zs, xn);
 #pragma unroll
-      for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
-      float l = lw_key(model_logweight<NX, NY, KRON>(model, xn, y_new));
-      if (!FULL && sl + k >= nslots) l = -INFINITY;  // past the end of the population
-      lw[half * 4 + k] = l;
-      mx = fmaxf(mx, l);
+        for (int d = 0; d < NX; ++d) { xo[d][k] = xn[d].x; xo[d][k + 1] = xn[d].y; }
+        float2 l = model_logweight<NX, NY, KRON>(model, xn, y_new);
+        if (!FULL && sl + k >= nslots) l.x = -INFINITY;  // past the end of the population
+        if (!FULL && sl + k + 1 >= nslots) l.y = -INFINITY;
+        lw[half * 4 + k] = l.x; lw[half * 4 + k + 1] = l.y;
+        mx = fmaxf(mx, fmaxf(l.x, l.y));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        T xs[NX], zs[NX], xn[NX];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) { xs[d] = xp[d][k]; zs[d] = z[d][k]; }
+        model_propagate<NX, KRON>(model, xs, zs, xn);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) xo[d][k] = xn[d];
+        float l = lw_key(model_logweight<NX, NY, KRON>(model, xn, y_new));
+        if (!FULL && sl + k >= nslots) l = -INFINITY;  // past the end of the population
+        lw[half * 4 + k] = l;
+        mx = fmaxf(mx, l);
+      }
     }
     if (FULL || sl < nslots) {
 #pragma unroll
@@ -1074,19 +1109,25 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       }
     }
     if constexpr (NX == 1) {
+      if constexpr (sizeof(T) == 4) {
+        const float2 a = r_sub(make_float2((float)xo[0][0], (float)xo[0][1]), (float)cen[0]), b = r_sub(make_float2((float)xo[0][2], (float)xo[0][3]), (float)cen[0]);
+        dxk[half * 4 + 0] = a.x; dxk[half * 4 + 1] = a.y; dxk[half * 4 + 2] = b.x; dxk[half * 4 + 3] = b.y;
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dxk[half * 4 + k] = (float)r_sub(xo[0][k], cen[0]);
+        for (int k = 0; k < 4; ++k) dxk[half * 4 + k] = (float)r_sub(xo[0][k], cen[0]);
+      }
     }
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  mx = warp_max_f32(mx);
   int32_t nb;
   const float nbf = block_exponent(mx, nb);
   uint32_t ssum = 0;
   if (nb != kNZero) {
-    float p[PZ_NACC(NX)];
+    // packed fp32 (FFMA2 / FADD2 / FMUL2): slots k, k+1 of a lane ride in one instruction; the lane's sums are
+    // kept as (even slots, odd slots) pairs and added once per block
+    float2 pp[PZ_NACC(NX)];
 #pragma unroll
-    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = 0.0f;
+    for (int r = 0; r < PZ_NACC(NX); ++r) pp[r] = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int sl = ob * kBlk + half * 128 + lane * 4;
@@ -1095,8 +1136,13 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
           const Quad<T> f = lds_quad(&s_par[d * TO + sl]);
+          if constexpr (sizeof(T) == 4) {
+            const float2 a = r_sub(make_float2((float)f.v[0], (float)f.v[1]), (float)cen[d]), b = r_sub(make_float2((float)f.v[2], (float)f.v[3]), (float)cen[d]);
+            dxv[d][0] = a.x; dxv[d][1] = a.y; dxv[d][2] = b.x; dxv[d][3] = b.y;
+          } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dxv[d][k] = (float)r_sub(f.v[k], cen[d]);
+            for (int k = 0; k < 4; ++k) dxv[d][k] = (float)r_sub(f.v[k], cen[d]);
+          }
         }
       } else {
 #pragma unroll
@@ -1104,25 +1150,29 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       }
       uint32_t qb[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float w;
-        weight_q<false>(lw[half * 4 + k], nbf, w, qb[k]);
-        const bool live = FULL || sl + k < nslots;
-        if (!live) w = 0.0f;  // (its q is already 0: lw = -inf)
-        ssum += qb[k];        // raw bits 0x4B000000 + q; the bias is removed after the warp sum
-        p[0] = __fadd_rn(p[0], w);
-        p[1] = __fmaf_rn(w, w, p[1]);
+      for (int k = 0; k < 4; k += 2) {
+        float2 w;
+        weight_q2(make_float2(lw[half * 4 + k], lw[half * 4 + k + 1]), nbf, w, qb[k], qb[k + 1]);
+        const bool live0 = FULL || sl + k < nslots, live1 = FULL || sl + k + 1 < nslots;
+        if (!live0) w.x = 0.0f;  // (its q is already 0: lw = -inf)
+        if (!live1) w.y = 0.0f;
+        ssum += qb[k] + qb[k + 1];  // raw bits 0x4B000000 + q; the bias is removed after the warp sum
+        pp[0] = __fadd2_rn(pp[0], w);
+        pp[1] = __ffma2_rn(w, w, pp[1]);
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          const float dx = live ? dxv[d][k] : 0.0f;
-          const float wd = __fmul_rn(w, dx);
-          p[2 + d] = __fadd_rn(p[2 + d], wd);
-          p[2 + NX + d] = __fmaf_rn(wd, dx, p[2 + NX + d]);
+          const float2 dx = make_float2(live0 ? dxv[d][k] : 0.0f, live1 ? dxv[d][k + 1] : 0.0f);
+          const float2 wd = __fmul2_rn(w, dx);
+          pp[2 + d] = __fadd2_rn(pp[2 + d], wd);
+          pp[2 + NX + d] = __ffma2_rn(wd, dx, pp[2 + NX + d]);
         }
       }
       if (FULL || sl < nslots)
         *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(__byte_perm(qb[0], qb[1], 0x5410), __byte_perm(qb[2], qb[3], 0x5410));
     }
+    float p[PZ_NACC(NX)];
+#pragma unroll
+    for (int r = 0; r < PZ_NACC(NX); ++r) p[r] = __fadd_rn(pp[r].x, pp[r].y);
     // fold the block's sums (scale 2^nb) into the lane accumulators (scale 2^aref)
     if (nb == aref) {
 #pragma unroll
@@ -1149,8 +1199,7 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       if (FULL || sl < nslots) *reinterpret_cast<uint2*>(&qout[j0l + sl]) = make_uint2(0u, 0u);
     }
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, d);
+  ssum = __reduce_add_sync(0xffffffffu, ssum);
   if (lane == 0) {
     const int64_t bo = (j0l / kBlk) + ob;
     a.eb[nxt][bo] = nb;
@@ -1194,15 +1243,30 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
     }
     __syncthreads();
   }
-  int tile = blockIdx.x;
-  do {   // one tile per CTA (REMOTE: a persistent grid strides over the tiles)
+  // A persistent grid strides over the tiles (launch_tile sizes it to the resident CTA count; with one CTA per tile the
+  // loop runs once): the inverse-CDF table, the observation, the plan constants and the centring constants are
+  // fetched once per CTA instead of once per tile.  The walk starts in the MIDDLE of the rank's tiles, so the boundary
+  // tiles of a sharded filter -- which wait for the neighbours' margins -- come up when the margins have long arrived.
+  T y_new[NY];
+  load_obs<T, NY>(a, t, y_new);
+  for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];   // (ordered before its first use by the tile's barriers)
+  T cen[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) {
+    if constexpr (sizeof(T) == 8) cen[d] = pl->center64[d]; else cen[d] = pl->center[d];
+  }
+  const int32_t pl_emax = pl->emax, pl_h0 = pl->h0;
+  const uint32_t pl_Mq = pl->Mq;
+  const int ntiles = a.ntiles_out;
+  const int tile_shift = (kPersist<T, NX, REMOTE> && gridDim.x < (unsigned)ntiles) ? ntiles / 2 : 0;
+  int tile_k = blockIdx.x;
+  do {
+  int tile = tile_k + tile_shift;
+  if (tile >= ntiles) tile -= ntiles;
   const int64_t j0l = (int64_t)tile * TO;  // local slot
   const int64_t jendl = (j0l + TO < a.n_local) ? j0l + TO : a.n_local;
   const uint32_t j0 = (uint32_t)(a.slot_base + j0l);
   const int nslots = (int)(jendl - j0l);
-
-  T y_new[NY];
-  load_obs<T, NY>(a, t, y_new);
   PZ_STAMP(blockIdx.x == 0 && tid == 0, 11);
   PZ_STAMP(blockIdx.x == gridDim.x - 1 && tid == 0, 14);
 
@@ -1241,13 +1305,12 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
         pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
       }
     }
-    for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
     // sentinel in (the mark word of) dimension 0 of every slot: "no head here"
     uint4* sz = reinterpret_cast<uint4*>(s_par);
     for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
     if constexpr (REMOTE) {
-      resample_tile_remote<(NX != 1), NW>(src, s_par, TO, a.p2p, cur, a.nblk, a.world, b_first, pl->emax, pl->h0, pl->Mq, j0, nslots,
+      resample_tile_remote<(NX != 1), NW>(src, s_par, TO, a.p2p, cur, a.nblk, a.world, b_first, pl_emax, pl_h0, pl_Mq, j0, nslots,
                                           lane, warp);
     } else {
       if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 8) {
@@ -1256,11 +1319,10 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
           pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
         }
       }
-      resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl->emax, pl->h0, pl->Mq, j0, nslots,
+      resample_tile<(NX != 1), NW>(src, s_par, TO, a.Q[cur], a.eb[cur], a.xb, b_first, a.b_hi, pl_emax, pl_h0, pl_Mq, j0, nslots,
                                lane, warp, first, pa, pb);
     }
   } else {
-    for (int i = tid; i < PZ_ICDF_ROWS; i += NT) s_tab[i] = g_icdf_tab[i];
     for (int sidx = tid; sidx < nslots; sidx += NT) {
       const int64_t p = ta.anc[j0l + sidx];
 #pragma unroll
@@ -1275,11 +1337,6 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
 #pragma unroll
   for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0.0f;
   int32_t aref = kNZero;
-  T cen[NX];
-#pragma unroll
-  for (int d = 0; d < NX; ++d) {
-    if constexpr (sizeof(T) == 8) cen[d] = pl->center64[d]; else cen[d] = pl->center[d];
-  }
   if (nslots == TO) {
     for (int ob = warp; ob < TO / kBlk; ob += NW)
       output_block<T, NX, NY, TO, MODE, KRON, true>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
@@ -1288,33 +1345,39 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
       output_block<T, NX, NY, TO, MODE, KRON, false>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   }
 
-  // ---- CTA-level reduction of the moment sums -> one record per tile
+  // ---- moment sums -> one record per tile: every warp reduces its lanes at its own scale 2^aref; after ONE barrier
+  // (the one that also frees the staging buffer for the next tile) the record's threads combine the warps
   if (lane == 0) s_eref[warp] = aref;
-  __syncthreads();
-  int32_t etile = kNZero;
 #pragma unroll
-  for (int w = 0; w < NW; ++w) etile = max(etile, s_eref[w]);
-  {
-    const double g = (aref == kNZero) ? 0.0 : pow2d(aref - etile);
+  for (int r = 0; r < PZ_NACC(NX); ++r) {
+    double x = (double)acc[r];
 #pragma unroll
-    for (int r = 0; r < PZ_NACC(NX); ++r) {
-      double x = (double)acc[r] * (r == 1 ? g * g : g);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
-      if (lane == 0) s_red[warp][r + 1] = x;
-    }
+    for (int d = 16; d > 0; d >>= 1) x += shfl_xor_f64(x, d);
+    if (lane == 0) s_red[warp][r + 1] = x;
   }
   __syncthreads();
   // record layout (kMaxRec doubles): [0] exponent, [1] sw, [2] sw2, [3..3+NX) sx, [3+NX..3+2NX) sxx
   if (tid < 3 + 2 * NX) {
+    int32_t etile = kNZero;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) etile = max(etile, s_eref[w]);
     double x = 0;
     if (tid == 0) x = (double)etile;
-    else for (int w = 0; w < NW; ++w) x += s_red[w][tid];
+    else {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int32_t ew = s_eref[w];
+        if (ew != kNZero) {
+          const double g = pow2d(ew - etile);
+          x += s_red[w][tid] * (tid == 2 ? g * g : g);
+        }
+      }
+    }
     a.rec[(size_t)tile * kMaxRec + tid] = x;
+    if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
   }
-  if (tid == 0 && etile != kNZero) atomicMax(&a.ctl->emax_acc, etile);
-  if constexpr (REMOTE) __syncthreads();   // the staging buffer and the reduction scratch are reused by the next tile
-  } while (REMOTE && (tile += (int)gridDim.x) < a.ntiles_out);
+  // (the next tile rewrites s_eref / s_red only after its own two barriers)
+  } while (kPersist<T, NX, REMOTE> && (tile_k += (int)gridDim.x) < ntiles);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1381,13 +1444,14 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
   __shared__ __align__(16) float s_anc[TO];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PlanDev* pl = g.plan;
-  const int64_t j0 = (int64_t)blockIdx.x * TO;
+  const int tile = (int)blockIdx.x + g.tile0;
+  const int64_t j0 = (int64_t)tile * TO;
   const int64_t jend = (j0 + TO < g.n) ? j0 + TO : g.n;
   const int nslots = (int)(jend - j0);
   for (int sidx = tid; sidx < TO; sidx += kThreads) s_anc[sidx] = __uint_as_float(kSentinel);
   __syncthreads();
   IndexSource src;
-  const int64_t b_first = (int64_t)g.tile_start[blockIdx.x];
+  const int64_t b_first = (int64_t)g.tile_start[tile];
   BlockIn first{};
   if (b_first + warp < g.nblk) first.load(generic_q(g), generic_eb(g), g.xb, b_first + warp, lane);
   resample_tile<true, kWarps>(src, s_anc, TO, generic_q(g), generic_eb(g), g.xb, b_first, g.nblk, pl->emax, pl->h0, pl->Mq, (uint32_t)j0,
@@ -1967,7 +2031,20 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done.fetch_or(bit, std::memory_order_release);
   }
-  kern<<<ta.a.ntiles_out, NT, smem, s>>>(ta);
+  // persistent grid: as many CTAs as are resident at once (PZ_PERSIST=0: one CTA per tile; PZ_PERSIST=k: k CTAs per SM)
+  static std::atomic<int> resident[64];
+  int grid = resident[dev & 63].load(std::memory_order_acquire);
+  if (grid == 0) {
+    int nsm = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    const char* e = getenv("PZ_PERSIST");
+    if (e && atoi(e) > 0) per_sm = atoi(e);
+    grid = (!kPersist<T, NX, false> || (e && atoi(e) == 0)) ? -1 : nsm * (per_sm > 0 ? per_sm : 1);
+    resident[dev & 63].store(grid, std::memory_order_release);
+  }
+  if (grid < 0 || grid > ta.a.ntiles_out) grid = ta.a.ntiles_out;
+  kern<<<grid, NT, smem, s>>>(ta);
   if constexpr (MODE == 0) {
     if (ta.a.p2p != nullptr) {   // sharded over peer memory: the remote-read fallback follows (it exits at once unless the margins overflowed)
       auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT), true>;
@@ -2105,7 +2182,46 @@ int launch_stats_from_lw(const GenericArgs& g, cudaStream_t s) {
 }
 
 int launch_generic_ancestors(const GenericArgs& g, cudaStream_t s) {
-  pf_ancestors<kGenericTileOut><<<g.ntiles_out, kThreads, 0, s>>>(g);
+  pf_ancestors<kGenericTileOut><<<g.ntiles_out, kThreads, 0, s>>>(g);   // tiles [g.tile0, g.tile0 + g.ntiles_out)
+  return 1;
+}
+
+// slices of a device's arrays -> the same offsets of its peers' arrays
+__global__ void __launch_bounds__(kThreads) pf_push_slices(const __grid_constant__ PushArgs p) {
+  const int64_t gid = (int64_t)blockIdx.x * kThreads + threadIdx.x, gsz = (int64_t)gridDim.x * kThreads;
+  for (int a = 0; a < p.n_arr; ++a) {
+    const int64_t n16 = p.bytes[a] / 16, n4 = (p.bytes[a] - n16 * 16) / 4;
+    const uint4* src = reinterpret_cast<const uint4*>(p.src[a]);
+    for (int64_t i = gid; i < n16; i += gsz) {
+      const uint4 v = src[i];
+      for (int q = 0; q < p.n_peers; ++q) reinterpret_cast<uint4*>(p.dst[q][a])[i] = v;
+    }
+    if (gid < n4) {
+      const uint32_t v = reinterpret_cast<const uint32_t*>(src + n16)[gid];
+      for (int q = 0; q < p.n_peers; ++q) reinterpret_cast<uint32_t*>(reinterpret_cast<uint4*>(p.dst[q][a]) + n16)[gid] = v;
+    }
+  }
+}
+int launch_push_slices(const PushArgs& p, cudaStream_t s) {
+  int64_t mx = 0;
+  for (int a = 0; a < p.n_arr; ++a) mx = p.bytes[a] > mx ? p.bytes[a] : mx;
+  int grid = (int)((mx / 16 + kThreads - 1) / kThreads);
+  grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+  pf_push_slices<<<grid, kThreads, 0, s>>>(p);
+  return 1;
+}
+
+// global block exponent of a gathered eb array (every device of a multi-device tracker holds all of them)
+__global__ void __launch_bounds__(kThreads) pf_emax_from_eb(const int32_t* __restrict__ eb, int64_t nblk, CtlDev* ctl) {
+  int32_t m = kNZero;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nblk; i += (int64_t)gridDim.x * kThreads) m = max(m, eb[i]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m != kNZero) atomicMax(&ctl->emax_acc, m);
+}
+int launch_emax_from_eb(const int32_t* eb, int64_t nblk, CtlDev* ctl, cudaStream_t s) {
+  int grid = cdiv(nblk, kThreads);
+  grid = grid > 148 ? 148 : grid;
+  pf_emax_from_eb<<<grid, kThreads, 0, s>>>(eb, nblk, ctl);
   return 1;
 }
 

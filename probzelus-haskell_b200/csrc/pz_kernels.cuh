@@ -201,6 +201,7 @@ struct GenericArgs {
   uint64_t seed;         // multinomial
   uint32_t step;
   int64_t n_draws;       // multinomial: number of iid draws (0: n)
+  int32_t tile0;         // pf_ancestors: first output tile of this launch (a device of a multi-device tracker takes a range)
 };
 int launch_ctl_reset(CtlDev* ctl, cudaStream_t s);
 int launch_generic_plan(const GenericArgs& g, bool stats_from_lw, cudaStream_t s);
@@ -220,11 +221,31 @@ void mtt_fill_params(const pz_model_desc* d, void* out_mttdev);
 void dbg_read_stamps(unsigned long long* out);  // debug build: %globaltimer stamps of the sharded exchange phases
 #endif
 int mtt_step_ctas(int64_t n);  // CTAs of mtt_step = rows of its per-CTA summary partials (5 doubles each)
+// A multi-device tracker (one process, D devices): device r owns the particles and output slots [j0, j_end) of the
+// global population; parents are read from their owners through peer pointers (sin_all, n_per particles per device).
+struct MttShard {
+  int64_t j0 = 0, j_end = 0;         // global range of this launch (j_end = n for a single device)
+  int64_t n_per = 0;                 // particles per device (0: single device, parents in `sin`)
+  const uint32_t* sin_all[8] = {};   // parent records of every device (current parity)
+};
+constexpr int kMttMaxDevices = 8;
 int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
-                    cudaStream_t s);
+                    cudaStream_t s, const MttShard* shard = nullptr);
+// n_ovf > 1: `overflow` holds one dropped-birth counter per device
 int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDev* ctl, pz_step_summary* summ, double ll_const,
-                       const unsigned long long* overflow, cudaStream_t s);
+                       const unsigned long long* overflow, cudaStream_t s, int n_ovf = 1);
+// Slices of up to 6 arrays stored into the same offsets of up to 8 devices' arrays (128-bit peer stores over NVLink):
+// the all-gather of a multi-device tracker's block statistics, 16-bit weights and summary partials.
+struct PushArgs {
+  int n_arr = 0, n_peers = 0;
+  const void* src[6] = {};
+  void* dst[8][6] = {};
+  int64_t bytes[6] = {};   // multiples of 4; src / dst 16-byte aligned
+};
+int launch_push_slices(const PushArgs& p, cudaStream_t s);
+int launch_emax_from_eb(const int32_t* eb, int64_t nblk, CtlDev* ctl, cudaStream_t s);
+int launch_mtt_gather_multi(const MttShard& sh, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
 int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
 
 }  // namespace pz

@@ -102,6 +102,28 @@ __device__ __forceinline__ void weight_q(float lw, float nbf, float& w, uint32_t
   weight_q_from_arg<CLAMP_HI>(__fmaf_rn(lw, kLog2e, -nbf), w, qbits);
 }
 
+// Two weights at once on the packed fp32 pipe (FFMA2 / FADD2 / FMUL2 of sm_100: two independent, individually
+// rounded IEEE operations per instruction, so the bits are those of weight_q<false> applied to each half; the step
+// kernel is instruction-issue bound and this halves the issue slots of the polynomial).
+__device__ __forceinline__ float2 pk(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void weight_q2(float2 lw, float nbf, float2& w, uint32_t& qb0, uint32_t& qb1) {
+  float2 d = __ffma2_rn(lw, pk(kLog2e), pk(-nbf));
+  d.x = fmaxf(d.x, -32.0f); d.y = fmaxf(d.y, -32.0f);
+  const float2 t = __fadd2_rn(d, pk(12582912.0f));
+  const float2 r = __fadd2_rn(t, pk(-12582912.0f));
+  const float2 f = __fadd2_rn(d, make_float2(-r.x, -r.y));
+  float2 p = pk(PZ_EXP2_C5);
+  p = __ffma2_rn(p, f, pk(PZ_EXP2_C4));
+  p = __ffma2_rn(p, f, pk(PZ_EXP2_C3));
+  p = __ffma2_rn(p, f, pk(PZ_EXP2_C2));
+  p = __ffma2_rn(p, f, pk(PZ_EXP2_C1));
+  p = __ffma2_rn(p, f, pk(1.0f));
+  w.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+  w.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+  const float2 q = __ffma2_rn(w, pk(32768.0f), pk(8388608.0f));
+  qb0 = __float_as_uint(q.x); qb1 = __float_as_uint(q.y);
+}
+
 // stored log-weights may hold anything: +inf and NaN count as -inf (zero weight)
 __device__ __forceinline__ float sanitize_lw(float lw) { return (lw == lw && lw < INFINITY) ? lw : -INFINITY; }
 

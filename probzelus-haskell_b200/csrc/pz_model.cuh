@@ -20,6 +20,13 @@ __device__ __forceinline__ float r_sub(float a, float b) { return __fsub_rn(a, b
 __device__ __forceinline__ double r_sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ float r_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double r_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+// two fp32 lanes per instruction (FFMA2 / FADD2 / FMUL2, sm_100): the same individually rounded operations on each half
+__device__ __forceinline__ float2 r_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 r_mul(float a, float2 b) { return __fmul2_rn(make_float2(a, a), b); }
+__device__ __forceinline__ float2 r_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 r_fma(float a, float2 b, float2 c) { return __ffma2_rn(make_float2(a, a), b, c); }
+__device__ __forceinline__ float2 r_sub(float a, float2 b) { return __fadd2_rn(make_float2(a, a), make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 r_sub(float2 a, float b) { return __fadd2_rn(a, make_float2(-b, -b)); }
 __device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
 template <class T> __device__ __forceinline__ const LgDevT<T>& model_of(const StepArgs& a);
@@ -38,11 +45,12 @@ __device__ __forceinline__ void load_obs(const StepArgs& a, uint32_t t, T (&y)[N
 // ------------------------------------------------------------------------------------------
 // linear-Gaussian model step (same operation order as the oracle's lg_propagate / lg_logweight)
 // ------------------------------------------------------------------------------------------
-template <int NX, class T>
-__device__ __forceinline__ void lg_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
+// (C: the model's coefficient type; V: the value type -- C itself, or float2 = two slots per packed instruction)
+template <int NX, class T, class V>
+__device__ __forceinline__ void lg_propagate(const LgDevT<T>& p, const V* x, const V* z, V* xn) {
 #pragma unroll
   for (int r = 0; r < NX; ++r) {
-    T acc = r_mul(p.F[r][0], x[0]);
+    V acc = r_mul(p.F[r][0], x[0]);
 #pragma unroll
     for (int c = 1; c < NX; ++c) acc = r_fma(p.F[r][c], x[c], acc);
 #pragma unroll
@@ -51,20 +59,20 @@ __device__ __forceinline__ void lg_propagate(const LgDevT<T>& p, const T* x, con
   }
 }
 
-template <int NX, int NY, class T>
-__device__ __forceinline__ T lg_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
-  T d[NY];
+template <int NX, int NY, class T, class V>
+__device__ __forceinline__ V lg_logweight(const LgDevT<T>& p, const V* xn, const T* y) {
+  V d[NY];
 #pragma unroll
   for (int k = 0; k < NY; ++k) {
-    T acc = r_mul(p.H[k][0], xn[0]);
+    V acc = r_mul(p.H[k][0], xn[0]);
 #pragma unroll
     for (int c = 1; c < NX; ++c) acc = r_fma(p.H[k][c], xn[c], acc);
     d[k] = r_sub(y[k], acc);
   }
-  T quad = 0;
+  V quad = V();
 #pragma unroll
   for (int k = 0; k < NY; ++k) {
-    T t = r_mul(p.Rinv[k][0], d[0]);
+    V t = r_mul(p.Rinv[k][0], d[0]);
 #pragma unroll
     for (int l = 1; l < NY; ++l) t = r_fma(p.Rinv[k][l], d[l], t);
     quad = (k == 0) ? r_mul(d[0], t) : r_fma(d[k], t, quad);
@@ -74,8 +82,8 @@ __device__ __forceinline__ T lg_logweight(const LgDevT<T>& p, const T* xn, const
 
 // position/velocity structured variants (LgDev::kron): same operations as the dense code minus the
 // terms whose coefficient is zero
-template <int NX, class T>
-__device__ __forceinline__ void kron_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
+template <int NX, class T, class V>
+__device__ __forceinline__ void kron_propagate(const LgDevT<T>& p, const V* x, const V* z, V* xn) {
   if constexpr (NX == 1) {  // F = 1: fl(1 * x) = x, so fma(L, z, fl(F x)) = fma(L, z, x)
     xn[0] = r_fma(p.klp, z[0], x[0]);
     return;
@@ -83,37 +91,37 @@ __device__ __forceinline__ void kron_propagate(const LgDevT<T>& p, const T* x, c
   constexpr int P = NX / 2;
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    T acc = r_mul(p.ka, x[i]);
+    V acc = r_mul(p.ka, x[i]);
     acc = r_fma(p.kb, x[P + i], acc);
     xn[i] = r_fma(p.klp, z[i], acc);
   }
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    T acc;
+    V acc;
     if (p.kc != (T)0) { acc = r_mul(p.kc, x[i]); acc = r_fma(p.kd, x[P + i], acc); }
     else acc = r_mul(p.kd, x[P + i]);
     xn[P + i] = r_fma(p.klv, z[P + i], acc);
   }
 }
 
-template <int NX, int NY, class T>
-__device__ __forceinline__ T kron_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
-  T quad = 0;
+template <int NX, int NY, class T, class V>
+__device__ __forceinline__ V kron_logweight(const LgDevT<T>& p, const V* xn, const T* y) {
+  V quad = V();
 #pragma unroll
   for (int k = 0; k < NY; ++k) {
-    const T d = r_sub(y[k], xn[k]);
-    const T t = r_mul(p.krinv, d);
+    const V d = r_sub(y[k], xn[k]);
+    const V t = r_mul(p.krinv, d);
     quad = (k == 0) ? r_mul(d, t) : r_fma(d, t, quad);
   }
   return r_mul(p.wscale, quad);
 }
 
-template <int NX, bool KRON, class T>
-__device__ __forceinline__ void model_propagate(const LgDevT<T>& p, const T* x, const T* z, T* xn) {
+template <int NX, bool KRON, class T, class V>
+__device__ __forceinline__ void model_propagate(const LgDevT<T>& p, const V* x, const V* z, V* xn) {
   if constexpr (KRON) kron_propagate<NX>(p, x, z, xn); else lg_propagate<NX>(p, x, z, xn);
 }
-template <int NX, int NY, bool KRON, class T>
-__device__ __forceinline__ T model_logweight(const LgDevT<T>& p, const T* xn, const T* y) {
+template <int NX, int NY, bool KRON, class T, class V>
+__device__ __forceinline__ V model_logweight(const LgDevT<T>& p, const V* xn, const T* y) {
   if constexpr (KRON) return kron_logweight<NX, NY>(p, xn, y); else return lg_logweight<NX, NY>(p, xn, y);
 }
 

@@ -124,7 +124,10 @@ struct MttArgs {
   const CtlDev* ctl;
   unsigned long long* overflow;  // counter of dropped births
   double* part;          // [gridDim.x][5]: per-CTA (max lw, sum w, sum w^2, sum w c, sum w c^2), w = exp(lw - max)
-  int64_t n;
+  int64_t n;             // end of this launch's particle range (global index)
+  int64_t j0;            // its start; sout and part are indexed relative to it
+  int64_t n_per;         // multi-device: particles per device (parents are read from their owners); 0: single device
+  const uint32_t* sin_all[kMttMaxDevices];
   int32_t n_obs;
   uint64_t seed;
   MttDev p;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     s_ln[tid] = a.p.lb * __expf(a.p.nb_norm - 0.5f * r2 / (a.p.bp + a.p.r));
   }
   __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * kMttThreads + tid;
+  const int64_t j = a.j0 + (int64_t)blockIdx.x * kMttThreads + tid;
   float out_lw = -INFINITY, out_cnt = 0.f;  // this particle's log-weight and track count (summary below)
   do {
   if (j >= a.n) break;
@@ -227,8 +230,12 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   const DerLocal dl{loc};
   const uint32_t t = a.ctl->t;
   const int64_t par = a.anc[j];
-  const uint32_t* __restrict__ src = a.sin + (size_t)par * kMttWords;
-  uint32_t* __restrict__ dst = a.sout + (size_t)j * kMttWords;
+  const uint32_t* __restrict__ src;
+  if (a.n_per) {   // the parent's record lives on the device that owns it (peer load over NVLink when it is not this one)
+    const int64_t owner = par / a.n_per;
+    src = a.sin_all[owner] + (size_t)(par - owner * a.n_per) * kMttWords;
+  } else src = a.sin + (size_t)par * kMttWords;
+  uint32_t* __restrict__ dst = a.sout + (size_t)(j - a.j0) * kMttWords;
   const uint4 hdr = *reinterpret_cast<const uint4*>(src);
   const int cnt = (int)hdr.x;
   const int cnt_fast = cnt < kMttFast ? cnt : kMttFast;
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
 // combine the per-CTA partials (log-sum-exp over their maxima) into the step summary
 constexpr int kFinalThreads = 1024, kFinalWarps = kFinalThreads / 32;
 __global__ void __launch_bounds__(kFinalThreads) mtt_summary_final(PlanDev* pl, const CtlDev* ctl, pz_step_summary* summ, int64_t n,
-                                                              double ll_const, const unsigned long long* overflow,
+                                                              double ll_const, const unsigned long long* overflow, int n_ovf,
                                                               const double* __restrict__ part, int32_t ncta) {
   __shared__ double s_m[kFinalWarps], s_v[kFinalWarps][4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -408,7 +415,9 @@ __global__ void __launch_bounds__(kFinalThreads) mtt_summary_final(PlanDev* pl, 
   o->ess = sw * sw / sw2;
   o->n_migrated = 0;
   o->e_max = pl->emax;
-  o->reserved = (int32_t)(*overflow > 0x7fffffffull ? 0x7fffffff : *overflow);
+  unsigned long long ovf = 0;
+  for (int i = 0; i < n_ovf; ++i) ovf += overflow[i];
+  o->reserved = (int32_t)(ovf > 0x7fffffffull ? 0x7fffffff : ovf);
   o->total_weight = pl->total;
 }
 
@@ -419,6 +428,17 @@ __global__ void mtt_gather_thin(const uint32_t* __restrict__ s, const int32_t* _
   if (sel >= n_sel) return;
   const int64_t p = anc[sel * stride];
   for (int w = threadIdx.x & 31; w < kMttWords; w += 32) out[(size_t)sel * kMttWords + w] = s[(size_t)p * kMttWords + w];
+}
+
+// the same on a multi-device tracker: the parent's record is read from the device that owns it
+__global__ void mtt_gather_thin_multi(MttShard sh, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
+                                      uint32_t* __restrict__ out) {
+  const int64_t sel = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (sel >= n_sel) return;
+  const int64_t p = anc[sel * stride];
+  const int64_t owner = p / sh.n_per;
+  const uint32_t* s = sh.sin_all[owner] + (size_t)(p - owner * sh.n_per) * kMttWords;
+  for (int w = threadIdx.x & 31; w < kMttWords; w += 32) out[(size_t)sel * kMttWords + w] = s[w];
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -454,9 +474,15 @@ int mtt_step_ctas(int64_t n) { return (int)((n + kMttThreads - 1) / kMttThreads)
 
 int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
-                    cudaStream_t s) {
+                    cudaStream_t s, const MttShard* shard) {
   MttArgs a;
   a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
+  a.j0 = 0; a.n_per = 0;
+  for (int i = 0; i < kMttMaxDevices; ++i) a.sin_all[i] = nullptr;
+  if (shard) {
+    a.j0 = shard->j0; a.n = shard->j_end; a.n_per = shard->n_per;
+    for (int i = 0; i < kMttMaxDevices; ++i) a.sin_all[i] = shard->sin_all[i];
+  }
   a.n_obs = n_obs;
   a.seed = seed; a.p = *reinterpret_cast<const MttDev*>(params);
   const size_t smem = (size_t)kMttDerived * kMttFast * kMttThreads * sizeof(float);  // 28 KB
@@ -468,13 +494,19 @@ int launch_mtt_step(const void* params, const uint32_t* sin, uint32_t* sout, con
     cudaFuncSetAttribute(mtt_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done.fetch_or(bit, std::memory_order_release);
   }
-  mtt_step<<<(unsigned)((n + kMttThreads - 1) / kMttThreads), kMttThreads, smem, s>>>(a);
+  mtt_step<<<(unsigned)((a.n - a.j0 + kMttThreads - 1) / kMttThreads), kMttThreads, smem, s>>>(a);
   return 1;
 }
 
 int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDev* ctl, pz_step_summary* summ, double ll_const,
-                       const unsigned long long* overflow, cudaStream_t s) {
-  mtt_summary_final<<<1, kFinalThreads, 0, s>>>(plan, ctl, summ, n, ll_const, overflow, part, mtt_step_ctas(n));
+                       const unsigned long long* overflow, cudaStream_t s, int n_ovf) {
+  mtt_summary_final<<<1, kFinalThreads, 0, s>>>(plan, ctl, summ, n, ll_const, overflow, n_ovf, part, mtt_step_ctas(n));
+  return 1;
+}
+
+int launch_mtt_gather_multi(const MttShard& sh, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
+  const int per_cta = kThreads / 32;
+  mtt_gather_thin_multi<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sh, anc, stride, n_sel, out);
   return 1;
 }
 

@@ -242,3 +242,43 @@ def test_gpu_tracker_long_stream_stays_symmetric_psd_and_on_the_oracle_evidence(
         zs.close()
     se = np.sqrt(glz.var(ddof=1) / seeds + clz.var(ddof=1) / seeds)
     assert abs(glz.mean() - clz.mean()) < 4 * se + 0.05 * Tz / 100, (glz, clz)
+
+
+def _tracker_runs_equal(pz, devices, n, steps, stride):
+    d, obs, truth = H.mtt_scenario(steps)
+    one = pz.zparticles(n, pz.mtt(), seed=5)
+    many = pz.zparticles_multi(n, pz.mtt(), devices, seed=5)
+    assert many.n == n
+    for t, o in enumerate(obs):
+        a, b = one.step(o), many.step(o)
+        for k in ("total_weight", "e_max", "ess", "log_evidence_inc", "step"):
+            assert getattr(a, k) == getattr(b, k), (t, k, getattr(a, k), getattr(b, k))
+        assert a.mean[0] == b.mean[0] and a.var[0] == b.var[0], t
+    ta, tb = one.read_tracks(stride=stride), many.read_tracks(stride=stride)
+    assert len(ta) == len(tb)
+    for pa, pb in zip(ta, tb):
+        assert [i for i, _, _ in pa] == [i for i, _, _ in pb]
+        for (_, ma, ca), (_, mb, cb) in zip(pa, pb):
+            assert np.array_equal(ma, mb) and np.array_equal(ca, cb)
+    one.close(); many.close()
+
+
+@pytest.mark.gpu
+def test_multi_device_tracker_equals_single_device(pz):
+    """configs[4] 'sharded tracker': the tracker over 2 devices of one process (pz_filter_create_multi) -- own output tiles
+    per device, parent records read from their owners, block statistics all-gathered by peer stores -- equals the
+    one-device run bit for bit: summaries every step, track records at the end."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _tracker_runs_equal(pz, [0, 1], 50000, 25, 41)
+
+
+@pytest.mark.gpu
+def test_sharded_tracker_path_on_one_device(pz, monkeypatch):
+    """The same sharded code path with 3 shards sharing device 0 (test hook PZ_MULTI_SAME_DEVICE): every kernel, push and
+    event dependency of the multi-device tracker runs on a one-GPU box and must reproduce the unsharded bits."""
+    monkeypatch.setenv("PZ_MULTI_SAME_DEVICE", "1")
+    _tracker_runs_equal(pz, [0, 0, 0], 30000, 20, 29)
+    with pytest.raises(pz.PzError):   # too few particles for the device count (whole 2048-slot tiles per device)
+        pz.zparticles_multi(3000, pz.mtt(), [0, 0, 0], seed=1)
