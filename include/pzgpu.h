@@ -59,9 +59,15 @@ enum {
   PZ_MODEL_MTT = 3,      /* Examples/MultiTargetTracking.hs:26-145                                   */
   PZ_MODEL_WALKER = 4,   /* Examples/Walker.hs:20-148: hybrid discrete / continuous walker under the MStream
                             `particles` filter (Inference.hs:73-86): weights carried across resampling          */
-  PZ_MODEL_BETA_BERNOULLI = 5 /* Examples/DelayedSamplingAbstract.hs:57-69 betaBernoulli under delayed sampling:
+  PZ_MODEL_BETA_BERNOULLI = 5, /* Examples/DelayedSamplingAbstract.hs:57-69 betaBernoulli under delayed sampling:
                             Beta prior, Bernoulli observations, conjugate update (DelayedSampling.hs:140,150-151;
                             SymbolicDistr.hs:165-188)                                                         */
+  PZ_MODEL_MULTICAM = 6  /* Examples/MultiCamera.hs:40-227: two cameras, box tracks over R^4 (F = H = I), appearance
+                            marginals over R^10 shared by the tracks of one identity, per-camera association with the
+                            custom proposal (:162-180).  nx = 4, ny = 0 (H = I, R = meas_var I implied).  Uses F / Q / x0 (box prior and clutter mean) and the
+                            `mtt` block (clutter_lambda per camera, new_track_lambda, survival_prob, birth_pos_var /
+                            birth_vel_var = box prior variances, meas_var; pd = 1).  Observation rows are 16 doubles:
+                            camera, pose[10], box[4], appearance reading                                          */
 };
 
 enum {
@@ -160,6 +166,7 @@ PZ_API int pz_model_rw1d(pz_model_desc* d, double q_var, double r_var);       /*
 PZ_API int pz_model_stt(pz_model_desc* d);                                    /* SingleTargetTracking.hs:39-54 */
 PZ_API int pz_model_mtt_track(pz_model_desc* d);                              /* MultiTargetTracking.hs:56-73  */
 PZ_API int pz_model_mtt(pz_model_desc* d);                                    /* MultiTargetTracking.hs:36-145 */
+PZ_API int pz_model_multicam(pz_model_desc* d);                               /* MultiCamera.hs:40-227 */
 PZ_API int pz_model_walker(pz_model_desc* d);                                 /* Walker.hs:20-148 (carry_weights = 1) */
 PZ_API int pz_model_beta_bernoulli(pz_model_desc* d, double a, double b);     /* DelayedSamplingAbstract.hs:57-69 (delayed = 1) */
 
@@ -214,6 +221,15 @@ PZ_API int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, i
  * count_out[i], id_out[i*16+k] (-1 past the count), mean_out[(i*16+k)*4..], cov_out[(i*16+k)*16..]. */
 PZ_API int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, double* mean_out,
                                  double* cov_out, int64_t n_sel_cap);
+
+/* MultiCamera tracker (PZ_MODEL_MULTICAM) output: for every `stride`-th resampled particle the list of `MarginalTrack`
+ * that processObservationsStream returns (MultiCamera.hs:208-216): count_out[i]; per track slot k < 16 (-1 / 0 past the
+ * count): id_out (trackID), identity_out (index into the particle's appearances), camera_out, start_out (startTime, may
+ * be NULL), mean_out[(i*16+k)*4..] and var_out[(i*16+k)*4..] (the box marginal: its covariance is diagonal);
+ * n_app_out[i] (may be NULL); app_mean_out[(i*16+a)*10..] and app_cov_out[(i*16+a)*100..] (both NULL or both given).     */
+PZ_API int pz_filter_read_mcam_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, int32_t* identity_out,
+                                      int32_t* camera_out, double* start_out, double* mean_out, double* var_out,
+                                      int32_t* n_app_out, double* app_mean_out, double* app_cov_out, int64_t n_sel_cap);
 
 /* Delayed-sampling filters (model.delayed = 1): the Gaussian marginal every particle carries,
  * `MDistr` (mean[nx], cov[nx*nx] row-major) -- what the reference serialises per particle as

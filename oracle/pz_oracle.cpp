@@ -1508,3 +1508,304 @@ int pzo_mtt_generate(const pz_model_desc* d, uint64_t seed, int64_t T, int32_t m
 }
 
 }  // extern "C"
+
+// =========================================================================================
+// MultiCamera tracker (Examples/MultiCamera.hs:40-227), restated in double with FULL matrices (the CUDA kernel
+// uses the diagonal structure F = H = I, diagonal Q / R / prior imply; this file does not).
+//
+// Per particle: a list of tracks (box marginal over R^4, trackID, identity, camera, startTime) and a growing list of
+// appearance marginals over R^10 shared by the tracks of one identity: the heap of zdsparticles (:224) reduced to
+// Kalman recursions:
+//   trackSurvivalMotion (:118-126)  survive ~ Bernoulli(exp(-deathRate tdiff)); posWH' ~ N(I posWH, diag(1,1,.1,.1)) -> predict
+//   tracksMotion        (:183-195)  births ~ Poisson(birthRate tdiff); newTrack (:96-108): camera ~ U{0,1},
+//                                   new appearance with probability 1/(A+1) (prior N(0, I10)) else identity ~ U{0..A-1};
+//                                   box prior N((0,0,1,1), diag(1,1,.2,.2)) (:88-94)
+//   trackMeasurement    (:128-132)  box ~ N(posWH, I4), pose ~ uniformNSphere, appear ~ N(pose . appearance, 1)
+//   assocWithClutterCustomProposal (:162-180), per camera, tracks in list order: lls over the remaining observations,
+//                                   i ~ categorical(lls / total), condition on observation i, weight *= total
+//                                   (likelihood times the proposal correction 1 / adjLL_i); no observation left for a
+//                                   track -> passert False (weight 0); the rest is clutter: count prior
+//                                   -(lgamma(nT + nC + 1) - lgamma(nC + 1)), Poisson(1) count, clutter densities
+//                                   box ~ N((0,0,1,1), I4), pose ~ N(0, I10), appear ~ N(0, 1) (:169-176, 182-189)
+// Observation row: 16 doubles (camera, pose[10], box[4], appear).
+// =========================================================================================
+namespace {
+
+constexpr uint32_t kStreamMcam = 0x4D43414Du;     // "MCAM"
+constexpr uint32_t kStreamMcamGen = 0x4D434147u;  // "MCAG"
+constexpr int kMcD = 10, kMcObsW = 16, kMcCams = 2;
+
+struct McTrack { int id, identity, camera; double start; double m[4]; double P[4][4]; };
+struct McApp { double m[kMcD]; double P[kMcD][kMcD]; };
+struct McConst {
+  double Q[4], ps, lb, lc, prior_m[4], prior_v[4], clutter_m[4], r_box, r_app;
+  int kmax, amax;
+};
+McConst mcam_const(const pz_model_desc* d) {
+  McConst c;
+  for (int i = 0; i < 4; ++i) { c.Q[i] = d->Q[i * 4 + i]; c.prior_m[i] = d->x0[i]; c.clutter_m[i] = d->x0[i]; }
+  c.prior_v[0] = c.prior_v[1] = d->mtt.birth_pos_var; c.prior_v[2] = c.prior_v[3] = d->mtt.birth_vel_var;
+  c.ps = d->mtt.survival_prob; c.lb = d->mtt.new_track_lambda; c.lc = d->mtt.clutter_lambda;
+  c.r_box = d->mtt.meas_var; c.r_app = 1.0;
+  c.kmax = d->mtt.k_max; c.amax = 16;
+  return c;
+}
+
+// log N(x; mu, S) for a dense symmetric positive definite S (mvNormal_ll0, MVDistributions.hs:45-46) by Cholesky
+template <int N>
+double ll_dense(const double* x, const double* mu, const double (*S)[N]) {
+  double L[N][N] = {};
+  double logdet = 0;
+  for (int j = 0; j < N; ++j) {
+    double s = S[j][j]; for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    L[j][j] = sqrt(s); logdet += 2 * log(L[j][j]);
+    for (int i = j + 1; i < N; ++i) { double t = S[i][j]; for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k]; L[i][j] = t / L[j][j]; }
+  }
+  double y[N], quad = 0;
+  for (int i = 0; i < N; ++i) { double t = x[i] - mu[i]; for (int k = 0; k < i; ++k) t -= L[i][k] * y[k]; y[i] = t / L[i][i]; quad += y[i] * y[i]; }
+  return -0.5 * (quad + logdet + N * log(2 * M_PI));
+}
+
+// logNSphereVolume (MVDistributions.hs:64-66)
+double log_nsphere_volume(int n) { return log((double)n) + n / 2.0 * log(M_PI) - lgamma(n / 2.0 + 1); }
+
+double mc_score(const McConst& c, const McTrack& t, const McApp& a, const double* row) {
+  const double* h = row + 1; const double* box = row + 11; const double app = row[15];
+  double S[4][4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = t.P[i][j] + (i == j ? c.r_box : 0.0);
+  double ll = ll_dense<4>(box, t.m, S);
+  ll += -log_nsphere_volume(kMcD);
+  double hm = 0, hPh = 0;
+  for (int i = 0; i < kMcD; ++i) { hm += h[i] * a.m[i]; for (int j = 0; j < kMcD; ++j) hPh += h[i] * a.P[i][j] * h[j]; }
+  const double s = hPh + c.r_app, d = app - hm;
+  ll += -0.5 * (d * d / s + log(s) + log(2 * M_PI));
+  return ll;
+}
+
+// kalmanUpdate (MVDistributions.hs:83-100) with H = I4, R = r I4: gain by Gaussian elimination on S = P + R
+void mc_update_box(const McConst& c, McTrack& t, const double* box) {
+  double S[4][8];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { S[i][j] = t.P[i][j] + (i == j ? c.r_box : 0.0); S[i][4 + j] = (i == j); }
+  for (int p = 0; p < 4; ++p) {
+    const double piv = S[p][p];
+    for (int j = 0; j < 8; ++j) S[p][j] /= piv;
+    for (int i = 0; i < 4; ++i) if (i != p) { const double f = S[i][p]; for (int j = 0; j < 8; ++j) S[i][j] -= f * S[p][j]; }
+  }
+  double K[4][4], y[4], Pn[4][4];
+  for (int i = 0; i < 4; ++i) { y[i] = box[i] - t.m[i]; for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += t.P[i][k] * S[k][4 + j]; K[i][j] = s; } }
+  for (int i = 0; i < 4; ++i) { double s = 0; for (int j = 0; j < 4; ++j) s += K[i][j] * y[j]; t.m[i] += s; }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += K[i][k] * t.P[k][j]; Pn[i][j] = t.P[i][j] - s; }
+  memcpy(t.P, Pn, sizeof(Pn));
+}
+void mc_update_app(const McConst& c, McApp& a, const double* h, double obs) {
+  double Ph[kMcD], hm = 0, s = c.r_app;
+  for (int i = 0; i < kMcD; ++i) { double t = 0; for (int j = 0; j < kMcD; ++j) t += a.P[i][j] * h[j]; Ph[i] = t; hm += h[i] * a.m[i]; }
+  for (int i = 0; i < kMcD; ++i) s += h[i] * Ph[i];
+  const double d = obs - hm;
+  for (int i = 0; i < kMcD; ++i) a.m[i] += Ph[i] / s * d;
+  for (int i = 0; i < kMcD; ++i) for (int j = 0; j < kMcD; ++j) a.P[i][j] -= Ph[i] * Ph[j] / s;
+}
+
+int mc_poisson(double lambda, double u) {   // inverse CDF on one uniform
+  int k = 0; double p = exp(-lambda), F = p;
+  while (u >= F && k < 64) { ++k; p *= lambda / k; F += p; }
+  return k;
+}
+
+struct OMcam {
+  pz_model_desc desc; McConst c;
+  int64_t n; uint64_t seed; uint32_t t = 0;
+  std::vector<std::vector<McTrack>> tr;
+  std::vector<std::vector<McApp>> apps;
+  std::vector<int> num_tracks;
+  std::vector<float> lw;
+  std::vector<int32_t> anc;
+  int64_t overflow = 0;
+};
+
+double mcam_particle_step(const McConst& c, std::vector<McTrack>& tracks, std::vector<McApp>& apps, int& num_tracks, double t_now,
+                          const double* obs, int M, U01& rng, int64_t* overflow) {
+  std::vector<McTrack> live;
+  for (auto& t : tracks)
+    if (rng.next() < c.ps) { for (int i = 0; i < 4; ++i) t.P[i][i] += c.Q[i]; live.push_back(t); }   // F = I
+  const int n_new = mc_poisson(c.lb, rng.next());
+  for (int i = 0; i < n_new; ++i) {
+    const double u_cam = rng.next(), u_new = rng.next(), u_id = rng.next();
+    int cam = (int)(u_cam * kMcCams); cam = cam < kMcCams ? cam : kMcCams - 1;
+    const int A = (int)apps.size();
+    bool fresh = u_new < 1.0 / (A + 1);
+    if (fresh && A >= c.amax) { fresh = false; ++*overflow; }
+    int identity;
+    if (fresh) {
+      McApp a; for (int x = 0; x < kMcD; ++x) { a.m[x] = 0; for (int y = 0; y < kMcD; ++y) a.P[x][y] = (x == y); }
+      apps.push_back(a); identity = A;
+    } else { identity = (int)(u_id * A); identity = identity < A ? identity : A - 1; }
+    if ((int)live.size() < c.kmax) {
+      McTrack t; t.id = num_tracks + 1 + i; t.identity = identity; t.camera = cam; t.start = t_now;
+      for (int x = 0; x < 4; ++x) { t.m[x] = c.prior_m[x]; for (int y = 0; y < 4; ++y) t.P[x][y] = (x == y) ? c.prior_v[x] : 0.0; }
+      live.push_back(t);
+    } else ++*overflow;
+  }
+  num_tracks += n_new;
+  double lw = 0;
+  bool dead = false;
+  for (int cam = 0; cam < kMcCams && !dead; ++cam) {
+    std::vector<int> idx;
+    for (int j = 0; j < M; ++j) if ((int)obs[j * kMcObsW] == cam) idx.push_back(j);
+    int nT = 0;
+    for (auto& t : live) {
+      if (t.camera != cam) continue;
+      ++nT;
+      if (idx.empty()) { dead = true; break; }   // passert False (:168-169)
+      std::vector<double> ll(idx.size());
+      double mx = -INFINITY;
+      for (size_t q = 0; q < idx.size(); ++q) { ll[q] = mc_score(c, t, apps[t.identity], obs + idx[q] * kMcObsW); mx = std::max(mx, ll[q]); }
+      double total = 0; for (double v : ll) total += exp(v - mx);
+      const double target = rng.next() * total;
+      size_t pick = idx.size() - 1; double cum = 0;
+      for (size_t q = 0; q < idx.size(); ++q) { cum += exp(ll[q] - mx); if (cum > target) { pick = q; break; } }
+      lw += mx + log(total);   // likelihood of the pick times the proposal correction total / like_pick
+      const double* row = obs + idx[pick] * kMcObsW;
+      mc_update_box(c, t, row + 11);
+      mc_update_app(c, apps[t.identity], row + 1, row[15]);
+      idx.erase(idx.begin() + pick);
+    }
+    if (dead) break;
+    const int nC = (int)idx.size();
+    lw += -(lgamma(nT + nC + 1.0) - lgamma(nC + 1.0));
+    lw += -c.lc + nC * log(c.lc) - lgamma(nC + 1.0);
+    for (int j : idx) {
+      const double* row = obs + j * kMcObsW;
+      double q4 = 0, q10 = 0;
+      for (int i = 0; i < 4; ++i) { const double d = row[11 + i] - c.clutter_m[i]; q4 += d * d; }
+      for (int i = 0; i < kMcD; ++i) q10 += row[1 + i] * row[1 + i];
+      lw += -0.5 * (q4 + 4 * log(2 * M_PI)) - 0.5 * (q10 + kMcD * log(2 * M_PI)) - 0.5 * (row[15] * row[15] + log(2 * M_PI));
+    }
+  }
+  tracks.swap(live);
+  return dead ? -INFINITY : lw;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* pzo_mcam_create(const pz_model_desc* d, int64_t n, uint64_t seed) {
+  OMcam* f = new OMcam();
+  f->desc = *d; f->c = mcam_const(d); f->n = n; f->seed = seed;
+  f->tr.resize(n); f->apps.resize(n); f->num_tracks.assign(n, 0); f->lw.assign(n, 0.0f); f->anc.assign(n, 0);
+  return f;
+}
+void pzo_mcam_destroy(void* h) { delete (OMcam*)h; }
+
+// one filter step (obs: n_obs rows of 16); outputs as pzo_mtt_step
+int pzo_mcam_step(void* h, const double* obs, int32_t n_obs, double* mean_cnt, double* var_cnt, double* logz) {
+  OMcam* f = (OMcam*)h;
+  ResamplePlan pl;
+  if (!build_plan(f->lw.data(), f->n, f->n, &pl)) return PZ_EDEGENERATE;
+  systematic_ancestors(pl, pzo_resample_uniform(f->seed, f->t), f->n, f->anc.data());
+  std::vector<std::vector<McTrack>> ntr(f->n);
+  std::vector<std::vector<McApp>> nap(f->n);
+  std::vector<int> nnt(f->n);
+  std::vector<double> lwd(f->n);
+  for (int64_t j = 0; j < f->n; ++j) {
+    ntr[j] = f->tr[f->anc[j]]; nap[j] = f->apps[f->anc[j]]; nnt[j] = f->num_tracks[f->anc[j]];
+    U01 rng(f->seed, (uint32_t)j, f->t, kStreamMcam);
+    lwd[j] = mcam_particle_step(f->c, ntr[j], nap[j], nnt[j], (double)f->t, obs, n_obs, rng, &f->overflow);
+    f->lw[j] = (float)lwd[j];
+  }
+  f->tr.swap(ntr); f->apps.swap(nap); f->num_tracks.swap(nnt);
+  double mx = -INFINITY; for (double v : lwd) mx = std::max(mx, v);
+  if (!(mx > -INFINITY)) { f->t += 1; return PZ_EDEGENERATE; }
+  double sw = 0, sc = 0, scc = 0;
+  for (int64_t j = 0; j < f->n; ++j) { double w = exp(lwd[j] - mx), c = (double)f->tr[j].size(); sw += w; sc += w * c; scc += w * c * c; }
+  if (mean_cnt) *mean_cnt = sc / sw;
+  if (var_cnt) *var_cnt = scc / sw - (sc / sw) * (sc / sw);
+  if (logz) *logz = mx + log(sw / f->n);
+  f->t += 1;
+  return 0;
+}
+
+void pzo_mcam_logw(void* h, float* out) { OMcam* f = (OMcam*)h; memcpy(out, f->lw.data(), f->n * sizeof(float)); }
+
+// tracks of particle i: returns the count; ids / identity / camera [k], mean[k*4..], cov[k*16..]; *n_app = its appearance count
+int pzo_mcam_particle(void* h, int64_t i, int32_t* ids, int32_t* identity, int32_t* camera, double* mean, double* cov, int32_t* n_app) {
+  OMcam* f = (OMcam*)h;
+  const auto& v = f->tr[i];
+  for (size_t k = 0; k < v.size(); ++k) {
+    ids[k] = v[k].id; identity[k] = v[k].identity; camera[k] = v[k].camera;
+    for (int a = 0; a < 4; ++a) { mean[k * 4 + a] = v[k].m[a]; for (int b = 0; b < 4; ++b) cov[k * 16 + a * 4 + b] = v[k].P[a][b]; }
+  }
+  if (n_app) *n_app = (int32_t)f->apps[i].size();
+  return (int)v.size();
+}
+// appearance a of particle i: mean[10], cov[100]
+int pzo_mcam_appearance(void* h, int64_t i, int32_t a, double* mean, double* cov) {
+  OMcam* f = (OMcam*)h;
+  if (a < 0 || a >= (int)f->apps[i].size()) return -1;
+  const McApp& ap = f->apps[i][a];
+  for (int x = 0; x < kMcD; ++x) { mean[x] = ap.m[x]; for (int y = 0; y < kMcD; ++y) cov[x * kMcD + y] = ap.P[x][y]; }
+  return 0;
+}
+
+// Ground truth + observations: zstepGen under MP.sim (generateGroundTruth, MultiCamera.hs:197-219).
+// obs_out [T][m_max][16]; n_obs_out[T]; truth_out [T][k_max][7] = (id, identity, camera, box[4]); n_truth_out[T].
+// (The reference shuffles each camera's list; the filter's result does not depend on the order only in
+// distribution, so the shuffle is kept.)
+int pzo_mcam_generate(const pz_model_desc* d, uint64_t seed, int64_t T, int32_t m_max, double* obs_out, int32_t* n_obs_out,
+                      double* truth_out, int32_t* n_truth_out) {
+  const McConst c = mcam_const(d);
+  struct Tr { int id, identity, camera; double x[4]; };
+  std::vector<Tr> tracks; std::vector<std::vector<double>> apps; int num_tracks = 0;
+  for (int64_t t = 0; t < T; ++t) {
+    U01 rng(seed, 0, (uint32_t)t, kStreamMcamGen);
+    std::vector<Tr> live;
+    for (auto& tr : tracks) if (rng.next() < c.ps) { for (int i = 0; i < 4; ++i) tr.x[i] += sqrt(c.Q[i]) * rng.normal(); live.push_back(tr); }
+    const int n_new = mc_poisson(c.lb, rng.next());
+    for (int i = 0; i < n_new; ++i) {
+      Tr nt; nt.id = num_tracks + 1 + i;
+      int cam = (int)(rng.next() * kMcCams); nt.camera = cam < kMcCams ? cam : kMcCams - 1;
+      const int A = (int)apps.size();
+      if (rng.next() < 1.0 / (A + 1) && A < c.amax) { std::vector<double> a(kMcD); for (auto& v : a) v = rng.normal(); apps.push_back(a); nt.identity = A; }
+      else { int id = (int)(rng.next() * A); nt.identity = id < A ? id : A - 1; }
+      for (int x = 0; x < 4; ++x) nt.x[x] = c.prior_m[x] + sqrt(c.prior_v[x]) * rng.normal();
+      if ((int)live.size() < c.kmax) live.push_back(nt);
+    }
+    num_tracks += n_new;
+    tracks.swap(live);
+    int M = 0;
+    for (int cam = 0; cam < kMcCams; ++cam) {
+      std::vector<std::vector<double>> rows;
+      for (auto& tr : tracks) {
+        if (tr.camera != cam) continue;
+        std::vector<double> row(kMcObsW); row[0] = cam;
+        double nrm = 0; for (int i = 0; i < kMcD; ++i) { row[1 + i] = rng.normal(); nrm += row[1 + i] * row[1 + i]; }
+        nrm = sqrt(nrm); double hm = 0;
+        for (int i = 0; i < kMcD; ++i) { row[1 + i] /= nrm; hm += row[1 + i] * apps[tr.identity][i]; }
+        for (int i = 0; i < 4; ++i) row[11 + i] = tr.x[i] + sqrt(c.r_box) * rng.normal();
+        row[15] = hm + sqrt(c.r_app) * rng.normal();
+        rows.push_back(row);
+      }
+      const int nC = mc_poisson(c.lc, rng.next());
+      for (int q = 0; q < nC; ++q) {
+        std::vector<double> row(kMcObsW); row[0] = cam;
+        for (int i = 0; i < kMcD; ++i) row[1 + i] = rng.normal();
+        for (int i = 0; i < 4; ++i) row[11 + i] = c.clutter_m[i] + rng.normal();
+        row[15] = rng.normal();
+        rows.push_back(row);
+      }
+      for (size_t i = rows.size(); i > 1; --i) { size_t j = (size_t)(rng.next() * i); std::swap(rows[i - 1], rows[j < i ? j : i - 1]); }
+      for (auto& row : rows) { if (M >= m_max) break; memcpy(obs_out + (t * m_max + M) * kMcObsW, row.data(), kMcObsW * sizeof(double)); ++M; }
+    }
+    n_obs_out[t] = M;
+    n_truth_out[t] = (int)tracks.size();
+    for (size_t k = 0; k < tracks.size(); ++k) {
+      double* o = truth_out + (t * c.kmax + k) * 7;
+      o[0] = tracks[k].id; o[1] = tracks[k].identity; o[2] = tracks[k].camera;
+      for (int a = 0; a < 4; ++a) o[3 + a] = tracks[k].x[a];
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -352,6 +352,9 @@ struct pz_filter {
   double* mtt_part = nullptr;                // per-CTA summary partials of mtt_step
   std::vector<char> mtt_params;
   int32_t mtt_mmax = 0;
+  bool is_mcam = false;                      // the MultiCamera tracker: same host path, its own record and step kernel
+  int tracker_words = 0;                     // 32-bit words per particle record
+  int tracker_obs_w = 2;                     // doubles per observation row (2: MTT detections; 16: MultiCamera rows)
   // multi-device tracker (a shard of a pz_filter_create_multi tracker): this device owns particles [mtt_j0, mtt_jend) of
   // the global population; the gathered arrays (16-bit weights, block exponents / sums, summary partials, dropped-birth
   // counters) exist once per step parity, so that a peer's push of step t+1 never lands in what step t still reads
@@ -715,7 +718,16 @@ int mtt_plan(pz_filter* f, int delta, double ll_const) {
 // arrays cover the whole population (every device derives the global plan from the gathered block statistics)
 int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device, pz_filter** out, int rank = 0, int world = 1,
                int64_t per = 0) {
-  if (model->nx != 4 || model->ny != 2) return fail(PZ_EINVAL, "the MTT descriptor needs the (4,2) track model");
+  const bool mcam = model->kind == PZ_MODEL_MULTICAM;
+  if (!mcam && (model->nx != 4 || model->ny != 2)) return fail(PZ_EINVAL, "the MTT descriptor needs the (4,2) track model");
+  if (mcam) {
+    if (model->nx != 4 || model->ny != 0) return fail(PZ_EINVAL, "the MultiCamera descriptor has a 4-dimensional box state (ny = 0: H = I and R = meas_var I are implied)");
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        if (model->F[i * 4 + j] != (i == j ? 1.0 : 0.0) || (i != j && model->Q[i * 4 + j] != 0.0))
+          return fail(PZ_EINVAL, "the MultiCamera kernel takes F = I and a diagonal Q (MultiCamera.hs:110-116)");
+    if (model->mtt.pd != 1.0) return fail(PZ_EINVAL, "MultiCamera: every live track is observed (pd = 1)");
+  }
   if (model->mtt.k_max != 16) return fail(PZ_EINVAL, "k_max must be 16 (one lane per track slot)");
   if (model->mtt.m_max < 1 || model->mtt.m_max > 32) return fail(PZ_EINVAL, "m_max must be in [1, 32]");
   if (n < 1 || n > (1ull << 28)) return fail(PZ_EINVAL, "n_particles must be in [1, 2^28] for the tracker");
@@ -727,6 +739,7 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   pz_filter* f = new (std::nothrow) pz_filter();
   if (!f) return fail(PZ_ENOMEM, "out of host memory");
   f->desc = *model; f->device = device; f->is_mtt = true; f->mtt_mmax = model->mtt.m_max;
+  f->is_mcam = mcam; f->tracker_words = mcam ? mcam_words_per_particle() : mtt_words_per_particle(); f->tracker_obs_w = mcam ? 16 : 2;
   f->mtt_world = world; f->mtt_rank = rank; f->mtt_per = world > 1 ? per : 0;
   f->mtt_j0 = world > 1 ? rank * per : 0;
   f->mtt_jend = world > 1 ? (((int64_t)(rank + 1) * per < (int64_t)n) ? (rank + 1) * per : (int64_t)n) : (int64_t)n;
@@ -738,9 +751,9 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   a.nscan = (int32_t)((a.nblk + kScanTile - 1) / kScanTile);
   a.ntiles_out = (int32_t)((a.n_local + kGenericTileOut - 1) / kGenericTileOut);
   a.ld = round_up(a.n_local, kPad);
-  f->mtt_params.resize(mtt_params_size());
-  mtt_fill_params(model, f->mtt_params.data());
-  const size_t sbytes = (size_t)(f->mtt_jend - f->mtt_j0) * mtt_words_per_particle() * sizeof(uint32_t);
+  if (mcam) { f->mtt_params.resize(mcam_params_size()); mcam_fill_params(model, f->mtt_params.data()); }
+  else { f->mtt_params.resize(mtt_params_size()); mtt_fill_params(model, f->mtt_params.data()); }
+  const size_t sbytes = (size_t)(f->mtt_jend - f->mtt_j0) * f->tracker_words * sizeof(uint32_t);
 #define PZ_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = fail(PZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); free_filter(f); return c_; } } while (0)
   PZ_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   PZ_TRY(cudaEventCreate(&f->ev0));
@@ -764,8 +777,8 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   PZ_TRY(cudaMalloc(&a.summ, (size_t)kObsRing * sizeof(pz_step_summary)));
   PZ_TRY(cudaMemsetAsync(a.summ, 0, (size_t)kObsRing * sizeof(pz_step_summary), f->stream));
   PZ_TRY(cudaMallocHost(&f->h_summ, (size_t)kObsRing * sizeof(pz_step_summary)));
-  PZ_TRY(cudaMalloc(&f->mtt_obs, 64 * sizeof(float)));
-  PZ_TRY(cudaMallocHost(&f->h_mtt_obs, 64 * sizeof(float)));
+  PZ_TRY(cudaMalloc(&f->mtt_obs, 32 * 16 * sizeof(float)));
+  PZ_TRY(cudaMallocHost(&f->h_mtt_obs, 32 * 16 * sizeof(float)));
   PZ_TRY(cudaMalloc(&f->mtt_overflow, sizeof(unsigned long long)));
   PZ_TRY(cudaMemsetAsync(f->mtt_overflow, 0, sizeof(unsigned long long), f->stream));
   PZ_TRY(cudaMalloc(&f->mtt_part, (size_t)mtt_step_ctas(a.n_local) * 5 * sizeof(double)));
@@ -797,19 +810,46 @@ int create_mtt(const pz_model_desc* model, uint64_t n, uint64_t seed, int device
   return PZ_OK;
 }
 
+// observation rows -> device (fp32); MTT: (z0, z1); MultiCamera: (camera, pose[10], box[4], appearance reading)
+int tracker_stage_obs(pz_filter* f, const double* obs, int32_t n_obs) {
+  const int w = f->tracker_obs_w;
+  for (int i = 0; i < w * n_obs; ++i) f->h_mtt_obs[i] = (float)obs[i];
+  if (n_obs) PZ_CUDA(cudaMemcpyAsync(f->mtt_obs, f->h_mtt_obs, (size_t)w * n_obs * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  return PZ_OK;
+}
+int tracker_launch_step(pz_filter* f, const uint32_t* sin, uint32_t* sout, double* part, int32_t n_obs, const MttShard* shard) {
+  if (f->is_mcam)
+    return launch_mcam_step(f->mtt_params.data(), sin, sout, f->g.anc, f->g.lw, f->mtt_obs, f->a.ctl, f->mtt_overflow, part, f->a.n_local,
+                            n_obs, f->a.seed, f->stream, shard);
+  return launch_mtt_step(f->mtt_params.data(), sin, sout, f->g.anc, f->g.lw, f->mtt_obs, f->a.ctl, f->mtt_overflow, part, f->a.n_local,
+                         n_obs, f->a.seed, f->stream, shard);
+}
+// per-step constants of the score added on the host.  MTT: -(lambda_c + lambda_b) - log M!  (poisson_ll,
+// Distributions.hs:168-169; :256-260); MultiCamera: every term is accumulated by the kernel.
+double tracker_ll_const(const pz_filter* f, int32_t n_obs) {
+  if (f->is_mcam) return 0.0;
+  return -(f->desc.mtt.clutter_lambda + f->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
+}
+int tracker_check_obs(const pz_filter* f, const double* obs, int32_t n_obs) {
+  if (n_obs < 0 || n_obs > f->mtt_mmax) return fail(PZ_ECAPACITY, "%d observations exceed m_max = %d", n_obs, f->mtt_mmax);
+  if (f->is_mcam)
+    for (int i = 0; i < n_obs; ++i)
+      if (!(obs[i * 16] == 0.0 || obs[i * 16] == 1.0)) return fail(PZ_EINVAL, "observation %d: camera id %g (expected 0 or 1)", i, obs[i * 16]);
+  return PZ_OK;
+}
+
 int mtt_step_host(pz_filter* f, const double* obs, int32_t n_obs, pz_step_summary* out) {
   StepArgs& a = f->a;
-  if (n_obs < 0 || n_obs > f->mtt_mmax) return fail(PZ_ECAPACITY, "%d observations exceed m_max = %d", n_obs, f->mtt_mmax);
+  int rc0 = tracker_check_obs(f, obs, n_obs);
+  if (rc0) return rc0;
   const uint32_t t0 = f->t;
-  for (int i = 0; i < 2 * n_obs; ++i) f->h_mtt_obs[i] = (float)obs[i];
-  if (n_obs) PZ_CUDA(cudaMemcpyAsync(f->mtt_obs, f->h_mtt_obs, 2 * n_obs * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+  rc0 = tracker_stage_obs(f, obs, n_obs);
+  if (rc0) return rc0;
   PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
   GenericArgs g = mtt_generic(f, 0);
   int n = launch_generic_ancestors(g, f->stream);
-  n += launch_mtt_step(f->mtt_params.data(), f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, a.ctl,
-                       f->mtt_overflow, f->mtt_part, a.n_local, n_obs, a.seed, f->stream);
-  // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
-  const double ll_const = -(f->desc.mtt.clutter_lambda + f->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
+  n += tracker_launch_step(f, f->mtt_s[t0 & 1], f->mtt_s[(t0 + 1) & 1], f->mtt_part, n_obs, nullptr);
+  const double ll_const = tracker_ll_const(f, n_obs);
   n += mtt_plan(f, 1, ll_const);
   f->t += 1;
   PZ_CUDA(cudaEventRecord(f->ev1, f->stream));
@@ -889,6 +929,9 @@ int create_mtt_multi(const pz_model_desc* model, uint64_t n, uint64_t seed, int 
   if (!parent) return fail(PZ_ENOMEM, "out of host memory");
   parent->desc = *model; parent->is_multi = true; parent->is_mtt = true; parent->device = device_ids[0];
   parent->mtt_mmax = model->mtt.m_max; parent->mtt_world = D; parent->mtt_per = per;
+  parent->is_mcam = model->kind == PZ_MODEL_MULTICAM;
+  parent->tracker_words = parent->is_mcam ? mcam_words_per_particle() : mtt_words_per_particle();
+  parent->tracker_obs_w = parent->is_mcam ? 16 : 2;
   memset(&parent->a, 0, sizeof(parent->a));
   auto bail = [&](int code) { free_filter(parent); return code; };
   for (int r = 0; r < D; ++r) {
@@ -934,27 +977,25 @@ MttShard mtt_shard_view(pz_filter* parent, pz_filter* sh, int rec_parity) {
 }
 
 int mtt_multi_step_host(pz_filter* p, const double* obs, int32_t n_obs, pz_step_summary* out) {
-  if (n_obs < 0 || n_obs > p->mtt_mmax) return fail(PZ_ECAPACITY, "%d observations exceed m_max = %d", n_obs, p->mtt_mmax);
+  int rc0 = tracker_check_obs(p->shards[0], obs, n_obs);
+  if (rc0) return rc0;
   const int D = (int)p->shards.size();
   const uint32_t t0 = p->t;
   const int pin = (int)(t0 & 1u), pout = pin ^ 1;
-  // per-step constants of the score: -(lambda_c + lambda_b) - log M!  (poisson_ll, Distributions.hs:168-169; :256-260)
-  const double ll_const = -(p->desc.mtt.clutter_lambda + p->desc.mtt.new_track_lambda) - lgamma(n_obs + 1.0);
+  const double ll_const = tracker_ll_const(p->shards[0], n_obs);
   int64_t launches = 0;
   for (int r = 0; r < D; ++r) {   // own slots: ancestors -> tracker step -> statistics -> push
     pz_filter* f = p->shards[r];
     PZ_CUDA(cudaSetDevice(f->device));
-    for (int i = 0; i < 2 * n_obs; ++i) f->h_mtt_obs[i] = (float)obs[i];
-    if (n_obs) PZ_CUDA(cudaMemcpyAsync(f->mtt_obs, f->h_mtt_obs, 2 * n_obs * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    rc0 = tracker_stage_obs(f, obs, n_obs);
+    if (rc0) return rc0;
     PZ_CUDA(cudaEventRecord(f->ev0, f->stream));
     GenericArgs g = mtt_generic(f, pin);
     g.tile0 = (int32_t)(f->mtt_j0 / kGenericTileOut);
     g.ntiles_out = (int32_t)((f->mtt_jend - f->mtt_j0 + kGenericTileOut - 1) / kGenericTileOut);
     launches += launch_generic_ancestors(g, f->stream);
     const MttShard ms = mtt_shard_view(p, f, (int)(t0 & 1u));
-    launches += launch_mtt_step(f->mtt_params.data(), nullptr, f->mtt_s[(t0 + 1) & 1], f->g.anc, f->g.lw, f->mtt_obs, f->a.ctl,
-                                f->mtt_overflow, mtt_bufs(f, pout).part + (f->mtt_j0 / 128) * 5, f->a.n_local, n_obs, f->a.seed,
-                                f->stream, &ms);
+    launches += tracker_launch_step(f, nullptr, f->mtt_s[(t0 + 1) & 1], mtt_bufs(f, pout).part + (f->mtt_j0 / 128) * 5, n_obs, &ms);
     launches += mtt_stats(f, pout);
     int rc = mtt_push(p, r, pout);
     if (rc < 0) return rc;
@@ -1336,8 +1377,8 @@ int create_common(const pz_model_desc* model, uint64_t n_global, uint64_t seed, 
                   const void* nccl_id, pz_filter** out, bool shard_only = false) {
   if (!model || !out) return fail(PZ_EINVAL, "null argument");
   *out = nullptr;
-  if (model->kind == PZ_MODEL_MTT) {
-    if (world != 1) return fail(PZ_EINVAL, "the tracker runs on one GPU");
+  if (model->kind == PZ_MODEL_MTT || model->kind == PZ_MODEL_MULTICAM) {
+    if (world != 1) return fail(PZ_EINVAL, "one tracker per process: several GPUs through pz_filter_create_multi");
     return create_mtt(model, n_global, seed, device, out);
   }
   if (model->kind == PZ_MODEL_BETA_BERNOULLI) {
@@ -1560,11 +1601,12 @@ int create_multi(const pz_model_desc* model, uint64_t n_global, uint64_t seed, i
   if (n_devices == 1) return create_common(model, n_global, seed, device_ids[0], 0, 1, nullptr, out);
   // (test hook: PZ_MULTI_SAME_DEVICE=1 lets the shards of a multi-device TRACKER share a device -- its exchange is ordered by
   // events, not by spinning kernels -- so that the sharded path runs on a one-GPU box)
-  const bool same_ok = model->kind == PZ_MODEL_MTT && getenv("PZ_MULTI_SAME_DEVICE") != nullptr;
+  const bool tracker = model->kind == PZ_MODEL_MTT || model->kind == PZ_MODEL_MULTICAM;
+  const bool same_ok = tracker && getenv("PZ_MULTI_SAME_DEVICE") != nullptr;
   for (int i = 0; i < n_devices; ++i)
     for (int j = 0; j < i; ++j)
       if (device_ids[i] == device_ids[j] && !same_ok) return fail(PZ_EINVAL, "device %d listed twice", device_ids[i]);
-  if (model->kind == PZ_MODEL_MTT) return create_mtt_multi(model, n_global, seed, n_devices, device_ids, out);
+  if (tracker) return create_mtt_multi(model, n_global, seed, n_devices, device_ids, out);
   if (model->kind != PZ_MODEL_RW1D && model->kind != PZ_MODEL_LINGAUSS)
     return fail(PZ_EINVAL, "multi-device filters: the linear-Gaussian families (RW1D / LINGAUSS) and the tracker (MTT)");
   if (model->delayed || model->carry_weights || model->ess_threshold > 0)
@@ -1778,6 +1820,28 @@ int pz_model_mtt(pz_model_desc* d) {
   return PZ_OK;
 }
 
+int pz_model_multicam(pz_model_desc* d) {
+  if (!d) return fail(PZ_EINVAL, "null descriptor");
+  fill_common(d, PZ_MODEL_MULTICAM, 4, 0);           // ny = 0: the box is observed directly, box ~ N(posWH, meas_var I) (:130)
+  const double tdiff = 1.0;                          // MultiCamera.hs:77-78
+  for (int i = 0; i < 4; ++i) {
+    d->F[i * 4 + i] = 1.0;                           // motionMatrix = eye (:113)
+    d->Q[i * 4 + i] = tdiff * (i < 2 ? 1.0 : 0.1);   // motionCov (:114-116)
+  }
+  d->x0[0] = d->x0[1] = 0.0; d->x0[2] = d->x0[3] = 1.0;   // mean of the box prior and of the clutter boxes (:91, :187)
+  d->mtt.clutter_lambda = 1.0;        // amtClutter, per camera (:184-185)
+  d->mtt.new_track_lambda = 0.1;      // birthRate * tdiff (:195, :206)
+  d->mtt.pd = 1.0;                    // every live track is measured (:140-146)
+  d->mtt.survival_prob = exp(-tdiff * 0.02);   // :120, :126
+  d->mtt.clutter_var = 1.0;           // clutter box covariance I (:187)
+  d->mtt.birth_pos_var = 1.0;         // box prior covariance diag(1, 1, 0.2, 0.2) (:93)
+  d->mtt.birth_vel_var = 0.2;
+  d->mtt.meas_var = 1.0;
+  d->mtt.k_max = 16;
+  d->mtt.m_max = 32;
+  return PZ_OK;
+}
+
 int pz_model_walker(pz_model_desc* d) {
   if (!d) return fail(PZ_EINVAL, "null descriptor");
   fill_common(d, PZ_MODEL_WALKER, 5, 2);
@@ -1835,7 +1899,8 @@ int64_t pz_filter_n_local(const pz_filter* f) {
 int pz_filter_step(pz_filter* f, const double* obs, int32_t n_obs, int32_t obs_dim, pz_step_summary* out) {
   if (!f || (!obs && n_obs > 0)) return fail(PZ_EINVAL, "null argument");
   if (f->is_mtt) {
-    if (obs_dim != 2) return fail(PZ_EINVAL, "tracker observations are rows of 2 doubles");
+    const int ow = f->tracker_obs_w;
+    if (obs_dim != ow) return fail(PZ_EINVAL, "tracker observations are rows of %d doubles", ow);
     if (f->is_multi) return mtt_multi_step_host(f, obs, n_obs, out);
     PZ_CUDA(cudaSetDevice(f->device));
     return mtt_step_host(f, obs, n_obs, out);
@@ -2094,10 +2159,8 @@ int pz_filter_read_particles(pz_filter* f, int32_t stride, double* out, int64_t 
   return PZ_OK;
 }
 
-int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, double* mean_out, double* cov_out,
-                          int64_t n_sel_cap) {
-  if (!f || !count_out || !id_out || !mean_out || !cov_out || stride < 1) return fail(PZ_EINVAL, "bad argument");
-  if (!f->is_mtt) return fail(PZ_ESTATE, "not a tracker filter");
+// thinned resampled population of a tracker: the raw records (W words each) of every stride-th output slot's parent
+static int tracker_gather(pz_filter* f, int32_t stride, int64_t n_sel_cap, std::vector<uint32_t>* h, int64_t* n_sel_out, int* W_out) {
   const StepArgs& a = f->a;
   const int64_t n_sel = (a.n_local + stride - 1) / stride;
   if (n_sel_cap < n_sel) return fail(PZ_EINVAL, "buffers too small: need %lld particles", (long long)n_sel);
@@ -2110,16 +2173,29 @@ int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int3
     launch_generic_ancestors(g, f->stream);
   } else rc = pending_ancestors(f, nullptr);
   if (rc) return rc;
-  const int W = mtt_words_per_particle();
+  const int W = f->tracker_words;
   uint32_t* d_out = nullptr;
   PZ_CUDA(cudaMalloc(&d_out, (size_t)n_sel * W * sizeof(uint32_t)));
-  if (parent->is_multi) launch_mtt_gather_multi(mtt_shard_view(parent, f, (int)(parent->t & 1u)), f->g.anc, stride, n_sel, d_out, f->stream);
-  else launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream);
-  std::vector<uint32_t> h((size_t)n_sel * W);
-  cudaError_t e = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
+  if (parent->is_multi) launch_mtt_gather_multi(mtt_shard_view(parent, f, (int)(parent->t & 1u)), f->g.anc, stride, n_sel, d_out, f->stream, W);
+  else launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream, W);
+  h->resize((size_t)n_sel * W);
+  cudaError_t e = cudaMemcpyAsync(h->data(), d_out, h->size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
   cudaFree(d_out);
   if (e != cudaSuccess) return fail(PZ_ECUDA, "read_tracks: %s", cudaGetErrorString(e));
+  *n_sel_out = n_sel; *W_out = W;
+  return PZ_OK;
+}
+
+int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, double* mean_out, double* cov_out,
+                          int64_t n_sel_cap) {
+  if (!f || !count_out || !id_out || !mean_out || !cov_out || stride < 1) return fail(PZ_EINVAL, "bad argument");
+  if (!f->is_mtt) return fail(PZ_ESTATE, "not a tracker filter");
+  if (f->is_mcam) return fail(PZ_ESTATE, "MultiCamera tracks are read with pz_filter_read_mcam_tracks");
+  std::vector<uint32_t> h;
+  int64_t n_sel = 0; int W = 0;
+  int rc = tracker_gather(f, stride, n_sel_cap, &h, &n_sel, &W);
+  if (rc) return rc;
   static const int tri[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
   for (int64_t i = 0; i < n_sel; ++i) {
     const uint32_t* p = h.data() + (size_t)i * W;
@@ -2133,6 +2209,47 @@ int pz_filter_read_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int3
       for (int c = 0; c < 4; ++c) mean_out[(i * 16 + k) * 4 + c] = k < cnt ? (double)fl[1 + c] : 0.0;
       for (int x = 0; x < 4; ++x) for (int y = 0; y < 4; ++y) cov_out[(i * 16 + k) * 16 + x * 4 + y] = k < cnt ? (double)fl[5 + tri[x][y]] : 0.0;
     }
+  }
+  return PZ_OK;
+}
+
+int pz_filter_read_mcam_tracks(pz_filter* f, int32_t stride, int32_t* count_out, int32_t* id_out, int32_t* identity_out,
+                               int32_t* camera_out, double* start_out, double* mean_out, double* var_out, int32_t* n_app_out,
+                               double* app_mean_out, double* app_cov_out, int64_t n_sel_cap) {
+  if (!f || !count_out || !id_out || !identity_out || !camera_out || !mean_out || !var_out || stride < 1) return fail(PZ_EINVAL, "bad argument");
+  if (!f->is_mtt || !f->is_mcam) return fail(PZ_ESTATE, "not a MultiCamera filter");
+  std::vector<uint32_t> h;
+  int64_t n_sel = 0; int W = 0;
+  int rc = tracker_gather(f, stride, n_sel_cap, &h, &n_sel, &W);
+  if (rc) return rc;
+  const int K = 16, A = 16, D = 10, apps0 = 4 + K * 12;
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const uint32_t* p = h.data() + (size_t)i * W;
+    const int cnt = (int)p[0], na = (int)p[2];
+    count_out[i] = cnt;
+    if (n_app_out) n_app_out[i] = na;
+    for (int k = 0; k < K; ++k) {
+      float fl[12];
+      memcpy(fl, p + 4 + 12 * k, sizeof(fl));
+      const uint32_t* r = p + 4 + 12 * k;
+      id_out[i * K + k] = k < cnt ? (int32_t)r[0] : -1;
+      identity_out[i * K + k] = k < cnt ? (int32_t)r[1] : -1;
+      camera_out[i * K + k] = k < cnt ? (int32_t)r[2] : -1;
+      if (start_out) start_out[i * K + k] = k < cnt ? (double)fl[3] : 0.0;
+      for (int c = 0; c < 4; ++c) { mean_out[(i * K + k) * 4 + c] = k < cnt ? (double)fl[4 + c] : 0.0; var_out[(i * K + k) * 4 + c] = k < cnt ? (double)fl[8 + c] : 0.0; }
+    }
+    if (app_mean_out && app_cov_out)
+      for (int ap = 0; ap < A; ++ap) {
+        float fl[66];
+        memcpy(fl, p + apps0 + 66 * ap, sizeof(fl));
+        for (int x = 0; x < D; ++x) {
+          app_mean_out[(i * A + ap) * D + x] = ap < na ? (double)fl[x] : 0.0;
+          for (int y = 0; y < D; ++y) {
+            const int lo = x <= y ? x : y, hi = x <= y ? y : x;
+            app_cov_out[((i * A + ap) * D + x) * D + y] = ap < na ? (double)fl[D + lo * D - (lo * (lo - 1)) / 2 + (hi - lo)] : 0.0;
+          }
+        }
+      }
   }
   return PZ_OK;
 }

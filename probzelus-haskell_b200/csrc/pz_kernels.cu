@@ -2019,7 +2019,12 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
   constexpr int NT = (NX == 1) ? PZ_NT1 : PZ_NTN;
   constexpr int TO = tile_blocks(NX, F64, SMALL) * kBlk;
   constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : (NX <= 4 ? PZ_OCC4D : 2)) : min_ctas(NX);
-  auto kern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT)>;
+#ifdef PZ_MINB1D   // A/B hook: resident CTAs per SM of the double NX = 1 kernel in units of its own CTA size
+  constexpr int MINB = (F64 && NX == 1) ? PZ_MINB1D : OCC * (kThreads / NT);
+#else
+  constexpr int MINB = OCC * (kThreads / NT);
+#endif
+  auto kern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB>;
   // staged parents [NX][TO] + inverse-CDF table
   const size_t smem = (size_t)NX * TO * sizeof(T) + PZ_ICDF_ROWS * sizeof(float4);
   // function attributes are per context (device); concurrent first launches set the same value
@@ -2047,7 +2052,7 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
   kern<<<grid, NT, smem, s>>>(ta);
   if constexpr (MODE == 0) {
     if (ta.a.p2p != nullptr) {   // sharded over peer memory: the remote-read fallback follows (it exits at once unless the margins overflowed)
-      auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, OCC * (kThreads / NT), true>;
+      auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB, true>;
       static std::atomic<unsigned long long> rattr_done{0};
       if (!(rattr_done.load(std::memory_order_acquire) & bit)) {
         cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

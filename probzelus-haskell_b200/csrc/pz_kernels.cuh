@@ -245,7 +245,14 @@ struct PushArgs {
 };
 int launch_push_slices(const PushArgs& p, cudaStream_t s);
 int launch_emax_from_eb(const int32_t* eb, int64_t nblk, CtlDev* ctl, cudaStream_t s);
-int launch_mtt_gather_multi(const MttShard& sh, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
-int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s);
+int launch_mtt_gather_multi(const MttShard& sh, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s, int words);
+// MultiCamera tracker (pz_mtt.cu): same calling convention as the MTT step
+int mcam_words_per_particle();
+size_t mcam_params_size();
+void mcam_fill_params(const pz_model_desc* d, void* out_mcamdev);
+int launch_mcam_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
+                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
+                     cudaStream_t s, const MttShard* shard = nullptr);
+int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s, int words);
 
 }  // namespace pz

@@ -208,6 +208,46 @@ __device__ __forceinline__ void mtt_pick(float target, int k, const Der& der, fl
   }
 }
 
+// per-CTA partial of the weighted track-count moments (no separate pass over the particles): every thread brings its
+// particle's log-weight and track count (-inf / 0 past the end); row `blockIdx.x` of `part` receives
+// (max lw, sum w, sum w^2, sum w c, sum w c^2), w = exp(lw - max)
+__device__ __forceinline__ void tracker_block_summary(float out_lw, float out_cnt, double* __restrict__ part) {
+  const int tid = threadIdx.x;
+  __shared__ float s_mx[kMttThreads / 32];
+  __shared__ double s_sum[kMttThreads / 32][4];
+  const int lane = tid & 31, warp = tid >> 5;
+  float mx = out_lw;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if (lane == 0) s_mx[warp] = mx;
+  __syncthreads();
+  mx = s_mx[0];
+#pragma unroll
+  for (int w = 1; w < kMttThreads / 32; ++w) mx = fmaxf(mx, s_mx[w]);
+  double v[4] = {0, 0, 0, 0};
+  if (out_lw > -INFINITY) {
+    const double w = exp((double)out_lw - (double)mx), c = (double)out_cnt;
+    v[0] = w; v[1] = w * w; v[2] = w * c; v[3] = w * c * c;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double x = v[r];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const long long y = __double_as_longlong(x);
+      const int lo = __shfl_xor_sync(0xffffffffu, (int)y, d), hi = __shfl_xor_sync(0xffffffffu, (int)(y >> 32), d);
+      x += __longlong_as_double(((long long)hi << 32) | (unsigned int)lo);
+    }
+    if (lane == 0) s_sum[warp][r] = x;
+  }
+  __syncthreads();
+  if (tid < 5) {
+    double x = (double)mx;
+    if (tid > 0) { x = 0; for (int w = 0; w < kMttThreads / 32; ++w) x += s_sum[w][tid - 1]; }
+    part[(size_t)blockIdx.x * 5 + tid] = x;
+  }
+}
+
 __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ MttArgs a) {
   extern __shared__ float s_der[];  // [kMttDerived][kMttFast][kMttThreads]
   __shared__ float s_z[32][2], s_lc[32], s_ln[32];
@@ -327,41 +367,244 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   out_cnt = (float)(n_surv + n_born);
   } while (0);
 
-  // ---- per-CTA partial of the weighted track-count moments (no separate pass over the particles)
-  __shared__ float s_mx[kMttThreads / 32];
-  __shared__ double s_sum[kMttThreads / 32][4];
-  const int lane = tid & 31, warp = tid >> 5;
-  float mx = out_lw;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-  if (lane == 0) s_mx[warp] = mx;
-  __syncthreads();
-  mx = s_mx[0];
-#pragma unroll
-  for (int w = 1; w < kMttThreads / 32; ++w) mx = fmaxf(mx, s_mx[w]);
-  double v[4] = {0, 0, 0, 0};
-  if (out_lw > -INFINITY) {
-    const double w = exp((double)out_lw - (double)mx), c = (double)out_cnt;
-    v[0] = w; v[1] = w * w; v[2] = w * c; v[3] = w * c * c;
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    double x = v[r];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const long long y = __double_as_longlong(x);
-      const int lo = __shfl_xor_sync(0xffffffffu, (int)y, d), hi = __shfl_xor_sync(0xffffffffu, (int)(y >> 32), d);
-      x += __longlong_as_double(((long long)hi << 32) | (unsigned int)lo);
-    }
-    if (lane == 0) s_sum[warp][r] = x;
-  }
-  __syncthreads();
-  if (tid < 5) {
-    double x = (double)mx;
-    if (tid > 0) { x = 0; for (int w = 0; w < kMttThreads / 32; ++w) x += s_sum[w][tid - 1]; }
-    a.part[(size_t)blockIdx.x * 5 + tid] = x;
-  }
+  tracker_block_summary(out_lw, out_cnt, a.part);
 }
+
+// =================================================================================================
+// MultiCamera tracker step (Examples/MultiCamera.hs:40-227), one thread per particle.
+//
+// A particle = up to 16 tracks (box marginal over R^4: F = H = I and diagonal Q / R / prior keep its covariance
+// DIAGONAL, so a track is 4 means + 4 variances; the CPU oracle carries the full matrices and agrees) and up to 16
+// appearance marginals over R^10 (mean + upper triangle of the covariance) shared by the tracks of one identity.
+//   tracksMotion (:183-195): survival Bernoulli(exp(-0.02)) and predict per track, Poisson(0.1) births, each with a
+//     camera ~ U{0,1}, a new appearance with probability 1 / (A + 1) or the identity of an existing one, the box
+//     prior N((0,0,1,1), diag(1,1,.2,.2));
+//   assocWithClutterCustomProposal (:162-180) per camera, tracks in list order: scores of the remaining observations
+//     (box predictive x uniform-sphere pose density x scalar appearance predictive), categorical pick, Kalman update
+//     of the box and rank-one update of the appearance, weight *= sum of the likelihoods; a track without an
+//     observation left kills the particle (passert False); the rest is clutter with the count prior of :166-167.
+// Record (1252 words): header {tracks, numTracks, appearances, flags}; 16 x 12 words {trackID, identity, camera,
+// startTime, mean[4], var[4]}; 16 x 66 words {mean[10], cov upper triangle[55], pad}.  The child's record is built in
+// place in global memory (it is this thread's own; only live parts move).  Statistical parity with the oracle (different
+// uniforms), exact agreement where the association is forced (tests/test_mcam.py).
+constexpr uint32_t kStreamMcam = 0x4D43414Du;  // "MCAM"
+constexpr int kMcK = 16, kMcA = 16, kMcD = 10, kMcTrackW = 12, kMcAppW = 66;
+constexpr int kMcApps0 = 4 + kMcK * kMcTrackW;            // 196
+constexpr int kMcWords = kMcApps0 + kMcA * kMcAppW;       // 1252
+constexpr int kMcObsW = 16;                               // camera, pose[10], box[4], appearance reading
+
+struct McamDev {
+  float q[4], prior_m[4], prior_v[4], clutter_m[4];
+  float ps, lb, lc, r_box, r_app, lsphere;
+};
+
+struct McamArgs {
+  const uint32_t* sin; uint32_t* sout; const int32_t* anc; float* lw; const float* obs; const CtlDev* ctl;
+  unsigned long long* overflow; double* part;
+  int64_t n, j0, n_per;
+  const uint32_t* sin_all[kMttMaxDevices];
+  int32_t n_obs; uint64_t seed;
+  McamDev p;
+};
+
+struct McRng {   // sequential uniforms of one particle: word (i & 3) of Philox call (i >> 2)
+  uint32_t j, t, k0, k1, call; U4 r; int have;
+  __device__ __forceinline__ float next() {
+    if (!have) { r = philox4x32_10(j, call++, t, kStreamMcam, k0, k1); have = 4; }
+    const uint32_t w = have == 4 ? r.x : (have == 3 ? r.y : (have == 2 ? r.z : r.w));
+    --have;
+    return u01(w);
+  }
+};
+
+__device__ __forceinline__ int mc_tri(int i, int j) { return i * kMcD - (i * (i - 1)) / 2 + (j - i); }  // i <= j
+
+__global__ void __launch_bounds__(kMttThreads) mcam_step(const __grid_constant__ McamArgs a) {
+  __shared__ float s_obs[32][kMcObsW];
+  __shared__ float s_cl[32], s_lfact[64];
+  const int tid = threadIdx.x;
+  const int M = a.n_obs;
+  const McamDev& p = a.p;
+  for (int i = tid; i < M * kMcObsW; i += kMttThreads) s_obs[i / kMcObsW][i % kMcObsW] = a.obs[i];
+  if (tid < 64) s_lfact[tid] = lgammaf((float)tid + 1.0f);
+  __syncthreads();
+  if (tid < M) {   // clutter density of observation tid: box ~ N(clutter_m, I4), pose ~ N(0, I10), reading ~ N(0, 1)
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float d = s_obs[tid][11 + i] - p.clutter_m[i]; q += d * d; }
+#pragma unroll
+    for (int i = 0; i < kMcD; ++i) q += s_obs[tid][1 + i] * s_obs[tid][1 + i];
+    q += s_obs[tid][15] * s_obs[tid][15];
+    s_cl[tid] = -0.5f * q - 0.5f * 15.0f * 1.8378770664093453f;
+  }
+  __syncthreads();
+  const int64_t j = a.j0 + (int64_t)blockIdx.x * kMttThreads + tid;
+  float out_lw = -INFINITY, out_cnt = 0.f;
+  do {
+  if (j >= a.n) break;
+  const uint32_t t = a.ctl->t;
+  const int64_t par = a.anc[j];
+  const uint32_t* __restrict__ src;
+  if (a.n_per) { const int64_t owner = par / a.n_per; src = a.sin_all[owner] + (size_t)(par - owner * a.n_per) * kMcWords; }
+  else src = a.sin + (size_t)par * kMcWords;
+  uint32_t* __restrict__ dst = a.sout + (size_t)(j - a.j0) * kMcWords;
+  const uint4 hdr = *reinterpret_cast<const uint4*>(src);
+  const int cnt = (int)hdr.x;
+  int num_tracks = (int)hdr.y, A = (int)hdr.z;
+  McRng rng{(uint32_t)j, t, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), 0u, U4{0, 0, 0, 0}, 0};
+  // the parent's appearances
+  for (int ap = 0; ap < A; ++ap) {
+    const uint2* s2 = reinterpret_cast<const uint2*>(src + kMcApps0 + ap * kMcAppW);
+    uint2* d2 = reinterpret_cast<uint2*>(dst + kMcApps0 + ap * kMcAppW);
+#pragma unroll 11
+    for (int w = 0; w < kMcAppW / 2; ++w) d2[w] = s2[w];
+  }
+  // tracksMotion: survival + predict, survivors compacted in order
+  int n_live = 0, ovf = 0;
+  for (int k = 0; k < cnt; ++k) {
+    if (!(rng.next() < p.ps)) continue;
+    const uint4* sp = reinterpret_cast<const uint4*>(src + 4 + kMcTrackW * k);
+    const uint4 w0 = sp[0], w1 = sp[1];
+    uint4 w2 = sp[2];
+    w2.x = __float_as_uint(__uint_as_float(w2.x) + p.q[0]); w2.y = __float_as_uint(__uint_as_float(w2.y) + p.q[1]);
+    w2.z = __float_as_uint(__uint_as_float(w2.z) + p.q[2]); w2.w = __float_as_uint(__uint_as_float(w2.w) + p.q[3]);
+    uint4* dp = reinterpret_cast<uint4*>(dst + 4 + kMcTrackW * n_live);
+    dp[0] = w0; dp[1] = w1; dp[2] = w2;
+    ++n_live;
+  }
+  // births (Poisson by the inverse CDF on one uniform)
+  int n_new = 0;
+  {
+    const float u = rng.next();
+    float pk = __expf(-p.lb), F = pk;
+    while (u >= F && n_new < 64) { ++n_new; pk *= p.lb / (float)n_new; F += pk; }
+  }
+  for (int i = 0; i < n_new; ++i) {
+    const float u_cam = rng.next(), u_new = rng.next(), u_id = rng.next();
+    int cam = (int)(u_cam * 2.0f); cam = cam < 2 ? cam : 1;
+    bool fresh = u_new < 1.0f / (float)(A + 1);
+    if (fresh && A >= kMcA) { fresh = false; ++ovf; }
+    int identity;
+    if (fresh) {
+      uint32_t* ap = dst + kMcApps0 + A * kMcAppW;
+      for (int w = 0; w < kMcAppW; ++w) ap[w] = 0u;
+      for (int d = 0; d < kMcD; ++d) ap[kMcD + mc_tri(d, d)] = __float_as_uint(1.0f);
+      identity = A; ++A;
+    } else { identity = (int)(u_id * (float)A); identity = identity < A ? identity : A - 1; }
+    if (n_live < kMcK) {
+      uint4* dp = reinterpret_cast<uint4*>(dst + 4 + kMcTrackW * n_live);
+      dp[0] = make_uint4((uint32_t)(num_tracks + 1 + i), (uint32_t)identity, (uint32_t)cam, __float_as_uint((float)t));
+      dp[1] = make_uint4(__float_as_uint(p.prior_m[0]), __float_as_uint(p.prior_m[1]), __float_as_uint(p.prior_m[2]), __float_as_uint(p.prior_m[3]));
+      dp[2] = make_uint4(__float_as_uint(p.prior_v[0]), __float_as_uint(p.prior_v[1]), __float_as_uint(p.prior_v[2]), __float_as_uint(p.prior_v[3]));
+      ++n_live;
+    } else ++ovf;
+  }
+  num_tracks += n_new;
+  // association, camera by camera
+  float lw = 0.f;
+  bool dead = false;
+  for (int cam = 0; cam < 2 && !dead; ++cam) {
+    uint32_t rem = 0;
+    for (int o = 0; o < M; ++o) if ((int)s_obs[o][0] == cam) rem |= 1u << o;
+    int nT = 0;
+    for (int k = 0; k < n_live; ++k) {
+      uint32_t* tw = dst + 4 + kMcTrackW * k;
+      if ((int)tw[2] != cam) continue;
+      ++nT;
+      if (!rem) { dead = true; break; }   // passert False: more tracks than observations in this camera
+      const int identity = (int)tw[1];
+      float m[4], v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { m[i] = __uint_as_float(tw[4 + i]); v[i] = __uint_as_float(tw[8 + i]); }
+      float* ap = reinterpret_cast<float*>(dst + kMcApps0 + identity * kMcAppW);
+      float am[kMcD], ac[55];
+#pragma unroll
+      for (int i = 0; i < kMcD; ++i) am[i] = ap[i];
+#pragma unroll
+      for (int i = 0; i < 55; ++i) ac[i] = ap[kMcD + i];
+      float lbox0 = -0.5f * 4.0f * 1.8378770664093453f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lbox0 -= 0.5f * __logf(v[i] + p.r_box);
+      float ll[32];
+      float mx = -INFINITY;
+      for (uint32_t rr = rem; rr; rr &= rr - 1) {
+        const int o = __ffs(rr) - 1;
+        const float* row = s_obs[o];
+        float quad = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float d = row[11 + i] - m[i]; quad += d * d / (v[i] + p.r_box); }
+        float hm = 0.f, hPh = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMcD; ++i) {
+          const float hi = row[1 + i];
+          hm += hi * am[i];
+          float acc = 0.5f * ac[mc_tri(i, i)] * hi;
+#pragma unroll
+          for (int jj = i + 1; jj < kMcD; ++jj) acc += ac[mc_tri(i, jj)] * row[1 + jj];
+          hPh += 2.0f * hi * acc;
+        }
+        const float sv = hPh + p.r_app, d = row[15] - hm;
+        const float l = lbox0 - 0.5f * quad + p.lsphere - 0.5f * (d * d / sv + __logf(sv) + 1.8378770664093453f);
+        ll[o] = l;
+        mx = fmaxf(mx, l);
+      }
+      float total = 0.f;
+      for (uint32_t rr = rem; rr; rr &= rr - 1) total += __expf(ll[__ffs(rr) - 1] - mx);
+      const float target = rng.next() * total;
+      int pick = -1, last = -1;
+      float cum = 0.f;
+      for (uint32_t rr = rem; rr; rr &= rr - 1) {
+        const int o = __ffs(rr) - 1;
+        last = o;
+        cum += __expf(ll[o] - mx);
+        if (pick < 0 && cum > target) pick = o;
+      }
+      if (pick < 0) pick = last;
+      lw += mx + __logf(total);
+      rem &= ~(1u << pick);
+      const float* row = s_obs[pick];
+      // condition the box (diagonal Kalman update, H = I) and the appearance (rank-one update) on the picked observation
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float K = v[i] / (v[i] + p.r_box);
+        m[i] += K * (row[11 + i] - m[i]);
+        v[i] -= K * v[i];
+        tw[4 + i] = __float_as_uint(m[i]); tw[8 + i] = __float_as_uint(v[i]);
+      }
+      float Ph[kMcD], hm = 0.f, sv = p.r_app;
+#pragma unroll
+      for (int i = 0; i < kMcD; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < kMcD; ++jj) acc += ac[i <= jj ? mc_tri(i, jj) : mc_tri(jj, i)] * row[1 + jj];
+        Ph[i] = acc;
+        hm += row[1 + i] * am[i];
+      }
+#pragma unroll
+      for (int i = 0; i < kMcD; ++i) sv += row[1 + i] * Ph[i];
+      const float isv = 1.0f / sv, d = row[15] - hm;
+#pragma unroll
+      for (int i = 0; i < kMcD; ++i) {
+        ap[i] = am[i] + Ph[i] * isv * d;
+#pragma unroll
+        for (int jj = i; jj < kMcD; ++jj) ap[kMcD + mc_tri(i, jj)] = ac[mc_tri(i, jj)] - Ph[i] * Ph[jj] * isv;
+      }
+    }
+    if (dead) break;
+    const int nC = __popc(rem);
+    lw += -(s_lfact[nT + nC] - s_lfact[nC]) + (-p.lc + (float)nC * __logf(p.lc) - s_lfact[nC]);
+    for (uint32_t rr = rem; rr; rr &= rr - 1) lw += s_cl[__ffs(rr) - 1];
+  }
+  if (dead) lw = -INFINITY;
+  *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)n_live, (uint32_t)num_tracks, (uint32_t)A, ovf ? 1u : 0u);
+  a.lw[j] = lw;
+  if (ovf) atomicAdd(a.overflow, (unsigned long long)ovf);
+  out_lw = sanitize_lw(lw);
+  out_cnt = (float)n_live;
+  } while (0);
+  tracker_block_summary(out_lw, out_cnt, a.part);
+}
+
 
 // combine the per-CTA partials (log-sum-exp over their maxima) into the step summary
 constexpr int kFinalThreads = 1024, kFinalWarps = kFinalThreads / 32;
@@ -423,22 +666,22 @@ __global__ void __launch_bounds__(kFinalThreads) mtt_summary_final(PlanDev* pl, 
 
 // thinned read of the resampled population: every stride-th output slot's parent record
 __global__ void mtt_gather_thin(const uint32_t* __restrict__ s, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
-                                uint32_t* __restrict__ out) {
+                                uint32_t* __restrict__ out, int W) {
   const int64_t sel = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (sel >= n_sel) return;
   const int64_t p = anc[sel * stride];
-  for (int w = threadIdx.x & 31; w < kMttWords; w += 32) out[(size_t)sel * kMttWords + w] = s[(size_t)p * kMttWords + w];
+  for (int w = threadIdx.x & 31; w < W; w += 32) out[(size_t)sel * W + w] = s[(size_t)p * W + w];
 }
 
 // the same on a multi-device tracker: the parent's record is read from the device that owns it
 __global__ void mtt_gather_thin_multi(MttShard sh, const int32_t* __restrict__ anc, int32_t stride, int64_t n_sel,
-                                      uint32_t* __restrict__ out) {
+                                      uint32_t* __restrict__ out, int W) {
   const int64_t sel = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (sel >= n_sel) return;
   const int64_t p = anc[sel * stride];
   const int64_t owner = p / sh.n_per;
-  const uint32_t* s = sh.sin_all[owner] + (size_t)(p - owner * sh.n_per) * kMttWords;
-  for (int w = threadIdx.x & 31; w < kMttWords; w += 32) out[(size_t)sel * kMttWords + w] = s[w];
+  const uint32_t* s = sh.sin_all[owner] + (size_t)(p - owner * sh.n_per) * W;
+  for (int w = threadIdx.x & 31; w < W; w += 32) out[(size_t)sel * W + w] = s[w];
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -469,6 +712,33 @@ void mtt_fill_params(const pz_model_desc* d, void* out_mttdev) {
 }
 
 size_t mtt_params_size() { return sizeof(MttDev); }
+
+// ---- MultiCamera host side -------------------------------------------------------------------
+int mcam_words_per_particle() { return kMcWords; }
+size_t mcam_params_size() { return sizeof(McamDev); }
+void mcam_fill_params(const pz_model_desc* d, void* out) {
+  McamDev& p = *reinterpret_cast<McamDev*>(out);
+  for (int i = 0; i < 4; ++i) { p.q[i] = (float)d->Q[i * 4 + i]; p.prior_m[i] = (float)d->x0[i]; p.clutter_m[i] = (float)d->x0[i]; }
+  p.prior_v[0] = p.prior_v[1] = (float)d->mtt.birth_pos_var; p.prior_v[2] = p.prior_v[3] = (float)d->mtt.birth_vel_var;
+  p.ps = (float)d->mtt.survival_prob; p.lb = (float)d->mtt.new_track_lambda; p.lc = (float)d->mtt.clutter_lambda;
+  p.r_box = (float)d->mtt.meas_var; p.r_app = 1.0f;
+  p.lsphere = (float)(-(log((double)kMcD) + kMcD / 2.0 * log(M_PI) - lgamma(kMcD / 2.0 + 1.0)));  // -logNSphereVolume, MVDistributions.hs:64-66
+}
+int launch_mcam_step(const void* params, const uint32_t* sin, uint32_t* sout, const int32_t* anc, float* lw, const float* obs,
+                     const CtlDev* ctl, unsigned long long* overflow, double* part, int64_t n, int32_t n_obs, uint64_t seed,
+                     cudaStream_t s, const MttShard* shard) {
+  McamArgs a;
+  a.sin = sin; a.sout = sout; a.anc = anc; a.lw = lw; a.obs = obs; a.ctl = ctl; a.overflow = overflow; a.part = part; a.n = n;
+  a.j0 = 0; a.n_per = 0;
+  for (int i = 0; i < kMttMaxDevices; ++i) a.sin_all[i] = nullptr;
+  if (shard) {
+    a.j0 = shard->j0; a.n = shard->j_end; a.n_per = shard->n_per;
+    for (int i = 0; i < kMttMaxDevices; ++i) a.sin_all[i] = shard->sin_all[i];
+  }
+  a.n_obs = n_obs; a.seed = seed; a.p = *reinterpret_cast<const McamDev*>(params);
+  mcam_step<<<(unsigned)((a.n - a.j0 + kMttThreads - 1) / kMttThreads), kMttThreads, 0, s>>>(a);
+  return 1;
+}
 
 int mtt_step_ctas(int64_t n) { return (int)((n + kMttThreads - 1) / kMttThreads); }
 
@@ -504,15 +774,15 @@ int launch_mtt_summary(const double* part, int64_t n, PlanDev* plan, const CtlDe
   return 1;
 }
 
-int launch_mtt_gather_multi(const MttShard& sh, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
+int launch_mtt_gather_multi(const MttShard& sh, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s, int words) {
   const int per_cta = kThreads / 32;
-  mtt_gather_thin_multi<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sh, anc, stride, n_sel, out);
+  mtt_gather_thin_multi<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sh, anc, stride, n_sel, out, words);
   return 1;
 }
 
-int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s) {
+int launch_mtt_gather(const uint32_t* sdata, const int32_t* anc, int32_t stride, int64_t n_sel, uint32_t* out, cudaStream_t s, int words) {
   const int per_cta = kThreads / 32;
-  mtt_gather_thin<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sdata, anc, stride, n_sel, out);
+  mtt_gather_thin<<<(unsigned)((n_sel + per_cta - 1) / per_cta), kThreads, 0, s>>>(sdata, anc, stride, n_sel, out, words);
   return 1;
 }
 

@@ -16,7 +16,7 @@ import numpy as np
 
 PZ_MAX_NX, PZ_MAX_NY = 6, 3
 PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF = 0, 1
-PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT, PZ_MODEL_WALKER, PZ_MODEL_BETA_BERNOULLI = 1, 2, 3, 4, 5
+PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT, PZ_MODEL_WALKER, PZ_MODEL_BETA_BERNOULLI, PZ_MODEL_MULTICAM = 1, 2, 3, 4, 5, 6
 PZ_DIST = {"bernoulli": 1, "categorical": 2, "poisson": 3, "uniform": 4, "exponential": 5, "normal": 6}
 _ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENCCL", -4: "EDEGENERATE", -5: "ECAPACITY", -6: "ENOMEM", -7: "ESTATE"}
 
@@ -66,6 +66,7 @@ _SYMBOLS = [
     "pz_filter_read_logw", "pz_filter_read_state_f64", "pz_filter_read_logw_f64", "pz_filter_read_posterior", "pz_filter_n_local", "pz_resample_systematic", "pz_resample_multinomial",
     "pz_filter_destroy", "pz_model_walker", "pz_model_beta_bernoulli", "pz_importance_resampling",
     "pz_dist_sample", "pz_dist_score", "pz_filter_reset", "pz_filter_create_multi",
+    "pz_model_multicam", "pz_filter_read_mcam_tracks",
 ]
 
 
@@ -96,7 +97,7 @@ def lib():
     f64p, i32p, f32p = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)
     L.pz_last_error.restype = C.c_char_p
     L.pz_model_rw1d.argtypes = [C.POINTER(ModelDesc), C.c_double, C.c_double]
-    for nm in ("pz_model_stt", "pz_model_mtt_track", "pz_model_mtt"):
+    for nm in ("pz_model_stt", "pz_model_mtt_track", "pz_model_mtt", "pz_model_multicam"):
         getattr(L, nm).argtypes = [C.POINTER(ModelDesc)]
     L.pz_filter_create.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
     L.pz_comm_unique_id.argtypes = [C.c_void_p]
@@ -108,6 +109,7 @@ def lib():
     L.pz_filter_step_profile.argtypes = [C.c_void_p, f64p, C.c_int32, C.c_int32, f64p]
     L.pz_filter_read_particles.argtypes = [C.c_void_p, C.c_int32, f64p, C.c_int64]
     L.pz_filter_read_tracks.argtypes = [C.c_void_p, C.c_int32, i32p, i32p, f64p, f64p, C.c_int64]
+    L.pz_filter_read_mcam_tracks.argtypes = [C.c_void_p, C.c_int32, i32p, i32p, i32p, i32p, f64p, f64p, f64p, i32p, f64p, f64p, C.c_int64]
     L.pz_filter_read_ancestors.argtypes = [C.c_void_p, i32p, C.c_int64]
     L.pz_filter_read_state.argtypes = [C.c_void_p, f32p, C.c_int64]
     L.pz_filter_read_logw.argtypes = [C.c_void_p, f32p, C.c_int64]
@@ -190,6 +192,13 @@ def mtt_track(resampler=PZ_RESAMPLE_SYSTEMATIC, delay=False, f64=False, carry_we
     return _variants(d, carry_weights, ess_threshold)
 
 
+def multicam():
+    """MultiCamera tracker constants: Examples/MultiCamera.hs:40-227.  Observation rows: (camera, pose[10], box[4], reading)."""
+    d = ModelDesc()
+    _check(lib().pz_model_multicam(C.byref(d)))
+    return d
+
+
 def mtt():
     """Multi-target tracker constants: Examples/MultiTargetTracking.hs:36-145."""
     d = ModelDesc()
@@ -246,6 +255,8 @@ class ZStream:
         s = StepSummary()
         if self.model.kind == PZ_MODEL_MTT:   # a (possibly empty) list of 2-D detections
             rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double) if y.size else None, y.size // 2, 2, C.byref(s))
+        elif self.model.kind == PZ_MODEL_MULTICAM:   # a (possibly empty) list of rows (camera, pose[10], box[4], reading)
+            rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double) if y.size else None, y.size // 16, 16, C.byref(s))
         else:
             rc = lib().pz_filter_step(self._h, _ptr(y, C.c_double), 1, y.size, C.byref(s))
         if rc in (0, -3, -4, -5):   # the library advanced its step for every one of these codes
@@ -261,6 +272,28 @@ class ZStream:
         _check(lib().pz_filter_read_tracks(self._h, stride, _ptr(cnt, C.c_int32), _ptr(ids, C.c_int32), _ptr(mean, C.c_double),
                                            _ptr(cov, C.c_double), n_sel))
         return [[(int(ids[i, k]), mean[i, k].copy(), cov[i, k].copy()) for k in range(cnt[i])] for i in range(n_sel)]
+
+    def read_mcam_tracks(self, stride=1, appearances=False):
+        """MultiCamera output (processObservationsStream, MultiCamera.hs:208-216): per selected resampled particle a dict
+        {"tracks": [(trackID, identity, camera, startTime, mean[4], var[4])], "n_app": A[, "app": [(mean[10], cov[10,10])]]}."""
+        n_sel = (self.n + stride - 1) // stride
+        cnt = np.zeros(n_sel, np.int32); ids = np.zeros((n_sel, 16), np.int32); idn = np.zeros((n_sel, 16), np.int32)
+        cam = np.zeros((n_sel, 16), np.int32); st = np.zeros((n_sel, 16)); mean = np.zeros((n_sel, 16, 4)); var = np.zeros((n_sel, 16, 4))
+        na = np.zeros(n_sel, np.int32)
+        am = np.zeros((n_sel, 16, 10)) if appearances else None
+        ac = np.zeros((n_sel, 16, 10, 10)) if appearances else None
+        _check(lib().pz_filter_read_mcam_tracks(self._h, stride, _ptr(cnt, C.c_int32), _ptr(ids, C.c_int32), _ptr(idn, C.c_int32),
+                                                _ptr(cam, C.c_int32), _ptr(st, C.c_double), _ptr(mean, C.c_double), _ptr(var, C.c_double),
+                                                _ptr(na, C.c_int32), _ptr(am, C.c_double) if appearances else None,
+                                                _ptr(ac, C.c_double) if appearances else None, n_sel))
+        out = []
+        for i in range(n_sel):
+            p = {"tracks": [(int(ids[i, k]), int(idn[i, k]), int(cam[i, k]), float(st[i, k]), mean[i, k].copy(), var[i, k].copy())
+                            for k in range(cnt[i])], "n_app": int(na[i])}
+            if appearances:
+                p["app"] = [(am[i, a].copy(), ac[i, a].copy()) for a in range(na[i])]
+            out.append(p)
+        return out
 
     def run(self, observations, want_summaries=True):
         """runStream over a whole observation array [T, ny]; returns the T summaries."""

@@ -117,6 +117,25 @@ def model_mtt():
     return d
 
 
+PZ_MODEL_MULTICAM = 6
+
+
+def model_multicam():
+    """Examples/MultiCamera.hs:77-78, 88-94, 110-126, 128-132, 182-195: the tracker's constants, written out independently of
+    pz_model_multicam (test_abi compares the two)."""
+    d = ModelDesc()
+    d.kind, d.nx, d.ny, d.scalar_ll_2x = PZ_MODEL_MULTICAM, 4, 0, 1   # ny = 0: H = I and R = meas_var I are implied
+    for i in range(4):
+        d.F[i * 4 + i] = 1.0
+        d.Q[i * 4 + i] = 1.0 if i < 2 else 0.1
+    d.x0[2] = d.x0[3] = 1.0
+    d.mtt.clutter_lambda, d.mtt.new_track_lambda, d.mtt.pd = 1.0, 0.1, 1.0
+    d.mtt.survival_prob = float(np.exp(-0.02))
+    d.mtt.clutter_var, d.mtt.birth_pos_var, d.mtt.birth_vel_var, d.mtt.meas_var = 1.0, 1.0, 0.2, 1.0
+    d.mtt.k_max, d.mtt.m_max = 16, 32
+    return d
+
+
 def desc_arrays(desc):
     nx, ny = desc.nx, desc.ny
     F = np.array(desc.F[: nx * nx]).reshape(nx, nx)
@@ -177,6 +196,14 @@ def oracle():
     lib.pzo_refpf_run.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64, f64p, C.c_int64, C.c_int, f64p, f64p, C.c_int]
     lib.pzo_num_threads.restype = C.c_int
     lib.pzo_mtt_generate.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_int64, C.c_int32, f64p, i32p, f64p, i32p]
+    lib.pzo_mcam_create.restype = C.c_void_p
+    lib.pzo_mcam_create.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64]
+    lib.pzo_mcam_destroy.argtypes = [C.c_void_p]
+    lib.pzo_mcam_step.argtypes = [C.c_void_p, f64p, C.c_int32, f64p, f64p, f64p]
+    lib.pzo_mcam_logw.argtypes = [C.c_void_p, f32p]
+    lib.pzo_mcam_particle.argtypes = [C.c_void_p, C.c_int64, i32p, i32p, i32p, f64p, f64p, i32p]
+    lib.pzo_mcam_appearance.argtypes = [C.c_void_p, C.c_int64, C.c_int32, f64p, f64p]
+    lib.pzo_mcam_generate.argtypes = [C.POINTER(ModelDesc), C.c_uint64, C.c_int64, C.c_int32, f64p, i32p, f64p, i32p]
     lib.pzo_mtt_create.restype = C.c_void_p
     lib.pzo_mtt_create.argtypes = [C.POINTER(ModelDesc), C.c_int64, C.c_uint64]
     lib.pzo_mtt_destroy.argtypes = [C.c_void_p]
@@ -345,6 +372,55 @@ def mtt_scenario(T, seed=5):
     lib.pzo_mtt_generate(C.byref(d), seed, T, 32, ptr(obs, C.c_double), ptr(nobs, C.c_int32), ptr(truth, C.c_double), ptr(ntr, C.c_int32))
     return d, [np.ascontiguousarray(obs[t, :nobs[t]]) for t in range(T)], \
         [[(int(truth[t, k, 0]), truth[t, k, 1:].copy()) for k in range(ntr[t])] for t in range(T)]
+
+
+def mcam_scenario(T, seed=11, clutter=0.05):
+    """Ground truth + observation rows from the generative model (generateGroundTruth, MultiCamera.hs:218-219).
+    Returns (desc, [obs_t as (M_t, 16) arrays], [truth_t as list of (id, identity, camera, box[4])]).
+    `clutter` replaces amtClutter = 1 in generator AND filter: the reference's track hypothesis scores a pose with the
+    constant uniform-sphere density whatever its norm (MVDistributions.hs:59-61), e^11 above the clutter's N(0, I10) pose
+    density, so at amtClutter = 1 every clutter row is explained by a newborn track that the next step cannot feed, and the
+    population dies (passert False, :168-169) within ~20 steps at any affordable N -- in the reference as in this restatement
+    (tests/test_mcam.py::test_reference_constants_starve_the_population shows it)."""
+    lib = oracle()
+    d = model_multicam()
+    d.mtt.clutter_lambda = clutter
+    obs = np.zeros((T, 32, 16)); nobs = np.zeros(T, np.int32)
+    truth = np.zeros((T, 16, 7)); ntr = np.zeros(T, np.int32)
+    lib.pzo_mcam_generate(C.byref(d), seed, T, 32, ptr(obs, C.c_double), ptr(nobs, C.c_int32), ptr(truth, C.c_double), ptr(ntr, C.c_int32))
+    return d, [np.ascontiguousarray(obs[t, :nobs[t]]) for t in range(T)], \
+        [[(int(truth[t, k, 0]), int(truth[t, k, 1]), int(truth[t, k, 2]), truth[t, k, 3:].copy()) for k in range(ntr[t])] for t in range(T)]
+
+
+class OracleMcam:
+    def __init__(self, desc, n, seed):
+        self.lib = oracle(); self.n = n
+        self.h = self.lib.pzo_mcam_create(C.byref(desc), n, seed)
+
+    def step(self, obs):
+        o = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 16)
+        m, v, lz = C.c_double(), C.c_double(), C.c_double()
+        rc = self.lib.pzo_mcam_step(self.h, ptr(o, C.c_double) if o.size else None, o.shape[0], C.byref(m), C.byref(v), C.byref(lz))
+        return rc, m.value, v.value, lz.value
+
+    def logw(self):
+        out = np.zeros(self.n, np.float32); self.lib.pzo_mcam_logw(self.h, ptr(out, C.c_float)); return out
+
+    def particle(self, i):
+        ids = np.zeros(16, np.int32); idn = np.zeros(16, np.int32); cam = np.zeros(16, np.int32)
+        mean = np.zeros((16, 4)); cov = np.zeros((16, 4, 4)); na = C.c_int32()
+        k = self.lib.pzo_mcam_particle(self.h, i, ptr(ids, C.c_int32), ptr(idn, C.c_int32), ptr(cam, C.c_int32), ptr(mean, C.c_double),
+                                       ptr(cov, C.c_double), C.byref(na))
+        return [(int(ids[q]), int(idn[q]), int(cam[q]), mean[q].copy(), cov[q].copy()) for q in range(k)], na.value
+
+    def appearance(self, i, a):
+        m = np.zeros(10); c = np.zeros((10, 10))
+        assert self.lib.pzo_mcam_appearance(self.h, i, a, ptr(m, C.c_double), ptr(c, C.c_double)) == 0
+        return m, c
+
+    def close(self):
+        if self.h:
+            self.lib.pzo_mcam_destroy(self.h); self.h = None
 
 
 class OracleMtt:
