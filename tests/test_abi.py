@@ -104,7 +104,13 @@ def test_every_argument_error_is_reported_before_device_work(pz):
     rc, msg = create(pz.mtt(), (1 << 28) + 1)
     assert rc == -1 and b"2^28" in msg
     rc, msg = create(pz.mtt(), 2 * 256 * 8, rank=0, world=2)
-    assert rc == -1 and b"one GPU" in msg
+    assert rc == -1 and b"pz_filter_create_multi" in msg   # a tracker over several GPUs is a single-process multi-device filter
+    mc = pz.multicam(); mc.F[1] = 0.5
+    rc, msg = create(mc, 1000)
+    assert rc == -1 and b"F = I" in msg
+    mc = pz.multicam(); mc.mtt.pd = 0.9
+    rc, msg = create(mc, 1000)
+    assert rc == -1 and b"pd = 1" in msg
     # null handles / buffers
     s = pz.StepSummary()
     y = (C.c_double * 1)(0.0)
