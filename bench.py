@@ -269,11 +269,12 @@ def synth_mtt_scenario(d, T, seed=5, m_max=32, warm_tracks=0):
     return out
 
 
-def measure_mtt(pz, n_p, K, W, tracks, with_cpu):
-    """configs[3]: the multi-target tracker (N = 10^6, up to 16 tracks), detections streamed step by step."""
+def measure_mtt(pz, n_p, K, W, tracks, with_cpu, devices=1):
+    """configs[3]: the multi-target tracker (N = 10^6, up to 16 tracks), detections streamed step by step.
+    devices > 1: configs[4]'s sharded tracker -- ONE process drives `devices` GPUs (pz_filter_create_multi), n_p particles in total."""
     import torch
     obs = synth_mtt_scenario(pz.mtt(), W + K, seed=5, warm_tracks=tracks)
-    zs = pz.zparticles(n_p, pz.mtt(), seed=1)
+    zs = pz.zparticles(n_p, pz.mtt(), seed=1) if devices <= 1 else pz.zparticles_multi(n_p, pz.mtt(), list(range(devices)), seed=1)
     for o in obs[:W]:
         zs.step(o)
     torch.cuda.synchronize()
@@ -292,7 +293,7 @@ def measure_mtt(pz, n_p, K, W, tracks, with_cpu):
     out = {
         "value": n_p * K / (dev_ms * 1e-3), "unit": "particle-updates/s", "ms_per_step": dev_ms / K, "dtype": "f32",
         "workload": f"multi-target tracker (MultiTargetTracking.hs), N={n_p} particles, up to 16 Rao-Blackwellised tracks (BASELINE.json configs[3])",
-        "mean_tracks_last_step": float(post.mean[0]), "steps": K,
+        "mean_tracks_last_step": float(post.mean[0]), "steps": K, "n_devices": devices,
         "e2e": {"value": n_p * K / wall, "unit": "particle-updates/s", "h2d_bytes_per_step": 8 * int(np.mean([len(o) for o in obs[W:]])),
                 "d2h_bytes_per_step": 144, "ms_per_step": wall / K * 1e3},
         "gpu_launches": int(launches),
@@ -523,6 +524,10 @@ def run_b200(args):
             for dt in ("f32", "f64"):
                 legs[f"{m}_{dt}"] = measure_lg(pz, m, dt, 10_000_000, kl, 3)
         legs["mtt_f32"] = measure_mtt(pz, 1_000_000, 10, 3, args.mtt_tracks, with_cpu=False)
+        import torch
+        if torch.cuda.device_count() >= 2:   # configs[4]'s sharded tracker: one process, every GPU of the box, 10^6 particles per GPU
+            nd = min(torch.cuda.device_count(), 8)
+            legs[f"mtt_f32_{nd}_devices"] = measure_mtt(pz, 1_000_000 * nd, 10, 3, args.mtt_tracks, with_cpu=False, devices=nd)
         legs["sustained_rw1d_" + args.dtype] = measure_lg(pz, "rw1d", args.dtype, n_p, 5, 3, profile=False, sustained=1000)["sustained"]
 
     # ---- CPU baseline on this box's host cores (bounded sample)
@@ -581,9 +586,9 @@ def run_mtt(args):
         raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback")
     pz = g.load_package()
     sampler = ClockSampler(0); sampler.start()
-    leg = measure_mtt(pz, args.particles, args.steps, args.warmup, args.mtt_tracks, with_cpu=not args.no_cpu)
+    leg = measure_mtt(pz, args.particles, args.steps, args.warmup, args.mtt_tracks, with_cpu=not args.no_cpu, devices=args.devices)
     clocks = sampler.summary()
-    line = {"metric": "particle-updates/sec", "value": leg["value"], "unit": leg["unit"], "n_gpus": 1, "steps": args.steps,
+    line = {"metric": "particle-updates/sec", "value": leg["value"], "unit": leg["unit"], "n_gpus": args.devices, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": leg["workload"], "model": "mtt", "particles_per_gpu": args.particles,
@@ -609,6 +614,7 @@ def main():
     ap.add_argument("--no-legs", action="store_true", help="skip the extra single-GPU legs of the default run")
     ap.add_argument("--no-parity", action="store_true", help="skip the sharded bit-equality check before the timed region")
     ap.add_argument("--mtt-tracks", type=int, default=8, help="tracker bench: targets present at t = 0")
+    ap.add_argument("--devices", type=int, default=1, help="tracker bench (--model mtt): GPUs driven by this ONE process (pz_filter_create_multi); --particles is the total")
     args = ap.parse_args()
     args.gpus = int(os.environ.get("WORLD_SIZE", args.gpus))
     if args.impl == "reference":

@@ -15,10 +15,10 @@
 -- arithmetic, by host/shim_mirror.c (tests/test_host_cli.py), by tests/ (ctypes) and by
 -- host/examples_gpu.cpp.
 module PzGpu
-  ( ModelDesc, Posterior (..), Track (..)
-  , rw1d, stt, sttDelayed, mttTrack, mtt, walker, betaBernoulli, withDouble, withDevices
+  ( ModelDesc, Posterior (..), Track (..), CamTrack (..)
+  , rw1d, stt, sttDelayed, mttTrack, mtt, multiCamera, walker, betaBernoulli, withDouble, withDevices
   , inferGPU, inferGPUOn, zparticlesGPU, zdsparticlesGPU, runStreamGPU, runAllGPU
-  , mttGPU
+  , mttGPU, multiCameraGPU
   ) where
 
 import Control.Monad (when, forM)
@@ -54,10 +54,18 @@ data Posterior = Posterior
 -- | One entry of the tracker's `Map id (mean, cov)` (MultiTargetTracking.hs:133-139).
 data Track = Track { trackId :: Int32, trackMean :: [Double], trackCov :: [[Double]] }
 
+-- | `MarginalTrack` of Examples/MultiCamera.hs:48-69: the box marginal (its covariance is diagonal), trackID, identity, camera.
+data CamTrack = CamTrack { camTrackId :: Int32, camIdentity :: Int32, camCamera :: Int32, camStart :: Double
+                         , camBoxMean :: [Double], camBoxVar :: [Double] }
+
 foreign import ccall unsafe "pz_model_rw1d" c_model_rw1d :: Ptr () -> CDouble -> CDouble -> IO CInt
 foreign import ccall unsafe "pz_model_stt" c_model_stt :: Ptr () -> IO CInt
 foreign import ccall unsafe "pz_model_mtt_track" c_model_mtt_track :: Ptr () -> IO CInt
 foreign import ccall unsafe "pz_model_mtt" c_model_mtt :: Ptr () -> IO CInt
+foreign import ccall unsafe "pz_model_multicam" c_model_multicam :: Ptr () -> IO CInt
+foreign import ccall unsafe "pz_filter_read_mcam_tracks"
+  c_read_mcam_tracks :: Ptr PzFilter -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr CDouble -> Ptr CDouble
+                     -> Ptr CDouble -> Ptr Int32 -> Ptr CDouble -> Ptr CDouble -> Int64 -> IO CInt
 foreign import ccall unsafe "pz_model_walker" c_model_walker :: Ptr () -> IO CInt
 foreign import ccall unsafe "pz_model_beta_bernoulli" c_model_beta_bernoulli :: Ptr () -> CDouble -> CDouble -> IO CInt
 foreign import ccall safe "pz_filter_create"
@@ -109,6 +117,10 @@ sttDelayed = do
 -- | The per-track model of Examples/MultiTargetTracking.hs:56-73.
 mttTrack :: IO ModelDesc
 mttTrack = mkDesc c_model_mtt_track
+
+-- | The two-camera tracker, Examples/MultiCamera.hs:40-227.
+multiCamera :: IO ModelDesc
+multiCamera = mkDesc c_model_multicam
 
 -- | The multi-target tracker, Examples/MultiTargetTracking.hs:26-145 (`examples mtt N`).
 mtt :: IO ModelDesc
@@ -232,5 +244,38 @@ mttGPU n seed = do
                       m <- peekArray 4 (pm `advancePtr` ((i * 16 + j) * 4))
                       v <- peekArray 16 (pv `advancePtr` ((i * 16 + j) * 16))
                       pure (Track tid (map realToFrac m) (chunks 4 (map realToFrac v)))
+          pure ((), (Posterior st le es mu va (const (pure [])), tracks))
+  pure (ZS.fromStep stepf ())
+
+-- | `MultiCamera.runMTTPF` (Examples/MultiCamera.hs:221-225): each step takes the frame's observation rows
+-- (camera, pose[10], box[4], appearance reading) and returns the posterior summary and, for every k-th resampled particle,
+-- its list of marginal tracks.
+multiCameraGPU :: Int -> Word64 -> IO (ZStream IO [[Double]] (Posterior, Int -> IO [[CamTrack]]))
+multiCameraGPU n seed = do
+  d@(ModelDesc dfp) <- multiCamera
+  h <- withForeignPtr dfp $ \dp -> alloca $ \out -> c_filter_create dp (fromIntegral n) seed 0 out >>= check >> peek out
+  fh <- newForeignPtr p_filter_destroy h
+  nx <- descNx d
+  let stepf () rows = withForeignPtr fh $ \f ->
+        withArray (map realToFrac (concat rows)) $ \po ->
+        allocaBytes sizeofSummary $ \ps -> do
+          c_filter_step f po (fromIntegral (length rows)) 16 ps >>= check
+          (st, le, es, mu, va) <- readSummary nx ps
+          let tracks k = withForeignPtr fh $ \f' -> do
+                nl <- c_n_local f'
+                let sel = (fromIntegral nl + k - 1) `div` k
+                allocaArray sel $ \pc -> allocaArray (sel * 16) $ \pid -> allocaArray (sel * 16) $ \pidn ->
+                  allocaArray (sel * 16) $ \pcam -> allocaArray (sel * 16) $ \pst ->
+                  allocaArray (sel * 16 * 4) $ \pm -> allocaArray (sel * 16 * 4) $ \pv -> do
+                    c_read_mcam_tracks f' (fromIntegral k) pc pid pidn pcam pst pm pv nullPtr nullPtr nullPtr (fromIntegral sel) >>= check
+                    cnt <- peekArray sel pc
+                    forM (zip [0 ..] cnt) $ \(i, c) -> forM [0 .. fromIntegral c - 1] $ \j -> do
+                      tid <- peekElemOff pid (i * 16 + j)
+                      idn <- peekElemOff pidn (i * 16 + j)
+                      cam <- peekElemOff pcam (i * 16 + j)
+                      s0 <- peekElemOff pst (i * 16 + j)
+                      m <- peekArray 4 (pm `advancePtr` ((i * 16 + j) * 4))
+                      v <- peekArray 4 (pv `advancePtr` ((i * 16 + j) * 4))
+                      pure (CamTrack tid idn cam (realToFrac s0) (map realToFrac m) (map realToFrac v))
           pure ((), (Posterior st le es mu va (const (pure [])), tracks))
   pure (ZS.fromStep stepf ())

@@ -151,6 +151,44 @@ int main(int argc, char** argv) {
     pz_filter_destroy(f);
   }
 
+  /* multiCameraGPU: observation rows (camera, pose[10], box[4], reading), then marginal tracks k (no appearance readout) */
+  {
+    check(pz_model_multicam((pz_model_desc*)d), "pz_model_multicam");
+    pz_filter* f = NULL;
+    check(pz_filter_create((const pz_model_desc*)d, 4000, 3, 0, &f), "pz_filter_create");
+    char ps[SIZEOF_SUMMARY];
+    double rows[2][16];
+    for (int t = 0; t < 3; ++t) {
+      for (int c = 0; c < 2; ++c) {
+        for (int i = 0; i < 16; ++i) rows[c][i] = 0.0;
+        rows[c][0] = c; rows[c][1 + (t + c) % 10] = 1.0;                       /* a unit pose */
+        rows[c][11] = 0.3 * t - 0.2 * c; rows[c][12] = 0.1 * c; rows[c][13] = 1.0; rows[c][14] = 1.1; rows[c][15] = 0.4 - 0.3 * c;
+      }
+      check(pz_filter_step(f, &rows[0][0], 2, 16, (pz_step_summary*)ps), "pz_filter_step (multicam)");
+    }
+    const int k = 500;
+    const int64_t nl = pz_filter_n_local(f), sel = (nl + k - 1) / k;
+    int32_t* pc = (int32_t*)malloc(sizeof(int32_t) * (size_t)sel);
+    int32_t* pid = (int32_t*)malloc(sizeof(int32_t) * (size_t)sel * 16);
+    int32_t* pidn = (int32_t*)malloc(sizeof(int32_t) * (size_t)sel * 16);
+    int32_t* pcam = (int32_t*)malloc(sizeof(int32_t) * (size_t)sel * 16);
+    double* pst = (double*)malloc(sizeof(double) * (size_t)sel * 16);
+    double* pm = (double*)malloc(sizeof(double) * (size_t)sel * 16 * 4);
+    double* pv = (double*)malloc(sizeof(double) * (size_t)sel * 16 * 4);
+    check(pz_filter_read_mcam_tracks(f, k, pc, pid, pidn, pcam, pst, pm, pv, NULL, NULL, NULL, sel), "pz_filter_read_mcam_tracks");
+    printf("{\"scenario\":\"multicam\",\"rows\":%lld,\"particles\":[", (long long)sel);
+    for (int64_t i = 0; i < sel; ++i) {
+      printf("%s[", i ? "," : "");
+      for (int j = 0; j < pc[i]; ++j)
+        printf("%s[%d,%d,%d,[%.9g,%.9g],%.9g]", j ? "," : "", pid[i * 16 + j], pidn[i * 16 + j], pcam[i * 16 + j], pm[(i * 16 + j) * 4],
+               pm[(i * 16 + j) * 4 + 1], pv[(i * 16 + j) * 4]);
+      printf("]");
+    }
+    printf("]}\n");
+    free(pc); free(pid); free(pidn); free(pcam); free(pst); free(pm); free(pv);
+    pz_filter_destroy(f);
+  }
+
   if (n_devices > 1) {   /* withDevices [0 .. n_devices - 1] */
     check(pz_model_mtt_track((pz_model_desc*)d), "pz_model_mtt_track");
     scenario_lg("multi_mtt_track", d, 256 * 40 * n_devices, n_devices, 1);

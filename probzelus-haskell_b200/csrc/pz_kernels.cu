@@ -770,6 +770,7 @@ struct StateSource {
     }
   }
   __device__ __forceinline__ void put(T* s_par, int stride, int slot, int k) const {
+    PZ_ASSERT(slot >= 0 && slot < stride);
 #pragma unroll
     for (int d = 0; d < NX; ++d) s_par[d * stride + slot] = v[d][k];
   }
@@ -788,7 +789,10 @@ struct IndexSource {  // generic path: payload = particle index
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[0][k] = __int_as_float((int32_t)i0 + k);
   }
-  __device__ __forceinline__ void put(float* s_par, int, int slot, int k) const { s_par[slot] = v[0][k]; }
+  __device__ __forceinline__ void put(float* s_par, int stride, int slot, int k) const {
+    PZ_ASSERT(slot >= 0 && slot < stride);
+    s_par[slot] = v[0][k];
+  }
   __device__ __forceinline__ float first(int k) const { return v[0][k]; }
 };
 
@@ -809,7 +813,7 @@ __device__ __forceinline__ void emit_head(const Source& src, typename Source::Sc
 // per-particle fast path.  The payload travels by value, so the caller's sources stay in registers.
 template <class S>
 __device__ __noinline__ void emit_long_runs(S payload, S* s_par, int lo, int hi) {
-  for (int s = (lo | 127) + 1; s < hi; s += 128) s_par[s] = payload;
+  for (int s = (lo | 127) + 1; s < hi; s += 128) { PZ_ASSERT(s >= 0); s_par[s] = payload; }
 }
 
 // Input side of one output tile [j0, j0 + nslots): every warp takes input blocks b_first + warp,
@@ -887,6 +891,7 @@ __device__ __forceinline__ bool resample_block(const Source& src, typename Sourc
     for (int k = 0; k < 8; ++k) e[k] = min(max(e[k], 0), nslots);
   }
   const int32_t eprev0 = eprev;
+  PZ_ASSERT(eprev0 >= 0 && e[7] <= nslots && e[7] >= eprev0);
 #pragma unroll
   for (int k = 0; k < 4; ++k) { emit_head<SEGDUP>(sa, s_par, stride, eprev, e[k], k); eprev = e[k]; }
 #pragma unroll
@@ -1061,6 +1066,7 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       for (int k = 0; k < 4; ++k) {
         if (head[k] != sl + k) {
           const int hk = FULL ? head[k] : max(head[k], 0);
+          PZ_ASSERT(hk >= 0 && hk < TO && hk <= sl + k);
 #pragma unroll
           for (int d = 0; d < NX; ++d) xp[d][k] = s_par[d * TO + hk];
         }
@@ -1273,6 +1279,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   if constexpr (MODE == 0) {
     // the first input block's weights: in flight during the prologue
     const int64_t b_first = (int64_t)a.tile_start[tile];
+    PZ_ASSERT(remote || (b_first >= a.b_lo && b_first <= a.b_hi));
     if (!remote && a.p2p != nullptr) {
       // sharded over peer memory: a boundary tile (its input blocks reach into a halo) waits here for the
       // neighbour's margins of this epoch (state / weights / exponents from pf_halo_push, boundary positions from
@@ -1325,6 +1332,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   } else {
     for (int sidx = tid; sidx < nslots; sidx += NT) {
       const int64_t p = ta.anc[j0l + sidx];
+      PZ_ASSERT(p >= 0 && p < a.n_local);
 #pragma unroll
       for (int d = 0; d < NX; ++d) s_par[d * TO + sidx] = xin[(size_t)d * a.ld + p];
     }
@@ -1464,7 +1472,10 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
     resolve_heads(bits, sl, lane, -1, head);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (sl + k < nslots) g.anc[j0 + sl + k] = head[k] >= 0 ? __float_as_int(s_anc[head[k]]) : -1;
+      if (sl + k < nslots) {
+        PZ_ASSERT(head[k] >= 0 && head[k] < TO && __float_as_int(s_anc[head[k]]) >= 0 && __float_as_int(s_anc[head[k]]) < g.n);
+        g.anc[j0 + sl + k] = head[k] >= 0 ? __float_as_int(s_anc[head[k]]) : -1;
+      }
   }
 }
 

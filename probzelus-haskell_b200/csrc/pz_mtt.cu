@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
   uint32_t* __restrict__ dst = a.sout + (size_t)(j - a.j0) * kMttWords;
   const uint4 hdr = *reinterpret_cast<const uint4*>(src);
   const int cnt = (int)hdr.x;
+  PZ_ASSERT(par >= 0 && cnt >= 0 && cnt <= 16 && (a.n_per == 0 || par / a.n_per < kMttMaxDevices));
   const int cnt_fast = cnt < kMttFast ? cnt : kMttFast;
   const int next_id = (int)hdr.y;
   const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(kMttThreads) mcam_step(const __grid_constant__
   const uint4 hdr = *reinterpret_cast<const uint4*>(src);
   const int cnt = (int)hdr.x;
   int num_tracks = (int)hdr.y, A = (int)hdr.z;
+  PZ_ASSERT(par >= 0 && cnt >= 0 && cnt <= kMcK && A >= 0 && A <= kMcA);
   McRng rng{(uint32_t)j, t, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), 0u, U4{0, 0, 0, 0}, 0};
   // the parent's appearances
   for (int ap = 0; ap < A; ++ap) {
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(kMttThreads) mcam_step(const __grid_constant__
       ++nT;
       if (!rem) { dead = true; break; }   // passert False: more tracks than observations in this camera
       const int identity = (int)tw[1];
+      PZ_ASSERT(identity >= 0 && identity < A);
       float m[4], v[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { m[i] = __uint_as_float(tw[4 + i]); v[i] = __uint_as_float(tw[8 + i]); }
@@ -560,6 +563,7 @@ __global__ void __launch_bounds__(kMttThreads) mcam_step(const __grid_constant__
         if (pick < 0 && cum > target) pick = o;
       }
       if (pick < 0) pick = last;
+      PZ_ASSERT(pick >= 0 && pick < M && ((rem >> pick) & 1u));
       lw += mx + __logf(total);
       rem &= ~(1u << pick);
       const float* row = s_obs[pick];

@@ -144,6 +144,21 @@ def test_shim_mirror_runs_the_haskell_call_sequence(pz):
     for p in m["particles"]:
         for tid, mean, var in p:
             assert tid >= 0 and all(np.isfinite(mean)) and var > 0
+    mc = sc["multicam"]   # multiCameraGPU: same call sequence through ctypes gives the same marginal tracks
+    zs = pz.zparticles(4000, pz.multicam(), seed=3)
+    for t in range(3):
+        rows = np.zeros((2, 16))
+        for c in range(2):
+            rows[c, 0] = c; rows[c, 1 + (t + c) % 10] = 1.0
+            rows[c, 11:16] = [0.3 * t - 0.2 * c, 0.1 * c, 1.0, 1.1, 0.4 - 0.3 * c]
+        zs.step(rows)
+    mine = zs.read_mcam_tracks(stride=500)
+    assert mc["rows"] == 8 == len(mine)
+    for got, p in zip(mc["particles"], mine):
+        assert [(g[0], g[1], g[2]) for g in got] == [(t[0], t[1], t[2]) for t in p["tracks"]]
+        for g, t in zip(got, p["tracks"]):
+            assert np.allclose(g[3], t[4][:2], rtol=1e-8) and np.isclose(g[4], t[5][0], rtol=1e-8)
+    zs.close()
     if ndev > 1:   # withDevices: the posterior of the multi-device handle equals the single-device one
         a, b = sc["multi_mtt_track"], sc["single_mtt_track_same_n"]
         assert a["n_local"] == 256 * 40 * ndev

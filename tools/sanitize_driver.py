@@ -36,6 +36,26 @@ if mode == "all":
         zs.step(rng.standard_normal((3, 2)) * 3)
     zs.read_tracks(100)
     zs.close()
+    # MultiCamera tracker: one row per camera, plus a clutter-like row
+    zs = pz.zparticles(4096, pz.multicam(), seed=4)
+    for t in range(3):
+        rows = np.zeros((3, 16)); rows[:, 0] = [0, 1, 1]
+        rows[:, 1:11] = rng.standard_normal((3, 10)); rows[:, 1:11] /= np.linalg.norm(rows[:, 1:11], axis=1, keepdims=True)
+        rows[:, 11:15] = rng.standard_normal((3, 4)) + [0, 0, 1, 1]; rows[:, 15] = rng.standard_normal(3)
+        try:
+            zs.step(rows)
+        except pz.PzError:
+            break
+    zs.read_mcam_tracks(100, appearances=True)
+    zs.close()
+    # the sharded tracker path with every shard on device 0 (test hook): ancestors per tile range, peer-pointer parent
+    # reads, slice pushes, event-ordered global plan
+    os.environ["PZ_MULTI_SAME_DEVICE"] = "1"
+    zs = pz.zparticles_multi(3 * 2048 + 500, pz.mtt(), [0, 0, 0], seed=3)
+    for t in range(3):
+        zs.step(rng.standard_normal((3, 2)) * 3)
+    zs.read_tracks(100)
+    zs.close()
     zs = pz.zparticles(100, pz.beta_bernoulli(), seed=0)
     zs.step([1.0]); zs.close()
     pz.resample_systematic(rng.standard_normal(5000), 0.3)
