@@ -28,6 +28,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "pz_kernels.cuh"
 #include "pz_math.cuh"
@@ -1018,6 +1019,25 @@ struct TileArgs {
 // N = 10^7 / 10^8 -- LG(4,2) f64 0.2293 -> 0.2242 ms, LG(6,3) f64 0.3594 -> 0.3508, LG(6,3) f32 0.1992 -> 0.1972, but
 // RW1D f64 0.5176 -> 0.5611, RW1D f32 0.4142 -> 0.4613, LG(4,2) f32 0.1501 -> 0.1561: the one-word states keep one CTA per tile
 template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE || (NX > 1 && (sizeof(T) == 8 || NX > 4));
+// index staging for the one-word states (PZ_IDX1: bit 0 fp32, bit 1 fp64): the input side stages the parent's INDEX (4 bytes
+// per head slot, no payload loads, no payload registers) and the output side gathers the parent's state from global memory
+// (sorted ancestors: the loads of a warp fall into a few adjacent lines)
+// Measured (RW1D, N = 10^8, pf_step_tile): fp64 0.4978 ms state-staged (6 CTAs per SM, 80 registers, 15-block tiles) ->
+// 0.4568 ms index-staged at 8 CTAs per SM (64 registers, 23-block tiles: 4 bytes per staged slot leave room for both);
+// index-staged at the old occupancy 0.5098 (the gather's extra latency without the extra warps); 9 / 10 CTAs 0.512 / 0.655
+// (spills).  fp32: 0.3806 state-staged vs 0.4008 index-staged (its staged word is 4 bytes either way), so fp32 stays.
+#ifndef PZ_IDX1
+#define PZ_IDX1 2
+#endif
+// PZ_IDXN: the same for the wide states (bit 0 / 1: NX = 4 fp32 / fp64, bit 2 / 3: NX = 6 fp32 / fp64); their centred new
+// states, which the moment pass reads back, then go through a per-warp scratch [NX][256] of floats instead of the
+// staging buffer (every lane reads back exactly what it wrote: no synchronisation)
+#ifndef PZ_IDXN
+#define PZ_IDXN 0
+#endif
+template <class T, int NX, int MODE, bool REMOTE> constexpr bool kIdxStage =
+    MODE == 0 && !REMOTE &&
+    (NX == 1 ? (((PZ_IDX1) >> (sizeof(T) == 8 ? 1 : 0)) & 1) : (((PZ_IDXN) >> ((NX <= 4 ? 0 : 2) + (sizeof(T) == 8 ? 1 : 0))) & 1));
 template <int NX> constexpr bool kPackModel = ((PZ_PACK_MODEL) >> (NX == 1 ? 0 : (NX <= 4 ? 1 : 2))) & 1;
 constexpr int min_ctas(int nx) { return nx == 1 ? PZ_OCC1 : (nx <= 4 ? PZ_OCC4 : PZ_OCC6); }
 #define PZ_NACC(nx) (2 + 2 * (nx))
@@ -1034,8 +1054,8 @@ __device__ __forceinline__ float lw_key(double lw) { return __double2float_rn(lw
 // machinery: the log-weight rounded to fp32 enters the block maximum and the weight polynomial, the centred state
 // x' - c (formed in double) is rounded to fp32 for the moment sums.  (Keeping those in double costs 24 registers
 // and an occupancy step for nothing the 16-bit weights or the fp64 tile totals could show.)
-template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL>
-__device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const float4* __restrict__ tab_m8, int ob,
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL, bool IDX, class S>
+__device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float* s_dx, const float4* __restrict__ tab_m8, int ob,
                                              int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const T* y_new,
                                              const T* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref) {
   T* __restrict__ xout = reinterpret_cast<T*>(a.X[nxt]);
@@ -1052,12 +1072,34 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
   for (int half = 0; half < 2; ++half) {
     const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
     T xp[NX][4];
+    if constexpr (IDX) {
+      // staged parent indices: resolve the heads, then gather the parents' states from global memory
+      const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[nxt ^ 1]);
+      const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
+      int head[4];
+      seg_carry = resolve_heads(bits, sl, lane, seg_carry, head);
+      if constexpr (NX != 1) seg_carry = -1;
+      const uint32_t own[4] = {bits.x, bits.y, bits.z, bits.w};
+      int32_t pidx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int hk = FULL ? head[k] : max(head[k], 0);
+        PZ_ASSERT(hk < TO && hk <= sl + k && (hk >= 0 || a.plan->total == 0));  // (total == 0: a degenerate plan covers no slot)
+        pidx[k] = (head[k] == sl + k) ? (int32_t)own[k] : __float_as_int(s_par[hk]);
+      }
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xp[d][k] = xin[(int64_t)d * a.ld + pidx[k]];
+      }
+    } else {
 #pragma unroll
     for (int d = 0; d < NX; ++d) {
       const Quad<T> f = lds_quad(&s_par[d * TO + sl]);
       xp[d][0] = f.v[0]; xp[d][1] = f.v[1]; xp[d][2] = f.v[2]; xp[d][3] = f.v[3];
     }
-    if constexpr (MODE == 0) {
+    }
+    if constexpr (MODE == 0 && !IDX) {
       int head[4];
       const uint4 bits = make_uint4(mark_word(xp[0][0]), mark_word(xp[0][1]), mark_word(xp[0][2]), mark_word(xp[0][3]));
       seg_carry = resolve_heads(bits, sl, lane, seg_carry, head);
@@ -1066,7 +1108,7 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
       for (int k = 0; k < 4; ++k) {
         if (head[k] != sl + k) {
           const int hk = FULL ? head[k] : max(head[k], 0);
-          PZ_ASSERT(hk >= 0 && hk < TO && hk <= sl + k);
+          PZ_ASSERT(hk < TO && hk <= sl + k && (hk >= 0 || a.plan->total == 0));  // (total == 0: a degenerate plan covers no slot)
 #pragma unroll
           for (int d = 0; d < NX; ++d) xp[d][k] = s_par[d * TO + hk];
         }
@@ -1111,7 +1153,20 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
 #pragma unroll
       for (int d = 0; d < NX; ++d) {
         st_quad(&xout[(size_t)d * a.ld + j0l + sl], xo[d]);
-        if constexpr (NX > 1) sts_quad(&s_par[d * TO + sl], xo[d]);
+        if constexpr (NX > 1 && !IDX) sts_quad(&s_par[d * TO + sl], xo[d]);
+      }
+    }
+    if constexpr (NX > 1 && IDX) {   // centred new state -> this lane's corner of the warp's scratch
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        float4 dx4;
+        if constexpr (sizeof(T) == 4) {
+          const float2 p0 = r_sub(make_float2((float)xo[d][0], (float)xo[d][1]), (float)cen[d]), p1 = r_sub(make_float2((float)xo[d][2], (float)xo[d][3]), (float)cen[d]);
+          dx4 = make_float4(p0.x, p0.y, p1.x, p1.y);
+        } else {
+          dx4 = make_float4((float)r_sub(xo[d][0], cen[d]), (float)r_sub(xo[d][1], cen[d]), (float)r_sub(xo[d][2], cen[d]), (float)r_sub(xo[d][3], cen[d]));
+        }
+        *reinterpret_cast<float4*>(&s_dx[d * kBlk + half * 128 + lane * 4]) = dx4;
       }
     }
     if constexpr (NX == 1) {
@@ -1138,7 +1193,13 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
     for (int half = 0; half < 2; ++half) {
       const int sl = ob * kBlk + half * 128 + lane * 4;
       float dxv[NX][4];
-      if constexpr (NX > 1) {
+      if constexpr (NX > 1 && IDX) {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          const float4 f = *reinterpret_cast<const float4*>(&s_dx[d * kBlk + half * 128 + lane * 4]);
+          dxv[d][0] = f.x; dxv[d][1] = f.y; dxv[d][2] = f.z; dxv[d][3] = f.w;
+        }
+      } else if constexpr (NX > 1) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
           const Quad<T> f = lds_quad(&s_par[d * TO + sl]);
@@ -1222,11 +1283,18 @@ __device__ __forceinline__ void output_block(const StepArgs& a, T* s_par, const 
 template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB, bool REMOTE = false>
 __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__ TileArgs ta) {
   constexpr int NW = NT / 32;
-  extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents | [256] float4 inverse-CDF table
-  T* s_par = reinterpret_cast<T*>(s_raw);
+  extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents (or [TO] parent indices) | [256] float4 inverse-CDF table
+  constexpr bool IDX = kIdxStage<T, NX, MODE, REMOTE>;
+  typedef typename std::conditional<IDX, float, T>::type S;                        // staged scalar
+  typedef typename std::conditional<IDX, IndexSource, StateSource<NX, T>>::type Src;
+  S* s_par = reinterpret_cast<S*>(s_raw);
   __shared__ int32_t s_eref[NW];
   __shared__ double s_red[NW][kMaxRec];
-  float4* s_tab = reinterpret_cast<float4*>(s_par + NX * TO);
+  // index-staged wide states: [TO] indices | per-warp scratch [NW][NX][256] floats | table
+  constexpr int kStageWords = IDX ? TO : NX * TO;
+  constexpr int kScratch = (IDX && NX > 1) ? NW * NX * kBlk : 0;
+  float* s_dx_all = reinterpret_cast<float*>(s_par + kStageWords);
+  float4* s_tab = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s_par + kStageWords) + kScratch * sizeof(float));
   const StepArgs& a = ta.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t t = a.ctl->t;
@@ -1300,27 +1368,27 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
       __syncthreads();
     }
     BlockIn first{};
-    StateSource<NX, T> src;
-    src.x = xin; src.ld = a.ld;
-    Quad<T> pa{}, pb{};
+    Src src;
+    if constexpr (!IDX) { src.x = xin; src.ld = a.ld; }
+    Quad<S> pa{}, pb{};
     if (!remote && b_first + warp < a.b_hi) {
       first.load(a.Q[cur], a.eb[cur], a.xb, b_first + warp, lane);
       // fp32 payloads of the first block are fetched here too; for doubles the 16 extra registers across the
       // barrier cost more than the exposed latency (measured: 0.568 ms hoisted vs 0.544 ms not, N = 10^8)
-      if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 4) {
+      if constexpr (Src::kPrefetch && sizeof(T) == 4) {
         pa = src.fetch((b_first + warp) * kBlk + lane * 4);
         pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
       }
     }
     // sentinel in (the mark word of) dimension 0 of every slot: "no head here"
     uint4* sz = reinterpret_cast<uint4*>(s_par);
-    for (int i = tid; i < TO * (int)sizeof(T) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    for (int i = tid; i < TO * (int)sizeof(S) / 16; i += NT) sz[i] = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
     __syncthreads();
     if constexpr (REMOTE) {
       resample_tile_remote<(NX != 1), NW>(src, s_par, TO, a.p2p, cur, a.nblk, a.world, b_first, pl_emax, pl_h0, pl_Mq, j0, nslots,
                                           lane, warp);
     } else {
-      if constexpr (StateSource<NX, T>::kPrefetch && sizeof(T) == 8) {
+      if constexpr (Src::kPrefetch && sizeof(T) == 8) {
         if (b_first + warp < a.b_hi) {
           pa = src.fetch((b_first + warp) * kBlk + lane * 4);
           pb = src.fetch((b_first + warp) * kBlk + lane * 4 + 128);
@@ -1347,10 +1415,10 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   int32_t aref = kNZero;
   if (nslots == TO) {
     for (int ob = warp; ob < TO / kBlk; ob += NW)
-      output_block<T, NX, NY, TO, MODE, KRON, true>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+      output_block<T, NX, NY, TO, MODE, KRON, true, IDX>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   } else {
     for (int ob = warp; ob * kBlk < nslots; ob += NW)
-      output_block<T, NX, NY, TO, MODE, KRON, false>(a, s_par, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+      output_block<T, NX, NY, TO, MODE, KRON, false, IDX>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   }
 
   // ---- moment sums -> one record per tile: every warp reduces its lanes at its own scale 2^aref; after ONE barrier
@@ -1473,7 +1541,8 @@ __global__ void __launch_bounds__(kThreads) pf_ancestors(const GenericArgs g) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (sl + k < nslots) {
-        PZ_ASSERT(head[k] >= 0 && head[k] < TO && __float_as_int(s_anc[head[k]]) >= 0 && __float_as_int(s_anc[head[k]]) < g.n);
+        // (head < 0: a degenerate plan -- every weight zero -- leaves slots uncovered; the host reports PZ_EDEGENERATE)
+        PZ_ASSERT(head[k] < TO && (head[k] < 0 || (__float_as_int(s_anc[head[k]]) >= 0 && __float_as_int(s_anc[head[k]]) < g.nblk * kBlk)));
         g.anc[j0 + sl + k] = head[k] >= 0 ? __float_as_int(s_anc[head[k]]) : -1;
       }
   }
@@ -1937,7 +2006,7 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 #define PZ_TB1 23    // output blocks per tile, NX = 1, float (a multiple of the warp count, minus 1)
 #endif
 #ifndef PZ_TB1D
-#define PZ_TB1D 15   // output blocks per tile, NX = 1, double
+#define PZ_TB1D 23   // output blocks per tile, NX = 1, double (index-staged: 4 bytes per slot)
 #endif
 #ifndef PZ_NTN
 #define PZ_NTN 256   // threads per CTA, NX > 1
@@ -1951,8 +2020,11 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 #ifndef PZ_OCC4D
 #define PZ_OCC4D 2   // resident CTAs per SM of the double NX = 4 kernel
 #endif
+#ifndef PZ_OCC6D
+#define PZ_OCC6D 2   // resident CTAs per SM of the double NX = 6 kernel
+#endif
 #ifndef PZ_OCC1D
-#define PZ_OCC1D 3   // resident 256-thread-equivalents per SM the double NX = 1 kernel's registers are held to
+#define PZ_OCC1D 4   // resident 256-thread-equivalents per SM the double NX = 1 kernel's registers are held to (8 CTAs of 128)
 #endif
 // small = true: the second tile size (PZ_TILE_OUT=small), kept so that the tests can check that results do
 // not depend on the tiling
@@ -2029,15 +2101,24 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
   constexpr bool F64 = sizeof(T) == 8;
   constexpr int NT = (NX == 1) ? PZ_NT1 : PZ_NTN;
   constexpr int TO = tile_blocks(NX, F64, SMALL) * kBlk;
-  constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : (NX <= 4 ? PZ_OCC4D : 2)) : min_ctas(NX);
-#ifdef PZ_MINB1D   // A/B hook: resident CTAs per SM of the double NX = 1 kernel in units of its own CTA size
+  constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : (NX <= 4 ? PZ_OCC4D : PZ_OCC6D)) : min_ctas(NX);
+  // resident CTAs per SM the registers are held to, in units of the kernel's own CTA size (PZ_MINB1 / PZ_MINB1D: A/B hooks
+  // for the one-word states, whose CTAs have 128 threads)
+#if defined(PZ_MINB1D) && defined(PZ_MINB1)
+  constexpr int MINB = NX == 1 ? (F64 ? PZ_MINB1D : PZ_MINB1) : OCC * (kThreads / NT);
+#elif defined(PZ_MINB1D)
   constexpr int MINB = (F64 && NX == 1) ? PZ_MINB1D : OCC * (kThreads / NT);
+#elif defined(PZ_MINB1)
+  constexpr int MINB = (!F64 && NX == 1) ? PZ_MINB1 : OCC * (kThreads / NT);
 #else
   constexpr int MINB = OCC * (kThreads / NT);
 #endif
   auto kern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB>;
-  // staged parents [NX][TO] + inverse-CDF table
-  const size_t smem = (size_t)NX * TO * sizeof(T) + PZ_ICDF_ROWS * sizeof(float4);
+  // staged parents [NX][TO] (or parent indices [TO]) + inverse-CDF table
+  const size_t smem_state = (size_t)NX * TO * sizeof(T) + PZ_ICDF_ROWS * sizeof(float4);
+  const size_t smem = kIdxStage<T, NX, MODE, false>
+                          ? (size_t)TO * sizeof(float) + (NX > 1 ? (size_t)(NT / 32) * NX * kBlk * sizeof(float) : 0) + PZ_ICDF_ROWS * sizeof(float4)
+                          : smem_state;
   // function attributes are per context (device); concurrent first launches set the same value
   static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
@@ -2066,11 +2147,11 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
       auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB, true>;
       static std::atomic<unsigned long long> rattr_done{0};
       if (!(rattr_done.load(std::memory_order_acquire) & bit)) {
-        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_state);
         rattr_done.fetch_or(bit, std::memory_order_release);
       }
       const int rgrid = ta.a.ntiles_out < 148 ? ta.a.ntiles_out : 148;
-      rkern<<<rgrid, NT, smem, s>>>(ta);
+      rkern<<<rgrid, NT, smem_state, s>>>(ta);
       return 2;
     }
   }
