@@ -951,10 +951,15 @@ __device__ __forceinline__ void resample_tile_remote(Source& src, typename Sourc
     const int64_t lb = gb - (int64_t)q * nblk;
     BlockIn in;
     in.load(p2p->Qall[q][cur], p2p->eball[q][cur], p2p->xball[q], lb, lane);
-    src.x = reinterpret_cast<const S*>(p2p->Xall[q][cur]);
     Quad<S> xa{}, xb4{};
-    if constexpr (Source::kPrefetch) { xa = src.fetch(lb * kBlk + lane * 4); xb4 = src.fetch(lb * kBlk + lane * 4 + 128); }
-    if (resample_block<SEGDUP>(src, s_par, stride, in, xa, xb4, lb, emax, h0, Mq, j0, nslots, lane)) break;
+    if constexpr (std::is_same<Source, IndexSource>::value) {
+      // index staging: the GLOBAL particle index is staged; the output side reads the parent from its owner
+      if (resample_block<SEGDUP>(src, s_par, stride, in, xa, xb4, gb, emax, h0, Mq, j0, nslots, lane)) break;
+    } else {
+      src.x = reinterpret_cast<const S*>(p2p->Xall[q][cur]);
+      if constexpr (Source::kPrefetch) { xa = src.fetch(lb * kBlk + lane * 4); xb4 = src.fetch(lb * kBlk + lane * 4 + 128); }
+      if (resample_block<SEGDUP>(src, s_par, stride, in, xa, xb4, lb, emax, h0, Mq, j0, nslots, lane)) break;
+    }
   }
 }
 
@@ -1018,7 +1023,9 @@ struct TileArgs {
 // persistent grid (a CTA strides over the tiles; table, observation and plan constants fetched once per CTA): measured at
 // N = 10^7 / 10^8 -- LG(4,2) f64 0.2293 -> 0.2242 ms, LG(6,3) f64 0.3594 -> 0.3508, LG(6,3) f32 0.1992 -> 0.1972, but
 // RW1D f64 0.5176 -> 0.5611, RW1D f32 0.4142 -> 0.4613, LG(4,2) f32 0.1501 -> 0.1561: the one-word states keep one CTA per tile
-template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE || (NX > 1 && (sizeof(T) == 8 || NX > 4));
+// With index staging and 23-block tiles (later in the round) the wide states lose that gain too (LG(6,3) fp64 0.2518 persistent vs
+// 0.2499, fp32 0.1853 vs 0.1828; LG(4,2) equal): only the remote-read fallback keeps its small persistent grid.
+template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE;
 // index staging for the one-word states (PZ_IDX1: bit 0 fp32, bit 1 fp64): the input side stages the parent's INDEX (4 bytes
 // per head slot, no payload loads, no payload registers) and the output side gathers the parent's state from global memory
 // (sorted ancestors: the loads of a warp fall into a few adjacent lines)
@@ -1032,11 +1039,14 @@ template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE || (NX 
 // PZ_IDXN: the same for the wide states (bit 0 / 1: NX = 4 fp32 / fp64, bit 2 / 3: NX = 6 fp32 / fp64); their centred new
 // states, which the moment pass reads back, then go through a per-warp scratch [NX][256] of floats instead of the
 // staging buffer (every lane reads back exactly what it wrote: no synchronisation)
+// Measured (N = 10^7, pf_step_tile, state-staged -> index-staged with 23-block tiles): LG(4,2) fp64 0.2236 -> 0.1768 ms,
+// LG(6,3) fp64 0.3519 -> 0.2532, LG(4,2) fp32 0.1463 -> 0.1337, LG(6,3) fp32 0.1977 -> 0.1857 (the staging buffer shrinks from
+// NX state words to one index word per slot, the input side loads no payload; tiles of 7 / 15 / 19 / 23 / 31 blocks were tried)
 #ifndef PZ_IDXN
-#define PZ_IDXN 0
+#define PZ_IDXN 15
 #endif
-template <class T, int NX, int MODE, bool REMOTE> constexpr bool kIdxStage =
-    MODE == 0 && !REMOTE &&
+template <class T, int NX, int MODE> constexpr bool kIdxStage =
+    MODE == 0 &&
     (NX == 1 ? (((PZ_IDX1) >> (sizeof(T) == 8 ? 1 : 0)) & 1) : (((PZ_IDXN) >> ((NX <= 4 ? 0 : 2) + (sizeof(T) == 8 ? 1 : 0))) & 1));
 template <int NX> constexpr bool kPackModel = ((PZ_PACK_MODEL) >> (NX == 1 ? 0 : (NX <= 4 ? 1 : 2))) & 1;
 constexpr int min_ctas(int nx) { return nx == 1 ? PZ_OCC1 : (nx <= 4 ? PZ_OCC4 : PZ_OCC6); }
@@ -1054,7 +1064,7 @@ __device__ __forceinline__ float lw_key(double lw) { return __double2float_rn(lw
 // machinery: the log-weight rounded to fp32 enters the block maximum and the weight polynomial, the centred state
 // x' - c (formed in double) is rounded to fp32 for the moment sums.  (Keeping those in double costs 24 registers
 // and an occupancy step for nothing the 16-bit weights or the fp64 tile totals could show.)
-template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL, bool IDX, class S>
+template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL, bool IDX, bool REMOTE, class S>
 __device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float* s_dx, const float4* __restrict__ tab_m8, int ob,
                                              int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const T* y_new,
                                              const T* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref) {
@@ -1087,10 +1097,22 @@ __device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float*
         PZ_ASSERT(hk < TO && hk <= sl + k && (hk >= 0 || a.plan->total == 0));  // (total == 0: a degenerate plan covers no slot)
         pidx[k] = (head[k] == sl + k) ? (int32_t)own[k] : __float_as_int(s_par[hk]);
       }
+      if constexpr (REMOTE) {   // global indices: the parent's state lives on the rank that owns it (NVLink load when it is a peer)
 #pragma unroll
-      for (int d = 0; d < NX; ++d) {
+        for (int k = 0; k < 4; ++k) {
+          const int q = pidx[k] / (int32_t)a.n_local;
+          const int32_t li = pidx[k] - q * (int32_t)a.n_local;
+          PZ_ASSERT(q >= 0 && q < a.world);
+          const T* __restrict__ xq = reinterpret_cast<const T*>(a.p2p->Xall[q][nxt ^ 1]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xp[d][k] = xin[(int64_t)d * a.ld + pidx[k]];
+          for (int d = 0; d < NX; ++d) xp[d][k] = xq[(int64_t)d * a.ld + li];
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xp[d][k] = xin[(int64_t)d * a.ld + pidx[k]];
+        }
       }
     } else {
 #pragma unroll
@@ -1284,7 +1306,7 @@ template <class T, int NX, int NY, int TO, int MODE, bool KRON, int NT, int MINB
 __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__ TileArgs ta) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char s_raw[];  // [NX][TO] staged parents (or [TO] parent indices) | [256] float4 inverse-CDF table
-  constexpr bool IDX = kIdxStage<T, NX, MODE, REMOTE>;
+  constexpr bool IDX = kIdxStage<T, NX, MODE>;
   typedef typename std::conditional<IDX, float, T>::type S;                        // staged scalar
   typedef typename std::conditional<IDX, IndexSource, StateSource<NX, T>>::type Src;
   S* s_par = reinterpret_cast<S*>(s_raw);
@@ -1415,10 +1437,10 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   int32_t aref = kNZero;
   if (nslots == TO) {
     for (int ob = warp; ob < TO / kBlk; ob += NW)
-      output_block<T, NX, NY, TO, MODE, KRON, true, IDX>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+      output_block<T, NX, NY, TO, MODE, KRON, true, IDX, REMOTE>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   } else {
     for (int ob = warp; ob * kBlk < nslots; ob += NW)
-      output_block<T, NX, NY, TO, MODE, KRON, false, IDX>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+      output_block<T, NX, NY, TO, MODE, KRON, false, IDX, REMOTE>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
   }
 
   // ---- moment sums -> one record per tile: every warp reduces its lanes at its own scale 2^aref; after ONE barrier
@@ -2012,10 +2034,10 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 #define PZ_NTN 256   // threads per CTA, NX > 1
 #endif
 #ifndef PZ_TBN
-#define PZ_TBN 15    // output blocks per tile, NX > 1, float
+#define PZ_TBN 23    // output blocks per tile, NX > 1, float
 #endif
 #ifndef PZ_TBND
-#define PZ_TBND 7    // output blocks per tile, NX > 1, double
+#define PZ_TBND 23   // output blocks per tile, NX > 1, double
 #endif
 #ifndef PZ_OCC4D
 #define PZ_OCC4D 2   // resident CTAs per SM of the double NX = 4 kernel
@@ -2116,7 +2138,7 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
   auto kern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB>;
   // staged parents [NX][TO] (or parent indices [TO]) + inverse-CDF table
   const size_t smem_state = (size_t)NX * TO * sizeof(T) + PZ_ICDF_ROWS * sizeof(float4);
-  const size_t smem = kIdxStage<T, NX, MODE, false>
+  const size_t smem = kIdxStage<T, NX, MODE>
                           ? (size_t)TO * sizeof(float) + (NX > 1 ? (size_t)(NT / 32) * NX * kBlk * sizeof(float) : 0) + PZ_ICDF_ROWS * sizeof(float4)
                           : smem_state;
   // function attributes are per context (device); concurrent first launches set the same value
@@ -2147,11 +2169,11 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
       auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB, true>;
       static std::atomic<unsigned long long> rattr_done{0};
       if (!(rattr_done.load(std::memory_order_acquire) & bit)) {
-        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_state);
+        cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         rattr_done.fetch_or(bit, std::memory_order_release);
       }
       const int rgrid = ta.a.ntiles_out < 148 ? ta.a.ntiles_out : 148;
-      rkern<<<rgrid, NT, smem_state, s>>>(ta);
+      rkern<<<rgrid, NT, smem, s>>>(ta);
       return 2;
     }
   }

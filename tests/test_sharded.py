@@ -284,21 +284,25 @@ def test_sharded_margin_overflow_falls_back_to_remote_reads(pz, model, tmp_path)
 
 
 @pytest.mark.gpu
-def test_multi_device_margin_overflow_falls_back_to_remote_reads(pz, monkeypatch):
-    """The same through pz_filter_create_multi (one process), on a stream with outliers that unbalances the ranks."""
+@pytest.mark.parametrize("mk,f64", [("mtt_track", False), ("mtt_track", True), ("stt", True), ("rw1d", True)],
+                         ids=["lg42-f32", "lg42-f64", "lg63-f64", "rw1d-f64"])
+def test_multi_device_margin_overflow_falls_back_to_remote_reads(pz, monkeypatch, mk, f64):
+    """The same through pz_filter_create_multi (one process), on a stream with outliers that unbalances the ranks; every
+    storage type whose step kernel stages parent INDICES (the remote kernel then stages global indices and gathers the
+    parent from its owner) and the state-staged fp32 path."""
     import torch
     ndev = torch.cuda.device_count()
     if ndev < 2:
         pytest.skip("needs 2 GPUs")
     monkeypatch.setenv("PZ_HALO_BLOCKS", "1")
-    hd = H.model_mtt_track()
+    hd = {"mtt_track": H.model_mtt_track, "stt": H.model_stt, "rw1d": H.model_rw1d}[mk]()
     T = 30
     obs, _ = H.gen_obs(hd, T)
     obs = obs.copy(); obs[5] += 6.0; obs[17] -= 9.0
     world = 2 if ndev < 4 else 4
     n = world * 256 * 300
-    one = pz.zparticles(n, pz.mtt_track(), seed=5)
-    many = pz.zparticles_multi(n, pz.mtt_track(), list(range(world)), seed=5)
+    one = pz.zparticles(n, getattr(pz, mk)(f64=f64), seed=5)
+    many = pz.zparticles_multi(n, getattr(pz, mk)(f64=f64), list(range(world)), seed=5)
     mig = 0
     for t in range(T):
         pa, pb = one.step(obs[t]), many.step(obs[t])
