@@ -1042,6 +1042,12 @@ template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE;
 // Measured (N = 10^7, pf_step_tile, state-staged -> index-staged with 23-block tiles): LG(4,2) fp64 0.2236 -> 0.1768 ms,
 // LG(6,3) fp64 0.3519 -> 0.2532, LG(4,2) fp32 0.1463 -> 0.1337, LG(6,3) fp32 0.1977 -> 0.1857 (the staging buffer shrinks from
 // NX state words to one index word per slot, the input side loads no payload; tiles of 7 / 15 / 19 / 23 / 31 blocks were tried)
+// (measured and rejected: with the bulk L2 prefetch of the tile's input range RW1D fp64 0.4558 -> 0.4682 ms, LG(4,2) fp64
+// 0.1663 -> 0.1935, LG(6,3) fp64 0.2358 -> 0.2539: the 47-280 KB bursts queue ahead of the input side's own latency-critical
+// weight loads; the gather's misses are better left spread over the output side)
+#ifndef PZ_L2_PREFETCH
+#define PZ_L2_PREFETCH 0
+#endif
 #ifndef PZ_IDXN
 #define PZ_IDXN 15
 #endif
@@ -1388,6 +1394,29 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
         }
       }
       __syncthreads();
+    }
+    if constexpr (IDX && !REMOTE) {
+      // Index staging leaves the parents' states untouched until the output side gathers them: one bulk L2 prefetch per
+      // state dimension (cp.async.bulk.prefetch.L2, issued by one thread) pulls the tile's input range -- the blocks
+      // [b_first, first block of the next tile] -- towards the SMs while the input side runs.  (A halo block that has not
+      // arrived yet may be prefetched stale: L2 is the coherence point of peer stores, a prefetch keeps no private copy.)
+      // Off by default (PZ_L2_PREFETCH): measured slower, see the macro.
+#if PZ_L2_PREFETCH
+      if (tid == 0) {
+        const int64_t b_nx = (tile + 1 < ntiles) ? (int64_t)a.tile_start[tile + 1] + 1 : a.b_hi;
+        int64_t nb = (b_nx < a.b_hi ? b_nx : a.b_hi) - b_first;
+        const int64_t cap = 2 * (TO / kBlk) + 2;   // a tile that draws on a long stretch of childless blocks: the head is enough
+        nb = nb < 0 ? 0 : (nb > cap ? cap : nb);
+        const uint32_t bytes = (uint32_t)(nb * kBlk * (int64_t)sizeof(T));
+        if (bytes) {
+#pragma unroll
+          for (int d = 0; d < NX; ++d) {
+            const T* p = xin + (int64_t)d * a.ld + b_first * kBlk;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+          }
+        }
+      }
+#endif
     }
     BlockIn first{};
     Src src;
@@ -2030,6 +2059,9 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 #ifndef PZ_TB1D
 #define PZ_TB1D 23   // output blocks per tile, NX = 1, double (index-staged: 4 bytes per slot)
 #endif
+#ifndef PZ_NT4D
+#define PZ_NT4D 128  // threads per CTA, NX = 4, double
+#endif
 #ifndef PZ_NTN
 #define PZ_NTN 256   // threads per CTA, NX > 1
 #endif
@@ -2121,7 +2153,8 @@ int launch_scan_partition(const StepArgs& a, int tile_out, cudaStream_t s) {
 template <class T, int NX, int NY, int MODE, bool KRON, bool SMALL>
 static int launch_tile(const TileArgs& ta, cudaStream_t s) {
   constexpr bool F64 = sizeof(T) == 8;
-  constexpr int NT = (NX == 1) ? PZ_NT1 : PZ_NTN;
+  // (LG(4,2) fp64 runs 128-thread CTAs, 4 per SM: 0.1730 -> 0.1676 ms at N = 10^7; the same costs LG(6,3) fp64 30 %)
+  constexpr int NT = (NX == 1) ? PZ_NT1 : ((NX == 4 && F64) ? PZ_NT4D : PZ_NTN);
   constexpr int TO = tile_blocks(NX, F64, SMALL) * kBlk;
   constexpr int OCC = F64 ? (NX == 1 ? PZ_OCC1D : (NX <= 4 ? PZ_OCC4D : PZ_OCC6D)) : min_ctas(NX);
   // resident CTAs per SM the registers are held to, in units of the kernel's own CTA size (PZ_MINB1 / PZ_MINB1D: A/B hooks
