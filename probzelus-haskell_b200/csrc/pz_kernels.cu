@@ -1045,6 +1045,13 @@ template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE;
 // (measured and rejected: with the bulk L2 prefetch of the tile's input range RW1D fp64 0.4558 -> 0.4682 ms, LG(4,2) fp64
 // 0.1663 -> 0.1935, LG(6,3) fp64 0.2358 -> 0.2539: the 47-280 KB bursts queue ahead of the input side's own latency-critical
 // weight loads; the gather's misses are better left spread over the output side)
+// Measured (RW1D fp64, N = 10^8): PZ_GATHER2 = 0 0.4577 ms, = 1 0.4388 ms (and 4 instead of 144 bytes of spills at 64 registers)
+#ifndef PZ_GATHER2
+#define PZ_GATHER2 1
+#endif
+#ifndef PZ_PREFETCH_NEXT
+#define PZ_PREFETCH_NEXT 0
+#endif
 #ifndef PZ_L2_PREFETCH
 #define PZ_L2_PREFETCH 0
 #endif
@@ -1070,10 +1077,57 @@ __device__ __forceinline__ float lw_key(double lw) { return __double2float_rn(lw
 // machinery: the log-weight rounded to fp32 enters the block maximum and the weight polynomial, the centred state
 // x' - c (formed in double) is rounded to fp32 for the moment sums.  (Keeping those in double costs 24 registers
 // and an occupancy step for nothing the 16-bit weights or the fp64 tile totals could show.)
+// Index-staged one-word states: resolve the heads of BOTH halves of output block ob and issue the loads of their parents'
+// states (PZ_GATHER2 = 1: at the top of output_block; = 2: one block ahead, while the previous block is still computing)
+template <class T, int TO, bool FULL>
+__device__ __forceinline__ void gather_parents(const StepArgs& a, const float* s_par, int ob, int lane, int nxt, T (&xpa)[2][4]) {
+  const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[nxt ^ 1]);
+  int seg_carry = -1;
+  if (ob > 0) seg_carry = last_head_before(s_par, ob * kBlk, lane);  // runs of <= 128 slots reach back one segment
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int sl = ob * kBlk + half * 128 + lane * 4;
+    const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
+    int head[4];
+    seg_carry = resolve_heads(bits, sl, lane, seg_carry, head);
+    const uint32_t own[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int hk = FULL ? head[k] : max(head[k], 0);
+      PZ_ASSERT(hk < TO && hk <= sl + k && (hk >= 0 || a.plan->total == 0));
+      const int32_t pi = (head[k] == sl + k) ? (int32_t)own[k] : __float_as_int(s_par[hk]);
+      xpa[half][k] = xin[pi];
+    }
+  }
+}
+
+// Index-staged wide states: non-binding L2 prefetches of the parents of output block ob (first and last slot of each lane's
+// quad, every state dimension), issued one block ahead -- no registers are held, the later gather hits L2 instead of HBM
+// (PZ_PREFETCH_NEXT)
+template <class T, int NX, int TO>
+__device__ __forceinline__ void prefetch_parents(const StepArgs& a, const float* s_par, int ob, int lane, int nxt) {
+  const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[nxt ^ 1]);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int sl = ob * kBlk + half * 128 + lane * 4;
+    const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
+    int head[4];
+    resolve_heads(bits, sl, lane, -1, head);   // (NX > 1: every segment starts with a head)
+    const int32_t p0 = (head[0] == sl) ? (int32_t)bits.x : __float_as_int(s_par[head[0]]);
+    const int32_t p3 = (head[3] == sl + 3) ? (int32_t)bits.w : __float_as_int(s_par[head[3]]);
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + (int64_t)d * a.ld + p0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + (int64_t)d * a.ld + p3));
+    }
+  }
+}
+
 template <class T, int NX, int NY, int TO, int MODE, bool KRON, bool FULL, bool IDX, bool REMOTE, class S>
 __device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float* s_dx, const float4* __restrict__ tab_m8, int ob,
                                              int nslots, int64_t j0l, uint32_t j0, uint32_t t, int nxt, const T* y_new,
-                                             const T* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref) {
+                                             const T* cen, int lane, float (&acc)[PZ_NACC(NX)], int32_t& aref,
+                                             const T (*xpre)[4] = nullptr) {
   T* __restrict__ xout = reinterpret_cast<T*>(a.X[nxt]);
   uint16_t* __restrict__ qout = a.Q[nxt];
   const LgDevT<T>& model = model_of<T>(a);
@@ -1081,14 +1135,28 @@ __device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float*
   float dxk[NX == 1 ? 8 : 1];  // NX = 1 keeps the centred new state in registers; wider states go through s_par
   float mx = -INFINITY;
   int seg_carry = -1;
-  if constexpr (MODE == 0 && NX == 1) {
+  constexpr bool kGather2 = IDX && NX == 1 && !REMOTE && (PZ_GATHER2 != 0);
+  if constexpr (MODE == 0 && NX == 1 && !kGather2) {
     if (ob > 0) seg_carry = last_head_before(s_par, ob * kBlk, lane);  // runs of <= 128 slots reach back one segment
+  }
+  T xpa[kGather2 ? 2 : 1][4];
+  if constexpr (kGather2) {
+    if (xpre != nullptr) {   // gathered one block ahead by the caller (PZ_GATHER2 = 2, full tiles)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xpa[h][k] = xpre[h][k];
+      }
+    } else gather_parents<T, TO, FULL>(a, reinterpret_cast<const float*>(s_par), ob, lane, nxt, xpa);
   }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int sl = ob * kBlk + half * 128 + lane * 4;  // tile-relative slot of this lane's quad
     T xp[NX][4];
-    if constexpr (IDX) {
+    if constexpr (kGather2) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xp[0][k] = xpa[half][k];
+    } else if constexpr (IDX) {
       // staged parent indices: resolve the heads, then gather the parents' states from global memory
       const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[nxt ^ 1]);
       const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
@@ -1465,8 +1533,27 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   for (int r = 0; r < PZ_NACC(NX); ++r) acc[r] = 0.0f;
   int32_t aref = kNZero;
   if (nslots == TO) {
-    for (int ob = warp; ob < TO / kBlk; ob += NW)
+    if constexpr (IDX && NX == 1 && !REMOTE && PZ_GATHER2 == 2) {
+      T xnext[2][4];
+      if (warp < TO / kBlk) gather_parents<T, TO, true>(a, reinterpret_cast<const float*>(s_par), warp, lane, nxt, xnext);
+      for (int ob = warp; ob < TO / kBlk; ob += NW) {
+        T xcur[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xcur[h][k] = xnext[h][k];
+        }
+        if (ob + NW < TO / kBlk) gather_parents<T, TO, true>(a, reinterpret_cast<const float*>(s_par), ob + NW, lane, nxt, xnext);
+        output_block<T, NX, NY, TO, MODE, KRON, true, IDX, REMOTE>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref, xcur);
+      }
+    } else {
+    for (int ob = warp; ob < TO / kBlk; ob += NW) {
+      if constexpr (IDX && NX > 1 && !REMOTE && (PZ_PREFETCH_NEXT != 0)) {
+        if (ob + NW < TO / kBlk) prefetch_parents<T, NX, TO>(a, reinterpret_cast<const float*>(s_par), ob + NW, lane, nxt);
+      }
       output_block<T, NX, NY, TO, MODE, KRON, true, IDX, REMOTE>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
+    }
+    }
   } else {
     for (int ob = warp; ob * kBlk < nslots; ob += NW)
       output_block<T, NX, NY, TO, MODE, KRON, false, IDX, REMOTE>(a, s_par, s_dx_all + warp * NX * kBlk, tab_m8, ob, nslots, j0l, j0, t, nxt, y_new, cen, lane, acc, aref);
