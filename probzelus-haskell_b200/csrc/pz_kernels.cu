@@ -1045,10 +1045,13 @@ template <class T, int NX, bool REMOTE> constexpr bool kPersist = REMOTE;
 // (measured and rejected: with the bulk L2 prefetch of the tile's input range RW1D fp64 0.4558 -> 0.4682 ms, LG(4,2) fp64
 // 0.1663 -> 0.1935, LG(6,3) fp64 0.2358 -> 0.2539: the 47-280 KB bursts queue ahead of the input side's own latency-critical
 // weight loads; the gather's misses are better left spread over the output side)
-// Measured (RW1D fp64, N = 10^8): PZ_GATHER2 = 0 0.4577 ms, = 1 0.4388 ms (and 4 instead of 144 bytes of spills at 64 registers)
+// Measured (RW1D fp64, N = 10^8): PZ_GATHER2 = 0 0.4577 ms (144 bytes of spills at 64 registers), = 1 0.4283 ms (no spills),
+// = 2 (gathered one block ahead, 16 more live registers) 0.4388 ms
 #ifndef PZ_GATHER2
 #define PZ_GATHER2 1
 #endif
+// (measured and rejected, like the bulk prefetch below: LG(4,2) fp64 0.1673 -> 0.1723 ms, LG(6,3) fp64 0.2344 -> 0.2557, fp32
+// +3-4 %: on this kernel every kind of prefetch instruction costs more than the latency it hides)
 #ifndef PZ_PREFETCH_NEXT
 #define PZ_PREFETCH_NEXT 0
 #endif
