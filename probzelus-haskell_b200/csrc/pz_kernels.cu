@@ -1080,6 +1080,9 @@ __device__ __forceinline__ float lw_key(double lw) { return __double2float_rn(lw
 // machinery: the log-weight rounded to fp32 enters the block maximum and the weight polynomial, the centred state
 // x' - c (formed in double) is rounded to fp32 for the moment sums.  (Keeping those in double costs 24 registers
 // and an occupancy step for nothing the 16-bit weights or the fp64 tile totals could show.)
+// (The staged indices are MEMORY indices, and the CDF order inside a block is lane-major -- offsets 0-3, 128-131, 4-7, ... --
+// so they are not monotone along the slots: a running maximum cannot replace the head positions.  Staging CDF positions
+// instead would be monotone but needs the 5-instruction position -> offset map per slot, which is what it would save.)
 // Index-staged one-word states: resolve the heads of BOTH halves of output block ob and issue the loads of their parents'
 // states (PZ_GATHER2 = 1: at the top of output_block; = 2: one block ahead, while the previous block is still computing)
 template <class T, int TO, bool FULL>
@@ -1406,6 +1409,9 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
       const int32_t ov = pl->shard_overflow;
       if (REMOTE ? ov != 1 : ov != 0) return;   // (2: a peer never answered -- the error is reported, neither kernel runs)
     }
+    // A degenerate plan (every weight zero: PZ_EDEGENERATE, reported by the step that produced it) covers no output slot, so
+    // there is no parent to gather: steps queued behind it (pz_filter_run) leave the population as it is until pz_filter_reset.
+    if (pl->degenerate) return;
   }
   if constexpr (REMOTE) {
     // every rank's boundary positions of this epoch must be complete before any block is read

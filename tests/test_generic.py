@@ -340,3 +340,25 @@ def test_reset_after_a_degenerate_step(pz):
         fresh2.step(obs[0])
         assert np.array_equal(zs.read_state(), fresh2.read_state())
         zs.close(); fresh.close(); fresh2.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mk,f64", [("rw1d", True), ("rw1d", False), ("stt", True), ("mtt_track", False)])
+def test_steps_queued_behind_a_degenerate_step_are_harmless(pz, mk, f64):
+    """pz_filter_run queues its steps without a host check in between: a step whose weights are all zero leaves a plan that
+    covers no output slot, and the step kernels behind it (which gather parents by index) must not touch memory through it.
+    The run reports PZ_EDEGENERATE, the context stays healthy and pz_filter_reset returns the handle to the prior."""
+    d = getattr(pz, mk)(f64=f64)
+    hd = {"rw1d": H.model_rw1d, "stt": H.model_stt, "mtt_track": H.model_mtt_track}[mk]()
+    obs, _ = H.gen_obs(hd, 12)
+    bad = obs.copy(); bad[3] = float("nan")
+    zs = pz.zparticles(100000, d, seed=3)
+    with pytest.raises(pz.PzError) as e:
+        zs.run(bad)
+    assert e.value.code == H.PZ_EDEGENERATE
+    zs.reset(seed=3)
+    fresh = pz.zparticles(100000, d, seed=3)
+    a, b = zs.run(obs), fresh.run(obs)
+    assert [p.total_weight for p in a] == [p.total_weight for p in b]
+    assert np.array_equal(zs.read_state(), fresh.read_state())
+    zs.close(); fresh.close()
