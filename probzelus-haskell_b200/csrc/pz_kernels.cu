@@ -1107,6 +1107,34 @@ __device__ __forceinline__ void gather_parents(const StepArgs& a, const float* s
   }
 }
 
+// The same for the wide states (PZ_GATHER2N: bit 0 / 1 NX = 4 fp32 / fp64, bit 2 / 3 NX = 6 fp32 / fp64): NX x 8 values in flight
+template <class T, int NX, int TO, bool FULL>
+__device__ __forceinline__ void gather_parents_wide(const StepArgs& a, const float* s_par, int ob, int lane, int nxt, T (&xpw)[2][NX][4]) {
+  const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[nxt ^ 1]);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int sl = ob * kBlk + half * 128 + lane * 4;
+    const uint4 bits = *reinterpret_cast<const uint4*>(&s_par[sl]);
+    int head[4];
+    resolve_heads(bits, sl, lane, -1, head);   // every segment of a wide state starts with a head
+    const uint32_t own[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int hk = FULL ? head[k] : max(head[k], 0);
+      const int32_t pi = (head[k] == sl + k) ? (int32_t)own[k] : __float_as_int(s_par[hk]);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) xpw[half][d][k] = xin[(int64_t)d * a.ld + pi];
+    }
+  }
+}
+// Measured (N = 10^7): LG(4,2) fp32 0.1348 -> 0.1268 ms (kept); LG(6,3) fp32 0.1854 -> 0.1885, LG(4,2) fp64 0.1680 -> 0.1683,
+// LG(6,3) fp64 0.2336 -> 0.2623 (48 more live registers: spills)
+#ifndef PZ_GATHER2N
+#define PZ_GATHER2N 1
+#endif
+template <class T, int NX> constexpr bool kGather2Wide =
+    NX > 1 && (((PZ_GATHER2N) >> ((NX <= 4 ? 0 : 2) + (sizeof(T) == 8 ? 1 : 0))) & 1);
+
 // Index-staged wide states: non-binding L2 prefetches of the parents of output block ob (first and last slot of each lane's
 // quad, every state dimension), issued one block ahead -- no registers are held, the later gather hits L2 instead of HBM
 // (PZ_PREFETCH_NEXT)
@@ -1145,6 +1173,9 @@ __device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float*
   if constexpr (MODE == 0 && NX == 1 && !kGather2) {
     if (ob > 0) seg_carry = last_head_before(s_par, ob * kBlk, lane);  // runs of <= 128 slots reach back one segment
   }
+  constexpr bool kG2W = IDX && !REMOTE && kGather2Wide<T, NX>;
+  T xpw[kG2W ? 2 : 1][NX][4];
+  if constexpr (kG2W) gather_parents_wide<T, NX, TO, FULL>(a, reinterpret_cast<const float*>(s_par), ob, lane, nxt, xpw);
   T xpa[kGather2 ? 2 : 1][4];
   if constexpr (kGather2) {
     if (xpre != nullptr) {   // gathered one block ahead by the caller (PZ_GATHER2 = 2, full tiles)
@@ -1162,6 +1193,12 @@ __device__ __forceinline__ void output_block(const StepArgs& a, S* s_par, float*
     if constexpr (kGather2) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) xp[0][k] = xpa[half][k];
+    } else if constexpr (kG2W) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xp[d][k] = xpw[half][d][k];
+      }
     } else if constexpr (IDX) {
       // staged parent indices: resolve the heads, then gather the parents' states from global memory
       const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[nxt ^ 1]);
