@@ -315,6 +315,67 @@ def measure_mtt(pz, n_p, K, W, tracks, with_cpu, devices=1):
     return out
 
 
+def synth_mcam_scenario(d, T, seed=7, clutter=0.05, warm_tracks=4):
+    """Observation rows of the two-camera model (MultiCamera.hs:183-206) in numpy: survival, Poisson births with a camera and
+    an identity, one row per live track and camera (box + unit pose + appearance reading), Poisson clutter.  Rows are
+    (camera, pose[10], box[4], reading).  The GPU arm does not execute oracle/."""
+    rng = np.random.default_rng(seed)
+    m = d.mtt
+    q = np.sqrt(np.array([d.Q[i * 4 + i] for i in range(4)])); x0 = np.array(list(d.x0)[:4])
+    pv = np.sqrt([m.birth_pos_var, m.birth_pos_var, m.birth_vel_var, m.birth_vel_var])
+    apps, tracks, out = [], [], []
+
+    def birth():
+        if not apps or rng.random() < 1.0 / (len(apps) + 1):
+            apps.append(rng.standard_normal(10)); ident = len(apps) - 1
+        else:
+            ident = int(rng.integers(len(apps)))
+        return [int(rng.integers(2)), ident, x0 + pv * rng.standard_normal(4)]
+    tracks = [birth() for _ in range(warm_tracks)]
+    for _ in range(T):
+        tracks = [[c, i, x + q * rng.standard_normal(4)] for c, i, x in tracks if rng.random() < m.survival_prob]
+        for _ in range(rng.poisson(m.new_track_lambda)):
+            if len(tracks) < 16:
+                tracks.append(birth())
+        rows = []
+        for cam in (0, 1):
+            for c, i, x in tracks:
+                if c != cam:
+                    continue
+                pose = rng.standard_normal(10); pose /= np.linalg.norm(pose)
+                rows.append(np.concatenate([[cam], pose, x + rng.standard_normal(4), [pose @ apps[i] + rng.standard_normal()]]))
+            for _ in range(rng.poisson(clutter)):
+                rows.append(np.concatenate([[cam], rng.standard_normal(10), x0 + rng.standard_normal(4), [rng.standard_normal()]]))
+        out.append(np.array(rows[:32], dtype=np.float64).reshape(-1, 16))
+    return out
+
+
+def measure_mcam(pz, n_p, K, W):
+    """the MultiCamera tracker (N particles, 4 targets in the scene at t = 0, clutter 0.05 per camera: at the
+    reference's amtClutter = 1 the model itself starves the population, tests/test_mcam.py)."""
+    import torch
+    d = pz.multicam(); d.mtt.clutter_lambda = 0.05
+    obs = synth_mcam_scenario(d, W + K)
+    zs = pz.zparticles(n_p, d, seed=1)
+    for o in obs[:W]:
+        zs.step(o)
+    torch.cuda.synchronize()
+    dev_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for o in obs[W:]:
+        post = zs.step(o)
+        ms, nl = zs.last_timing()
+        dev_ms += ms; launches += nl
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    zs.close()
+    return {"value": n_p * K / (dev_ms * 1e-3), "unit": "particle-updates/s", "ms_per_step": dev_ms / K, "dtype": "f32", "steps": K,
+            "workload": f"MultiCamera tracker (MultiCamera.hs), N={n_p} particles, 2 cameras, appearance marginals over R^10",
+            "mean_tracks_last_step": float(post.mean[0]),
+            "e2e": {"value": n_p * K / wall, "unit": "particle-updates/s", "ms_per_step": wall / K * 1e3},
+            "gpu_launches": int(launches)}
+
+
 def measure_lg(pz, name, dtype, n_p, K, W, device=0, profile=True, sustained=0):
     """One single-GPU leg: device-resident K steps, end-to-end K steps, per-kernel events."""
     import torch
@@ -524,6 +585,10 @@ def run_b200(args):
             for dt in ("f32", "f64"):
                 legs[f"{m}_{dt}"] = measure_lg(pz, m, dt, 10_000_000, kl, 3)
         legs["mtt_f32"] = measure_mtt(pz, 1_000_000, 10, 3, args.mtt_tracks, with_cpu=False)
+        try:
+            legs["multicam_f32"] = measure_mcam(pz, 100_000, 10, 3)
+        except Exception as exc:   # the model can starve a population (passert False); the leg must not take the headline down
+            legs["multicam_f32"] = {"error": str(exc)[:200]}
         import torch
         if torch.cuda.device_count() >= 2:   # configs[4]'s sharded tracker: one process, every GPU of the box, 10^6 particles per GPU
             nd = min(torch.cuda.device_count(), 8)

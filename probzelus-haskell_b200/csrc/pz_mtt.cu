@@ -163,19 +163,28 @@ __device__ __forceinline__ void store_track(uint32_t* __restrict__ rec, const Tr
 //      coasting Bernoulli for the others, survivors compacted in id order, then births.
 // HBM traffic is the parent record read once and the child record written once.
 constexpr int kMttThreads = 128;
-constexpr int kMttDerived = 7;   // m0, m1, s00, s01, s11, lnorm, likelihood scratch
+constexpr int kMttDerived = 7;   // m0, m1, A, B, C, L (likelihood = 2^(L + A d0^2 + B d0 d1 + C d1^2)), likelihood scratch
 constexpr int kMttFast = 8;      // track slots whose derived data live in shared memory; the rest (rare) in local memory
 
-// derived-data accessors: slots [0, 8) in shared memory [field][slot][thread], slots [8, 16) in a per-thread array
+// derived-data accessors: slots [0, 8) in shared memory [field][slot pair][thread] as float2 (two slots ride in one packed
+// FFMA2 / FADD2 / FMUL2 and one 64-bit shared-memory access), slots [8, 16) in a per-thread array
 struct DerShared {
   float* base; int tid;
-  __device__ __forceinline__ float& operator()(int f, int k) const { return base[(f * kMttFast + k) * kMttThreads + tid]; }
+  __device__ __forceinline__ float& operator()(int f, int k) const {
+    return base[(((f * (kMttFast / 2) + (k >> 1)) * kMttThreads + tid) << 1) + (k & 1)];
+  }
+  __device__ __forceinline__ float2& pair(int f, int kp) const {
+    return reinterpret_cast<float2*>(base)[(f * (kMttFast / 2) + kp) * kMttThreads + tid];
+  }
 };
 struct DerLocal {
   float* loc;
   __device__ __forceinline__ float& operator()(int f, int k) const { return loc[f * (16 - kMttFast) + (k - kMttFast)]; }
 };
 
+// (Parking the predicted track in slot k of the child's record so that pass C need not load and predict the parent's track a
+// second time was measured: 0.649 vs 0.465 ms per step -- the extra 64-byte stores and L2 read-backs cost far more than the
+// ~50 FMAs of the second predict.)
 template <class Der>
 __device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __restrict__ src, int k, const Der& der) {
   Track tr;
@@ -183,20 +192,35 @@ __device__ __forceinline__ void mtt_derive(const MttDev& p, const uint32_t* __re
   predict(p, tr);
   const float sa = tr.c[0] + p.r, sb = tr.c[1], sd = tr.c[4] + p.r;
   const float det = sa * sd - sb * sb, idet = 1.0f / det;
+  // p_s p_d N(z; H m, S) = 2^(L + A d0^2 + B d0 d1 + C d1^2), d = z - H m: every constant folded here, once per track
+  constexpr float kL2e = 1.4426950408889634f;
   der(0, k) = tr.m[0]; der(1, k) = tr.m[1];
-  der(2, k) = sd * idet; der(3, k) = -sb * idet; der(4, k) = sa * idet;
-  der(5, k) = -0.5f * __logf(det) - 1.8378770664093453f;
+  der(2, k) = -0.5f * kL2e * sd * idet; der(3, k) = kL2e * sb * idet; der(4, k) = -0.5f * kL2e * sa * idet;
+  der(5, k) = kL2e * (-0.5f * __logf(det) - 1.8378770664093453f + __logf(p.pspd));
 }
 template <class Der>
 __device__ __forceinline__ float mtt_like(const MttDev& p, float z0, float z1, uint32_t assigned, int k, const Der& der) {
   float like = 0.f;
   if (!((assigned >> k) & 1u)) {
     const float d0 = z0 - der(0, k), d1 = z1 - der(1, k);
-    const float quad = der(2, k) * d0 * d0 + 2.0f * der(3, k) * d0 * d1 + der(4, k) * d1 * d1;
-    like = p.pspd * __expf(der(5, k) - 0.5f * quad);
+    like = exp2f(fmaf(der(4, k) * d1, d1, fmaf(fmaf(der(2, k), d0, der(3, k) * d1), d0, der(5, k))));
   }
   der(6, k) = like;
   return like;
+}
+// two shared-memory slots (2 kp, 2 kp + 1) at once; slot 2 kp + 1 may be past the track count
+__device__ __forceinline__ float mtt_like_pair(float z0, float z1, uint32_t assigned, int kp, int cnt, const DerShared& der) {
+  const float2 m0 = der.pair(0, kp), m1 = der.pair(1, kp), A = der.pair(2, kp), B = der.pair(3, kp), C = der.pair(4, kp), L = der.pair(5, kp);
+  const float2 d0 = __fadd2_rn(make_float2(z0, z0), make_float2(-m0.x, -m0.y));
+  const float2 d1 = __fadd2_rn(make_float2(z1, z1), make_float2(-m1.x, -m1.y));
+  const float2 t = __ffma2_rn(A, d0, __fmul2_rn(B, d1));
+  const float2 q = __ffma2_rn(__fmul2_rn(C, d1), d1, __ffma2_rn(t, d0, L));
+  const int k = 2 * kp;
+  float2 like;
+  like.x = ((assigned >> k) & 1u) ? 0.f : exp2f(q.x);
+  like.y = (((assigned >> (k + 1)) & 1u) || k + 1 >= cnt) ? 0.f : exp2f(q.y);
+  der.pair(6, kp) = like;
+  return like.x + like.y;
 }
 template <class Der>
 __device__ __forceinline__ void mtt_pick(float target, int k, const Der& der, float& cum, int& pick, int& last) {
@@ -298,7 +322,7 @@ __global__ void __launch_bounds__(kMttThreads) mtt_step(const __grid_constant__ 
     const uint32_t word = (o & 3) == 0 ? rnd.x : ((o & 3) == 1 ? rnd.y : ((o & 3) == 2 ? rnd.z : rnd.w));
     const float z0 = s_z[o][0], z1 = s_z[o][1];
     float ttot = 0.f;
-    for (int k = 0; k < cnt_fast; ++k) ttot += mtt_like(a.p, z0, z1, assigned, k, ds);
+    for (int kp = 0; 2 * kp < cnt_fast; ++kp) ttot += mtt_like_pair(z0, z1, assigned, kp, cnt_fast, ds);
     for (int k = kMttFast; k < cnt; ++k) ttot += mtt_like(a.p, z0, z1, assigned, k, dl);
     const float lc = s_lc[o], ln = s_ln[o];
     const float tot = lc + ln + ttot;
