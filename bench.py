@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-MODELS = {"rw1d": (1, 1), "lg42": (4, 2), "lg63": (6, 3), "mtt": (4, 2)}
+MODELS = {"rw1d": (1, 1), "lg42": (4, 2), "lg63": (6, 3), "mtt": (4, 2), "mcam": (4, 0)}
 HEADLINE_PARTICLES = 100_000_000
 
 
@@ -688,6 +688,18 @@ def main():
         if args.particles == HEADLINE_PARTICLES:
             args.particles = 1_000_000
         run_mtt(args)
+    elif args.model == "mcam":   # the MultiCamera tracker alone: a plain line, no roofline claim
+        import torch
+        import __graft_entry__ as g
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback")
+        n_p = 100_000 if args.particles == HEADLINE_PARTICLES else args.particles
+        leg = measure_mcam(g.load_package(), n_p, args.steps, args.warmup)
+        print(json.dumps({"metric": "particle-updates/sec", "value": leg["value"], "unit": leg["unit"], "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": leg["workload"], "model": "mcam", "particles_per_gpu": n_p},
+                          "e2e": leg["e2e"], "gpu_launches": leg["gpu_launches"]}))
     else:
         run_b200(args)
 
