@@ -222,3 +222,23 @@ def test_gpu_multicam_resampling_readout_and_errors(pz, monkeypatch):
     assert [[x[:4] for x in p["tracks"]] for p in pa] == [[x[:4] for x in p["tracks"]] for p in pb]
     assert all(np.array_equal(x[4], y[4]) for p, q in zip(pa, pb) for x, y in zip(p["tracks"], q["tracks"]))
     one.close(); many.close()
+
+
+@pytest.mark.gpu
+def test_multi_device_multicam_equals_single_device(pz):
+    """The MultiCamera tracker over 2 real devices of one process (parent records read over NVLink) equals the one-device run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d, obs, truth = H.mcam_scenario(20)
+    one = pz.zparticles(30000, _gpu_model(pz, d), seed=6)
+    many = pz.zparticles_multi(30000, _gpu_model(pz, d), [0, 1], seed=6)
+    for o in obs:
+        a, b = one.step(o), many.step(o)
+        assert (a.total_weight, a.e_max, a.ess, a.log_evidence_inc, a.mean[0]) == (b.total_weight, b.e_max, b.ess, b.log_evidence_inc, b.mean[0])
+    pa, pb = one.read_mcam_tracks(stride=61, appearances=True), many.read_mcam_tracks(stride=61, appearances=True)
+    for p, q in zip(pa, pb):
+        assert [x[:4] for x in p["tracks"]] == [x[:4] for x in q["tracks"]] and p["n_app"] == q["n_app"]
+        assert all(np.array_equal(x[4], y[4]) and np.array_equal(x[5], y[5]) for x, y in zip(p["tracks"], q["tracks"]))
+        assert all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(p["app"], q["app"]))
+    one.close(); many.close()
