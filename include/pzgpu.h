@@ -178,7 +178,11 @@ PZ_API int pz_filter_create(const pz_model_desc* model, uint64_t n_particles, ui
  * Haskell host calls): the particles are sharded over the devices, resampling is global, the exchange runs over
  * NVLink peer memory inside the step kernels; pz_filter_step / pz_filter_run / pz_filter_read_state /
  * pz_filter_destroy apply to the returned handle unchanged (the taps that address one device's memory do not).
- * n_particles must be divisible by n_devices * 256.  RW1D / LINGAUSS.                                       */
+ * n_particles must be divisible by n_devices * 256.  RW1D / LINGAUSS.
+ * PZ_MODEL_MTT / PZ_MODEL_MULTICAM: the trackers shard too (any n_particles that leaves every device at least one
+ * 2048-slot resampling tile): each device steps its own particles, parent records are read from their owners over
+ * NVLink, the block statistics are all-gathered by peer stores and every device derives the global plan; the run
+ * equals the one-device run bit for bit.  pz_filter_read_tracks / pz_filter_read_mcam_tracks apply to the handle.    */
 PZ_API int pz_filter_create_multi(const pz_model_desc* model, uint64_t n_particles, uint64_t seed, int n_devices,
                                   const int* device_ids, pz_filter** out);
 
