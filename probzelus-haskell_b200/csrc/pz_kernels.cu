@@ -119,6 +119,16 @@ __device__ __forceinline__ unsigned long long wait_sys(const unsigned long long*
   return v;
 }
 // 2^k as a float for k <= 0 (0 when it would underflow)
+// Programmatic dependent launch (PZ_PDL=1, single-GPU fused step): a kernel launched with the programmatic-serialization
+// attribute may become resident while its predecessor in the stream is still running; griddepcontrol.wait holds it until the
+// predecessor has completed and its writes are visible, so nothing of the predecessor's output is touched before it.  The
+// trigger follows at once: the successor's CTAs then take the SM slots that free up in this kernel's last wave and start the
+// moment it ends (launch latency and ramp hidden).  Both instructions are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // warp maximum in one instruction (CREDUX.MAX.F32, sm_100a): NaN inputs are ignored, as by the fmaxf butterfly it replaces
 __device__ __forceinline__ float warp_max_f32(float v) {
   float m;
@@ -435,6 +445,7 @@ __device__ void write_summary(PlanDev* pl, pz_step_summary* o, uint32_t t, int n
 }
 
 __global__ void __launch_bounds__(kThreads) pf_scan_blocks(const ScanArgs s) {
+  pdl_wait_then_trigger();
   __shared__ u64 s_warp[kWarps];
   __shared__ u64 s_prefix;
   __shared__ uint32_t s_tile, s_last;
@@ -691,6 +702,7 @@ struct PartArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) pf_partition(const PartArgs p) {
+  pdl_wait_then_trigger();
   const int64_t J = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const PlanDev* pl = p.plan;
   PZ_STAMP(J == 0, 9);
@@ -1436,6 +1448,7 @@ __global__ void __launch_bounds__(NT, MINB) pf_step_tile(const __grid_constant__
   float4* s_tab = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s_par + kStageWords) + kScratch * sizeof(float));
   const StepArgs& a = ta.a;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait_then_trigger();
   const uint32_t t = a.ctl->t;
   const int cur = t & 1, nxt = cur ^ 1;
   const T* __restrict__ xin = reinterpret_cast<const T*>(a.X[cur]);
@@ -2260,12 +2273,29 @@ static int partition_grid(int64_t ntiles, int64_t nscan, int64_t nbound) {
   return g > 4096 ? 4096 : g;
 }
 
+// PZ_PDL=1: the kernels of a single-GPU fused step are launched with programmatic stream serialization
+static bool use_pdl(const StepArgs& a) {
+  static const int on = [] { const char* e = getenv("PZ_PDL"); return e ? atoi(e) : 0; }();
+  return on != 0 && a.p2p == nullptr && a.world == 1;
+}
+template <class Kern, class Arg>
+static void launch_maybe_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t s, bool pdl, const Arg& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 static int partition(const StepArgs& a, int tile_out, int delta, cudaStream_t s) {
   PartArgs pa{a.pbx, a.xb, a.b_lo, a.b_hi, a.tile_start, a.scan_status, a.plan, a.ctl, a.nblk, a.slot_base, a.n_global,
               a.ntiles_out, tile_out, a.nscan, delta, a.p2p, a.rank, a.world, a.wait_ticks};
   int grid = partition_grid(a.ntiles_out, a.nscan, a.b_hi - a.b_lo + 1);
   if (a.p2p && grid > 592) grid = 592;  // every CTA polls a flag: keep the whole grid resident
-  pf_partition<<<grid, kThreads, 0, s>>>(pa);
+  if (use_pdl(a)) launch_maybe_pdl(pf_partition, grid, kThreads, 0, s, true, pa);
+  else pf_partition<<<grid, kThreads, 0, s>>>(pa);
   return 1;
 }
 
@@ -2274,7 +2304,8 @@ int launch_partition_only(const StepArgs& a, int tile_out, cudaStream_t s) { ret
 // Scan + partition of the population in buffer (ctl->t + delta) & 1.  delta = 1 after a step.
 static int scan_partition(const StepArgs& a, int delta, int tile_out, cudaStream_t s) {
   ScanArgs sc = make_scan(a, delta, delta == 1);
-  pf_scan_blocks<<<a.nscan + sc.npush, kThreads, 0, s>>>(sc);
+  if (use_pdl(a)) launch_maybe_pdl(pf_scan_blocks, a.nscan + sc.npush, kThreads, 0, s, true, sc);
+  else pf_scan_blocks<<<a.nscan + sc.npush, kThreads, 0, s>>>(sc);
   partition(a, tile_out, delta, s);
   return 2;
 }
@@ -2329,7 +2360,8 @@ static int launch_tile(const TileArgs& ta, cudaStream_t s) {
     resident[dev & 63].store(grid, std::memory_order_release);
   }
   if (grid < 0 || grid > ta.a.ntiles_out) grid = ta.a.ntiles_out;
-  kern<<<grid, NT, smem, s>>>(ta);
+  if (MODE == 0 && use_pdl(ta.a)) launch_maybe_pdl(kern, grid, NT, smem, s, true, ta);
+  else kern<<<grid, NT, smem, s>>>(ta);
   if constexpr (MODE == 0) {
     if (ta.a.p2p != nullptr) {   // sharded over peer memory: the remote-read fallback follows (it exits at once unless the margins overflowed)
       auto rkern = pf_step_tile<T, NX, NY, TO, MODE, KRON, NT, MINB, true>;
