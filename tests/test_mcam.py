@@ -242,3 +242,54 @@ def test_multi_device_multicam_equals_single_device(pz):
         assert all(np.array_equal(x[4], y[4]) and np.array_equal(x[5], y[5]) for x, y in zip(p["tracks"], q["tracks"]))
         assert all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(p["app"], q["app"]))
     one.close(); many.close()
+
+
+def _first_step_logweight(d, rows):
+    """Closed form of the step-0 log-weight of a particle born with exactly one track in each camera (no clutter row):
+    per camera log N(box; prior mean, prior var + 1) - logNSphereVolume(10) + log N(reading; 0, |pose|^2 + 1), the count prior
+    -(lgamma(nT + nC + 1) - lgamma(nC + 1)) with nT = 1, nC = 0, and the Poisson(clutter) probability of no clutter row."""
+    from scipy.special import gammaln
+    from scipy.stats import norm
+    pm = np.array([0, 0, 1, 1.0]); pv = np.array([d.mtt.birth_pos_var, d.mtt.birth_pos_var, d.mtt.birth_vel_var, d.mtt.birth_vel_var])
+    log_vol = np.log(10.0) + 5.0 * np.log(np.pi) - gammaln(6.0)
+    lw = 0.0
+    for c in range(2):
+        r = rows[c]
+        lw += norm.logpdf(r[11:15], pm, np.sqrt(pv + d.mtt.meas_var)).sum() - log_vol
+        lw += norm.logpdf(r[15], 0.0, np.sqrt(r[1:11] @ r[1:11] + 1.0))
+        lw += -(gammaln(2.0) - gammaln(1.0)) - d.mtt.clutter_lambda
+    return lw
+
+
+def test_oracle_first_step_logweight_against_scipy():
+    """Pins every term of the score (box predictive, sphere constant, appearance predictive, count prior, clutter count)."""
+    rows = _forced_stream(1)[0]
+    d = _forced_desc(); d.mtt.new_track_lambda = 2.0
+    orc = H.OracleMcam(d, 3000, 11)
+    assert orc.step(rows)[0] == 0
+    lw, ref, found = orc.logw(), _first_step_logweight(d, rows), 0
+    for i in range(3000):
+        tracks, na = orc.particle(i)
+        if len(tracks) == 2 and sorted(c for _, _, c, _, _ in tracks) == [0, 1] and tracks[0][1] != tracks[1][1]:
+            # (two tracks of ONE identity share the appearance: the second camera then scores against the updated marginal)
+            assert abs(lw[i] - ref) < 1e-5 * abs(ref), (lw[i], ref)   # (the oracle returns its log-weights as fp32)
+            found += 1
+    assert found > 10
+    orc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_first_step_logweight_against_scipy(pz):
+    rows = _forced_stream(1)[0]
+    d = pz.multicam(); d.mtt.survival_prob = 1.0; d.mtt.new_track_lambda = 2.0
+    zs = pz.zparticles(3000, d, seed=11)
+    zs.step(rows)
+    lw = zs.read_logw()
+    # the pending population (pre-resample) is what the log-weights belong to: find its one-track-per-camera particles by weight
+    ref = _first_step_logweight(d, rows)
+    close = np.abs(lw - ref) < 2e-3
+    assert close.sum() > 10   # P(two births, one per camera, distinct identities) = Poisson(2; 2) / 2 / 2 = 0.068: ~200 of 3000
+    # every other finite log-weight belongs to a different configuration and differs by far more than fp32 rounding
+    others = lw[np.isfinite(lw) & ~close]
+    assert others.size == 0 or np.min(np.abs(others - ref)) > 0.05
+    zs.close()
