@@ -355,6 +355,8 @@ struct pz_filter {
   bool is_mcam = false;                      // the MultiCamera tracker: same host path, its own record and step kernel
   int tracker_words = 0;                     // 32-bit words per particle record
   int tracker_obs_w = 2;                     // doubles per observation row (2: MTT detections; 16: MultiCamera rows)
+  uint32_t* tracker_thin = nullptr;          // read_tracks scratch: the thinned records (grown on demand, kept across calls)
+  int64_t tracker_thin_cap = 0;              // in 32-bit words
   // multi-device tracker (a shard of a pz_filter_create_multi tracker): this device owns particles [mtt_j0, mtt_jend) of
   // the global population; the gathered arrays (16-bit weights, block exponents / sums, summary partials, dropped-birth
   // counters) exist once per step parity, so that a peer's push of step t+1 never lands in what step t still reads
@@ -467,6 +469,7 @@ void free_filter(pz_filter* f) {
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   cudaFree(f->mbox); cudaFree(f->d_p2p);
   cudaFree(f->mtt_s[0]); cudaFree(f->mtt_s[1]); cudaFree(f->mtt_obs); cudaFree(f->mtt_overflow); cudaFree(f->mtt_part);
+  cudaFree(f->tracker_thin);
   cudaFree(f->mtt_q16b); cudaFree(f->mtt_sbb); cudaFree(f->mtt_partb); cudaFree(f->mtt_ovf[0]); cudaFree(f->mtt_ovf[1]);
   cudaFree(f->gen_lw[0]); cudaFree(f->gen_lw[1]); cudaFree(f->gen_obs); cudaFree(f->gen_part); cudaFree(f->gen_state); cudaFree(f->beta);
   if (f->h_gen_obs) cudaFreeHost(f->h_gen_obs);
@@ -2174,14 +2177,17 @@ static int tracker_gather(pz_filter* f, int32_t stride, int64_t n_sel_cap, std::
   } else rc = pending_ancestors(f, nullptr);
   if (rc) return rc;
   const int W = f->tracker_words;
-  uint32_t* d_out = nullptr;
-  PZ_CUDA(cudaMalloc(&d_out, (size_t)n_sel * W * sizeof(uint32_t)));
+  if (f->tracker_thin_cap < n_sel * W) {   // the visualiser calls this every frame: no allocation per call
+    cudaFree(f->tracker_thin); f->tracker_thin = nullptr; f->tracker_thin_cap = 0;
+    PZ_CUDA(cudaMalloc(&f->tracker_thin, (size_t)n_sel * W * sizeof(uint32_t)));
+    f->tracker_thin_cap = n_sel * W;
+  }
+  uint32_t* d_out = f->tracker_thin;
   if (parent->is_multi) launch_mtt_gather_multi(mtt_shard_view(parent, f, (int)(parent->t & 1u)), f->g.anc, stride, n_sel, d_out, f->stream, W);
   else launch_mtt_gather(f->mtt_s[f->t & 1], f->g.anc, stride, n_sel, d_out, f->stream, W);
   h->resize((size_t)n_sel * W);
   cudaError_t e = cudaMemcpyAsync(h->data(), d_out, h->size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
-  cudaFree(d_out);
   if (e != cudaSuccess) return fail(PZ_ECUDA, "read_tracks: %s", cudaGetErrorString(e));
   *n_sel_out = n_sel; *W_out = W;
   return PZ_OK;
