@@ -2028,6 +2028,7 @@ int pz_filter_last_timing(pz_filter* f, double* ms, int64_t* launches) {
 
 static int read_state_common(pz_filter* f, float* out32, double* out64, int64_t out_len) {
   if (!f || (!out32 && !out64)) return fail(PZ_EINVAL, "null argument");
+  if (f->is_mtt) return fail(PZ_ESTATE, "tracker state is read with pz_filter_read_tracks / pz_filter_read_mcam_tracks");
   if (f->is_multi) {   // shard after shard: out[d][r * n_shard + i]
     const int R = (int)f->shards.size(), nx = f->a.model.nx;
     const int64_t ns = f->a.n_local, n = ns * R;
@@ -2122,6 +2123,7 @@ int pz_filter_read_logw_f64(pz_filter* f, double* out, int64_t n) { return read_
 
 int pz_filter_read_ancestors(pz_filter* f, int32_t* out, int64_t n) {
   if (!f || !out) return fail(PZ_EINVAL, "null argument");
+  if (f->is_multi) return fail(PZ_ESTATE, "ancestor taps are per device; not available on a multi-device handle");
   if (f->is_rb) return fail(PZ_ESTATE, "a delayed-sampling filter has equal weights and no sampled state");
   if (n < f->a.n_local) return fail(PZ_EINVAL, "buffer too small");
   PZ_CUDA(cudaSetDevice(f->device));

@@ -282,3 +282,18 @@ def test_sharded_tracker_path_on_one_device(pz, monkeypatch):
     _tracker_runs_equal(pz, [0, 0, 0], 30000, 20, 29)
     with pytest.raises(pz.PzError):   # too few particles for the device count (whole 2048-slot tiles per device)
         pz.zparticles_multi(3000, pz.mtt(), [0, 0, 0], seed=1)
+
+
+@pytest.mark.gpu
+def test_taps_on_a_multi_device_tracker_are_refused(pz, monkeypatch):
+    """The per-device taps (state, log-weights, ancestors, particles, reset) return PZ_ESTATE on a multi-device tracker handle
+    instead of touching one shard's memory; the track readers work."""
+    monkeypatch.setenv("PZ_MULTI_SAME_DEVICE", "1")
+    zs = pz.zparticles_multi(3 * 2048 + 100, pz.mtt(), [0, 0], seed=1)
+    zs.step(np.array([[0.5, -0.5]]))
+    for call in (zs.read_state, zs.read_logw, zs.read_ancestors, lambda: zs.read_particles(10), lambda: zs.reset(1)):
+        with pytest.raises(pz.PzError) as e:
+            call()
+        assert e.value.code == -7
+    assert len(zs.read_tracks(stride=100)) == (3 * 2048 + 100 + 99) // 100
+    zs.close()
