@@ -6,6 +6,9 @@
 //                                   Gaussian marginal, printed as {"mean":..,"cov":..}; delay=False the bootstrap filter
 //   examples-gpu rw1d [N]           runKalman1DParticles (Examples/Demo.hs:200-210), one flat array per line
 //                                   for Generic1D.java
+//   examples-gpu walker [N]         Walker.run (Examples/Walker.hs:112-148): 1000 measurements of a simulated walker, the
+//                                   MStream filter `particles 1000`, one `show`n summary per step:
+//                                   ([(frequency,MotionType)..],(mean x,mean y),(mean vx,mean vy))
 // Options: --steps T (default: run until the pipe closes, as ZS.runStream does), --emit P (particles
 // written per line, default 100: the visualiser draws every particle it is given), --seed S.
 //
@@ -16,6 +19,7 @@
 //   examples-gpu mtt 1000000 | mvn exec:java -Dexec.mainClass=glimpsetracks.App
 // works as the reference's README describes.  This stands in for the Haskell host (haskell/PzGpu.hs),
 // which cannot be compiled in this image.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -116,6 +120,102 @@ int run_lg(const pz_model_desc& d, uint64_t n, long steps, int emit, uint64_t se
   return 0;
 }
 
+// ---- Walker.run ----------------------------------------------------------------------------------------------------
+// Haskell's `show` of a Double: shortest digits that round-trip; decimal notation for 0.1 <= |x| < 10^7, else d.ddde<n>
+std::string show_double(double x) {
+  if (std::isnan(x)) return "NaN";
+  if (std::isinf(x)) return x > 0 ? "Infinity" : "-Infinity";
+  char buf[64];
+  int prec = 1;
+  for (; prec <= 17; ++prec) { snprintf(buf, sizeof(buf), "%.*e", prec - 1, x); if (strtod(buf, nullptr) == x) break; }
+  std::string m(buf);                       // [-]d.ddde[+-]xx
+  const bool neg = m[0] == '-';
+  if (neg) m.erase(0, 1);
+  const size_t epos = m.find('e');
+  const int ex = atoi(m.c_str() + epos + 1);
+  std::string digits;
+  for (size_t i = 0; i < epos; ++i) if (m[i] != '.') digits += m[i];
+  std::string out;
+  if (x == 0) out = "0.0";
+  else if (ex >= -1 && ex < 7) {
+    if (ex == -1) out = "0." + digits;
+    else {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)ex + 1));
+      while ((int)ip.size() < ex + 1) ip += '0';
+      std::string fp = digits.size() > (size_t)ex + 1 ? digits.substr(ex + 1) : "0";
+      out = ip + "." + fp;
+    }
+  } else {
+    out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "e" + std::to_string(ex);
+  }
+  return (neg ? "-" : "") + out;
+}
+
+struct WalkerTruth { double x = 0, y = 0, vx = 0, vy = 0; int mt = 0; };
+
+void walker_init_velocity(const pz_walker_params& w, Sim& sim, int mt, double& vx, double& vy) {   // initVelocity, Walker.hs:51-64
+  if (w.speed_hi[mt] <= 0) { vx = vy = 0; return; }
+  const double speed = w.speed_lo[mt] + (w.speed_hi[mt] - w.speed_lo[mt]) * sim.u();
+  const double ang = 2 * M_PI * sim.u();
+  vx = speed * std::cos(ang); vy = speed * std::sin(ang);
+}
+void walker_coast(const pz_walker_params& w, Sim& sim, double dt, WalkerTruth& s) {   // coast, Walker.hs:31-39 (D.normal takes a VARIANCE)
+  const double sd = std::sqrt(std::sqrt(dt) * w.pos_noise);
+  s.x += s.vx * dt + sd * sim.n();
+  s.y += s.vy * dt + sd * sim.n();
+}
+void walker_motion(const pz_walker_params& w, Sim& sim, double dt, WalkerTruth& s) {   // motion, Walker.hs:66-80
+  for (int guard = 0; guard < 100000; ++guard) {
+    double rate[3], tot = 0;
+    for (int to = 0; to < 3; ++to) { rate[to] = w.half_life[s.mt][to] > 0 ? std::log(2.0) / w.half_life[s.mt][to] : 0; tot += rate[to]; }
+    const double e = -std::log(1.0 - sim.u());
+    const double t_tr = w.exp_mean_as_written ? e * tot : e / tot;   // D.exponential is handed recip(sum rates) as its RATE (:69)
+    if (t_tr > dt) { walker_coast(w, sim, dt, s); return; }
+    walker_coast(w, sim, t_tr, s);
+    double u = sim.u() * tot; int mt = 2;
+    for (int to = 0; to < 3; ++to) { if (u < rate[to]) { mt = to; break; } u -= rate[to]; }
+    s.mt = mt;
+    walker_init_velocity(w, sim, mt, s.vx, s.vy);
+    dt -= t_tr;
+  }
+}
+
+int run_walker(uint64_t n, long steps, uint64_t seed) {
+  pz_model_desc d;
+  if (pz_model_walker(&d)) die("pz_model_walker");
+  pz_filter* f = nullptr;
+  if (pz_filter_create(&d, n, seed, 0, &f)) die("pz_filter_create");
+  const pz_walker_params& w = d.walker;
+  Sim sim(seed ^ 0xA0761D6478BD642Full);
+  WalkerTruth tr;   // walkerInit (:105-111)
+  { double u = sim.u(); tr.mt = u < w.p_init[0] ? 0 : (u < w.p_init[0] + w.p_init[1] ? 1 : 2); walker_init_velocity(w, sim, tr.mt, tr.vx, tr.vy); }
+  if (steps < 0) steps = 1000;   // generateWalker 1000 (:147)
+  std::vector<double> parts((size_t)n * 5);
+  static const char* names[3] = {"Stationary", "Walking", "Running"};
+  for (long t = 0; t < steps; ++t) {
+    walker_motion(w, sim, w.dt, tr);
+    const double y[2] = {tr.x + w.obs_std * sim.n(), tr.y + w.obs_std * sim.n()};   // walkerGenMeasurement (:96-103)
+    pz_step_summary s;
+    if (pz_filter_step(f, y, 1, 2, &s)) die("pz_filter_step");
+    if (pz_filter_read_particles(f, 1, parts.data(), (int64_t)parts.size())) die("pz_filter_read_particles");
+    double cnt[3] = {0, 0, 0}, m[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < n; ++i) {
+      const double* p = &parts[(size_t)i * 5];
+      for (int k = 0; k < 4; ++k) m[k] += p[k];
+      const int mt = (int)p[4];
+      if (mt >= 0 && mt < 3) cnt[mt] += 1;
+    }
+    std::string line = "([";   // summarize (:137-143): frequencies in constructor order, then the two averaged pairs
+    bool first = true;
+    for (int k = 0; k < 3; ++k)
+      if (cnt[k] > 0) { line += (first ? "(" : ",(") + show_double(cnt[k] / (double)n) + "," + names[k] + ")"; first = false; }
+    line += "],(" + show_double(m[0] / n) + "," + show_double(m[1] / n) + "),(" + show_double(m[2] / n) + "," + show_double(m[3] / n) + "))";
+    if (puts(line.c_str()) < 0 || fflush(stdout) != 0) break;
+  }
+  pz_filter_destroy(f);
+  return 0;
+}
+
 struct GtTrack { int id; double x[4]; };
 
 int run_mtt(uint64_t n, long steps, int emit, uint64_t seed) {
@@ -202,7 +302,7 @@ int run_mtt(uint64_t n, long steps, int emit, uint64_t seed) {
 }
 
 void usage() {
-  fputs("usage: examples-gpu {mtt [N] | stt [delay] [N] | rw1d [N]} [--steps T] [--emit P] [--seed S]\n"
+  fputs("usage: examples-gpu {mtt [N] | stt [delay] [N] | rw1d [N] | walker [N]} [--steps T] [--emit P] [--seed S]\n"
         "  one JSON line per time step on stdout (java/src/main/java/glimpsetracks/App.java, Generic1D.java)\n", stderr);
 }
 
@@ -235,6 +335,7 @@ int main(int argc, char** argv) {
     if (pz_model_rw1d(&d, 1.0, 3.0)) die("pz_model_rw1d");
     return run_lg(d, strtoull(nth(1, "1000").c_str(), nullptr, 10), steps, emit, seed, true);             // Demo.hs:206
   }
+  if (pos[0] == "walker") return run_walker(strtoull(nth(1, "1000").c_str(), nullptr, 10), steps, seed);   // particles 1000, Walker.hs:135
   usage();
   return 2;
 }

@@ -22,7 +22,7 @@ def build():
 def test_cli_builds_and_reports_usage():
     build()
     r = subprocess.run([EXE, "--help"], capture_output=True, text=True)
-    assert r.returncode == 0 and "mtt [N]" in r.stderr and "stt [delay] [N]" in r.stderr
+    assert r.returncode == 0 and "mtt [N]" in r.stderr and "stt [delay] [N]" in r.stderr and "walker [N]" in r.stderr
     r = subprocess.run([EXE], capture_output=True, text=True)
     assert r.returncode == 2
     r = subprocess.run([EXE, "stt", "Maybe", "100"], capture_output=True, text=True)
@@ -87,6 +87,28 @@ def test_cli_streams_lines_the_visualiser_parses():
     rows = [json.loads(ln) for ln in r.stdout.strip().split("\n")]
     assert len(rows) == 8 and all(len(v) == 3 for v in rows)        # Generic1D.java: one double per series
     assert all(abs(v[2] - v[1]) < 6.0 for v in rows)                 # the posterior mean follows the truth
+
+
+@pytest.mark.gpu
+def test_cli_walker_prints_the_reference_summary():
+    """`examples walker` (Walker.run, Examples/Walker.hs:137-148): one Haskell-`show`n tuple per measurement:
+    ([(frequency,MotionType)..],(mean x,mean y),(mean vx,mean vy)), frequencies of the resampled particles' motion types."""
+    import re
+    build()
+    r = subprocess.run([EXE, "walker", "2000", "--steps", "12", "--seed", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert len(lines) == 12
+    num = r"-?(?:\d+\.\d+(?:e-?\d+)?|NaN|Infinity)"
+    pat = re.compile(rf"^\(\[((?:\({num},(?:Stationary|Walking|Running)\),?)+)\],\(({num}),({num})\),\(({num}),({num})\)\)$")
+    for ln in lines:
+        m = pat.match(ln)
+        assert m, ln
+        freqs = [float(x) for x in re.findall(rf"\(({num}),", m.group(1))]
+        assert abs(sum(freqs) - 1.0) < 1e-9 and all(0 < f <= 1 for f in freqs)
+        names = re.findall(r"(Stationary|Walking|Running)", m.group(1))
+        assert names == sorted(names, key=["Stationary", "Walking", "Running"].index) and len(set(names)) == len(names)
+        assert all(float(m.group(k)) == float(m.group(k)) and abs(float(m.group(k))) < 1e9 for k in (2, 3, 4, 5))
 
 
 MIRROR = os.path.join(H.ROOT, "host", "shim-mirror")
