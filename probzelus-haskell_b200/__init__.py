@@ -13,7 +13,7 @@ from .infer import (  # noqa: F401
     PzError, ModelDesc, StepSummary, Posterior, ZStream, lib, lib_path, exported_symbols,
     rw1d, stt, mtt_track, mtt, zparticles, zdsparticles, infer, run_stream,
     resample_systematic, resample_multinomial, comm_unique_id, zparticles_sharded,
-    PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF, json_line_tracks, json_line_generic1d,
+    PZ_RESAMPLE_SYSTEMATIC, PZ_RESAMPLE_MULTINOMIAL_REF, json_line_tracks, json_line_generic1d, json_line_mcam,
     walker, beta_bernoulli, zparticles_multi, importance_resampling, dist_sample, dist_score, WalkerParams,
     PZ_MODEL_RW1D, PZ_MODEL_LINGAUSS, PZ_MODEL_MTT, PZ_MODEL_WALKER, PZ_MODEL_BETA_BERNOULLI, PZ_MODEL_MULTICAM, multicam,
 )

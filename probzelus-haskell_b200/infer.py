@@ -476,6 +476,30 @@ def json_line_tracks(ground_truth, particles, observations):
     return "[" + gt + "," + ps + "," + ob + "]"
 
 
+def json_line_mcam(ground_truth, particles, observations):
+    """One line of `MultiCamera.runExample` (Examples/MultiCamera.hs:221-227): the aeson encoding of
+    (groundTruth :: [Track], particles :: [[MarginalTrack]], obs :: [(CameraID, R 10, R 4, R 1)]).  A track is the generic
+    record encoding of TrackG (:48-57) in declaration order -- posWH, startTime, trackID, identity, camera -- with posWH a bare
+    array for the ground truth (R 4, MVDistributions.hs:24-25) and {"mean":..,"cov":..} for a marginal (DSProg.hs:52-54,
+    DelayedSampling.hs:69-73).  ground_truth: [(trackID, identity, camera, box[4])] (mcam_scenario's rows; startTime unknown: 0);
+    particles: ZStream.read_mcam_tracks()'s list; observations: rows (camera, pose[10], box[4], reading)."""
+    def vec(v):
+        return "[" + ",".join(_num(a) for a in v) + "]"
+
+    def obj(pos, start, tid, ident, cam):
+        return '{"posWH":%s,"startTime":%s,"trackID":%d,"identity":%d,"camera":%d}' % (pos, _num(start), tid, ident, cam)
+
+    gt = "[" + ",".join(obj(vec(t[-1]), t[3] if len(t) > 4 else 0.0, t[0], t[1], t[2]) for t in ground_truth) + "]"
+
+    def marginal(mean, var):
+        cov = ",".join(vec([var[i] if i == j else 0.0 for j in range(4)]) for i in range(4))
+        return '{"mean":%s,"cov":[%s]}' % (vec(mean), cov)
+    ps = "[" + ",".join("[" + ",".join(obj(marginal(m, v), st, tid, idn, cam) for tid, idn, cam, st, m, v in p["tracks"]) + "]"
+                        for p in particles) + "]"
+    ob = "[" + ",".join("[%d,%s,%s,%s]" % (int(o[0]), vec(o[1:11]), vec(o[11:15]), vec(o[15:16])) for o in observations) + "]"
+    return "[" + gt + "," + ps + "," + ob + "]"
+
+
 def json_line_generic1d(values):
     """One line for Generic1D.java (:333-348): a flat array, one double per plotted series."""
     return "[" + ",".join(_num(v) for v in values) + "]"

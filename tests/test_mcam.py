@@ -293,3 +293,25 @@ def test_gpu_first_step_logweight_against_scipy(pz):
     others = lw[np.isfinite(lw) & ~close]
     assert others.size == 0 or np.min(np.abs(others - ref)) > 0.05
     zs.close()
+
+
+def test_json_line_is_the_aeson_encoding_of_the_reference_triple(pz):
+    """(groundTruth, particles, obs) as `encode` writes it (MultiCamera.hs:221-227): generic record objects in declaration
+    order, bare arrays for R n, {"mean","cov"} for a marginal, 4-tuples as arrays."""
+    import json
+    d, obs, truth = H.mcam_scenario(30)
+    t = max(range(30), key=lambda i: len(truth[i]))
+    parts = [{"tracks": [(3, 0, 1, 2.0, np.array([0.1, 0.2, 1.0, 1.1]), np.array([0.5, 0.5, 0.2, 0.2]))], "n_app": 1},
+             {"tracks": [], "n_app": 0}]
+    line = pz.json_line_mcam(truth[t], parts, obs[t])
+    arr = json.loads(line)
+    assert len(arr) == 3 and len(arr[0]) == len(truth[t]) and len(arr[1]) == 2 and len(arr[2]) == len(obs[t])
+    for g, (tid, idn, cam, box) in zip(arr[0], truth[t]):
+        assert list(g.keys()) == ["posWH", "startTime", "trackID", "identity", "camera"]
+        assert (g["trackID"], g["identity"], g["camera"]) == (tid, idn, cam) and np.allclose(g["posWH"], box, rtol=1e-8)
+    m = arr[1][0][0]
+    assert list(m.keys()) == ["posWH", "startTime", "trackID", "identity", "camera"] and m["startTime"] == 2
+    assert m["posWH"]["mean"] == [0.1, 0.2, 1, 1.1] and np.array_equal(np.diag(m["posWH"]["cov"]), [0.5, 0.5, 0.2, 0.2])
+    assert arr[1][1] == []
+    for o, row in zip(arr[2], obs[t]):
+        assert o[0] == int(row[0]) and len(o[1]) == 10 and len(o[2]) == 4 and len(o[3]) == 1 and np.allclose(o[2], row[11:15], rtol=1e-8)
