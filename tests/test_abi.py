@@ -105,6 +105,29 @@ def test_every_argument_error_is_reported_before_device_work(pz):
     assert rc == -1 and b"2^28" in msg
     rc, msg = create(pz.mtt(), 2 * 256 * 8, rank=0, world=2)
     assert rc == -1 and b"pz_filter_create_multi" in msg   # a tracker over several GPUs is a single-process multi-device filter
+    # multi-device (one process): device list and per-device share are checked before any device is touched
+    def create_multi(d, n, ids):
+        h = C.c_void_p()
+        arr = (C.c_int * len(ids))(*ids)
+        rc = L.pz_filter_create_multi(C.byref(d), n, 0, len(ids), arr, C.byref(h))
+        assert not h.value
+        return rc, L.pz_last_error()
+    rc, msg = create_multi(pz.mtt(), 100000, [0, 0])
+    assert rc == -1 and b"listed twice" in msg
+    rc, msg = create_multi(pz.mtt(), 100000, list(range(9)))
+    assert rc == -1 and b"up to 8 devices" in msg
+    monkey = os.environ.get("PZ_MULTI_SAME_DEVICE")
+    os.environ["PZ_MULTI_SAME_DEVICE"] = "1"
+    try:
+        rc, msg = create_multi(pz.mtt(), 3000, [0, 0, 0])
+        assert rc == -1 and b"too few for 3 devices" in msg   # whole 2048-slot resampling tiles per device
+        rc, msg = create_multi(pz.rw1d(), 256 * 8, [0, 0])
+        assert rc == -1 and b"listed twice" in msg             # the hook applies to the trackers only
+    finally:
+        if monkey is None:
+            del os.environ["PZ_MULTI_SAME_DEVICE"]
+        else:
+            os.environ["PZ_MULTI_SAME_DEVICE"] = monkey
     mc = pz.multicam(); mc.F[1] = 0.5
     rc, msg = create(mc, 1000)
     assert rc == -1 and b"F = I" in msg
