@@ -592,7 +592,10 @@ def run_b200(args):
         import torch
         if torch.cuda.device_count() >= 2:   # configs[4]'s sharded tracker: one process, every GPU of the box, 10^6 particles per GPU
             nd = min(torch.cuda.device_count(), 8)
-            legs[f"mtt_f32_{nd}_devices"] = measure_mtt(pz, 1_000_000 * nd, 10, 3, args.mtt_tracks, with_cpu=False, devices=nd)
+            try:
+                legs[f"mtt_f32_{nd}_devices"] = measure_mtt(pz, 1_000_000 * nd, 10, 3, args.mtt_tracks, with_cpu=False, devices=nd)
+            except Exception as exc:   # (no peer path between some pair of devices, ...): the leg must not take the headline down
+                legs[f"mtt_f32_{nd}_devices"] = {"error": str(exc)[:200]}
         legs["sustained_rw1d_" + args.dtype] = measure_lg(pz, "rw1d", args.dtype, n_p, 5, 3, profile=False, sustained=1000)["sustained"]
 
     # ---- CPU baseline on this box's host cores (bounded sample)
